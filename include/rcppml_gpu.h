@@ -1,0 +1,171 @@
+/*
+ * rcppml_gpu.h — C ABI of the B200-native sparse-NMF ALS engine (RcppML_gpu.so).
+ *
+ * Part 1 are the symbols the reference's CPU-side bridge dlsym()s / .C()s out of
+ * RcppML_gpu.so (citations are into the reference tree). A maintainer switches
+ * backends by dropping this library where R/gpu_backend.R:149-171 looks for it.
+ * Part 2 are NEW symbols (prefix rcppml_b200_) for callers that keep data resident
+ * on the device (bench, multi-GPU, masked fits); they are ABI extensions and are
+ * listed as such in INTEGRATION.md.
+ *
+ * All symbols: plain C, pointers + sizes only, never throw, never call into R.
+ */
+#ifndef RCPPML_GPU_H
+#define RCPPML_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ========================================================================
+ * Part 1 — reference ABI
+ * ===================================================================== */
+
+/* Replaces src/gpu_bridge_cluster.cu:24-47 (called from R/gpu_backend.R:101-106 via .C and
+ * from inst/include/FactorNet/gpu/loader.hpp:73-92 via dlsym on every nmf()).
+ * out_status = 0 and num_gpus > 0 mean "GPU plan available". */
+void rcppml_gpu_detect(int* num_gpus, double* total_mem_mb, double* free_mem_mb, int* max_gpus,
+                       int* out_status);
+
+/* Replaces src/gpu_bridge_nmf.cu:460-624; function-pointer type at
+ * inst/include/FactorNet/gpu/bridge_nmf.hpp:39-75; called at bridge_nmf.hpp:310-342.
+ * CSC of A (m x n): col_ptr[n+1], row_idx[nnz], values[nnz] (double on the wire, fp32 inside).
+ * W is k x m column-major (= W_T), H is k x n column-major, d is k; all in/out.
+ * Supported: loss_type 0 (MSE), solver_mode 0 (CD) / !=0 (Cholesky+clip), L1/L2, upper
+ * bounds, nonneg flags, norm_type 0/1/2. Anything else (L21, ortho, graph, guides,
+ * projective, symmetric, non-MSE loss, k > 128) sets *out_status = -1 so that the
+ * reference gateway (nmf/fit.hpp:125-133) takes its CPU path; there is no CPU fallback here. */
+void rcppml_gpu_nmf_unified_float(
+    const int* col_ptr, const int* row_idx, const double* values,
+    int* m, int* n, int* nnz, int* k,
+    double* W, double* H, double* d,
+    int* max_iter, double* tol,
+    double* L1_H, double* L1_W, double* L2_H, double* L2_W,
+    double* L21_H, double* L21_W,
+    double* ortho_H, double* ortho_W,
+    double* ub_H, double* ub_W,
+    int* cd_maxit, int* verbose, int* seed,
+    int* loss_every, int* patience,
+    int* nonneg_W, int* nonneg_H,
+    int* loss_type, double* huber_delta,
+    int* irls_max_iter, double* irls_tol,
+    int* norm_type,
+    int* projective, int* symmetric,
+    int* solver_mode,
+    const int* graph_W_p, const int* graph_W_i, const double* graph_W_x,
+    int* graph_W_dim, int* graph_W_nnz, double* graph_W_lambda,
+    const int* graph_H_p, const int* graph_H_i, const double* graph_H_x,
+    int* graph_H_dim, int* graph_H_nnz, double* graph_H_lambda,
+    int* gp_dispersion_mode,
+    double* gp_theta_init, double* gp_theta_max, double* gp_theta_min,
+    double* nb_size_init, double* nb_size_max, double* nb_size_min,
+    double* gamma_phi_init, double* gamma_phi_max, double* gamma_phi_min,
+    double* robust_delta, double* tweedie_power,
+    double* out_theta, int* out_theta_len,
+    const int* guide_H_labels_flat, const int* guide_H_ns,
+    const double* guide_H_lambdas, const int* guide_H_ncs, int* guide_H_count,
+    int* out_iter, int* out_converged, double* out_loss,
+    int* out_status,
+    double* out_tol);
+
+/* ========================================================================
+ * Part 2 — device-resident engine (ABI extension)
+ * ===================================================================== */
+
+typedef struct rcppml_b200_engine rcppml_b200_engine;
+
+/* Mirrors the fields of NMFConfig<float> (core/config.hpp:54-454) that exist on this path.
+ * The W/H pairs follow src/RcppFunctions_nmf.cpp:59-72. */
+typedef struct {
+    int   k;
+    int   max_iter;      /* used by rcppml_b200_fit only */
+    float tol;
+    float L1_W, L1_H, L2_W, L2_H, ub_W, ub_H;
+    int   nonneg_W, nonneg_H;
+    int   cd_maxit;      /* <=0 -> 10  (src/RcppFunctions_nmf.cpp:75) */
+    float cd_tol;        /* <=0 -> 1e-8 (src/RcppFunctions_nmf.cpp:76; core/constants.hpp:64) */
+    int   norm_type;     /* 0=L1 1=L2 2=None */
+    int   solver_mode;   /* 0=CD, else Cholesky+clip (fused_nnls.hpp:156) */
+    int   patience;      /* core/constants.hpp:89 default 5 */
+    int   verbose;
+} rcppml_b200_config;
+
+typedef struct {
+    int    iterations;
+    int    converged;
+    float  train_loss;
+    float  final_tol;
+    int    status;          /* 0 ok; 1 = non-positive Cholesky pivot seen */
+    int    gpu_launches;    /* kernels launched by the engine since begin_fit */
+    double loop_ms;         /* CUDA-event time of iterations run by the last fit/iterate */
+} rcppml_b200_result;
+
+/* Named sections follow the reference profiler (profiling/cpu_timer.hpp; fit_cpu.hpp:490-536). */
+enum {
+    RCPPML_B200_SEC_GRAM_H = 0,        /* "gram_H"            */
+    RCPPML_B200_SEC_SOLVE_H = 1,       /* "fused_rhs_nnls_H"  */
+    RCPPML_B200_SEC_SCALE_H = 2,       /* "scaling"           */
+    RCPPML_B200_SEC_GRAM_W = 3,        /* "gram_W"            */
+    RCPPML_B200_SEC_SOLVE_W = 4,       /* "fused_rhs_nnls_W"  */
+    RCPPML_B200_SEC_SCALE_W = 5,       /* "scaling"           */
+    RCPPML_B200_SEC_LOSS = 6,          /* "loss"              */
+    RCPPML_B200_SEC_COMM = 7,          /* multi-GPU exchange  */
+    RCPPML_B200_NUM_SECTIONS = 8
+};
+
+const char* rcppml_b200_last_error(void);
+int  rcppml_b200_engine_create(rcppml_b200_engine** out, int device);
+void rcppml_b200_engine_destroy(rcppml_b200_engine* e);
+
+/* A is m x n CSC with ascending row indices per column (dgCMatrix). The engine copies it,
+ * builds CSC(A^T) on the device (stable, ascending — Eigen transpose(), nmf/fit_cpu.hpp:251-253)
+ * and tr(A^T A) (primitives/primitives.hpp:101-115). Host pointers. */
+int rcppml_b200_set_matrix_f32(rcppml_b200_engine* e, int m, int n, int64_t nnz, const int* col_ptr,
+                               const int* row_idx, const float* values);
+int rcppml_b200_set_matrix_f64(rcppml_b200_engine* e, int m, int n, int64_t nnz, const int* col_ptr,
+                               const int* row_idx, const double* values);
+/* Synthetic generator of SURVEY.md §8d, on the device. Columns [col_begin, col_begin+n_local)
+ * of the m x n_global matrix; per column round(m*density) candidate rows
+ * SplitMix64::hash(seed, t, j) mod m, sorted + deduplicated; value 0.5 + uniform<float>(seed+1, r, j). */
+int rcppml_b200_set_matrix_synthetic(rcppml_b200_engine* e, int m, int n_local, int col_begin, double density,
+                                     uint64_t seed);
+/* Copies the device CSC back (for checking the generator). Pass NULL to skip an array. */
+int rcppml_b200_get_matrix(rcppml_b200_engine* e, int64_t* nnz, int* col_ptr, int* row_idx, float* values);
+int rcppml_b200_get_matrix_t(rcppml_b200_engine* e, int* col_ptr, int* row_idx, float* values);
+
+/* Factors: W_T is k x m column-major, H is k x n column-major (host, leading dimension k). */
+int rcppml_b200_set_factors_f32(rcppml_b200_engine* e, int k, const float* W_T, const float* H);
+int rcppml_b200_set_factors_f64(rcppml_b200_engine* e, int k, const double* W_T, const double* H);
+/* nmf/nmf_init.hpp:167-182 on the device: one SplitMix64(seed) stream, W_T first, then H.
+ * h_col_begin/h_cols_global place a column shard of H inside the global stream. */
+int rcppml_b200_init_factors(rcppml_b200_engine* e, int k, uint32_t seed, int h_col_begin);
+int rcppml_b200_get_factors_f32(rcppml_b200_engine* e, float* W_T, float* H, float* d);
+int rcppml_b200_get_factors_f64(rcppml_b200_engine* e, double* W_T, double* H, double* d);
+
+/* nmf_fit loop (nmf/fit_cpu.hpp:444-1825). begin_fit resets iteration state (iter = 0);
+ * iterate enqueues up to n_iters further ALS iterations and returns after they finished. */
+int rcppml_b200_begin_fit(rcppml_b200_engine* e, const rcppml_b200_config* cfg);
+int rcppml_b200_iterate(rcppml_b200_engine* e, int n_iters);
+int rcppml_b200_fit(rcppml_b200_engine* e, const rcppml_b200_config* cfg);   /* begin_fit + iterate(max_iter) */
+int rcppml_b200_get_result(rcppml_b200_engine* e, rcppml_b200_result* out);
+int rcppml_b200_get_loss_history(rcppml_b200_engine* e, float* out, int capacity);
+/* Per-section CUDA-event times (ms) and launch counts accumulated since begin_fit. */
+int rcppml_b200_set_profiling(rcppml_b200_engine* e, int enabled);
+int rcppml_b200_get_profile(rcppml_b200_engine* e, double* ms /*[NUM_SECTIONS]*/, int* launches /*[NUM_SECTIONS]*/);
+
+/* Single half-steps on the resident data, for unit parity tests (fused_nnls.hpp:71,156).
+ * which: 0 = H-update (gram(W_T) + solve over columns of A), 1 = W-update. warm_start as fit_cpu.hpp:523. */
+int rcppml_b200_half_step(rcppml_b200_engine* e, const rcppml_b200_config* cfg, int which, int warm_start,
+                          int normalize_after);
+
+/* Multi-GPU (one process per GPU). id is an ncclUniqueId (128 bytes) created on rank 0 and
+ * distributed by the host launcher. After comm_init the engine's matrix is a column shard. */
+int rcppml_b200_nccl_unique_id(char* id128);
+int rcppml_b200_comm_init(rcppml_b200_engine* e, int rank, int world, const char* id128);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RCPPML_GPU_H */

@@ -1,0 +1,10 @@
+"""rcppml_b200 — B200-native (sm_100a) sparse-NMF ALS engine behind RcppML's GPU bridge.
+
+Only the ALS hot path of the reference lives here: the CUDA engine in csrc/
+(built to lib/RcppML_gpu.so, exporting the reference's C ABI) and the host-side mirror of the
+reference interface for this path.
+"""
+from .engine import Engine, FitResult, make_config, nccl_unique_id  # noqa: F401
+from .bridge import bridge_nmf_sparse, gpu_detect  # noqa: F401
+
+__all__ = ["Engine", "FitResult", "make_config", "nccl_unique_id", "bridge_nmf_sparse", "gpu_detect"]

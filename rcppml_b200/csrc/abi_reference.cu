@@ -1,0 +1,135 @@
+// abi_reference.cu — the symbols the reference's bridge resolves out of RcppML_gpu.so
+// (include/rcppml_gpu.h, part 1). Thin shims over the device-resident engine.
+#include "engine.hpp"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <memory>
+
+namespace {
+
+// FACTORNET_GPU_WARN (core/logging.hpp:132) prints to stderr; the .so never calls into R.
+void warn(const char* what) { std::fprintf(stderr, "[RcppML_gpu/b200] %s\n", what); }
+
+}  // namespace
+
+extern "C" {
+
+// src/gpu_bridge_cluster.cu:24-47
+void rcppml_gpu_detect(int* num_gpus, double* total_mem_mb, double* free_mem_mb, int* max_gpus, int* out_status) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) count = 0;
+    int usable = 0;
+    const int cap = max_gpus ? *max_gpus : 0;
+    for (int dev = 0; dev < count; ++dev) {
+        cudaDeviceProp prop{};
+        if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) continue;
+        if (prop.major < 10) continue;                       // this library carries sm_100a code only
+        size_t free_b = 0, total_b = 0;
+        if (cudaSetDevice(dev) != cudaSuccess || cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) continue;
+        if (usable < cap) {
+            if (total_mem_mb) total_mem_mb[usable] = static_cast<double>(total_b) / (1024.0 * 1024.0);
+            if (free_mem_mb) free_mem_mb[usable] = static_cast<double>(free_b) / (1024.0 * 1024.0);
+        }
+        ++usable;
+    }
+    if (count > 0) cudaSetDevice(0);                         // src/gpu_bridge_common.cuh:60
+    if (num_gpus) *num_gpus = usable;
+    if (out_status) *out_status = usable > 0 ? 0 : -1;
+}
+
+// src/gpu_bridge_nmf.cu:460-624
+void rcppml_gpu_nmf_unified_float(
+    const int* col_ptr, const int* row_idx, const double* values,
+    int* m, int* n, int* nnz, int* k,
+    double* W, double* H, double* d,
+    int* max_iter, double* tol,
+    double* L1_H, double* L1_W, double* L2_H, double* L2_W,
+    double* L21_H, double* L21_W,
+    double* ortho_H, double* ortho_W,
+    double* ub_H, double* ub_W,
+    int* cd_maxit, int* verbose, int* /*seed*/,
+    int* /*loss_every*/, int* patience,
+    int* nonneg_W, int* nonneg_H,
+    int* loss_type, double* /*huber_delta*/,
+    int* /*irls_max_iter*/, double* /*irls_tol*/,
+    int* norm_type,
+    int* projective, int* symmetric,
+    int* solver_mode,
+    const int*, const int*, const double*, int*, int* graph_W_nnz, double*,
+    const int*, const int*, const double*, int*, int* graph_H_nnz, double*,
+    int* /*gp_dispersion_mode*/,
+    double*, double*, double*, double*, double*, double*, double*, double*, double*,
+    double* robust_delta, double* /*tweedie_power*/,
+    double* /*out_theta*/, int* out_theta_len,
+    const int*, const int*, const double*, const int*, int* guide_H_count,
+    int* out_iter, int* out_converged, double* out_loss,
+    int* out_status,
+    double* out_tol)
+{
+    if (!out_status) return;
+    *out_status = -1;
+    try {
+        // Features outside the sparse-MSE ALS path are refused, not emulated: the caller
+        // (nmf/fit.hpp:125-133) owns the CPU fallback.
+        const char* refuse = nullptr;
+        if (*loss_type != 0) refuse = "non-MSE loss is outside the B200 ALS path";
+        else if (robust_delta && *robust_delta > 0) refuse = "robust IRLS is outside the B200 ALS path";
+        else if (*projective || *symmetric) refuse = "projective/symmetric NMF is outside the B200 ALS path";
+        else if (*L21_H > 0 || *L21_W > 0) refuse = "L21 is outside the B200 ALS path";
+        else if (*ortho_H > 0 || *ortho_W > 0) refuse = "angular/ortho penalty is outside the B200 ALS path";
+        else if ((graph_W_nnz && *graph_W_nnz > 0) || (graph_H_nnz && *graph_H_nnz > 0)) refuse = "graph regularisation is outside the B200 ALS path";
+        else if (guide_H_count && *guide_H_count > 0) refuse = "classifier guides are outside the B200 ALS path";
+        else if (*k < 1 || *k > b200::kMaxKP) refuse = "rank must be in [1, 128] on the B200 ALS path";
+        else if (*max_iter <= 0) refuse = "max_iter must be positive";
+        if (refuse) { warn(refuse); return; }
+
+        int count = 0;
+        if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) { warn("no CUDA device"); return; }
+
+        b200::Engine E(0);
+        E.set_matrix_host<double>(*m, *n, static_cast<int64_t>(*nnz), col_ptr, row_idx, values);
+        E.set_factors_host<double>(*k, W, H);
+
+        rcppml_b200_config cfg{};
+        cfg.k = *k;
+        cfg.max_iter = *max_iter;
+        cfg.tol = static_cast<float>(*tol);
+        cfg.L1_H = static_cast<float>(*L1_H); cfg.L1_W = static_cast<float>(*L1_W);
+        cfg.L2_H = static_cast<float>(*L2_H); cfg.L2_W = static_cast<float>(*L2_W);
+        cfg.ub_H = static_cast<float>(*ub_H); cfg.ub_W = static_cast<float>(*ub_W);
+        cfg.nonneg_W = *nonneg_W != 0; cfg.nonneg_H = *nonneg_H != 0;
+        cfg.cd_maxit = *cd_maxit;
+        cfg.cd_tol = 1e-8f;                       // not on the wire: core/constants.hpp:64
+        cfg.norm_type = *norm_type;
+        cfg.solver_mode = *solver_mode;
+        cfg.patience = *patience;
+        cfg.verbose = *verbose;
+
+        E.begin_fit(cfg);
+        E.iterate(cfg.max_iter);
+        rcppml_b200_result res{};
+        E.get_result(&res);
+        if (res.status != 0) { warn("Gram matrix not positive definite (Cholesky pivot <= 0)"); return; }
+        E.get_factors_host<double>(W, H, d);
+
+        if (out_theta_len) *out_theta_len = 0;
+        if (out_iter) *out_iter = res.iterations;
+        if (out_converged) *out_converged = res.converged;
+        if (out_loss) *out_loss = static_cast<double>(res.train_loss);
+        if (out_tol) *out_tol = static_cast<double>(res.final_tol);
+        if (*verbose)
+            std::fprintf(stderr, "[RcppML_gpu/b200] %d iterations, loss %.6g, loop %.3f ms, %d launches\n",
+                         res.iterations, res.train_loss, res.loop_ms, res.gpu_launches);
+        *out_status = 0;
+    } catch (const std::exception& ex) {
+        warn(ex.what());
+        *out_status = -1;
+    } catch (...) {
+        warn("unknown error");
+        *out_status = -1;
+    }
+}
+
+}  // extern "C"

@@ -1,0 +1,658 @@
+// engine.cu — host side of the sm_100a ALS engine: device memory, the iteration schedule of
+// nmf_fit (nmf/fit_cpu.hpp:444-1825) as a stream of kernels with NO per-iteration host
+// synchronisation (convergence bookkeeping lives in DevState on the device), and the
+// rcppml_b200_* C ABI declared in include/rcppml_gpu.h.
+#include "engine.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+namespace b200 {
+
+thread_local std::string g_last_error;
+
+// ---------------------------------------------------------------------------------------------
+// kernel dispatch by padded rank
+// ---------------------------------------------------------------------------------------------
+template <int LANES, int SOLVER, int BSRC, int OUT>
+static void launch_half_step_t(const HalfStepParams& p, int num_sms, cudaStream_t stream, int* grid_out) {
+    auto kern = half_step_kernel<LANES, 1, SOLVER, BSRC, OUT>;
+    const size_t smem = half_step_smem_bytes<LANES, 1, SOLVER, OUT>();
+    static thread_local int cached_occ = -1;
+    if (cached_occ < 0) {
+        B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        int occ = 0;
+        B200_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));
+        B200_REQUIRE(occ > 0, "half_step_kernel does not fit on an SM");
+        cached_occ = occ;
+    }
+    // Persistent grid: a multiple of the SM count (148 on B200) x resident CTAs per SM.
+    const int grid = num_sms * cached_occ;
+    if (grid_out) { *grid_out = grid; return; }
+    kern<<<grid, 256, smem, stream>>>(p);
+}
+
+template <int SOLVER, int BSRC, int OUT>
+static void launch_half_step_l(int lanes, const HalfStepParams& p, int num_sms, cudaStream_t s, int* grid_out) {
+    switch (lanes) {
+        case 4: launch_half_step_t<4, SOLVER, BSRC, OUT>(p, num_sms, s, grid_out); break;
+        case 8: launch_half_step_t<8, SOLVER, BSRC, OUT>(p, num_sms, s, grid_out); break;
+        case 16: launch_half_step_t<16, SOLVER, BSRC, OUT>(p, num_sms, s, grid_out); break;
+        case 32: launch_half_step_t<32, SOLVER, BSRC, OUT>(p, num_sms, s, grid_out); break;
+        default: throw std::runtime_error("unsupported lane-group width");
+    }
+}
+
+// grid_out != nullptr: only report the grid this configuration would use (for buffer sizing).
+static void launch_half_step(int lanes, int solver, int bsrc, int out, const HalfStepParams& p, int num_sms,
+                             cudaStream_t s, int* grid_out = nullptr) {
+    if (out == OUT_RHS) {
+        launch_half_step_l<SOLVER_CD, BSRC_GATHER, OUT_RHS>(lanes, p, num_sms, s, grid_out);
+    } else if (bsrc == BSRC_GATHER) {
+        if (solver == SOLVER_CD) launch_half_step_l<SOLVER_CD, BSRC_GATHER, OUT_SOLVE>(lanes, p, num_sms, s, grid_out);
+        else launch_half_step_l<SOLVER_CHOL, BSRC_GATHER, OUT_SOLVE>(lanes, p, num_sms, s, grid_out);
+    } else {
+        if (solver == SOLVER_CD) launch_half_step_l<SOLVER_CD, BSRC_LOAD, OUT_SOLVE>(lanes, p, num_sms, s, grid_out);
+        else launch_half_step_l<SOLVER_CHOL, BSRC_LOAD, OUT_SOLVE>(lanes, p, num_sms, s, grid_out);
+    }
+}
+
+static void launch_normalize_gram(int KP, float* X, long long ncols, const float* d, int normalize, double* partials,
+                                  const int* stop, int grid, cudaStream_t s) {
+    switch (KP) {
+        case 16: normalize_gram_kernel<16, 64><<<grid, 256, 0, s>>>(X, ncols, d, normalize, partials, stop); break;
+        case 32: normalize_gram_kernel<32, 64><<<grid, 256, 0, s>>>(X, ncols, d, normalize, partials, stop); break;
+        case 64: normalize_gram_kernel<64, 32><<<grid, 256, 0, s>>>(X, ncols, d, normalize, partials, stop); break;
+        case 128: normalize_gram_kernel<128, 32><<<grid, 256, 0, s>>>(X, ncols, d, normalize, partials, stop); break;
+        default: throw std::runtime_error("unsupported padded rank");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Engine
+// ---------------------------------------------------------------------------------------------
+Engine::Engine(int dev) : device(dev) {
+    B200_CUDA_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop{};
+    B200_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    num_sms = prop.multiProcessorCount;
+    B200_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    B200_CUDA_CHECK(cudaEventCreate(&ev_loop_begin));
+    B200_CUDA_CHECK(cudaEventCreate(&ev_loop_end));
+    state.ensure(1);
+    counters.ensure(8);
+    sweep_counter.ensure(1);
+    B200_CUDA_CHECK(cudaMallocHost(&h_state, sizeof(DevState) * 2));
+    B200_CUDA_CHECK(cudaMemsetAsync(state.ptr, 0, sizeof(DevState), stream));
+    B200_CUDA_CHECK(cudaMemsetAsync(sweep_counter.ptr, 0, sizeof(unsigned long long), stream));
+}
+
+Engine::~Engine() {
+    cudaSetDevice(device);
+    cudaStreamSynchronize(stream);
+    for (auto& sec : prof_events)
+        for (auto& pr : sec) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    cudaEventDestroy(ev_loop_begin);
+    cudaEventDestroy(ev_loop_end);
+    if (h_state) cudaFreeHost(h_state);
+    comm_destroy();
+    cudaStreamDestroy(stream);
+}
+
+void Engine::use_device() const { B200_CUDA_CHECK(cudaSetDevice(device)); }
+
+// ---- matrix ---------------------------------------------------------------------------------
+void Engine::finish_matrix() {
+    // tr(AᵀA) in fp64 (primitives/primitives.hpp:101-115)
+    const int nb = 1024;
+    DeviceBuffer<double> part;
+    part.ensure(nb);
+    sumsq_kernel<<<nb, 256, 0, stream>>>(Ax.ptr, nnz, part.ptr);
+    std::vector<double> hp(nb);
+    B200_CUDA_CHECK(cudaMemcpyAsync(hp.data(), part.ptr, nb * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    B200_CUDA_CHECK(cudaStreamSynchronize(stream));
+    double s = 0.0;
+    for (double v : hp) s += v;
+    trAtA_local = s;
+    trAtA = static_cast<float>(s);
+    build_transpose();
+    matrix_ready = true;
+}
+
+void Engine::build_transpose() {
+    // Stable LSD radix sort of (row, position): positions — hence column indices — stay ascending
+    // within each row, exactly the order Eigen's transpose() produces.
+    Atp.ensure(static_cast<size_t>(m) + 1);
+    Ati.ensure(std::max<int64_t>(nnz, 1) + 4);
+    Atx.ensure(std::max<int64_t>(nnz, 1) + 4);
+    if (nnz == 0) {
+        B200_CUDA_CHECK(cudaMemsetAsync(Atp.ptr, 0, (static_cast<size_t>(m) + 1) * sizeof(int), stream));
+        B200_CUDA_CHECK(cudaStreamSynchronize(stream));
+        return;
+    }
+    DeviceBuffer<int> col_of, keys_out;
+    DeviceBuffer<unsigned> perm_in, perm_out;
+    col_of.ensure(nnz); keys_out.ensure(nnz); perm_in.ensure(nnz); perm_out.ensure(nnz);
+    const int T = 256;
+    const unsigned gb = static_cast<unsigned>((nnz + T - 1) / T);
+    expand_columns_kernel<<<gb, T, 0, stream>>>(Ap.ptr, n, nnz, col_of.ptr);
+    iota_kernel<<<gb, T, 0, stream>>>(perm_in.ptr, nnz);
+    int end_bit = 1;
+    while ((1LL << end_bit) < static_cast<long long>(m) && end_bit < 31) ++end_bit;
+    size_t temp_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, Ai.ptr, keys_out.ptr, perm_in.ptr, perm_out.ptr, nnz, 0,
+                                    end_bit, stream);
+    DeviceBuffer<unsigned char> temp;
+    temp.ensure(temp_bytes);
+    B200_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(temp.ptr, temp_bytes, Ai.ptr, keys_out.ptr, perm_in.ptr,
+                                                    perm_out.ptr, nnz, 0, end_bit, stream));
+    permute_gather_kernel<<<gb, T, 0, stream>>>(perm_out.ptr, col_of.ptr, Ax.ptr, nnz, Ati.ptr, Atx.ptr);
+    row_pointers_kernel<<<(m + 1 + T - 1) / T, T, 0, stream>>>(keys_out.ptr, nnz, m, Atp.ptr);
+    B200_CUDA_CHECK(cudaGetLastError());
+    B200_CUDA_CHECK(cudaStreamSynchronize(stream));
+}
+
+template <class ValT>
+void Engine::set_matrix_host(int m_, int n_, int64_t nnz_, const int* col_ptr, const int* row_idx, const ValT* values) {
+    use_device();
+    B200_REQUIRE(m_ > 0 && n_ > 0 && nnz_ >= 0, "set_matrix: bad dimensions");
+    B200_REQUIRE(nnz_ < (1LL << 31), "set_matrix: nnz must fit int32 (reference boundary, bridge_nmf.hpp:196)");
+    m = m_; n = n_; nnz = nnz_; col_begin = 0;
+    Ap.ensure(static_cast<size_t>(n) + 1);
+    Ai.ensure(std::max<int64_t>(nnz, 1) + 4);
+    Ax.ensure(std::max<int64_t>(nnz, 1) + 4);
+    B200_CUDA_CHECK(cudaMemcpyAsync(Ap.ptr, col_ptr, (static_cast<size_t>(n) + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
+    if (nnz > 0) {
+        B200_CUDA_CHECK(cudaMemcpyAsync(Ai.ptr, row_idx, nnz * sizeof(int), cudaMemcpyHostToDevice, stream));
+        if (std::is_same<ValT, float>::value) {
+            B200_CUDA_CHECK(cudaMemcpyAsync(Ax.ptr, values, nnz * sizeof(float), cudaMemcpyHostToDevice, stream));
+        } else {
+            DeviceBuffer<double> tmp;
+            tmp.ensure(nnz);
+            B200_CUDA_CHECK(cudaMemcpyAsync(tmp.ptr, values, nnz * sizeof(double), cudaMemcpyHostToDevice, stream));
+            f64_to_f32_kernel<<<static_cast<unsigned>((nnz + 255) / 256), 256, 0, stream>>>(tmp.ptr, Ax.ptr, nnz);
+            B200_CUDA_CHECK(cudaStreamSynchronize(stream));
+        }
+    }
+    h2d_bytes += (static_cast<size_t>(n) + 1) * sizeof(int) + nnz * (sizeof(int) + sizeof(ValT));
+    finish_matrix();
+}
+template void Engine::set_matrix_host<float>(int, int, int64_t, const int*, const int*, const float*);
+template void Engine::set_matrix_host<double>(int, int, int64_t, const int*, const int*, const double*);
+
+void Engine::set_matrix_synthetic(int m_, int n_local, int col_begin_, double density, uint64_t seed) {
+    use_device();
+    B200_REQUIRE(m_ > 0 && n_local > 0, "synthetic: bad dimensions");
+    const long long cnt_ll = std::llround(static_cast<double>(m_) * density);
+    B200_REQUIRE(cnt_ll >= 1 && cnt_ll <= 8192, "synthetic: round(m*density) must be in [1, 8192]");
+    const int cnt = static_cast<int>(cnt_ll);
+    m = m_; n = n_local; col_begin = col_begin_;
+    DeviceBuffer<int> counts;
+    counts.ensure(static_cast<size_t>(n) + 1);
+    Ap.ensure(static_cast<size_t>(n) + 1);
+    auto run = [&](int pass, int* rows, float* vals) {
+        if (cnt <= 1024) synth_column_kernel<1024><<<n, 256, 0, stream>>>(m, n, col_begin, cnt, seed, pass, counts.ptr, Ap.ptr, rows, vals);
+        else if (cnt <= 4096) synth_column_kernel<4096><<<n, 256, 0, stream>>>(m, n, col_begin, cnt, seed, pass, counts.ptr, Ap.ptr, rows, vals);
+        else synth_column_kernel<8192><<<n, 256, 0, stream>>>(m, n, col_begin, cnt, seed, pass, counts.ptr, Ap.ptr, rows, vals);
+        B200_CUDA_CHECK(cudaGetLastError());
+    };
+    run(0, nullptr, nullptr);
+    B200_CUDA_CHECK(cudaMemsetAsync(counts.ptr + n, 0, sizeof(int), stream));
+    size_t temp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, temp_bytes, counts.ptr, Ap.ptr, n + 1, stream);
+    DeviceBuffer<unsigned char> temp;
+    temp.ensure(temp_bytes);
+    B200_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(temp.ptr, temp_bytes, counts.ptr, Ap.ptr, n + 1, stream));
+    int total = 0;
+    B200_CUDA_CHECK(cudaMemcpyAsync(&total, Ap.ptr + n, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    B200_CUDA_CHECK(cudaStreamSynchronize(stream));
+    B200_REQUIRE(total >= 0, "synthetic: nnz overflowed int32");
+    nnz = total;
+    Ai.ensure(std::max<int64_t>(nnz, 1) + 4);
+    Ax.ensure(std::max<int64_t>(nnz, 1) + 4);
+    run(1, Ai.ptr, Ax.ptr);
+    finish_matrix();
+}
+
+// ---- factors --------------------------------------------------------------------------------
+void Engine::alloc_factors(int k_) {
+    B200_REQUIRE(matrix_ready, "set a matrix before the factors");
+    B200_REQUIRE(k_ >= 1 && k_ <= kMaxKP, "rank must be in [1, 128]");
+    k = k_;
+    LANES = lanes_for_rank(k);
+    KP = padded_rank(k);
+    W_T.ensure(static_cast<size_t>(m) * KP);
+    H.ensure(static_cast<size_t>(n) * KP);
+    d.ensure(KP);
+    G_w.ensure(static_cast<size_t>(KP) * KP);
+    G_h.ensure(static_cast<size_t>(KP) * KP);
+    M1.ensure(static_cast<size_t>(KP) * KP);
+    M2.ensure(static_cast<size_t>(KP) * KP);
+    diag.ensure(KP);
+    gram_grid = num_sms * 2;
+    gram_partials.ensure(static_cast<size_t>(gram_grid) * KP * KP);
+    // the solve grid depends on the instantiation; size the partial buffers for the largest
+    int gmax = 0;
+    HalfStepParams dummy{};
+    for (int solver = 0; solver < 2; ++solver) {
+        int g = 0;
+        launch_half_step(LANES, solver, BSRC_GATHER, OUT_SOLVE, dummy, num_sms, stream, &g);
+        gmax = std::max(gmax, g);
+        launch_half_step(LANES, solver, BSRC_LOAD, OUT_SOLVE, dummy, num_sms, stream, &g);
+        gmax = std::max(gmax, g);
+    }
+    solve_grid_max = gmax;
+    norm_partials.ensure(static_cast<size_t>(gmax) * KP);
+    cross_partials.ensure(gmax);
+    std::vector<float> ones(KP, 1.f);
+    B200_CUDA_CHECK(cudaMemcpyAsync(d.ptr, ones.data(), KP * sizeof(float), cudaMemcpyHostToDevice, stream));
+    B200_CUDA_CHECK(cudaStreamSynchronize(stream));
+    factors_ready = true;
+}
+
+template <class T>
+void Engine::set_factors_host(int k_, const T* W_T_host, const T* H_host) {
+    use_device();
+    alloc_factors(k_);
+    auto upload = [&](const T* src, float* dst, long long ncols) {
+        DeviceBuffer<T> tmp;
+        tmp.ensure(static_cast<size_t>(ncols) * k);
+        B200_CUDA_CHECK(cudaMemcpyAsync(tmp.ptr, src, static_cast<size_t>(ncols) * k * sizeof(T), cudaMemcpyHostToDevice, stream));
+        const long long total = ncols * KP;
+        pad_convert_kernel<T><<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(tmp.ptr, dst, ncols, k, KP);
+        B200_CUDA_CHECK(cudaStreamSynchronize(stream));
+        h2d_bytes += static_cast<size_t>(ncols) * k * sizeof(T);
+    };
+    upload(W_T_host, W_T.ptr, m);
+    upload(H_host, H.ptr, n);
+}
+template void Engine::set_factors_host<float>(int, const float*, const float*);
+template void Engine::set_factors_host<double>(int, const double*, const double*);
+
+void Engine::init_factors(int k_, uint32_t seed, int h_col_begin) {
+    use_device();
+    alloc_factors(k_);
+    const unsigned long long state0 = (seed == 0) ? 12345ULL : static_cast<unsigned long long>(seed);   // rng.hpp:73
+    const long long tw = static_cast<long long>(m) * KP, th = static_cast<long long>(n) * KP;
+    init_uniform_kernel<<<static_cast<unsigned>((tw + 255) / 256), 256, 0, stream>>>(W_T.ptr, m, k, KP, state0, 0ULL);
+    const unsigned long long first_h = static_cast<unsigned long long>(m) * k + static_cast<unsigned long long>(h_col_begin) * k;
+    init_uniform_kernel<<<static_cast<unsigned>((th + 255) / 256), 256, 0, stream>>>(H.ptr, n, k, KP, state0, first_h);
+    B200_CUDA_CHECK(cudaGetLastError());
+    B200_CUDA_CHECK(cudaStreamSynchronize(stream));
+}
+
+template <class T>
+void Engine::get_factors_host(T* W_T_host, T* H_host, T* d_host) {
+    use_device();
+    B200_REQUIRE(factors_ready, "no factors");
+    auto download = [&](const float* src, T* dst, long long ncols) {
+        if (!dst) return;
+        DeviceBuffer<T> tmp;
+        tmp.ensure(static_cast<size_t>(ncols) * k);
+        const long long total = ncols * k;
+        unpad_convert_kernel<T><<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(src, tmp.ptr, ncols, k, KP);
+        B200_CUDA_CHECK(cudaMemcpyAsync(dst, tmp.ptr, static_cast<size_t>(total) * sizeof(T), cudaMemcpyDeviceToHost, stream));
+        B200_CUDA_CHECK(cudaStreamSynchronize(stream));
+        d2h_bytes += static_cast<size_t>(total) * sizeof(T);
+    };
+    download(W_T.ptr, W_T_host, m);
+    download(H.ptr, H_host, n);
+    download(d.ptr, d_host, 1);
+}
+template void Engine::get_factors_host<float>(float*, float*, float*);
+template void Engine::get_factors_host<double>(double*, double*, double*);
+
+// ---- profiling sections -----------------------------------------------------------------------
+void Engine::sec_begin(int sec) {
+    if (!profiling) return;
+    auto& pool = prof_events[sec];
+    if (prof_used[sec] == static_cast<int>(pool.size())) {
+        cudaEvent_t a, b;
+        B200_CUDA_CHECK(cudaEventCreate(&a));
+        B200_CUDA_CHECK(cudaEventCreate(&b));
+        pool.emplace_back(a, b);
+    }
+    B200_CUDA_CHECK(cudaEventRecord(pool[prof_used[sec]].first, stream));
+}
+void Engine::sec_end(int sec) {
+    if (!profiling) return;
+    B200_CUDA_CHECK(cudaEventRecord(prof_events[sec][prof_used[sec]].second, stream));
+    ++prof_used[sec];
+}
+void Engine::collect_profile() {
+    if (!profiling) return;
+    for (int s = 0; s < RCPPML_B200_NUM_SECTIONS; ++s) {
+        for (int i = 0; i < prof_used[s]; ++i) {
+            float ms = 0.f;
+            B200_CUDA_CHECK(cudaEventElapsedTime(&ms, prof_events[s][i].first, prof_events[s][i].second));
+            prof_ms[s] += ms;
+        }
+        prof_used[s] = 0;
+    }
+}
+
+// ---- one iteration ----------------------------------------------------------------------------
+void Engine::normalize_cfg(const rcppml_b200_config& c) {
+    cfg = c;
+    B200_REQUIRE(cfg.k == k, "config rank differs from the factors' rank");
+    if (cfg.cd_maxit <= 0) cfg.cd_maxit = 10;          // src/RcppFunctions_nmf.cpp:75
+    if (!(cfg.cd_tol > 0.f)) cfg.cd_tol = 1e-8f;       // src/RcppFunctions_nmf.cpp:76
+    if (cfg.patience <= 0) cfg.patience = 5;           // core/constants.hpp:89
+    B200_REQUIRE(cfg.tol >= 0.f, "tol must be non-negative");                          // core/config.hpp:426
+    B200_REQUIRE(cfg.norm_type >= 0 && cfg.norm_type <= 2, "norm_type must be 0, 1 or 2");
+}
+
+void Engine::gram(float* X, long long ncols, bool normalize, float* G_out, int sec) {
+    sec_begin(sec);
+    launch_normalize_gram(KP, X, ncols, d.ptr, normalize ? 1 : 0, gram_partials.ptr, &state.ptr->stop, gram_grid, stream);
+    gram_reduce_kernel<<<(KP * KP + 255) / 256, 256, 0, stream>>>(gram_partials.ptr, gram_grid, KP, k, G_out, &state.ptr->stop);
+    launches[sec] += 2;
+    sec_end(sec);
+}
+
+void Engine::prepare_solver(const float* G, float L2, int sec) {
+    sec_begin(sec);
+    const int solver = cfg.solver_mode == 0 ? SOLVER_CD : SOLVER_CHOL;
+    const size_t smem = static_cast<size_t>(KP) * KP * sizeof(float);
+    static thread_local bool attr_set = false;
+    if (!attr_set) {
+        B200_CUDA_CHECK(cudaFuncSetAttribute(prepare_solver_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * 4));
+        attr_set = true;
+    }
+    prepare_solver_kernel<<<1, 128, smem, stream>>>(G, KP, k, L2, solver, M1.ptr, M2.ptr, diag.ptr, state.ptr);
+    launches[sec] += 1;
+    sec_end(sec);
+}
+
+static int pick_cols_per_fetch(long long nnz, long long ncols) {
+    // ~2K non-zeros per group fetch bounds the tail imbalance; 1..16 columns
+    const double avg = ncols > 0 ? static_cast<double>(nnz) / static_cast<double>(ncols) : 1.0;
+    int c = static_cast<int>(2048.0 / std::max(1.0, avg));
+    return std::max(1, std::min(16, c));
+}
+
+void Engine::solve(int which, bool warm, int sec) {
+    HalfStepParams p{};
+    const bool h = (which == 0);
+    p.colptr = h ? Ap.ptr : Atp.ptr;
+    p.rowidx = h ? Ai.ptr : Ati.ptr;
+    p.vals = h ? Ax.ptr : Atx.ptr;
+    p.F = h ? W_T.ptr : H.ptr;
+    p.X = h ? H.ptr : W_T.ptr;
+    p.M1 = M1.ptr; p.M2 = M2.ptr; p.diag = diag.ptr;
+    p.B = nullptr; p.nslots = 0; p.slot_stride = 0;
+    p.ncols = h ? n : m;
+    p.col_offset = 0;
+    p.k = k;
+    p.L1 = h ? cfg.L1_H : cfg.L1_W;
+    p.ub = h ? cfg.ub_H : cfg.ub_W;
+    p.cd_tol = cfg.cd_tol;
+    p.inv_k = 1.0f / static_cast<float>(k);            // nnls_batch.hpp:84
+    p.cd_maxit = cfg.cd_maxit;
+    p.nonneg = h ? cfg.nonneg_H : cfg.nonneg_W;
+    p.warm = warm ? 1 : 0;
+    p.norm_type = cfg.norm_type;
+    p.want_cross = h ? 0 : 1;
+    p.cols_per_fetch = pick_cols_per_fetch(nnz, p.ncols);
+    p.work_counter = counters.ptr + which;
+    p.norm_partials = norm_partials.ptr;
+    p.cross_partials = cross_partials.ptr;
+    p.stop_flag = &state.ptr->stop;
+    p.sweep_counter = sweep_counter.ptr;
+    const int solver = cfg.solver_mode == 0 ? SOLVER_CD : SOLVER_CHOL;
+    int grid = 0;
+    launch_half_step(LANES, solver, BSRC_GATHER, OUT_SOLVE, p, num_sms, stream, &grid);
+    last_solve_grid = grid;
+    sec_begin(sec);
+    B200_CUDA_CHECK(cudaMemsetAsync(p.work_counter, 0, sizeof(int), stream));
+    launch_half_step(LANES, solver, BSRC_GATHER, OUT_SOLVE, p, num_sms, stream);
+    launches[sec] += 1;
+    sec_end(sec);
+}
+
+void Engine::scale_finalize(int sec) {
+    sec_begin(sec);
+    scale_finalize_kernel<<<1, 128, 0, stream>>>(norm_partials.ptr, last_solve_grid, KP, k, cfg.norm_type, d.ptr, nullptr, &state.ptr->stop);
+    launches[sec] += 1;
+    sec_end(sec);
+}
+
+void Engine::enqueue_iteration() {
+    const bool warm = iters_enqueued > 0;                                   // fit_cpu.hpp:523 / :755
+    const bool normalize = cfg.norm_type != 2;
+    // ---- H update (fit_cpu.hpp:488-645)
+    if (iters_enqueued == 0) gram(W_T.ptr, m, false, G_w.ptr, RCPPML_B200_SEC_GRAM_H);   // :491 (later: reuse G_wt)
+    prepare_solver(G_w.ptr, cfg.L2_H, RCPPML_B200_SEC_GRAM_H);              // :506
+    solve(0, warm, RCPPML_B200_SEC_SOLVE_H);                                // :516-535 (+ :636 upper bound)
+    scale_finalize(RCPPML_B200_SEC_SCALE_H);                                // :644
+    // ---- W update (fit_cpu.hpp:713-893)
+    gram(H.ptr, n, normalize, G_h.ptr, RCPPML_B200_SEC_GRAM_W);             // :644 (normalise) + :715
+    prepare_solver(G_h.ptr, cfg.L2_W, RCPPML_B200_SEC_GRAM_W);              // :738
+    solve(1, warm, RCPPML_B200_SEC_SOLVE_W);                                // :748-767 (+ :884)
+    scale_finalize(RCPPML_B200_SEC_SCALE_W);                                // :892
+    // ---- loss (fit_cpu.hpp:1729-1809): Gram of the new W_T doubles as next iteration's gram_H
+    sec_begin(RCPPML_B200_SEC_LOSS);
+    const bool was = profiling; profiling = false;                         // nested section: account under LOSS
+    gram(W_T.ptr, m, normalize, G_w.ptr, RCPPML_B200_SEC_LOSS);             // :892 (normalise) + :1735
+    profiling = was;
+    loss_kernel<<<1, 256, 0, stream>>>(G_w.ptr, G_h.ptr, d.ptr, KP, k, cross_partials.ptr, last_solve_grid, trAtA,
+                                       cfg.tol, cfg.patience, loss_hist.ptr, static_cast<int>(loss_hist.count), state.ptr);
+    launches[RCPPML_B200_SEC_LOSS] += 1;
+    sec_end(RCPPML_B200_SEC_LOSS);
+    ++iters_enqueued;
+}
+
+void Engine::begin_fit(const rcppml_b200_config& c) {
+    use_device();
+    B200_REQUIRE(matrix_ready && factors_ready, "begin_fit: matrix and factors must be set first");
+    normalize_cfg(c);
+    B200_REQUIRE(world == 1 || comm_ready(), "begin_fit: communicator not initialised");
+    iters_enqueued = 0;
+    loss_hist.ensure(static_cast<size_t>(std::max(cfg.max_iter, 1024)));
+    DevState s0{};
+    s0.prev_loss = 3.402823466e+38f;                                        // fit_cpu.hpp:281
+    B200_CUDA_CHECK(cudaMemcpyAsync(state.ptr, &s0, sizeof(DevState), cudaMemcpyHostToDevice, stream));
+    B200_CUDA_CHECK(cudaMemsetAsync(sweep_counter.ptr, 0, sizeof(unsigned long long), stream));
+    std::vector<float> ones(KP, 1.f);                                       // d = 1 (fit_cpu.hpp:198)
+    B200_CUDA_CHECK(cudaMemcpyAsync(d.ptr, ones.data(), KP * sizeof(float), cudaMemcpyHostToDevice, stream));
+    B200_CUDA_CHECK(cudaStreamSynchronize(stream));
+    for (int s = 0; s < RCPPML_B200_NUM_SECTIONS; ++s) { prof_ms[s] = 0.0; launches[s] = 0; prof_used[s] = 0; }
+    fit_active = true;
+    loop_ms = 0.0;
+}
+
+void Engine::iterate(int n_iters) {
+    use_device();
+    B200_REQUIRE(fit_active, "iterate: call begin_fit first");
+    B200_CUDA_CHECK(cudaEventRecord(ev_loop_begin, stream));
+    // The host never waits inside the loop: convergence is decided on the device (DevState) and
+    // kernels enqueued after `stop` return immediately. Every 8 iterations the host peeks at the
+    // flag only to avoid enqueuing a long tail of no-op launches.
+    for (int it = 0; it < n_iters; ++it) {
+        if (world > 1) enqueue_iteration_sharded(); else enqueue_iteration();
+        if ((it & 7) == 7 && cfg.tol > 0.f) {
+            B200_CUDA_CHECK(cudaMemcpyAsync(h_state, state.ptr, sizeof(DevState), cudaMemcpyDeviceToHost, stream));
+            B200_CUDA_CHECK(cudaStreamSynchronize(stream));
+            if (h_state->stop) break;
+        }
+    }
+    B200_CUDA_CHECK(cudaEventRecord(ev_loop_end, stream));
+    B200_CUDA_CHECK(cudaGetLastError());
+    B200_CUDA_CHECK(cudaStreamSynchronize(stream));
+    float ms = 0.f;
+    B200_CUDA_CHECK(cudaEventElapsedTime(&ms, ev_loop_begin, ev_loop_end));
+    loop_ms = ms;
+    collect_profile();
+}
+
+void Engine::half_step_only(const rcppml_b200_config& c, int which, bool warm, bool normalize_after) {
+    use_device();
+    B200_REQUIRE(matrix_ready && factors_ready, "half_step: matrix and factors must be set first");
+    B200_REQUIRE(world == 1, "half_step: single-GPU diagnostic entry");
+    normalize_cfg(c);
+    DevState s0{};
+    s0.prev_loss = 3.402823466e+38f;
+    B200_CUDA_CHECK(cudaMemcpyAsync(state.ptr, &s0, sizeof(DevState), cudaMemcpyHostToDevice, stream));
+    const bool h = (which == 0);
+    gram(h ? W_T.ptr : H.ptr, h ? m : n, false, h ? G_w.ptr : G_h.ptr, RCPPML_B200_SEC_GRAM_H);
+    prepare_solver(h ? G_w.ptr : G_h.ptr, h ? cfg.L2_H : cfg.L2_W, RCPPML_B200_SEC_GRAM_H);
+    solve(which, warm, h ? RCPPML_B200_SEC_SOLVE_H : RCPPML_B200_SEC_SOLVE_W);
+    scale_finalize(RCPPML_B200_SEC_SCALE_H);
+    if (normalize_after && cfg.norm_type != 2)
+        gram(h ? H.ptr : W_T.ptr, h ? n : m, true, h ? G_h.ptr : G_w.ptr, RCPPML_B200_SEC_GRAM_W);
+    B200_CUDA_CHECK(cudaGetLastError());
+    B200_CUDA_CHECK(cudaStreamSynchronize(stream));
+}
+
+void Engine::get_result(rcppml_b200_result* out) {
+    use_device();
+    DevState s{};
+    B200_CUDA_CHECK(cudaMemcpyAsync(&s, state.ptr, sizeof(DevState), cudaMemcpyDeviceToHost, stream));
+    unsigned long long sw = 0;
+    B200_CUDA_CHECK(cudaMemcpyAsync(&sw, sweep_counter.ptr, sizeof(sw), cudaMemcpyDeviceToHost, stream));
+    B200_CUDA_CHECK(cudaStreamSynchronize(stream));
+    out->iterations = s.iter;
+    out->converged = s.converged;
+    out->train_loss = s.train_loss;
+    out->final_tol = s.final_tol;
+    out->status = s.chol_fail ? 1 : 0;
+    int total = 0;
+    for (int i = 0; i < RCPPML_B200_NUM_SECTIONS; ++i) total += launches[i];
+    out->gpu_launches = total;
+    out->loop_ms = loop_ms;
+    cd_sweeps = sw;
+}
+
+}  // namespace b200
+
+// =============================================================================================
+// C ABI (include/rcppml_gpu.h, part 2)
+// =============================================================================================
+using b200::Engine;
+
+#define B200_API_BEGIN try {
+#define B200_API_END                                                      \
+    return 0;                                                             \
+    }                                                                     \
+    catch (const std::exception& ex) {                                    \
+        b200::g_last_error = ex.what();                                   \
+        return -1;                                                        \
+    }                                                                     \
+    catch (...) {                                                         \
+        b200::g_last_error = "unknown error";                             \
+        return -1;                                                        \
+    }
+
+struct rcppml_b200_engine {
+    Engine impl;
+    explicit rcppml_b200_engine(int dev) : impl(dev) {}
+};
+
+extern "C" {
+
+const char* rcppml_b200_last_error(void) { return b200::g_last_error.c_str(); }
+
+int rcppml_b200_engine_create(rcppml_b200_engine** out, int device) {
+    B200_API_BEGIN
+    B200_REQUIRE(out != nullptr, "engine_create: null output");
+    int count = 0;
+    B200_CUDA_CHECK(cudaGetDeviceCount(&count));
+    B200_REQUIRE(device >= 0 && device < count, "engine_create: no such CUDA device");
+    *out = new rcppml_b200_engine(device);
+    B200_API_END
+}
+void rcppml_b200_engine_destroy(rcppml_b200_engine* e) { delete e; }
+
+int rcppml_b200_set_matrix_f32(rcppml_b200_engine* e, int m, int n, int64_t nnz, const int* col_ptr, const int* row_idx, const float* values) {
+    B200_API_BEGIN e->impl.set_matrix_host<float>(m, n, nnz, col_ptr, row_idx, values); B200_API_END
+}
+int rcppml_b200_set_matrix_f64(rcppml_b200_engine* e, int m, int n, int64_t nnz, const int* col_ptr, const int* row_idx, const double* values) {
+    B200_API_BEGIN e->impl.set_matrix_host<double>(m, n, nnz, col_ptr, row_idx, values); B200_API_END
+}
+int rcppml_b200_set_matrix_synthetic(rcppml_b200_engine* e, int m, int n_local, int col_begin, double density, uint64_t seed) {
+    B200_API_BEGIN e->impl.set_matrix_synthetic(m, n_local, col_begin, density, seed); B200_API_END
+}
+static void copy_csc(Engine& E, const int* dp, const int* di, const float* dx, int ncols, int* p, int* i, float* x) {
+    E.use_device();
+    if (p) B200_CUDA_CHECK(cudaMemcpy(p, dp, (static_cast<size_t>(ncols) + 1) * sizeof(int), cudaMemcpyDeviceToHost));
+    if (i && E.nnz) B200_CUDA_CHECK(cudaMemcpy(i, di, E.nnz * sizeof(int), cudaMemcpyDeviceToHost));
+    if (x && E.nnz) B200_CUDA_CHECK(cudaMemcpy(x, dx, E.nnz * sizeof(float), cudaMemcpyDeviceToHost));
+}
+int rcppml_b200_get_matrix(rcppml_b200_engine* e, int64_t* nnz, int* col_ptr, int* row_idx, float* values) {
+    B200_API_BEGIN
+    B200_REQUIRE(e->impl.matrix_ready, "no matrix");
+    if (nnz) *nnz = e->impl.nnz;
+    copy_csc(e->impl, e->impl.Ap.ptr, e->impl.Ai.ptr, e->impl.Ax.ptr, e->impl.n, col_ptr, row_idx, values);
+    B200_API_END
+}
+int rcppml_b200_get_matrix_t(rcppml_b200_engine* e, int* col_ptr, int* row_idx, float* values) {
+    B200_API_BEGIN
+    B200_REQUIRE(e->impl.matrix_ready, "no matrix");
+    copy_csc(e->impl, e->impl.Atp.ptr, e->impl.Ati.ptr, e->impl.Atx.ptr, e->impl.m, col_ptr, row_idx, values);
+    B200_API_END
+}
+int rcppml_b200_set_factors_f32(rcppml_b200_engine* e, int k, const float* W_T, const float* H) {
+    B200_API_BEGIN e->impl.set_factors_host<float>(k, W_T, H); B200_API_END
+}
+int rcppml_b200_set_factors_f64(rcppml_b200_engine* e, int k, const double* W_T, const double* H) {
+    B200_API_BEGIN e->impl.set_factors_host<double>(k, W_T, H); B200_API_END
+}
+int rcppml_b200_init_factors(rcppml_b200_engine* e, int k, uint32_t seed, int h_col_begin) {
+    B200_API_BEGIN e->impl.init_factors(k, seed, h_col_begin); B200_API_END
+}
+int rcppml_b200_get_factors_f32(rcppml_b200_engine* e, float* W_T, float* H, float* d) {
+    B200_API_BEGIN e->impl.get_factors_host<float>(W_T, H, d); B200_API_END
+}
+int rcppml_b200_get_factors_f64(rcppml_b200_engine* e, double* W_T, double* H, double* d) {
+    B200_API_BEGIN e->impl.get_factors_host<double>(W_T, H, d); B200_API_END
+}
+int rcppml_b200_begin_fit(rcppml_b200_engine* e, const rcppml_b200_config* cfg) {
+    B200_API_BEGIN e->impl.begin_fit(*cfg); B200_API_END
+}
+int rcppml_b200_iterate(rcppml_b200_engine* e, int n_iters) {
+    B200_API_BEGIN e->impl.iterate(n_iters); B200_API_END
+}
+int rcppml_b200_fit(rcppml_b200_engine* e, const rcppml_b200_config* cfg) {
+    B200_API_BEGIN
+    B200_REQUIRE(cfg->max_iter > 0, "max_iter must be positive");        // core/config.hpp:424
+    e->impl.begin_fit(*cfg);
+    e->impl.iterate(cfg->max_iter);
+    B200_API_END
+}
+int rcppml_b200_get_result(rcppml_b200_engine* e, rcppml_b200_result* out) {
+    B200_API_BEGIN e->impl.get_result(out); B200_API_END
+}
+int rcppml_b200_get_loss_history(rcppml_b200_engine* e, float* out, int capacity) {
+    B200_API_BEGIN
+    Engine& E = e->impl;
+    E.use_device();
+    const int cnt = std::min<int>(capacity, static_cast<int>(E.loss_hist.count));
+    if (cnt > 0) B200_CUDA_CHECK(cudaMemcpy(out, E.loss_hist.ptr, cnt * sizeof(float), cudaMemcpyDeviceToHost));
+    B200_API_END
+}
+int rcppml_b200_set_profiling(rcppml_b200_engine* e, int enabled) {
+    B200_API_BEGIN e->impl.profiling = enabled != 0; B200_API_END
+}
+int rcppml_b200_get_profile(rcppml_b200_engine* e, double* ms, int* launches) {
+    B200_API_BEGIN
+    for (int s = 0; s < RCPPML_B200_NUM_SECTIONS; ++s) {
+        if (ms) ms[s] = e->impl.prof_ms[s];
+        if (launches) launches[s] = e->impl.launches[s];
+    }
+    B200_API_END
+}
+int rcppml_b200_half_step(rcppml_b200_engine* e, const rcppml_b200_config* cfg, int which, int warm_start, int normalize_after) {
+    B200_API_BEGIN e->impl.half_step_only(*cfg, which, warm_start != 0, normalize_after != 0); B200_API_END
+}
+int64_t rcppml_b200_cd_sweeps(rcppml_b200_engine* e) { return static_cast<int64_t>(e->impl.cd_sweeps); }
+int rcppml_b200_get_counters(rcppml_b200_engine* e, int64_t* h2d_bytes, int64_t* d2h_bytes) {
+    B200_API_BEGIN
+    if (h2d_bytes) *h2d_bytes = static_cast<int64_t>(e->impl.h2d_bytes);
+    if (d2h_bytes) *d2h_bytes = static_cast<int64_t>(e->impl.d2h_bytes);
+    B200_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,329 @@
+// kernels_dense.cuh — the dense k×k / k×n pieces of one ALS iteration:
+//   * normalize_gram_kernel : X[i,:] /= d_i fused with the Gram G = X·Xᵀ of the normalised factor
+//     (nmf/variant_helpers.hpp:302-304 + primitives/cpu/gram.hpp:58-67), one pass over X
+//   * gram_reduce_kernel    : fixed-order fp64 reduction of the per-CTA Gram partials
+//   * prepare_solver_kernel : G += L2·I (fit_cpu.hpp:506,738) and, for solver_mode != 0, the LLT
+//     factorisation (fused_nnls.hpp:185) in the oracle's operation order
+//   * scale_finalize_kernel : d_i = Σ partials (+sqrt) + 1e-15 (variant_helpers.hpp:297-301)
+//   * loss_kernel           : Gram-trick loss + convergence/patience (fit_cpu.hpp:1729-1809)
+#pragma once
+
+#include "common.cuh"
+#include <type_traits>
+
+namespace b200 {
+
+// Device-resident iteration state: lets the host enqueue iterations without synchronising.
+struct DevState {
+    int stop;               // set when converged (patience reached) -> later kernels exit at once
+    int iter;               // iterations completed (result.iterations)
+    int converged;
+    int patience_counter;
+    int chol_fail;          // first non-positive pivot index + 1 (0 = none)
+    float prev_loss;
+    float final_tol;
+    float train_loss;
+};
+
+// ---------------------------------------------------------------------------------------------
+// normalize + Gram. X is [ncols][KP] (row c = column c of the reference's k×ncols matrix).
+// 256 threads as a 16×16 grid, each owning an R×R tile of G (R = KP/16). Column tiles of TC
+// columns are staged in shared memory; after every tile the fp32 tile sums are flushed into
+// fp64 accumulators, so no fp32 chain is longer than TC terms.
+// ---------------------------------------------------------------------------------------------
+template <int KP, int TC>
+static __global__ void __launch_bounds__(256) normalize_gram_kernel(float* __restrict__ X, long long ncols,
+                                                             const float* __restrict__ d, int normalize,
+                                                             double* __restrict__ partials,
+                                                             const int* __restrict__ stop_flag) {
+    constexpr int R = KP / 16;
+    constexpr int V4 = KP / 4;                       // float4 per column
+    __shared__ __align__(16) float sX[TC][KP];
+    __shared__ float sD[KP];
+    if (*stop_flag) return;
+    for (int t = threadIdx.x; t < KP; t += blockDim.x) sD[t] = normalize ? d[t] : 1.f;
+    __syncthreads();
+
+    const int ti = threadIdx.x / 16, tj = threadIdx.x % 16;
+    // Second-level accumulator: fp64 when it fits in registers (R <= 4), else fp32 over the
+    // (short: ncols / (TC*gridDim)) sequence of tile sums. The cross-CTA reduction is fp64 either way.
+    using Acc2 = typename std::conditional<(R <= 4), double, float>::type;
+    Acc2 acc64[R][R];
+#pragma unroll
+    for (int a = 0; a < R; ++a)
+#pragma unroll
+        for (int b = 0; b < R; ++b) acc64[a][b] = Acc2(0);
+
+    const long long ntiles = (ncols + TC - 1) / TC;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long c0 = tile * TC;
+        const long long left = ncols - c0;
+        const int nc = left < TC ? static_cast<int>(left) : TC;
+        float4* X4 = reinterpret_cast<float4*>(X + c0 * KP);
+        for (int t = threadIdx.x; t < TC * V4; t += blockDim.x) {
+            const int c = t / V4, q = t % V4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c < nc) {
+                v = X4[t];
+                if (normalize) {                     // padded coordinates hold 0 and sD = 1 there... (d padded = 1)
+                    v.x = __fdiv_rn(v.x, sD[q * 4 + 0]);
+                    v.y = __fdiv_rn(v.y, sD[q * 4 + 1]);
+                    v.z = __fdiv_rn(v.z, sD[q * 4 + 2]);
+                    v.w = __fdiv_rn(v.w, sD[q * 4 + 3]);
+                    X4[t] = v;
+                }
+            }
+            *reinterpret_cast<float4*>(&sX[c][q * 4]) = v;
+        }
+        __syncthreads();
+        float acc[R][R];
+#pragma unroll
+        for (int a = 0; a < R; ++a)
+#pragma unroll
+            for (int b = 0; b < R; ++b) acc[a][b] = 0.f;
+#pragma unroll 4
+        for (int c = 0; c < TC; ++c) {
+            float av[R], bv[R];
+#pragma unroll
+            for (int a = 0; a < R; ++a) av[a] = sX[c][ti * R + a];
+#pragma unroll
+            for (int b = 0; b < R; ++b) bv[b] = sX[c][tj * R + b];
+#pragma unroll
+            for (int a = 0; a < R; ++a)
+#pragma unroll
+                for (int b = 0; b < R; ++b) acc[a][b] = fmaf(av[a], bv[b], acc[a][b]);
+        }
+#pragma unroll
+        for (int a = 0; a < R; ++a)
+#pragma unroll
+            for (int b = 0; b < R; ++b) acc64[a][b] += static_cast<Acc2>(acc[a][b]);
+        __syncthreads();
+    }
+    double* out = partials + static_cast<size_t>(blockIdx.x) * KP * KP;
+#pragma unroll
+    for (int a = 0; a < R; ++a)
+#pragma unroll
+        for (int b = 0; b < R; ++b)
+            out[(tj * R + b) * KP + (ti * R + a)] = static_cast<double>(acc64[a][b]);   // G(i,j) at [j*KP+i]
+}
+
+// G[e] = float(Σ_cta partials[cta][e]) in CTA order; symmetrised from the lower triangle
+// (gram.hpp:64-65) with tiny_num on the diagonal (gram.hpp:66). Padded rows/cols stay 0.
+static __global__ void gram_reduce_kernel(const double* __restrict__ partials, int nparts, int KP, int k,
+                                   float* __restrict__ G, const int* __restrict__ stop_flag) {
+    if (*stop_flag) return;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= KP * KP) return;
+    const int i = e % KP, j = e / KP;
+    const int lo = (i >= j) ? (j * KP + i) : (i * KP + j);     // lower-triangle source element
+    double s = 0.0;
+    for (int c = 0; c < nparts; ++c) s += partials[static_cast<size_t>(c) * KP * KP + lo];
+    float v = static_cast<float>(s);
+    if (i == j) v = __fadd_rn(v, 1e-15f);
+    if (i >= k || j >= k) v = 0.f;
+    G[e] = v;
+}
+
+// One CTA. CD: M1 = G + L2·I, diag = diag(M1) (0 on padding). CHOL: unblocked left-looking LLT
+// in the oracle's order (dot accumulated sequentially, then subtracted, IEEE sqrt/div):
+// M1 = strictly-lower L (col-major), M2[p*KP+i] = L(p,i) (i<p), diag = diag(L).
+static __global__ void __launch_bounds__(128) prepare_solver_kernel(const float* __restrict__ G, int KP, int k, float L2,
+                                                            int solver, float* __restrict__ M1,
+                                                            float* __restrict__ M2, float* __restrict__ diag,
+                                                            DevState* __restrict__ st) {
+    extern __shared__ float sL[];          // KP*KP, col-major working copy
+    if (st->stop) return;
+    const int tid = threadIdx.x;
+    for (int e = tid; e < KP * KP; e += blockDim.x) {
+        float v = G[e];
+        const int i = e % KP, j = e / KP;
+        if (i == j && i < k && L2 > 0.f) v = __fadd_rn(v, L2);
+        sL[e] = v;
+    }
+    __syncthreads();
+    if (solver == 0) {
+        for (int e = tid; e < KP * KP; e += blockDim.x) M1[e] = sL[e];
+        for (int i = tid; i < KP; i += blockDim.x) diag[i] = sL[i * KP + i];
+        return;
+    }
+    // Left-looking Cholesky, thread i owns row i. sL is overwritten column by column (lower part).
+    for (int j = 0; j < k; ++j) {
+        float ljj = 0.f;
+        {   // every thread recomputes the pivot redundantly (broadcast reads) -> no extra barrier
+            float s = 0.f;
+            for (int p = 0; p < j; ++p) {
+                const float l = sL[p * KP + j];
+                s = __fadd_rn(s, __fmul_rn(l, l));
+            }
+            const float x = __fsub_rn(sL[j * KP + j], s);
+            if (!(x > 0.f)) {
+                if (tid == 0 && st->chol_fail == 0) st->chol_fail = j + 1;
+                ljj = 0.f;
+            } else {
+                ljj = __fsqrt_rn(x);
+            }
+        }
+        const int i = tid;
+        float lij = 0.f;
+        if (i > j && i < k) {
+            float t = 0.f;
+            for (int p = 0; p < j; ++p) t = __fadd_rn(t, __fmul_rn(sL[p * KP + i], sL[p * KP + j]));
+            lij = __fdiv_rn(__fsub_rn(sL[j * KP + i], t), ljj);
+        }
+        __syncthreads();                   // all reads of column j (as G) done
+        if (i > j && i < k) sL[j * KP + i] = lij;
+        if (i == j) sL[j * KP + j] = ljj;
+        __syncthreads();
+    }
+    for (int e = tid; e < KP * KP; e += blockDim.x) {
+        const int i = e % KP, j = e / KP;                  // e = j*KP + i  -> element (row i, col j)
+        M1[e] = (i > j && i < k) ? sL[e] : 0.f;            // strictly lower, col-major
+        // M2[p*KP + c] = L(p, c) for c < p: take p = j (slot row), c = i
+        M2[e] = (i < j && j < k) ? sL[i * KP + j] : 0.f;
+    }
+    for (int i = tid; i < KP; i += blockDim.x) diag[i] = (i < k) ? sL[i * KP + i] : 1.f;
+}
+
+// d_i = float(Σ_cta partials[cta][i]) (+sqrt for L2) + 1e-15 ; padded d_i = 1.
+// Also re-arms the work counter of the next solve kernel.
+static __global__ void scale_finalize_kernel(const double* __restrict__ partials, int nparts, int KP, int k, int norm_type,
+                                      float* __restrict__ d, int* __restrict__ work_counter,
+                                      const int* __restrict__ stop_flag) {
+    if (*stop_flag) return;
+    const int i = threadIdx.x;
+    if (i == 0 && work_counter) *work_counter = 0;
+    if (i >= KP) return;
+    if (i >= k || norm_type == 2) { d[i] = 1.f; return; }
+    double s = 0.0;
+    for (int c = 0; c < nparts; ++c) s += partials[static_cast<size_t>(c) * KP + i];
+    float v = static_cast<float>(s);
+    if (norm_type == 1) v = __fsqrt_rn(v);
+    d[i] = __fadd_rn(v, 1e-15f);
+}
+
+// loss = trAtA − 2·cross + Σ_ij d_i d_j G_wt(i,j) G_h(i,j)   (fit_cpu.hpp:1747-1753), then the
+// convergence / patience bookkeeping of fit_cpu.hpp:1769-1811. One CTA of 256 threads.
+static __global__ void __launch_bounds__(256) loss_kernel(const float* __restrict__ G_wt, const float* __restrict__ G_h,
+                                                   const float* __restrict__ d, int KP, int k,
+                                                   const double* __restrict__ cross_partials, int nparts,
+                                                   float trAtA, float tol, int patience,
+                                                   float* __restrict__ loss_hist, int hist_cap,
+                                                   DevState* __restrict__ st) {
+    __shared__ double sred[256];
+    if (st->stop) return;
+    double r = 0.0;
+    for (int e = threadIdx.x; e < KP * KP; e += blockDim.x) {
+        const int i = e % KP, j = e / KP;
+        if (i < k && j < k) {
+            const float t = __fmul_rn(__fmul_rn(__fmul_rn(d[i], d[j]), G_wt[e]), G_h[e]);
+            r += static_cast<double>(t);
+        }
+    }
+    sred[threadIdx.x] = r;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double recon = 0.0;
+        for (int t = 0; t < 256; ++t) recon += sred[t];
+        double cross = 0.0;
+        for (int c = 0; c < nparts; ++c) cross += cross_partials[c];
+        const float loss = __fadd_rn(__fsub_rn(trAtA, __fmul_rn(2.f, static_cast<float>(cross))),
+                                     static_cast<float>(recon));
+        const int iter = st->iter;
+        if (iter < hist_cap) loss_hist[iter] = loss;
+        bool loss_conv = false;
+        if (iter > 0) {
+            const float rel = __fdiv_rn(fabsf(__fsub_rn(st->prev_loss, loss)),
+                                        __fadd_rn(fabsf(st->prev_loss), 1e-15f));
+            st->final_tol = rel;
+            if (rel < tol) loss_conv = true;
+        }
+        st->prev_loss = loss;
+        st->train_loss = loss;
+        st->iter = iter + 1;
+        if (iter > 0) {
+            if (loss_conv) {
+                if (++st->patience_counter >= patience) {
+                    st->converged = 1;
+                    st->stop = 1;
+                }
+            } else {
+                st->patience_counter = 0;
+            }
+        }
+    }
+}
+
+// ---- small utilities -----------------------------------------------------------------------
+
+// dst[c][0..KP) = (float)src[c][0..k), zero padded.   (double→float at the R boundary:
+// src/RcppFunctions_nmf.cpp:4-5; src/gpu_bridge_nmf.cu:578-592)
+template <class SrcT>
+static __global__ void pad_convert_kernel(const SrcT* __restrict__ src, float* __restrict__ dst, long long ncols, int k,
+                                   int KP) {
+    const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= ncols * KP) return;
+    const long long c = e / KP;
+    const int i = static_cast<int>(e % KP);
+    dst[e] = (i < k) ? static_cast<float>(src[c * k + i]) : 0.f;
+}
+template <class DstT>
+static __global__ void unpad_convert_kernel(const float* __restrict__ src, DstT* __restrict__ dst, long long ncols, int k,
+                                     int KP) {
+    const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= ncols * k) return;
+    const long long c = e / k;
+    const int i = static_cast<int>(e % k);
+    dst[e] = static_cast<DstT>(src[c * KP + i]);
+}
+static __global__ void f64_to_f32_kernel(const double* __restrict__ src, float* __restrict__ dst, long long n) {
+    const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e < n) dst[e] = static_cast<float>(src[e]);
+}
+
+__device__ __forceinline__ unsigned long long splitmix_mix(unsigned long long z) {
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ unsigned long long splitmix_hash(unsigned long long seed, unsigned i, unsigned j) {
+    return splitmix_mix(seed + static_cast<unsigned long long>(i) * 0x9e3779b97f4a7c15ULL +
+                        static_cast<unsigned long long>(j) * 0x6c62272e07bb0142ULL);          // rng.hpp:129-138
+}
+// uniform<float>() = float(u64) / float(UINT64_MAX) ; float(UINT64_MAX) == 2^64 (rng.hpp:102-104)
+__device__ __forceinline__ float u64_to_unit_float(unsigned long long z) {
+    return __fdiv_rn(__ull2float_rn(z), 18446744073709551616.0f);
+}
+
+// Element e (0-based) of the sequential stream SplitMix64(seed): state after e+1 increments is
+// seed + (e+1)·γ, so the stream is random-access (rng.hpp:89-95). dst is [ncols][KP] padded;
+// stream element of (column c, coordinate i) is first_elem + c·k + i (fill_uniform, rng.hpp:195-201).
+static __global__ void init_uniform_kernel(float* __restrict__ dst, long long ncols, int k, int KP,
+                                    unsigned long long state0, unsigned long long first_elem) {
+    const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= ncols * KP) return;
+    const long long c = e / KP;
+    const int i = static_cast<int>(e % KP);
+    if (i >= k) { dst[e] = 0.f; return; }
+    const unsigned long long idx = first_elem + static_cast<unsigned long long>(c) * k + i;
+    const unsigned long long state = state0 + (idx + 1ULL) * 0x9e3779b97f4a7c15ULL;
+    dst[e] = u64_to_unit_float(splitmix_mix(state));
+}
+
+// tr(AᵀA) partials (primitives/primitives.hpp:101-115) in fp64; reduced on the host.
+static __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x, long long n,
+                                                    double* __restrict__ partials) {
+    __shared__ double s[256];
+    double a = 0.0;
+    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < n;
+         e += static_cast<long long>(gridDim.x) * blockDim.x)
+        a += static_cast<double>(x[e]) * static_cast<double>(x[e]);
+    s[threadIdx.x] = a;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (threadIdx.x < w) s[threadIdx.x] += s[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partials[blockIdx.x] = s[0];
+}
+
+}  // namespace b200

@@ -1,0 +1,495 @@
+// kernels_solve.cuh — the fused half-step kernel: per sparse column, gather b = F·a_j in CSC
+// order, apply L1, warm-start, solve the k×k NNLS (coordinate descent or Cholesky+clip), clip /
+// bound, write x_j, and emit the partial sums the rest of the iteration needs (row norms for
+// the diagonal scaling, <x, b_raw> for the Gram-trick loss). B is never materialised.
+//
+// Replaces (reference): primitives/cpu/fused_nnls.hpp:71-134 (CD) and :156-221 (Cholesky+clip),
+// primitives/cpu/nnls_batch.hpp:71-132 (cd_nnls_col_fixed), features/bounds.hpp:38, the
+// accumulation half of nmf/variant_helpers.hpp:287-305, and fused_nnls.hpp:306-362 (loss cross term).
+//
+// Arithmetic contract: every per-column operation is performed in the SAME order
+// and with the SAME roundings as the CPU path — separate IEEE mul and add (no FMA contraction:
+// the reference package is built without FMA), IEEE division, sequential CSC order per
+// coordinate. A lane group owns the column; a lane owns 4 consecutive coordinates, so no
+// cross-lane reduction ever touches b or x: shuffles only BROADCAST the pivot coordinate.
+#pragma once
+
+#include "common.cuh"
+
+namespace b200 {
+
+enum : int { SOLVER_CD = 0, SOLVER_CHOL = 1 };
+enum : int { BSRC_GATHER = 0, BSRC_LOAD = 1 };
+enum : int { OUT_SOLVE = 0, OUT_RHS = 1 };
+
+struct HalfStepParams {
+    // sparse operand (CSC of A for the H-update, CSC of Aᵀ for the W-update)
+    const int* __restrict__ colptr;
+    const int* __restrict__ rowidx;
+    const float* __restrict__ vals;
+    // dense operands, leading dimension KP (zero padded)
+    const float* __restrict__ F;       // gathered factor [rows][KP]
+    float* __restrict__ X;             // solution        [ncols][KP] (in: warm start, out: x)
+    const float* __restrict__ M1;      // CD: G(+L2) col-major | CHOL: strictly-lower L col-major
+    const float* __restrict__ M2;      // CHOL: LT[p*KP+i] = L(p,i) for i<p, else 0
+    const float* __restrict__ diag;    // CD: diag(G)          | CHOL: diag(L)
+    // BSRC_LOAD / OUT_RHS: dense right-hand sides [nslots][ncols][KP]
+    float* __restrict__ B;
+    int nslots;
+    long long slot_stride;
+    int ncols;
+    int col_offset;                    // first column handled (row-block solves in multi-GPU)
+    int k;
+    float L1;
+    float ub;
+    float cd_tol;
+    float inv_k;
+    int cd_maxit;
+    int nonneg;
+    int warm;
+    int norm_type;                     // 0: sum|x|, 1: sum x², 2: none
+    int want_cross;
+    int cols_per_fetch;
+    int* work_counter;
+    double* norm_partials;             // [gridDim.x][KP]
+    double* cross_partials;            // [gridDim.x]
+    const int* stop_flag;
+    unsigned long long* sweep_counter; // optional: total CD sweeps (diagnostics)
+};
+
+template <int LANES>
+__device__ __forceinline__ float gshfl(unsigned mask, float v, int src) {
+    return __shfl_sync(mask, v, src, LANES);
+}
+template <int LANES>
+__device__ __forceinline__ int gshfl(unsigned mask, int v, int src) {
+    return __shfl_sync(mask, v, src, LANES);
+}
+
+// acc[e] = acc[e] + v*f[e], separately rounded (matches SSE2 Eigen `b += v * col`).
+__device__ __forceinline__ void axpy4(float (&acc)[4], float v, const float4& f) {
+    acc[0] = __fadd_rn(acc[0], __fmul_rn(v, f.x));
+    acc[1] = __fadd_rn(acc[1], __fmul_rn(v, f.y));
+    acc[2] = __fadd_rn(acc[2], __fmul_rn(v, f.z));
+    acc[3] = __fadd_rn(acc[3], __fmul_rn(v, f.w));
+}
+// b[e] = b[e] - g[e]*s
+__device__ __forceinline__ void sub_scaled4(float (&b)[4], const float4& g, float s) {
+    b[0] = __fsub_rn(b[0], __fmul_rn(g.x, s));
+    b[1] = __fsub_rn(b[1], __fmul_rn(g.y, s));
+    b[2] = __fsub_rn(b[2], __fmul_rn(g.z, s));
+    b[3] = __fsub_rn(b[3], __fmul_rn(g.w, s));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Gather: b = Σ_p vals[p] · F[:, rowidx[p]] for p in [p0, p1), CSC order, per-lane coordinates.
+// idx/val are fetched LANES at a time (one coalesced segment per group) and broadcast by shuffle;
+// up to UN independent 128-bit row loads are in flight per lane.
+// ---------------------------------------------------------------------------------------------
+template <int LANES, int NV>
+__device__ __forceinline__ void gather_column(const HalfStepParams& p, int p0, int p1, int gl, unsigned gmask,
+                                              float (&b)[NV][4]) {
+    constexpr int KP = LANES * 4 * NV;
+    constexpr int UN = (LANES < 8) ? LANES : 8;
+#pragma unroll
+    for (int nv = 0; nv < NV; ++nv)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) b[nv][e] = 0.f;
+
+    int nidx = 0;
+    float nval = 0.f;
+    if (p0 + gl < p1) {
+        nidx = __ldg(p.rowidx + p0 + gl);
+        nval = __ldg(p.vals + p0 + gl);
+    }
+    for (int base = p0; base < p1; base += LANES) {
+        const int ridx = nidx;
+        const float rval = nval;
+        const int nb = base + LANES + gl;            // prefetch the next idx/val segment
+        nidx = 0;
+        nval = 0.f;
+        if (nb < p1) {
+            nidx = __ldg(p.rowidx + nb);
+            nval = __ldg(p.vals + nb);
+        }
+        const int cnt = min(LANES, p1 - base);
+#pragma unroll
+        for (int s = 0; s < LANES; s += UN) {
+            if (s < cnt) {
+                float4 f[UN][NV];
+                float v[UN];
+#pragma unroll
+                for (int u = 0; u < UN; ++u) {
+                    const int r = gshfl<LANES>(gmask, ridx, s + u);
+                    v[u] = gshfl<LANES>(gmask, rval, s + u);
+                    if (s + u < cnt) {
+                        const float4* row = reinterpret_cast<const float4*>(p.F + static_cast<size_t>(r) * KP);
+#pragma unroll
+                        for (int nv = 0; nv < NV; ++nv) f[u][nv] = __ldg(row + nv * LANES + gl);
+                    } else {
+#pragma unroll
+                        for (int nv = 0; nv < NV; ++nv) f[u][nv] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < UN; ++u)
+#pragma unroll
+                    for (int nv = 0; nv < NV; ++nv) axpy4(b[nv], v[u], f[u][nv]);   // tail: v = 0, f = 0 -> exact no-op
+            }
+        }
+    }
+}
+
+// b -= G·x restated as tmp = Σ_i G(:,i)·x_i (sequential in i), b -= tmp  (fused_nnls.hpp:121-123).
+template <int LANES, int NV>
+__device__ __forceinline__ void warm_start_correct(const float* sG, int k, int gl, unsigned gmask,
+                                                   const float (&x)[NV][4], float (&b)[NV][4]) {
+    constexpr int KP = LANES * 4 * NV;
+    const float4* sG4 = reinterpret_cast<const float4*>(sG);
+    float tmp[NV][4];
+#pragma unroll
+    for (int nv = 0; nv < NV; ++nv)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) tmp[nv][e] = 0.f;
+#pragma unroll
+    for (int nv = 0; nv < NV; ++nv) {
+#pragma unroll 1
+        for (int owner = 0; owner < LANES; ++owner) {
+            const int i0 = (nv * LANES + owner) * 4;
+            if (i0 >= k) break;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float xi = gshfl<LANES>(gmask, x[nv][e], owner);
+                if (i0 + e < k) {
+#pragma unroll
+                    for (int nv2 = 0; nv2 < NV; ++nv2) {
+                        const float4 g = sG4[(i0 + e) * (KP / 4) + nv2 * LANES + gl];
+                        axpy4(tmp[nv2], xi, g);   // tmp += g*xi (commutative product, same rounding)
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int nv = 0; nv < NV; ++nv)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) b[nv][e] = __fsub_rn(b[nv][e], tmp[nv][e]);
+}
+
+// cd_nnls_col_fixed (nnls_batch.hpp:71-132) with L1 = L2 = upper_bound = 0 as the fused path calls it.
+template <int LANES, int NV>
+__device__ __forceinline__ int cd_solve(const HalfStepParams& p, const float* sG, const float* sDiag, int gl,
+                                        unsigned gmask, float (&x)[NV][4], float (&b)[NV][4]) {
+    constexpr int KP = LANES * 4 * NV;
+    const float4* sG4 = reinterpret_cast<const float4*>(sG);
+    const int k = p.k;
+    const bool nonneg = p.nonneg != 0;
+    const bool check = p.cd_tol > 0.f;
+    int sweeps = p.cd_maxit;
+    for (int it = 0; it < p.cd_maxit; ++it) {
+        float tol_sum = 0.f;
+#pragma unroll
+        for (int nv = 0; nv < NV; ++nv) {
+#pragma unroll 1
+            for (int owner = 0; owner < LANES; ++owner) {
+                const int i0 = (nv * LANES + owner) * 4;
+                if (i0 >= k) break;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int i = i0 + e;
+                    const float bi = gshfl<LANES>(gmask, b[nv][e], owner);
+                    const float xi = gshfl<LANES>(gmask, x[nv][e], owner);
+                    const float gd = sDiag[i];                     // 0 for padded coordinates
+                    float ad = 0.f, xn = xi;
+                    if (gd > 0.f) {                                // :90
+                        const float diff = __fdiv_rn(bi, gd);      // :92
+                        const float nval = __fadd_rn(xi, diff);    // :97
+                        if (nonneg && nval < 0.f) {                // :100-103
+                            ad = -xi;
+                            xn = 0.f;
+                        } else {                                   // :108-112
+                            ad = diff;
+                            xn = (diff == 0.f) ? xi : nval;
+                        }
+                    }
+                    if (ad != 0.f) {                               // `continue` when nothing changes
+                        if (check)                                 // :115-118
+                            tol_sum = __fadd_rn(tol_sum, __fdiv_rn(fabsf(ad), __fadd_rn(fabsf(xn), 1e-15f)));
+                        if (gl == owner) x[nv][e] = xn;
+#pragma unroll
+                        for (int nv2 = 0; nv2 < NV; ++nv2) {       // :121-124 residual update
+                            const float4 g = sG4[i * (KP / 4) + nv2 * LANES + gl];
+                            sub_scaled4(b[nv2], g, ad);
+                        }
+                    }
+                }
+            }
+        }
+        if (check && __fmul_rn(tol_sum, p.inv_k) < p.cd_tol) {     // :127-129
+            sweeps = it + 1;
+            break;
+        }
+    }
+    return sweeps;
+}
+
+// x = L⁻ᵀ L⁻¹ b, column-oriented substitution with IEEE division (Eigen LLT::solve restated,
+// fused_nnls.hpp:210). On exit b holds x.
+template <int LANES, int NV>
+__device__ __forceinline__ void chol_solve(const float* sLs, const float* sLT, const float* sDiag, int k, int gl,
+                                           unsigned gmask, float (&b)[NV][4]) {
+    constexpr int KP = LANES * 4 * NV;
+    const float4* sLs4 = reinterpret_cast<const float4*>(sLs);
+    const float4* sLT4 = reinterpret_cast<const float4*>(sLT);
+    // forward: L y = b
+#pragma unroll
+    for (int nv = 0; nv < NV; ++nv) {
+#pragma unroll 1
+        for (int owner = 0; owner < LANES; ++owner) {
+            const int i0 = (nv * LANES + owner) * 4;
+            if (i0 >= k) break;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int pi = i0 + e;
+                const float bp = gshfl<LANES>(gmask, b[nv][e], owner);
+                if (pi < k) {
+                    const float y = __fdiv_rn(bp, sDiag[pi]);
+                    if (gl == owner) b[nv][e] = y;
+#pragma unroll
+                    for (int nv2 = 0; nv2 < NV; ++nv2) {
+                        if (nv2 >= nv) {                            // rows above the pivot block are zero
+                            const float4 l = sLs4[pi * (KP / 4) + nv2 * LANES + gl];
+                            sub_scaled4(b[nv2], l, y);              // strictly lower: rows <= p untouched
+                        }
+                    }
+                }
+            }
+        }
+    }
+    // backward: Lᵀ x = y
+#pragma unroll
+    for (int nv = NV - 1; nv >= 0; --nv) {
+#pragma unroll 1
+        for (int owner = LANES - 1; owner >= 0; --owner) {
+            const int i0 = (nv * LANES + owner) * 4;
+            if (i0 >= k) continue;
+#pragma unroll
+            for (int e = 3; e >= 0; --e) {
+                const int pi = i0 + e;
+                const float yp = gshfl<LANES>(gmask, b[nv][e], owner);
+                if (pi < k) {
+                    const float xp = __fdiv_rn(yp, sDiag[pi]);
+                    if (gl == owner) b[nv][e] = xp;
+#pragma unroll
+                    for (int nv2 = 0; nv2 < NV; ++nv2) {
+                        if (nv2 <= nv) {
+                            const float4 l = sLT4[pi * (KP / 4) + nv2 * LANES + gl];
+                            sub_scaled4(b[nv2], l, xp);
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The kernel. Persistent CTAs; a warp pulls batches of columns from a global counter; each
+// LANES-wide lane group handles one column at a time.
+//   BSRC_GATHER: b gathered from the CSC operand (single-GPU fused path)
+//   BSRC_LOAD  : b = Σ_slots B[slot][col] in slot order (multi-GPU: partial RHS from every rank)
+//   OUT_SOLVE  : solve and write X;  OUT_RHS: write the raw gathered b to B[0] (partial RHS)
+// ---------------------------------------------------------------------------------------------
+template <int LANES, int NV, int SOLVER, int BSRC, int OUT>
+__global__ void __launch_bounds__(256) half_step_kernel(const HalfStepParams p) {
+    constexpr int KP = LANES * 4 * NV;
+    constexpr int GPW = 32 / LANES;   // groups per warp
+    extern __shared__ __align__(16) float smem[];
+    if (*p.stop_flag) return;
+
+    float* sM1 = smem;
+    float* sM2 = smem + ((OUT == OUT_SOLVE) ? KP * KP : 0);
+    float* sDiag = sM2 + ((OUT == OUT_SOLVE && SOLVER == SOLVER_CHOL) ? KP * KP : 0);
+    double* sRed = reinterpret_cast<double*>(sDiag + KP);    // [256/LANES][KP] norms + [256] cross; 8-byte aligned (KP % 16 == 0)
+
+    if (OUT == OUT_SOLVE) {
+        const float4* g4 = reinterpret_cast<const float4*>(p.M1);
+        float4* s4 = reinterpret_cast<float4*>(sM1);
+        for (int t = threadIdx.x; t < KP * KP / 4; t += blockDim.x) s4[t] = g4[t];
+        if (SOLVER == SOLVER_CHOL) {
+            const float4* l4 = reinterpret_cast<const float4*>(p.M2);
+            float4* t4 = reinterpret_cast<float4*>(sM2);
+            for (int t = threadIdx.x; t < KP * KP / 4; t += blockDim.x) t4[t] = l4[t];
+        }
+        for (int t = threadIdx.x; t < KP; t += blockDim.x) sDiag[t] = p.diag[t];
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const int gl = lane % LANES;
+    const int gw = lane / LANES;
+    const unsigned gmask = (LANES == 32) ? 0xffffffffu : (((1u << LANES) - 1u) << (gw * LANES));
+
+    // Running Σ|x| (or Σx²) over the columns this group solved. fp64: the column→group assignment
+    // is dynamic, so only an (effectively) order-independent accumulator keeps d run-to-run stable.
+    double rs[NV][4];
+#pragma unroll
+    for (int nv = 0; nv < NV; ++nv)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) rs[nv][e] = 0.0;
+    double cross = 0.0;
+    unsigned long long my_sweeps = 0;
+
+    const int fetch = p.cols_per_fetch * GPW;
+    for (;;) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(p.work_counter, fetch);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= p.ncols) break;
+        for (int c = 0; c < p.cols_per_fetch; ++c) {
+            const int jl = base + c * GPW + gw;     // neighbouring groups take neighbouring columns
+            if (jl >= p.ncols) continue;            // whole group skips together
+            const int j = jl + p.col_offset;
+
+            float b[NV][4];
+            if (BSRC == BSRC_GATHER) {
+                const int p0 = __ldg(p.colptr + j);
+                const int p1 = __ldg(p.colptr + j + 1);
+                gather_column<LANES, NV>(p, p0, p1, gl, gmask, b);
+            } else {
+#pragma unroll
+                for (int nv = 0; nv < NV; ++nv) {
+                    const float4 v0 = *reinterpret_cast<const float4*>(p.B + static_cast<size_t>(j) * KP +
+                                                                       (nv * LANES + gl) * 4);
+                    b[nv][0] = v0.x; b[nv][1] = v0.y; b[nv][2] = v0.z; b[nv][3] = v0.w;
+                }
+                for (int s = 1; s < p.nslots; ++s) {   // fixed slot (rank) order -> deterministic sum
+#pragma unroll
+                    for (int nv = 0; nv < NV; ++nv) {
+                        const float4 v = *reinterpret_cast<const float4*>(
+                            p.B + static_cast<size_t>(s) * p.slot_stride + static_cast<size_t>(j) * KP +
+                            (nv * LANES + gl) * 4);
+                        b[nv][0] = __fadd_rn(b[nv][0], v.x); b[nv][1] = __fadd_rn(b[nv][1], v.y);
+                        b[nv][2] = __fadd_rn(b[nv][2], v.z); b[nv][3] = __fadd_rn(b[nv][3], v.w);
+                    }
+                }
+            }
+
+            if (OUT == OUT_RHS) {
+#pragma unroll
+                for (int nv = 0; nv < NV; ++nv)
+                    *reinterpret_cast<float4*>(p.B + static_cast<size_t>(j) * KP + (nv * LANES + gl) * 4) =
+                        make_float4(b[nv][0], b[nv][1], b[nv][2], b[nv][3]);
+                continue;
+            }
+
+            float braw[NV][4];
+            if (p.want_cross) {
+#pragma unroll
+                for (int nv = 0; nv < NV; ++nv)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) braw[nv][e] = b[nv][e];
+            }
+            if (p.L1 > 0.f) {                                       // fused_nnls.hpp:117 / :202
+#pragma unroll
+                for (int nv = 0; nv < NV; ++nv)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if ((nv * LANES + gl) * 4 + e < p.k) b[nv][e] = __fsub_rn(b[nv][e], p.L1);
+            }
+
+            float* xcol = p.X + static_cast<size_t>(j) * KP;
+            float x[NV][4];
+            if (SOLVER == SOLVER_CD) {
+#pragma unroll
+                for (int nv = 0; nv < NV; ++nv) {
+                    const float4 xv = *reinterpret_cast<const float4*>(xcol + (nv * LANES + gl) * 4);
+                    x[nv][0] = xv.x; x[nv][1] = xv.y; x[nv][2] = xv.z; x[nv][3] = xv.w;
+                }
+                if (p.warm) warm_start_correct<LANES, NV>(sM1, p.k, gl, gmask, x, b);
+                my_sweeps += cd_solve<LANES, NV>(p, sM1, sDiag, gl, gmask, x, b);
+            } else {
+                chol_solve<LANES, NV>(sM1, sM2, sDiag, p.k, gl, gmask, b);
+#pragma unroll
+                for (int nv = 0; nv < NV; ++nv)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float v = b[nv][e];
+                        if (p.nonneg && v < 0.f) v = 0.f;           // fused_nnls.hpp:212-214
+                        x[nv][e] = v;
+                    }
+            }
+            if (p.ub > 0.f) {                                       // features/bounds.hpp:38 (post-hoc)
+#pragma unroll
+                for (int nv = 0; nv < NV; ++nv)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) x[nv][e] = fminf(x[nv][e], p.ub);
+            }
+#pragma unroll
+            for (int nv = 0; nv < NV; ++nv)
+                *reinterpret_cast<float4*>(xcol + (nv * LANES + gl) * 4) =
+                    make_float4(x[nv][0], x[nv][1], x[nv][2], x[nv][3]);
+
+            if (p.norm_type == 0) {
+#pragma unroll
+                for (int nv = 0; nv < NV; ++nv)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) rs[nv][e] += static_cast<double>(fabsf(x[nv][e]));
+            } else if (p.norm_type == 1) {
+#pragma unroll
+                for (int nv = 0; nv < NV; ++nv)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        rs[nv][e] += static_cast<double>(x[nv][e]) * static_cast<double>(x[nv][e]);
+            }
+            if (p.want_cross) {                                     // Σ_i x_i · b_raw,i  (x = d∘w_normalised)
+                double s = 0.0;
+#pragma unroll
+                for (int nv = 0; nv < NV; ++nv)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) s += static_cast<double>(x[nv][e]) * static_cast<double>(braw[nv][e]);
+                cross += s;
+            }
+        }
+    }
+
+    if (OUT == OUT_RHS) return;
+
+    // CTA reduction in fp64 through shared memory in a FIXED order, then one partial per CTA
+    // (the finalize kernels sum the per-CTA partials in CTA order).
+    constexpr int NGROUPS = 256 / LANES;
+    const int grp = threadIdx.x / LANES;
+    if (p.norm_type != 2) {
+#pragma unroll
+        for (int nv = 0; nv < NV; ++nv)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) sRed[grp * KP + (nv * LANES + gl) * 4 + e] = rs[nv][e];
+    }
+    double* sCross = sRed + NGROUPS * KP;
+    sCross[threadIdx.x] = cross;
+    if (p.sweep_counter && gl == 0 && my_sweeps) atomicAdd(p.sweep_counter, my_sweeps);
+    __syncthreads();
+    if (p.norm_type != 2) {
+        for (int t = threadIdx.x; t < KP; t += blockDim.x) {
+            double s = 0.0;
+            for (int g = 0; g < NGROUPS; ++g) s += sRed[g * KP + t];
+            p.norm_partials[static_cast<size_t>(blockIdx.x) * KP + t] = s;
+        }
+    }
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        if (p.want_cross)
+            for (int t = 0; t < 256; ++t) s += sCross[t];
+        p.cross_partials[blockIdx.x] = s;
+    }
+}
+
+template <int LANES, int NV, int SOLVER, int OUT>
+inline size_t half_step_smem_bytes() {
+    constexpr int KP = LANES * 4 * NV;
+    size_t f = KP;                                           // diag
+    if (OUT == OUT_SOLVE) f += static_cast<size_t>(KP) * KP * (SOLVER == SOLVER_CHOL ? 2 : 1);
+    return f * sizeof(float) + (static_cast<size_t>(256 / LANES) * KP + 256) * sizeof(double);
+}
+
+}  // namespace b200

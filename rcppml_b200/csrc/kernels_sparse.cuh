@@ -1,0 +1,117 @@
+// kernels_sparse.cuh — one-time sparse set-up on the device:
+//   * CSC(Aᵀ) with ascending inner indices (Eigen's A.transpose(), nmf/fit_cpu.hpp:251-253) by a
+//     STABLE radix sort of (row key, position) pairs — stability keeps columns ascending per row
+//   * the O(nnz) synthetic matrix generator of SURVEY.md §8d
+// CUB (CUDA toolkit header library) provides the radix sort / scans; this is set-up, not the hot loop.
+#pragma once
+
+#include "common.cuh"
+#include "kernels_dense.cuh"   // splitmix helpers
+
+#include <cub/cub.cuh>
+
+namespace b200 {
+
+// col_of[p] = j such that colptr[j] <= p < colptr[j+1]
+static __global__ void expand_columns_kernel(const int* __restrict__ colptr, int n, long long nnz, int* __restrict__ col_of) {
+    const long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (p >= nnz) return;
+    int lo = 0, hi = n;                 // invariant: colptr[lo] <= p < colptr[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(colptr + mid) <= p) lo = mid; else hi = mid;
+    }
+    col_of[p] = lo;
+}
+
+static __global__ void iota_kernel(unsigned* __restrict__ x, long long n) {
+    const long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (p < n) x[p] = static_cast<unsigned>(p);
+}
+
+// Ti[q] = col_of[perm[q]], Tx[q] = vals[perm[q]]
+static __global__ void permute_gather_kernel(const unsigned* __restrict__ perm, const int* __restrict__ col_of,
+                                      const float* __restrict__ vals, long long nnz, int* __restrict__ Ti,
+                                      float* __restrict__ Tx) {
+    const long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (q >= nnz) return;
+    const unsigned p = perm[q];
+    Ti[q] = col_of[p];
+    Tx[q] = vals[p];
+}
+
+// Tp[r] = first position q with sorted_rows[q] >= r  (r = 0..m)
+static __global__ void row_pointers_kernel(const int* __restrict__ sorted_rows, long long nnz, int m, int* __restrict__ Tp) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > m) return;
+    long long lo = 0, hi = nnz;         // first index with key >= r
+    while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        if (sorted_rows[mid] < r) lo = mid + 1; else hi = mid;
+    }
+    Tp[r] = static_cast<int>(lo);
+}
+
+// --------------------------------------------------------------------------------------------
+// Synthetic generator. One CTA per column; candidates are sorted in shared memory (bitonic),
+// de-duplicated, counted (pass 0) or written (pass 1).
+// --------------------------------------------------------------------------------------------
+template <int NMAX>   // power of two >= candidates per column
+static __global__ void __launch_bounds__(256) synth_column_kernel(int m, int n_local, int col_begin, int cnt,
+                                                           unsigned long long seed, int pass,
+                                                           int* __restrict__ counts,
+                                                           const int* __restrict__ colptr,
+                                                           int* __restrict__ rowidx, float* __restrict__ vals) {
+    __shared__ unsigned sk[NMAX];
+    __shared__ int sbase[257];
+    const int jl = blockIdx.x;
+    if (jl >= n_local) return;
+    const unsigned j = static_cast<unsigned>(col_begin + jl);
+    for (int t = threadIdx.x; t < NMAX; t += 256)
+        sk[t] = (t < cnt) ? static_cast<unsigned>(splitmix_hash(seed, static_cast<unsigned>(t), j) %
+                                                  static_cast<unsigned long long>(m))
+                          : 0xFFFFFFFFu;
+    __syncthreads();
+    for (int size = 2; size <= NMAX; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = threadIdx.x; t < NMAX / 2; t += 256) {
+                const int lo = 2 * t - (t & (stride - 1));      // index with the `stride` bit clear
+                const int hi = lo + stride;
+                const bool up = ((lo & size) == 0);
+                const unsigned a = sk[lo], b = sk[hi];
+                if ((a > b) == up) { sk[lo] = b; sk[hi] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    // unique count per contiguous chunk
+    constexpr int CH = NMAX / 256 > 0 ? NMAX / 256 : 1;
+    const int c0 = threadIdx.x * CH;
+    int uniq = 0;
+    for (int t = c0; t < c0 + CH && t < NMAX; ++t) {
+        const unsigned v = sk[t];
+        if (v != 0xFFFFFFFFu && (t == 0 || sk[t - 1] != v)) ++uniq;
+    }
+    sbase[threadIdx.x + 1] = uniq;
+    if (threadIdx.x == 0) sbase[0] = 0;
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (int t = 1; t <= 256; ++t) sbase[t] += sbase[t - 1];
+    __syncthreads();
+    if (pass == 0) {
+        if (threadIdx.x == 0) counts[jl] = sbase[256];
+        return;
+    }
+    const int out0 = colptr[jl];
+    int w = out0 + sbase[threadIdx.x];
+    for (int t = c0; t < c0 + CH && t < NMAX; ++t) {
+        const unsigned v = sk[t];
+        if (v != 0xFFFFFFFFu && (t == 0 || sk[t - 1] != v)) {
+            rowidx[w] = static_cast<int>(v);
+            vals[w] = __fadd_rn(0.5f, u64_to_unit_float(splitmix_hash(seed + 1ULL, v, j)));
+            ++w;
+        }
+    }
+}
+
+}  // namespace b200

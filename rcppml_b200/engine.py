@@ -1,0 +1,174 @@
+"""Device-resident engine wrapper (ABI extension rcppml_b200_*, include/rcppml_gpu.h part 2).
+
+Dense factors cross this boundary as C-contiguous float32 arrays of shape (cols, k): row c is
+column c of the reference's k × cols column-major matrix (W_T: k × m, H: k × n).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from ._lib import Config, Result
+
+
+def _p(a, ty):
+    return a.ctypes.data_as(C.POINTER(ty)) if a is not None else None
+
+
+def make_config(k, *, max_iter=100, tol=1e-4, L1=(0.0, 0.0), L2=(0.0, 0.0), upper_bound=(0.0, 0.0),
+                nonneg=(True, True), cd_maxit=100, cd_tol=1e-8, norm_type=0, solver_mode=0, patience=5,
+                verbose=False) -> Config:
+    """Pairs are (W, H) as at the R boundary (src/RcppFunctions_nmf.cpp:59-72)."""
+    return Config(k=k, max_iter=max_iter, tol=tol, L1_W=L1[0], L1_H=L1[1], L2_W=L2[0], L2_H=L2[1],
+                  ub_W=upper_bound[0], ub_H=upper_bound[1], nonneg_W=int(nonneg[0]), nonneg_H=int(nonneg[1]),
+                  cd_maxit=cd_maxit, cd_tol=cd_tol, norm_type=norm_type, solver_mode=solver_mode,
+                  patience=patience, verbose=int(verbose))
+
+
+@dataclass
+class FitResult:
+    iterations: int
+    converged: bool
+    train_loss: float
+    final_tol: float
+    status: int
+    gpu_launches: int
+    loop_ms: float
+
+
+class Engine:
+    def __init__(self, device: int = 0):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        _lib.check(self._lib.rcppml_b200_engine_create(C.byref(self._h), device), "engine_create")
+        self.m = self.n = self.k = 0
+        self.nnz = 0
+
+    def close(self):
+        if self._h:
+            self._lib.rcppml_b200_engine_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- matrix
+    def set_matrix(self, m, n, indptr, indices, data):
+        indptr = np.ascontiguousarray(indptr, dtype=np.int32)
+        indices = np.ascontiguousarray(indices, dtype=np.int32)
+        nnz = int(indptr[n])
+        if data.dtype == np.float64:
+            data = np.ascontiguousarray(data)
+            rc = self._lib.rcppml_b200_set_matrix_f64(self._h, m, n, nnz, _p(indptr, C.c_int), _p(indices, C.c_int),
+                                                      _p(data, C.c_double))
+        else:
+            data = np.ascontiguousarray(data, dtype=np.float32)
+            rc = self._lib.rcppml_b200_set_matrix_f32(self._h, m, n, nnz, _p(indptr, C.c_int), _p(indices, C.c_int),
+                                                      _p(data, C.c_float))
+        _lib.check(rc, "set_matrix")
+        self.m, self.n, self.nnz = m, n, nnz
+
+    def set_matrix_synthetic(self, m, n_local, col_begin, density, seed):
+        _lib.check(self._lib.rcppml_b200_set_matrix_synthetic(self._h, m, n_local, col_begin, density, seed),
+                   "set_matrix_synthetic")
+        nnz = C.c_int64(0)
+        _lib.check(self._lib.rcppml_b200_get_matrix(self._h, C.byref(nnz), None, None, None), "get_matrix")
+        self.m, self.n, self.nnz = m, n_local, nnz.value
+
+    def get_matrix(self):
+        p = np.empty(self.n + 1, np.int32)
+        i = np.empty(self.nnz, np.int32)
+        x = np.empty(self.nnz, np.float32)
+        nnz = C.c_int64(0)
+        _lib.check(self._lib.rcppml_b200_get_matrix(self._h, C.byref(nnz), _p(p, C.c_int), _p(i, C.c_int),
+                                                    _p(x, C.c_float)), "get_matrix")
+        return p, i, x
+
+    def get_matrix_t(self):
+        p = np.empty(self.m + 1, np.int32)
+        i = np.empty(self.nnz, np.int32)
+        x = np.empty(self.nnz, np.float32)
+        _lib.check(self._lib.rcppml_b200_get_matrix_t(self._h, _p(p, C.c_int), _p(i, C.c_int), _p(x, C.c_float)),
+                   "get_matrix_t")
+        return p, i, x
+
+    # ---- factors
+    def set_factors(self, W_T, H):
+        W_T = np.ascontiguousarray(W_T, dtype=np.float32)
+        H = np.ascontiguousarray(H, dtype=np.float32)
+        assert W_T.shape[0] == self.m and H.shape[0] == self.n and W_T.shape[1] == H.shape[1]
+        self.k = W_T.shape[1]
+        _lib.check(self._lib.rcppml_b200_set_factors_f32(self._h, self.k, _p(W_T, C.c_float), _p(H, C.c_float)),
+                   "set_factors")
+
+    def init_factors(self, k, seed, h_col_begin=0):
+        _lib.check(self._lib.rcppml_b200_init_factors(self._h, k, seed, h_col_begin), "init_factors")
+        self.k = k
+
+    def get_factors(self):
+        W_T = np.empty((self.m, self.k), np.float32)
+        H = np.empty((self.n, self.k), np.float32)
+        d = np.empty(self.k, np.float32)
+        _lib.check(self._lib.rcppml_b200_get_factors_f32(self._h, _p(W_T, C.c_float), _p(H, C.c_float),
+                                                         _p(d, C.c_float)), "get_factors")
+        return W_T, H, d
+
+    # ---- fit
+    def begin_fit(self, cfg: Config):
+        _lib.check(self._lib.rcppml_b200_begin_fit(self._h, C.byref(cfg)), "begin_fit")
+
+    def iterate(self, n_iters: int):
+        _lib.check(self._lib.rcppml_b200_iterate(self._h, n_iters), "iterate")
+
+    def fit(self, cfg: Config) -> FitResult:
+        _lib.check(self._lib.rcppml_b200_fit(self._h, C.byref(cfg)), "fit")
+        return self.result()
+
+    def half_step(self, cfg: Config, which: int, warm_start: bool, normalize_after: bool = False):
+        _lib.check(self._lib.rcppml_b200_half_step(self._h, C.byref(cfg), which, int(warm_start),
+                                                   int(normalize_after)), "half_step")
+
+    def result(self) -> FitResult:
+        r = Result()
+        _lib.check(self._lib.rcppml_b200_get_result(self._h, C.byref(r)), "get_result")
+        return FitResult(r.iterations, bool(r.converged), r.train_loss, r.final_tol, r.status, r.gpu_launches,
+                         r.loop_ms)
+
+    def loss_history(self, count: int) -> np.ndarray:
+        out = np.zeros(max(count, 1), np.float32)
+        _lib.check(self._lib.rcppml_b200_get_loss_history(self._h, _p(out, C.c_float), count), "loss_history")
+        return out[:count]
+
+    def cd_sweeps(self) -> int:
+        return int(self._lib.rcppml_b200_cd_sweeps(self._h))
+
+    def set_profiling(self, on: bool):
+        _lib.check(self._lib.rcppml_b200_set_profiling(self._h, int(on)), "set_profiling")
+
+    def profile(self):
+        ms = (C.c_double * _lib.NUM_SECTIONS)()
+        ln = (C.c_int * _lib.NUM_SECTIONS)()
+        _lib.check(self._lib.rcppml_b200_get_profile(self._h, ms, ln), "get_profile")
+        return ({name: ms[i] for i, name in enumerate(_lib.SECTION_NAMES)},
+                {name: ln[i] for i, name in enumerate(_lib.SECTION_NAMES)})
+
+    def counters(self):
+        a, b = C.c_int64(0), C.c_int64(0)
+        _lib.check(self._lib.rcppml_b200_get_counters(self._h, C.byref(a), C.byref(b)), "get_counters")
+        return a.value, b.value
+
+    # ---- multi-GPU
+    def comm_init(self, rank: int, world: int, unique_id: bytes):
+        _lib.check(self._lib.rcppml_b200_comm_init(self._h, rank, world, unique_id), "comm_init")
+
+
+def nccl_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    _lib.check(_lib.load().rcppml_b200_nccl_unique_id(buf), "nccl_unique_id")
+    return buf.raw

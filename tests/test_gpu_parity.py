@@ -1,0 +1,177 @@
+"""GPU parity tests: the CUDA engine (through the C ABI of RcppML_gpu.so) against the CPU oracle
+on the same seeded inputs. Bit-exact for integer work (generator, transpose, RNG); 1e-5 relative
+for fp32 factors (tests/helpers.py:RTOL), identical zero patterns (active sets)."""
+import numpy as np
+import pytest
+
+from helpers import RTOL, random_csc, rel_err, zero_pattern_equal
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import rcppml_b200 as rb
+    e = rb.Engine(0)
+    yield e
+    e.close()
+
+
+def test_detect_reports_b200():
+    import rcppml_b200 as rb
+    info = rb.gpu_detect()
+    assert info["status"] == 0 and info["num_gpus"] >= 1
+    assert info["total_mem_mb"][0] > 100_000
+
+
+def test_synthetic_generator_bit_exact(eng):
+    from rcppml_b200 import synth
+    for (m, n_local, col_begin, dens) in [(5000, 300, 0, 0.01), (20000, 128, 77, 0.05), (100000, 64, 5, 0.03)]:
+        eng.set_matrix_synthetic(m, n_local, col_begin, dens, synth.SEED_A)
+        p, i, x = eng.get_matrix()
+        hp, hi, hx = synth.synth_csc(m, n_local, col_begin, dens, synth.SEED_A)
+        assert np.array_equal(p, hp) and np.array_equal(i, hi) and np.array_equal(x, hx)
+
+
+def test_transpose_bit_exact(eng, oracle):
+    A = random_csc(700, 400, 0.05, 3, ragged=True)
+    eng.set_matrix(700, 400, A.indptr, A.indices, A.data)
+    tp, ti, tx = eng.get_matrix_t()
+    op, oi, ox = oracle.transpose_csc(A.indptr, A.indices, A.data, 700, 400)
+    assert np.array_equal(tp, op) and np.array_equal(ti, oi) and np.array_equal(tx, ox)
+
+
+def test_init_factors_bit_exact(eng, oracle):
+    A = random_csc(300, 200, 0.05, 4)
+    eng.set_matrix(300, 200, A.indptr, A.indices, A.data)
+    for k, seed in [(7, 42), (64, 0), (20, 123456)]:
+        eng.init_factors(k, seed)
+        W, H, _ = eng.get_factors()
+        oW, oH = oracle.initialize_factors(k, 300, 200, seed)
+        assert np.array_equal(W, oW) and np.array_equal(H, oH)
+
+
+@pytest.mark.parametrize("k", [6, 20, 32, 64, 128])
+@pytest.mark.parametrize("solver", [0, 1])
+def test_half_steps_match_oracle(eng, oracle, k, solver):
+    import rcppml_b200 as rb
+    m, n = 900, 500
+    A = random_csc(m, n, 0.04, 10 + k, ragged=True)
+    At = oracle.transpose_csc(A.indptr, A.indices, A.data, m, n)
+    W0, H0 = oracle.initialize_factors(k, m, n, 42)
+    L1 = (0.01, 0.02)
+    L2 = (0.03, 0.0)
+    cfg = rb.make_config(k, L1=L1, L2=L2, solver_mode=solver, cd_maxit=100)
+    eng.set_matrix(m, n, A.indptr, A.indices, A.data)
+    for warm in (False, True):
+        # ---- H update
+        eng.set_factors(W0, H0)
+        eng.half_step(cfg, 0, warm)
+        _, H_gpu, d_gpu = eng.get_factors()
+        G = oracle.gram(W0)
+        G[np.diag_indices(k)] += np.float32(L2[1])
+        H_ref = H0.copy()
+        oracle.half_step(A.indptr, A.indices, A.data, W0, G, H_ref, solver_mode=solver, L1=L1[1], warm_start=warm)
+        assert rel_err(H_gpu, H_ref) <= RTOL, (k, solver, warm, rel_err(H_gpu, H_ref))
+        assert zero_pattern_equal(H_gpu, H_ref)
+        d_ref = np.abs(H_ref.astype(np.float64)).sum(axis=0).astype(np.float32) + np.float32(1e-15)
+        assert rel_err(d_gpu, d_ref) <= RTOL
+        # ---- W update
+        eng.set_factors(W0, H0)
+        eng.half_step(cfg, 1, warm)
+        W_gpu, _, _ = eng.get_factors()
+        G = oracle.gram(H0)
+        G[np.diag_indices(k)] += np.float32(L2[0])
+        W_ref = W0.copy()
+        oracle.half_step(At[0], At[1], At[2], H0, G, W_ref, solver_mode=solver, L1=L1[0], warm_start=warm)
+        assert rel_err(W_gpu, W_ref) <= RTOL, (k, solver, warm, rel_err(W_gpu, W_ref))
+        assert zero_pattern_equal(W_gpu, W_ref)
+
+
+CASES = [
+    # name, m, n, density, k, kwargs
+    ("cd_k8", 500, 200, 0.08, 8, dict(solver_mode=0)),
+    ("chol_k8", 500, 200, 0.08, 8, dict(solver_mode=1)),
+    ("cd_k20_L1", 800, 610, 0.05, 20, dict(solver_mode=0, L1=(0.01, 0.01))),
+    ("cd_k32", 1200, 700, 0.03, 32, dict(solver_mode=0)),
+    ("chol_k64", 2000, 900, 0.03, 64, dict(solver_mode=1)),
+    ("cd_k64_L1L2", 1500, 800, 0.03, 64, dict(solver_mode=0, L1=(0.01, 0.01), L2=(0.01, 0.01))),
+    ("chol_k128_L1L2", 1500, 1100, 0.04, 128, dict(solver_mode=1, L1=(0.01, 0.01), L2=(0.01, 0.01))),
+    ("chol_k32_ub_l2norm", 600, 400, 0.06, 32, dict(solver_mode=1, upper_bound=(0.02, 0.05), norm_type=1)),
+    ("cd_k16_nonorm_seminmf", 600, 400, 0.06, 16, dict(solver_mode=0, norm_type=2, nonneg=(True, False))),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_full_fit_matches_oracle(eng, oracle, case):
+    import rcppml_b200 as rb
+    name, m, n, dens, k, kw = case
+    iters = 8
+    A = random_csc(m, n, dens, 7, counts=("k20" in name), ragged=True)
+    W0, H0 = oracle.initialize_factors(k, m, n, 42)
+    ref = oracle.nmf_fit(A.indptr, A.indices, A.data, m, n, k, W0, H0, max_iter=iters, tol=0.0, threads=0, **kw)
+    eng.set_matrix(m, n, A.indptr, A.indices, A.data)
+    eng.set_factors(W0, H0)
+    res = eng.fit(rb.make_config(k, max_iter=iters, tol=0.0, **kw))
+    W, H, d = eng.get_factors()
+    assert res.status == 0 and res.iterations == iters == ref.iterations
+    errs = dict(W=rel_err(W, ref.W_T), H=rel_err(H, ref.H), d=rel_err(d, ref.d),
+                loss=rel_err(eng.loss_history(iters), ref.loss_history))
+    print(name, errs, "sweeps gpu/oracle", eng.cd_sweeps(), ref.cd_sweeps)
+    assert errs["W"] <= RTOL and errs["H"] <= RTOL and errs["d"] <= RTOL, errs
+    assert errs["loss"] <= 1e-5, errs
+    assert zero_pattern_equal(W, ref.W_T) and zero_pattern_equal(H, ref.H)
+    if kw.get("solver_mode", 0) == 0:
+        assert eng.cd_sweeps() == ref.cd_sweeps
+
+
+def test_convergence_and_patience(eng, oracle):
+    import rcppml_b200 as rb
+    m, n, k = 400, 300, 6
+    A = random_csc(m, n, 0.1, 11)
+    W0, H0 = oracle.initialize_factors(k, m, n, 1)
+    ref = oracle.nmf_fit(A.indptr, A.indices, A.data, m, n, k, W0, H0, max_iter=200, tol=1e-4, solver_mode=1)
+    eng.set_matrix(m, n, A.indptr, A.indices, A.data)
+    eng.set_factors(W0, H0)
+    res = eng.fit(rb.make_config(k, max_iter=200, tol=1e-4, solver_mode=1))
+    assert ref.converged and res.converged
+    assert res.iterations == ref.iterations
+    assert abs(res.train_loss - ref.train_loss) <= 1e-5 * abs(ref.train_loss)
+
+
+def test_reference_abi_unified_float(oracle):
+    """Through the 73-pointer reference entry point, packed like bridge_nmf.hpp:199-342."""
+    import rcppml_b200 as rb
+    m, n, k = 700, 450, 20
+    A = random_csc(m, n, 0.05, 21, counts=True)
+    W0, H0 = oracle.initialize_factors(k, m, n, 42)
+    kw = dict(L1=(0.01, 0.01), solver_mode=0)
+    ref = oracle.nmf_fit(A.indptr, A.indices, A.data, m, n, k, W0, H0, max_iter=6, tol=0.0, **kw)
+    out = rb.bridge_nmf_sparse(A.indptr, A.indices, A.data, m, n, k, W0, H0, max_iter=6, tol=0.0, **kw)
+    assert out.status == 0 and out.iterations == 6
+    assert rel_err(out.W_T, ref.W_T) <= RTOL and rel_err(out.H, ref.H) <= RTOL and rel_err(out.d, ref.d) <= RTOL
+    assert abs(out.train_loss - ref.train_loss) <= 1e-5 * abs(ref.train_loss)
+    # unsupported feature -> status -1, buffers untouched (the reference gateway then takes its CPU path)
+    bad = rb.bridge_nmf_sparse(A.indptr, A.indices, A.data, m, n, k, W0, H0, max_iter=2, L21=(0.1, 0.0))
+    assert bad.status == -1 and np.array_equal(bad.W_T, W0)
+
+
+def test_large_synthetic_properties(eng):
+    """Full-width rows at reduced column count: size-independent properties (non-negativity,
+    unit L1 row norms, monotone loss, determinism run to run)."""
+    import rcppml_b200 as rb
+    from rcppml_b200 import synth
+    m, n, k = 200_000, 20_000, 64
+    eng.set_matrix_synthetic(m, n, 0, 1e-3, synth.SEED_A)
+    outs = []
+    for _ in range(2):
+        eng.init_factors(k, 42)
+        res = eng.fit(rb.make_config(k, max_iter=5, tol=0.0, solver_mode=1))
+        W, H, d = eng.get_factors()
+        hist = eng.loss_history(5)
+        outs.append((W, H, d, hist))
+        assert res.status == 0 and W.min() >= 0 and H.min() >= 0
+        assert np.allclose(W.sum(axis=0, dtype=np.float64), 1.0, atol=1e-4)
+        assert np.all(np.diff(hist) <= 1e-6 * hist[0])
+    for a, b in zip(outs[0], outs[1]):
+        assert np.array_equal(a, b)
