@@ -485,6 +485,7 @@ typedef struct {
     int threads;
     int sort_model;
     int has_mask;
+    double time_budget_s;   // > 0: stop after the first iteration that ends past the budget (bench only)
 } orc_config;
 
 typedef struct {
@@ -495,6 +496,7 @@ typedef struct {
     int chol_info;          // first non-positive Cholesky pivot seen (0 = none)
     double loop_seconds;    // wall time of the iteration loop only
     long cd_sweeps;         // total CD sweeps over all columns (solver_mode 0)
+    double* iter_seconds;   // optional [max_iter]: wall time at the end of each iteration (since loop start)
 } orc_result;
 
 void orc_splitmix_next(uint64_t seed, int count, uint64_t* out) {
@@ -733,6 +735,11 @@ int orc_nmf_fit_f32(const int* Ap, const int* Ai, const float* Ax, long m, long 
             } else patience_counter = 0;
         }
         res->iterations = iter + 1;                                          // :1811
+        if (res->iter_seconds || cfg->time_budget_s > 0) {
+            const double el = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
+            if (res->iter_seconds) res->iter_seconds[iter] = el;
+            if (cfg->time_budget_s > 0 && el > cfg->time_budget_s) break;
+        }
     }
     res->loop_seconds = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
     if (res->train_loss == 0.f) res->train_loss = prev_loss;                 // :1842-1845
@@ -750,6 +757,46 @@ int orc_nmf_fit_f32(const int* Ap, const int* Ai, const float* Ax, long m, long 
         std::copy(dd.begin(), dd.end(), d);
     }
     return 0;
+}
+
+// SURVEY.md §8d synthetic generator (host twin of csrc/kernels_sparse.cuh synth_column_kernel;
+// rcppml_b200/synth.py is the numpy twin). Two passes: counts, then fill. Rows >= m_keep are
+// dropped (m_keep = m keeps everything): the leading m_keep × n_local block is the CPU sample.
+long orc_synth_csc(long m, long n_local, long col_begin, double density, uint64_t seed, long m_keep, int pass,
+                   int* Ap, int* Ai, float* Ax, int threads) {
+    const long cnt = std::llround(static_cast<double>(m) * density);
+    if (pass == 0) Ap[0] = 0;
+#pragma omp parallel num_threads(std::max(1, threads))
+    {
+        std::vector<uint32_t> rows(cnt);
+#pragma omp for schedule(static)
+        for (long jl = 0; jl < n_local; ++jl) {
+            const uint32_t j = static_cast<uint32_t>(col_begin + jl);
+            for (long t = 0; t < cnt; ++t)
+                rows[t] = static_cast<uint32_t>(orc::SplitMix64::hash(seed, static_cast<uint32_t>(t), j) %
+                                                static_cast<uint64_t>(m));
+            std::sort(rows.begin(), rows.end());
+            const long u = std::unique(rows.begin(), rows.end()) - rows.begin();
+            long kept = 0;
+            while (kept < u && static_cast<long>(rows[kept]) < m_keep) ++kept;
+            if (pass == 0) {
+                Ap[jl + 1] = static_cast<int>(kept);
+            } else {
+                long w = Ap[jl];
+                for (long t = 0; t < kept; ++t, ++w) {
+                    Ai[w] = static_cast<int>(rows[t]);
+                    const uint64_t h = orc::SplitMix64::hash(seed + 1, rows[t], j);
+                    Ax[w] = 0.5f + static_cast<float>(h) / static_cast<float>(UINT64_MAX);
+                }
+            }
+        }
+    }
+    if (pass == 0) {
+        long total = 0;
+        for (long jl = 0; jl < n_local; ++jl) { const long c = Ap[jl + 1]; Ap[jl + 1] = static_cast<int>(total += c); }
+        return total;
+    }
+    return Ap[n_local];
 }
 
 int orc_max_threads(void) {

@@ -32,7 +32,7 @@ class _Cfg(C.Structure):
         ("nonneg_W", C.c_int), ("nonneg_H", C.c_int),
         ("cd_maxit", C.c_int), ("cd_tol", C.c_float),
         ("norm_type", C.c_int), ("solver_mode", C.c_int), ("patience", C.c_int),
-        ("threads", C.c_int), ("sort_model", C.c_int), ("has_mask", C.c_int),
+        ("threads", C.c_int), ("sort_model", C.c_int), ("has_mask", C.c_int), ("time_budget_s", C.c_double),
     ]
 
 
@@ -40,6 +40,7 @@ class _Res(C.Structure):
     _fields_ = [
         ("iterations", C.c_int), ("converged", C.c_int), ("train_loss", C.c_float), ("final_tol", C.c_float),
         ("chol_info", C.c_int), ("loop_seconds", C.c_double), ("cd_sweeps", C.c_long),
+        ("iter_seconds", C.POINTER(C.c_double)),
     ]
 
 
@@ -56,6 +57,7 @@ def lib():
         _lib.orc_is_holdout.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64]
         _lib.orc_trace_AtA_f32.restype = C.c_float
         _lib.orc_loss_cross_term_f32.restype = C.c_float
+        _lib.orc_synth_csc.restype = C.c_long
     return _lib
 
 
@@ -233,6 +235,20 @@ def loss_cross_term(Atp, Ati, Atx, W_T, H, d, threads=1):
                                                 _p(d, C.c_float), k, threads))
 
 
+def synth_csc(m, n_local, col_begin=0, density=1e-3, seed=20260101, m_keep=None, threads=0):
+    """SURVEY.md §8d generator on the host (OpenMP). Returns (indptr, indices, data)."""
+    m_keep = m if m_keep is None else m_keep
+    threads = threads or max_threads()
+    Ap = np.zeros(n_local + 1, dtype=np.int32)
+    nnz = lib().orc_synth_csc(C.c_long(m), C.c_long(n_local), C.c_long(col_begin), C.c_double(density),
+                              C.c_uint64(seed), C.c_long(m_keep), 0, _p(Ap, C.c_int), None, None, threads)
+    Ai = np.empty(nnz, dtype=np.int32)
+    Ax = np.empty(nnz, dtype=np.float32)
+    lib().orc_synth_csc(C.c_long(m), C.c_long(n_local), C.c_long(col_begin), C.c_double(density), C.c_uint64(seed),
+                        C.c_long(m_keep), 1, _p(Ap, C.c_int), _p(Ai, C.c_int), _p(Ax, C.c_float), threads)
+    return Ap, Ai, Ax
+
+
 def max_threads() -> int:
     return int(lib().orc_max_threads())
 
@@ -251,11 +267,12 @@ class OracleResult:
     loop_seconds: float
     cd_sweeps: int
     loss_history: np.ndarray = field(default_factory=lambda: np.zeros(0, np.float32))
+    iter_seconds: np.ndarray = field(default_factory=lambda: np.zeros(0, np.float64))
 
 
 def nmf_fit(Ap, Ai, Ax, m, n, k, W_T0, H0, *, max_iter=100, tol=1e-4, L1=(0.0, 0.0), L2=(0.0, 0.0),
             upper_bound=(0.0, 0.0), nonneg=(True, True), cd_maxit=100, cd_tol=1e-8, norm_type=0, solver_mode=0,
-            patience=5, threads=0, sort_model=False, mask=None) -> OracleResult:
+            patience=5, threads=0, sort_model=False, mask=None, time_budget_s=0.0) -> OracleResult:
     """nmf_fit<CPU,float,Sparse> (nmf/fit_cpu.hpp:172). Pairs are (W, H) as at the R boundary
     (src/RcppFunctions_nmf.cpp:59-72). mask = (Mp, Mi) CSC pattern of masked entries or None."""
     Ap, Ai, Ax = _i32(Ap), _i32(Ai), _f32(Ax)
@@ -266,16 +283,20 @@ def nmf_fit(Ap, Ai, Ax, m, n, k, W_T0, H0, *, max_iter=100, tol=1e-4, L1=(0.0, 0
     cfg = _Cfg(k=k, max_iter=max_iter, tol=tol, L1_W=L1[0], L1_H=L1[1], L2_W=L2[0], L2_H=L2[1],
                ub_W=upper_bound[0], ub_H=upper_bound[1], nonneg_W=int(nonneg[0]), nonneg_H=int(nonneg[1]),
                cd_maxit=cd_maxit, cd_tol=cd_tol, norm_type=norm_type, solver_mode=solver_mode, patience=patience,
-               threads=threads, sort_model=int(sort_model), has_mask=int(mask is not None))
+               threads=threads, sort_model=int(sort_model), has_mask=int(mask is not None),
+               time_budget_s=time_budget_s)
     Mp = Mi = None
     if mask is not None:
         Mp, Mi = _i32(mask[0]), _i32(mask[1])
     hist = np.zeros(max_iter, dtype=np.float32)
     res = _Res()
+    it_s = np.zeros(max_iter, dtype=np.float64)
+    res.iter_seconds = _p(it_s, C.c_double)
     rc = lib().orc_nmf_fit_f32(_p(Ap, C.c_int), _p(Ai, C.c_int), _p(Ax, C.c_float), C.c_long(m), C.c_long(n),
                                C.byref(cfg), _p(W_T, C.c_float), _p(H, C.c_float), _p(d, C.c_float),
                                _p(Mp, C.c_int), _p(Mi, C.c_int), _p(hist, C.c_float), C.byref(res))
     if rc != 0:
         raise ValueError("oracle: invalid configuration (core/config.hpp:421-432)")
     return OracleResult(W_T, H, d, res.iterations, bool(res.converged), res.train_loss, res.final_tol,
-                        res.chol_info, res.loop_seconds, res.cd_sweeps, hist[:res.iterations].copy())
+                        res.chol_info, res.loop_seconds, res.cd_sweeps, hist[:res.iterations].copy(),
+                        it_s[:res.iterations].copy())

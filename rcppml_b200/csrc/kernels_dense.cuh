@@ -28,8 +28,7 @@ struct DevState {
 // ---------------------------------------------------------------------------------------------
 // normalize + Gram. X is [ncols][KP] (row c = column c of the reference's k×ncols matrix).
 // 256 threads as a 16×16 grid, each owning an R×R tile of G (R = KP/16). Column tiles of TC
-// columns are staged in shared memory; after every tile the fp32 tile sums are flushed into
-// fp64 accumulators, so no fp32 chain is longer than TC terms.
+// columns are staged in shared memory; products and sums are fp64 (see below).
 // ---------------------------------------------------------------------------------------------
 template <int KP, int TC>
 static __global__ void __launch_bounds__(256) normalize_gram_kernel(float* __restrict__ X, long long ncols,
@@ -45,14 +44,15 @@ static __global__ void __launch_bounds__(256) normalize_gram_kernel(float* __res
     __syncthreads();
 
     const int ti = threadIdx.x / 16, tj = threadIdx.x % 16;
-    // Second-level accumulator: fp64 when it fits in registers (R <= 4), else fp32 over the
-    // (short: ncols / (TC*gridDim)) sequence of tile sums. The cross-CTA reduction is fp64 either way.
-    using Acc2 = typename std::conditional<(R <= 4), double, float>::type;
-    Acc2 acc64[R][R];
+    // fp64 accumulation of exact fp32×fp32 products: the result, rounded once to fp32 by
+    // gram_reduce_kernel, is the order-independent "correctly rounded" Gram the oracle defines
+    // (oracle/nmf_oracle.cpp gram()). B200 runs DFMA at half the FFMA rate, the Gram is <5 % of
+    // an iteration, and a G that matches bit for bit keeps every column solve bit-identical.
+    double acc[R][R];
 #pragma unroll
     for (int a = 0; a < R; ++a)
 #pragma unroll
-        for (int b = 0; b < R; ++b) acc64[a][b] = Acc2(0);
+        for (int b = 0; b < R; ++b) acc[a][b] = 0.0;
 
     const long long ntiles = (ncols + TC - 1) / TC;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -65,7 +65,7 @@ static __global__ void __launch_bounds__(256) normalize_gram_kernel(float* __res
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (c < nc) {
                 v = X4[t];
-                if (normalize) {                     // padded coordinates hold 0 and sD = 1 there... (d padded = 1)
+                if (normalize) {                     // padded coordinates hold 0 and d = 1 there
                     v.x = __fdiv_rn(v.x, sD[q * 4 + 0]);
                     v.y = __fdiv_rn(v.y, sD[q * 4 + 1]);
                     v.z = __fdiv_rn(v.z, sD[q * 4 + 2]);
@@ -76,27 +76,18 @@ static __global__ void __launch_bounds__(256) normalize_gram_kernel(float* __res
             *reinterpret_cast<float4*>(&sX[c][q * 4]) = v;
         }
         __syncthreads();
-        float acc[R][R];
-#pragma unroll
-        for (int a = 0; a < R; ++a)
-#pragma unroll
-            for (int b = 0; b < R; ++b) acc[a][b] = 0.f;
-#pragma unroll 4
+#pragma unroll 2
         for (int c = 0; c < TC; ++c) {
-            float av[R], bv[R];
+            double av[R], bv[R];
 #pragma unroll
-            for (int a = 0; a < R; ++a) av[a] = sX[c][ti * R + a];
+            for (int a = 0; a < R; ++a) av[a] = static_cast<double>(sX[c][ti * R + a]);
 #pragma unroll
-            for (int b = 0; b < R; ++b) bv[b] = sX[c][tj * R + b];
+            for (int b = 0; b < R; ++b) bv[b] = static_cast<double>(sX[c][tj * R + b]);
 #pragma unroll
             for (int a = 0; a < R; ++a)
 #pragma unroll
-                for (int b = 0; b < R; ++b) acc[a][b] = fmaf(av[a], bv[b], acc[a][b]);
+                for (int b = 0; b < R; ++b) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
         }
-#pragma unroll
-        for (int a = 0; a < R; ++a)
-#pragma unroll
-            for (int b = 0; b < R; ++b) acc64[a][b] += static_cast<Acc2>(acc[a][b]);
         __syncthreads();
     }
     double* out = partials + static_cast<size_t>(blockIdx.x) * KP * KP;
@@ -104,7 +95,7 @@ static __global__ void __launch_bounds__(256) normalize_gram_kernel(float* __res
     for (int a = 0; a < R; ++a)
 #pragma unroll
         for (int b = 0; b < R; ++b)
-            out[(tj * R + b) * KP + (ti * R + a)] = static_cast<double>(acc64[a][b]);   // G(i,j) at [j*KP+i]
+            out[(tj * R + b) * KP + (ti * R + a)] = acc[a][b];   // G(i,j) at [j*KP+i]
 }
 
 // G[e] = float(Σ_cta partials[cta][e]) in CTA order; symmetrised from the lower triangle
