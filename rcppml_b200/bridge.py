@@ -41,72 +41,95 @@ def gpu_detect(max_gpus: int = 8):
             "free_mem_mb": list(free)[:cnt]}
 
 
-def bridge_nmf_sparse(indptr, indices, data, m, n, k, W_T0, H0, *, max_iter=100, tol=1e-4, L1=(0.0, 0.0),
-                      L2=(0.0, 0.0), L21=(0.0, 0.0), angular=(0.0, 0.0), upper_bound=(0.0, 0.0),
-                      nonneg=(True, True), cd_maxit=100, verbose=False, seed=42, loss_every=1, patience=5,
-                      loss_type=0, norm_type=0, projective=False, symmetric=False, solver_mode=0) -> BridgeResult:
-    """All (a, b) pairs are (W, H). W_T0: (m, k), H0: (n, k) — any float dtype (sent as double)."""
-    lib = _lib.load()
+class PackedCall:
+    """The 73 pointer arguments of rcppml_gpu_nmf_unified_float, packed once (bridge_nmf.hpp:199-307).
+
+    col_ptr/row_idx must be int32, values/W/H float64 C-contiguous; they are passed BY REFERENCE
+    (W, H are overwritten in place, like the reference's W_flat/H_flat), so a caller can keep them in
+    pinned memory and time exactly the native call.
+    """
+
+    def __init__(self, col_ptr, row_idx, values, m, n, k, W, H, *, max_iter=100, tol=1e-4, L1=(0.0, 0.0),
+                 L2=(0.0, 0.0), L21=(0.0, 0.0), angular=(0.0, 0.0), upper_bound=(0.0, 0.0), nonneg=(True, True),
+                 cd_maxit=100, verbose=False, seed=42, loss_every=1, patience=5, loss_type=0, norm_type=0,
+                 projective=False, symmetric=False, solver_mode=0):
+        lib = _lib.load()
+        assert col_ptr.dtype == np.int32 and row_idx.dtype == np.int32
+        assert values.dtype == np.float64 and W.dtype == np.float64 and H.dtype == np.float64
+        assert W.shape == (m, k) and H.shape == (n, k) and W.flags.c_contiguous and H.flags.c_contiguous
+        nnz = int(col_ptr[n])
+        self.W, self.H = W, H
+        self.d = np.ones(k, dtype=np.float64)                                 # :208
+        I, D = C.c_int, C.c_double
+        ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
+        dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+        self._keep = [col_ptr, row_idx, values]
+
+        def i_(v):
+            x = I(int(v)); self._keep.append(x); return C.byref(x)
+
+        def d_(v):
+            x = D(float(v)); self._keep.append(x); return C.byref(x)
+
+        one_i = np.zeros(1, np.int32)          # dummies: pack_graph :144-151, guides :300-304
+        one_d = np.zeros(1, np.float64)
+        theta = np.zeros(max(m, 1), np.float64)                               # :284
+        self._keep += [one_i, one_d, theta]
+        self._theta_len, self._iter, self._conv, self._status = I(0), I(0), I(0), I(0)
+        self._loss, self._tol = D(0.0), D(0.0)
+        self._args = [
+            ip(col_ptr), ip(row_idx), dp(values),
+            i_(m), i_(n), i_(nnz), i_(k),
+            dp(W), dp(H), dp(self.d),
+            i_(max_iter), d_(tol),
+            d_(L1[1]), d_(L1[0]), d_(L2[1]), d_(L2[0]),          # L1_H, L1_W, L2_H, L2_W
+            d_(L21[1]), d_(L21[0]),
+            d_(angular[1]), d_(angular[0]),
+            d_(upper_bound[1]), d_(upper_bound[0]),
+            i_(cd_maxit), i_(verbose), i_(seed),
+            i_(loss_every), i_(patience),
+            i_(nonneg[0]), i_(nonneg[1]),
+            i_(loss_type), d_(1.0),
+            i_(20), d_(1e-4),
+            i_(norm_type),
+            i_(projective), i_(symmetric),
+            i_(solver_mode),
+            ip(one_i), ip(one_i), dp(one_d), i_(0), i_(0), d_(0.0),       # graph_W
+            ip(one_i), ip(one_i), dp(one_d), i_(0), i_(0), d_(0.0),       # graph_H
+            i_(0),
+            d_(0.1), d_(5.0), d_(0.0), d_(10.0), d_(1e6), d_(1e-2), d_(1.0), d_(1e4), d_(1e-6),
+            d_(0.0), d_(1.5),
+            dp(theta), C.byref(self._theta_len),
+            ip(one_i), ip(one_i), dp(one_d), ip(one_i), i_(0),
+            C.byref(self._iter), C.byref(self._conv), C.byref(self._loss),
+            C.byref(self._status),
+            C.byref(self._tol),
+        ]
+        assert len(self._args) == 73, len(self._args)
+        self._fn = lib.rcppml_gpu_nmf_unified_float
+        self._fn.restype = None
+
+    def __call__(self):
+        self._fn(*self._args)
+        return self
+
+    status = property(lambda self: self._status.value)
+    iterations = property(lambda self: self._iter.value)
+    converged = property(lambda self: bool(self._conv.value))
+    train_loss = property(lambda self: self._loss.value)
+    final_tol = property(lambda self: self._tol.value)
+
+
+def bridge_nmf_sparse(indptr, indices, data, m, n, k, W_T0, H0, **kw) -> BridgeResult:
+    """All (a, b) keyword pairs are (W, H). W_T0: (m, k), H0: (n, k) — any float dtype (sent as double)."""
     col_ptr = np.ascontiguousarray(indptr, dtype=np.int32)
     row_idx = np.ascontiguousarray(indices, dtype=np.int32)
-    nnz = int(col_ptr[n])
     values = np.ascontiguousarray(data, dtype=np.float64)                 # bridge_nmf.hpp:200-203
     if row_idx.size == 0:
         row_idx = np.zeros(1, np.int32)
         values = np.zeros(1, np.float64)
-    W = np.ascontiguousarray(W_T0, dtype=np.float64).copy()               # :206-219 (k×m col-major)
-    H = np.ascontiguousarray(H0, dtype=np.float64).copy()                 # :221-230
-    assert W.shape == (m, k) and H.shape == (n, k)
-    d = np.ones(k, dtype=np.float64)                                      # :208
-
-    I, D = C.c_int, C.c_double
-    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
-    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
-    keep = []
-
-    def i_(v):
-        x = I(int(v)); keep.append(x); return C.byref(x)
-
-    def d_(v):
-        x = D(float(v)); keep.append(x); return C.byref(x)
-
-    one_i = np.zeros(1, np.int32)          # dummies: pack_graph :144-151, guides :300-304
-    one_d = np.zeros(1, np.float64)
-    theta = np.zeros(max(m, 1), np.float64)                               # :284
-    out_theta_len, out_iter, out_conv, out_status = I(0), I(0), I(0), I(0)
-    out_loss, out_tol = D(0.0), D(0.0)
-
-    args = [
-        ip(col_ptr), ip(row_idx), dp(values),
-        i_(m), i_(n), i_(nnz), i_(k),
-        dp(W), dp(H), dp(d),
-        i_(max_iter), d_(tol),
-        d_(L1[1]), d_(L1[0]), d_(L2[1]), d_(L2[0]),          # L1_H, L1_W, L2_H, L2_W
-        d_(L21[1]), d_(L21[0]),
-        d_(angular[1]), d_(angular[0]),
-        d_(upper_bound[1]), d_(upper_bound[0]),
-        i_(cd_maxit), i_(verbose), i_(seed),
-        i_(loss_every), i_(patience),
-        i_(nonneg[0]), i_(nonneg[1]),
-        i_(loss_type), d_(1.0),
-        i_(20), d_(1e-4),
-        i_(norm_type),
-        i_(projective), i_(symmetric),
-        i_(solver_mode),
-        ip(one_i), ip(one_i), dp(one_d), i_(0), i_(0), d_(0.0),       # graph_W
-        ip(one_i), ip(one_i), dp(one_d), i_(0), i_(0), d_(0.0),       # graph_H
-        i_(0),
-        d_(0.1), d_(5.0), d_(0.0), d_(10.0), d_(1e6), d_(1e-2), d_(1.0), d_(1e4), d_(1e-6),
-        d_(0.0), d_(1.5),
-        dp(theta), C.byref(out_theta_len),
-        ip(one_i), ip(one_i), dp(one_d), ip(one_i), i_(0),
-        C.byref(out_iter), C.byref(out_conv), C.byref(out_loss),
-        C.byref(out_status),
-        C.byref(out_tol),
-    ]
-    assert len(args) == 73, len(args)
-    fn = lib.rcppml_gpu_nmf_unified_float
-    fn.restype = None
-    fn(*args)
-    return BridgeResult(W.astype(np.float32), H.astype(np.float32), d.astype(np.float32), out_iter.value,
-                        bool(out_conv.value), out_loss.value, out_tol.value, out_status.value)
+    W = np.array(W_T0, dtype=np.float64, order="C")                       # :206-219 (k×m col-major)
+    H = np.array(H0, dtype=np.float64, order="C")                         # :221-230
+    call = PackedCall(col_ptr, row_idx, values, m, n, k, W, H, **kw)()
+    return BridgeResult(W.astype(np.float32), H.astype(np.float32), call.d.astype(np.float32), call.iterations,
+                        call.converged, call.train_loss, call.final_tol, call.status)
