@@ -116,14 +116,6 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def shard_columns(n: int, world: int, rank: int):
-    """Contiguous column ranges; the synthetic matrix has a constant candidate count per column, so an even
-    split is already nnz-balanced."""
-    lo = (n * rank) // world
-    hi = (n * (rank + 1)) // world
-    return lo, hi - lo
-
-
 def solver_mode(args):
     return 1 if args.solver == "cholesky" else 0
 
@@ -254,6 +246,7 @@ def main():
 
     mode = solver_mode(args)
     m, n, k = args.m, args.n, args.k
+    from rcppml_b200.shard import shard_columns
     col_begin, n_local = shard_columns(n, world, rank)
     eng = rb.Engine(local_rank)
     eng.set_matrix_synthetic(m, n_local, col_begin, args.density, SEED_A)

@@ -47,8 +47,8 @@ static void launch_half_step_l(int lanes, const HalfStepParams& p, int num_sms, 
 }
 
 // grid_out != nullptr: only report the grid this configuration would use (for buffer sizing).
-static void launch_half_step(int lanes, int solver, int bsrc, int out, const HalfStepParams& p, int num_sms,
-                             cudaStream_t s, int* grid_out = nullptr) {
+void launch_half_step(int lanes, int solver, int bsrc, int out, const HalfStepParams& p, int num_sms,
+                      cudaStream_t s, int* grid_out) {
     if (out == OUT_RHS) {
         launch_half_step_l<SOLVER_CD, BSRC_GATHER, OUT_RHS>(lanes, p, num_sms, s, grid_out);
     } else if (bsrc == BSRC_GATHER) {
@@ -224,7 +224,9 @@ void Engine::alloc_factors(int k_) {
     k = k_;
     LANES = lanes_for_rank(k);
     KP = padded_rank(k);
-    W_T.ensure(static_cast<size_t>(m) * KP);
+    m_pad = ((m + world - 1) / world) * world;                  // equal row blocks for reduce-scatter / all-gather
+    W_T.ensure(static_cast<size_t>(m_pad) * KP);
+    B200_CUDA_CHECK(cudaMemsetAsync(W_T.ptr, 0, static_cast<size_t>(m_pad) * KP * sizeof(float), stream));
     H.ensure(static_cast<size_t>(n) * KP);
     d.ensure(KP);
     G_w.ensure(static_cast<size_t>(KP) * KP);
@@ -245,8 +247,9 @@ void Engine::alloc_factors(int k_) {
         gmax = std::max(gmax, g);
     }
     solve_grid_max = gmax;
-    norm_partials.ensure(static_cast<size_t>(gmax) * KP);
-    cross_partials.ensure(gmax);
+    solve_partials.ensure(static_cast<size_t>(gmax) * (KP + 1));
+    red_gram.ensure(static_cast<size_t>(KP) * KP);
+    red_small.ensure(KP + 1);
     std::vector<float> ones(KP, 1.f);
     B200_CUDA_CHECK(cudaMemcpyAsync(d.ptr, ones.data(), KP * sizeof(float), cudaMemcpyHostToDevice, stream));
     B200_CUDA_CHECK(cudaStreamSynchronize(stream));
@@ -345,11 +348,15 @@ void Engine::normalize_cfg(const rcppml_b200_config& c) {
     B200_REQUIRE(cfg.norm_type >= 0 && cfg.norm_type <= 2, "norm_type must be 0, 1 or 2");
 }
 
-void Engine::gram(float* X, long long ncols, bool normalize, float* G_out, int sec) {
+void Engine::gram(float* X, long long ncols, bool normalize, float* G_out, int sec, bool reduce_over_ranks) {
     sec_begin(sec);
     launch_normalize_gram(KP, X, ncols, d.ptr, normalize ? 1 : 0, gram_partials.ptr, &state.ptr->stop, gram_grid, stream);
-    gram_reduce_kernel<<<(KP * KP + 255) / 256, 256, 0, stream>>>(gram_partials.ptr, gram_grid, KP, k, G_out, &state.ptr->stop);
+    const int nelem = KP * KP;
+    sum_partials_kernel<<<(nelem + 31) / 32, dim3(32, 8), 0, stream>>>(gram_partials.ptr, gram_grid, nelem, red_gram.ptr, &state.ptr->stop);
     launches[sec] += 2;
+    if (reduce_over_ranks && world > 1) allreduce_f64(red_gram.ptr, nelem);
+    gram_from_sums_kernel<<<(nelem + 255) / 256, 256, 0, stream>>>(red_gram.ptr, KP, k, G_out, &state.ptr->stop);
+    launches[sec] += 1;
     sec_end(sec);
 }
 
@@ -374,7 +381,7 @@ static int pick_cols_per_fetch(long long nnz, long long ncols) {
     return std::max(1, std::min(16, c));
 }
 
-void Engine::solve(int which, bool warm, int sec) {
+HalfStepParams Engine::solve_params(int which, bool warm) const {
     HalfStepParams p{};
     const bool h = (which == 0);
     p.colptr = h ? Ap.ptr : Atp.ptr;
@@ -398,10 +405,15 @@ void Engine::solve(int which, bool warm, int sec) {
     p.want_cross = h ? 0 : 1;
     p.cols_per_fetch = pick_cols_per_fetch(nnz, p.ncols);
     p.work_counter = counters.ptr + which;
-    p.norm_partials = norm_partials.ptr;
-    p.cross_partials = cross_partials.ptr;
+    p.partials = solve_partials.ptr;
+    p.b_local_index = 0;
     p.stop_flag = &state.ptr->stop;
     p.sweep_counter = sweep_counter.ptr;
+    return p;
+}
+
+void Engine::solve(int which, bool warm, int sec) {
+    HalfStepParams p = solve_params(which, warm);
     const int solver = cfg.solver_mode == 0 ? SOLVER_CD : SOLVER_CHOL;
     int grid = 0;
     launch_half_step(LANES, solver, BSRC_GATHER, OUT_SOLVE, p, num_sms, stream, &grid);
@@ -413,11 +425,20 @@ void Engine::solve(int which, bool warm, int sec) {
     sec_end(sec);
 }
 
-void Engine::scale_finalize(int sec) {
+void Engine::scale_finalize(int sec, bool reduce_over_ranks) {
     sec_begin(sec);
-    scale_finalize_kernel<<<1, 128, 0, stream>>>(norm_partials.ptr, last_solve_grid, KP, k, cfg.norm_type, d.ptr, nullptr, &state.ptr->stop);
-    launches[sec] += 1;
+    const int nelem = KP + 1;                                   // k row sums + the loss cross term
+    sum_partials_kernel<<<(nelem + 31) / 32, dim3(32, 8), 0, stream>>>(solve_partials.ptr, last_solve_grid, nelem, red_small.ptr, &state.ptr->stop);
+    if (reduce_over_ranks && world > 1) allreduce_f64(red_small.ptr, nelem);
+    scale_from_sums_kernel<<<1, 128, 0, stream>>>(red_small.ptr, KP, k, cfg.norm_type, d.ptr, &state.ptr->stop);
+    launches[sec] += 2;
     sec_end(sec);
+}
+
+void Engine::loss(int sec) {
+    loss_kernel<<<1, 256, 0, stream>>>(G_w.ptr, G_h.ptr, d.ptr, KP, k, red_small.ptr + KP, 1, trAtA, cfg.tol,
+                                       cfg.patience, loss_hist.ptr, static_cast<int>(loss_hist.count), state.ptr);
+    launches[sec] += 1;
 }
 
 void Engine::enqueue_iteration() {
@@ -438,9 +459,7 @@ void Engine::enqueue_iteration() {
     const bool was = profiling; profiling = false;                         // nested section: account under LOSS
     gram(W_T.ptr, m, normalize, G_w.ptr, RCPPML_B200_SEC_LOSS);             // :892 (normalise) + :1735
     profiling = was;
-    loss_kernel<<<1, 256, 0, stream>>>(G_w.ptr, G_h.ptr, d.ptr, KP, k, cross_partials.ptr, last_solve_grid, trAtA,
-                                       cfg.tol, cfg.patience, loss_hist.ptr, static_cast<int>(loss_hist.count), state.ptr);
-    launches[RCPPML_B200_SEC_LOSS] += 1;
+    loss(RCPPML_B200_SEC_LOSS);
     sec_end(RCPPML_B200_SEC_LOSS);
     ++iters_enqueued;
 }
@@ -545,11 +564,6 @@ using b200::Engine;
         b200::g_last_error = "unknown error";                             \
         return -1;                                                        \
     }
-
-struct rcppml_b200_engine {
-    Engine impl;
-    explicit rcppml_b200_engine(int dev) : impl(dev) {}
-};
 
 extern "C" {
 

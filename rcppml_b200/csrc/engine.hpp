@@ -18,6 +18,10 @@ namespace b200 {
 
 extern thread_local std::string g_last_error;
 
+// grid_out != nullptr: only report the persistent grid this instantiation uses (buffer sizing).
+void launch_half_step(int lanes, int solver, int bsrc, int out, const HalfStepParams& p, int num_sms,
+                      cudaStream_t s, int* grid_out = nullptr);
+
 class Engine {
 public:
     explicit Engine(int device);
@@ -64,7 +68,8 @@ public:
     int k = 0, KP = 0, LANES = 0;
     DeviceBuffer<float> W_T, H, d;
     DeviceBuffer<float> G_w, G_h, M1, M2, diag;
-    DeviceBuffer<double> gram_partials, norm_partials, cross_partials;
+    DeviceBuffer<double> gram_partials, solve_partials;   // per-CTA partials (fixed-order reductions)
+    DeviceBuffer<double> red_gram, red_small;             // reduced sums: k×k Gram | k row sums + cross term
     DeviceBuffer<int> counters;
     DeviceBuffer<unsigned long long> sweep_counter;
     DeviceBuffer<DevState> state;
@@ -87,9 +92,9 @@ public:
     // multi-GPU
     ncclComm* comm = nullptr;
     int rank = 0, world = 1;
-    DeviceBuffer<float> B_part;       // k × m partial right-hand side of the W-update (this rank's columns)
+    DeviceBuffer<float> B_part;       // m_pad × KP partial right-hand side of the W-update (this rank's columns)
     DeviceBuffer<float> B_blk;        // reduced row block owned by this rank
-    DeviceBuffer<double> red_buf;     // small all-reduce staging (Gram, norms, loss scalars)
+    int m_pad = 0;                    // m rounded up to a multiple of world (equal row blocks)
     int row_begin = 0, row_count = 0; // rows of A (columns of Aᵀ) this rank solves in the W-update
 
 private:
@@ -102,12 +107,21 @@ private:
     void sec_begin(int sec);
     void sec_end(int sec);
     void collect_profile();
-    void gram(float* X, long long ncols, bool normalize, float* G_out, int sec);
+    void gram(float* X, long long ncols, bool normalize, float* G_out, int sec, bool reduce_over_ranks = false);
+    void loss(int sec);
+    void allreduce_f64(double* buf, size_t count);
     void prepare_solver(const float* G, float L2, int sec);
+    HalfStepParams solve_params(int which, bool warm) const;
     void solve(int which, bool warm, int sec);
-    void scale_finalize(int sec);
+    void scale_finalize(int sec, bool reduce_over_ranks = false);
     void enqueue_iteration();
     void enqueue_iteration_sharded();
 };
 
 }  // namespace b200
+
+// The opaque handle of the C ABI.
+struct rcppml_b200_engine {
+    b200::Engine impl;
+    explicit rcppml_b200_engine(int dev) : impl(dev) {}
+};

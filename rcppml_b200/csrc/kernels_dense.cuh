@@ -98,18 +98,37 @@ static __global__ void __launch_bounds__(256) normalize_gram_kernel(float* __res
             out[(tj * R + b) * KP + (ti * R + a)] = acc[a][b];   // G(i,j) at [j*KP+i]
 }
 
-// G[e] = float(Σ_cta partials[cta][e]) in CTA order; symmetrised from the lower triangle
-// (gram.hpp:64-65) with tiny_num on the diagonal (gram.hpp:66). Padded rows/cols stay 0.
-static __global__ void gram_reduce_kernel(const double* __restrict__ partials, int nparts, int KP, int k,
-                                   float* __restrict__ G, const int* __restrict__ stop_flag) {
+// out[e] = Σ_c partials[c][e] in a FIXED order: 8 interleaved slices per element (slice s takes
+// c ≡ s mod 8, ascending), combined in slice order. blockDim = (32, 8).
+static __global__ void __launch_bounds__(256) sum_partials_kernel(const double* __restrict__ partials, int nparts,
+                                                                  int nelem, double* __restrict__ out,
+                                                                  const int* __restrict__ stop_flag) {
+    __shared__ double s[8][33];
+    if (*stop_flag) return;
+    const int e = blockIdx.x * 32 + threadIdx.x;
+    double a = 0.0;
+    if (e < nelem)
+        for (int c = threadIdx.y; c < nparts; c += 8) a += partials[static_cast<size_t>(c) * nelem + e];
+    s[threadIdx.y][threadIdx.x] = a;
+    __syncthreads();
+    if (threadIdx.y == 0 && e < nelem) {
+        double t = 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) t += s[q][threadIdx.x];
+        out[e] = t;
+    }
+}
+
+// G = float(sums) symmetrised from the lower triangle (gram.hpp:64-65) with tiny_num on the
+// diagonal (gram.hpp:66). Padded rows/cols stay 0. `sums` may have been all-reduced over ranks.
+static __global__ void gram_from_sums_kernel(const double* __restrict__ sums, int KP, int k, float* __restrict__ G,
+                                             const int* __restrict__ stop_flag) {
     if (*stop_flag) return;
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= KP * KP) return;
     const int i = e % KP, j = e / KP;
     const int lo = (i >= j) ? (j * KP + i) : (i * KP + j);     // lower-triangle source element
-    double s = 0.0;
-    for (int c = 0; c < nparts; ++c) s += partials[static_cast<size_t>(c) * KP * KP + lo];
-    float v = static_cast<float>(s);
+    float v = static_cast<float>(sums[lo]);
     if (i == j) v = __fadd_rn(v, 1e-15f);
     if (i >= k || j >= k) v = 0.f;
     G[e] = v;
@@ -175,19 +194,15 @@ static __global__ void __launch_bounds__(128) prepare_solver_kernel(const float*
     for (int i = tid; i < KP; i += blockDim.x) diag[i] = (i < k) ? sL[i * KP + i] : 1.f;
 }
 
-// d_i = float(Σ_cta partials[cta][i]) (+sqrt for L2) + 1e-15 ; padded d_i = 1.
-// Also re-arms the work counter of the next solve kernel.
-static __global__ void scale_finalize_kernel(const double* __restrict__ partials, int nparts, int KP, int k, int norm_type,
-                                      float* __restrict__ d, int* __restrict__ work_counter,
-                                      const int* __restrict__ stop_flag) {
+// d_i = float(sums_i) (+sqrt for L2) + 1e-15 (variant_helpers.hpp:297-301); padded d_i = 1.
+// `sums` are the fp64 row sums over all columns (all-reduced over ranks when sharded).
+static __global__ void scale_from_sums_kernel(const double* __restrict__ sums, int KP, int k, int norm_type,
+                                              float* __restrict__ d, const int* __restrict__ stop_flag) {
     if (*stop_flag) return;
     const int i = threadIdx.x;
-    if (i == 0 && work_counter) *work_counter = 0;
     if (i >= KP) return;
     if (i >= k || norm_type == 2) { d[i] = 1.f; return; }
-    double s = 0.0;
-    for (int c = 0; c < nparts; ++c) s += partials[static_cast<size_t>(c) * KP + i];
-    float v = static_cast<float>(s);
+    float v = static_cast<float>(sums[i]);
     if (norm_type == 1) v = __fsqrt_rn(v);
     d[i] = __fadd_rn(v, 1e-15f);
 }

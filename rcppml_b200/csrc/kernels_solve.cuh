@@ -51,8 +51,8 @@ struct HalfStepParams {
     int want_cross;
     int cols_per_fetch;
     int* work_counter;
-    double* norm_partials;             // [gridDim.x][KP]
-    double* cross_partials;            // [gridDim.x]
+    double* partials;                  // [gridDim.x][KP+1]: Σ|x| (or Σx²) per coordinate, then <x, b_raw>
+    int b_local_index;                 // BSRC_LOAD: B is indexed by the local column (row-block solves)
     const int* stop_flag;
     unsigned long long* sweep_counter; // optional: total CD sweeps (diagnostics)
 };
@@ -357,9 +357,10 @@ __global__ void __launch_bounds__(256) half_step_kernel(const HalfStepParams p) 
                 const int p1 = __ldg(p.colptr + j + 1);
                 gather_column<LANES, NV>(p, p0, p1, gl, gmask, b);
             } else {
+                const int jb = p.b_local_index ? jl : j;
 #pragma unroll
                 for (int nv = 0; nv < NV; ++nv) {
-                    const float4 v0 = *reinterpret_cast<const float4*>(p.B + static_cast<size_t>(j) * KP +
+                    const float4 v0 = *reinterpret_cast<const float4*>(p.B + static_cast<size_t>(jb) * KP +
                                                                        (nv * LANES + gl) * 4);
                     b[nv][0] = v0.x; b[nv][1] = v0.y; b[nv][2] = v0.z; b[nv][3] = v0.w;
                 }
@@ -367,7 +368,7 @@ __global__ void __launch_bounds__(256) half_step_kernel(const HalfStepParams p) 
 #pragma unroll
                     for (int nv = 0; nv < NV; ++nv) {
                         const float4 v = *reinterpret_cast<const float4*>(
-                            p.B + static_cast<size_t>(s) * p.slot_stride + static_cast<size_t>(j) * KP +
+                            p.B + static_cast<size_t>(s) * p.slot_stride + static_cast<size_t>(jb) * KP +
                             (nv * LANES + gl) * 4);
                         b[nv][0] = __fadd_rn(b[nv][0], v.x); b[nv][1] = __fadd_rn(b[nv][1], v.y);
                         b[nv][2] = __fadd_rn(b[nv][2], v.z); b[nv][3] = __fadd_rn(b[nv][3], v.w);
@@ -473,14 +474,16 @@ __global__ void __launch_bounds__(256) half_step_kernel(const HalfStepParams p) 
         for (int t = threadIdx.x; t < KP; t += blockDim.x) {
             double s = 0.0;
             for (int g = 0; g < NGROUPS; ++g) s += sRed[g * KP + t];
-            p.norm_partials[static_cast<size_t>(blockIdx.x) * KP + t] = s;
+            p.partials[static_cast<size_t>(blockIdx.x) * (KP + 1) + t] = s;
         }
+    } else {
+        for (int t = threadIdx.x; t < KP; t += blockDim.x) p.partials[static_cast<size_t>(blockIdx.x) * (KP + 1) + t] = 0.0;
     }
     if (threadIdx.x == 0) {
         double s = 0.0;
         if (p.want_cross)
             for (int t = 0; t < 256; ++t) s += sCross[t];
-        p.cross_partials[blockIdx.x] = s;
+        p.partials[static_cast<size_t>(blockIdx.x) * (KP + 1) + KP] = s;
     }
 }
 

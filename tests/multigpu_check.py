@@ -1,0 +1,76 @@
+"""Run under torchrun with N ranks (one per GPU): the column-sharded fit must agree with the
+single-GPU fit of the same matrix to fp32 reassociation (B is summed across ranks), inside the
+1e-5 relative budget, and be identical on every rank.
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+      --master-port 29511 tests/multigpu_check.py
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import rcppml_b200 as rb  # noqa: E402
+from rcppml_b200 import shard, synth  # noqa: E402
+
+
+def rel_err(a, b):
+    return float(np.abs(a.astype(np.float64) - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    m, n, dens = 120_000, 9_001, 2e-3           # n not divisible by world on purpose; m neither for world=8
+    worst = 0.0
+    for k, solver, kw in [(64, 1, {}), (64, 0, dict(L1=(0.01, 0.01))), (20, 0, dict(L2=(0.01, 0.01))),
+                          (128, 1, dict(L1=(0.01, 0.01), L2=(0.01, 0.01)))]:
+        iters = 4
+        lo, cnt = shard.shard_columns(n, world, rank)
+        eng = rb.Engine(local)
+        eng.set_matrix_synthetic(m, cnt, lo, dens, synth.SEED_A)
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(rb.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        eng.comm_init(rank, world, uid.cpu().numpy().tobytes())
+        eng.init_factors(k, 42, lo)
+        cfg = rb.make_config(k, max_iter=iters, tol=0.0, solver_mode=solver, **kw)
+        res = eng.fit(cfg)
+        W, H, d = eng.get_factors()
+        hist = eng.loss_history(iters)
+        eng.close()
+        assert res.iterations == iters and res.status == 0
+
+        # every rank must hold the same replicated W_T / d / loss
+        t = torch.from_numpy(np.concatenate([W.ravel(), d, hist])).cuda()
+        t0 = t.clone()
+        dist.broadcast(t0, 0)
+        assert torch.equal(t, t0), "replicated state differs between ranks"
+
+        # single-GPU reference on this rank's own GPU (full matrix)
+        ref = rb.Engine(local)
+        ref.set_matrix_synthetic(m, n, 0, dens, synth.SEED_A)
+        ref.init_factors(k, 42, 0)
+        ref.fit(cfg)
+        W1, H1, d1 = ref.get_factors()
+        hist1 = ref.loss_history(iters)
+        ref.close()
+        errs = dict(W=rel_err(W, W1), H=rel_err(H, H1[lo:lo + cnt]), d=rel_err(d, d1), loss=rel_err(hist, hist1))
+        worst = max(worst, *errs.values())
+        if rank == 0:
+            print(f"k={k} solver={solver} world={world}: {errs}", flush=True)
+        assert max(errs.values()) <= 1e-5, errs
+    dist.barrier()
+    if rank == 0:
+        print(f"MULTIGPU_CHECK_OK world={world} worst_rel_err={worst:.3e}", flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
