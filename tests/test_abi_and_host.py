@@ -1,0 +1,114 @@
+"""CPU: the C-ABI library loads and exports every symbol include/rcppml_gpu.h declares (no compute
+without a GPU), fails loudly instead of falling back, and the host-side logic (packing, sharding,
+synthetic generator twin) is right."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "rcppml_gpu.h")
+
+
+def _declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(rcppml_(?:gpu|b200)_\w+)\s*\(", src)))
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_library_exports_every_declared_symbol():
+    from rcppml_b200 import _lib
+    lib = _lib.load()
+    names = _declared_symbols()
+    assert "rcppml_gpu_nmf_unified_float" in names and "rcppml_gpu_detect" in names and len(names) >= 20
+    for nm in names:
+        assert hasattr(lib, nm), f"{nm} declared in include/rcppml_gpu.h but not exported"
+
+
+def test_library_is_sm100a_only():
+    from rcppml_b200 import _lib
+    out = os.popen(f"cuobjdump -lelf {_lib.LIB_PATH} 2>/dev/null").read()
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU failure mode")
+def test_no_gpu_means_loud_failure_not_fallback():
+    import rcppml_b200 as rb
+    from rcppml_b200._lib import NativeLibraryError
+    info = rb.gpu_detect()
+    assert info["num_gpus"] == 0 and info["status"] == -1             # src/gpu_bridge_cluster.cu:33-36
+    with pytest.raises(NativeLibraryError):
+        rb.Engine(0)
+    W0 = np.random.default_rng(0).random((30, 4))
+    H0 = np.random.default_rng(1).random((20, 4))
+    indptr = np.arange(21, dtype=np.int32)
+    out = rb.bridge_nmf_sparse(indptr, np.arange(20, dtype=np.int32) % 30, np.ones(20), 30, 20, 4, W0, H0, max_iter=2)
+    assert out.status == -1 and out.iterations == 0                   # caller (nmf/fit.hpp:125-133) owns the CPU path
+    assert np.array_equal(out.W_T, W0.astype(np.float32))
+
+
+def test_bridge_packs_73_pointers_in_reference_order():
+    from rcppml_b200.bridge import PackedCall
+    m, n, k = 6, 5, 3
+    indptr = np.array([0, 1, 2, 3, 4, 5], np.int32)
+    call = PackedCall(indptr, np.zeros(5, np.int32), np.ones(5), m, n, k, np.ones((m, k)), np.ones((n, k)),
+                      max_iter=7, tol=0.5, L1=(0.1, 0.2), L2=(0.3, 0.4), upper_bound=(1.0, 2.0), nonneg=(True, False),
+                      cd_maxit=11, seed=9, patience=4, norm_type=1, solver_mode=1)
+    a = call._args
+    assert len(a) == 73                                               # gpu/bridge_nmf.hpp:39-75
+    val = lambda x: x._obj.value
+    assert [val(a[i]) for i in (3, 4, 5, 6)] == [m, n, 5, k]
+    assert val(a[10]) == 7 and val(a[11]) == 0.5
+    assert [val(a[i]) for i in (12, 13, 14, 15)] == [0.2, 0.1, 0.4, 0.3]   # L1_H, L1_W, L2_H, L2_W
+    assert [val(a[i]) for i in (20, 21)] == [2.0, 1.0]                     # ub_H, ub_W
+    assert val(a[22]) == 11 and val(a[24]) == 9 and val(a[26]) == 4
+    assert [val(a[i]) for i in (27, 28)] == [1, 0]                         # nonneg_W, nonneg_H
+    assert val(a[33]) == 1 and val(a[36]) == 1                             # norm_type, solver_mode
+
+
+def test_config_mapping():
+    import rcppml_b200 as rb
+    c = rb.make_config(8, L1=(0.1, 0.2), L2=(0.3, 0.4), upper_bound=(1, 2), nonneg=(False, True), solver_mode=1)
+    assert (c.L1_W, c.L1_H) == (np.float32(0.1), np.float32(0.2)) and (c.ub_W, c.ub_H) == (1.0, 2.0)
+    assert (c.nonneg_W, c.nonneg_H) == (0, 1) and c.cd_maxit == 100 and c.patience == 5
+
+
+def test_shard_helpers():
+    from rcppml_b200 import shard
+    for n, world in [(100000, 8), (9001, 2), (7, 8), (10, 3)]:
+        parts = [shard.shard_columns(n, world, r) for r in range(world)]
+        assert parts[0][0] == 0 and sum(c for _, c in parts) == n
+        assert all(parts[i][0] + parts[i][1] == parts[i + 1][0] for i in range(world - 1))
+    rng = np.random.default_rng(0)
+    counts = rng.integers(0, 50, 1000)
+    indptr = np.concatenate([[0], np.cumsum(counts)])
+    parts = shard.shard_columns_by_nnz(indptr, 4)
+    assert parts[0][0] == 0 and sum(c for _, c in parts) == 1000
+    loads = [indptr[lo + c] - indptr[lo] for lo, c in parts]
+    assert max(loads) - min(loads) <= 2 * counts.max()
+    p, i, x = shard.extract_shard(indptr, np.arange(indptr[-1]), np.arange(indptr[-1], dtype=np.float32), 10, 5)
+    assert p[0] == 0 and p[-1] == i.size == x.size == indptr[15] - indptr[10]
+
+
+def test_synth_numpy_twin_matches_oracle_generator(oracle):
+    from rcppml_b200 import synth
+    for (m, n_local, col_begin, dens) in [(5000, 300, 0, 0.01), (20000, 64, 77, 0.05)]:
+        a = synth.synth_csc(m, n_local, col_begin, dens)
+        b = oracle.synth_csc(m, n_local, col_begin, dens)
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    p, i, x = synth.synth_csc(100000, 50, 0, 1e-3)
+    assert np.all(np.diff(p) <= 100) and np.all(np.diff(p) >= 95)       # ~0.1 % dedupe loss
+    assert x.min() >= 0.5 and x.max() < 1.5 and np.all(i < 100000)
+    for j in range(50):
+        assert np.all(np.diff(i[p[j]:p[j + 1]]) > 0)                   # sorted, unique rows

@@ -175,3 +175,20 @@ def test_large_synthetic_properties(eng):
         assert np.all(np.diff(hist) <= 1e-6 * hist[0])
     for a, b in zip(outs[0], outs[1]):
         assert np.array_equal(a, b)
+
+
+def test_multi_gpu_matches_single_gpu():
+    """Column-sharded fit over NCCL (tests/multigpu_check.py) — needs >= 2 GPUs on the box."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 8 if ngpu >= 8 else (4 if ngpu >= 4 else 2)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "multigpu_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "MULTIGPU_CHECK_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]

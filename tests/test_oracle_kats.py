@@ -1,0 +1,226 @@
+"""CPU: pins the oracle against every known-answer / property test the reference holds for this path
+(tests/cpp/test_rng.cpp, test_nnls.cpp, test_gram.cpp, tests/testthat/test_nmf.R, test_norm.R,
+test_upper_bound.R, test_loss_monotonicity.R) and against the published SplitMix64 vectors.
+The reference holds NO golden W/d/H vectors, so factor values stay "parity unpinned"."""
+import numpy as np
+import pytest
+
+from helpers import random_csc
+
+
+# ---- rng/rng.hpp -------------------------------------------------------------------------------
+def test_splitmix64_published_vectors(oracle):
+    # Vigna's splitmix64.c reference output for seed 1234567 (widely reproduced test vector)
+    want = [6457827717110365317, 3203168211198807973, 9817491932198370423, 4593380528125082431,
+            16408922859458223821]
+    assert oracle.splitmix_next(1234567, 5).tolist() == want
+
+
+def test_rng_cases_of_test_rng_cpp(oracle):
+    a, b = oracle.splitmix_next(42, 100), oracle.splitmix_next(42, 100)
+    assert np.array_equal(a, b)                                         # rng_deterministic_same_seed (:9-15)
+    assert (a == oracle.splitmix_next(99, 100)).sum() < 5               # rng_different_seeds_differ (:17-25)
+    u = oracle.UniformStream(12345).fill_f64(1, 1000)
+    assert u.min() >= 0.0 and u.max() < 1.0                             # rng_uniform_range (:27-34)
+    assert np.array_equal(oracle.splitmix_next(0, 4), oracle.splitmix_next(12345, 4))   # zero seed remapped (:36-39)
+    assert oracle.splitmix_hash(42, 5, 10) == oracle.splitmix_hash(42, 5, 10)           # hash deterministic (:41-45)
+    assert oracle.splitmix_hash(42, 5, 10) != oracle.splitmix_hash(42, 10, 5)           # position sensitive (:47-51)
+    cnt = sum(oracle.is_holdout(42, i, j, 10) for i in range(100) for j in range(100))
+    assert 0.05 < cnt / 10000 < 0.15                                    # rng_holdout_fraction_approx (:61-73)
+    M = oracle.UniformStream(42).fill_f64(5, 10)
+    assert M.min() >= 0 and M.max() < 1 and M.max() - M.min() > 0.1     # rng_fill_uniform_matrix (:75-84)
+
+
+def test_initialize_factors_one_stream(oracle):
+    W, H = oracle.initialize_factors(3, 4, 5, 42)                       # nmf_init.hpp:167-182
+    s = oracle.UniformStream(42).fill_f32(1, 3 * 4 + 3 * 5).ravel()
+    assert np.array_equal(W.ravel(), s[:12]) and np.array_equal(H.ravel(), s[12:])
+
+
+# ---- nnls_batch.hpp ----------------------------------------------------------------------------
+def _gram64(oracle, H):
+    return oracle.gram(np.ascontiguousarray(H.T))                       # rows of H.T = columns of H
+
+
+def test_nnls_cases_of_test_nnls_cpp(oracle):
+    rng = np.random.default_rng(0)
+    # nnls_identity_gram (:11-29)
+    k, n = 3, 5
+    G = np.eye(k) + 1e-10 * np.eye(k)
+    B = np.abs(rng.uniform(-1, 1, (n, k)))
+    X = np.zeros((n, k))
+    oracle.nnls_batch_f64(G, B.copy(), X)
+    assert np.allclose(X, B, atol=1e-4)
+    # nnls_nonnegativity (:31-45)
+    k, n = 4, 10
+    G = _gram64(oracle, rng.uniform(-1, 1, (k, 20)))
+    X = np.zeros((n, k))
+    oracle.nnls_batch_f64(G, rng.uniform(-1, 1, (n, k)), X)
+    assert X.min() >= 0.0
+    # nnls_unconstrained (:47-63)
+    G = np.eye(3) + 1e-10 * np.eye(3)
+    B = rng.uniform(-1, 1, (5, 3)); B[0, 0] = -1.0
+    X = np.zeros((5, 3))
+    oracle.nnls_batch_f64(G, B.copy(), X, nonneg=False)
+    assert abs(X[0, 0] - B[0, 0]) < 1e-4
+    # nnls_known_solution (:65-84): G=[[2,1],[1,2]], b=[3,3] -> x=[1,1]
+    G = np.array([[2.0, 1.0], [1.0, 2.0]]) + 1e-10 * np.eye(2)
+    X = np.zeros((1, 2))
+    oracle.nnls_batch_f64(G, np.array([[3.0, 3.0]]), X)
+    assert np.allclose(X, 1.0, atol=1e-4)
+    # nnls_l1_sparsity (:86-107)
+    k, n = 4, 10
+    G = _gram64(oracle, np.abs(rng.uniform(-1, 1, (k, 50))))
+    B = np.abs(rng.uniform(-1, 1, (n, k)))
+    X0, X1 = np.zeros((n, k)), np.zeros((n, k))
+    oracle.nnls_batch_f64(G, B.copy(), X0)
+    oracle.nnls_batch_f64(G, B.copy(), X1, L1=1.0)
+    assert np.abs(X0).sum() >= np.abs(X1).sum()
+    # nnls_warm_start (:109-133)
+    k, n = 3, 5
+    G = _gram64(oracle, np.abs(rng.uniform(-1, 1, (k, 20))))
+    B = np.abs(rng.uniform(-1, 1, (n, k)))
+    Xc = np.zeros((n, k))
+    oracle.nnls_batch_f64(G, B.copy(), Xc)
+    Xw = Xc.copy()
+    oracle.nnls_batch_f64(G, B.copy(), Xw, warm_start=True)
+    assert np.allclose(Xc, Xw, atol=1e-4)
+
+
+def test_cd_solves_kkt(oracle):
+    """Oracle self-check: CD output satisfies the NNLS KKT conditions."""
+    rng = np.random.default_rng(1)
+    k = 12
+    F = rng.random((200, k))
+    G = oracle.gram(F)
+    b0 = (F.T @ rng.random(200)) * np.where(rng.random(k) < 0.3, -1.0, 1.0)
+    b, x = b0.copy(), np.zeros(k)
+    oracle.cd_nnls_col(G, b, x, maxit=5000, cd_tol=1e-14)
+    grad = G @ x - b0
+    assert x.min() >= 0
+    assert np.all(np.abs(grad[x > 0]) < 1e-6 * np.abs(b0).max())
+    assert np.all(grad[x == 0] > -1e-6 * np.abs(b0).max())
+
+
+# ---- gram.hpp ------------------------------------------------------------------------------------
+def test_gram_cases_of_test_gram_cpp(oracle):
+    rng = np.random.default_rng(2)
+    G = oracle.gram(np.eye(3))                                          # gram_identity (:11-27)
+    assert np.allclose(np.diag(G), 1.0, atol=1e-6) and np.allclose(G - np.diag(np.diag(G)), 0, atol=1e-10)
+    H = rng.uniform(-1, 1, (4, 20))
+    G = _gram64(oracle, H)
+    assert np.allclose(G, G.T, atol=1e-12)                              # gram_symmetric (:29-41)
+    assert np.all(np.diag(G) > 0)                                       # gram_positive_diagonal (:43-53)
+    H = rng.uniform(-1, 1, (3, 10))
+    assert np.allclose(_gram64(oracle, H), H @ H.T, atol=1e-8)          # gram_matches_manual (:55-71)
+    H = rng.uniform(-1, 1, (3, 15))
+    assert np.allclose(_gram64(oracle, 2 * H), 4 * _gram64(oracle, H), atol=1e-6)   # gram_scaled_input (:73-90)
+
+
+def test_cholesky_restatement_solves(oracle):
+    rng = np.random.default_rng(3)
+    F = rng.random((300, 16)).astype(np.float32)
+    G = oracle.gram(F)
+    L, info = oracle.cholesky_factor(G)
+    assert info == 0
+    b = rng.random(16).astype(np.float32)
+    x = oracle.cholesky_solve(L, b)
+    assert np.allclose(G.astype(np.float64) @ x, b, rtol=0, atol=2e-3 * np.abs(b).max())
+    _, info = oracle.cholesky_factor(-np.eye(4, dtype=np.float32))
+    assert info == 1
+
+
+# ---- property suites of tests/testthat re-expressed --------------------------------------------------
+@pytest.fixture(scope="module")
+def small_problem(oracle):
+    m, n, k = 300, 200, 6
+    A = random_csc(m, n, 0.1, 5, counts=True)
+    W0, H0 = oracle.initialize_factors(k, m, n, 123)
+    return A, m, n, k, W0, H0
+
+
+def _fit(oracle, P, **kw):
+    A, m, n, k, W0, H0 = P
+    return oracle.nmf_fit(A.indptr, A.indices, A.data, m, n, k, W0, H0, tol=0.0, **kw)
+
+
+@pytest.mark.parametrize("solver", [0, 1])
+def test_nmf_properties_test_nmf_R(oracle, small_problem, solver):
+    r1 = _fit(oracle, small_problem, max_iter=1, solver_mode=solver)
+    r20 = _fit(oracle, small_problem, max_iter=20, solver_mode=solver)
+    assert r20.train_loss <= r1.train_loss                              # test_nmf.R:4-26
+    assert r20.W_T.min() >= 0 and r20.H.min() >= 0
+    again = _fit(oracle, small_problem, max_iter=20, solver_mode=solver)
+    assert np.array_equal(again.W_T, r20.W_T)                           # test_nmf.R:58-72 (same seed, identical)
+    hist = r20.loss_history                                             # test_loss_monotonicity.R
+    assert np.all(np.diff(hist) <= 1e-5 * hist[0])
+    # loss from the Gram trick == explicit ||A - W d H||^2 (oracle self-check 3)
+    A = small_problem[0]
+    R = A.toarray() - (r20.W_T * r20.d) @ r20.H.T
+    assert abs((R.astype(np.float64) ** 2).sum() - r20.train_loss) <= 2e-4 * r20.train_loss
+
+
+def test_l1_increases_sparsity_test_nmf_R(oracle, small_problem):
+    r0 = _fit(oracle, small_problem, max_iter=15)
+    r1 = _fit(oracle, small_problem, max_iter=15, L1=(0.5, 0.5))
+    assert (r1.W_T == 0).sum() + (r1.H == 0).sum() > (r0.W_T == 0).sum() + (r0.H == 0).sum()   # test_nmf.R:40-54
+
+
+def test_norm_types_test_norm_R(oracle, small_problem):
+    r = _fit(oracle, small_problem, max_iter=5, norm_type=0)            # test_norm.R:35-52
+    assert np.allclose(r.W_T.sum(axis=0), 1.0, atol=1e-5)
+    r = _fit(oracle, small_problem, max_iter=5, norm_type=1)
+    assert np.allclose(np.sqrt((r.W_T.astype(np.float64) ** 2).sum(axis=0)), 1.0, atol=1e-5)
+    r = _fit(oracle, small_problem, max_iter=5, norm_type=2)
+    assert np.all(r.d == 1.0)
+
+
+def test_upper_bound_test_upper_bound_R(oracle, small_problem):
+    A, m, n, k, W0, H0 = small_problem
+    r = oracle.nmf_fit(A.indptr, A.indices, A.data, m, n, k, W0, H0, max_iter=5, tol=0.0, norm_type=2,
+                       upper_bound=(0.3, 0.4))                           # test_upper_bound.R:24-41
+    assert r.W_T.max() <= 0.3 + 1e-7 and r.H.max() <= 0.4 + 1e-7
+
+
+def test_convergence_patience_and_sort(oracle, small_problem):
+    r = _fit(oracle, small_problem, max_iter=3, sort_model=True)
+    assert np.all(np.diff(r.d) <= 0)                                    # core/result.hpp:169-189
+    A, m, n, k, W0, H0 = small_problem
+    c = oracle.nmf_fit(A.indptr, A.indices, A.data, m, n, k, W0, H0, max_iter=500, tol=1e-3, solver_mode=1)
+    assert c.converged and c.iterations < 500 and c.final_tol < 1e-3    # fit_cpu.hpp:1769-1809 (5 consecutive)
+    with pytest.raises(ValueError):
+        oracle.nmf_fit(A.indptr, A.indices, A.data, m, n, k, W0, H0, max_iter=0)        # core/config.hpp:424
+
+
+def test_masked_path_ignores_masked_entries(oracle):
+    """nmf/masked_nnls.hpp: corrupting masked entries of A must not change the fit."""
+    m, n, k = 120, 90, 5
+    A = random_csc(m, n, 0.2, 8)
+    M = random_csc(m, n, 0.05, 9)
+    W0, H0 = oracle.initialize_factors(k, m, n, 7)
+    A2 = A.copy().tolil()
+    rows, cols = M.nonzero()
+    for r_, c_ in zip(rows[:50], cols[:50]):
+        if A2[r_, c_] != 0:
+            A2[r_, c_] = 37.0
+    A2 = A2.tocsc(); A2.sort_indices()
+    for solver in (0, 1):
+        a = oracle.nmf_fit(A.indptr, A.indices, A.data, m, n, k, W0, H0, max_iter=4, tol=0.0, solver_mode=solver,
+                           mask=(M.indptr, M.indices))
+        b = oracle.nmf_fit(A2.indptr, A2.indices, A2.data, m, n, k, W0, H0, max_iter=4, tol=0.0, solver_mode=solver,
+                           mask=(M.indptr, M.indices))
+        assert np.array_equal(a.W_T, b.W_T) and np.array_equal(a.H, b.H) and a.train_loss == b.train_loss
+
+
+def test_golden_fixture_regression(oracle):
+    """tests/golden/oracle_small_fit.npz was produced by tests/golden/make_golden.py FROM THE ORACLE
+    (the reference cannot run here); it freezes the restatement against accidental change."""
+    import os
+    path = os.path.join(os.path.dirname(__file__), "golden", "oracle_small_fit.npz")
+    g = np.load(path)
+    for solver in (0, 1):
+        r = oracle.nmf_fit(g["indptr"], g["indices"], g["data"], int(g["m"]), int(g["n"]), int(g["k"]), g["W0"],
+                           g["H0"], max_iter=int(g["iters"]), tol=0.0, solver_mode=solver, L1=(0.01, 0.02),
+                           L2=(0.0, 0.01), threads=1)
+        assert np.array_equal(r.W_T, g[f"W_{solver}"]) and np.array_equal(r.H, g[f"H_{solver}"])
+        assert np.array_equal(r.d, g[f"d_{solver}"]) and np.array_equal(r.loss_history, g[f"loss_{solver}"])
