@@ -160,6 +160,12 @@ int rcppml_b200_get_profile(rcppml_b200_engine* e, double* ms /*[NUM_SECTIONS]*/
 int rcppml_b200_half_step(rcppml_b200_engine* e, const rcppml_b200_config* cfg, int which, int warm_start,
                           int normalize_after);
 
+/* Diagnostics: total CD sweeps of the last fit; host<->device bytes moved by the set/get calls; bitwise
+ * self-test of the FMA-corrected division the solvers use (must report 0 mismatches vs IEEE). */
+int64_t rcppml_b200_cd_sweeps(rcppml_b200_engine* e);
+int rcppml_b200_get_counters(rcppml_b200_engine* e, int64_t* h2d_bytes, int64_t* d2h_bytes);
+int rcppml_b200_selftest_division(int64_t n, uint64_t seed, int64_t* mismatches);
+
 /* Multi-GPU (one process per GPU). id is an ncclUniqueId (128 bytes) created on rank 0 and
  * distributed by the host launcher. After comm_init the engine's matrix is a column shard. */
 int rcppml_b200_nccl_unique_id(char* id128);

@@ -91,6 +91,7 @@ def load() -> C.CDLL:
     lib.rcppml_b200_half_step.argtypes = [E, C.POINTER(Config), C.c_int, C.c_int, C.c_int]
     lib.rcppml_b200_cd_sweeps.argtypes = [E]
     lib.rcppml_b200_cd_sweeps.restype = C.c_int64
+    lib.rcppml_b200_selftest_division.argtypes = [C.c_int64, C.c_uint64, C.POINTER(C.c_int64)]
     lib.rcppml_b200_get_counters.argtypes = [E, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     lib.rcppml_b200_nccl_unique_id.argtypes = [C.c_char_p]
     lib.rcppml_b200_comm_init.argtypes = [E, C.c_int, C.c_int, C.c_char_p]

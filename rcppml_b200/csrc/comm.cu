@@ -110,12 +110,13 @@ void Engine::enqueue_iteration_sharded() {
         p.col_offset = row_begin;
         p.cols_per_fetch = 8;
         p.work_counter = counters.ptr + 3;
+        const int geom = geometry_for(0, row_count);          // pure solve: two words per lane when available
         int grid = 0;
-        launch_half_step(LANES, solver, BSRC_LOAD, OUT_SOLVE, p, num_sms, stream, &grid);
+        launch_half_step(geom, solver, BSRC_LOAD, OUT_SOLVE, p, num_sms, stream, &grid);
         last_solve_grid = grid;
         sec_begin(RCPPML_B200_SEC_SOLVE_W);
         B200_CUDA_CHECK(cudaMemsetAsync(p.work_counter, 0, sizeof(int), stream));
-        launch_half_step(LANES, solver, BSRC_LOAD, OUT_SOLVE, p, num_sms, stream);
+        launch_half_step(geom, solver, BSRC_LOAD, OUT_SOLVE, p, num_sms, stream);
         launches[RCPPML_B200_SEC_SOLVE_W] += 1;
         sec_end(RCPPML_B200_SEC_SOLVE_W);
     }

@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -17,10 +18,10 @@ thread_local std::string g_last_error;
 // ---------------------------------------------------------------------------------------------
 // kernel dispatch by padded rank
 // ---------------------------------------------------------------------------------------------
-template <int LANES, int SOLVER, int BSRC, int OUT>
+template <int LANES, int NV, int SOLVER, int BSRC, int OUT>
 static void launch_half_step_t(const HalfStepParams& p, int num_sms, cudaStream_t stream, int* grid_out) {
-    auto kern = half_step_kernel<LANES, 1, SOLVER, BSRC, OUT>;
-    const size_t smem = half_step_smem_bytes<LANES, 1, SOLVER, OUT>();
+    auto kern = half_step_kernel<LANES, NV, SOLVER, BSRC, OUT>;
+    const size_t smem = half_step_smem_bytes<LANES, NV, SOLVER, OUT>();
     static thread_local int cached_occ = -1;
     if (cached_occ < 0) {
         B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -37,12 +38,15 @@ static void launch_half_step_t(const HalfStepParams& p, int num_sms, cudaStream_
 
 template <int SOLVER, int BSRC, int OUT>
 static void launch_half_step_l(int lanes, const HalfStepParams& p, int num_sms, cudaStream_t s, int* grid_out) {
+    // `lanes` encodes (LANES, NV) as LANES + 100*(NV-1): a lane owns NV 128-bit words of a factor row
     switch (lanes) {
-        case 4: launch_half_step_t<4, SOLVER, BSRC, OUT>(p, num_sms, s, grid_out); break;
-        case 8: launch_half_step_t<8, SOLVER, BSRC, OUT>(p, num_sms, s, grid_out); break;
-        case 16: launch_half_step_t<16, SOLVER, BSRC, OUT>(p, num_sms, s, grid_out); break;
-        case 32: launch_half_step_t<32, SOLVER, BSRC, OUT>(p, num_sms, s, grid_out); break;
-        default: throw std::runtime_error("unsupported lane-group width");
+        case 4: launch_half_step_t<4, 1, SOLVER, BSRC, OUT>(p, num_sms, s, grid_out); break;
+        case 8: launch_half_step_t<8, 1, SOLVER, BSRC, OUT>(p, num_sms, s, grid_out); break;
+        case 16: launch_half_step_t<16, 1, SOLVER, BSRC, OUT>(p, num_sms, s, grid_out); break;
+        case 32: launch_half_step_t<32, 1, SOLVER, BSRC, OUT>(p, num_sms, s, grid_out); break;
+        case 108: launch_half_step_t<8, 2, SOLVER, BSRC, OUT>(p, num_sms, s, grid_out); break;
+        case 116: launch_half_step_t<16, 2, SOLVER, BSRC, OUT>(p, num_sms, s, grid_out); break;
+        default: throw std::runtime_error("unsupported lane-group geometry");
     }
 }
 
@@ -63,10 +67,10 @@ void launch_half_step(int lanes, int solver, int bsrc, int out, const HalfStepPa
 static void launch_normalize_gram(int KP, float* X, long long ncols, const float* d, int normalize, double* partials,
                                   const int* stop, int grid, cudaStream_t s) {
     switch (KP) {
-        case 16: normalize_gram_kernel<16, 64><<<grid, 256, 0, s>>>(X, ncols, d, normalize, partials, stop); break;
-        case 32: normalize_gram_kernel<32, 64><<<grid, 256, 0, s>>>(X, ncols, d, normalize, partials, stop); break;
-        case 64: normalize_gram_kernel<64, 32><<<grid, 256, 0, s>>>(X, ncols, d, normalize, partials, stop); break;
-        case 128: normalize_gram_kernel<128, 32><<<grid, 256, 0, s>>>(X, ncols, d, normalize, partials, stop); break;
+        case 16: normalize_gram_kernel<16, 64><<<grid, kGramThreads, 0, s>>>(X, ncols, d, normalize, partials, stop); break;
+        case 32: normalize_gram_kernel<32, 64><<<grid, kGramThreads, 0, s>>>(X, ncols, d, normalize, partials, stop); break;
+        case 64: normalize_gram_kernel<64, 32><<<grid, kGramThreads, 0, s>>>(X, ncols, d, normalize, partials, stop); break;
+        case 128: normalize_gram_kernel<128, 32><<<grid, kGramThreads, 0, s>>>(X, ncols, d, normalize, partials, stop); break;
         default: throw std::runtime_error("unsupported padded rank");
     }
 }
@@ -224,6 +228,8 @@ void Engine::alloc_factors(int k_) {
     k = k_;
     LANES = lanes_for_rank(k);
     KP = padded_rank(k);
+    nv_override = 0;
+    if (const char* env = std::getenv("RCPPML_B200_NV")) nv_override = std::atoi(env);   // tuning knob (1 or 2)
     m_pad = ((m + world - 1) / world) * world;                  // equal row blocks for reduce-scatter / all-gather
     W_T.ensure(static_cast<size_t>(m_pad) * KP);
     B200_CUDA_CHECK(cudaMemsetAsync(W_T.ptr, 0, static_cast<size_t>(m_pad) * KP * sizeof(float), stream));
@@ -233,18 +239,22 @@ void Engine::alloc_factors(int k_) {
     G_h.ensure(static_cast<size_t>(KP) * KP);
     M1.ensure(static_cast<size_t>(KP) * KP);
     M2.ensure(static_cast<size_t>(KP) * KP);
-    diag.ensure(KP);
-    gram_grid = num_sms * 2;
+    dblk.ensure(static_cast<size_t>(KP) * 4);
+    rcp.ensure(KP);
+    gram_grid = num_sms * 4;
     gram_partials.ensure(static_cast<size_t>(gram_grid) * KP * KP);
+    B200_CUDA_CHECK(cudaMemsetAsync(gram_partials.ptr, 0, gram_partials.bytes(), stream));   // upper tiles are never written
     // the solve grid depends on the instantiation; size the partial buffers for the largest
     int gmax = 0;
     HalfStepParams dummy{};
     for (int solver = 0; solver < 2; ++solver) {
-        int g = 0;
-        launch_half_step(LANES, solver, BSRC_GATHER, OUT_SOLVE, dummy, num_sms, stream, &g);
-        gmax = std::max(gmax, g);
-        launch_half_step(LANES, solver, BSRC_LOAD, OUT_SOLVE, dummy, num_sms, stream, &g);
-        gmax = std::max(gmax, g);
+        for (int geom : {LANES, (KP == 64 || KP == 128) ? 100 + KP / 8 : LANES}) {
+            int g = 0;
+            launch_half_step(geom, solver, BSRC_GATHER, OUT_SOLVE, dummy, num_sms, stream, &g);
+            gmax = std::max(gmax, g);
+            launch_half_step(geom, solver, BSRC_LOAD, OUT_SOLVE, dummy, num_sms, stream, &g);
+            gmax = std::max(gmax, g);
+        }
     }
     solve_grid_max = gmax;
     solve_partials.ensure(static_cast<size_t>(gmax) * (KP + 1));
@@ -369,9 +379,24 @@ void Engine::prepare_solver(const float* G, float L2, int sec) {
         B200_CUDA_CHECK(cudaFuncSetAttribute(prepare_solver_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * 4));
         attr_set = true;
     }
-    prepare_solver_kernel<<<1, 128, smem, stream>>>(G, KP, k, L2, solver, M1.ptr, M2.ptr, diag.ptr, state.ptr);
+    prepare_solver_kernel<<<1, 128, smem, stream>>>(G, KP, k, L2, solver, M1.ptr, M2.ptr, dblk.ptr, rcp.ptr, state.ptr);
     launches[sec] += 1;
     sec_end(sec);
+}
+
+// Lane geometry per launch. A lane owns NV 128-bit words of a factor row. Short columns (few
+// non-zeros, the solve dominates) run faster with half as many lanes per column owning two words
+// each (twice the columns per warp share every pivot broadcast); long columns (gather dominates)
+// prefer one word per lane. Measured on B200 at k = 64: W-update (100 nnz/col) 3.78 -> 2.94 ms with
+// NV = 2, H-update (1000 nnz/col) 1.87 -> 1.97 ms.
+int Engine::geometry_for(long long nnz_, long long ncols) const {
+    int nv = 1;
+    if (KP == 64 || KP == 128) {
+        const double avg = ncols > 0 ? static_cast<double>(nnz_) / static_cast<double>(ncols) : 0.0;
+        nv = (avg < 400.0) ? 2 : 1;
+        if (nv_override == 1 || nv_override == 2) nv = nv_override;
+    }
+    return nv == 2 ? 100 + KP / 8 : LANES;
 }
 
 static int pick_cols_per_fetch(long long nnz, long long ncols) {
@@ -389,7 +414,7 @@ HalfStepParams Engine::solve_params(int which, bool warm) const {
     p.vals = h ? Ax.ptr : Atx.ptr;
     p.F = h ? W_T.ptr : H.ptr;
     p.X = h ? H.ptr : W_T.ptr;
-    p.M1 = M1.ptr; p.M2 = M2.ptr; p.diag = diag.ptr;
+    p.M1 = M1.ptr; p.M2 = M2.ptr; p.dblk = dblk.ptr; p.rcp = rcp.ptr;
     p.B = nullptr; p.nslots = 0; p.slot_stride = 0;
     p.ncols = h ? n : m;
     p.col_offset = 0;
@@ -415,12 +440,13 @@ HalfStepParams Engine::solve_params(int which, bool warm) const {
 void Engine::solve(int which, bool warm, int sec) {
     HalfStepParams p = solve_params(which, warm);
     const int solver = cfg.solver_mode == 0 ? SOLVER_CD : SOLVER_CHOL;
+    const int geom = geometry_for(nnz, p.ncols);
     int grid = 0;
-    launch_half_step(LANES, solver, BSRC_GATHER, OUT_SOLVE, p, num_sms, stream, &grid);
+    launch_half_step(geom, solver, BSRC_GATHER, OUT_SOLVE, p, num_sms, stream, &grid);
     last_solve_grid = grid;
     sec_begin(sec);
     B200_CUDA_CHECK(cudaMemsetAsync(p.work_counter, 0, sizeof(int), stream));
-    launch_half_step(LANES, solver, BSRC_GATHER, OUT_SOLVE, p, num_sms, stream);
+    launch_half_step(geom, solver, BSRC_GATHER, OUT_SOLVE, p, num_sms, stream);
     launches[sec] += 1;
     sec_end(sec);
 }
@@ -660,6 +686,19 @@ int rcppml_b200_get_profile(rcppml_b200_engine* e, double* ms, int* launches) {
 }
 int rcppml_b200_half_step(rcppml_b200_engine* e, const rcppml_b200_config* cfg, int which, int warm_start, int normalize_after) {
     B200_API_BEGIN e->impl.half_step_only(*cfg, which, warm_start != 0, normalize_after != 0); B200_API_END
+}
+// Bitwise check of the FMA-corrected division used by the solvers against __fdiv_rn.
+int rcppml_b200_selftest_division(int64_t n, uint64_t seed, int64_t* mismatches) {
+    B200_API_BEGIN
+    unsigned long long* d_bad = nullptr;
+    B200_CUDA_CHECK(cudaMalloc(&d_bad, sizeof(unsigned long long)));
+    B200_CUDA_CHECK(cudaMemset(d_bad, 0, sizeof(unsigned long long)));
+    b200::selftest_division_kernel<<<148 * 8, 256>>>(n, seed, d_bad);
+    unsigned long long bad = 0;
+    B200_CUDA_CHECK(cudaMemcpy(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost));
+    cudaFree(d_bad);
+    *mismatches = static_cast<int64_t>(bad);
+    B200_API_END
 }
 int64_t rcppml_b200_cd_sweeps(rcppml_b200_engine* e) { return static_cast<int64_t>(e->impl.cd_sweeps); }
 int rcppml_b200_get_counters(rcppml_b200_engine* e, int64_t* h2d_bytes, int64_t* d2h_bytes) {

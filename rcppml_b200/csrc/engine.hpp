@@ -65,9 +65,10 @@ public:
     float trAtA = 0.f;          // global tr(AᵀA) (summed over ranks after comm_init)
     double trAtA_local = 0.0;
 
-    int k = 0, KP = 0, LANES = 0;
+    int k = 0, KP = 0, LANES = 0, nv_override = 0;
+    int geometry_for(long long nnz, long long ncols) const;
     DeviceBuffer<float> W_T, H, d;
-    DeviceBuffer<float> G_w, G_h, M1, M2, diag;
+    DeviceBuffer<float> G_w, G_h, M1, M2, dblk, rcp;
     DeviceBuffer<double> gram_partials, solve_partials;   // per-CTA partials (fixed-order reductions)
     DeviceBuffer<double> red_gram, red_small;             // reduced sums: k×k Gram | k row sums + cross term
     DeviceBuffer<int> counters;

@@ -27,27 +27,39 @@ struct DevState {
 
 // ---------------------------------------------------------------------------------------------
 // normalize + Gram. X is [ncols][KP] (row c = column c of the reference's k×ncols matrix).
-// 256 threads as a 16×16 grid, each owning an R×R tile of G (R = KP/16). Column tiles of TC
-// columns are staged in shared memory; products and sums are fp64 (see below).
+// G is symmetric: only the 136 lower-triangular R×R tiles of the 16×16 tile grid are computed
+// (R = KP/16), one per thread (160 threads = 5 warps, 24 idle lanes). Column tiles of TC columns are
+// staged in shared memory ALREADY CONVERTED to fp64 (one F2F per element per tile instead of one per
+// element per column per thread); the inner loop is LDS.64/128 + DFMA only.
 // ---------------------------------------------------------------------------------------------
+constexpr int kGramThreads = 160;
+
 template <int KP, int TC>
-static __global__ void __launch_bounds__(256) normalize_gram_kernel(float* __restrict__ X, long long ncols,
+static __global__ void __launch_bounds__(kGramThreads) normalize_gram_kernel(float* __restrict__ X, long long ncols,
                                                              const float* __restrict__ d, int normalize,
                                                              double* __restrict__ partials,
                                                              const int* __restrict__ stop_flag) {
     constexpr int R = KP / 16;
     constexpr int V4 = KP / 4;                       // float4 per column
-    __shared__ __align__(16) float sX[TC][KP];
+    __shared__ __align__(16) double sX[TC][KP];
     __shared__ float sD[KP];
     if (*stop_flag) return;
     for (int t = threadIdx.x; t < KP; t += blockDim.x) sD[t] = normalize ? d[t] : 1.f;
     __syncthreads();
 
-    const int ti = threadIdx.x / 16, tj = threadIdx.x % 16;
+    // thread -> lower-triangular tile (ti >= tj): t = ti(ti+1)/2 + tj
+    int ti = 0, tj = 0;
+    const bool active = threadIdx.x < 136;
+    if (active) {
+        int t = threadIdx.x;
+        while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+        tj = t - ti * (ti + 1) / 2;
+    }
     // fp64 accumulation of exact fp32×fp32 products: the result, rounded once to fp32 by
-    // gram_reduce_kernel, is the order-independent "correctly rounded" Gram the oracle defines
-    // (oracle/nmf_oracle.cpp gram()). B200 runs DFMA at half the FFMA rate, the Gram is <5 % of
-    // an iteration, and a G that matches bit for bit keeps every column solve bit-identical.
+    // gram_from_sums_kernel, is the order-independent "correctly rounded" Gram the oracle defines
+    // (oracle/nmf_oracle.cpp gram()). A G that matches bit for bit keeps every column solve
+    // bit-identical to the CPU path; B200 runs DFMA at half the FFMA rate and the Gram is a few
+    // percent of an iteration.
     double acc[R][R];
 #pragma unroll
     for (int a = 0; a < R; ++a)
@@ -73,29 +85,35 @@ static __global__ void __launch_bounds__(256) normalize_gram_kernel(float* __res
                     X4[t] = v;
                 }
             }
-            *reinterpret_cast<float4*>(&sX[c][q * 4]) = v;
+            double2* dst = reinterpret_cast<double2*>(&sX[c][q * 4]);
+            dst[0] = make_double2(static_cast<double>(v.x), static_cast<double>(v.y));
+            dst[1] = make_double2(static_cast<double>(v.z), static_cast<double>(v.w));
         }
         __syncthreads();
+        if (active) {
 #pragma unroll 2
-        for (int c = 0; c < TC; ++c) {
-            double av[R], bv[R];
+            for (int c = 0; c < TC; ++c) {
+                double av[R], bv[R];
 #pragma unroll
-            for (int a = 0; a < R; ++a) av[a] = static_cast<double>(sX[c][ti * R + a]);
+                for (int a = 0; a < R; ++a) av[a] = sX[c][ti * R + a];
 #pragma unroll
-            for (int b = 0; b < R; ++b) bv[b] = static_cast<double>(sX[c][tj * R + b]);
+                for (int b = 0; b < R; ++b) bv[b] = sX[c][tj * R + b];
 #pragma unroll
-            for (int a = 0; a < R; ++a)
+                for (int a = 0; a < R; ++a)
 #pragma unroll
-                for (int b = 0; b < R; ++b) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+                    for (int b = 0; b < R; ++b) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+            }
         }
         __syncthreads();
     }
-    double* out = partials + static_cast<size_t>(blockIdx.x) * KP * KP;
+    if (active) {
+        double* out = partials + static_cast<size_t>(blockIdx.x) * KP * KP;
 #pragma unroll
-    for (int a = 0; a < R; ++a)
+        for (int a = 0; a < R; ++a)
 #pragma unroll
-        for (int b = 0; b < R; ++b)
-            out[(tj * R + b) * KP + (ti * R + a)] = acc[a][b];   // G(i,j) at [j*KP+i]
+            for (int b = 0; b < R; ++b)
+                out[(tj * R + b) * KP + (ti * R + a)] = acc[a][b];   // G(i,j), i >= j tile-wise, at [j*KP+i]
+    }
 }
 
 // out[e] = Σ_c partials[c][e] in a FIXED order: 8 interleaved slices per element (slice s takes
@@ -134,13 +152,17 @@ static __global__ void gram_from_sums_kernel(const double* __restrict__ sums, in
     G[e] = v;
 }
 
-// One CTA. CD: M1 = G + L2·I, diag = diag(M1) (0 on padding). CHOL: unblocked left-looking LLT
-// in the oracle's order (dot accumulated sequentially, then subtracted, IEEE sqrt/div):
-// M1 = strictly-lower L (col-major), M2[p*KP+i] = L(p,i) (i<p), diag = diag(L).
+// One CTA. Builds the k×k operands of the solve kernel from G (+ L2·I, fit_cpu.hpp:506,738):
+//   CD  : M1 = G (+L2·I), rcp = RN(1/G_ii) (0 if G_ii <= 0)
+//   CHOL: unblocked left-looking LLT in the oracle's order (dot accumulated sequentially, then
+//         subtracted, IEEE sqrt/div — fused_nnls.hpp:185 restated); M1 = strictly-lower L (col-major),
+//         M2[p*KP+i] = L(p,i) (i<p), both with the diagonal blocks zeroed; dblk = diagonal blocks of L
+//         (lower triangle incl. diagonal, [q][row][col]); rcp = RN(1/L_pp).
+// Padded pivots get dblk diagonal 1 (CHOL) / 0 (CD) so that they solve to 0 / are skipped.
 static __global__ void __launch_bounds__(128) prepare_solver_kernel(const float* __restrict__ G, int KP, int k, float L2,
                                                             int solver, float* __restrict__ M1,
-                                                            float* __restrict__ M2, float* __restrict__ diag,
-                                                            DevState* __restrict__ st) {
+                                                            float* __restrict__ M2, float* __restrict__ dblk,
+                                                            float* __restrict__ rcp, DevState* __restrict__ st) {
     extern __shared__ float sL[];          // KP*KP, col-major working copy
     if (st->stop) return;
     const int tid = threadIdx.x;
@@ -151,47 +173,60 @@ static __global__ void __launch_bounds__(128) prepare_solver_kernel(const float*
         sL[e] = v;
     }
     __syncthreads();
-    if (solver == 0) {
-        for (int e = tid; e < KP * KP; e += blockDim.x) M1[e] = sL[e];
-        for (int i = tid; i < KP; i += blockDim.x) diag[i] = sL[i * KP + i];
-        return;
-    }
-    // Left-looking Cholesky, thread i owns row i. sL is overwritten column by column (lower part).
-    for (int j = 0; j < k; ++j) {
-        float ljj = 0.f;
-        {   // every thread recomputes the pivot redundantly (broadcast reads) -> no extra barrier
-            float s = 0.f;
-            for (int p = 0; p < j; ++p) {
-                const float l = sL[p * KP + j];
-                s = __fadd_rn(s, __fmul_rn(l, l));
+    if (solver != 0) {
+        // Left-looking Cholesky, thread i owns row i. sL is overwritten column by column (lower part).
+        for (int j = 0; j < k; ++j) {
+            float ljj = 0.f;
+            {   // every thread recomputes the pivot redundantly (broadcast reads) -> no extra barrier
+                float s = 0.f;
+                for (int p = 0; p < j; ++p) {
+                    const float l = sL[p * KP + j];
+                    s = __fadd_rn(s, __fmul_rn(l, l));
+                }
+                const float x = __fsub_rn(sL[j * KP + j], s);
+                if (!(x > 0.f)) {
+                    if (tid == 0 && st->chol_fail == 0) st->chol_fail = j + 1;
+                    ljj = 0.f;
+                } else {
+                    ljj = __fsqrt_rn(x);
+                }
             }
-            const float x = __fsub_rn(sL[j * KP + j], s);
-            if (!(x > 0.f)) {
-                if (tid == 0 && st->chol_fail == 0) st->chol_fail = j + 1;
-                ljj = 0.f;
-            } else {
-                ljj = __fsqrt_rn(x);
+            const int i = tid;
+            float lij = 0.f;
+            if (i > j && i < k) {
+                float t = 0.f;
+                for (int p = 0; p < j; ++p) t = __fadd_rn(t, __fmul_rn(sL[p * KP + i], sL[p * KP + j]));
+                lij = __fdiv_rn(__fsub_rn(sL[j * KP + i], t), ljj);
             }
+            __syncthreads();                   // all reads of column j (as G) done
+            if (i > j && i < k) sL[j * KP + i] = lij;
+            if (i == j) sL[j * KP + j] = ljj;
+            __syncthreads();
         }
-        const int i = tid;
-        float lij = 0.f;
-        if (i > j && i < k) {
-            float t = 0.f;
-            for (int p = 0; p < j; ++p) t = __fadd_rn(t, __fmul_rn(sL[p * KP + i], sL[p * KP + j]));
-            lij = __fdiv_rn(__fsub_rn(sL[j * KP + i], t), ljj);
-        }
-        __syncthreads();                   // all reads of column j (as G) done
-        if (i > j && i < k) sL[j * KP + i] = lij;
-        if (i == j) sL[j * KP + j] = ljj;
-        __syncthreads();
     }
     for (int e = tid; e < KP * KP; e += blockDim.x) {
         const int i = e % KP, j = e / KP;                  // e = j*KP + i  -> element (row i, col j)
-        M1[e] = (i > j && i < k) ? sL[e] : 0.f;            // strictly lower, col-major
-        // M2[p*KP + c] = L(p, c) for c < p: take p = j (slot row), c = i
-        M2[e] = (i < j && j < k) ? sL[i * KP + j] : 0.f;
+        const bool in_block = (i / 4) == (j / 4);
+        if (solver == 0) {
+            M1[e] = sL[e];
+        } else {
+            M1[e] = (i > j && i < k && !in_block) ? sL[e] : 0.f;            // strictly lower, col-major
+            // M2[p*KP + c] = L(p, c) for c < p: slot row p = j, c = i
+            M2[e] = (i < j && j < k && !in_block) ? sL[i * KP + j] : 0.f;
+        }
     }
-    for (int i = tid; i < KP; i += blockDim.x) diag[i] = (i < k) ? sL[i * KP + i] : 1.f;
+    for (int e = tid; e < KP * 4; e += blockDim.x) {        // dblk[q][a][b] = M(4q+a, 4q+b)
+        const int q = e / 16, a = (e / 4) % 4, b = e % 4;
+        const int i = q * 4 + a, j = q * 4 + b;
+        float v;
+        if (solver == 0) v = (i < k && j < k) ? sL[j * KP + i] : 0.f;
+        else v = (i < k && j < k) ? ((j <= i) ? sL[j * KP + i] : 0.f) : ((i == j) ? 1.f : 0.f);
+        dblk[e] = v;
+    }
+    for (int i = tid; i < KP; i += blockDim.x) {
+        const float dg = (i < k) ? sL[i * KP + i] : ((solver == 0) ? 0.f : 1.f);
+        rcp[i] = (dg > 0.f) ? __frcp_rn(dg) : 0.f;
+    }
 }
 
 // d_i = float(sums_i) (+sqrt for L2) + 1e-15 (variant_helpers.hpp:297-301); padded d_i = 1.

@@ -30,9 +30,11 @@ struct HalfStepParams {
     // dense operands, leading dimension KP (zero padded)
     const float* __restrict__ F;       // gathered factor [rows][KP]
     float* __restrict__ X;             // solution        [ncols][KP] (in: warm start, out: x)
-    const float* __restrict__ M1;      // CD: G(+L2) col-major | CHOL: strictly-lower L col-major
-    const float* __restrict__ M2;      // CHOL: LT[p*KP+i] = L(p,i) for i<p, else 0
-    const float* __restrict__ diag;    // CD: diag(G)          | CHOL: diag(L)
+    // k×k operands prepared by prepare_solver_kernel; "z" = 4×4 diagonal blocks zeroed (CHOL only)
+    const float* __restrict__ M1;      // CD: G+L2·I (col-major, full) | CHOL: Lz (strictly-lower L, col-major)
+    const float* __restrict__ M2;      // CHOL: LTz[p*KP+i] = L(p,i) for i<p
+    const float* __restrict__ dblk;    // [KP/4][4][4] diagonal blocks (CD: of G; CHOL: of L incl. diagonal)
+    const float* __restrict__ rcp;     // [KP] RN(1/diag) (0 where the diagonal is <= 0)
     // BSRC_LOAD / OUT_RHS: dense right-hand sides [nslots][ncols][KP]
     float* __restrict__ B;
     int nslots;
@@ -90,7 +92,7 @@ template <int LANES, int NV>
 __device__ __forceinline__ void gather_column(const HalfStepParams& p, int p0, int p1, int gl, unsigned gmask,
                                               float (&b)[NV][4]) {
     constexpr int KP = LANES * 4 * NV;
-    constexpr int UN = (LANES < 8) ? LANES : 8;
+    constexpr int UN = (LANES * NV <= 8) ? LANES : (8 / NV > 0 ? 8 / NV : 1);   // 128-bit loads in flight: 8 per lane
 #pragma unroll
     for (int nv = 0; nv < NV; ++nv)
 #pragma unroll
@@ -102,6 +104,7 @@ __device__ __forceinline__ void gather_column(const HalfStepParams& p, int p0, i
         nidx = __ldg(p.rowidx + p0 + gl);
         nval = __ldg(p.vals + p0 + gl);
     }
+    const float4* Fl = reinterpret_cast<const float4*>(p.F) + gl;
     for (int base = p0; base < p1; base += LANES) {
         const int ridx = nidx;
         const float rval = nval;
@@ -112,32 +115,53 @@ __device__ __forceinline__ void gather_column(const HalfStepParams& p, int p0, i
             nidx = __ldg(p.rowidx + nb);
             nval = __ldg(p.vals + nb);
         }
-        const int cnt = min(LANES, p1 - base);
+        const int cnt = p1 - base;
+        if (cnt >= LANES) {                          // full batch: no predication at all
 #pragma unroll
-        for (int s = 0; s < LANES; s += UN) {
-            if (s < cnt) {
+            for (int s = 0; s < LANES; s += UN) {
                 float4 f[UN][NV];
                 float v[UN];
 #pragma unroll
                 for (int u = 0; u < UN; ++u) {
                     const int r = gshfl<LANES>(gmask, ridx, s + u);
                     v[u] = gshfl<LANES>(gmask, rval, s + u);
-                    if (s + u < cnt) {
-                        const float4* row = reinterpret_cast<const float4*>(p.F + static_cast<size_t>(r) * KP);
+                    const float4* row = Fl + static_cast<size_t>(r) * (KP / 4);
 #pragma unroll
-                        for (int nv = 0; nv < NV; ++nv) f[u][nv] = __ldg(row + nv * LANES + gl);
-                    } else {
-#pragma unroll
-                        for (int nv = 0; nv < NV; ++nv) f[u][nv] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
+                    for (int nv = 0; nv < NV; ++nv) f[u][nv] = __ldg(row + nv * LANES);
                 }
 #pragma unroll
                 for (int u = 0; u < UN; ++u)
 #pragma unroll
-                    for (int nv = 0; nv < NV; ++nv) axpy4(b[nv], v[u], f[u][nv]);   // tail: v = 0, f = 0 -> exact no-op
+                    for (int nv = 0; nv < NV; ++nv) axpy4(b[nv], v[u], f[u][nv]);
+            }
+        } else {                                     // ragged tail (< LANES entries), element by element
+            for (int s = 0; s < cnt; ++s) {
+                const int r = gshfl<LANES>(gmask, ridx, s);
+                const float v = gshfl<LANES>(gmask, rval, s);
+                const float4* row = Fl + static_cast<size_t>(r) * (KP / 4);
+#pragma unroll
+                for (int nv = 0; nv < NV; ++nv) axpy4(b[nv], v, __ldg(row + nv * LANES));
             }
         }
     }
+}
+
+// IEEE-exact a/d from a correctly rounded reciprocal r = RN(1/d): two FMA correction steps
+// (Markstein): after the first q is faithful, after the second it is the correctly rounded
+// quotient. 5 instructions instead of the ~15 (MUFU + slow path) of a generic __fdiv_rn; the
+// guard hands results outside the comfortable exponent range to __fdiv_rn. Verified bit for bit
+// against __fdiv_rn by rcppml_b200_selftest_division (tests/test_gpu_parity.py).
+__device__ __forceinline__ float div_exact(float a, float d, float r) {
+    float q = __fmul_rn(a, r);
+    float e = __fmaf_rn(-d, q, a);
+    q = __fmaf_rn(e, r, q);
+    e = __fmaf_rn(-d, q, a);
+    q = __fmaf_rn(e, r, q);
+    const float aq = fabsf(q);
+    if (!(aq > 1e-30f && aq < 1e30f)) {
+        if (a != 0.f) q = __fdiv_rn(a, d);
+    }
+    return q;
 }
 
 // b -= G·x restated as tmp = Σ_i G(:,i)·x_i (sequential in i), b -= tmp  (fused_nnls.hpp:121-123).
@@ -178,7 +202,7 @@ __device__ __forceinline__ void warm_start_correct(const float* sG, int k, int g
 
 // cd_nnls_col_fixed (nnls_batch.hpp:71-132) with L1 = L2 = upper_bound = 0 as the fused path calls it.
 template <int LANES, int NV>
-__device__ __forceinline__ int cd_solve(const HalfStepParams& p, const float* sG, const float* sDiag, int gl,
+__device__ __forceinline__ int cd_solve(const HalfStepParams& p, const float* sG, const float* sRcp, int gl,
                                         unsigned gmask, float (&x)[NV][4], float (&b)[NV][4]) {
     constexpr int KP = LANES * 4 * NV;
     const float4* sG4 = reinterpret_cast<const float4*>(sG);
@@ -199,10 +223,10 @@ __device__ __forceinline__ int cd_solve(const HalfStepParams& p, const float* sG
                     const int i = i0 + e;
                     const float bi = gshfl<LANES>(gmask, b[nv][e], owner);
                     const float xi = gshfl<LANES>(gmask, x[nv][e], owner);
-                    const float gd = sDiag[i];                     // 0 for padded coordinates
+                    const float gd = sG[i * KP + i];               // 0 for padded coordinates
                     float ad = 0.f, xn = xi;
                     if (gd > 0.f) {                                // :90
-                        const float diff = __fdiv_rn(bi, gd);      // :92
+                        const float diff = div_exact(bi, gd, sRcp[i]);   // :92
                         const float nval = __fadd_rn(xi, diff);    // :97
                         if (nonneg && nval < 0.f) {                // :100-103
                             ad = -xi;
@@ -233,61 +257,95 @@ __device__ __forceinline__ int cd_solve(const HalfStepParams& p, const float* sG
     return sweeps;
 }
 
-// x = L⁻ᵀ L⁻¹ b, column-oriented substitution with IEEE division (Eigen LLT::solve restated,
-// fused_nnls.hpp:210). On exit b holds x.
+// x = L⁻ᵀ L⁻¹ b, column-oriented substitution with IEEE-exact division (Eigen LLT::solve restated,
+// fused_nnls.hpp:210), blocked by 4 pivots like cd_solve. sLz / sLTz: strictly-lower L (col-major)
+// and its rows (LT[p*KP+i] = L(p,i)) with the 4×4 diagonal blocks zeroed; sDblk: the diagonal
+// blocks [q][row][col] (lower triangle incl. the diagonal); sRcp: RN(1/L_pp). On exit b holds x.
 template <int LANES, int NV>
-__device__ __forceinline__ void chol_solve(const float* sLs, const float* sLT, const float* sDiag, int k, int gl,
-                                           unsigned gmask, float (&b)[NV][4]) {
+__device__ __forceinline__ void chol_solve(const float* sLz, const float* sLTz, const float* sDblk,
+                                           const float* sRcp, int k, int gl, unsigned gmask, float (&b)[NV][4]) {
     constexpr int KP = LANES * 4 * NV;
-    const float4* sLs4 = reinterpret_cast<const float4*>(sLs);
-    const float4* sLT4 = reinterpret_cast<const float4*>(sLT);
+    const float4* sL4 = reinterpret_cast<const float4*>(sLz);
+    const float4* sLT4 = reinterpret_cast<const float4*>(sLTz);
+    const float4* sD4 = reinterpret_cast<const float4*>(sDblk);
+    const float4* sR4 = reinterpret_cast<const float4*>(sRcp);
     // forward: L y = b
 #pragma unroll
     for (int nv = 0; nv < NV; ++nv) {
 #pragma unroll 1
         for (int owner = 0; owner < LANES; ++owner) {
-            const int i0 = (nv * LANES + owner) * 4;
-            if (i0 >= k) break;
+            const int q = nv * LANES + owner;
+            if (q * 4 >= k) break;
+            float t[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) t[e] = gshfl<LANES>(gmask, b[nv][e], owner);
+            const float4 d1 = sD4[q * 4 + 1], d2 = sD4[q * 4 + 2], d3 = sD4[q * 4 + 3];
+            const float d00 = sDblk[q * 16];
+            const float4 r = sR4[q];
+            float y[4];
+            y[0] = div_exact(t[0], d00, r.x);
+            t[1] = __fsub_rn(t[1], __fmul_rn(d1.x, y[0]));
+            y[1] = div_exact(t[1], d1.y, r.y);
+            t[2] = __fsub_rn(t[2], __fmul_rn(d2.x, y[0]));
+            t[2] = __fsub_rn(t[2], __fmul_rn(d2.y, y[1]));
+            y[2] = div_exact(t[2], d2.z, r.z);
+            t[3] = __fsub_rn(t[3], __fmul_rn(d3.x, y[0]));
+            t[3] = __fsub_rn(t[3], __fmul_rn(d3.y, y[1]));
+            t[3] = __fsub_rn(t[3], __fmul_rn(d3.z, y[2]));
+            y[3] = div_exact(t[3], d3.w, r.w);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const int pi = i0 + e;
-                const float bp = gshfl<LANES>(gmask, b[nv][e], owner);
-                if (pi < k) {
-                    const float y = __fdiv_rn(bp, sDiag[pi]);
-                    if (gl == owner) b[nv][e] = y;
 #pragma unroll
-                    for (int nv2 = 0; nv2 < NV; ++nv2) {
-                        if (nv2 >= nv) {                            // rows above the pivot block are zero
-                            const float4 l = sLs4[pi * (KP / 4) + nv2 * LANES + gl];
-                            sub_scaled4(b[nv2], l, y);              // strictly lower: rows <= p untouched
-                        }
+                for (int nv2 = 0; nv2 < NV; ++nv2) {
+                    if (nv2 >= nv) {                                // rows above the pivot block are zero
+                        const float4 l = sL4[(q * 4 + e) * (KP / 4) + nv2 * LANES + gl];
+                        sub_scaled4(b[nv2], l, y[e]);               // zero on rows <= block: exact no-op
                     }
                 }
             }
+            if (gl == owner) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) b[nv][e] = y[e];
+            }
         }
     }
-    // backward: Lᵀ x = y
+    // backward: Lᵀ x = y   (pivots descending; within a block rows 3,2,1,0)
 #pragma unroll
     for (int nv = NV - 1; nv >= 0; --nv) {
 #pragma unroll 1
         for (int owner = LANES - 1; owner >= 0; --owner) {
-            const int i0 = (nv * LANES + owner) * 4;
-            if (i0 >= k) continue;
+            const int q = nv * LANES + owner;
+            if (q * 4 >= k) continue;
+            float t[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) t[e] = gshfl<LANES>(gmask, b[nv][e], owner);
+            const float4 d1 = sD4[q * 4 + 1], d2 = sD4[q * 4 + 2], d3 = sD4[q * 4 + 3];
+            const float d00 = sDblk[q * 16];
+            const float4 r = sR4[q];
+            float x[4];
+            x[3] = div_exact(t[3], d3.w, r.w);
+            t[2] = __fsub_rn(t[2], __fmul_rn(d3.z, x[3]));      // y_i -= L(p,i)·x_p for i < p
+            t[1] = __fsub_rn(t[1], __fmul_rn(d3.y, x[3]));
+            t[0] = __fsub_rn(t[0], __fmul_rn(d3.x, x[3]));
+            x[2] = div_exact(t[2], d2.z, r.z);
+            t[1] = __fsub_rn(t[1], __fmul_rn(d2.y, x[2]));
+            t[0] = __fsub_rn(t[0], __fmul_rn(d2.x, x[2]));
+            x[1] = div_exact(t[1], d1.y, r.y);
+            t[0] = __fsub_rn(t[0], __fmul_rn(d1.x, x[1]));
+            x[0] = div_exact(t[0], d00, r.x);
 #pragma unroll
             for (int e = 3; e >= 0; --e) {
-                const int pi = i0 + e;
-                const float yp = gshfl<LANES>(gmask, b[nv][e], owner);
-                if (pi < k) {
-                    const float xp = __fdiv_rn(yp, sDiag[pi]);
-                    if (gl == owner) b[nv][e] = xp;
 #pragma unroll
-                    for (int nv2 = 0; nv2 < NV; ++nv2) {
-                        if (nv2 <= nv) {
-                            const float4 l = sLT4[pi * (KP / 4) + nv2 * LANES + gl];
-                            sub_scaled4(b[nv2], l, xp);
-                        }
+                for (int nv2 = 0; nv2 < NV; ++nv2) {
+                    if (nv2 <= nv) {
+                        const float4 l = sLT4[(q * 4 + e) * (KP / 4) + nv2 * LANES + gl];
+                        sub_scaled4(b[nv2], l, x[e]);
                     }
                 }
+            }
+            if (gl == owner) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) b[nv][e] = x[e];
             }
         }
     }
@@ -309,8 +367,9 @@ __global__ void __launch_bounds__(256) half_step_kernel(const HalfStepParams p) 
 
     float* sM1 = smem;
     float* sM2 = smem + ((OUT == OUT_SOLVE) ? KP * KP : 0);
-    float* sDiag = sM2 + ((OUT == OUT_SOLVE && SOLVER == SOLVER_CHOL) ? KP * KP : 0);
-    double* sRed = reinterpret_cast<double*>(sDiag + KP);    // [256/LANES][KP] norms + [256] cross; 8-byte aligned (KP % 16 == 0)
+    float* sDblk = sM2 + ((OUT == OUT_SOLVE && SOLVER == SOLVER_CHOL) ? KP * KP : 0);
+    float* sRcp = sDblk + KP * 4;
+    double* sRed = reinterpret_cast<double*>(sRcp + KP);     // [256/LANES][KP] norms + [256] cross; 8-byte aligned (KP % 16 == 0)
 
     if (OUT == OUT_SOLVE) {
         const float4* g4 = reinterpret_cast<const float4*>(p.M1);
@@ -321,7 +380,8 @@ __global__ void __launch_bounds__(256) half_step_kernel(const HalfStepParams p) 
             float4* t4 = reinterpret_cast<float4*>(sM2);
             for (int t = threadIdx.x; t < KP * KP / 4; t += blockDim.x) t4[t] = l4[t];
         }
-        for (int t = threadIdx.x; t < KP; t += blockDim.x) sDiag[t] = p.diag[t];
+        for (int t = threadIdx.x; t < KP * 4; t += blockDim.x) sDblk[t] = p.dblk[t];
+        for (int t = threadIdx.x; t < KP; t += blockDim.x) sRcp[t] = p.rcp[t];
     }
     __syncthreads();
 
@@ -408,9 +468,9 @@ __global__ void __launch_bounds__(256) half_step_kernel(const HalfStepParams p) 
                     x[nv][0] = xv.x; x[nv][1] = xv.y; x[nv][2] = xv.z; x[nv][3] = xv.w;
                 }
                 if (p.warm) warm_start_correct<LANES, NV>(sM1, p.k, gl, gmask, x, b);
-                my_sweeps += cd_solve<LANES, NV>(p, sM1, sDiag, gl, gmask, x, b);
+                my_sweeps += cd_solve<LANES, NV>(p, sM1, sRcp, gl, gmask, x, b);
             } else {
-                chol_solve<LANES, NV>(sM1, sM2, sDiag, p.k, gl, gmask, b);
+                chol_solve<LANES, NV>(sM1, sM2, sDblk, sRcp, p.k, gl, gmask, b);
 #pragma unroll
                 for (int nv = 0; nv < NV; ++nv)
 #pragma unroll
@@ -490,9 +550,32 @@ __global__ void __launch_bounds__(256) half_step_kernel(const HalfStepParams p) 
 template <int LANES, int NV, int SOLVER, int OUT>
 inline size_t half_step_smem_bytes() {
     constexpr int KP = LANES * 4 * NV;
-    size_t f = KP;                                           // diag
+    size_t f = KP * 5;                                       // diagonal blocks + reciprocals
     if (OUT == OUT_SOLVE) f += static_cast<size_t>(KP) * KP * (SOLVER == SOLVER_CHOL ? 2 : 1);
     return f * sizeof(float) + (static_cast<size_t>(256 / LANES) * KP + 256) * sizeof(double);
+}
+
+// Self-test: div_exact vs __fdiv_rn on pseudo-random operands (normal range), bitwise.
+static __global__ void selftest_division_kernel(long long n, unsigned long long seed,
+                                                unsigned long long* __restrict__ mismatches) {
+    unsigned long long bad = 0;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        unsigned long long z = seed + static_cast<unsigned long long>(i + 1) * 0x9e3779b97f4a7c15ULL;
+        z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+        z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+        z ^= z >> 31;
+        // random mantissas/signs, exponents within 2^±20 of 1.0; every 4th sample uses near-1 mantissas
+        unsigned ma = static_cast<unsigned>(z) & 0x007fffffu, md = static_cast<unsigned>(z >> 23) & 0x007fffffu;
+        if ((i & 3) == 3) { ma |= 0x007ff000u; md &= 0x00000fffu; }
+        const unsigned ea = 107u + (static_cast<unsigned>(z >> 46) % 41u), ed = 107u + (static_cast<unsigned>(z >> 52) % 41u);
+        const float a = __uint_as_float(((static_cast<unsigned>(z >> 63) & 1u) << 31) | (ea << 23) | ma);
+        const float d = __uint_as_float((ed << 23) | md);
+        const float want = __fdiv_rn(a, d);
+        const float got = div_exact(a, d, __frcp_rn(d));
+        if (__float_as_uint(want) != __float_as_uint(got)) ++bad;
+    }
+    if (bad) atomicAdd(mismatches, bad);
 }
 
 }  // namespace b200

@@ -24,6 +24,15 @@ def test_detect_reports_b200():
     assert info["total_mem_mb"][0] > 100_000
 
 
+def test_fma_division_is_ieee_exact():
+    """The solvers divide with two FMA corrections of a*RN(1/d); must equal __fdiv_rn bit for bit."""
+    import ctypes as C
+    from rcppml_b200 import _lib
+    bad = C.c_int64(-1)
+    _lib.check(_lib.load().rcppml_b200_selftest_division(2_000_000_000, 12345, C.byref(bad)), "selftest")
+    assert bad.value == 0, bad.value
+
+
 def test_synthetic_generator_bit_exact(eng):
     from rcppml_b200 import synth
     for (m, n_local, col_begin, dens) in [(5000, 300, 0, 0.01), (20000, 128, 77, 0.05), (100000, 64, 5, 0.03)]:
