@@ -131,11 +131,23 @@ int rcppml_b200_set_matrix_f64(rcppml_b200_engine* e, int m, int n, int64_t nnz,
  * SplitMix64::hash(seed, t, j) mod m, sorted + deduplicated; value 0.5 + uniform<float>(seed+1, r, j). */
 int rcppml_b200_set_matrix_synthetic(rcppml_b200_engine* e, int m, int n_local, int col_begin, double density,
                                      uint64_t seed);
-/* Copies the device CSC back (for checking the generator). Pass NULL to skip an array. */
+/* Sharded variants (after rcppml_b200_comm_init). Rank g of N owns the column block J_g and the row block
+ * I_g of equal-size partitions (block = ceil(n/N) resp. ceil(m/N), see rcppml_b200_get_shard) and needs
+ * A[:, J_g] (CSC, global row ids) for the H half-step and A[I_g, :] (CSC over all n columns, row ids relative
+ * to the block) for the W half-step. */
+int rcppml_b200_set_matrix_synthetic_sharded(rcppml_b200_engine* e, int m, int n, double density, uint64_t seed);
+int rcppml_b200_set_matrix_sharded_f32(rcppml_b200_engine* e, int m, int n, const int* colblk_ptr,
+                                       const int* colblk_idx, const float* colblk_val, const int* rowblk_ptr,
+                                       const int* rowblk_idx, const float* rowblk_val);
+int rcppml_b200_get_shard(rcppml_b200_engine* e, int* col_begin, int* n_loc, int* row_begin, int* m_loc,
+                          int64_t* nnz_global);
+/* Copies the device CSC operands back (for checking the generator / transpose). Pass NULL to skip an array.
+ * get_matrix: A[:, J] (n_loc columns); get_matrix_t: A[I, :]^T (m_loc columns, global column ids). */
 int rcppml_b200_get_matrix(rcppml_b200_engine* e, int64_t* nnz, int* col_ptr, int* row_idx, float* values);
 int rcppml_b200_get_matrix_t(rcppml_b200_engine* e, int* col_ptr, int* row_idx, float* values);
 
-/* Factors: W_T is k x m column-major, H is k x n column-major (host, leading dimension k). */
+/* Factors: W_T is k x m column-major, H is k x n column-major (host, leading dimension k). Always the FULL
+ * factors, also when sharded (they are replicated on every rank). */
 int rcppml_b200_set_factors_f32(rcppml_b200_engine* e, int k, const float* W_T, const float* H);
 int rcppml_b200_set_factors_f64(rcppml_b200_engine* e, int k, const double* W_T, const double* H);
 /* nmf/nmf_init.hpp:167-182 on the device: one SplitMix64(seed) stream, W_T first, then H.
@@ -166,8 +178,8 @@ int64_t rcppml_b200_cd_sweeps(rcppml_b200_engine* e);
 int rcppml_b200_get_counters(rcppml_b200_engine* e, int64_t* h2d_bytes, int64_t* d2h_bytes);
 int rcppml_b200_selftest_division(int64_t n, uint64_t seed, int64_t* mismatches);
 
-/* Multi-GPU (one process per GPU). id is an ncclUniqueId (128 bytes) created on rank 0 and
- * distributed by the host launcher. After comm_init the engine's matrix is a column shard. */
+/* Multi-GPU (one process per GPU). id is an ncclUniqueId (128 bytes) created on rank 0 and distributed by
+ * the host launcher. comm_init must be the first call after engine_create; then use the *_sharded setters. */
 int rcppml_b200_nccl_unique_id(char* id128);
 int rcppml_b200_comm_init(rcppml_b200_engine* e, int rank, int world, const char* id128);
 

@@ -74,6 +74,9 @@ def load() -> C.CDLL:
     lib.rcppml_b200_set_matrix_f32.argtypes = [E, C.c_int, C.c_int, C.c_int64, ip, ip, fp]
     lib.rcppml_b200_set_matrix_f64.argtypes = [E, C.c_int, C.c_int, C.c_int64, ip, ip, dp]
     lib.rcppml_b200_set_matrix_synthetic.argtypes = [E, C.c_int, C.c_int, C.c_int, C.c_double, C.c_uint64]
+    lib.rcppml_b200_set_matrix_synthetic_sharded.argtypes = [E, C.c_int, C.c_int, C.c_double, C.c_uint64]
+    lib.rcppml_b200_set_matrix_sharded_f32.argtypes = [E, C.c_int, C.c_int, ip, ip, fp, ip, ip, fp]
+    lib.rcppml_b200_get_shard.argtypes = [E, ip, ip, ip, ip, C.POINTER(C.c_int64)]
     lib.rcppml_b200_get_matrix.argtypes = [E, C.POINTER(C.c_int64), ip, ip, fp]
     lib.rcppml_b200_get_matrix_t.argtypes = [E, ip, ip, fp]
     lib.rcppml_b200_set_factors_f32.argtypes = [E, C.c_int, fp, fp]

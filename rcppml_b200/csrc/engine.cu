@@ -109,8 +109,31 @@ Engine::~Engine() {
 void Engine::use_device() const { B200_CUDA_CHECK(cudaSetDevice(device)); }
 
 // ---- matrix ---------------------------------------------------------------------------------
+// Two sparse operands live on the device:
+//   opH = A[:, J]  as CSC (n_loc columns, inner = global row id)    — gathered by the H half-step
+//   opW = A[I, :]ᵀ as CSC (m_loc columns, inner = global column id) — gathered by the W half-step
+// Single GPU: J = all columns, I = all rows, opW = opHᵀ. Sharded (world > 1): J / I are this rank's
+// column / row block, so BOTH half-steps stay fully fused and local; only factors are exchanged.
+static void block_of(int total, int world, int rank, int* begin, int* count) {
+    const int nb = (total + world - 1) / world;
+    const int lo = std::min(total, rank * nb);
+    *begin = lo;
+    *count = std::min(total, lo + nb) - lo;
+}
+
+void Engine::set_dims(int m_, int n_) {
+    B200_REQUIRE(m_ > 0 && n_ > 0, "set_matrix: bad dimensions");
+    m = m_; n = n_;
+    block_of(n, world, rank, &col_begin, &n_loc);
+    block_of(m, world, rank, &row_begin, &m_loc);
+    m_pad = ((m + world - 1) / world) * world;
+    n_pad = ((n + world - 1) / world) * world;
+    matrix_ready = false;
+    factors_ready = false;
+}
+
 void Engine::finish_matrix() {
-    // tr(AᵀA) in fp64 (primitives/primitives.hpp:101-115)
+    // tr(AᵀA) in fp64 (primitives/primitives.hpp:101-115) over this rank's column block, then over ranks
     const int nb = 1024;
     DeviceBuffer<double> part;
     part.ensure(nb);
@@ -120,104 +143,173 @@ void Engine::finish_matrix() {
     B200_CUDA_CHECK(cudaStreamSynchronize(stream));
     double s = 0.0;
     for (double v : hp) s += v;
-    trAtA_local = s;
+    double cnt = static_cast<double>(nnz);
+    if (world > 1) {
+        DeviceBuffer<double> t;
+        t.ensure(2);
+        const double h[2] = {s, cnt};
+        B200_CUDA_CHECK(cudaMemcpyAsync(t.ptr, h, sizeof(h), cudaMemcpyHostToDevice, stream));
+        allreduce_f64(t.ptr, 2);
+        double r[2];
+        B200_CUDA_CHECK(cudaMemcpyAsync(r, t.ptr, sizeof(r), cudaMemcpyDeviceToHost, stream));
+        B200_CUDA_CHECK(cudaStreamSynchronize(stream));
+        s = r[0]; cnt = r[1];
+    }
     trAtA = static_cast<float>(s);
-    build_transpose();
+    nnz_global = static_cast<int64_t>(cnt);
     matrix_ready = true;
 }
 
-void Engine::build_transpose() {
-    // Stable LSD radix sort of (row, position): positions — hence column indices — stay ascending
-    // within each row, exactly the order Eigen's transpose() produces.
-    Atp.ensure(static_cast<size_t>(m) + 1);
-    Ati.ensure(std::max<int64_t>(nnz, 1) + 4);
-    Atx.ensure(std::max<int64_t>(nnz, 1) + 4);
-    if (nnz == 0) {
-        B200_CUDA_CHECK(cudaMemsetAsync(Atp.ptr, 0, (static_cast<size_t>(m) + 1) * sizeof(int), stream));
+// dst = srcᵀ with ascending inner indices. src: CSC with `ncols` columns and `nrows` rows.
+// Stable LSD radix sort of (row, position): positions — hence column indices — stay ascending
+// within each row, exactly the order Eigen's transpose() produces (nmf/fit_cpu.hpp:251-253).
+void Engine::transpose_csc(const int* sp, const int* si, const float* sx, int ncols, int nrows, int64_t cnt,
+                           DeviceBuffer<int>& dp, DeviceBuffer<int>& di, DeviceBuffer<float>& dx, int col_id_offset) {
+    dp.ensure(static_cast<size_t>(nrows) + 1);
+    di.ensure(std::max<int64_t>(cnt, 1) + 4);
+    dx.ensure(std::max<int64_t>(cnt, 1) + 4);
+    if (cnt == 0) {
+        B200_CUDA_CHECK(cudaMemsetAsync(dp.ptr, 0, (static_cast<size_t>(nrows) + 1) * sizeof(int), stream));
         B200_CUDA_CHECK(cudaStreamSynchronize(stream));
         return;
     }
     DeviceBuffer<int> col_of, keys_out;
     DeviceBuffer<unsigned> perm_in, perm_out;
-    col_of.ensure(nnz); keys_out.ensure(nnz); perm_in.ensure(nnz); perm_out.ensure(nnz);
+    col_of.ensure(cnt); keys_out.ensure(cnt); perm_in.ensure(cnt); perm_out.ensure(cnt);
     const int T = 256;
-    const unsigned gb = static_cast<unsigned>((nnz + T - 1) / T);
-    expand_columns_kernel<<<gb, T, 0, stream>>>(Ap.ptr, n, nnz, col_of.ptr);
-    iota_kernel<<<gb, T, 0, stream>>>(perm_in.ptr, nnz);
+    const unsigned gb = static_cast<unsigned>((cnt + T - 1) / T);
+    expand_columns_kernel<<<gb, T, 0, stream>>>(sp, ncols, cnt, col_of.ptr, col_id_offset);
+    iota_kernel<<<gb, T, 0, stream>>>(perm_in.ptr, cnt);
     int end_bit = 1;
-    while ((1LL << end_bit) < static_cast<long long>(m) && end_bit < 31) ++end_bit;
+    while ((1LL << end_bit) < static_cast<long long>(nrows) && end_bit < 31) ++end_bit;
     size_t temp_bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, Ai.ptr, keys_out.ptr, perm_in.ptr, perm_out.ptr, nnz, 0,
-                                    end_bit, stream);
+    cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, si, keys_out.ptr, perm_in.ptr, perm_out.ptr, cnt, 0, end_bit, stream);
     DeviceBuffer<unsigned char> temp;
     temp.ensure(temp_bytes);
-    B200_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(temp.ptr, temp_bytes, Ai.ptr, keys_out.ptr, perm_in.ptr,
-                                                    perm_out.ptr, nnz, 0, end_bit, stream));
-    permute_gather_kernel<<<gb, T, 0, stream>>>(perm_out.ptr, col_of.ptr, Ax.ptr, nnz, Ati.ptr, Atx.ptr);
-    row_pointers_kernel<<<(m + 1 + T - 1) / T, T, 0, stream>>>(keys_out.ptr, nnz, m, Atp.ptr);
+    B200_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(temp.ptr, temp_bytes, si, keys_out.ptr, perm_in.ptr, perm_out.ptr,
+                                                    cnt, 0, end_bit, stream));
+    permute_gather_kernel<<<gb, T, 0, stream>>>(perm_out.ptr, col_of.ptr, sx, cnt, di.ptr, dx.ptr);
+    row_pointers_kernel<<<(nrows + 1 + T - 1) / T, T, 0, stream>>>(keys_out.ptr, cnt, nrows, dp.ptr);
     B200_CUDA_CHECK(cudaGetLastError());
     B200_CUDA_CHECK(cudaStreamSynchronize(stream));
 }
 
 template <class ValT>
-void Engine::set_matrix_host(int m_, int n_, int64_t nnz_, const int* col_ptr, const int* row_idx, const ValT* values) {
-    use_device();
-    B200_REQUIRE(m_ > 0 && n_ > 0 && nnz_ >= 0, "set_matrix: bad dimensions");
-    B200_REQUIRE(nnz_ < (1LL << 31), "set_matrix: nnz must fit int32 (reference boundary, bridge_nmf.hpp:196)");
-    m = m_; n = n_; nnz = nnz_; col_begin = 0;
-    Ap.ensure(static_cast<size_t>(n) + 1);
-    Ai.ensure(std::max<int64_t>(nnz, 1) + 4);
-    Ax.ensure(std::max<int64_t>(nnz, 1) + 4);
-    B200_CUDA_CHECK(cudaMemcpyAsync(Ap.ptr, col_ptr, (static_cast<size_t>(n) + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
-    if (nnz > 0) {
-        B200_CUDA_CHECK(cudaMemcpyAsync(Ai.ptr, row_idx, nnz * sizeof(int), cudaMemcpyHostToDevice, stream));
+void Engine::upload_csc(int ncols, int64_t cnt, const int* col_ptr, const int* row_idx, const ValT* values,
+                        DeviceBuffer<int>& dp, DeviceBuffer<int>& di, DeviceBuffer<float>& dx) {
+    B200_REQUIRE(cnt >= 0 && cnt < (1LL << 31), "set_matrix: nnz must fit int32 (reference boundary, bridge_nmf.hpp:196)");
+    dp.ensure(static_cast<size_t>(ncols) + 1);
+    di.ensure(std::max<int64_t>(cnt, 1) + 4);
+    dx.ensure(std::max<int64_t>(cnt, 1) + 4);
+    B200_CUDA_CHECK(cudaMemcpyAsync(dp.ptr, col_ptr, (static_cast<size_t>(ncols) + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
+    if (cnt > 0) {
+        B200_CUDA_CHECK(cudaMemcpyAsync(di.ptr, row_idx, cnt * sizeof(int), cudaMemcpyHostToDevice, stream));
         if (std::is_same<ValT, float>::value) {
-            B200_CUDA_CHECK(cudaMemcpyAsync(Ax.ptr, values, nnz * sizeof(float), cudaMemcpyHostToDevice, stream));
+            B200_CUDA_CHECK(cudaMemcpyAsync(dx.ptr, values, cnt * sizeof(float), cudaMemcpyHostToDevice, stream));
         } else {
             DeviceBuffer<double> tmp;
-            tmp.ensure(nnz);
-            B200_CUDA_CHECK(cudaMemcpyAsync(tmp.ptr, values, nnz * sizeof(double), cudaMemcpyHostToDevice, stream));
-            f64_to_f32_kernel<<<static_cast<unsigned>((nnz + 255) / 256), 256, 0, stream>>>(tmp.ptr, Ax.ptr, nnz);
+            tmp.ensure(cnt);
+            B200_CUDA_CHECK(cudaMemcpyAsync(tmp.ptr, values, cnt * sizeof(double), cudaMemcpyHostToDevice, stream));
+            f64_to_f32_kernel<<<static_cast<unsigned>((cnt + 255) / 256), 256, 0, stream>>>(tmp.ptr, dx.ptr, cnt);
             B200_CUDA_CHECK(cudaStreamSynchronize(stream));
         }
     }
-    h2d_bytes += (static_cast<size_t>(n) + 1) * sizeof(int) + nnz * (sizeof(int) + sizeof(ValT));
+    B200_CUDA_CHECK(cudaStreamSynchronize(stream));
+    h2d_bytes += (static_cast<size_t>(ncols) + 1) * sizeof(int) + cnt * (sizeof(int) + sizeof(ValT));
+}
+
+template <class ValT>
+void Engine::set_matrix_host(int m_, int n_, int64_t nnz_, const int* col_ptr, const int* row_idx, const ValT* values) {
+    use_device();
+    B200_REQUIRE(world == 1, "set_matrix: with a communicator use set_matrix_sharded");
+    set_dims(m_, n_);
+    nnz = nnz_;
+    upload_csc<ValT>(n, nnz, col_ptr, row_idx, values, Ap, Ai, Ax);
+    transpose_csc(Ap.ptr, Ai.ptr, Ax.ptr, n, m, nnz, Atp, Ati, Atx, 0);
+    nnz_w = nnz;
     finish_matrix();
 }
 template void Engine::set_matrix_host<float>(int, int, int64_t, const int*, const int*, const float*);
 template void Engine::set_matrix_host<double>(int, int, int64_t, const int*, const int*, const double*);
 
-void Engine::set_matrix_synthetic(int m_, int n_local, int col_begin_, double density, uint64_t seed) {
+// Sharded: the caller hands this rank its column block A[:, J] (CSC, n_loc columns, global row ids) and
+// its row block A[I, :] (CSC, n columns, row ids relative to the block). See rcppml_b200/shard.py.
+template <class ValT>
+void Engine::set_matrix_sharded(int m_, int n_, const int* cb_ptr, const int* cb_idx, const ValT* cb_val,
+                                const int* rb_ptr, const int* rb_idx, const ValT* rb_val) {
     use_device();
-    B200_REQUIRE(m_ > 0 && n_local > 0, "synthetic: bad dimensions");
+    set_dims(m_, n_);
+    nnz = cb_ptr[n_loc];
+    upload_csc<ValT>(n_loc, nnz, cb_ptr, cb_idx, cb_val, Ap, Ai, Ax);
+    DeviceBuffer<int> rp, ri;
+    DeviceBuffer<float> rx;
+    nnz_w = rb_ptr[n];
+    upload_csc<ValT>(n, nnz_w, rb_ptr, rb_idx, rb_val, rp, ri, rx);
+    transpose_csc(rp.ptr, ri.ptr, rx.ptr, n, std::max(m_loc, 1), nnz_w, Atp, Ati, Atx, 0);
+    finish_matrix();
+}
+template void Engine::set_matrix_sharded<float>(int, int, const int*, const int*, const float*, const int*, const int*, const float*);
+template void Engine::set_matrix_sharded<double>(int, int, const int*, const int*, const double*, const int*, const int*, const double*);
+
+// SURVEY.md §8d generator. Columns [c0, c0+nc), rows kept in [r0, r1) and stored relative to r0.
+void Engine::synth_block(int m_, int c0, int nc, int r0, int r1, double density, uint64_t seed, DeviceBuffer<int>& dp,
+                         DeviceBuffer<int>& di, DeviceBuffer<float>& dx, int64_t* cnt_out) {
     const long long cnt_ll = std::llround(static_cast<double>(m_) * density);
     B200_REQUIRE(cnt_ll >= 1 && cnt_ll <= 8192, "synthetic: round(m*density) must be in [1, 8192]");
     const int cnt = static_cast<int>(cnt_ll);
-    m = m_; n = n_local; col_begin = col_begin_;
     DeviceBuffer<int> counts;
-    counts.ensure(static_cast<size_t>(n) + 1);
-    Ap.ensure(static_cast<size_t>(n) + 1);
+    counts.ensure(static_cast<size_t>(nc) + 1);
+    dp.ensure(static_cast<size_t>(nc) + 1);
     auto run = [&](int pass, int* rows, float* vals) {
-        if (cnt <= 1024) synth_column_kernel<1024><<<n, 256, 0, stream>>>(m, n, col_begin, cnt, seed, pass, counts.ptr, Ap.ptr, rows, vals);
-        else if (cnt <= 4096) synth_column_kernel<4096><<<n, 256, 0, stream>>>(m, n, col_begin, cnt, seed, pass, counts.ptr, Ap.ptr, rows, vals);
-        else synth_column_kernel<8192><<<n, 256, 0, stream>>>(m, n, col_begin, cnt, seed, pass, counts.ptr, Ap.ptr, rows, vals);
+        if (cnt <= 1024) synth_column_kernel<1024><<<nc, 256, 0, stream>>>(m_, nc, c0, cnt, r0, r1, seed, pass, counts.ptr, dp.ptr, rows, vals);
+        else if (cnt <= 4096) synth_column_kernel<4096><<<nc, 256, 0, stream>>>(m_, nc, c0, cnt, r0, r1, seed, pass, counts.ptr, dp.ptr, rows, vals);
+        else synth_column_kernel<8192><<<nc, 256, 0, stream>>>(m_, nc, c0, cnt, r0, r1, seed, pass, counts.ptr, dp.ptr, rows, vals);
         B200_CUDA_CHECK(cudaGetLastError());
     };
     run(0, nullptr, nullptr);
-    B200_CUDA_CHECK(cudaMemsetAsync(counts.ptr + n, 0, sizeof(int), stream));
+    B200_CUDA_CHECK(cudaMemsetAsync(counts.ptr + nc, 0, sizeof(int), stream));
     size_t temp_bytes = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, temp_bytes, counts.ptr, Ap.ptr, n + 1, stream);
+    cub::DeviceScan::ExclusiveSum(nullptr, temp_bytes, counts.ptr, dp.ptr, nc + 1, stream);
     DeviceBuffer<unsigned char> temp;
     temp.ensure(temp_bytes);
-    B200_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(temp.ptr, temp_bytes, counts.ptr, Ap.ptr, n + 1, stream));
+    B200_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(temp.ptr, temp_bytes, counts.ptr, dp.ptr, nc + 1, stream));
     int total = 0;
-    B200_CUDA_CHECK(cudaMemcpyAsync(&total, Ap.ptr + n, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    B200_CUDA_CHECK(cudaMemcpyAsync(&total, dp.ptr + nc, sizeof(int), cudaMemcpyDeviceToHost, stream));
     B200_CUDA_CHECK(cudaStreamSynchronize(stream));
     B200_REQUIRE(total >= 0, "synthetic: nnz overflowed int32");
-    nnz = total;
-    Ai.ensure(std::max<int64_t>(nnz, 1) + 4);
-    Ax.ensure(std::max<int64_t>(nnz, 1) + 4);
-    run(1, Ai.ptr, Ax.ptr);
+    *cnt_out = total;
+    di.ensure(std::max<int64_t>(total, 1) + 4);
+    dx.ensure(std::max<int64_t>(total, 1) + 4);
+    run(1, di.ptr, dx.ptr);
+    B200_CUDA_CHECK(cudaStreamSynchronize(stream));
+}
+
+// Stand-alone matrix made of columns [col_begin, col_begin + n_local) of the generator's m × ∞ family.
+void Engine::set_matrix_synthetic(int m_, int n_local, int col_begin_, double density, uint64_t seed) {
+    use_device();
+    B200_REQUIRE(world == 1, "set_matrix_synthetic: with a communicator use set_matrix_synthetic_sharded");
+    set_dims(m_, n_local);
+    synth_block(m, col_begin_, n, 0, m, density, seed, Ap, Ai, Ax, &nnz);
+    transpose_csc(Ap.ptr, Ai.ptr, Ax.ptr, n, m, nnz, Atp, Ati, Atx, 0);
+    nnz_w = nnz;
+    finish_matrix();
+}
+
+// The m × n generator matrix, this rank's column block and row block (any world size).
+void Engine::set_matrix_synthetic_sharded(int m_, int n_, double density, uint64_t seed) {
+    use_device();
+    set_dims(m_, n_);
+    synth_block(m, col_begin, std::max(n_loc, 1), 0, m, density, seed, Ap, Ai, Ax, &nnz);
+    if (n_loc == 0) nnz = 0;
+    if (world == 1) {
+        transpose_csc(Ap.ptr, Ai.ptr, Ax.ptr, n, m, nnz, Atp, Ati, Atx, 0);
+        nnz_w = nnz;
+    } else {
+        DeviceBuffer<int> rp, ri;
+        DeviceBuffer<float> rx;
+        synth_block(m, 0, n, row_begin, row_begin + m_loc, density, seed, rp, ri, rx, &nnz_w);
+        transpose_csc(rp.ptr, ri.ptr, rx.ptr, n, std::max(m_loc, 1), nnz_w, Atp, Ati, Atx, 0);
+    }
     finish_matrix();
 }
 
@@ -230,10 +322,10 @@ void Engine::alloc_factors(int k_) {
     KP = padded_rank(k);
     nv_override = 0;
     if (const char* env = std::getenv("RCPPML_B200_NV")) nv_override = std::atoi(env);   // tuning knob (1 or 2)
-    m_pad = ((m + world - 1) / world) * world;                  // equal row blocks for reduce-scatter / all-gather
-    W_T.ensure(static_cast<size_t>(m_pad) * KP);
+    W_T.ensure(static_cast<size_t>(m_pad) * KP);          // padded to equal row / column blocks (all-gather)
+    H.ensure(static_cast<size_t>(n_pad) * KP);
     B200_CUDA_CHECK(cudaMemsetAsync(W_T.ptr, 0, static_cast<size_t>(m_pad) * KP * sizeof(float), stream));
-    H.ensure(static_cast<size_t>(n) * KP);
+    B200_CUDA_CHECK(cudaMemsetAsync(H.ptr, 0, static_cast<size_t>(n_pad) * KP * sizeof(float), stream));
     d.ensure(KP);
     G_w.ensure(static_cast<size_t>(KP) * KP);
     G_h.ensure(static_cast<size_t>(KP) * KP);
@@ -252,8 +344,6 @@ void Engine::alloc_factors(int k_) {
             int g = 0;
             launch_half_step(geom, solver, BSRC_GATHER, OUT_SOLVE, dummy, num_sms, stream, &g);
             gmax = std::max(gmax, g);
-            launch_half_step(geom, solver, BSRC_LOAD, OUT_SOLVE, dummy, num_sms, stream, &g);
-            gmax = std::max(gmax, g);
         }
     }
     solve_grid_max = gmax;
@@ -266,6 +356,7 @@ void Engine::alloc_factors(int k_) {
     factors_ready = true;
 }
 
+// W_T (k × m) and H (k × n) are FULL (replicated on every rank when sharded).
 template <class T>
 void Engine::set_factors_host(int k_, const T* W_T_host, const T* H_host) {
     use_device();
@@ -285,6 +376,8 @@ void Engine::set_factors_host(int k_, const T* W_T_host, const T* H_host) {
 template void Engine::set_factors_host<float>(int, const float*, const float*);
 template void Engine::set_factors_host<double>(int, const double*, const double*);
 
+// nmf/nmf_init.hpp:167-182: one SplitMix64(seed) stream, W_T first, then H. h_col_begin shifts H inside
+// a wider stream (the matrix is columns [h_col_begin, h_col_begin + n) of a larger problem).
 void Engine::init_factors(int k_, uint32_t seed, int h_col_begin) {
     use_device();
     alloc_factors(k_);
@@ -412,12 +505,12 @@ HalfStepParams Engine::solve_params(int which, bool warm) const {
     p.colptr = h ? Ap.ptr : Atp.ptr;
     p.rowidx = h ? Ai.ptr : Ati.ptr;
     p.vals = h ? Ax.ptr : Atx.ptr;
-    p.F = h ? W_T.ptr : H.ptr;
-    p.X = h ? H.ptr : W_T.ptr;
+    p.F = h ? W_T.ptr : H.ptr;                          // full (replicated) factor being gathered
+    p.X = h ? H.ptr : W_T.ptr;                          // full factor being solved; this rank owns a block of it
     p.M1 = M1.ptr; p.M2 = M2.ptr; p.dblk = dblk.ptr; p.rcp = rcp.ptr;
-    p.B = nullptr; p.nslots = 0; p.slot_stride = 0;
-    p.ncols = h ? n : m;
-    p.col_offset = 0;
+    p.B = nullptr; p.nslots = 0; p.slot_stride = 0; p.b_local_index = 0;
+    p.ncols = h ? n_loc : m_loc;
+    p.col_offset = h ? col_begin : row_begin;
     p.k = k;
     p.L1 = h ? cfg.L1_H : cfg.L1_W;
     p.ub = h ? cfg.ub_H : cfg.ub_W;
@@ -428,10 +521,9 @@ HalfStepParams Engine::solve_params(int which, bool warm) const {
     p.warm = warm ? 1 : 0;
     p.norm_type = cfg.norm_type;
     p.want_cross = h ? 0 : 1;
-    p.cols_per_fetch = pick_cols_per_fetch(nnz, p.ncols);
+    p.cols_per_fetch = pick_cols_per_fetch(h ? nnz : nnz_w, p.ncols);
     p.work_counter = counters.ptr + which;
     p.partials = solve_partials.ptr;
-    p.b_local_index = 0;
     p.stop_flag = &state.ptr->stop;
     p.sweep_counter = sweep_counter.ptr;
     return p;
@@ -440,7 +532,7 @@ HalfStepParams Engine::solve_params(int which, bool warm) const {
 void Engine::solve(int which, bool warm, int sec) {
     HalfStepParams p = solve_params(which, warm);
     const int solver = cfg.solver_mode == 0 ? SOLVER_CD : SOLVER_CHOL;
-    const int geom = geometry_for(nnz, p.ncols);
+    const int geom = geometry_for(which == 0 ? nnz : nnz_w, p.ncols);
     int grid = 0;
     launch_half_step(geom, solver, BSRC_GATHER, OUT_SOLVE, p, num_sms, stream, &grid);
     last_solve_grid = grid;
@@ -467,26 +559,35 @@ void Engine::loss(int sec) {
     launches[sec] += 1;
 }
 
+// One ALS iteration (nmf/fit_cpu.hpp:444-1825). With world > 1 every rank solves its own column block of
+// H and row block of W_T with the SAME fused kernels (its sparse operands are A[:,J_g] and A[I_g,:]ᵀ), the
+// k×k Grams / row sums / loss cross term are all-reduced in fp64, and the two factor blocks are all-gathered.
+// No right-hand side ever crosses NVLink, and every column's arithmetic is identical to the single-GPU run.
 void Engine::enqueue_iteration() {
     const bool warm = iters_enqueued > 0;                                   // fit_cpu.hpp:523 / :755
     const bool normalize = cfg.norm_type != 2;
+    const bool sharded = world > 1;
+    float* Hblk = H.ptr + static_cast<size_t>(col_begin) * KP;
+    float* Wblk = W_T.ptr + static_cast<size_t>(row_begin) * KP;
     // ---- H update (fit_cpu.hpp:488-645)
-    if (iters_enqueued == 0) gram(W_T.ptr, m, false, G_w.ptr, RCPPML_B200_SEC_GRAM_H);   // :491 (later: reuse G_wt)
+    if (iters_enqueued == 0) gram(Wblk, m_loc, false, G_w.ptr, RCPPML_B200_SEC_GRAM_H, sharded);   // :491
     prepare_solver(G_w.ptr, cfg.L2_H, RCPPML_B200_SEC_GRAM_H);              // :506
     solve(0, warm, RCPPML_B200_SEC_SOLVE_H);                                // :516-535 (+ :636 upper bound)
-    scale_finalize(RCPPML_B200_SEC_SCALE_H);                                // :644
+    scale_finalize(RCPPML_B200_SEC_SCALE_H, sharded);                       // :644
     // ---- W update (fit_cpu.hpp:713-893)
-    gram(H.ptr, n, normalize, G_h.ptr, RCPPML_B200_SEC_GRAM_W);             // :644 (normalise) + :715
+    gram(Hblk, n_loc, normalize, G_h.ptr, RCPPML_B200_SEC_GRAM_W, sharded); // :644 (normalise) + :715
+    if (sharded) allgather_rows(H.ptr, n_pad / world, RCPPML_B200_SEC_COMM);
     prepare_solver(G_h.ptr, cfg.L2_W, RCPPML_B200_SEC_GRAM_W);              // :738
     solve(1, warm, RCPPML_B200_SEC_SOLVE_W);                                // :748-767 (+ :884)
-    scale_finalize(RCPPML_B200_SEC_SCALE_W);                                // :892
+    scale_finalize(RCPPML_B200_SEC_SCALE_W, sharded);                       // :892
     // ---- loss (fit_cpu.hpp:1729-1809): Gram of the new W_T doubles as next iteration's gram_H
     sec_begin(RCPPML_B200_SEC_LOSS);
     const bool was = profiling; profiling = false;                         // nested section: account under LOSS
-    gram(W_T.ptr, m, normalize, G_w.ptr, RCPPML_B200_SEC_LOSS);             // :892 (normalise) + :1735
+    gram(Wblk, m_loc, normalize, G_w.ptr, RCPPML_B200_SEC_LOSS, sharded);   // :892 (normalise) + :1735
     profiling = was;
     loss(RCPPML_B200_SEC_LOSS);
     sec_end(RCPPML_B200_SEC_LOSS);
+    if (sharded) allgather_rows(W_T.ptr, m_pad / world, RCPPML_B200_SEC_COMM);
     ++iters_enqueued;
 }
 
@@ -517,7 +618,7 @@ void Engine::iterate(int n_iters) {
     // kernels enqueued after `stop` return immediately. Every 8 iterations the host peeks at the
     // flag only to avoid enqueuing a long tail of no-op launches.
     for (int it = 0; it < n_iters; ++it) {
-        if (world > 1) enqueue_iteration_sharded(); else enqueue_iteration();
+        enqueue_iteration();
         if ((it & 7) == 7 && cfg.tol > 0.f) {
             B200_CUDA_CHECK(cudaMemcpyAsync(h_state, state.ptr, sizeof(DevState), cudaMemcpyDeviceToHost, stream));
             B200_CUDA_CHECK(cudaStreamSynchronize(stream));
@@ -615,23 +716,39 @@ int rcppml_b200_set_matrix_f64(rcppml_b200_engine* e, int m, int n, int64_t nnz,
 int rcppml_b200_set_matrix_synthetic(rcppml_b200_engine* e, int m, int n_local, int col_begin, double density, uint64_t seed) {
     B200_API_BEGIN e->impl.set_matrix_synthetic(m, n_local, col_begin, density, seed); B200_API_END
 }
-static void copy_csc(Engine& E, const int* dp, const int* di, const float* dx, int ncols, int* p, int* i, float* x) {
+int rcppml_b200_set_matrix_synthetic_sharded(rcppml_b200_engine* e, int m, int n, double density, uint64_t seed) {
+    B200_API_BEGIN e->impl.set_matrix_synthetic_sharded(m, n, density, seed); B200_API_END
+}
+int rcppml_b200_set_matrix_sharded_f32(rcppml_b200_engine* e, int m, int n, const int* cb_ptr, const int* cb_idx,
+                                       const float* cb_val, const int* rb_ptr, const int* rb_idx, const float* rb_val) {
+    B200_API_BEGIN e->impl.set_matrix_sharded<float>(m, n, cb_ptr, cb_idx, cb_val, rb_ptr, rb_idx, rb_val); B200_API_END
+}
+int rcppml_b200_get_shard(rcppml_b200_engine* e, int* col_begin, int* n_loc, int* row_begin, int* m_loc, int64_t* nnz_global) {
+    B200_API_BEGIN
+    if (col_begin) *col_begin = e->impl.col_begin;
+    if (n_loc) *n_loc = e->impl.n_loc;
+    if (row_begin) *row_begin = e->impl.row_begin;
+    if (m_loc) *m_loc = e->impl.m_loc;
+    if (nnz_global) *nnz_global = e->impl.nnz_global;
+    B200_API_END
+}
+static void copy_csc(Engine& E, const int* dp, const int* di, const float* dx, int ncols, int64_t cnt, int* p, int* i, float* x) {
     E.use_device();
     if (p) B200_CUDA_CHECK(cudaMemcpy(p, dp, (static_cast<size_t>(ncols) + 1) * sizeof(int), cudaMemcpyDeviceToHost));
-    if (i && E.nnz) B200_CUDA_CHECK(cudaMemcpy(i, di, E.nnz * sizeof(int), cudaMemcpyDeviceToHost));
-    if (x && E.nnz) B200_CUDA_CHECK(cudaMemcpy(x, dx, E.nnz * sizeof(float), cudaMemcpyDeviceToHost));
+    if (i && cnt) B200_CUDA_CHECK(cudaMemcpy(i, di, cnt * sizeof(int), cudaMemcpyDeviceToHost));
+    if (x && cnt) B200_CUDA_CHECK(cudaMemcpy(x, dx, cnt * sizeof(float), cudaMemcpyDeviceToHost));
 }
 int rcppml_b200_get_matrix(rcppml_b200_engine* e, int64_t* nnz, int* col_ptr, int* row_idx, float* values) {
     B200_API_BEGIN
     B200_REQUIRE(e->impl.matrix_ready, "no matrix");
     if (nnz) *nnz = e->impl.nnz;
-    copy_csc(e->impl, e->impl.Ap.ptr, e->impl.Ai.ptr, e->impl.Ax.ptr, e->impl.n, col_ptr, row_idx, values);
+    copy_csc(e->impl, e->impl.Ap.ptr, e->impl.Ai.ptr, e->impl.Ax.ptr, e->impl.n_loc, e->impl.nnz, col_ptr, row_idx, values);
     B200_API_END
 }
 int rcppml_b200_get_matrix_t(rcppml_b200_engine* e, int* col_ptr, int* row_idx, float* values) {
     B200_API_BEGIN
     B200_REQUIRE(e->impl.matrix_ready, "no matrix");
-    copy_csc(e->impl, e->impl.Atp.ptr, e->impl.Ati.ptr, e->impl.Atx.ptr, e->impl.m, col_ptr, row_idx, values);
+    copy_csc(e->impl, e->impl.Atp.ptr, e->impl.Ati.ptr, e->impl.Atx.ptr, e->impl.m_loc, e->impl.nnz_w, col_ptr, row_idx, values);
     B200_API_END
 }
 int rcppml_b200_set_factors_f32(rcppml_b200_engine* e, int k, const float* W_T, const float* H) {

@@ -31,10 +31,14 @@ public:
 
     void use_device() const;
 
-    // matrix (column shard [col_begin, col_begin + n) of an m × n_global matrix when world > 1)
+    // matrix: single GPU (whole A) or this rank's column block + row block (see engine.cu)
     template <class ValT>
     void set_matrix_host(int m, int n, int64_t nnz, const int* col_ptr, const int* row_idx, const ValT* values);
+    template <class ValT>
+    void set_matrix_sharded(int m, int n, const int* cb_ptr, const int* cb_idx, const ValT* cb_val, const int* rb_ptr,
+                            const int* rb_idx, const ValT* rb_val);
     void set_matrix_synthetic(int m, int n_local, int col_begin, double density, uint64_t seed);
+    void set_matrix_synthetic_sharded(int m, int n, double density, uint64_t seed);
 
     // factors
     template <class T> void set_factors_host(int k, const T* W_T, const T* H);
@@ -57,13 +61,15 @@ public:
     int num_sms = kNumSMs;
     cudaStream_t stream = nullptr;
 
-    int m = 0, n = 0, col_begin = 0;
-    int64_t nnz = 0;
+    int m = 0, n = 0;                       // global shape of A
+    int col_begin = 0, n_loc = 0;           // this rank's column block J (H half-step)
+    int row_begin = 0, m_loc = 0;           // this rank's row block I (W half-step)
+    int m_pad = 0, n_pad = 0;               // m, n rounded up to a multiple of world (equal all-gather blocks)
+    int64_t nnz = 0, nnz_w = 0, nnz_global = 0;   // nnz of A[:,J], of A[I,:], of A
     bool matrix_ready = false, factors_ready = false, fit_active = false;
     DeviceBuffer<int> Ap, Ai, Atp, Ati;
     DeviceBuffer<float> Ax, Atx;
-    float trAtA = 0.f;          // global tr(AᵀA) (summed over ranks after comm_init)
-    double trAtA_local = 0.0;
+    float trAtA = 0.f;          // tr(AᵀA) of the whole matrix
 
     int k = 0, KP = 0, LANES = 0, nv_override = 0;
     int geometry_for(long long nnz, long long ncols) const;
@@ -93,16 +99,20 @@ public:
     // multi-GPU
     ncclComm* comm = nullptr;
     int rank = 0, world = 1;
-    DeviceBuffer<float> B_part;       // m_pad × KP partial right-hand side of the W-update (this rank's columns)
-    DeviceBuffer<float> B_blk;        // reduced row block owned by this rank
-    int m_pad = 0;                    // m rounded up to a multiple of world (equal row blocks)
-    int row_begin = 0, row_count = 0; // rows of A (columns of Aᵀ) this rank solves in the W-update
 
 private:
     cudaEvent_t ev_loop_begin = nullptr, ev_loop_end = nullptr;
 
+    void set_dims(int m, int n);
     void finish_matrix();
-    void build_transpose();
+    void transpose_csc(const int* sp, const int* si, const float* sx, int ncols, int nrows, int64_t cnt,
+                       DeviceBuffer<int>& dp, DeviceBuffer<int>& di, DeviceBuffer<float>& dx, int col_id_offset);
+    template <class ValT>
+    void upload_csc(int ncols, int64_t cnt, const int* col_ptr, const int* row_idx, const ValT* values,
+                    DeviceBuffer<int>& dp, DeviceBuffer<int>& di, DeviceBuffer<float>& dx);
+    void synth_block(int m, int c0, int nc, int r0, int r1, double density, uint64_t seed, DeviceBuffer<int>& dp,
+                     DeviceBuffer<int>& di, DeviceBuffer<float>& dx, int64_t* cnt_out);
+    void allgather_rows(float* buf, int rows_per_rank, int sec);
     void alloc_factors(int k);
     void normalize_cfg(const rcppml_b200_config& c);
     void sec_begin(int sec);
@@ -116,7 +126,6 @@ private:
     void solve(int which, bool warm, int sec);
     void scale_finalize(int sec, bool reduce_over_ranks = false);
     void enqueue_iteration();
-    void enqueue_iteration_sharded();
 };
 
 }  // namespace b200

@@ -40,7 +40,7 @@ struct HalfStepParams {
     int nslots;
     long long slot_stride;
     int ncols;
-    int col_offset;                    // first column handled (row-block solves in multi-GPU)
+    int col_offset;                    // X row of local column 0 (this rank's block of the replicated factor)
     int k;
     float L1;
     float ub;
@@ -413,8 +413,8 @@ __global__ void __launch_bounds__(256) half_step_kernel(const HalfStepParams p) 
 
             float b[NV][4];
             if (BSRC == BSRC_GATHER) {
-                const int p0 = __ldg(p.colptr + j);
-                const int p1 = __ldg(p.colptr + j + 1);
+                const int p0 = __ldg(p.colptr + jl);    // the sparse operand is local to this rank
+                const int p1 = __ldg(p.colptr + jl + 1);
                 gather_column<LANES, NV>(p, p0, p1, gl, gmask, b);
             } else {
                 const int jb = p.b_local_index ? jl : j;

@@ -13,7 +13,8 @@
 namespace b200 {
 
 // col_of[p] = j such that colptr[j] <= p < colptr[j+1]
-static __global__ void expand_columns_kernel(const int* __restrict__ colptr, int n, long long nnz, int* __restrict__ col_of) {
+static __global__ void expand_columns_kernel(const int* __restrict__ colptr, int n, long long nnz, int* __restrict__ col_of,
+                                             int col_id_offset) {
     const long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (p >= nnz) return;
     int lo = 0, hi = n;                 // invariant: colptr[lo] <= p < colptr[hi]
@@ -21,7 +22,7 @@ static __global__ void expand_columns_kernel(const int* __restrict__ colptr, int
         const int mid = (lo + hi) >> 1;
         if (__ldg(colptr + mid) <= p) lo = mid; else hi = mid;
     }
-    col_of[p] = lo;
+    col_of[p] = lo + col_id_offset;
 }
 
 static __global__ void iota_kernel(unsigned* __restrict__ x, long long n) {
@@ -58,6 +59,7 @@ static __global__ void row_pointers_kernel(const int* __restrict__ sorted_rows, 
 // --------------------------------------------------------------------------------------------
 template <int NMAX>   // power of two >= candidates per column
 static __global__ void __launch_bounds__(256) synth_column_kernel(int m, int n_local, int col_begin, int cnt,
+                                                           int row_lo, int row_hi,   // keep rows in [row_lo,row_hi), stored relative
                                                            unsigned long long seed, int pass,
                                                            int* __restrict__ counts,
                                                            const int* __restrict__ colptr,
@@ -90,7 +92,9 @@ static __global__ void __launch_bounds__(256) synth_column_kernel(int m, int n_l
     int uniq = 0;
     for (int t = c0; t < c0 + CH && t < NMAX; ++t) {
         const unsigned v = sk[t];
-        if (v != 0xFFFFFFFFu && (t == 0 || sk[t - 1] != v)) ++uniq;
+        if (v != 0xFFFFFFFFu && (t == 0 || sk[t - 1] != v) && v >= static_cast<unsigned>(row_lo) &&
+            v < static_cast<unsigned>(row_hi))
+            ++uniq;
     }
     sbase[threadIdx.x + 1] = uniq;
     if (threadIdx.x == 0) sbase[0] = 0;
@@ -106,8 +110,9 @@ static __global__ void __launch_bounds__(256) synth_column_kernel(int m, int n_l
     int w = out0 + sbase[threadIdx.x];
     for (int t = c0; t < c0 + CH && t < NMAX; ++t) {
         const unsigned v = sk[t];
-        if (v != 0xFFFFFFFFu && (t == 0 || sk[t - 1] != v)) {
-            rowidx[w] = static_cast<int>(v);
+        if (v != 0xFFFFFFFFu && (t == 0 || sk[t - 1] != v) && v >= static_cast<unsigned>(row_lo) &&
+            v < static_cast<unsigned>(row_hi)) {
+            rowidx[w] = static_cast<int>(v) - row_lo;
             vals[w] = __fadd_rn(0.5f, u64_to_unit_float(splitmix_hash(seed + 1ULL, v, j)));
             ++w;
         }

@@ -45,7 +45,9 @@ class Engine:
         self._h = C.c_void_p()
         _lib.check(self._lib.rcppml_b200_engine_create(C.byref(self._h), device), "engine_create")
         self.m = self.n = self.k = 0
-        self.nnz = 0
+        self.nnz = 0                 # non-zeros of this rank's column block
+        self.nnz_global = 0
+        self.col_begin = self.n_loc = self.row_begin = self.m_loc = 0
 
     def close(self):
         if self._h:
@@ -72,17 +74,43 @@ class Engine:
             rc = self._lib.rcppml_b200_set_matrix_f32(self._h, m, n, nnz, _p(indptr, C.c_int), _p(indices, C.c_int),
                                                       _p(data, C.c_float))
         _lib.check(rc, "set_matrix")
-        self.m, self.n, self.nnz = m, n, nnz
+        self._refresh_shard(m, n)
 
     def set_matrix_synthetic(self, m, n_local, col_begin, density, seed):
         _lib.check(self._lib.rcppml_b200_set_matrix_synthetic(self._h, m, n_local, col_begin, density, seed),
                    "set_matrix_synthetic")
+        self._refresh_shard(m, n_local)
+
+    def _refresh_shard(self, m, n):
+        cb, nl, rb, ml, ng = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0), C.c_int64(0)
+        _lib.check(self._lib.rcppml_b200_get_shard(self._h, C.byref(cb), C.byref(nl), C.byref(rb), C.byref(ml),
+                                                   C.byref(ng)), "get_shard")
+        self.m, self.n = m, n
+        self.col_begin, self.n_loc, self.row_begin, self.m_loc, self.nnz_global = (cb.value, nl.value, rb.value,
+                                                                                  ml.value, ng.value)
         nnz = C.c_int64(0)
         _lib.check(self._lib.rcppml_b200_get_matrix(self._h, C.byref(nnz), None, None, None), "get_matrix")
-        self.m, self.n, self.nnz = m, n_local, nnz.value
+        self.nnz = nnz.value
+
+    def set_matrix_synthetic_sharded(self, m, n, density, seed):
+        """This rank's column and row block of the m x n generator matrix (any world size)."""
+        _lib.check(self._lib.rcppml_b200_set_matrix_synthetic_sharded(self._h, m, n, density, seed),
+                   "set_matrix_synthetic_sharded")
+        self._refresh_shard(m, n)
+
+    def set_matrix_sharded(self, m, n, col_block, row_block):
+        """col_block / row_block: (indptr, indices, data) as produced by rcppml_b200.shard.extract_*."""
+        arrs = []
+        for (p_, i_, x_) in (col_block, row_block):
+            arrs += [np.ascontiguousarray(p_, np.int32), np.ascontiguousarray(i_, np.int32),
+                     np.ascontiguousarray(x_, np.float32)]
+        _lib.check(self._lib.rcppml_b200_set_matrix_sharded_f32(
+            self._h, m, n, _p(arrs[0], C.c_int), _p(arrs[1], C.c_int), _p(arrs[2], C.c_float),
+            _p(arrs[3], C.c_int), _p(arrs[4], C.c_int), _p(arrs[5], C.c_float)), "set_matrix_sharded")
+        self._refresh_shard(m, n)
 
     def get_matrix(self):
-        p = np.empty(self.n + 1, np.int32)
+        p = np.empty(self.n_loc + 1, np.int32)
         i = np.empty(self.nnz, np.int32)
         x = np.empty(self.nnz, np.float32)
         nnz = C.c_int64(0)
@@ -91,10 +119,12 @@ class Engine:
         return p, i, x
 
     def get_matrix_t(self):
-        p = np.empty(self.m + 1, np.int32)
-        i = np.empty(self.nnz, np.int32)
-        x = np.empty(self.nnz, np.float32)
-        _lib.check(self._lib.rcppml_b200_get_matrix_t(self._h, _p(p, C.c_int), _p(i, C.c_int), _p(x, C.c_float)),
+        p = np.empty(self.m_loc + 1, np.int32)
+        _lib.check(self._lib.rcppml_b200_get_matrix_t(self._h, _p(p, C.c_int), None, None), "get_matrix_t")
+        cnt = int(p[-1])
+        i = np.empty(cnt, np.int32)
+        x = np.empty(cnt, np.float32)
+        _lib.check(self._lib.rcppml_b200_get_matrix_t(self._h, None, _p(i, C.c_int), _p(x, C.c_float)),
                    "get_matrix_t")
         return p, i, x
 

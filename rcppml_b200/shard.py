@@ -4,11 +4,15 @@ from __future__ import annotations
 import numpy as np
 
 
-def shard_columns(n: int, world: int, rank: int):
-    """Even contiguous split of n columns. Returns (first_column, count)."""
-    lo = (n * rank) // world
-    hi = (n * (rank + 1)) // world
-    return lo, hi - lo
+def block_of(total: int, world: int, rank: int):
+    """The engine's partition (csrc/engine.cu block_of): equal blocks of ceil(total/world) items, the last
+    ranks may get fewer (or none). Returns (first, count)."""
+    nb = -(-total // world)
+    lo = min(total, rank * nb)
+    return lo, min(total, lo + nb) - lo
+
+
+shard_columns = block_of
 
 
 def shard_columns_by_nnz(indptr, world: int):
@@ -24,6 +28,17 @@ def shard_columns_by_nnz(indptr, world: int):
         bounds.append(min(max(j, bounds[-1]), n))
     bounds.append(n)
     return [(bounds[r], bounds[r + 1] - bounds[r]) for r in range(world)]
+
+
+def extract_row_block(indptr, indices, data, first: int, count: int):
+    """CSC of A[first:first+count, :] over ALL columns, row ids relative to the block (the W half-step
+    operand of the rank owning those rows)."""
+    indptr = np.asarray(indptr, dtype=np.int64)
+    indices = np.asarray(indices)
+    keep = (indices >= first) & (indices < first + count)
+    csum = np.concatenate([[0], np.cumsum(keep)])
+    new_ptr = csum[indptr].astype(np.int32)
+    return new_ptr, (indices[keep] - first).astype(np.int32), np.asarray(data)[keep]
 
 
 def extract_shard(indptr, indices, data, first: int, count: int):

@@ -87,9 +87,11 @@ def test_config_mapping():
 def test_shard_helpers():
     from rcppml_b200 import shard
     for n, world in [(100000, 8), (9001, 2), (7, 8), (10, 3)]:
-        parts = [shard.shard_columns(n, world, r) for r in range(world)]
+        parts = [shard.block_of(n, world, r) for r in range(world)]
         assert parts[0][0] == 0 and sum(c for _, c in parts) == n
         assert all(parts[i][0] + parts[i][1] == parts[i + 1][0] for i in range(world - 1))
+        nb = -(-n // world)
+        assert all(lo == min(n, r * nb) and c <= nb for r, (lo, c) in enumerate(parts))   # equal all-gather blocks
     rng = np.random.default_rng(0)
     counts = rng.integers(0, 50, 1000)
     indptr = np.concatenate([[0], np.cumsum(counts)])

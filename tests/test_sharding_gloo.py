@@ -1,7 +1,8 @@
-"""CPU, world_size 2 over gloo: the column-sharded ALS schedule the CUDA engine runs over NCCL
-(rcppml_b200/csrc/comm.cu) — local H half-steps, all-reduced row sums and Grams, partial W-update
-right-hand sides reduce-scattered by row blocks, row-block solves, all-gather of W_T — restated
-with the CPU oracle's primitives and gloo collectives, must reproduce the unsharded oracle fit."""
+"""CPU, world_size 2 over gloo: the sharded ALS schedule the CUDA engine runs over NCCL
+(rcppml_b200/csrc/engine.cu enqueue_iteration + comm.cu) — column blocks of H solved from A[:,J_g],
+row blocks of W solved from A[I_g,:]^T, all-reduced Grams / row sums / cross term, all-gather of the
+factor blocks — restated with the CPU oracle's primitives and gloo collectives, must reproduce the
+unsharded oracle fit. Also covers the host-side shard helpers (rcppml_b200/shard.py)."""
 import os
 import sys
 
@@ -21,47 +22,57 @@ def _allreduce(x):
     return t.numpy()
 
 
+def _allgather_rows(block, first, total):
+    """All-gather of disjoint row blocks (emulated with an all-reduce of zero-padded arrays)."""
+    full = np.zeros((total, block.shape[1]), np.float32)
+    full[first:first + block.shape[0]] = block
+    return _allreduce(full)
+
+
 def _sharded_fit(rank, world, A, m, n, k, W0, H0, iters, solver, L1, L2):
     from oracle import oracle as O
     from rcppml_b200 import shard
-    lo, cnt = shard.shard_columns(n, world, rank)
+    lo, cnt = shard.block_of(n, world, rank)          # my columns of H
+    r0, rc = shard.block_of(m, world, rank)           # my rows of W
     Ap, Ai, Ax = shard.extract_shard(A.indptr, A.indices, A.data, lo, cnt)
     Ai, Ax = np.ascontiguousarray(Ai, np.int32), np.ascontiguousarray(Ax, np.float32)
-    Atp, Ati, Atx = O.transpose_csc(Ap, Ai, Ax, m, cnt)
-    W_T, H = W0.copy(), H0[lo:lo + cnt].copy()
-    m_pad = ((m + world - 1) // world) * world
-    mb = m_pad // world
-    r0, r1 = rank * mb, min(m, (rank + 1) * mb)
+    Rp, Ri, Rx = shard.extract_row_block(A.indptr, A.indices, A.data, r0, rc)
+    Atp, Ati, Atx = O.transpose_csc(Rp, Ri, np.ascontiguousarray(Rx, np.float32), rc, n)   # A[I,:]^T: rc columns
+    W_T, H = W0.copy(), H0.copy()                      # replicated
     trAtA = np.float32(_allreduce(np.array([np.sum(Ax.astype(np.float64) ** 2)]))[0])
     hist = []
-    G_w = O.gram(W_T)
+
+    def gram64(X):
+        return X.astype(np.float64).T @ X.astype(np.float64)
+
+    def finish_gram(S):
+        G = _allreduce(S).astype(np.float32)
+        G[np.diag_indices(k)] += np.float32(1e-15)
+        return G
+
+    G_w = finish_gram(gram64(W_T[r0:r0 + rc]))
     for it in range(iters):
         warm = it > 0
-        # H half-step on local columns
+        # H half-step on my columns, gathering from the replicated W_T
         G = G_w.copy(); G[np.diag_indices(k)] += np.float32(L2[1])
-        O.half_step(Ap, Ai, Ax, W_T, G, H, solver_mode=solver, L1=L1[1], warm_start=warm)
-        d = (_allreduce(np.abs(H.astype(np.float64)).sum(axis=0)).astype(np.float32) + np.float32(1e-15))
-        H /= d
-        G_h = _allreduce(H.astype(np.float64).T @ H.astype(np.float64)).astype(np.float32)
-        G_h[np.diag_indices(k)] += np.float32(1e-15)
-        # W half-step: partial RHS -> reduce-scatter (all-reduce + slice here) -> row-block solve -> all-gather
-        B = np.zeros((m_pad, k), np.float32)
-        B[:m] = O.rhs(Atp, Ati, Atx, m, H)
-        B = _allreduce(B)[r0:r1].copy()
-        B_raw = B.copy()
+        Hb = H[lo:lo + cnt].copy()
+        O.half_step(Ap, Ai, Ax, W_T, G, Hb, solver_mode=solver, L1=L1[1], warm_start=warm)
+        d = (_allreduce(np.abs(Hb.astype(np.float64)).sum(axis=0)).astype(np.float32) + np.float32(1e-15))
+        Hb /= d
+        G_h = finish_gram(gram64(Hb))
+        H = _allgather_rows(Hb, lo, n)
+        # W half-step on my rows, gathering from the replicated H (no right-hand side is exchanged)
         G = G_h.copy(); G[np.diag_indices(k)] += np.float32(L2[0])
-        Wblk = W_T[r0:r1].copy()
-        O.solve_given_rhs(B, G, Wblk, solver_mode=solver, L1=L1[0], warm_start=warm)
-        sums = _allreduce(np.concatenate([np.abs(Wblk.astype(np.float64)).sum(axis=0),
-                                          [np.sum(Wblk.astype(np.float64) * B_raw.astype(np.float64))]]))
+        Wb = W_T[r0:r0 + rc].copy()
+        B_raw = O.rhs(Atp, Ati, Atx, rc, H)
+        O.half_step(Atp, Ati, Atx, H, G, Wb, solver_mode=solver, L1=L1[0], warm_start=warm)
+        sums = _allreduce(np.concatenate([np.abs(Wb.astype(np.float64)).sum(axis=0),
+                                          [np.sum(Wb.astype(np.float64) * B_raw.astype(np.float64))]]))
         d = sums[:k].astype(np.float32) + np.float32(1e-15)
         cross = np.float32(sums[k])
-        Wblk /= d
-        G_w = _allreduce(Wblk.astype(np.float64).T @ Wblk.astype(np.float64)).astype(np.float32)
-        G_w[np.diag_indices(k)] += np.float32(1e-15)
-        full = np.zeros((m_pad, k), np.float32)
-        full[r0:r1] = Wblk
-        W_T = _allreduce(full)[:m].copy()                       # all-gather (disjoint blocks)
+        Wb /= d
+        G_w = finish_gram(gram64(Wb))
+        W_T = _allgather_rows(Wb, r0, m)
         recon = np.float32(np.sum((np.outer(d, d) * G_w * G_h).astype(np.float64)))
         hist.append(np.float32(trAtA - np.float32(2) * cross + recon))
     return W_T, H, d, np.array(hist), (lo, cnt)
@@ -80,7 +91,7 @@ def _worker(rank, world, port, q):
         ref = O.nmf_fit(A.indptr, A.indices, A.data, m, n, k, W0, H0, max_iter=iters, tol=0.0, solver_mode=solver,
                         L1=L1, L2=L2, threads=1)
         W_T, H, d, hist, (lo, cnt) = _sharded_fit(rank, world, A, m, n, k, W0, H0, iters, solver, L1, L2)
-        errs = dict(W=rel_err(W_T, ref.W_T), H=rel_err(H, ref.H[lo:lo + cnt]), d=rel_err(d, ref.d),
+        errs = dict(W=rel_err(W_T, ref.W_T), H=rel_err(H, ref.H), d=rel_err(d, ref.d),
                     loss=rel_err(hist, ref.loss_history))
         msgs.append((solver, errs))
         ok = ok and max(errs.values()) <= 1e-5
