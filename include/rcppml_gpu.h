@@ -70,6 +70,44 @@ void rcppml_gpu_nmf_unified_float(
     int* out_status,
     double* out_tol);
 
+/* ABI EXTENSION of Part 1: the same call with the explicit user mask, which the reference bridge does not carry
+ * (gpu/bridge_nmf.hpp:39-75). mask_p[n+1] / mask_i[*mask_nnz]: CSC pattern of the masked entries of A
+ * (nmf/masked_nnls.hpp:97-282; the fit then follows fit_cpu.hpp:560-564, :799-810, :1686-1691).
+ * The 73 arguments of rcppml_gpu_nmf_unified_float follow the three mask arguments. */
+void rcppml_gpu_nmf_masked_unified_float(
+    const int* mask_p, const int* mask_i, int* mask_nnz,
+    const int* col_ptr, const int* row_idx, const double* values,
+    int* m, int* n, int* nnz, int* k,
+    double* W, double* H, double* d,
+    int* max_iter, double* tol,
+    double* L1_H, double* L1_W, double* L2_H, double* L2_W,
+    double* L21_H, double* L21_W,
+    double* ortho_H, double* ortho_W,
+    double* ub_H, double* ub_W,
+    int* cd_maxit, int* verbose, int* seed,
+    int* loss_every, int* patience,
+    int* nonneg_W, int* nonneg_H,
+    int* loss_type, double* huber_delta,
+    int* irls_max_iter, double* irls_tol,
+    int* norm_type,
+    int* projective, int* symmetric,
+    int* solver_mode,
+    const int* graph_W_p, const int* graph_W_i, const double* graph_W_x,
+    int* graph_W_dim, int* graph_W_nnz, double* graph_W_lambda,
+    const int* graph_H_p, const int* graph_H_i, const double* graph_H_x,
+    int* graph_H_dim, int* graph_H_nnz, double* graph_H_lambda,
+    int* gp_dispersion_mode,
+    double* gp_theta_init, double* gp_theta_max, double* gp_theta_min,
+    double* nb_size_init, double* nb_size_max, double* nb_size_min,
+    double* gamma_phi_init, double* gamma_phi_max, double* gamma_phi_min,
+    double* robust_delta, double* tweedie_power,
+    double* out_theta, int* out_theta_len,
+    const int* guide_H_labels_flat, const int* guide_H_ns,
+    const double* guide_H_lambdas, const int* guide_H_ncs, int* guide_H_count,
+    int* out_iter, int* out_converged, double* out_loss,
+    int* out_status,
+    double* out_tol);
+
 /* ========================================================================
  * Part 2 — device-resident engine (ABI extension)
  * ===================================================================== */
@@ -145,6 +183,10 @@ int rcppml_b200_get_shard(rcppml_b200_engine* e, int* col_begin, int* n_loc, int
  * get_matrix: A[:, J] (n_loc columns); get_matrix_t: A[I, :]^T (m_loc columns, global column ids). */
 int rcppml_b200_get_matrix(rcppml_b200_engine* e, int64_t* nnz, int* col_ptr, int* row_idx, float* values);
 int rcppml_b200_get_matrix_t(rcppml_b200_engine* e, int* col_ptr, int* row_idx, float* values);
+
+/* Explicit user mask (single GPU): CSC pattern (m x n) of the masked entries; mask_nnz = 0 clears it.
+ * With a mask set, fits follow the reference's masked path (nmf/masked_nnls.hpp). */
+int rcppml_b200_set_mask(rcppml_b200_engine* e, int64_t mask_nnz, const int* mask_col_ptr, const int* mask_row_idx);
 
 /* Factors: W_T is k x m column-major, H is k x n column-major (host, leading dimension k). Always the FULL
  * factors, also when sharded (they are replicated on every rank). */

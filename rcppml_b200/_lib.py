@@ -79,6 +79,7 @@ def load() -> C.CDLL:
     lib.rcppml_b200_get_shard.argtypes = [E, ip, ip, ip, ip, C.POINTER(C.c_int64)]
     lib.rcppml_b200_get_matrix.argtypes = [E, C.POINTER(C.c_int64), ip, ip, fp]
     lib.rcppml_b200_get_matrix_t.argtypes = [E, ip, ip, fp]
+    lib.rcppml_b200_set_mask.argtypes = [E, C.c_int64, ip, ip]
     lib.rcppml_b200_set_factors_f32.argtypes = [E, C.c_int, fp, fp]
     lib.rcppml_b200_set_factors_f64.argtypes = [E, C.c_int, dp, dp]
     lib.rcppml_b200_init_factors.argtypes = [E, C.c_int, C.c_uint32, C.c_int]

@@ -52,7 +52,7 @@ class PackedCall:
     def __init__(self, col_ptr, row_idx, values, m, n, k, W, H, *, max_iter=100, tol=1e-4, L1=(0.0, 0.0),
                  L2=(0.0, 0.0), L21=(0.0, 0.0), angular=(0.0, 0.0), upper_bound=(0.0, 0.0), nonneg=(True, True),
                  cd_maxit=100, verbose=False, seed=42, loss_every=1, patience=5, loss_type=0, norm_type=0,
-                 projective=False, symmetric=False, solver_mode=0):
+                 projective=False, symmetric=False, solver_mode=0, mask=None):
         lib = _lib.load()
         assert col_ptr.dtype == np.int32 and row_idx.dtype == np.int32
         assert values.dtype == np.float64 and W.dtype == np.float64 and H.dtype == np.float64
@@ -107,6 +107,14 @@ class PackedCall:
         ]
         assert len(self._args) == 73, len(self._args)
         self._fn = lib.rcppml_gpu_nmf_unified_float
+        if mask is not None:                  # ABI extension: mask pattern + the same 73 arguments
+            mp = np.ascontiguousarray(mask[0], np.int32)
+            mi = np.ascontiguousarray(mask[1], np.int32)
+            if mi.size == 0:
+                mi = np.zeros(1, np.int32)
+            self._keep += [mp, mi]
+            self._args = [ip(mp), ip(mi), i_(int(mp[n]))] + self._args
+            self._fn = lib.rcppml_gpu_nmf_masked_unified_float
         self._fn.restype = None
 
     def __call__(self):

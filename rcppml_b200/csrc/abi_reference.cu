@@ -39,8 +39,115 @@ void rcppml_gpu_detect(int* num_gpus, double* total_mem_mb, double* free_mem_mb,
     if (out_status) *out_status = usable > 0 ? 0 : -1;
 }
 
+// Shared body of the standard entry point and its masked extension.
+static void nmf_unified_impl(
+    const int* mask_p, const int* mask_i, const int* mask_nnz,
+    const int* col_ptr, const int* row_idx, const double* values,
+    int* m, int* n, int* nnz, int* k,
+    double* W, double* H, double* d,
+    int* max_iter, double* tol,
+    double* L1_H, double* L1_W, double* L2_H, double* L2_W,
+    double* L21_H, double* L21_W,
+    double* ortho_H, double* ortho_W,
+    double* ub_H, double* ub_W,
+    int* cd_maxit, int* verbose, int* /*seed*/,
+    int* /*loss_every*/, int* patience,
+    int* nonneg_W, int* nonneg_H,
+    int* loss_type, double* /*huber_delta*/,
+    int* /*irls_max_iter*/, double* /*irls_tol*/,
+    int* norm_type,
+    int* projective, int* symmetric,
+    int* solver_mode,
+    const int*, const int*, const double*, int*, int* graph_W_nnz, double*,
+    const int*, const int*, const double*, int*, int* graph_H_nnz, double*,
+    int* /*gp_dispersion_mode*/,
+    double*, double*, double*, double*, double*, double*, double*, double*, double*,
+    double* robust_delta, double* /*tweedie_power*/,
+    double* /*out_theta*/, int* out_theta_len,
+    const int*, const int*, const double*, const int*, int* guide_H_count,
+    int* out_iter, int* out_converged, double* out_loss,
+    int* out_status,
+    double* out_tol);
+
 // src/gpu_bridge_nmf.cu:460-624
 void rcppml_gpu_nmf_unified_float(
+    const int* col_ptr, const int* row_idx, const double* values,
+    int* m, int* n, int* nnz, int* k,
+    double* W, double* H, double* d,
+    int* max_iter, double* tol,
+    double* L1_H, double* L1_W, double* L2_H, double* L2_W,
+    double* L21_H, double* L21_W,
+    double* ortho_H, double* ortho_W,
+    double* ub_H, double* ub_W,
+    int* cd_maxit, int* verbose, int* seed,
+    int* loss_every, int* patience,
+    int* nonneg_W, int* nonneg_H,
+    int* loss_type, double* huber_delta,
+    int* irls_max_iter, double* irls_tol,
+    int* norm_type,
+    int* projective, int* symmetric,
+    int* solver_mode,
+    const int* gWp, const int* gWi, const double* gWx, int* gWd, int* graph_W_nnz, double* gWl,
+    const int* gHp, const int* gHi, const double* gHx, int* gHd, int* graph_H_nnz, double* gHl,
+    int* gp_dispersion_mode,
+    double* t1, double* t2, double* t3, double* t4, double* t5, double* t6, double* t7, double* t8, double* t9,
+    double* robust_delta, double* tweedie_power,
+    double* out_theta, int* out_theta_len,
+    const int* g1, const int* g2, const double* g3, const int* g4, int* guide_H_count,
+    int* out_iter, int* out_converged, double* out_loss,
+    int* out_status,
+    double* out_tol)
+{
+    nmf_unified_impl(nullptr, nullptr, nullptr, col_ptr, row_idx, values, m, n, nnz, k, W, H, d, max_iter, tol, L1_H, L1_W,
+                     L2_H, L2_W, L21_H, L21_W, ortho_H, ortho_W, ub_H, ub_W, cd_maxit, verbose, seed, loss_every, patience,
+                     nonneg_W, nonneg_H, loss_type, huber_delta, irls_max_iter, irls_tol, norm_type, projective, symmetric,
+                     solver_mode, gWp, gWi, gWx, gWd, graph_W_nnz, gWl, gHp, gHi, gHx, gHd, graph_H_nnz, gHl,
+                     gp_dispersion_mode, t1, t2, t3, t4, t5, t6, t7, t8, t9, robust_delta, tweedie_power, out_theta,
+                     out_theta_len, g1, g2, g3, g4, guide_H_count, out_iter, out_converged, out_loss, out_status, out_tol);
+}
+
+// ABI EXTENSION (not in the reference): the standard entry point plus the user mask, which the reference
+// bridge does not carry (gpu/bridge_nmf.hpp:39-75). mask_p[n+1] / mask_i[mask_nnz] are the CSC
+// pattern of the masked entries (nmf/masked_nnls.hpp). Same 73 arguments follow.
+void rcppml_gpu_nmf_masked_unified_float(
+    const int* mask_p, const int* mask_i, int* mask_nnz,
+    const int* col_ptr, const int* row_idx, const double* values,
+    int* m, int* n, int* nnz, int* k,
+    double* W, double* H, double* d,
+    int* max_iter, double* tol,
+    double* L1_H, double* L1_W, double* L2_H, double* L2_W,
+    double* L21_H, double* L21_W,
+    double* ortho_H, double* ortho_W,
+    double* ub_H, double* ub_W,
+    int* cd_maxit, int* verbose, int* seed,
+    int* loss_every, int* patience,
+    int* nonneg_W, int* nonneg_H,
+    int* loss_type, double* huber_delta,
+    int* irls_max_iter, double* irls_tol,
+    int* norm_type,
+    int* projective, int* symmetric,
+    int* solver_mode,
+    const int* gWp, const int* gWi, const double* gWx, int* gWd, int* graph_W_nnz, double* gWl,
+    const int* gHp, const int* gHi, const double* gHx, int* gHd, int* graph_H_nnz, double* gHl,
+    int* gp_dispersion_mode,
+    double* t1, double* t2, double* t3, double* t4, double* t5, double* t6, double* t7, double* t8, double* t9,
+    double* robust_delta, double* tweedie_power,
+    double* out_theta, int* out_theta_len,
+    const int* g1, const int* g2, const double* g3, const int* g4, int* guide_H_count,
+    int* out_iter, int* out_converged, double* out_loss,
+    int* out_status,
+    double* out_tol)
+{
+    nmf_unified_impl(mask_p, mask_i, mask_nnz, col_ptr, row_idx, values, m, n, nnz, k, W, H, d, max_iter, tol, L1_H, L1_W,
+                     L2_H, L2_W, L21_H, L21_W, ortho_H, ortho_W, ub_H, ub_W, cd_maxit, verbose, seed, loss_every, patience,
+                     nonneg_W, nonneg_H, loss_type, huber_delta, irls_max_iter, irls_tol, norm_type, projective, symmetric,
+                     solver_mode, gWp, gWi, gWx, gWd, graph_W_nnz, gWl, gHp, gHi, gHx, gHd, graph_H_nnz, gHl,
+                     gp_dispersion_mode, t1, t2, t3, t4, t5, t6, t7, t8, t9, robust_delta, tweedie_power, out_theta,
+                     out_theta_len, g1, g2, g3, g4, guide_H_count, out_iter, out_converged, out_loss, out_status, out_tol);
+}
+
+static void nmf_unified_impl(
+    const int* mask_p, const int* mask_i, const int* mask_nnz,
     const int* col_ptr, const int* row_idx, const double* values,
     int* m, int* n, int* nnz, int* k,
     double* W, double* H, double* d,
@@ -90,6 +197,7 @@ void rcppml_gpu_nmf_unified_float(
 
         b200::Engine E(0);
         E.set_matrix_host<double>(*m, *n, static_cast<int64_t>(*nnz), col_ptr, row_idx, values);
+        if (mask_p && mask_i && mask_nnz && *mask_nnz > 0) E.set_mask(*mask_nnz, mask_p, mask_i);
         E.set_factors_host<double>(*k, W, H);
 
         rcppml_b200_config cfg{};

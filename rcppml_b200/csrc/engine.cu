@@ -75,6 +75,33 @@ static void launch_normalize_gram(int KP, float* X, long long ncols, const float
     }
 }
 
+template <int KP>
+static void launch_masked_t(const MaskedParams& p, int num_sms, cudaStream_t s, int* grid_out) {
+    auto kern = masked_half_step_kernel<KP>;
+    const size_t smem = masked_smem_bytes<KP>();
+    const int threads = masked_warps<KP>() * 32;
+    static thread_local int cached_occ = -1;
+    if (cached_occ < 0) {
+        B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        int occ = 0;
+        B200_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+        B200_REQUIRE(occ > 0, "masked_half_step_kernel does not fit on an SM");
+        cached_occ = occ;
+    }
+    const int grid = num_sms * cached_occ;
+    if (grid_out) { *grid_out = grid; return; }
+    kern<<<grid, threads, smem, s>>>(p);
+}
+static void launch_masked(int KP, const MaskedParams& p, int num_sms, cudaStream_t s, int* grid_out = nullptr) {
+    switch (KP) {
+        case 16: launch_masked_t<16>(p, num_sms, s, grid_out); break;
+        case 32: launch_masked_t<32>(p, num_sms, s, grid_out); break;
+        case 64: launch_masked_t<64>(p, num_sms, s, grid_out); break;
+        case 128: launch_masked_t<128>(p, num_sms, s, grid_out); break;
+        default: throw std::runtime_error("unsupported padded rank");
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Engine
 // ---------------------------------------------------------------------------------------------
@@ -346,6 +373,7 @@ void Engine::alloc_factors(int k_) {
             gmax = std::max(gmax, g);
         }
     }
+    { int g = 0; MaskedParams md{}; launch_masked(KP, md, num_sms, stream, &g); gmax = std::max(gmax, g); }
     solve_grid_max = gmax;
     solve_partials.ensure(static_cast<size_t>(gmax) * (KP + 1));
     red_gram.ensure(static_cast<size_t>(KP) * KP);
@@ -591,6 +619,92 @@ void Engine::enqueue_iteration() {
     ++iters_enqueued;
 }
 
+// ---- explicit user mask (nmf/masked_nnls.hpp) ---------------------------------------------------
+// mask: CSC pattern m × n of the masked entries (the reference masks entries whose stored value is
+// non-zero, masked_nnls.hpp:116-118 — callers pass that pattern). The transposed pattern is built on
+// the device (fit_cpu.hpp:273-278). Pass nnz = 0 to clear.
+void Engine::set_mask(int64_t mnnz, const int* mask_ptr, const int* mask_idx) {
+    use_device();
+    B200_REQUIRE(matrix_ready, "set_mask: set the matrix first");
+    B200_REQUIRE(world == 1, "set_mask: the masked path is single-GPU");
+    has_mask = false;
+    if (mnnz <= 0) return;
+    Mp.ensure(static_cast<size_t>(n) + 1);
+    Mi.ensure(mnnz + 4);
+    B200_CUDA_CHECK(cudaMemcpyAsync(Mp.ptr, mask_ptr, (static_cast<size_t>(n) + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
+    B200_CUDA_CHECK(cudaMemcpyAsync(Mi.ptr, mask_idx, mnnz * sizeof(int), cudaMemcpyHostToDevice, stream));
+    DeviceBuffer<float> ones, onesT;
+    ones.ensure(mnnz + 4);
+    B200_CUDA_CHECK(cudaMemsetAsync(ones.ptr, 0, (mnnz + 4) * sizeof(float), stream));
+    B200_CUDA_CHECK(cudaStreamSynchronize(stream));
+    transpose_csc(Mp.ptr, Mi.ptr, ones.ptr, n, m, mnnz, MTp, MTi, onesT, 0);
+    mask_nnz = mnnz;
+    has_mask = true;
+}
+
+void Engine::masked_solve(int which, bool warm, const float* G, int sec) {
+    MaskedParams p{};
+    const bool h = (which == 0);
+    p.colptr = h ? Ap.ptr : Atp.ptr;
+    p.rowidx = h ? Ai.ptr : Ati.ptr;
+    p.vals = h ? Ax.ptr : Atx.ptr;
+    p.mptr = h ? Mp.ptr : MTp.ptr;
+    p.midx = h ? Mi.ptr : MTi.ptr;
+    p.F = h ? W_T.ptr : H.ptr;
+    p.X = h ? H.ptr : W_T.ptr;
+    p.G = G;
+    p.ncols = h ? n : m;
+    p.k = k;
+    p.L1 = h ? cfg.L1_H : cfg.L1_W;
+    p.L2 = h ? cfg.L2_H : cfg.L2_W;
+    p.ub = h ? cfg.ub_H : cfg.ub_W;
+    p.cd_tol = cfg.cd_tol;
+    p.inv_k = 1.0f / static_cast<float>(k);
+    p.cd_maxit = cfg.cd_maxit;
+    p.nonneg = h ? cfg.nonneg_H : cfg.nonneg_W;
+    p.warm = warm ? 1 : 0;
+    p.solver = (cfg.solver_mode == 1) ? 1 : 0;       // masked_solve_col tests `== 1` (masked_nnls.hpp:56)
+    p.norm_type = cfg.norm_type;
+    p.work_counter = counters.ptr + 4 + which;
+    p.partials = solve_partials.ptr;
+    p.state = state.ptr;
+    p.sweep_counter = sweep_counter.ptr;
+    int grid = 0;
+    launch_masked(KP, p, num_sms, stream, &grid);
+    B200_REQUIRE(static_cast<size_t>(grid) * (KP + 1) <= solve_partials.count, "partials buffer too small");
+    last_solve_grid = grid;
+    sec_begin(sec);
+    B200_CUDA_CHECK(cudaMemsetAsync(p.work_counter, 0, sizeof(int), stream));
+    launch_masked(KP, p, num_sms, stream);
+    launches[sec] += 1;
+    sec_end(sec);
+}
+
+// fit_cpu.hpp with use_mask: :560-564 (H), :799-810 (W), :1686-1691 (loss).
+void Engine::enqueue_iteration_masked() {
+    const bool warm = iters_enqueued > 0;
+    const bool normalize = cfg.norm_type != 2;
+    if (iters_enqueued == 0) gram(W_T.ptr, m, false, G_w.ptr, RCPPML_B200_SEC_GRAM_H);   // :562 rebuilt unmodified
+    masked_solve(0, warm, G_w.ptr, RCPPML_B200_SEC_SOLVE_H);
+    scale_finalize(RCPPML_B200_SEC_SCALE_H);
+    gram(H.ptr, n, normalize, G_h.ptr, RCPPML_B200_SEC_GRAM_W);                           // :644 + :801
+    masked_solve(1, warm, G_h.ptr, RCPPML_B200_SEC_SOLVE_W);
+    scale_finalize(RCPPML_B200_SEC_SCALE_W);
+    sec_begin(RCPPML_B200_SEC_LOSS);
+    const bool was = profiling; profiling = false;
+    gram(W_T.ptr, m, normalize, G_w.ptr, RCPPML_B200_SEC_LOSS);                           // normalise + next gram_H
+    profiling = was;
+    const int lgrid = num_sms * 4;
+    if (loss_partials.count < static_cast<size_t>(lgrid)) loss_partials.ensure(lgrid);
+    masked_loss_kernel<<<lgrid, 256, 0, stream>>>(Ap.ptr, Ai.ptr, Ax.ptr, Mp.ptr, Mi.ptr, n, KP, k, W_T.ptr, H.ptr, d.ptr,
+                                                  loss_partials.ptr, &state.ptr->stop);
+    masked_loss_finalize_kernel<<<1, 32, 0, stream>>>(loss_partials.ptr, lgrid, cfg.tol, cfg.patience, loss_hist.ptr,
+                                                      static_cast<int>(loss_hist.count), state.ptr);
+    launches[RCPPML_B200_SEC_LOSS] += 2;
+    sec_end(RCPPML_B200_SEC_LOSS);
+    ++iters_enqueued;
+}
+
 void Engine::begin_fit(const rcppml_b200_config& c) {
     use_device();
     B200_REQUIRE(matrix_ready && factors_ready, "begin_fit: matrix and factors must be set first");
@@ -618,7 +732,7 @@ void Engine::iterate(int n_iters) {
     // kernels enqueued after `stop` return immediately. Every 8 iterations the host peeks at the
     // flag only to avoid enqueuing a long tail of no-op launches.
     for (int it = 0; it < n_iters; ++it) {
-        enqueue_iteration();
+        if (has_mask) enqueue_iteration_masked(); else enqueue_iteration();
         if ((it & 7) == 7 && cfg.tol > 0.f) {
             B200_CUDA_CHECK(cudaMemcpyAsync(h_state, state.ptr, sizeof(DevState), cudaMemcpyDeviceToHost, stream));
             B200_CUDA_CHECK(cudaStreamSynchronize(stream));
@@ -750,6 +864,9 @@ int rcppml_b200_get_matrix_t(rcppml_b200_engine* e, int* col_ptr, int* row_idx, 
     B200_REQUIRE(e->impl.matrix_ready, "no matrix");
     copy_csc(e->impl, e->impl.Atp.ptr, e->impl.Ati.ptr, e->impl.Atx.ptr, e->impl.m_loc, e->impl.nnz_w, col_ptr, row_idx, values);
     B200_API_END
+}
+int rcppml_b200_set_mask(rcppml_b200_engine* e, int64_t mask_nnz, const int* mask_col_ptr, const int* mask_row_idx) {
+    B200_API_BEGIN e->impl.set_mask(mask_nnz, mask_col_ptr, mask_row_idx); B200_API_END
 }
 int rcppml_b200_set_factors_f32(rcppml_b200_engine* e, int k, const float* W_T, const float* H) {
     B200_API_BEGIN e->impl.set_factors_host<float>(k, W_T, H); B200_API_END

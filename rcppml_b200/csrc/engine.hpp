@@ -4,6 +4,7 @@
 #include "../../include/rcppml_gpu.h"
 #include "common.cuh"
 #include "kernels_dense.cuh"
+#include "kernels_masked.cuh"
 #include "kernels_solve.cuh"
 #include "kernels_sparse.cuh"
 
@@ -40,6 +41,8 @@ public:
     void set_matrix_synthetic(int m, int n_local, int col_begin, double density, uint64_t seed);
     void set_matrix_synthetic_sharded(int m, int n, double density, uint64_t seed);
 
+    void set_mask(int64_t mask_nnz, const int* mask_ptr, const int* mask_idx);
+
     // factors
     template <class T> void set_factors_host(int k, const T* W_T, const T* H);
     template <class T> void get_factors_host(T* W_T, T* H, T* d);
@@ -69,6 +72,10 @@ public:
     bool matrix_ready = false, factors_ready = false, fit_active = false;
     DeviceBuffer<int> Ap, Ai, Atp, Ati;
     DeviceBuffer<float> Ax, Atx;
+    bool has_mask = false;                  // explicit user mask (nmf/masked_nnls.hpp); pattern + transposed pattern
+    int64_t mask_nnz = 0;
+    DeviceBuffer<int> Mp, Mi, MTp, MTi;
+    DeviceBuffer<double> loss_partials;
     float trAtA = 0.f;          // tr(AᵀA) of the whole matrix
 
     int k = 0, KP = 0, LANES = 0, nv_override = 0;
@@ -126,6 +133,8 @@ private:
     void solve(int which, bool warm, int sec);
     void scale_finalize(int sec, bool reduce_over_ranks = false);
     void enqueue_iteration();
+    void enqueue_iteration_masked();
+    void masked_solve(int which, bool warm, const float* G, int sec);
 };
 
 }  // namespace b200

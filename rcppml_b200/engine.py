@@ -128,6 +128,16 @@ class Engine:
                    "get_matrix_t")
         return p, i, x
 
+    def set_mask(self, mask_indptr=None, mask_indices=None):
+        """CSC pattern (m x n) of masked entries (nmf/masked_nnls.hpp); None clears the mask."""
+        if mask_indptr is None:
+            _lib.check(self._lib.rcppml_b200_set_mask(self._h, 0, None, None), "set_mask")
+            return
+        mp = np.ascontiguousarray(mask_indptr, np.int32)
+        mi = np.ascontiguousarray(mask_indices, np.int32)
+        _lib.check(self._lib.rcppml_b200_set_mask(self._h, int(mp[self.n]), _p(mp, C.c_int), _p(mi, C.c_int)),
+                   "set_mask")
+
     # ---- factors
     def set_factors(self, W_T, H):
         W_T = np.ascontiguousarray(W_T, dtype=np.float32)

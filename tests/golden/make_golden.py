@@ -25,3 +25,14 @@ for solver in (0, 1):
     out[f"W_{solver}"], out[f"H_{solver}"], out[f"d_{solver}"], out[f"loss_{solver}"] = r.W_T, r.H, r.d, r.loss_history
 np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "oracle_small_fit.npz"), **out)
 print("wrote oracle_small_fit.npz")
+
+# pbmc3k[0:500, 0:200] — the block of the reference's GPU accuracy test (tests/testthat/test_gpu_accuracy.R:26-34),
+# cut from the matrix the reference's own .spz decoder produced (oracle/_ref/pbmc3k.bin, `make -C oracle ref`).
+from helpers import load_pbmc3k  # noqa: E402
+A = load_pbmc3k()
+if A is not None:
+    B = A[:500, :200].tocsc()
+    B.sort_indices()
+    np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "pbmc3k_500x200.npz"),
+                        indptr=B.indptr.astype(np.int32), indices=B.indices.astype(np.int32), data=B.data.astype(np.float32))
+    print("wrote pbmc3k_500x200.npz", B.shape, B.nnz)

@@ -35,3 +35,31 @@ def random_csc(m, n, density, seed, *, counts=False, ragged=False):
 
 def zero_pattern_equal(a, b):
     return bool(np.array_equal(np.asarray(a) == 0, np.asarray(b) == 0))
+
+
+def load_pbmc3k():
+    """The reference's real dataset (inst/extdata/pbmc3k.spz, 13714 x 2700 counts), decoded by the REFERENCE's
+    own StreamPress reader at build time into oracle/_ref/pbmc3k.bin (`make -C oracle ref`; git-ignored but it
+    travels to the GPU box). Returns a scipy CSC matrix or None when the fixture is not present."""
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "pbmc3k.bin")
+    if not os.path.exists(path):
+        return None
+    with open(path, "rb") as f:
+        m, n = np.fromfile(f, np.int32, 2)
+        nnz = int(np.fromfile(f, np.int64, 1)[0])
+        p = np.fromfile(f, np.int32, n + 1)
+        i = np.fromfile(f, np.int32, nnz)
+        x = np.fromfile(f, np.float32, nnz)
+    A = sp.csc_matrix((x, i, p), shape=(int(m), int(n)))
+    A.sort_indices()
+    return A
+
+
+def load_pbmc3k_block():
+    """tests/golden/pbmc3k_500x200.npz: rows 0..499, columns 0..199 of pbmc3k — the block the reference's own
+    GPU accuracy test uses (tests/testthat/test_gpu_accuracy.R:26-34). Committed; made by
+    tests/golden/make_golden.py from oracle/_ref/pbmc3k.bin."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pbmc3k_500x200.npz"))
+    return sp.csc_matrix((g["data"], g["indices"], g["indptr"]), shape=(500, 200))
