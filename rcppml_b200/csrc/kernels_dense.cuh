@@ -66,16 +66,22 @@ static __global__ void __launch_bounds__(kGramThreads) normalize_gram_kernel(flo
 #pragma unroll
         for (int b = 0; b < R; ++b) acc[a][b] = 0.0;
 
+    // Software pipeline: the next tile's rows are fetched into registers (and normalised) while the
+    // current tile is being multiplied, then converted to fp64 and stored to shared memory.
+    constexpr int PER = (TC * V4 + kGramThreads - 1) / kGramThreads;     // float4 per thread per tile
     const long long ntiles = (ncols + TC - 1) / TC;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    float4 pre[PER];
+    auto fetch = [&](long long tile) {
         const long long c0 = tile * TC;
         const long long left = ncols - c0;
         const int nc = left < TC ? static_cast<int>(left) : TC;
         float4* X4 = reinterpret_cast<float4*>(X + c0 * KP);
-        for (int t = threadIdx.x; t < TC * V4; t += blockDim.x) {
-            const int c = t / V4, q = t % V4;
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            const int t = threadIdx.x + u * kGramThreads;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (c < nc) {
+            if (t < TC * V4 && t / V4 < nc) {
+                const int q = t % V4;
                 v = X4[t];
                 if (normalize) {                     // padded coordinates hold 0 and d = 1 there
                     v.x = __fdiv_rn(v.x, sD[q * 4 + 0]);
@@ -85,13 +91,26 @@ static __global__ void __launch_bounds__(kGramThreads) normalize_gram_kernel(flo
                     X4[t] = v;
                 }
             }
-            double2* dst = reinterpret_cast<double2*>(&sX[c][q * 4]);
-            dst[0] = make_double2(static_cast<double>(v.x), static_cast<double>(v.y));
-            dst[1] = make_double2(static_cast<double>(v.z), static_cast<double>(v.w));
+            pre[u] = v;
+        }
+    };
+    long long tile = blockIdx.x;
+    if (tile < ntiles) fetch(tile);
+    for (; tile < ntiles; tile += gridDim.x) {
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            const int t = threadIdx.x + u * kGramThreads;
+            if (t < TC * V4) {
+                const int c = t / V4, q = t % V4;
+                double2* dst = reinterpret_cast<double2*>(&sX[c][q * 4]);
+                dst[0] = make_double2(static_cast<double>(pre[u].x), static_cast<double>(pre[u].y));
+                dst[1] = make_double2(static_cast<double>(pre[u].z), static_cast<double>(pre[u].w));
+            }
         }
         __syncthreads();
+        if (tile + gridDim.x < ntiles) fetch(tile + gridDim.x);      // overlaps with the DFMA loop below
         if (active) {
-#pragma unroll 2
+#pragma unroll 4
             for (int c = 0; c < TC; ++c) {
                 double av[R], bv[R];
 #pragma unroll
