@@ -108,6 +108,20 @@ void rcppml_gpu_nmf_masked_unified_float(
     int* out_status,
     double* out_tol);
 
+/* ABI EXTENSIONS for predict() / nnls() / evaluate() — the reference runs these on the CPU in fp64 and has no GPU
+ * entry for them. Same .C conventions: every scalar behind a pointer, status out.
+ *
+ * rcppml_gpu_nnls_double: Rcpp_predict (src/RcppFunctions_utils.cpp:23-53) and c_nnls (:314-366) in fp64 on the GPU.
+ *   w_T: k x m column-major fixed factor; h: k x n column-major output (and warm start when *warm_start != 0).
+ *   predict(): nonneg=1, cd_maxit=100, cd_tol=1e-8, warm_start=0.  nnls(): as passed by R/solve.R:311,339.
+ * rcppml_gpu_evaluate_double: MSE of A ~ W diag(d) H (compute_mse, :60-90); mask_zeros != 0 -> over non-zeros only. */
+void rcppml_gpu_nnls_double(const int* col_ptr, const int* row_idx, const double* values, int* m, int* n, int* nnz,
+                            int* k, const double* w_T, double* h, double* L1, double* L2, double* upper_bound,
+                            int* nonneg, int* cd_maxit, double* cd_tol, int* warm_start, int* out_status);
+void rcppml_gpu_evaluate_double(const int* col_ptr, const int* row_idx, const double* values, int* m, int* n, int* nnz,
+                                int* k, const double* w_T, const double* d, const double* h, int* mask_zeros,
+                                double* out_loss, int* out_status);
+
 /* ========================================================================
  * Part 2 — device-resident engine (ABI extension)
  * ===================================================================== */

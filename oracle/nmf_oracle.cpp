@@ -799,6 +799,65 @@ long orc_synth_csc(long m, long n_local, long col_begin, double density, uint64_
     return Ap[n_local];
 }
 
+// ---------------------------------------------------------------------------
+// src/RcppFunctions_utils.cpp:23-53 (Rcpp_predict) and :314-366 (c_nnls), fp64.
+// w_T: k×m col-major; h: k×n (in: warm start when warm_start, out: solution).
+// ---------------------------------------------------------------------------
+void orc_project_f64(const int* Ap, const int* Ai, const double* Ax, long m, long n, int k, const double* w_T,
+                     double* h, double L1, double L2, double upper_bound, int nonneg, int cd_maxit, double cd_tol,
+                     int warm_start, int threads) {
+    std::vector<double> G(static_cast<size_t>(k) * k);
+    orc::gram(w_T, k, m, G.data(), threads);                                   // :32 (adds tiny_num once)
+    for (int i = 0; i < k; ++i) G[static_cast<long>(i) * k + i] += 1e-15;      // :33 / :327 tiny_num again
+    if (L2 > 0) for (int i = 0; i < k; ++i) G[static_cast<long>(i) * k + i] += L2;
+#pragma omp parallel num_threads(std::max(1, threads))
+    {
+        std::vector<double> b(k), tmp(k);
+#pragma omp for schedule(dynamic, 16)
+        for (long j = 0; j < n; ++j) {
+            orc::gather_rhs(Ap, Ai, Ax, j, w_T, k, b.data());                  // rhs.hpp:64-68
+            double* x = h + j * k;
+            if (warm_start) {                                                  // :346-356 — no cd_tol passed
+                orc::warm_start_correct(G.data(), x, k, b.data(), tmp.data());
+                orc::cd_nnls_col_fixed(G.data(), b.data(), x, k, L1, 0.0, nonneg != 0, cd_maxit, upper_bound, 0.0);
+            } else {                                                           // nnls_batch.hpp:167-184
+                for (int i = 0; i < k; ++i) x[i] = 0.0;
+                orc::cd_nnls_col_fixed(G.data(), b.data(), x, k, L1, 0.0, nonneg != 0, cd_maxit, upper_bound, cd_tol);
+            }
+        }
+    }
+}
+
+// src/RcppFunctions_utils.cpp:60-90 (compute_mse): explicit over the non-zeros (mask_zeros) or over all m·n
+// entries through the dense reconstruction W·diag(d)·H, fp64. Dense form only for small shapes.
+double orc_evaluate_mse_f64(const int* Ap, const int* Ai, const double* Ax, long m, long n, int k, const double* w_T,
+                            const double* d, const double* h, int mask_zeros) {
+    double total = 0.0;
+    if (mask_zeros) {
+        long cnt = 0;
+        for (long j = 0; j < n; ++j)
+            for (long p = Ap[j]; p < Ap[j + 1]; ++p) {
+                double pred = 0.0;
+                for (int f = 0; f < k; ++f) pred += w_T[static_cast<long>(Ai[p]) * k + f] * d[f] * h[j * k + f];
+                const double r = Ax[p] - pred;
+                total += r * r;
+                ++cnt;
+            }
+        return cnt > 0 ? total / static_cast<double>(cnt) : 0.0;
+    }
+    std::vector<double> col(m);
+    for (long j = 0; j < n; ++j) {
+        for (long i = 0; i < m; ++i) {
+            double pred = 0.0;
+            for (int f = 0; f < k; ++f) pred += w_T[i * k + f] * d[f] * h[j * k + f];
+            col[i] = -pred;
+        }
+        for (long p = Ap[j]; p < Ap[j + 1]; ++p) col[Ai[p]] += Ax[p];
+        for (long i = 0; i < m; ++i) total += col[i] * col[i];
+    }
+    return total / (static_cast<double>(m) * static_cast<double>(n));
+}
+
 int orc_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -58,6 +58,7 @@ def lib():
         _lib.orc_trace_AtA_f32.restype = C.c_float
         _lib.orc_loss_cross_term_f32.restype = C.c_float
         _lib.orc_synth_csc.restype = C.c_long
+        _lib.orc_evaluate_mse_f64.restype = C.c_double
     return _lib
 
 
@@ -247,6 +248,33 @@ def synth_csc(m, n_local, col_begin=0, density=1e-3, seed=20260101, m_keep=None,
     lib().orc_synth_csc(C.c_long(m), C.c_long(n_local), C.c_long(col_begin), C.c_double(density), C.c_uint64(seed),
                         C.c_long(m_keep), 1, _p(Ap, C.c_int), _p(Ai, C.c_int), _p(Ax, C.c_float), threads)
     return Ap, Ai, Ax
+
+
+def project_f64(Ap, Ai, Ax, m, n, w_T, *, L1=0.0, L2=0.0, upper_bound=0.0, nonneg=True, cd_maxit=100, cd_tol=1e-8,
+                warm_start=None, threads=1):
+    """Rcpp_predict / c_nnls (src/RcppFunctions_utils.cpp:23-53, 314-366), fp64. w_T: (m, k). Returns h (n, k)."""
+    Ap, Ai = _i32(Ap), _i32(Ai)
+    Ax = np.ascontiguousarray(Ax, np.float64)
+    w_T = np.ascontiguousarray(w_T, np.float64)
+    k = w_T.shape[1]
+    h = np.zeros((n, k), np.float64) if warm_start is None else np.array(warm_start, np.float64, order="C")
+    lib().orc_project_f64(_p(Ap, C.c_int), _p(Ai, C.c_int), _p(Ax, C.c_double), C.c_long(m), C.c_long(n), k,
+                          _p(w_T, C.c_double), _p(h, C.c_double), C.c_double(L1), C.c_double(L2),
+                          C.c_double(upper_bound), int(nonneg), cd_maxit, C.c_double(cd_tol),
+                          int(warm_start is not None), threads)
+    return h
+
+
+def evaluate_mse_f64(Ap, Ai, Ax, m, n, w_T, d, h, mask_zeros=False):
+    """compute_mse (src/RcppFunctions_utils.cpp:60-90), fp64. w_T: (m, k), h: (n, k)."""
+    Ap, Ai = _i32(Ap), _i32(Ai)
+    Ax = np.ascontiguousarray(Ax, np.float64)
+    w_T = np.ascontiguousarray(w_T, np.float64)
+    h = np.ascontiguousarray(h, np.float64)
+    d = np.ascontiguousarray(d, np.float64)
+    return float(lib().orc_evaluate_mse_f64(_p(Ap, C.c_int), _p(Ai, C.c_int), _p(Ax, C.c_double), C.c_long(m),
+                                            C.c_long(n), w_T.shape[1], _p(w_T, C.c_double), _p(d, C.c_double),
+                                            _p(h, C.c_double), int(mask_zeros)))
 
 
 def max_threads() -> int:

@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "RcppML_gpu.so")
+# RCPPML_B200_LIB selects an experiment build (csrc/Makefile VARIANT=...); default is the product library.
+LIB_PATH = os.environ.get("RCPPML_B200_LIB") or os.path.join(_HERE, "lib", "RcppML_gpu.so")
 
 NUM_SECTIONS = 8
 SECTION_NAMES = ("gram_H", "fused_rhs_nnls_H", "scaling_H", "gram_W", "fused_rhs_nnls_W", "scaling_W", "loss",

@@ -83,6 +83,19 @@ __device__ __forceinline__ void sub_scaled4(float (&b)[4], const float4& g, floa
     b[3] = __fsub_rn(b[3], __fmul_rn(g.w, s));
 }
 
+// 128-bit load of a factor-row word on the read-only path. -DB200_GATHER_NOALLOC selects
+// ld.global.nc.L1::no_allocate (rows are used once per SM; don't let them evict the CSC segments).
+__device__ __forceinline__ float4 ldg_row(const float4* ptr) {
+#ifdef B200_GATHER_NOALLOC
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(ptr));
+    return r;
+#else
+    return __ldg(ptr);
+#endif
+}
+
 // ---------------------------------------------------------------------------------------------
 // Gather: b = Σ_p vals[p] · F[:, rowidx[p]] for p in [p0, p1), CSC order, per-lane coordinates.
 // idx/val are fetched LANES at a time (one coalesced segment per group) and broadcast by shuffle;
@@ -92,7 +105,11 @@ template <int LANES, int NV>
 __device__ __forceinline__ void gather_column(const HalfStepParams& p, int p0, int p1, int gl, unsigned gmask,
                                               float (&b)[NV][4]) {
     constexpr int KP = LANES * 4 * NV;
-    constexpr int UN = (LANES * NV <= 8) ? LANES : (8 / NV > 0 ? 8 / NV : 1);   // 128-bit loads in flight: 8 per lane
+#ifndef B200_GATHER_UN
+#define B200_GATHER_UN 8
+#endif
+    constexpr int UNW = B200_GATHER_UN;                                          // 128-bit loads in flight per lane
+    constexpr int UN = (LANES * NV <= UNW) ? LANES : (UNW / NV > 0 ? UNW / NV : 1);
 #pragma unroll
     for (int nv = 0; nv < NV; ++nv)
 #pragma unroll
@@ -127,7 +144,7 @@ __device__ __forceinline__ void gather_column(const HalfStepParams& p, int p0, i
                     v[u] = gshfl<LANES>(gmask, rval, s + u);
                     const float4* row = Fl + static_cast<size_t>(r) * (KP / 4);
 #pragma unroll
-                    for (int nv = 0; nv < NV; ++nv) f[u][nv] = __ldg(row + nv * LANES);
+                    for (int nv = 0; nv < NV; ++nv) f[u][nv] = ldg_row(row + nv * LANES);
                 }
 #pragma unroll
                 for (int u = 0; u < UN; ++u)

@@ -313,3 +313,38 @@ def test_multi_gpu_matches_single_gpu():
            "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "multigpu_check.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0 and "MULTIGPU_CHECK_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("k", [5, 20, 64, 100])
+def test_predict_nnls_match_reference_semantics(oracle, k):
+    """predict()/nnls() on the GPU (rcppml_gpu_nnls_double) vs Rcpp_predict / c_nnls restated in fp64."""
+    from rcppml_b200 import project
+    m, n = 700, 300
+    A = random_csc(m, n, 0.06, 70 + k, counts=True, ragged=True)
+    rng = np.random.default_rng(k)
+    w = rng.random((m, k))
+    Ax64 = A.data.astype(np.float64)
+    for kw in (dict(), dict(L1=0.05, L2=0.1), dict(upper_bound=0.3), dict(nonneg=False, L2=0.01)):
+        ref = oracle.project_f64(A.indptr, A.indices, Ax64, m, n, w, **kw)            # (n, k)
+        got = project.nnls(w, A, **kw)                                                 # (k, n)
+        assert rel_err(got.T, ref) <= 1e-9, (k, kw, rel_err(got.T, ref))
+        assert zero_pattern_equal(got.T, ref)
+    ref = oracle.project_f64(A.indptr, A.indices, Ax64, m, n, w, L1=0.02)
+    assert rel_err(project.predict(w, A, L1=0.02).T, ref) <= 1e-9
+    # c_nnls warm start: B -= G h0, CD without tolerance (src/RcppFunctions_utils.cpp:346-356)
+    h0 = rng.random((k, n)) * 0.1
+    ref = oracle.project_f64(A.indptr, A.indices, Ax64, m, n, w, warm_start=h0.T, cd_maxit=7)
+    got = project.nnls(w, A, warm_start=h0, cd_maxit=7)
+    assert rel_err(got.T, ref) <= 1e-9
+
+
+def test_evaluate_matches_dense_reconstruction(oracle):
+    from rcppml_b200 import project
+    m, n, k = 300, 200, 12
+    A = random_csc(m, n, 0.1, 77, counts=True)
+    rng = np.random.default_rng(5)
+    w, h, d = rng.random((m, k)), rng.random((k, n)), rng.random(k) + 0.5
+    for mz in (False, True):
+        ref = oracle.evaluate_mse_f64(A.indptr, A.indices, A.data.astype(np.float64), m, n, w, d, h.T, mask_zeros=mz)
+        got = project.evaluate(A, w, d, h, mask_zeros=mz)
+        assert abs(got - ref) <= 1e-10 * abs(ref), (mz, got, ref)
