@@ -27,12 +27,14 @@ struct DevState {
 
 // ---------------------------------------------------------------------------------------------
 // normalize + Gram. X is [ncols][KP] (row c = column c of the reference's k×ncols matrix).
-// G is symmetric: only the 136 lower-triangular R×R tiles of the 16×16 tile grid are computed
-// (R = KP/16), one per thread (160 threads = 5 warps, 24 idle lanes). Column tiles of TC columns are
-// staged in shared memory ALREADY CONVERTED to fp64 (one F2F per element per tile instead of one per
-// element per column per thread); the inner loop is LDS.64/128 + DFMA only.
+// G is symmetric: of the 16×16 grid of R×R tiles (R = KP/16) only the lower triangle is needed. A warp owns
+// a 4×8 block of tiles (lane -> tile row 4·bi + lane/8, tile column 8·bj + lane%8) so that a shared-memory
+// read of the warp touches only 4 (rows) or 8 (columns) distinct 32-byte chunks — 1 wavefront per LDS.128;
+// 6 of the 8 blocks intersect the lower triangle -> 6 warps. Column tiles of TC columns are staged in shared
+// memory ALREADY CONVERTED to fp64 (rows padded by 16 B per 128 B against bank conflicts); the next tile is
+// prefetched into registers while the current one is multiplied; the inner loop is LDS.128 + DFMA only.
 // ---------------------------------------------------------------------------------------------
-constexpr int kGramThreads = 160;
+constexpr int kGramThreads = 192;
 
 template <int KP, int TC>
 static __global__ void __launch_bounds__(kGramThreads) normalize_gram_kernel(float* __restrict__ X, long long ncols,
@@ -41,20 +43,19 @@ static __global__ void __launch_bounds__(kGramThreads) normalize_gram_kernel(flo
                                                              const int* __restrict__ stop_flag) {
     constexpr int R = KP / 16;
     constexpr int V4 = KP / 4;                       // float4 per column
-    __shared__ __align__(16) double sX[TC][KP];
+    constexpr int ROWD = KP + (KP / 16) * 2;         // doubles per staged row incl. padding (2 doubles per 16)
+    __shared__ __align__(16) double sX[TC][ROWD];
     __shared__ float sD[KP];
     if (*stop_flag) return;
     for (int t = threadIdx.x; t < KP; t += blockDim.x) sD[t] = normalize ? d[t] : 1.f;
     __syncthreads();
 
-    // thread -> lower-triangular tile (ti >= tj): t = ti(ti+1)/2 + tj
-    int ti = 0, tj = 0;
-    const bool active = threadIdx.x < 136;
-    if (active) {
-        int t = threadIdx.x;
-        while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
-        tj = t - ti * (ti + 1) / 2;
-    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bi = (warp < 4) ? warp : warp - 2;     // blocks (0,0) (1,0) (2,0) (3,0) (2,1) (3,1)
+    const int bj = (warp < 4) ? 0 : 1;
+    const int ti = 4 * bi + (lane >> 3), tj = 8 * bj + (lane & 7);
+    auto pos = [](int i) { return i + (i / 16) * 2; };          // padded position of coordinate i in a staged row
+    const int pa = pos(ti * R), pb = pos(tj * R);               // R <= 8 consecutive coordinates never straddle a pad
     // fp64 accumulation of exact fp32×fp32 products: the result, rounded once to fp32 by
     // gram_from_sums_kernel, is the order-independent "correctly rounded" Gram the oracle defines
     // (oracle/nmf_oracle.cpp gram()). A G that matches bit for bit keeps every column solve
@@ -66,8 +67,6 @@ static __global__ void __launch_bounds__(kGramThreads) normalize_gram_kernel(flo
 #pragma unroll
         for (int b = 0; b < R; ++b) acc[a][b] = 0.0;
 
-    // Software pipeline: the next tile's rows are fetched into registers (and normalised) while the
-    // current tile is being multiplied, then converted to fp64 and stored to shared memory.
     constexpr int PER = (TC * V4 + kGramThreads - 1) / kGramThreads;     // float4 per thread per tile
     const long long ntiles = (ncols + TC - 1) / TC;
     float4 pre[PER];
@@ -102,30 +101,28 @@ static __global__ void __launch_bounds__(kGramThreads) normalize_gram_kernel(flo
             const int t = threadIdx.x + u * kGramThreads;
             if (t < TC * V4) {
                 const int c = t / V4, q = t % V4;
-                double2* dst = reinterpret_cast<double2*>(&sX[c][q * 4]);
+                double2* dst = reinterpret_cast<double2*>(&sX[c][pos(q * 4)]);
                 dst[0] = make_double2(static_cast<double>(pre[u].x), static_cast<double>(pre[u].y));
                 dst[1] = make_double2(static_cast<double>(pre[u].z), static_cast<double>(pre[u].w));
             }
         }
         __syncthreads();
         if (tile + gridDim.x < ntiles) fetch(tile + gridDim.x);      // overlaps with the DFMA loop below
-        if (active) {
 #pragma unroll 4
-            for (int c = 0; c < TC; ++c) {
-                double av[R], bv[R];
+        for (int c = 0; c < TC; ++c) {
+            double av[R], bv[R];
 #pragma unroll
-                for (int a = 0; a < R; ++a) av[a] = sX[c][ti * R + a];
+            for (int a = 0; a < R; ++a) av[a] = sX[c][pa + a];
 #pragma unroll
-                for (int b = 0; b < R; ++b) bv[b] = sX[c][tj * R + b];
+            for (int b = 0; b < R; ++b) bv[b] = sX[c][pb + b];
 #pragma unroll
-                for (int a = 0; a < R; ++a)
+            for (int a = 0; a < R; ++a)
 #pragma unroll
-                    for (int b = 0; b < R; ++b) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
-            }
+                for (int b = 0; b < R; ++b) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
         }
         __syncthreads();
     }
-    if (active) {
+    if (ti >= tj) {                                  // tiles above the diagonal are redundant
         double* out = partials + static_cast<size_t>(blockIdx.x) * KP * KP;
 #pragma unroll
         for (int a = 0; a < R; ++a)

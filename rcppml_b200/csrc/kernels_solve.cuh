@@ -375,8 +375,11 @@ __device__ __forceinline__ void chol_solve(const float* sLz, const float* sLTz, 
 //   BSRC_LOAD  : b = Σ_slots B[slot][col] in slot order (multi-GPU: partial RHS from every rank)
 //   OUT_SOLVE  : solve and write X;  OUT_RHS: write the raw gathered b to B[0] (partial RHS)
 // ---------------------------------------------------------------------------------------------
+#ifndef B200_SOLVE_MIN_CTAS
+#define B200_SOLVE_MIN_CTAS 3   // <= 85 registers: 3 CTAs (24 warps) per SM; 4 CTAs (64 regs) spills and is no faster
+#endif
 template <int LANES, int NV, int SOLVER, int BSRC, int OUT>
-__global__ void __launch_bounds__(256) half_step_kernel(const HalfStepParams p) {
+__global__ void __launch_bounds__(256, B200_SOLVE_MIN_CTAS) half_step_kernel(const HalfStepParams p) {
     constexpr int KP = LANES * 4 * NV;
     constexpr int GPW = 32 / LANES;   // groups per warp
     extern __shared__ __align__(16) float smem[];
