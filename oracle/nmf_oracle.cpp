@@ -469,6 +469,14 @@ T masked_loss(const int* Ap, const int* Ai, const T* Ax, long m, long n, const T
 // ===========================================================================
 // C interface (ctypes)
 // ===========================================================================
+static int orc_max_threads_impl() {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
 extern "C" {
 
 typedef struct {
@@ -856,6 +864,236 @@ double orc_evaluate_mse_f64(const int* Ap, const int* Ai, const double* Ax, long
         for (long i = 0; i < m; ++i) total += col[i] * col[i];
     }
     return total / (static_cast<double>(m) * static_cast<double>(n));
+}
+
+// ---------------------------------------------------------------------------
+// nmf/fit_cv.hpp:124-1667 — nmf_fit_cv<CPU,float,Sparse>: speckled-mask cross-validation NMF, restricted to
+// the sparse / MSE / standard-variant / no-user-mask path. The lazy mask is
+// nmf/speckled_cv.hpp:58-160 (SplitMix64 position hash, integer — bit-exact everywhere).
+// Order-opaque pieces: the per-column Gram correction (Eigen rankUpdate(-1), cv_detail.hpp:67-85) is restated
+// as sequential fp32 rank-1 downdates in test-row order; dots / norms / loss sums are fp64-accumulated.
+// ---------------------------------------------------------------------------
+typedef struct {
+    int k, max_iter;
+    float tol;
+    float L1_W, L1_H, L2_W, L2_H, ub_W, ub_H;
+    int nonneg_W, nonneg_H;
+    int cd_maxit;
+    int norm_type, solver_mode;
+    int cv_patience;             // core/config.hpp:257 (default 5; not on the bridge wire)
+    int threads;
+    float holdout_fraction;      // core/config.hpp:236
+    uint32_t cv_seed, seed;      // effective_cv_seed(): cv_seed != 0 ? cv_seed : seed (core/config.hpp:416-418)
+    int mask_zeros;
+} orc_cv_config;
+
+typedef struct {
+    int iterations, converged, best_iter;
+    float train_loss, test_loss, best_test_loss, final_tol;
+    double loop_seconds;
+    long n_test;                 // held-out entries (last evaluation)
+} orc_cv_result;
+
+static void cv_solve_col(const float* G, const float* F, const std::vector<int>& test, int k, float* Gl, float* Lc,
+                         float* b, float* x, float L1, bool nonneg, int cd_maxit, int solver_mode) {
+    std::copy(G, G + static_cast<long>(k) * k, Gl);                              // cv_detail.hpp:74
+    for (int r : test) {                                                         // :75-84 (restated, see header)
+        const float* f = F + static_cast<long>(r) * k;
+        for (int c = 0; c < k; ++c)
+            for (int a = 0; a < k; ++a) Gl[static_cast<long>(c) * k + a] -= f[a] * f[c];
+    }
+    if (solver_mode == 1) {                                                      // cholesky_clip.hpp:65-106
+        if (L1 > 0) for (int i = 0; i < k; ++i) b[i] -= L1;
+        orc::cholesky_factor(Gl, k, Lc);
+        std::copy(b, b + k, x);
+        orc::cholesky_solve_inplace(Lc, k, x);
+        if (nonneg) for (int i = 0; i < k; ++i) x[i] = std::max(x[i], 0.f);
+    } else {                                                                     // fit_cv.hpp:469-472: no cd_tol
+        orc::cd_nnls_col_fixed(Gl, b, x, k, L1, 0.f, nonneg, cd_maxit, 0.f, 0.f);
+    }
+}
+
+int orc_nmf_fit_cv_f32(const int* Ap, const int* Ai, const float* Ax, long m, long n, const orc_cv_config* cfg,
+                       float* W_T, float* H, float* d, float* train_hist, float* test_hist, orc_cv_result* res) {
+    using namespace orc;
+    const int k = cfg->k;
+    if (k <= 0 || cfg->max_iter <= 0 || cfg->cd_maxit <= 0) return -1;
+    const long nnz = Ap[n];
+    const int threads = cfg->threads > 0 ? cfg->threads : orc_max_threads_impl();
+    // speckled_cv.hpp:117-127
+    const uint32_t eff = cfg->cv_seed != 0 ? cfg->cv_seed : cfg->seed;
+    const uint64_t mseed = (eff == 0) ? 12345ULL : static_cast<uint64_t>(eff);
+    const double hf = static_cast<double>(cfg->holdout_fraction);               // fit_cv.hpp:183
+    const uint64_t inv_prob = hf > 0 ? static_cast<uint64_t>(1.0 / hf) : 0;
+    auto held = [&](long i, long j) {
+        return SplitMix64::is_holdout(mseed, static_cast<uint32_t>(i), static_cast<uint32_t>(j), inv_prob);
+    };
+    const bool mz = cfg->mask_zeros != 0;
+    for (int i = 0; i < k; ++i) d[i] = 1.f;
+    const float trAtA = trace_AtA(Ax, nnz);                                      // :351
+    std::vector<int> Atp(m + 1), Ati(nnz);
+    std::vector<float> Atx(nnz);
+    transpose_csc(Ap, Ai, Ax, m, n, Atp.data(), Ati.data(), Atx.data());
+    std::vector<float> G(static_cast<size_t>(k) * k), G_H_saved(G.size()), G_W_new(G.size());
+    std::vector<float> B_W_full(static_cast<size_t>(k) * m);
+    float prev_conv_loss = std::numeric_limits<float>::max();                   // :348
+    float best_test_loss = std::numeric_limits<float>::max();                   // :354
+    int best_iter = 0, patience_count = 0;
+    *res = orc_cv_result{};
+    const auto t0 = std::chrono::high_resolution_clock::now();
+
+    auto normalise = [&](float* X, long cols) {                                  // :536-548 / :849-858
+        if (cfg->norm_type == 2) { for (int i = 0; i < k; ++i) d[i] = 1.f; return; }
+        extract_scaling(X, k, cols, d, cfg->norm_type, threads);
+    };
+
+    for (int iter = 0; iter < cfg->max_iter; ++iter) {
+        // ---------------- H update (:409-476)
+        gram(W_T, k, m, G.data(), threads);
+        for (int i = 0; i < k; ++i) G[static_cast<long>(i) * k + i] += 1e-15f;   // :414
+        if (cfg->L2_H > 0) for (int i = 0; i < k; ++i) G[static_cast<long>(i) * k + i] += cfg->L2_H;
+#pragma omp parallel num_threads(threads)
+        {
+            std::vector<float> b(k), x(k), Gl(static_cast<size_t>(k) * k), Lc(Gl.size());
+            std::vector<int> test;
+#pragma omp for schedule(dynamic, 64)
+            for (long j = 0; j < n; ++j) {
+                std::fill(b.begin(), b.end(), 0.f);                              // cv_detail.hpp:305-340
+                test.clear();
+                if (mz) {
+                    for (long p = Ap[j]; p < Ap[j + 1]; ++p) {
+                        if (held(Ai[p], j)) test.push_back(Ai[p]);
+                        else { const float v = Ax[p]; const float* f = W_T + static_cast<long>(Ai[p]) * k;
+                               for (int t = 0; t < k; ++t) b[t] += v * f[t]; }
+                    }
+                } else {
+                    long p = Ap[j];
+                    for (long i = 0; i < m; ++i) {
+                        float v = 0.f;
+                        if (p < Ap[j + 1] && Ai[p] == i) { v = Ax[p]; ++p; }
+                        if (held(i, j)) test.push_back(static_cast<int>(i));
+                        else if (v != 0.f) { const float* f = W_T + i * k; for (int t = 0; t < k; ++t) b[t] += v * f[t]; }
+                    }
+                }
+                std::copy(H + j * k, H + (j + 1) * k, x.begin());                // :460 x_local = H.col(j)
+                cv_solve_col(G.data(), W_T, test, k, Gl.data(), Lc.data(), b.data(), x.data(), cfg->L1_H,
+                             cfg->nonneg_H != 0, cfg->cd_maxit, cfg->solver_mode);
+                std::copy(x.begin(), x.end(), H + j * k);
+            }
+        }
+        if (cfg->ub_H > 0) apply_upper_bound(H, static_cast<long>(k) * n, cfg->ub_H);     // :528-529
+        normalise(H, n);
+
+        // ---------------- W update (:560-735)
+        gram(H, k, n, G.data(), threads);
+        G_H_saved = G;                                                           // :573-576
+        for (int i = 0; i < k; ++i) G[static_cast<long>(i) * k + i] += 1e-15f;   // :578
+        if (cfg->L2_W > 0) for (int i = 0; i < k; ++i) G[static_cast<long>(i) * k + i] += cfg->L2_W;
+#pragma omp parallel num_threads(threads)
+        {
+            std::vector<float> b(k), bf(k), x(k), Gl(static_cast<size_t>(k) * k), Lc(Gl.size());
+            std::vector<int> test;
+            std::vector<float> tval;
+#pragma omp for schedule(dynamic, 64)
+            for (long i = 0; i < m; ++i) {
+                std::fill(b.begin(), b.end(), 0.f);                              // cv_detail.hpp:357-405
+                test.clear(); tval.clear();
+                if (mz) {
+                    for (long p = Atp[i]; p < Atp[i + 1]; ++p) {
+                        if (held(i, Ati[p])) { test.push_back(Ati[p]); tval.push_back(Atx[p]); }
+                        else { const float v = Atx[p]; const float* f = H + static_cast<long>(Ati[p]) * k;
+                               for (int t = 0; t < k; ++t) b[t] += v * f[t]; }
+                    }
+                } else {
+                    long p = Atp[i];
+                    for (long c = 0; c < n; ++c) {
+                        float v = 0.f;
+                        if (p < Atp[i + 1] && Ati[p] == c) { v = Atx[p]; ++p; }
+                        if (held(i, c)) { test.push_back(static_cast<int>(c)); tval.push_back(v); }
+                        else if (v != 0.f) { const float* f = H + c * k; for (int t = 0; t < k; ++t) b[t] += v * f[t]; }
+                    }
+                }
+                bf = b;                                                          // :609-653 full RHS (train, then test entries)
+                for (size_t q = 0; q < test.size(); ++q)
+                    if (tval[q] != 0.f) { const float* f = H + static_cast<long>(test[q]) * k;
+                                          for (int t = 0; t < k; ++t) bf[t] += tval[q] * f[t]; }
+                std::copy(bf.begin(), bf.end(), B_W_full.begin() + i * k);
+                std::copy(W_T + i * k, W_T + (i + 1) * k, x.begin());            // :700
+                cv_solve_col(G.data(), H, test, k, Gl.data(), Lc.data(), b.data(), x.data(), cfg->L1_W,
+                             cfg->nonneg_W != 0, cfg->cd_maxit, cfg->solver_mode);
+                std::copy(x.begin(), x.end(), W_T + i * k);
+            }
+        }
+        if (cfg->ub_W > 0) apply_upper_bound(W_T, static_cast<long>(k) * m, cfg->ub_W);   // :843-844
+        normalise(W_T, m);
+
+        // ---------------- loss (:1349-1548), every iteration (cv_patience > 0, track_train_loss)
+        double test_sq = 0.0;
+        long n_test = 0;
+#pragma omp parallel for num_threads(threads) schedule(dynamic, 64) reduction(+ : test_sq, n_test)
+        for (long j = 0; j < n; ++j) {
+            auto pred_at = [&](long i) {
+                double s = 0.0;
+                for (int f = 0; f < k; ++f) s += static_cast<double>(W_T[i * k + f] * d[f]) * static_cast<double>(H[j * k + f]);
+                return static_cast<float>(s);
+            };
+            if (mz) {
+                for (long p = Ap[j]; p < Ap[j + 1]; ++p)
+                    if (held(Ai[p], j)) { const float df = Ax[p] - pred_at(Ai[p]); test_sq += static_cast<double>(df * df); ++n_test; }
+            } else {
+                long p = Ap[j];
+                for (long i = 0; i < m; ++i) {
+                    if (held(i, j)) {
+                        float a = 0.f;
+                        if (p < Ap[j + 1] && Ai[p] == i) { a = Ax[p]; ++p; }
+                        const float df = a - pred_at(i);
+                        test_sq += static_cast<double>(df * df);
+                        ++n_test;
+                    } else if (p < Ap[j + 1] && Ai[p] == i) ++p;
+                }
+            }
+        }
+        const float test_sq_error = static_cast<float>(test_sq);
+        double cross = 0.0;                                                      // :1511-1515
+        for (long i = 0; i < m; ++i)
+            for (int r = 0; r < k; ++r)
+                cross += static_cast<double>(d[r] * W_T[i * k + r]) * static_cast<double>(B_W_full[i * k + r]);
+        gram(W_T, k, m, G_W_new.data(), threads);                                // :1518-1519
+        double recon = 0.0;
+        for (int r = 0; r < k; ++r)
+            for (int s2 = 0; s2 < k; ++s2)
+                recon += static_cast<double>(d[r] * d[s2] * G_W_new[static_cast<long>(s2) * k + r] *
+                                             G_H_saved[static_cast<long>(s2) * k + r]);
+        const float total_sq = std::max(trAtA - 2.f * static_cast<float>(cross) + static_cast<float>(recon), 0.f);
+        const float train_sq_error = std::max(total_sq - test_sq_error, 0.f);     // :1533
+        const long total_entries = mz ? nnz : m * n;
+        const long n_train = total_entries - n_test;
+        const float train_loss = n_train > 0 ? train_sq_error / static_cast<float>(n_train) : 0.f;
+        const float test_loss = n_test > 0 ? test_sq_error / static_cast<float>(n_test) : 0.f;
+        if (train_hist) train_hist[iter] = train_loss;
+        if (test_hist) test_hist[iter] = test_loss;
+        res->train_loss = train_loss; res->test_loss = test_loss; res->n_test = n_test;
+
+        float rel = 0.f;                                                         // :1565-1569
+        if (iter > 0) rel = std::abs(prev_conv_loss - test_loss) / (std::abs(prev_conv_loss) + 1e-15f);
+        if (test_loss < best_test_loss) { best_test_loss = test_loss; best_iter = iter; patience_count = 0; }   // :1584-1590
+        else ++patience_count;
+        if (cfg->cv_patience > 0 && patience_count >= cfg->cv_patience) {        // :1600-1606
+            res->iterations = iter + 1; res->converged = 0; break;
+        }
+        if (iter > 0) {                                                          // :1609-1619
+            res->final_tol = rel;
+            if (rel < cfg->tol) { res->iterations = iter + 1; res->converged = 1; break; }
+        }
+        prev_conv_loss = test_loss;
+        res->iterations = iter + 1;
+    }
+    res->loop_seconds = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
+    res->best_test_loss = best_test_loss;
+    res->best_iter = best_iter;
+    for (long j = 0; j < n; ++j)                                                 // :1639-1641 absorb d into H
+        for (int i = 0; i < k; ++i) H[j * k + i] *= d[i];
+    return 0;
 }
 
 int orc_max_threads(void) {

@@ -44,6 +44,25 @@ class _Res(C.Structure):
     ]
 
 
+class _CvCfg(C.Structure):
+    _fields_ = [
+        ("k", C.c_int), ("max_iter", C.c_int), ("tol", C.c_float),
+        ("L1_W", C.c_float), ("L1_H", C.c_float), ("L2_W", C.c_float), ("L2_H", C.c_float),
+        ("ub_W", C.c_float), ("ub_H", C.c_float), ("nonneg_W", C.c_int), ("nonneg_H", C.c_int),
+        ("cd_maxit", C.c_int), ("norm_type", C.c_int), ("solver_mode", C.c_int), ("cv_patience", C.c_int),
+        ("threads", C.c_int), ("holdout_fraction", C.c_float), ("cv_seed", C.c_uint32), ("seed", C.c_uint32),
+        ("mask_zeros", C.c_int),
+    ]
+
+
+class _CvRes(C.Structure):
+    _fields_ = [
+        ("iterations", C.c_int), ("converged", C.c_int), ("best_iter", C.c_int),
+        ("train_loss", C.c_float), ("test_loss", C.c_float), ("best_test_loss", C.c_float), ("final_tol", C.c_float),
+        ("loop_seconds", C.c_double), ("n_test", C.c_long),
+    ]
+
+
 _lib = None
 
 
@@ -275,6 +294,49 @@ def evaluate_mse_f64(Ap, Ai, Ax, m, n, w_T, d, h, mask_zeros=False):
     return float(lib().orc_evaluate_mse_f64(_p(Ap, C.c_int), _p(Ai, C.c_int), _p(Ax, C.c_double), C.c_long(m),
                                             C.c_long(n), w_T.shape[1], _p(w_T, C.c_double), _p(d, C.c_double),
                                             _p(h, C.c_double), int(mask_zeros)))
+
+
+@dataclass
+class OracleCvResult:
+    W_T: np.ndarray          # (m, k) normalised
+    H: np.ndarray            # (n, k) with d absorbed (fit_cv.hpp:1639-1641)
+    d: np.ndarray
+    iterations: int
+    converged: bool
+    best_iter: int
+    train_loss: float
+    test_loss: float
+    best_test_loss: float
+    final_tol: float
+    n_test: int
+    train_history: np.ndarray
+    test_history: np.ndarray
+    loop_seconds: float
+
+
+def nmf_fit_cv(Ap, Ai, Ax, m, n, k, W_T0, H0, *, max_iter=100, tol=1e-4, L1=(0.0, 0.0), L2=(0.0, 0.0),
+               upper_bound=(0.0, 0.0), nonneg=(True, True), cd_maxit=100, norm_type=0, solver_mode=0, cv_patience=5,
+               threads=0, holdout_fraction=0.1, cv_seed=0, seed=42, mask_zeros=True) -> OracleCvResult:
+    """nmf_fit_cv<CPU,float,Sparse> (nmf/fit_cv.hpp:124), MSE / standard variant / no user mask."""
+    Ap, Ai, Ax = _i32(Ap), _i32(Ai), _f32(Ax)
+    W_T, H = _f32(W_T0).copy(), _f32(H0).copy()
+    d = np.ones(k, np.float32)
+    cfg = _CvCfg(k=k, max_iter=max_iter, tol=tol, L1_W=L1[0], L1_H=L1[1], L2_W=L2[0], L2_H=L2[1],
+                 ub_W=upper_bound[0], ub_H=upper_bound[1], nonneg_W=int(nonneg[0]), nonneg_H=int(nonneg[1]),
+                 cd_maxit=cd_maxit, norm_type=norm_type, solver_mode=solver_mode, cv_patience=cv_patience,
+                 threads=threads, holdout_fraction=holdout_fraction, cv_seed=cv_seed, seed=seed,
+                 mask_zeros=int(mask_zeros))
+    tr, te = np.zeros(max_iter, np.float32), np.zeros(max_iter, np.float32)
+    res = _CvRes()
+    rc = lib().orc_nmf_fit_cv_f32(_p(Ap, C.c_int), _p(Ai, C.c_int), _p(Ax, C.c_float), C.c_long(m), C.c_long(n),
+                                  C.byref(cfg), _p(W_T, C.c_float), _p(H, C.c_float), _p(d, C.c_float),
+                                  _p(tr, C.c_float), _p(te, C.c_float), C.byref(res))
+    if rc != 0:
+        raise ValueError("oracle: invalid CV configuration")
+    it = res.iterations
+    return OracleCvResult(W_T, H, d, it, bool(res.converged), res.best_iter, res.train_loss, res.test_loss,
+                          res.best_test_loss, res.final_tol, res.n_test, tr[:it].copy(), te[:it].copy(),
+                          res.loop_seconds)
 
 
 def max_threads() -> int:

@@ -520,10 +520,14 @@ int Engine::geometry_for(long long nnz_, long long ncols) const {
     return nv == 2 ? 100 + KP / 8 : LANES;
 }
 
-static int pick_cols_per_fetch(long long nnz, long long ncols) {
-    // ~2K non-zeros per group fetch bounds the tail imbalance; 1..16 columns
+static int pick_cols_per_fetch(long long nnz, long long ncols, int num_sms) {
+    // ~2K non-zeros per group fetch bounds the tail imbalance; 1..16 columns. With few columns per rank
+    // (sharded runs) also keep >= ~8 fetches per resident warp, or half the warps would sit idle while the
+    // others work through an oversized batch (measured: 125K rows on 8 GPUs took 2x their share).
     const double avg = ncols > 0 ? static_cast<double>(nnz) / static_cast<double>(ncols) : 1.0;
     int c = static_cast<int>(2048.0 / std::max(1.0, avg));
+    const long long groups = static_cast<long long>(num_sms) * 3 * 8 * 4;      // resident lane groups (upper bound)
+    c = static_cast<int>(std::min<long long>(c, std::max<long long>(1, ncols / (groups * 8))));
     return std::max(1, std::min(16, c));
 }
 
@@ -549,7 +553,7 @@ HalfStepParams Engine::solve_params(int which, bool warm) const {
     p.warm = warm ? 1 : 0;
     p.norm_type = cfg.norm_type;
     p.want_cross = h ? 0 : 1;
-    p.cols_per_fetch = pick_cols_per_fetch(h ? nnz : nnz_w, p.ncols);
+    p.cols_per_fetch = pick_cols_per_fetch(h ? nnz : nnz_w, p.ncols, num_sms);
     p.work_counter = counters.ptr + which;
     p.partials = solve_partials.ptr;
     p.stop_flag = &state.ptr->stop;
