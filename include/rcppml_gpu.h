@@ -70,6 +70,31 @@ void rcppml_gpu_nmf_unified_float(
     int* out_status,
     double* out_tol);
 
+/* Replaces src/gpu_bridge_nmf.cu:340-455; function-pointer type gpu/bridge_nmf.hpp:78-99 (51 pointers), called by
+ * bridge_nmf_cv_sparse (gpu/bridge_nmf.hpp:399+). Speckled-mask cross-validation NMF; cv_patience is not on the
+ * wire (default 5). Unsupported (status -1): non-MSE loss, graphs, projective, symmetric, k > 128. */
+void rcppml_gpu_nmf_cv_unified_float(
+    const int* col_ptr, const int* row_idx, const double* values,
+    int* m, int* n, int* nnz, int* k,
+    double* W, double* H, double* d,
+    int* max_iter, double* tol,
+    double* L1_H, double* L1_W, double* L2_H, double* L2_W,
+    int* cd_maxit, int* verbose, int* seed,
+    double* holdout_frac, int* cv_seed, int* mask_zeros,
+    int* nonneg_W, int* nonneg_H,
+    int* norm_type,
+    int* loss_type, double* huber_delta,
+    int* irls_max_iter, double* irls_tol,
+    const int* graph_W_p, const int* graph_W_i, const double* graph_W_x,
+    int* graph_W_dim, int* graph_W_nnz, double* graph_W_lambda,
+    const int* graph_H_p, const int* graph_H_i, const double* graph_H_x,
+    int* graph_H_dim, int* graph_H_nnz, double* graph_H_lambda,
+    int* projective, int* symmetric, int* solver_mode,
+    int* out_iter, int* out_converged,
+    double* out_train_loss, double* out_test_loss,
+    double* out_best_test, int* out_best_iter,
+    int* out_status);
+
 /* ABI EXTENSION of Part 1: the same call with the explicit user mask, which the reference bridge does not carry
  * (gpu/bridge_nmf.hpp:39-75). mask_p[n+1] / mask_i[*mask_nnz]: CSC pattern of the masked entries of A
  * (nmf/masked_nnls.hpp:97-282; the fit then follows fit_cpu.hpp:560-564, :799-810, :1686-1691).
@@ -154,6 +179,21 @@ typedef struct {
     double loop_ms;         /* CUDA-event time of iterations run by the last fit/iterate */
 } rcppml_b200_result;
 
+/* Cross-validation (nmf/fit_cv.hpp): speckled hold-out mask evaluated in-kernel from a position hash. */
+typedef struct {
+    float    holdout_fraction;   /* core/config.hpp:236; inv_prob = (uint64)(1/(double)fraction): 0.1f -> 9 */
+    uint32_t cv_seed;            /* 0 -> use seed (core/config.hpp:416-418); effective 0 -> 12345 */
+    uint32_t seed;
+    int      mask_zeros;         /* 1: only non-zeros can be held out; 0: every cell of A is hashed */
+    int      cv_patience;        /* core/config.hpp:257 (default 5; <0 -> 5); 0 disables early stopping */
+} rcppml_b200_cv_config;
+
+typedef struct {
+    float   train_loss, test_loss, best_test_loss;   /* mean squared errors (fit_cv.hpp:1544-1547) */
+    int     best_iter;
+    int64_t n_test;
+} rcppml_b200_cv_result;
+
 /* Named sections follow the reference profiler (profiling/cpu_timer.hpp; fit_cpu.hpp:490-536). */
 enum {
     RCPPML_B200_SEC_GRAM_H = 0,        /* "gram_H"            */
@@ -218,6 +258,11 @@ int rcppml_b200_begin_fit(rcppml_b200_engine* e, const rcppml_b200_config* cfg);
 int rcppml_b200_iterate(rcppml_b200_engine* e, int n_iters);
 int rcppml_b200_fit(rcppml_b200_engine* e, const rcppml_b200_config* cfg);   /* begin_fit + iterate(max_iter) */
 int rcppml_b200_get_result(rcppml_b200_engine* e, rcppml_b200_result* out);
+/* nmf_fit_cv (single GPU): MSE, standard variant, no user mask. On return H has d absorbed (fit_cv.hpp:1639-1641),
+ * get_result gives iterations / converged / final_tol, get_cv_result the losses. */
+int rcppml_b200_fit_cv(rcppml_b200_engine* e, const rcppml_b200_config* cfg, const rcppml_b200_cv_config* cv);
+int rcppml_b200_get_cv_result(rcppml_b200_engine* e, rcppml_b200_cv_result* out);
+int rcppml_b200_get_cv_history(rcppml_b200_engine* e, float* train, float* test, int capacity);
 int rcppml_b200_get_loss_history(rcppml_b200_engine* e, float* out, int capacity);
 /* Per-section CUDA-event times (ms) and launch counts accumulated since begin_fit. */
 int rcppml_b200_set_profiling(rcppml_b200_engine* e, int enabled);

@@ -41,6 +41,18 @@ class Result(C.Structure):
     ]
 
 
+class CvConfig(C.Structure):
+    """rcppml_b200_cv_config (include/rcppml_gpu.h)."""
+    _fields_ = [("holdout_fraction", C.c_float), ("cv_seed", C.c_uint32), ("seed", C.c_uint32),
+                ("mask_zeros", C.c_int), ("cv_patience", C.c_int)]
+
+
+class CvResult(C.Structure):
+    """rcppml_b200_cv_result (include/rcppml_gpu.h)."""
+    _fields_ = [("train_loss", C.c_float), ("test_loss", C.c_float), ("best_test_loss", C.c_float),
+                ("best_iter", C.c_int), ("n_test", C.c_int64)]
+
+
 _lib = None
 
 
@@ -89,6 +101,9 @@ def load() -> C.CDLL:
     lib.rcppml_b200_begin_fit.argtypes = [E, C.POINTER(Config)]
     lib.rcppml_b200_iterate.argtypes = [E, C.c_int]
     lib.rcppml_b200_fit.argtypes = [E, C.POINTER(Config)]
+    lib.rcppml_b200_fit_cv.argtypes = [E, C.POINTER(Config), C.POINTER(CvConfig)]
+    lib.rcppml_b200_get_cv_result.argtypes = [E, C.POINTER(CvResult)]
+    lib.rcppml_b200_get_cv_history.argtypes = [E, fp, fp, C.c_int]
     lib.rcppml_b200_get_result.argtypes = [E, C.POINTER(Result)]
     lib.rcppml_b200_get_loss_history.argtypes = [E, fp, C.c_int]
     lib.rcppml_b200_set_profiling.argtypes = [E, C.c_int]

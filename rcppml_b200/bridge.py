@@ -141,3 +141,73 @@ def bridge_nmf_sparse(indptr, indices, data, m, n, k, W_T0, H0, **kw) -> BridgeR
     call = PackedCall(col_ptr, row_idx, values, m, n, k, W, H, **kw)()
     return BridgeResult(W.astype(np.float32), H.astype(np.float32), call.d.astype(np.float32), call.iterations,
                         call.converged, call.train_loss, call.final_tol, call.status)
+
+
+@dataclass
+class BridgeCvResult:
+    W_T: np.ndarray
+    H: np.ndarray            # d absorbed (fit_cv.hpp:1639-1646)
+    d: np.ndarray
+    iterations: int
+    converged: bool
+    train_loss: float
+    test_loss: float
+    best_test_loss: float
+    best_iter: int
+    status: int
+
+
+def bridge_nmf_cv_sparse(indptr, indices, data, m, n, k, W_T0, H0, *, max_iter=100, tol=1e-4, L1=(0.0, 0.0),
+                         L2=(0.0, 0.0), nonneg=(True, True), cd_maxit=100, verbose=False, seed=42, holdout_fraction=0.1,
+                         cv_seed=0, mask_zeros=True, norm_type=0, loss_type=0, projective=False, symmetric=False,
+                         solver_mode=0) -> BridgeCvResult:
+    """ctypes twin of bridge_nmf_cv_sparse (gpu/bridge_nmf.hpp:399+): the 51-pointer
+    rcppml_gpu_nmf_cv_unified_float call (type at gpu/bridge_nmf.hpp:78-99). Pairs are (W, H)."""
+    lib = _lib.load()
+    col_ptr = np.ascontiguousarray(indptr, dtype=np.int32)
+    row_idx = np.ascontiguousarray(indices, dtype=np.int32)
+    values = np.ascontiguousarray(data, dtype=np.float64)
+    W = np.array(W_T0, dtype=np.float64, order="C")
+    H = np.array(H0, dtype=np.float64, order="C")
+    d = np.ones(k, dtype=np.float64)
+    I, D = C.c_int, C.c_double
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    keep = []
+
+    def i_(v):
+        x = I(int(v)); keep.append(x); return C.byref(x)
+
+    def d_(v):
+        x = D(float(v)); keep.append(x); return C.byref(x)
+
+    one_i, one_d = np.zeros(1, np.int32), np.zeros(1, np.float64)
+    out_iter, out_conv, out_best_iter, out_status = I(0), I(0), I(0), I(0)
+    out_train, out_test, out_best = D(0.0), D(0.0), D(0.0)
+    args = [
+        ip(col_ptr), ip(row_idx), dp(values),
+        i_(m), i_(n), i_(int(col_ptr[n])), i_(k),
+        dp(W), dp(H), dp(d),
+        i_(max_iter), d_(tol),
+        d_(L1[1]), d_(L1[0]), d_(L2[1]), d_(L2[0]),
+        i_(cd_maxit), i_(verbose), i_(seed),
+        d_(holdout_fraction), i_(cv_seed), i_(mask_zeros),
+        i_(nonneg[0]), i_(nonneg[1]),
+        i_(norm_type),
+        i_(loss_type), d_(1.0),
+        i_(20), d_(1e-4),
+        ip(one_i), ip(one_i), dp(one_d), i_(0), i_(0), d_(0.0),
+        ip(one_i), ip(one_i), dp(one_d), i_(0), i_(0), d_(0.0),
+        i_(projective), i_(symmetric), i_(solver_mode),
+        C.byref(out_iter), C.byref(out_conv),
+        C.byref(out_train), C.byref(out_test),
+        C.byref(out_best), C.byref(out_best_iter),
+        C.byref(out_status),
+    ]
+    assert len(args) == 51, len(args)
+    fn = lib.rcppml_gpu_nmf_cv_unified_float
+    fn.restype = None
+    fn(*args)
+    return BridgeCvResult(W.astype(np.float32), H.astype(np.float32), d.astype(np.float32), out_iter.value,
+                          bool(out_conv.value), out_train.value, out_test.value, out_best.value, out_best_iter.value,
+                          out_status.value)

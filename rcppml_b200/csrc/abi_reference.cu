@@ -39,6 +39,78 @@ void rcppml_gpu_detect(int* num_gpus, double* total_mem_mb, double* free_mem_mb,
     if (out_status) *out_status = usable > 0 ? 0 : -1;
 }
 
+// src/gpu_bridge_nmf.cu:340-455 (51 pointers, gpu/bridge_nmf.hpp:78-99)
+void rcppml_gpu_nmf_cv_unified_float(
+    const int* col_ptr, const int* row_idx, const double* values,
+    int* m, int* n, int* nnz, int* k,
+    double* W, double* H, double* d,
+    int* max_iter, double* tol,
+    double* L1_H, double* L1_W, double* L2_H, double* L2_W,
+    int* cd_maxit, int* verbose, int* seed,
+    double* holdout_frac, int* cv_seed, int* mask_zeros,
+    int* nonneg_W, int* nonneg_H,
+    int* norm_type,
+    int* loss_type, double* /*huber_delta*/,
+    int* /*irls_max_iter*/, double* /*irls_tol*/,
+    const int*, const int*, const double*, int*, int* graph_W_nnz, double*,
+    const int*, const int*, const double*, int*, int* graph_H_nnz, double*,
+    int* projective, int* symmetric, int* solver_mode,
+    int* out_iter, int* out_converged,
+    double* out_train_loss, double* out_test_loss,
+    double* out_best_test, int* out_best_iter,
+    int* out_status)
+{
+    if (!out_status) return;
+    *out_status = -1;
+    try {
+        const char* refuse = nullptr;
+        if (*loss_type != 0) refuse = "non-MSE loss is outside the B200 CV path";
+        else if (*projective || *symmetric) refuse = "projective/symmetric NMF is outside the B200 CV path";
+        else if ((graph_W_nnz && *graph_W_nnz > 0) || (graph_H_nnz && *graph_H_nnz > 0)) refuse = "graph regularisation is outside the B200 CV path";
+        else if (*k < 1 || *k > b200::kMaxKP) refuse = "rank must be in [1, 128] on the B200 CV path";
+        else if (*max_iter <= 0) refuse = "max_iter must be positive";
+        if (refuse) { warn(refuse); return; }
+        int count = 0;
+        if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) { warn("no CUDA device"); return; }
+        b200::Engine E(0);
+        E.set_matrix_host<double>(*m, *n, static_cast<int64_t>(*nnz), col_ptr, row_idx, values);
+        E.set_factors_host<double>(*k, W, H);
+        rcppml_b200_config cfg{};
+        cfg.k = *k; cfg.max_iter = *max_iter; cfg.tol = static_cast<float>(*tol);
+        cfg.L1_H = static_cast<float>(*L1_H); cfg.L1_W = static_cast<float>(*L1_W);
+        cfg.L2_H = static_cast<float>(*L2_H); cfg.L2_W = static_cast<float>(*L2_W);
+        cfg.nonneg_W = *nonneg_W != 0; cfg.nonneg_H = *nonneg_H != 0;
+        cfg.cd_maxit = *cd_maxit; cfg.cd_tol = 1e-8f;
+        cfg.norm_type = *norm_type; cfg.solver_mode = *solver_mode; cfg.patience = 5; cfg.verbose = *verbose;
+        rcppml_b200_cv_config cv{};
+        cv.holdout_fraction = static_cast<float>(*holdout_frac);         // src/gpu_bridge_nmf.cu:379
+        cv.cv_seed = static_cast<uint32_t>(*cv_seed);
+        cv.seed = static_cast<uint32_t>(*seed);
+        cv.mask_zeros = *mask_zeros != 0;
+        cv.cv_patience = 5;                                              // core/config.hpp:257, not on the wire
+        E.fit_cv(cfg, cv);
+        rcppml_b200_result res{};
+        E.get_result(&res);
+        if (res.status != 0) { warn("Gram matrix not positive definite (Cholesky pivot <= 0)"); return; }
+        rcppml_b200_cv_result cr{};
+        E.get_cv_result(&cr);
+        E.get_factors_host<double>(W, H, d);
+        if (out_iter) *out_iter = res.iterations;
+        if (out_converged) *out_converged = res.converged;
+        if (out_train_loss) *out_train_loss = cr.train_loss;
+        if (out_test_loss) *out_test_loss = cr.test_loss;
+        if (out_best_test) *out_best_test = cr.best_test_loss;
+        if (out_best_iter) *out_best_iter = cr.best_iter;
+        *out_status = 0;
+    } catch (const std::exception& ex) {
+        warn(ex.what());
+        *out_status = -1;
+    } catch (...) {
+        warn("unknown error");
+        *out_status = -1;
+    }
+}
+
 // Shared body of the standard entry point and its masked extension.
 static void nmf_unified_impl(
     const int* mask_p, const int* mask_i, const int* mask_nnz,

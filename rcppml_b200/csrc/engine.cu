@@ -102,6 +102,48 @@ static void launch_masked(int KP, const MaskedParams& p, int num_sms, cudaStream
     }
 }
 
+template <int KP>
+static void launch_cv_t(const CvParams& p, int num_sms, cudaStream_t s, int* grid_out) {
+    auto kern = cv_half_step_kernel<KP>;
+    const size_t smem = masked_smem_bytes<KP>();
+    const int threads = masked_warps<KP>() * 32;
+    static thread_local int cached_occ = -1;
+    if (cached_occ < 0) {
+        B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        int occ = 0;
+        B200_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+        B200_REQUIRE(occ > 0, "cv_half_step_kernel does not fit on an SM");
+        cached_occ = occ;
+    }
+    const int grid = num_sms * cached_occ;
+    if (grid_out) { *grid_out = grid; return; }
+    kern<<<grid, threads, smem, s>>>(p);
+}
+static void launch_cv(int KP, const CvParams& p, int num_sms, cudaStream_t s, int* grid_out = nullptr) {
+    switch (KP) {
+        case 16: launch_cv_t<16>(p, num_sms, s, grid_out); break;
+        case 32: launch_cv_t<32>(p, num_sms, s, grid_out); break;
+        case 64: launch_cv_t<64>(p, num_sms, s, grid_out); break;
+        case 128: launch_cv_t<128>(p, num_sms, s, grid_out); break;
+        default: throw std::runtime_error("unsupported padded rank");
+    }
+}
+
+// out = G with (G_ii + 1e-15) + L2 on the diagonal (fit_cv.hpp:414-417 / :578-581)
+static __global__ void cv_prepare_gram_kernel(const float* __restrict__ G, int KP, int k, float L2, float* __restrict__ out,
+                                              const int* __restrict__ stop_flag) {
+    if (*stop_flag) return;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= KP * KP) return;
+    const int i = e % KP, j = e / KP;
+    float v = G[e];
+    if (i == j && i < k) {
+        v = __fadd_rn(v, 1e-15f);
+        if (L2 > 0.f) v = __fadd_rn(v, L2);
+    }
+    out[e] = v;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Engine
 // ---------------------------------------------------------------------------------------------
@@ -114,7 +156,7 @@ Engine::Engine(int dev) : device(dev) {
     B200_CUDA_CHECK(cudaEventCreate(&ev_loop_begin));
     B200_CUDA_CHECK(cudaEventCreate(&ev_loop_end));
     state.ensure(1);
-    counters.ensure(8);
+    counters.ensure(16);
     sweep_counter.ensure(1);
     B200_CUDA_CHECK(cudaMallocHost(&h_state, sizeof(DevState) * 2));
     B200_CUDA_CHECK(cudaMemsetAsync(state.ptr, 0, sizeof(DevState), stream));
@@ -374,6 +416,7 @@ void Engine::alloc_factors(int k_) {
         }
     }
     { int g = 0; MaskedParams md{}; launch_masked(KP, md, num_sms, stream, &g); gmax = std::max(gmax, g); }
+    { int g = 0; CvParams cd{}; launch_cv(KP, cd, num_sms, stream, &g); gmax = std::max(gmax, g); }
     solve_grid_max = gmax;
     solve_partials.ensure(static_cast<size_t>(gmax) * (KP + 1));
     red_gram.ensure(static_cast<size_t>(KP) * KP);
@@ -709,6 +752,113 @@ void Engine::enqueue_iteration_masked() {
     ++iters_enqueued;
 }
 
+// ---- speckled-mask cross-validation (nmf/fit_cv.hpp) -----------------------------------------------
+void Engine::cv_solve(int which, int sec) {
+    CvParams p{};
+    const bool h = (which == 0);
+    p.colptr = h ? Ap.ptr : Atp.ptr;
+    p.rowidx = h ? Ai.ptr : Ati.ptr;
+    p.vals = h ? Ax.ptr : Atx.ptr;
+    p.F = h ? W_T.ptr : H.ptr;
+    p.X = h ? H.ptr : W_T.ptr;
+    p.G = M1.ptr;
+    p.ncols = h ? n : m;
+    p.nrows = h ? m : n;
+    p.k = k;
+    p.transposed = h ? 0 : 1;
+    p.mask_zeros = cv.mask_zeros;
+    p.seed = cv_seed_state;
+    p.threshold = cv_threshold;
+    p.holdout_enabled = cv_inv_prob != 0;
+    p.L1 = h ? cfg.L1_H : cfg.L1_W;
+    p.ub = h ? cfg.ub_H : cfg.ub_W;
+    p.cd_maxit = cfg.cd_maxit;
+    p.nonneg = h ? cfg.nonneg_H : cfg.nonneg_W;
+    p.solver = (cfg.solver_mode == 1) ? 1 : 0;              // fit_cv.hpp:461 tests `== 1`
+    p.norm_type = cfg.norm_type;
+    p.want_cross = h ? 0 : 1;
+    p.work_counter = counters.ptr + 6 + which;
+    p.partials = solve_partials.ptr;
+    p.state = state.ptr;
+    int grid = 0;
+    launch_cv(KP, p, num_sms, stream, &grid);
+    B200_REQUIRE(static_cast<size_t>(grid) * (KP + 1) <= solve_partials.count, "partials buffer too small");
+    last_solve_grid = grid;
+    sec_begin(sec);
+    B200_CUDA_CHECK(cudaMemsetAsync(p.work_counter, 0, sizeof(int), stream));
+    launch_cv(KP, p, num_sms, stream);
+    launches[sec] += 1;
+    sec_end(sec);
+}
+
+void Engine::enqueue_iteration_cv() {
+    const bool normalize = cfg.norm_type != 2;
+    const int ge = (KP * KP + 255) / 256;
+    if (iters_enqueued == 0) gram(W_T.ptr, m, false, G_w.ptr, RCPPML_B200_SEC_GRAM_H);      // fit_cv.hpp:413
+    cv_prepare_gram_kernel<<<ge, 256, 0, stream>>>(G_w.ptr, KP, k, cfg.L2_H, M1.ptr, &state.ptr->stop);   // :414-417
+    cv_solve(0, RCPPML_B200_SEC_SOLVE_H);                                                    // :431-476, :528
+    scale_finalize(RCPPML_B200_SEC_SCALE_H);                                                 // :536-548
+    gram(H.ptr, n, normalize, G_h.ptr, RCPPML_B200_SEC_GRAM_W);                              // :570 (= G_H_saved)
+    cv_prepare_gram_kernel<<<ge, 256, 0, stream>>>(G_h.ptr, KP, k, cfg.L2_W, M1.ptr, &state.ptr->stop);   // :578-581
+    cv_solve(1, RCPPML_B200_SEC_SOLVE_W);                                                    // :598-735, :843
+    scale_finalize(RCPPML_B200_SEC_SCALE_W);                                                 // :849-858
+    sec_begin(RCPPML_B200_SEC_LOSS);
+    const bool was = profiling; profiling = false;
+    gram(W_T.ptr, m, normalize, G_w.ptr, RCPPML_B200_SEC_LOSS);                              // normalise + :1518
+    profiling = was;
+    const int lgrid = num_sms * 4;
+    if (loss_partials.count < static_cast<size_t>(lgrid) * 2) loss_partials.ensure(static_cast<size_t>(lgrid) * 2);
+    cv_test_loss_kernel<<<lgrid, 256, 0, stream>>>(Ap.ptr, Ai.ptr, Ax.ptr, n, m, KP, k, cv.mask_zeros, cv_seed_state,
+                                                   cv_threshold, cv_inv_prob != 0, W_T.ptr, H.ptr, d.ptr,
+                                                   loss_partials.ptr, &state.ptr->stop);
+    const long long total_entries = cv.mask_zeros ? nnz_global : static_cast<long long>(m) * n;
+    cv_loss_finalize_kernel<<<1, 256, 0, stream>>>(G_w.ptr, G_h.ptr, d.ptr, KP, k, red_small.ptr + KP, loss_partials.ptr,
+                                                   lgrid, trAtA, total_entries, cfg.tol, cv.cv_patience, loss_hist.ptr,
+                                                   test_hist.ptr, static_cast<int>(loss_hist.count), state.ptr,
+                                                   cv_state.ptr);
+    launches[RCPPML_B200_SEC_GRAM_H] += 1; launches[RCPPML_B200_SEC_GRAM_W] += 1; launches[RCPPML_B200_SEC_LOSS] += 2;
+    sec_end(RCPPML_B200_SEC_LOSS);
+    ++iters_enqueued;
+}
+
+void Engine::fit_cv(const rcppml_b200_config& c, const rcppml_b200_cv_config& cvc) {
+    use_device();
+    B200_REQUIRE(world == 1, "fit_cv: the cross-validation path is single-GPU");
+    B200_REQUIRE(!has_mask, "fit_cv: a user mask together with the speckled mask is not supported");
+    B200_REQUIRE(cvc.holdout_fraction >= 0.f && cvc.holdout_fraction < 1.f, "holdout_fraction must be in [0, 1)");   // core/config.hpp:428
+    B200_REQUIRE(c.max_iter > 0, "max_iter must be positive");
+    cv = cvc;
+    if (cv.cv_patience < 0) cv.cv_patience = 5;
+    // nmf/speckled_cv.hpp:117-127: seed remap, inv_prob from the FLOAT fraction (0.1f -> 9, i.e. 11.1 % held out)
+    const uint32_t eff = cv.cv_seed != 0 ? cv.cv_seed : cv.seed;                 // core/config.hpp:416-418
+    cv_seed_state = (eff == 0) ? 12345ULL : static_cast<unsigned long long>(eff);
+    const double hf = static_cast<double>(cv.holdout_fraction);
+    cv_inv_prob = hf > 0 ? static_cast<unsigned long long>(1.0 / hf) : 0ULL;
+    cv_threshold = cv_inv_prob ? (0xFFFFFFFFFFFFFFFFULL / cv_inv_prob) : 0ULL;
+    begin_fit(c);
+    test_hist.ensure(loss_hist.count);
+    cv_state.ensure(1);
+    CvState s0{};
+    s0.prev_conv_loss = 3.402823466e+38f;
+    s0.best_test_loss = 3.402823466e+38f;
+    B200_CUDA_CHECK(cudaMemcpyAsync(cv_state.ptr, &s0, sizeof(CvState), cudaMemcpyHostToDevice, stream));
+    cv_active = true;
+    iterate(cfg.max_iter);
+    cv_active = false;
+    const long long th = static_cast<long long>(n) * KP;
+    cv_absorb_d_kernel<<<static_cast<unsigned>((th + 255) / 256), 256, 0, stream>>>(H.ptr, n, KP, d.ptr);   // :1639-1641
+    B200_CUDA_CHECK(cudaStreamSynchronize(stream));
+}
+
+void Engine::get_cv_result(rcppml_b200_cv_result* out) {
+    use_device();
+    B200_REQUIRE(cv_state.ptr != nullptr, "no cross-validation fit has run");
+    CvState s{};
+    B200_CUDA_CHECK(cudaMemcpy(&s, cv_state.ptr, sizeof(CvState), cudaMemcpyDeviceToHost));
+    out->train_loss = s.train_loss; out->test_loss = s.test_loss; out->best_test_loss = s.best_test_loss;
+    out->best_iter = s.best_iter; out->n_test = s.n_test;
+}
+
 void Engine::begin_fit(const rcppml_b200_config& c) {
     use_device();
     B200_REQUIRE(matrix_ready && factors_ready, "begin_fit: matrix and factors must be set first");
@@ -736,8 +886,8 @@ void Engine::iterate(int n_iters) {
     // kernels enqueued after `stop` return immediately. Every 8 iterations the host peeks at the
     // flag only to avoid enqueuing a long tail of no-op launches.
     for (int it = 0; it < n_iters; ++it) {
-        if (has_mask) enqueue_iteration_masked(); else enqueue_iteration();
-        if ((it & 7) == 7 && cfg.tol > 0.f) {
+        if (cv_active) enqueue_iteration_cv(); else if (has_mask) enqueue_iteration_masked(); else enqueue_iteration();
+        if ((it & 7) == 7 && (cfg.tol > 0.f || cv_active)) {
             B200_CUDA_CHECK(cudaMemcpyAsync(h_state, state.ptr, sizeof(DevState), cudaMemcpyDeviceToHost, stream));
             B200_CUDA_CHECK(cudaStreamSynchronize(stream));
             if (h_state->stop) break;
@@ -898,6 +1048,21 @@ int rcppml_b200_fit(rcppml_b200_engine* e, const rcppml_b200_config* cfg) {
     B200_REQUIRE(cfg->max_iter > 0, "max_iter must be positive");        // core/config.hpp:424
     e->impl.begin_fit(*cfg);
     e->impl.iterate(cfg->max_iter);
+    B200_API_END
+}
+int rcppml_b200_fit_cv(rcppml_b200_engine* e, const rcppml_b200_config* cfg, const rcppml_b200_cv_config* cv) {
+    B200_API_BEGIN e->impl.fit_cv(*cfg, *cv); B200_API_END
+}
+int rcppml_b200_get_cv_result(rcppml_b200_engine* e, rcppml_b200_cv_result* out) {
+    B200_API_BEGIN e->impl.get_cv_result(out); B200_API_END
+}
+int rcppml_b200_get_cv_history(rcppml_b200_engine* e, float* train, float* test, int capacity) {
+    B200_API_BEGIN
+    Engine& E = e->impl;
+    E.use_device();
+    const int cnt = std::min<int>(capacity, static_cast<int>(E.test_hist.count));
+    if (cnt > 0 && train) B200_CUDA_CHECK(cudaMemcpy(train, E.loss_hist.ptr, cnt * sizeof(float), cudaMemcpyDeviceToHost));
+    if (cnt > 0 && test) B200_CUDA_CHECK(cudaMemcpy(test, E.test_hist.ptr, cnt * sizeof(float), cudaMemcpyDeviceToHost));
     B200_API_END
 }
 int rcppml_b200_get_result(rcppml_b200_engine* e, rcppml_b200_result* out) {

@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include "kernels_dense.cuh"
 #include "kernels_masked.cuh"
+#include "kernels_cv.cuh"
 #include "kernels_solve.cuh"
 #include "kernels_sparse.cuh"
 
@@ -53,6 +54,8 @@ public:
     void iterate(int n_iters);
     void half_step_only(const rcppml_b200_config& cfg, int which, bool warm, bool normalize_after);
     void get_result(rcppml_b200_result* out);
+    void fit_cv(const rcppml_b200_config& cfg, const rcppml_b200_cv_config& cv);
+    void get_cv_result(rcppml_b200_cv_result* out);
 
     // multi-GPU (comm.cu)
     void comm_init(int rank, int world, const char* id128);
@@ -76,6 +79,12 @@ public:
     int64_t mask_nnz = 0;
     DeviceBuffer<int> Mp, Mi, MTp, MTi;
     DeviceBuffer<double> loss_partials;
+    // speckled-mask cross-validation state (nmf/fit_cv.hpp)
+    bool cv_active = false;
+    rcppml_b200_cv_config cv{};
+    unsigned long long cv_seed_state = 0, cv_inv_prob = 0, cv_threshold = 0;
+    DeviceBuffer<CvState> cv_state;
+    DeviceBuffer<float> test_hist;
     float trAtA = 0.f;          // tr(AᵀA) of the whole matrix
 
     int k = 0, KP = 0, LANES = 0, nv_override = 0;
@@ -134,6 +143,8 @@ private:
     void scale_finalize(int sec, bool reduce_over_ranks = false);
     void enqueue_iteration();
     void enqueue_iteration_masked();
+    void enqueue_iteration_cv();
+    void cv_solve(int which, int sec);
     void masked_solve(int which, bool warm, const float* G, int sec);
 };
 

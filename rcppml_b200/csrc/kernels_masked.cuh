@@ -17,6 +17,137 @@
 
 namespace b200 {
 
+// ---- warp-cooperative dense solvers on a per-warp k×k matrix in shared memory (col-major, ld = KP+1) ----
+// A lane owns coordinates lane, lane+32, … (NC of them). Used by the explicit-mask and the CV kernels.
+
+// cd_nnls_col_fixed (nnls_batch.hpp:71-132) with upper_bound = 0, L2 = 0. L1 != 0 acts inside the sweep (:94).
+template <int KP>
+__device__ __forceinline__ int warp_cd_solve(const float* Gl, float (&b)[(KP + 31) / 32], float (&x)[(KP + 31) / 32],
+                                             int k, float L1, bool nonneg, int maxit, float cd_tol, float inv_k,
+                                             int lane) {
+    constexpr int NC = (KP + 31) / 32;
+    constexpr int LD = KP + 1;
+    const bool check = cd_tol > 0.f;
+    for (int it = 0; it < maxit; ++it) {
+        float tol_sum = 0.f;
+        for (int i = 0; i < k; ++i) {
+            const int owner = i & 31, slot = i >> 5;
+            float bi = 0.f, xi = 0.f;
+#pragma unroll
+            for (int t = 0; t < NC; ++t)
+                if (t == slot) {
+                    bi = __shfl_sync(0xffffffffu, b[t], owner);
+                    xi = __shfl_sync(0xffffffffu, x[t], owner);
+                }
+            const float gd = Gl[i * LD + i];
+            float ad = 0.f, xn = xi;
+            if (gd > 0.f) {
+                float diff = __fdiv_rn(bi, gd);
+                if (L1 != 0.f) diff = __fsub_rn(diff, L1);
+                const float nval = __fadd_rn(xi, diff);
+                if (nonneg && nval < 0.f) { ad = -xi; xn = 0.f; }
+                else { ad = diff; xn = (diff == 0.f) ? xi : nval; }
+            }
+            if (ad != 0.f) {
+                if (check) tol_sum = __fadd_rn(tol_sum, __fdiv_rn(fabsf(ad), __fadd_rn(fabsf(xn), 1e-15f)));
+#pragma unroll
+                for (int t = 0; t < NC; ++t) {
+                    if (t == slot && lane == owner) x[t] = xn;
+                    const int row = lane + 32 * t;
+                    if (row < k) b[t] = __fsub_rn(b[t], __fmul_rn(Gl[i * LD + row], ad));
+                }
+            }
+        }
+        if (check && __fmul_rn(tol_sum, inv_k) < cd_tol) return it + 1;
+    }
+    return maxit;
+}
+
+// Eigen::LLT restated (oracle order): in-place left-looking factorisation of Gl, then x := L⁻ᵀ L⁻¹ b by
+// column-oriented substitution with IEEE division. b holds the rhs on entry and x on exit. Returns the
+// first non-positive pivot index + 1 (0 = ok).
+template <int KP>
+__device__ __forceinline__ int warp_chol_solve(float* Gl, float (&b)[(KP + 31) / 32], int k, int lane) {
+    constexpr int NC = (KP + 31) / 32;
+    constexpr int LD = KP + 1;
+    int fail = 0;
+    for (int jj = 0; jj < k; ++jj) {
+        float s = 0.f;
+        for (int pp = 0; pp < jj; ++pp) {
+            const float l = Gl[pp * LD + jj];
+            s = __fadd_rn(s, __fmul_rn(l, l));
+        }
+        const float xx = __fsub_rn(Gl[jj * LD + jj], s);
+        float ljj = 0.f;
+        if (!(xx > 0.f)) { if (!fail) fail = jj + 1; } else ljj = __fsqrt_rn(xx);
+        float lij[NC];
+#pragma unroll
+        for (int t = 0; t < NC; ++t) {
+            const int i = lane + 32 * t;
+            lij[t] = 0.f;
+            if (i > jj && i < k) {
+                float tt = 0.f;
+                for (int pp = 0; pp < jj; ++pp) tt = __fadd_rn(tt, __fmul_rn(Gl[pp * LD + i], Gl[pp * LD + jj]));
+                lij[t] = __fdiv_rn(__fsub_rn(Gl[jj * LD + i], tt), ljj);
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < NC; ++t) {
+            const int i = lane + 32 * t;
+            if (i > jj && i < k) Gl[jj * LD + i] = lij[t];
+            if (i == jj) Gl[jj * LD + jj] = ljj;
+        }
+        __syncwarp();
+    }
+    for (int pp = 0; pp < k; ++pp) {
+        const int owner = pp & 31, slot = pp >> 5;
+        float bp = 0.f;
+#pragma unroll
+        for (int t = 0; t < NC; ++t) if (t == slot) bp = __shfl_sync(0xffffffffu, b[t], owner);
+        const float y = __fdiv_rn(bp, Gl[pp * LD + pp]);
+#pragma unroll
+        for (int t = 0; t < NC; ++t) {
+            const int i = lane + 32 * t;
+            if (t == slot && lane == owner) b[t] = y;
+            else if (i > pp && i < k) b[t] = __fsub_rn(b[t], __fmul_rn(Gl[pp * LD + i], y));
+        }
+    }
+    for (int pp = k - 1; pp >= 0; --pp) {
+        const int owner = pp & 31, slot = pp >> 5;
+        float yp = 0.f;
+#pragma unroll
+        for (int t = 0; t < NC; ++t) if (t == slot) yp = __shfl_sync(0xffffffffu, b[t], owner);
+        const float xp = __fdiv_rn(yp, Gl[pp * LD + pp]);
+#pragma unroll
+        for (int t = 0; t < NC; ++t) {
+            const int i = lane + 32 * t;
+            if (t == slot && lane == owner) b[t] = xp;
+            else if (i < pp) b[t] = __fsub_rn(b[t], __fmul_rn(Gl[i * LD + pp], xp));   // L(pp, i)
+        }
+    }
+    return fail;
+}
+
+// Gl -= f fᵀ for one factor row f (staged through sf), separately rounded, column by column.
+template <int KP>
+__device__ __forceinline__ void warp_rank1_downdate(float* Gl, float* sf, const float* __restrict__ f, int k, int lane) {
+    constexpr int NC = (KP + 31) / 32;
+    constexpr int LD = KP + 1;
+    __syncwarp();
+    for (int c = lane; c < KP; c += 32) sf[c] = __ldg(f + c);
+    __syncwarp();
+    for (int col = 0; col < k; ++col) {
+        const float fc = sf[col];
+#pragma unroll
+        for (int t = 0; t < NC; ++t) {
+            const int row = lane + 32 * t;
+            if (row < k) Gl[col * LD + row] = __fsub_rn(Gl[col * LD + row], __fmul_rn(sf[row], fc));
+        }
+    }
+    __syncwarp();
+}
+
 struct MaskedParams {
     const int* __restrict__ colptr;    // sparse operand (A or Aᵀ), CSC
     const int* __restrict__ rowidx;
@@ -86,21 +217,8 @@ __global__ void __launch_bounds__(256) masked_half_step_kernel(const MaskedParam
         // ---- G_local = G_full − Σ_{r masked} f_r f_rᵀ (masked_nnls.hpp:136-138)
         for (int e = lane; e < KP * KP; e += 32) Gl[(e / KP) * LD + (e % KP)] = p.G[e];
         __syncwarp();
-        for (int e = mb; e < me; ++e) {
-            const int r = __ldg(p.midx + e);
-            const float* f = p.F + static_cast<size_t>(r) * KP;
-            for (int c = lane; c < KP; c += 32) sf[c] = __ldg(f + c);
-            __syncwarp();
-            for (int col = 0; col < k; ++col) {
-                const float fc = sf[col];
-#pragma unroll
-                for (int t = 0; t < NC; ++t) {
-                    const int row = lane + 32 * t;
-                    if (row < k) Gl[col * LD + row] = __fsub_rn(Gl[col * LD + row], __fmul_rn(sf[row], fc));
-                }
-            }
-            __syncwarp();
-        }
+        for (int e = mb; e < me; ++e)
+            warp_rank1_downdate<KP>(Gl, sf, p.F + static_cast<size_t>(__ldg(p.midx + e)) * KP, k, lane);
         // ---- L1 / L2 (masked_nnls.hpp:141-144): unconditional, like the reference
 #pragma unroll
         for (int t = 0; t < NC; ++t) {
@@ -121,98 +239,11 @@ __global__ void __launch_bounds__(256) masked_half_step_kernel(const MaskedParam
                 const int c = lane + 32 * t;
                 x[t] = (p.warm && c < KP) ? xcol[c] : 0.f;          // :146-148 (b is NOT corrected)
             }
-            const bool nonneg = p.nonneg != 0, check = p.cd_tol > 0.f;
-            int sweeps = p.cd_maxit;
-            for (int it = 0; it < p.cd_maxit; ++it) {
-                float tol_sum = 0.f;
-                for (int i = 0; i < k; ++i) {
-                    const int owner = i & 31, slot = i >> 5;
-                    float bi = 0.f, xi = 0.f;
-#pragma unroll
-                    for (int t = 0; t < NC; ++t)
-                        if (t == slot) {
-                            bi = __shfl_sync(0xffffffffu, b[t], owner);
-                            xi = __shfl_sync(0xffffffffu, x[t], owner);
-                        }
-                    const float gd = Gl[i * LD + i];
-                    float ad = 0.f, xn = xi;
-                    if (gd > 0.f) {
-                        const float diff = __fdiv_rn(bi, gd);
-                        const float nval = __fadd_rn(xi, diff);
-                        if (nonneg && nval < 0.f) { ad = -xi; xn = 0.f; }
-                        else { ad = diff; xn = (diff == 0.f) ? xi : nval; }
-                    }
-                    if (ad != 0.f) {
-                        if (check) tol_sum = __fadd_rn(tol_sum, __fdiv_rn(fabsf(ad), __fadd_rn(fabsf(xn), 1e-15f)));
-#pragma unroll
-                        for (int t = 0; t < NC; ++t) {
-                            if (t == slot && lane == owner) x[t] = xn;
-                            const int row = lane + 32 * t;
-                            if (row < k) b[t] = __fsub_rn(b[t], __fmul_rn(Gl[i * LD + row], ad));
-                        }
-                    }
-                }
-                if (check && __fmul_rn(tol_sum, p.inv_k) < p.cd_tol) { sweeps = it + 1; break; }
-            }
-            my_sweeps += sweeps;
+            my_sweeps += warp_cd_solve<KP>(Gl, b, x, k, 0.f, p.nonneg != 0, p.cd_maxit, p.cd_tol, p.inv_k, lane);
         } else {
-            // ---- cholesky_clip_col (cholesky_clip.hpp:65-106): LLT of G_local in the oracle's order, in place
-            for (int jj = 0; jj < k; ++jj) {
-                float s = 0.f;
-                for (int pp = 0; pp < jj; ++pp) {
-                    const float l = Gl[pp * LD + jj];
-                    s = __fadd_rn(s, __fmul_rn(l, l));
-                }
-                const float xx = __fsub_rn(Gl[jj * LD + jj], s);
-                float ljj = 0.f;
-                if (!(xx > 0.f)) { if (!chol_fail) chol_fail = jj + 1; } else ljj = __fsqrt_rn(xx);
-                float lij[NC];
-#pragma unroll
-                for (int t = 0; t < NC; ++t) {
-                    const int i = lane + 32 * t;
-                    lij[t] = 0.f;
-                    if (i > jj && i < k) {
-                        float tt = 0.f;
-                        for (int pp = 0; pp < jj; ++pp) tt = __fadd_rn(tt, __fmul_rn(Gl[pp * LD + i], Gl[pp * LD + jj]));
-                        lij[t] = __fdiv_rn(__fsub_rn(Gl[jj * LD + i], tt), ljj);
-                    }
-                }
-                __syncwarp();
-#pragma unroll
-                for (int t = 0; t < NC; ++t) {
-                    const int i = lane + 32 * t;
-                    if (i > jj && i < k) Gl[jj * LD + i] = lij[t];
-                    if (i == jj) Gl[jj * LD + jj] = ljj;
-                }
-                __syncwarp();
-            }
-            // forward / backward substitution, column oriented, IEEE division (x := L⁻ᵀ L⁻¹ b)
-            for (int pp = 0; pp < k; ++pp) {
-                const int owner = pp & 31, slot = pp >> 5;
-                float bp = 0.f;
-#pragma unroll
-                for (int t = 0; t < NC; ++t) if (t == slot) bp = __shfl_sync(0xffffffffu, b[t], owner);
-                const float y = __fdiv_rn(bp, Gl[pp * LD + pp]);
-#pragma unroll
-                for (int t = 0; t < NC; ++t) {
-                    const int i = lane + 32 * t;
-                    if (t == slot && lane == owner) b[t] = y;
-                    else if (i > pp && i < k) b[t] = __fsub_rn(b[t], __fmul_rn(Gl[pp * LD + i], y));
-                }
-            }
-            for (int pp = k - 1; pp >= 0; --pp) {
-                const int owner = pp & 31, slot = pp >> 5;
-                float yp = 0.f;
-#pragma unroll
-                for (int t = 0; t < NC; ++t) if (t == slot) yp = __shfl_sync(0xffffffffu, b[t], owner);
-                const float xp = __fdiv_rn(yp, Gl[pp * LD + pp]);
-#pragma unroll
-                for (int t = 0; t < NC; ++t) {
-                    const int i = lane + 32 * t;
-                    if (t == slot && lane == owner) b[t] = xp;
-                    else if (i < pp) b[t] = __fsub_rn(b[t], __fmul_rn(Gl[i * LD + pp], xp));   // L(pp, i)
-                }
-            }
+            // ---- cholesky_clip_col (cholesky_clip.hpp:65-106): per-column LLT of G_local
+            const int f = warp_chol_solve<KP>(Gl, b, k, lane);
+            if (f && !chol_fail) chol_fail = f;
 #pragma unroll
             for (int t = 0; t < NC; ++t) {
                 float v = b[t];

@@ -170,6 +170,20 @@ class Engine:
         _lib.check(self._lib.rcppml_b200_fit(self._h, C.byref(cfg)), "fit")
         return self.result()
 
+    def fit_cv(self, cfg: Config, *, holdout_fraction=0.1, cv_seed=0, seed=42, mask_zeros=True, cv_patience=5):
+        """nmf_fit_cv (nmf/fit_cv.hpp:124): speckled-mask cross-validation. Returns (FitResult, cv dict)."""
+        cv = _lib.CvConfig(holdout_fraction=holdout_fraction, cv_seed=cv_seed, seed=seed, mask_zeros=int(mask_zeros),
+                           cv_patience=cv_patience)
+        _lib.check(self._lib.rcppml_b200_fit_cv(self._h, C.byref(cfg), C.byref(cv)), "fit_cv")
+        r = _lib.CvResult()
+        _lib.check(self._lib.rcppml_b200_get_cv_result(self._h, C.byref(r)), "get_cv_result")
+        res = self.result()
+        it = res.iterations
+        tr, te = np.zeros(max(it, 1), np.float32), np.zeros(max(it, 1), np.float32)
+        _lib.check(self._lib.rcppml_b200_get_cv_history(self._h, _p(tr, C.c_float), _p(te, C.c_float), it), "cv_history")
+        return res, dict(train_loss=r.train_loss, test_loss=r.test_loss, best_test_loss=r.best_test_loss,
+                         best_iter=r.best_iter, n_test=r.n_test, train_history=tr[:it], test_history=te[:it])
+
     def half_step(self, cfg: Config, which: int, warm_start: bool, normalize_after: bool = False):
         _lib.check(self._lib.rcppml_b200_half_step(self._h, C.byref(cfg), which, int(warm_start),
                                                    int(normalize_after)), "half_step")

@@ -348,3 +348,59 @@ def test_evaluate_matches_dense_reconstruction(oracle):
         ref = oracle.evaluate_mse_f64(A.indptr, A.indices, A.data.astype(np.float64), m, n, w, d, h.T, mask_zeros=mz)
         got = project.evaluate(A, w, d, h, mask_zeros=mz)
         assert abs(got - ref) <= 1e-10 * abs(ref), (mz, got, ref)
+
+
+CV_CASES = [
+    # k, solver, mask_zeros, kwargs
+    (6, 0, True, dict(cd_maxit=15)),
+    (6, 1, True, dict()),
+    (20, 1, True, dict(L1=(0.01, 0.02), L2=(0.02, 0.01))),
+    (32, 0, True, dict(cd_maxit=10, L1=(0.01, 0.01))),
+    (64, 1, True, dict()),
+    (8, 1, False, dict()),
+    (8, 0, False, dict(cd_maxit=10)),
+    (128, 1, True, dict(L2=(0.01, 0.01))),
+]
+
+
+@pytest.mark.parametrize("k,solver,mask_zeros,kw", CV_CASES, ids=[f"k{c[0]}_s{c[1]}_mz{int(c[2])}" for c in CV_CASES])
+def test_cv_fit_matches_oracle(eng, oracle, k, solver, mask_zeros, kw):
+    """Speckled-mask cross-validation (nmf/fit_cv.hpp): hash mask bit-exact (same held-out count), factors and
+    train/test loss histories within 1e-5, same early-stopping iteration."""
+    import rcppml_b200 as rb
+    m, n, iters = 350, 240, 12
+    A = random_csc(m, n, 0.12, 60 + k, counts=True, ragged=True)
+    W0, H0 = oracle.initialize_factors(k, m, n, 42)
+    cd_maxit = kw.pop("cd_maxit", 100)
+    ref = oracle.nmf_fit_cv(A.indptr, A.indices, A.data, m, n, k, W0, H0, max_iter=iters, tol=1e-6, solver_mode=solver,
+                            mask_zeros=mask_zeros, holdout_fraction=0.1, cv_seed=7, seed=42, cd_maxit=cd_maxit, **kw)
+    eng.set_matrix(m, n, A.indptr, A.indices, A.data)
+    eng.set_factors(W0, H0)
+    res, cv = eng.fit_cv(rb.make_config(k, max_iter=iters, tol=1e-6, solver_mode=solver, cd_maxit=cd_maxit, **kw),
+                         holdout_fraction=0.1, cv_seed=7, seed=42, mask_zeros=mask_zeros)
+    W, H, d = eng.get_factors()
+    assert res.status == 0
+    assert cv["n_test"] == ref.n_test                       # integer hash mask: bit-exact
+    assert res.iterations == ref.iterations and res.converged == ref.converged and cv["best_iter"] == ref.best_iter
+    errs = dict(W=rel_err(W, ref.W_T), H=rel_err(H, ref.H), d=rel_err(d, ref.d),
+                test=rel_err(cv["test_history"], ref.test_history), train=rel_err(cv["train_history"], ref.train_history))
+    print(k, solver, mask_zeros, res.iterations, errs)
+    assert max(errs["W"], errs["H"], errs["d"], errs["test"]) <= RTOL, errs
+    assert errs["train"] <= 1e-4, errs                      # Gram-trick train loss: difference of large sums
+    assert abs(cv["best_test_loss"] - ref.best_test_loss) <= 1e-5 * abs(ref.best_test_loss)
+
+
+def test_cv_reference_abi(oracle):
+    """Through the 51-pointer rcppml_gpu_nmf_cv_unified_float (gpu/bridge_nmf.hpp:78-99)."""
+    import rcppml_b200 as rb
+    m, n, k = 300, 220, 10
+    A = random_csc(m, n, 0.1, 99, counts=True)
+    W0, H0 = oracle.initialize_factors(k, m, n, 42)
+    ref = oracle.nmf_fit_cv(A.indptr, A.indices, A.data, m, n, k, W0, H0, max_iter=8, tol=1e-7, solver_mode=1,
+                            mask_zeros=True, holdout_fraction=0.1, cv_seed=0, seed=42)
+    out = rb.bridge_nmf_cv_sparse(A.indptr, A.indices, A.data, m, n, k, W0, H0, max_iter=8, tol=1e-7, solver_mode=1,
+                                  mask_zeros=True, holdout_fraction=0.1, cv_seed=0, seed=42)
+    assert out.status == 0 and out.iterations == ref.iterations and out.best_iter == ref.best_iter
+    assert rel_err(out.W_T, ref.W_T) <= RTOL and rel_err(out.H, ref.H) <= RTOL and rel_err(out.d, ref.d) <= RTOL
+    assert abs(out.test_loss - ref.test_loss) <= 1e-5 * abs(ref.test_loss)
+    assert abs(out.best_test_loss - ref.best_test_loss) <= 1e-5 * abs(ref.best_test_loss)
