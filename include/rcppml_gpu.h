@@ -283,6 +283,14 @@ int rcppml_b200_selftest_division(int64_t n, uint64_t seed, int64_t* mismatches)
  * the host launcher. comm_init must be the first call after engine_create; then use the *_sharded setters. */
 int rcppml_b200_nccl_unique_id(char* id128);
 int rcppml_b200_comm_init(rcppml_b200_engine* e, int rank, int world, const char* id128);
+/* Peer-memory fast path (NVLink / NVSwitch P2P, world <= 8). After the factors exist on every rank:
+ * export this rank's 192-byte CUDA IPC handle triple {W_T, H, exchange buffer}, all-gather the triples with
+ * the host launcher (rank-major, world x 192 bytes), import. From then on the sharded ALS loop makes no
+ * NCCL call: half_step_kernel stores every solved column into all replicas while it runs (the factor
+ * all-gather overlaps the solve), and the k x k / k-vector fp64 all-reduces are one-shot peer-memory kernels
+ * that sum in rank order (bit-identical on every rank). Without these two calls the loop uses NCCL. */
+int rcppml_b200_comm_ipc_export(rcppml_b200_engine* e, char* handles192);
+int rcppml_b200_comm_ipc_import(rcppml_b200_engine* e, const char* all_handles);
 
 #ifdef __cplusplus
 }

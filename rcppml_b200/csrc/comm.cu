@@ -38,7 +38,20 @@ void Engine::comm_init(int rank_, int world_, const char* id128) {
     comm = reinterpret_cast<ncclComm*>(c);
 }
 
+void Engine::comm_ipc_close() {
+    if (!peers_ready) return;
+    cudaStreamSynchronize(stream);
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) continue;
+        cudaIpcCloseMemHandle(peer_W[r]);
+        cudaIpcCloseMemHandle(peer_H[r]);
+        cudaIpcCloseMemHandle(peer_x[r]);
+    }
+    peers_ready = false;
+}
+
 void Engine::comm_destroy() {
+    comm_ipc_close();
     if (comm) {
         ncclCommDestroy(as_comm(comm));
         comm = nullptr;
@@ -46,7 +59,57 @@ void Engine::comm_destroy() {
 }
 
 void Engine::allreduce_f64(double* buf, size_t count) {
+    if (peers_ready && static_cast<int>(count) <= xchg_ne_max) {
+        // one-shot all-reduce over peer memory (kernels_dense.cuh xchg_allreduce_kernel)
+        XchgParams x{};
+        for (int r = 0; r < world; ++r) x.peer[r] = peer_x[r];
+        x.rank = rank; x.world = world; x.ne_max = xchg_ne_max;
+        x.seq = ++xchg_seq;
+        x.phase = static_cast<int>(x.seq & 1ULL);
+        xchg_allreduce_kernel<<<1, 1024, 0, stream>>>(buf, static_cast<int>(count), buf, x, state.ptr);
+        launches[RCPPML_B200_SEC_COMM] += 1;
+        return;
+    }
     B200_NCCL_CHECK(ncclAllReduce(buf, buf, count, ncclDouble, ncclSum, as_comm(comm), stream));
+}
+
+// CUDA IPC handles of this rank's W_T, H and exchange buffer (3 x 64 bytes). Call after the factors exist.
+void Engine::comm_ipc_export(char* handles192) {
+    use_device();
+    B200_REQUIRE(world > 1 && factors_ready, "comm_ipc_export: needs a communicator and allocated factors");
+    comm_ipc_close();
+    xchg_ne_max = KP * KP;
+    const size_t doubles = static_cast<size_t>(2) * world * xchg_ne_max + 16;
+    xbuf.ensure(doubles);
+    B200_CUDA_CHECK(cudaMemsetAsync(xbuf.ptr, 0, xbuf.bytes(), stream));
+    B200_CUDA_CHECK(cudaStreamSynchronize(stream));
+    xchg_seq = 0;
+    cudaIpcMemHandle_t hs[3];
+    B200_CUDA_CHECK(cudaIpcGetMemHandle(&hs[0], W_T.ptr));
+    B200_CUDA_CHECK(cudaIpcGetMemHandle(&hs[1], H.ptr));
+    B200_CUDA_CHECK(cudaIpcGetMemHandle(&hs[2], xbuf.ptr));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    std::memcpy(handles192, hs, sizeof(hs));
+}
+
+void Engine::comm_ipc_import(const char* all) {
+    use_device();
+    B200_REQUIRE(world > 1 && world <= 8 && xbuf.ptr != nullptr, "comm_ipc_import: call comm_ipc_export first (world <= 8)");
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) {
+            peer_W[r] = W_T.ptr; peer_H[r] = H.ptr; peer_x[r] = xbuf.ptr;
+            continue;
+        }
+        cudaIpcMemHandle_t hs[3];
+        std::memcpy(hs, all + static_cast<size_t>(r) * 192, sizeof(hs));
+        void* p[3] = {nullptr, nullptr, nullptr};
+        for (int q = 0; q < 3; ++q)
+            B200_CUDA_CHECK(cudaIpcOpenMemHandle(&p[q], hs[q], cudaIpcMemLazyEnablePeerAccess));
+        peer_W[r] = static_cast<float*>(p[0]);
+        peer_H[r] = static_cast<float*>(p[1]);
+        peer_x[r] = static_cast<double*>(p[2]);
+    }
+    peers_ready = true;
 }
 
 // In-place all-gather of equal row blocks of a replicated factor: rank g contributes rows

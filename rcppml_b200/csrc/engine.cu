@@ -391,6 +391,9 @@ void Engine::alloc_factors(int k_) {
     KP = padded_rank(k);
     nv_override = 0;
     if (const char* env = std::getenv("RCPPML_B200_NV")) nv_override = std::atoi(env);   // tuning knob (1 or 2)
+    if (peers_ready && (static_cast<size_t>(m_pad) * KP > W_T.count || static_cast<size_t>(n_pad) * KP > H.count ||
+                        KP * KP > xchg_ne_max))
+        comm_ipc_close();                                 // the mapped buffers are about to move: back to NCCL
     W_T.ensure(static_cast<size_t>(m_pad) * KP);          // padded to equal row / column blocks (all-gather)
     H.ensure(static_cast<size_t>(n_pad) * KP);
     B200_CUDA_CHECK(cudaMemsetAsync(W_T.ptr, 0, static_cast<size_t>(m_pad) * KP * sizeof(float), stream));
@@ -522,6 +525,16 @@ void Engine::normalize_cfg(const rcppml_b200_config& c) {
     B200_REQUIRE(cfg.norm_type >= 0 && cfg.norm_type <= 2, "norm_type must be 0, 1 or 2");
 }
 
+// Peer-memory sharding: the other ranks' half_step_kernel pushed their solved (un-normalised) columns into this
+// replica; divide them by d here (same IEEE division as the owner applies to its block).
+void Engine::normalize_peer_blocks(float* X, long long ncols, long long lo, long long hi, bool normalize) {
+    if (!normalize || ncols == hi - lo) return;
+    sec_begin(RCPPML_B200_SEC_COMM);
+    scale_columns_kernel<<<num_sms * 8, 256, 0, stream>>>(X, ncols, KP, d.ptr, lo, hi, &state.ptr->stop);
+    launches[RCPPML_B200_SEC_COMM] += 1;
+    sec_end(RCPPML_B200_SEC_COMM);
+}
+
 void Engine::gram(float* X, long long ncols, bool normalize, float* G_out, int sec, bool reduce_over_ranks) {
     sec_begin(sec);
     launch_normalize_gram(KP, X, ncols, d.ptr, normalize ? 1 : 0, gram_partials.ptr, &state.ptr->stop, gram_grid, stream);
@@ -537,13 +550,9 @@ void Engine::gram(float* X, long long ncols, bool normalize, float* G_out, int s
 void Engine::prepare_solver(const float* G, float L2, int sec) {
     sec_begin(sec);
     const int solver = cfg.solver_mode == 0 ? SOLVER_CD : SOLVER_CHOL;
-    const size_t smem = static_cast<size_t>(KP) * KP * sizeof(float);
-    static thread_local bool attr_set = false;
-    if (!attr_set) {
-        B200_CUDA_CHECK(cudaFuncSetAttribute(prepare_solver_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * 4));
-        attr_set = true;
-    }
-    prepare_solver_kernel<<<1, 128, smem, stream>>>(G, KP, k, L2, solver, M1.ptr, M2.ptr, dblk.ptr, rcp.ptr, state.ptr);
+    const size_t smem = static_cast<size_t>(2) * KP * KP * sizeof(float);
+    B200_CUDA_CHECK(cudaFuncSetAttribute(prepare_solver_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 128 * 128 * 4));
+    prepare_solver_kernel<<<1, kPrepThreads, smem, stream>>>(G, KP, k, L2, solver, M1.ptr, M2.ptr, dblk.ptr, rcp.ptr, state.ptr);
     launches[sec] += 1;
     sec_end(sec);
 }
@@ -601,6 +610,11 @@ HalfStepParams Engine::solve_params(int which, bool warm) const {
     p.partials = solve_partials.ptr;
     p.stop_flag = &state.ptr->stop;
     p.sweep_counter = sweep_counter.ptr;
+    p.npeers = 0;
+    if (peers_ready) {
+        for (int r = 0; r < world; ++r)
+            if (r != rank) p.peerX[p.npeers++] = h ? peer_H[r] : peer_W[r];
+    }
     return p;
 }
 
@@ -642,16 +656,21 @@ void Engine::enqueue_iteration() {
     const bool warm = iters_enqueued > 0;                                   // fit_cpu.hpp:523 / :755
     const bool normalize = cfg.norm_type != 2;
     const bool sharded = world > 1;
+    // With peer-mapped factors (comm_ipc_import) the solve kernels replicate every solved column into the
+    // other GPUs' copies while they run, the small all-reduces are one-shot peer-memory kernels, and each
+    // rank normalises the whole replicated factor locally: no NCCL call in the loop, no exposed all-gather.
+    const bool p2p = sharded && peers_ready;
     float* Hblk = H.ptr + static_cast<size_t>(col_begin) * KP;
     float* Wblk = W_T.ptr + static_cast<size_t>(row_begin) * KP;
     // ---- H update (fit_cpu.hpp:488-645)
     if (iters_enqueued == 0) gram(Wblk, m_loc, false, G_w.ptr, RCPPML_B200_SEC_GRAM_H, sharded);   // :491
     prepare_solver(G_w.ptr, cfg.L2_H, RCPPML_B200_SEC_GRAM_H);              // :506
     solve(0, warm, RCPPML_B200_SEC_SOLVE_H);                                // :516-535 (+ :636 upper bound)
-    scale_finalize(RCPPML_B200_SEC_SCALE_H, sharded);                       // :644
+    scale_finalize(RCPPML_B200_SEC_SCALE_H, sharded);                       // :644 (p2p: also the barrier)
     // ---- W update (fit_cpu.hpp:713-893)
     gram(Hblk, n_loc, normalize, G_h.ptr, RCPPML_B200_SEC_GRAM_W, sharded); // :644 (normalise) + :715
-    if (sharded) allgather_rows(H.ptr, n_pad / world, RCPPML_B200_SEC_COMM);
+    if (p2p) normalize_peer_blocks(H.ptr, n, col_begin, col_begin + n_loc, normalize);
+    else if (sharded) allgather_rows(H.ptr, n_pad / world, RCPPML_B200_SEC_COMM);
     prepare_solver(G_h.ptr, cfg.L2_W, RCPPML_B200_SEC_GRAM_W);              // :738
     solve(1, warm, RCPPML_B200_SEC_SOLVE_W);                                // :748-767 (+ :884)
     scale_finalize(RCPPML_B200_SEC_SCALE_W, sharded);                       // :892
@@ -662,7 +681,8 @@ void Engine::enqueue_iteration() {
     profiling = was;
     loss(RCPPML_B200_SEC_LOSS);
     sec_end(RCPPML_B200_SEC_LOSS);
-    if (sharded) allgather_rows(W_T.ptr, m_pad / world, RCPPML_B200_SEC_COMM);
+    if (p2p) normalize_peer_blocks(W_T.ptr, m, row_begin, row_begin + m_loc, normalize);
+    else if (sharded) allgather_rows(W_T.ptr, m_pad / world, RCPPML_B200_SEC_COMM);
     ++iters_enqueued;
 }
 
@@ -932,7 +952,7 @@ void Engine::get_result(rcppml_b200_result* out) {
     out->converged = s.converged;
     out->train_loss = s.train_loss;
     out->final_tol = s.final_tol;
-    out->status = s.chol_fail ? 1 : 0;
+    out->status = s.chol_fail ? 1 : (s.comm_error ? 2 : 0);
     int total = 0;
     for (int i = 0; i < RCPPML_B200_NUM_SECTIONS; ++i) total += launches[i];
     out->gpu_launches = total;
@@ -1018,6 +1038,12 @@ int rcppml_b200_get_matrix_t(rcppml_b200_engine* e, int* col_ptr, int* row_idx, 
     B200_REQUIRE(e->impl.matrix_ready, "no matrix");
     copy_csc(e->impl, e->impl.Atp.ptr, e->impl.Ati.ptr, e->impl.Atx.ptr, e->impl.m_loc, e->impl.nnz_w, col_ptr, row_idx, values);
     B200_API_END
+}
+int rcppml_b200_comm_ipc_export(rcppml_b200_engine* e, char* handles192) {
+    B200_API_BEGIN e->impl.comm_ipc_export(handles192); B200_API_END
+}
+int rcppml_b200_comm_ipc_import(rcppml_b200_engine* e, const char* all_handles) {
+    B200_API_BEGIN e->impl.comm_ipc_import(all_handles); B200_API_END
 }
 int rcppml_b200_set_mask(rcppml_b200_engine* e, int64_t mask_nnz, const int* mask_col_ptr, const int* mask_row_idx) {
     B200_API_BEGIN e->impl.set_mask(mask_nnz, mask_col_ptr, mask_row_idx); B200_API_END

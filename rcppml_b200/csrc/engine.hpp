@@ -61,6 +61,10 @@ public:
     void comm_init(int rank, int world, const char* id128);
     void comm_destroy();
     bool comm_ready() const { return comm != nullptr; }
+    // Peer-memory fast path (NVLink P2P): exchange CUDA IPC handles of {W_T, H, exchange buffer} between ranks.
+    void comm_ipc_export(char* handles192);
+    void comm_ipc_import(const char* all_handles /* world x 192 bytes, rank-major */);
+    void comm_ipc_close();
 
     // ---- state (public: the C ABI shims read it) ------------------------------------------
     int device = 0;
@@ -115,6 +119,13 @@ public:
     // multi-GPU
     ncclComm* comm = nullptr;
     int rank = 0, world = 1;
+    bool peers_ready = false;
+    float* peer_W[8] = {};            // every rank's W_T / H / exchange buffer (own pointers at [rank])
+    float* peer_H[8] = {};
+    double* peer_x[8] = {};
+    DeviceBuffer<double> xbuf;        // data[2][world][ne_max] + flags[2][8]
+    int xchg_ne_max = 0;
+    unsigned long long xchg_seq = 0;
 
 private:
     cudaEvent_t ev_loop_begin = nullptr, ev_loop_end = nullptr;
@@ -135,6 +146,7 @@ private:
     void sec_end(int sec);
     void collect_profile();
     void gram(float* X, long long ncols, bool normalize, float* G_out, int sec, bool reduce_over_ranks = false);
+    void normalize_peer_blocks(float* X, long long ncols, long long lo, long long hi, bool normalize);
     void loss(int sec);
     void allreduce_f64(double* buf, size_t count);
     void prepare_solver(const float* G, float L2, int sec);

@@ -20,6 +20,7 @@ struct DevState {
     int converged;
     int patience_counter;
     int chol_fail;          // first non-positive pivot index + 1 (0 = none)
+    int comm_error;         // a peer-memory exchange timed out
     float prev_loss;
     float final_tol;
     float train_loss;
@@ -132,6 +133,32 @@ static __global__ void __launch_bounds__(kGramThreads) normalize_gram_kernel(flo
     }
 }
 
+// X[c][:] /= d for the columns c in [0, lo) and [hi, ncols): peer-memory sharded runs normalise the blocks the
+// OTHER ranks solved (pushed un-normalised into this rank's replica by their half_step_kernel) with the same
+// IEEE division normalize_gram_kernel applies to the own block. Pure HBM streaming.
+static __global__ void __launch_bounds__(256) scale_columns_kernel(float* __restrict__ X, long long ncols, int KP,
+                                                                   const float* __restrict__ d, long long lo,
+                                                                   long long hi, const int* __restrict__ stop_flag) {
+    __shared__ float sD[kMaxKP];
+    if (*stop_flag) return;
+    for (int t = threadIdx.x; t < KP; t += blockDim.x) sD[t] = d[t];
+    __syncthreads();
+    const int V4 = KP / 4;
+    const long long head = lo * V4, skip = (hi - lo) * V4, total = (ncols - (hi - lo)) * V4;
+    float4* X4 = reinterpret_cast<float4*>(X);
+    for (long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
+         t += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long w = t < head ? t : t + skip;
+        const int q = static_cast<int>(w % V4);
+        float4 v = X4[w];
+        v.x = __fdiv_rn(v.x, sD[q * 4 + 0]);
+        v.y = __fdiv_rn(v.y, sD[q * 4 + 1]);
+        v.z = __fdiv_rn(v.z, sD[q * 4 + 2]);
+        v.w = __fdiv_rn(v.w, sD[q * 4 + 3]);
+        X4[w] = v;
+    }
+}
+
 // out[e] = Σ_c partials[c][e] in a FIXED order: 8 interleaved slices per element (slice s takes
 // c ≡ s mod 8, ascending), combined in slice order. blockDim = (32, 8).
 static __global__ void __launch_bounds__(256) sum_partials_kernel(const double* __restrict__ partials, int nparts,
@@ -150,6 +177,59 @@ static __global__ void __launch_bounds__(256) sum_partials_kernel(const double* 
 #pragma unroll
         for (int q = 0; q < 8; ++q) t += s[q][threadIdx.x];
         out[e] = t;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// One-shot all-reduce over NVLink peer memory, fused with nothing but itself: every rank stores its
+// vector into slot[rank] of EVERY rank's exchange buffer (P2P stores), publishes a sequence number, waits
+// for the world's sequence numbers, and sums the slots in rank order — the same order on every rank, so
+// the result is bit-identical everywhere. Replaces a ~40 us ncclAllReduce of a few KB with a ~10 us kernel.
+// Because a rank only signals after its previous stream work completed, the exchange is also the barrier
+// that orders the P2P factor replication of half_step_kernel against the peers' next reads.
+// xbuf layout (per rank): double data[2][world][ne_max]; unsigned long long flags[2][8].
+// ---------------------------------------------------------------------------------------------
+struct XchgParams {
+    double* peer[8];                 // exchange buffer base of every rank (peer[rank] = own)
+    int rank, world;
+    int ne_max;
+    unsigned long long seq;          // strictly increasing per call, same on every rank
+    int phase;                       // seq & 1
+};
+
+__device__ __forceinline__ unsigned long long* xchg_flags(double* base, int world, int ne_max, int phase) {
+    return reinterpret_cast<unsigned long long*>(base + static_cast<size_t>(2) * world * ne_max) + phase * 8;
+}
+
+static __global__ void __launch_bounds__(1024) xchg_allreduce_kernel(const double* __restrict__ local, int nelem,
+                                                                     double* __restrict__ out, const XchgParams x,
+                                                                     DevState* __restrict__ st) {
+    if (st->stop) return;            // identical on every rank (convergence is decided from all-reduced data)
+    const size_t slot = (static_cast<size_t>(x.phase) * x.world + x.rank) * x.ne_max;
+    for (int r = 0; r < x.world; ++r) {
+        double* dst = x.peer[r] + slot;
+        for (int e = threadIdx.x; e < nelem; e += blockDim.x) dst[e] = local[e];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < x.world) {
+        unsigned long long* f = xchg_flags(x.peer[threadIdx.x], x.world, x.ne_max, x.phase) + x.rank;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(x.seq) : "memory");
+        const unsigned long long* mine = xchg_flags(x.peer[x.rank], x.world, x.ne_max, x.phase) + threadIdx.x;
+        unsigned long long v = 0;
+        const long long t0 = clock64();
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+            if (v >= x.seq) break;
+            if (clock64() - t0 > 4000000000LL) { st->comm_error = 1; break; }     // ~2 s: never hang the GPU
+        }
+    }
+    __syncthreads();
+    const double* base = x.peer[x.rank] + static_cast<size_t>(x.phase) * x.world * x.ne_max;
+    for (int e = threadIdx.x; e < nelem; e += blockDim.x) {
+        double s = 0.0;
+        for (int r = 0; r < x.world; ++r) s += __ldcg(base + static_cast<size_t>(r) * x.ne_max + e);
+        out[e] = s;
     }
 }
 
@@ -175,49 +255,50 @@ static __global__ void gram_from_sums_kernel(const double* __restrict__ sums, in
 //         M2[p*KP+i] = L(p,i) (i<p), both with the diagonal blocks zeroed; dblk = diagonal blocks of L
 //         (lower triangle incl. diagonal, [q][row][col]); rcp = RN(1/L_pp).
 // Padded pivots get dblk diagonal 1 (CHOL) / 0 (CD) so that they solve to 0 / are skipped.
-static __global__ void __launch_bounds__(128) prepare_solver_kernel(const float* __restrict__ G, int KP, int k, float L2,
+constexpr int kPrepThreads = 1024;
+static __global__ void __launch_bounds__(kPrepThreads) prepare_solver_kernel(const float* __restrict__ G, int KP, int k, float L2,
                                                             int solver, float* __restrict__ M1,
                                                             float* __restrict__ M2, float* __restrict__ dblk,
                                                             float* __restrict__ rcp, DevState* __restrict__ st) {
-    extern __shared__ float sL[];          // KP*KP, col-major working copy
+    extern __shared__ float sL[];          // KP*KP col-major working copy, then KP*KP running dot products T
     if (st->stop) return;
     const int tid = threadIdx.x;
+    float* sT = sL + KP * KP;
     for (int e = tid; e < KP * KP; e += blockDim.x) {
         float v = G[e];
         const int i = e % KP, j = e / KP;
         if (i == j && i < k && L2 > 0.f) v = __fadd_rn(v, L2);
         sL[e] = v;
+        if (solver != 0) sT[e] = 0.f;
     }
     __syncthreads();
     if (solver != 0) {
-        // Left-looking Cholesky, thread i owns row i. sL is overwritten column by column (lower part).
+        // LLT in the oracle's operation order: L(i,j) = (G(i,j) - t_ij) / L(j,j) with the dot product
+        // t_ij = sum_{p<j} L(i,p)·L(j,p) accumulated sequentially in p (separately rounded mul and add), and
+        // L(j,j) = sqrt(G(j,j) - t_jj). The dots are kept as RUNNING sums T(i,j) that every finished column p
+        // updates for all pairs (i >= j > p) at once — the same additions in the same order as the left-looking
+        // loop, but k steps of O(1) depth instead of k dependent dots of length j (≈65 us -> ≈6 us at k = 64).
+        const int ti = tid % KP, tj0 = tid / KP, tjs = blockDim.x / KP;
         for (int j = 0; j < k; ++j) {
+            // column j from G and T (thread i owns row i; every thread recomputes the pivot: broadcast reads)
+            const float x = __fsub_rn(sL[j * KP + j], sT[j * KP + j]);
             float ljj = 0.f;
-            {   // every thread recomputes the pivot redundantly (broadcast reads) -> no extra barrier
-                float s = 0.f;
-                for (int p = 0; p < j; ++p) {
-                    const float l = sL[p * KP + j];
-                    s = __fadd_rn(s, __fmul_rn(l, l));
-                }
-                const float x = __fsub_rn(sL[j * KP + j], s);
-                if (!(x > 0.f)) {
-                    if (tid == 0 && st->chol_fail == 0) st->chol_fail = j + 1;
-                    ljj = 0.f;
-                } else {
-                    ljj = __fsqrt_rn(x);
-                }
+            if (!(x > 0.f)) {
+                if (tid == 0 && st->chol_fail == 0) st->chol_fail = j + 1;
+            } else {
+                ljj = __fsqrt_rn(x);
             }
-            const int i = tid;
             float lij = 0.f;
-            if (i > j && i < k) {
-                float t = 0.f;
-                for (int p = 0; p < j; ++p) t = __fadd_rn(t, __fmul_rn(sL[p * KP + i], sL[p * KP + j]));
-                lij = __fdiv_rn(__fsub_rn(sL[j * KP + i], t), ljj);
-            }
+            if (tid > j && tid < k) lij = __fdiv_rn(__fsub_rn(sL[j * KP + tid], sT[j * KP + tid]), ljj);
             __syncthreads();                   // all reads of column j (as G) done
-            if (i > j && i < k) sL[j * KP + i] = lij;
-            if (i == j) sL[j * KP + j] = ljj;
+            if (tid > j && tid < k) sL[j * KP + tid] = lij;
+            if (tid == j) sL[j * KP + j] = ljj;
             __syncthreads();
+            // T(i,c) += L(i,j)·L(c,j) for j < c <= i < k
+            const float li = sL[j * KP + ti];
+            for (int c = j + 1 + tj0; c < k; c += tjs)
+                if (ti >= c && ti < k) sT[c * KP + ti] = __fadd_rn(sT[c * KP + ti], __fmul_rn(li, sL[j * KP + c]));
+            __syncthreads();                   // T(:,j+1) complete before the next column reads it
         }
     }
     for (int e = tid; e < KP * KP; e += blockDim.x) {

@@ -57,6 +57,10 @@ struct HalfStepParams {
     int b_local_index;                 // BSRC_LOAD: B is indexed by the local column (row-block solves)
     const int* stop_flag;
     unsigned long long* sweep_counter; // optional: total CD sweeps (diagnostics)
+    // Sharded runs with peer-mapped factors: every solved column is ALSO stored straight into the replicas of
+    // X on the other GPUs (NVLink P2P stores), so the "all-gather" of the factor overlaps with the solve.
+    float* peerX[7];
+    int npeers;
 };
 
 template <int LANES>
@@ -510,6 +514,13 @@ __global__ void __launch_bounds__(256, B200_SOLVE_MIN_CTAS) half_step_kernel(con
             for (int nv = 0; nv < NV; ++nv)
                 *reinterpret_cast<float4*>(xcol + (nv * LANES + gl) * 4) =
                     make_float4(x[nv][0], x[nv][1], x[nv][2], x[nv][3]);
+            for (int q = 0; q < p.npeers; ++q) {                    // replicate to the peers' copies of X
+                float* pc = p.peerX[q] + static_cast<size_t>(j) * KP;
+#pragma unroll
+                for (int nv = 0; nv < NV; ++nv)
+                    *reinterpret_cast<float4*>(pc + (nv * LANES + gl) * 4) =
+                        make_float4(x[nv][0], x[nv][1], x[nv][2], x[nv][3]);
+            }
 
             if (p.norm_type == 0) {
 #pragma unroll

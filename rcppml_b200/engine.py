@@ -221,6 +221,25 @@ class Engine:
     def comm_init(self, rank: int, world: int, unique_id: bytes):
         _lib.check(self._lib.rcppml_b200_comm_init(self._h, rank, world, unique_id), "comm_init")
 
+    def comm_enable_p2p(self, dist) -> bool:
+        """Peer-memory fast path (include/rcppml_gpu.h: comm_ipc_export/import). `dist` is an initialised
+        torch.distributed (only used to all-gather the 192-byte IPC handle triples). Call on every rank after
+        the factors exist. Returns False (and leaves the NCCL path active) when RCPPML_B200_P2P=0."""
+        import os
+        import torch
+        if os.environ.get("RCPPML_B200_P2P", "1") == "0":
+            return False
+        world = dist.get_world_size()
+        buf = C.create_string_buffer(192)
+        _lib.check(self._lib.rcppml_b200_comm_ipc_export(self._h, buf), "comm_ipc_export")
+        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+        mine = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).to(dev)
+        allh = torch.empty(world * 192, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allh, mine)
+        _lib.check(self._lib.rcppml_b200_comm_ipc_import(self._h, allh.cpu().numpy().tobytes()), "comm_ipc_import")
+        dist.barrier()
+        return True
+
 
 def nccl_unique_id() -> bytes:
     buf = C.create_string_buffer(128)

@@ -28,8 +28,10 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     m, n, dens = 120_000, 9_001, 2e-3           # n not divisible by world on purpose; m neither for world=8
     worst = 0.0
-    for k, solver, kw in [(64, 1, {}), (64, 0, dict(L1=(0.01, 0.01))), (20, 0, dict(L2=(0.01, 0.01))),
-                          (128, 1, dict(L1=(0.01, 0.01), L2=(0.01, 0.01)))]:
+    cases = [(64, 1, {}), (64, 0, dict(L1=(0.01, 0.01))), (20, 0, dict(L2=(0.01, 0.01))),
+             (128, 1, dict(L1=(0.01, 0.01), L2=(0.01, 0.01)))]
+    # every case with the peer-memory loop (no NCCL call inside the iteration) and with the NCCL loop
+    for p2p, (k, solver, kw) in [(a, b) for a in (True, False) for b in cases]:
         iters = 4
         eng = rb.Engine(local)
         uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
@@ -47,6 +49,8 @@ def main():
         else:
             eng.set_matrix_synthetic_sharded(m, n, dens, synth.SEED_A)
         eng.init_factors(k, 42, 0)
+        if p2p:
+            assert eng.comm_enable_p2p(dist), "peer-memory path not enabled"
         cfg = rb.make_config(k, max_iter=iters, tol=0.0, solver_mode=solver, **kw)
         res = eng.fit(cfg)
         W, H, d = eng.get_factors()
@@ -73,7 +77,7 @@ def main():
         exact = bool(np.array_equal(W, W1) and np.array_equal(H, H1) and np.array_equal(d, d1))
         worst = max(worst, *errs.values())
         if rank == 0:
-            print(f"k={k} solver={solver} world={world}: bit-identical={exact} {errs}", flush=True)
+            print(f"k={k} solver={solver} world={world} p2p={p2p}: bit-identical={exact} {errs}", flush=True)
         assert max(errs.values()) <= 1e-5, errs
     dist.barrier()
     if rank == 0:
