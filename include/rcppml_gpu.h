@@ -70,6 +70,30 @@ void rcppml_gpu_nmf_unified_float(
     int* out_status,
     double* out_tol);
 
+/* Replaces src/gpu_bridge_nmf.cu:879-967 (39 pointers), called through R's .C by .gpu_nmf_zerocopy
+ * (R/gpu_backend.R:183-265). col_ptr / row_idx (int32) and values (double) are DEVICE arrays (sp_read_gpu); their
+ * addresses are passed encoded as doubles. W (k x m), H (k x n), d are host doubles, in/out. No solver_mode on
+ * this wire: Cholesky+clip (the reference's struct default, core/config.hpp:133). The reference computes this
+ * entry in fp64; this engine runs its fp32 ALS loop (values converted on the device). */
+void rcppml_gpu_nmf_zerocopy_double(
+    double* d_col_ptr_addr, double* d_row_idx_addr, double* d_values_addr,
+    int* m, int* n, double* nnz_d, int* k,
+    double* W, double* H, double* d,
+    int* max_iter, double* tol,
+    double* L1_H, double* L1_W, double* L2_H, double* L2_W,
+    double* L21_H, double* L21_W,
+    double* ortho_H, double* ortho_W,
+    double* ub_H, double* ub_W,
+    int* cd_maxit, int* verbose, int* seed,
+    int* loss_every, int* patience,
+    int* nonneg_W, int* nonneg_H,
+    int* loss_type, double* huber_delta,
+    int* irls_max_iter, double* irls_tol,
+    int* norm_type,
+    int* out_iter, int* out_converged, double* out_loss,
+    int* out_status,
+    double* out_tol);
+
 /* Replaces src/gpu_bridge_nmf.cu:340-455; function-pointer type gpu/bridge_nmf.hpp:78-99 (51 pointers), called by
  * bridge_nmf_cv_sparse (gpu/bridge_nmf.hpp:399+). Speckled-mask cross-validation NMF; cv_patience is not on the
  * wire (default 5). Unsupported (status -1): non-MSE loss, graphs, projective, symmetric, k > 128. */
@@ -291,6 +315,14 @@ int rcppml_b200_comm_init(rcppml_b200_engine* e, int rank, int world, const char
  * that sum in rank order (bit-identical on every rank). Without these two calls the loop uses NCCL. */
 int rcppml_b200_comm_ipc_export(rcppml_b200_engine* e, char* handles192);
 int rcppml_b200_comm_ipc_import(rcppml_b200_engine* e, const char* all_handles);
+
+/* The engine behind the reference entry points (part 1) is cached per process: device buffers and staging areas
+ * are grow-only, so repeated calls make no cudaMalloc / cudaFree (the reference builds its GPUContext per call,
+ * nmf/fit_gpu.cuh:552; SURVEY.md 8b allows process-global caching). RCPPML_B200_CACHE=0 disables the cache;
+ * release_cache frees the device memory now. last_call_phases: host wall-clock (ms) of the last part-1 call:
+ * [0] matrix upload (+fp64->fp32) [1] device transpose + tr(AtA) [2] factor upload [3] ALS loop [4] factor download. */
+int rcppml_b200_release_cache(void);
+int rcppml_b200_last_call_phases(double* ms5);
 
 #ifdef __cplusplus
 }

@@ -5,6 +5,6 @@ Only the ALS hot path of the reference lives here: the CUDA engi
 reference interface for this path.
 """
 from .engine import Engine, FitResult, make_config, nccl_unique_id  # noqa: F401
-from .bridge import bridge_nmf_cv_sparse, bridge_nmf_sparse, gpu_detect  # noqa: F401
+from .bridge import bridge_nmf_cv_sparse, bridge_nmf_sparse, gpu_detect, gpu_nmf_zerocopy  # noqa: F401
 
-__all__ = ["Engine", "FitResult", "make_config", "nccl_unique_id", "bridge_nmf_sparse", "bridge_nmf_cv_sparse", "gpu_detect"]
+__all__ = ["Engine", "FitResult", "make_config", "nccl_unique_id", "bridge_nmf_sparse", "bridge_nmf_cv_sparse", "gpu_detect", "gpu_nmf_zerocopy"]

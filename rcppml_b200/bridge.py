@@ -211,3 +211,55 @@ def bridge_nmf_cv_sparse(indptr, indices, data, m, n, k, W_T0, H0, *, max_iter=1
     return BridgeCvResult(W.astype(np.float32), H.astype(np.float32), d.astype(np.float32), out_iter.value,
                           bool(out_conv.value), out_train.value, out_test.value, out_best.value, out_best_iter.value,
                           out_status.value)
+
+
+def gpu_nmf_zerocopy(col_ptr_addr: int, row_idx_addr: int, values_addr: int, m, n, nnz, k, W_T0, H0, *, maxit=100,
+                     tol=1e-4, seed=42, L1=(0.0, 0.0), L2=(0.0, 0.0), L21=(0.0, 0.0), ortho=(0.0, 0.0),
+                     upper_bound=(0.0, 0.0), cd_maxit=10, verbose=False, nonneg=(True, True), loss_every=1, patience=5,
+                     loss_type=0, huber_delta=1.0, irls_max_iter=20, irls_tol=1e-4, norm_type=0) -> BridgeResult:
+    """ctypes twin of `.gpu_nmf_zerocopy` (R/gpu_backend.R:183-265): the 39-argument `.C` call of
+    rcppml_gpu_nmf_zerocopy_double. The CSC arrays (int32 col_ptr / row_idx, float64 values) are DEVICE arrays
+    whose addresses travel as doubles. NB this R wrapper sends the FIRST element of each penalty pair as the
+    H value (L1_H = L1[1] in R's 1-based indexing, R/gpu_backend.R:240-249) while nonneg is (W, H); kept."""
+    lib = _lib.load()
+    W = np.array(W_T0, dtype=np.float64, order="C")
+    H = np.array(H0, dtype=np.float64, order="C")
+    assert W.shape == (m, k) and H.shape == (n, k)
+    d = np.ones(k, dtype=np.float64)
+    I, D = C.c_int, C.c_double
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    keep = []
+
+    def i_(v):
+        x = I(int(v)); keep.append(x); return C.byref(x)
+
+    def d_(v):
+        x = D(float(v)); keep.append(x); return C.byref(x)
+
+    out_iter, out_conv, out_status = I(0), I(0), I(0)
+    out_loss, out_tol = D(0.0), D(0.0)
+    args = [
+        d_(col_ptr_addr), d_(row_idx_addr), d_(values_addr),
+        i_(m), i_(n), d_(nnz), i_(k),
+        dp(W), dp(H), dp(d),
+        i_(maxit), d_(tol),
+        d_(L1[0]), d_(L1[1]), d_(L2[0]), d_(L2[1]),              # *_H = pair[1] in R = first element
+        d_(L21[0]), d_(L21[1]),
+        d_(ortho[0]), d_(ortho[1]),
+        d_(upper_bound[0]), d_(upper_bound[1]),
+        i_(cd_maxit), i_(verbose), i_(seed),
+        i_(loss_every), i_(patience),
+        i_(nonneg[0]), i_(nonneg[1]),
+        i_(loss_type), d_(huber_delta),
+        i_(irls_max_iter), d_(irls_tol),
+        i_(norm_type),
+        C.byref(out_iter), C.byref(out_conv), C.byref(out_loss),
+        C.byref(out_status),
+        C.byref(out_tol),
+    ]
+    assert len(args) == 39, len(args)
+    fn = lib.rcppml_gpu_nmf_zerocopy_double
+    fn.restype = None
+    fn(*args)
+    return BridgeResult(W.astype(np.float32), H.astype(np.float32), d.astype(np.float32), out_iter.value,
+                        bool(out_conv.value), out_loss.value, out_tol.value, out_status.value)

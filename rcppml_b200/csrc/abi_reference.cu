@@ -6,11 +6,47 @@
 #include <cstdio>
 #include <cstdlib>
 #include <memory>
+#include <mutex>
 
 namespace {
 
 // FACTORNET_GPU_WARN (core/logging.hpp:132) prints to stderr; the .so never calls into R.
 void warn(const char* what) { std::fprintf(stderr, "[RcppML_gpu/b200] %s\n", what); }
+
+// The reference creates its GPUContext per call (nmf/fit_gpu.cuh:552). Here the engine behind the reference entry
+// points is cached per process (SURVEY.md §8b "may cache contexts in process-global state"): its device buffers
+// and staging areas are grow-only, so repeated nmf() calls make no cudaMalloc / cudaFree at all. The calls are
+// synchronous on the R main thread; the mutex only guards against misuse. RCPPML_B200_CACHE=0 restores one
+// engine per call; rcppml_b200_release_cache() frees the device memory (also runs at dyn.unload / exit).
+std::mutex g_mu;
+std::unique_ptr<b200::Engine> g_engine;
+double g_phases[5] = {0, 0, 0, 0, 0};
+
+struct EngineLease {
+    std::unique_lock<std::mutex> lock;
+    std::unique_ptr<b200::Engine> own;
+    b200::Engine* e = nullptr;
+    explicit EngineLease(int dev) : lock(g_mu) {
+        const char* env = std::getenv("RCPPML_B200_CACHE");
+        if (env && env[0] == '0') {
+            own.reset(new b200::Engine(dev));
+            e = own.get();
+            return;
+        }
+        if (!g_engine || g_engine->device != dev) {
+            g_engine.reset();
+            g_engine.reset(new b200::Engine(dev));
+        }
+        e = g_engine.get();
+    }
+    bool ok = false;
+    void commit() { ok = true; }                     // the call succeeded: keep the cached engine
+    ~EngineLease() {
+        if (e) for (int i = 0; i < 5; ++i) g_phases[i] = e->phase_ms[i];
+        if (!ok && !own) g_engine.reset();           // any failure: never reuse an engine in an unknown state
+    }
+    b200::Engine& get() { return *e; }
+};
 
 }  // namespace
 
@@ -72,7 +108,8 @@ void rcppml_gpu_nmf_cv_unified_float(
         if (refuse) { warn(refuse); return; }
         int count = 0;
         if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) { warn("no CUDA device"); return; }
-        b200::Engine E(0);
+        EngineLease lease(0);
+        b200::Engine& E = lease.get();
         E.set_matrix_host<double>(*m, *n, static_cast<int64_t>(*nnz), col_ptr, row_idx, values);
         E.set_factors_host<double>(*k, W, H);
         rcppml_b200_config cfg{};
@@ -101,6 +138,88 @@ void rcppml_gpu_nmf_cv_unified_float(
         if (out_test_loss) *out_test_loss = cr.test_loss;
         if (out_best_test) *out_best_test = cr.best_test_loss;
         if (out_best_iter) *out_best_iter = cr.best_iter;
+        lease.commit();
+        *out_status = 0;
+    } catch (const std::exception& ex) {
+        warn(ex.what());
+        *out_status = -1;
+    } catch (...) {
+        warn("unknown error");
+        *out_status = -1;
+    }
+}
+
+// src/gpu_bridge_nmf.cu:879-967 (39 pointers; called through R's .C from R/gpu_backend.R:225-265). The CSC arrays
+// already live in DEVICE memory (sp_read_gpu): their addresses arrive encoded as doubles because R has no int64.
+// The reference runs this entry in fp64 with its config defaults (no solver_mode on this wire: the struct default
+// is Cholesky+clip, core/config.hpp:133); this engine converts the values to fp32 on the device and runs the same
+// fp32 ALS loop as the standard entry — factors agree with the reference's fp64 run to fp32 accuracy.
+void rcppml_gpu_nmf_zerocopy_double(
+    double* d_col_ptr_addr, double* d_row_idx_addr, double* d_values_addr,
+    int* m, int* n, double* nnz_d, int* k,
+    double* W, double* H, double* d,
+    int* max_iter, double* tol,
+    double* L1_H, double* L1_W, double* L2_H, double* L2_W,
+    double* L21_H, double* L21_W,
+    double* ortho_H, double* ortho_W,
+    double* ub_H, double* ub_W,
+    int* cd_maxit, int* verbose, int* /*seed*/,
+    int* /*loss_every*/, int* patience,
+    int* nonneg_W, int* nonneg_H,
+    int* loss_type, double* /*huber_delta*/,
+    int* /*irls_max_iter*/, double* /*irls_tol*/,
+    int* norm_type,
+    int* out_iter, int* out_converged, double* out_loss,
+    int* out_status,
+    double* out_tol)
+{
+    if (!out_status) return;
+    *out_status = -1;
+    try {
+        const char* refuse = nullptr;
+        if (*loss_type != 0) refuse = "non-MSE loss is outside the B200 ALS path";
+        else if (*L21_H > 0 || *L21_W > 0) refuse = "L21 is outside the B200 ALS path";
+        else if (*ortho_H > 0 || *ortho_W > 0) refuse = "angular/ortho penalty is outside the B200 ALS path";
+        else if (*k < 1 || *k > b200::kMaxKP) refuse = "rank must be in [1, 128] on the B200 ALS path";
+        else if (*max_iter <= 0) refuse = "max_iter must be positive";
+        else if (!(*nnz_d >= 0 && *nnz_d < 2147483648.0)) refuse = "nnz must fit int32";
+        if (refuse) { warn(refuse); return; }
+        auto to_ptr = [](double addr) { return reinterpret_cast<void*>(static_cast<uintptr_t>(addr)); };
+        const int* dev_col_ptr = static_cast<const int*>(to_ptr(*d_col_ptr_addr));
+        const int* dev_row_idx = static_cast<const int*>(to_ptr(*d_row_idx_addr));
+        const double* dev_values = static_cast<const double*>(to_ptr(*d_values_addr));
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, dev_col_ptr) != cudaSuccess || at.type != cudaMemoryTypeDevice) {
+            cudaGetLastError();
+            warn("zero-copy entry: col_ptr is not a device pointer");
+            return;
+        }
+        EngineLease lease(at.device);                        // run where the matrix already is
+        b200::Engine& E = lease.get();
+        E.set_matrix_host<double>(*m, *n, static_cast<int64_t>(*nnz_d), dev_col_ptr, dev_row_idx, dev_values);
+        E.h2d_bytes = 0;                                     // the matrix never crossed PCIe
+        E.set_factors_host<double>(*k, W, H);
+        rcppml_b200_config cfg{};
+        cfg.k = *k; cfg.max_iter = *max_iter; cfg.tol = static_cast<float>(*tol);
+        cfg.L1_H = static_cast<float>(*L1_H); cfg.L1_W = static_cast<float>(*L1_W);
+        cfg.L2_H = static_cast<float>(*L2_H); cfg.L2_W = static_cast<float>(*L2_W);
+        cfg.ub_H = static_cast<float>(*ub_H); cfg.ub_W = static_cast<float>(*ub_W);
+        cfg.nonneg_W = *nonneg_W != 0; cfg.nonneg_H = *nonneg_H != 0;
+        cfg.cd_maxit = *cd_maxit; cfg.cd_tol = 1e-8f;
+        cfg.norm_type = *norm_type;
+        cfg.solver_mode = 1;                                 // core/config.hpp:133 (not on this wire)
+        cfg.patience = *patience; cfg.verbose = *verbose;
+        E.begin_fit(cfg);
+        E.iterate(cfg.max_iter);
+        rcppml_b200_result res{};
+        E.get_result(&res);
+        if (res.status != 0) { warn("Gram matrix not positive definite (Cholesky pivot <= 0)"); return; }
+        E.get_factors_host<double>(W, H, d);
+        if (out_iter) *out_iter = res.iterations;
+        if (out_converged) *out_converged = res.converged;
+        if (out_loss) *out_loss = static_cast<double>(res.train_loss);
+        if (out_tol) *out_tol = static_cast<double>(res.final_tol);
+        lease.commit();
         *out_status = 0;
     } catch (const std::exception& ex) {
         warn(ex.what());
@@ -267,7 +386,8 @@ static void nmf_unified_impl(
         int count = 0;
         if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) { warn("no CUDA device"); return; }
 
-        b200::Engine E(0);
+        EngineLease lease(0);
+        b200::Engine& E = lease.get();
         E.set_matrix_host<double>(*m, *n, static_cast<int64_t>(*nnz), col_ptr, row_idx, values);
         if (mask_p && mask_i && mask_nnz && *mask_nnz > 0) E.set_mask(*mask_nnz, mask_p, mask_i);
         E.set_factors_host<double>(*k, W, H);
@@ -302,6 +422,7 @@ static void nmf_unified_impl(
         if (*verbose)
             std::fprintf(stderr, "[RcppML_gpu/b200] %d iterations, loss %.6g, loop %.3f ms, %d launches\n",
                          res.iterations, res.train_loss, res.loop_ms, res.gpu_launches);
+        lease.commit();
         *out_status = 0;
     } catch (const std::exception& ex) {
         warn(ex.what());
@@ -310,6 +431,20 @@ static void nmf_unified_impl(
         warn("unknown error");
         *out_status = -1;
     }
+}
+
+// ABI EXTENSIONS around the cached engine (see EngineLease above).
+int rcppml_b200_release_cache(void) {
+    std::lock_guard<std::mutex> g(g_mu);
+    g_engine.reset();
+    return 0;
+}
+// Host wall-clock (ms) of the phases of the last reference-ABI call: matrix upload (+fp64->fp32), device
+// transpose + tr(AtA), factor upload, ALS loop (CUDA events), factor download.
+int rcppml_b200_last_call_phases(double* ms5) {
+    std::lock_guard<std::mutex> g(g_mu);
+    for (int i = 0; i < 5; ++i) ms5[i] = g_phases[i];
+    return 0;
 }
 
 }  // extern "C"

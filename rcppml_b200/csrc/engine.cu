@@ -5,6 +5,8 @@
 #include "engine.hpp"
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -46,6 +48,8 @@ static void launch_half_step_l(int lanes, const HalfStepParams& p, int num_sms, 
         case 32: launch_half_step_t<32, 1, SOLVER, BSRC, OUT>(p, num_sms, s, grid_out); break;
         case 108: launch_half_step_t<8, 2, SOLVER, BSRC, OUT>(p, num_sms, s, grid_out); break;
         case 116: launch_half_step_t<16, 2, SOLVER, BSRC, OUT>(p, num_sms, s, grid_out); break;
+        case 304: launch_half_step_t<4, 4, SOLVER, BSRC, OUT>(p, num_sms, s, grid_out); break;
+        case 308: launch_half_step_t<8, 4, SOLVER, BSRC, OUT>(p, num_sms, s, grid_out); break;
         default: throw std::runtime_error("unsupported lane-group geometry");
     }
 }
@@ -147,7 +151,10 @@ static __global__ void cv_prepare_gram_kernel(const float* __restrict__ G, int K
 // ---------------------------------------------------------------------------------------------
 // Engine
 // ---------------------------------------------------------------------------------------------
+static std::atomic<int> g_engine_counter{0};
+
 Engine::Engine(int dev) : device(dev) {
+    const_slot = g_engine_counter.fetch_add(1) % kConstSlots;
     B200_CUDA_CHECK(cudaSetDevice(device));
     cudaDeviceProp prop{};
     B200_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
@@ -204,8 +211,7 @@ void Engine::set_dims(int m_, int n_) {
 void Engine::finish_matrix() {
     // tr(AᵀA) in fp64 (primitives/primitives.hpp:101-115) over this rank's column block, then over ranks
     const int nb = 1024;
-    DeviceBuffer<double> part;
-    part.ensure(nb);
+    struct { double* ptr; } part{scratch<double>(6, nb)};
     sumsq_kernel<<<nb, 256, 0, stream>>>(Ax.ptr, nnz, part.ptr);
     std::vector<double> hp(nb);
     B200_CUDA_CHECK(cudaMemcpyAsync(hp.data(), part.ptr, nb * sizeof(double), cudaMemcpyDeviceToHost, stream));
@@ -242,9 +248,10 @@ void Engine::transpose_csc(const int* sp, const int* si, const float* sx, int nc
         B200_CUDA_CHECK(cudaStreamSynchronize(stream));
         return;
     }
-    DeviceBuffer<int> col_of, keys_out;
-    DeviceBuffer<unsigned> perm_in, perm_out;
-    col_of.ensure(cnt); keys_out.ensure(cnt); perm_in.ensure(cnt); perm_out.ensure(cnt);
+    struct P { int* ptr; };
+    struct U { unsigned* ptr; };
+    const P col_of{scratch<int>(1, cnt)}, keys_out{scratch<int>(2, cnt)};
+    const U perm_in{scratch<unsigned>(3, cnt)}, perm_out{scratch<unsigned>(4, cnt)};
     const int T = 256;
     const unsigned gb = static_cast<unsigned>((cnt + T - 1) / T);
     expand_columns_kernel<<<gb, T, 0, stream>>>(sp, ncols, cnt, col_of.ptr, col_id_offset);
@@ -253,8 +260,7 @@ void Engine::transpose_csc(const int* sp, const int* si, const float* sx, int nc
     while ((1LL << end_bit) < static_cast<long long>(nrows) && end_bit < 31) ++end_bit;
     size_t temp_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, si, keys_out.ptr, perm_in.ptr, perm_out.ptr, cnt, 0, end_bit, stream);
-    DeviceBuffer<unsigned char> temp;
-    temp.ensure(temp_bytes);
+    struct { unsigned char* ptr; } temp{scratch<unsigned char>(5, temp_bytes)};
     B200_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(temp.ptr, temp_bytes, si, keys_out.ptr, perm_in.ptr, perm_out.ptr,
                                                     cnt, 0, end_bit, stream));
     permute_gather_kernel<<<gb, T, 0, stream>>>(perm_out.ptr, col_of.ptr, sx, cnt, di.ptr, dx.ptr);
@@ -266,20 +272,27 @@ void Engine::transpose_csc(const int* sp, const int* si, const float* sx, int nc
 template <class ValT>
 void Engine::upload_csc(int ncols, int64_t cnt, const int* col_ptr, const int* row_idx, const ValT* values,
                         DeviceBuffer<int>& dp, DeviceBuffer<int>& di, DeviceBuffer<float>& dx) {
+    // cudaMemcpyDefault: the sources may be host OR device pointers (zero-copy entry, UVA decides)
     B200_REQUIRE(cnt >= 0 && cnt < (1LL << 31), "set_matrix: nnz must fit int32 (reference boundary, bridge_nmf.hpp:196)");
     dp.ensure(static_cast<size_t>(ncols) + 1);
     di.ensure(std::max<int64_t>(cnt, 1) + 4);
     dx.ensure(std::max<int64_t>(cnt, 1) + 4);
-    B200_CUDA_CHECK(cudaMemcpyAsync(dp.ptr, col_ptr, (static_cast<size_t>(ncols) + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
+    B200_CUDA_CHECK(cudaMemcpyAsync(dp.ptr, col_ptr, (static_cast<size_t>(ncols) + 1) * sizeof(int), cudaMemcpyDefault, stream));
     if (cnt > 0) {
-        B200_CUDA_CHECK(cudaMemcpyAsync(di.ptr, row_idx, cnt * sizeof(int), cudaMemcpyHostToDevice, stream));
+        B200_CUDA_CHECK(cudaMemcpyAsync(di.ptr, row_idx, cnt * sizeof(int), cudaMemcpyDefault, stream));
         if (std::is_same<ValT, float>::value) {
-            B200_CUDA_CHECK(cudaMemcpyAsync(dx.ptr, values, cnt * sizeof(float), cudaMemcpyHostToDevice, stream));
+            B200_CUDA_CHECK(cudaMemcpyAsync(dx.ptr, values, cnt * sizeof(float), cudaMemcpyDefault, stream));
         } else {
-            DeviceBuffer<double> tmp;
-            tmp.ensure(cnt);
-            B200_CUDA_CHECK(cudaMemcpyAsync(tmp.ptr, values, cnt * sizeof(double), cudaMemcpyHostToDevice, stream));
-            f64_to_f32_kernel<<<static_cast<unsigned>((cnt + 255) / 256), 256, 0, stream>>>(tmp.ptr, dx.ptr, cnt);
+            cudaPointerAttributes at{};
+            const bool on_device = cudaPointerGetAttributes(&at, values) == cudaSuccess && at.type == cudaMemoryTypeDevice;
+            cudaGetLastError();
+            const double* src = reinterpret_cast<const double*>(values);
+            if (!on_device) {                                  // host doubles: stage once, convert on the device
+                double* tmp = scratch<double>(0, cnt);
+                B200_CUDA_CHECK(cudaMemcpyAsync(tmp, values, cnt * sizeof(double), cudaMemcpyDefault, stream));
+                src = tmp;
+            }
+            f64_to_f32_kernel<<<static_cast<unsigned>((cnt + 255) / 256), 256, 0, stream>>>(src, dx.ptr, cnt);
             B200_CUDA_CHECK(cudaStreamSynchronize(stream));
         }
     }
@@ -293,10 +306,15 @@ void Engine::set_matrix_host(int m_, int n_, int64_t nnz_, const int* col_ptr, c
     B200_REQUIRE(world == 1, "set_matrix: with a communicator use set_matrix_sharded");
     set_dims(m_, n_);
     nnz = nnz_;
+    const auto t0 = std::chrono::steady_clock::now();
     upload_csc<ValT>(n, nnz, col_ptr, row_idx, values, Ap, Ai, Ax);
+    const auto t1 = std::chrono::steady_clock::now();
     transpose_csc(Ap.ptr, Ai.ptr, Ax.ptr, n, m, nnz, Atp, Ati, Atx, 0);
     nnz_w = nnz;
     finish_matrix();
+    has_mask = false;                                      // a new matrix invalidates the previous mask
+    phase_ms[0] = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    phase_ms[1] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();
 }
 template void Engine::set_matrix_host<float>(int, int, int64_t, const int*, const int*, const float*);
 template void Engine::set_matrix_host<double>(int, int, int64_t, const int*, const int*, const double*);
@@ -390,7 +408,9 @@ void Engine::alloc_factors(int k_) {
     LANES = lanes_for_rank(k);
     KP = padded_rank(k);
     nv_override = 0;
-    if (const char* env = std::getenv("RCPPML_B200_NV")) nv_override = std::atoi(env);   // tuning knob (1 or 2)
+    if (const char* env = std::getenv("RCPPML_B200_NV")) nv_override = std::atoi(env);   // tuning knobs (1, 2 or 4)
+    nv_short_override = 0;
+    if (const char* env = std::getenv("RCPPML_B200_NV_SHORT")) nv_short_override = std::atoi(env);
     if (peers_ready && (static_cast<size_t>(m_pad) * KP > W_T.count || static_cast<size_t>(n_pad) * KP > H.count ||
                         KP * KP > xchg_ne_max))
         comm_ipc_close();                                 // the mapped buffers are about to move: back to NCCL
@@ -403,8 +423,7 @@ void Engine::alloc_factors(int k_) {
     G_h.ensure(static_cast<size_t>(KP) * KP);
     M1.ensure(static_cast<size_t>(KP) * KP);
     M2.ensure(static_cast<size_t>(KP) * KP);
-    dblk.ensure(static_cast<size_t>(KP) * 4);
-    rcp.ensure(KP);
+    dblk.ensure(sizeof(SolverConsts) / sizeof(float));       // [kMaxKP*4] diagonal blocks, then [kMaxKP] reciprocals
     gram_grid = num_sms * 4;
     gram_partials.ensure(static_cast<size_t>(gram_grid) * KP * KP);
     B200_CUDA_CHECK(cudaMemsetAsync(gram_partials.ptr, 0, gram_partials.bytes(), stream));   // upper tiles are never written
@@ -412,7 +431,7 @@ void Engine::alloc_factors(int k_) {
     int gmax = 0;
     HalfStepParams dummy{};
     for (int solver = 0; solver < 2; ++solver) {
-        for (int geom : {LANES, (KP == 64 || KP == 128) ? 100 + KP / 8 : LANES}) {
+        for (int geom : {LANES, (KP == 64 || KP == 128) ? 100 + KP / 8 : LANES, (KP == 64 || KP == 128) ? 300 + KP / 16 : LANES}) {
             int g = 0;
             launch_half_step(geom, solver, BSRC_GATHER, OUT_SOLVE, dummy, num_sms, stream, &g);
             gmax = std::max(gmax, g);
@@ -435,9 +454,9 @@ template <class T>
 void Engine::set_factors_host(int k_, const T* W_T_host, const T* H_host) {
     use_device();
     alloc_factors(k_);
+    const auto t0 = std::chrono::steady_clock::now();
     auto upload = [&](const T* src, float* dst, long long ncols) {
-        DeviceBuffer<T> tmp;
-        tmp.ensure(static_cast<size_t>(ncols) * k);
+        struct { T* ptr; } tmp{scratch<T>(0, static_cast<size_t>(ncols) * k)};
         B200_CUDA_CHECK(cudaMemcpyAsync(tmp.ptr, src, static_cast<size_t>(ncols) * k * sizeof(T), cudaMemcpyHostToDevice, stream));
         const long long total = ncols * KP;
         pad_convert_kernel<T><<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(tmp.ptr, dst, ncols, k, KP);
@@ -446,6 +465,7 @@ void Engine::set_factors_host(int k_, const T* W_T_host, const T* H_host) {
     };
     upload(W_T_host, W_T.ptr, m);
     upload(H_host, H.ptr, n);
+    phase_ms[2] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 }
 template void Engine::set_factors_host<float>(int, const float*, const float*);
 template void Engine::set_factors_host<double>(int, const double*, const double*);
@@ -468,10 +488,10 @@ template <class T>
 void Engine::get_factors_host(T* W_T_host, T* H_host, T* d_host) {
     use_device();
     B200_REQUIRE(factors_ready, "no factors");
+    const auto t0 = std::chrono::steady_clock::now();
     auto download = [&](const float* src, T* dst, long long ncols) {
         if (!dst) return;
-        DeviceBuffer<T> tmp;
-        tmp.ensure(static_cast<size_t>(ncols) * k);
+        struct { T* ptr; } tmp{scratch<T>(0, static_cast<size_t>(ncols) * k)};
         const long long total = ncols * k;
         unpad_convert_kernel<T><<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(src, tmp.ptr, ncols, k, KP);
         B200_CUDA_CHECK(cudaMemcpyAsync(dst, tmp.ptr, static_cast<size_t>(total) * sizeof(T), cudaMemcpyDeviceToHost, stream));
@@ -481,6 +501,7 @@ void Engine::get_factors_host(T* W_T_host, T* H_host, T* d_host) {
     download(W_T.ptr, W_T_host, m);
     download(H.ptr, H_host, n);
     download(d.ptr, d_host, 1);
+    phase_ms[4] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 }
 template void Engine::get_factors_host<float>(float*, float*, float*);
 template void Engine::get_factors_host<double>(double*, double*, double*);
@@ -552,7 +573,11 @@ void Engine::prepare_solver(const float* G, float L2, int sec) {
     const int solver = cfg.solver_mode == 0 ? SOLVER_CD : SOLVER_CHOL;
     const size_t smem = static_cast<size_t>(2) * KP * KP * sizeof(float);
     B200_CUDA_CHECK(cudaFuncSetAttribute(prepare_solver_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 128 * 128 * 4));
-    prepare_solver_kernel<<<1, kPrepThreads, smem, stream>>>(G, KP, k, L2, solver, M1.ptr, M2.ptr, dblk.ptr, rcp.ptr, state.ptr);
+    prepare_solver_kernel<<<1, kPrepThreads, smem, stream>>>(G, KP, k, L2, solver, M1.ptr, M2.ptr, dblk.ptr, dblk.ptr + kMaxKP * 4, state.ptr);
+    // warp-uniform operands -> this engine's constant-memory slot (kernels_solve.cuh SolverConsts); rcp follows
+    // dblk in one device buffer, laid out like the struct
+    B200_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_solver, dblk.ptr, sizeof(SolverConsts), sizeof(SolverConsts) * const_slot,
+                                            cudaMemcpyDeviceToDevice, stream));
     launches[sec] += 1;
     sec_end(sec);
 }
@@ -567,9 +592,10 @@ int Engine::geometry_for(long long nnz_, long long ncols) const {
     if (KP == 64 || KP == 128) {
         const double avg = ncols > 0 ? static_cast<double>(nnz_) / static_cast<double>(ncols) : 0.0;
         nv = (avg < 400.0) ? 2 : 1;
-        if (nv_override == 1 || nv_override == 2) nv = nv_override;
+        if (avg < 400.0 && (nv_short_override == 1 || nv_short_override == 2 || nv_short_override == 4)) nv = nv_short_override;
+        if (nv_override == 1 || nv_override == 2 || nv_override == 4) nv = nv_override;
     }
-    return nv == 2 ? 100 + KP / 8 : LANES;
+    return nv == 1 ? LANES : 100 * (nv - 1) + KP / (4 * nv);
 }
 
 static int pick_cols_per_fetch(long long nnz, long long ncols, int num_sms) {
@@ -591,7 +617,7 @@ HalfStepParams Engine::solve_params(int which, bool warm) const {
     p.vals = h ? Ax.ptr : Atx.ptr;
     p.F = h ? W_T.ptr : H.ptr;                          // full (replicated) factor being gathered
     p.X = h ? H.ptr : W_T.ptr;                          // full factor being solved; this rank owns a block of it
-    p.M1 = M1.ptr; p.M2 = M2.ptr; p.dblk = dblk.ptr; p.rcp = rcp.ptr;
+    p.M1 = M1.ptr; p.M2 = M2.ptr; p.dblk = dblk.ptr; p.rcp = dblk.ptr + kMaxKP * 4; p.cslot = const_slot;
     p.B = nullptr; p.nslots = 0; p.slot_stride = 0; p.b_local_index = 0;
     p.ncols = h ? n_loc : m_loc;
     p.col_offset = h ? col_begin : row_begin;
@@ -919,6 +945,7 @@ void Engine::iterate(int n_iters) {
     float ms = 0.f;
     B200_CUDA_CHECK(cudaEventElapsedTime(&ms, ev_loop_begin, ev_loop_end));
     loop_ms = ms;
+    phase_ms[3] = ms;
     collect_profile();
 }
 

@@ -91,10 +91,11 @@ public:
     DeviceBuffer<float> test_hist;
     float trAtA = 0.f;          // tr(AᵀA) of the whole matrix
 
-    int k = 0, KP = 0, LANES = 0, nv_override = 0;
+    int k = 0, KP = 0, LANES = 0, nv_override = 0, nv_short_override = 0;
     int geometry_for(long long nnz, long long ncols) const;
     DeviceBuffer<float> W_T, H, d;
-    DeviceBuffer<float> G_w, G_h, M1, M2, dblk, rcp;
+    DeviceBuffer<float> G_w, G_h, M1, M2, dblk;     // dblk: SolverConsts image (diagonal blocks, then reciprocals)
+    int const_slot = 0;
     DeviceBuffer<double> gram_partials, solve_partials;   // per-CTA partials (fixed-order reductions)
     DeviceBuffer<double> red_gram, red_small;             // reduced sums: k×k Gram | k row sums + cross term
     DeviceBuffer<int> counters;
@@ -109,6 +110,18 @@ public:
     double loop_ms = 0.0;
     unsigned long long cd_sweeps = 0;
     size_t h2d_bytes = 0, d2h_bytes = 0;
+
+    // Grow-only staging buffers (fp64 wire copies, transpose temporaries): a cached engine (abi_reference.cu)
+    // makes its second and later calls without a single cudaMalloc / cudaFree.
+    std::array<DeviceBuffer<unsigned char>, 8> scratch_;
+    template <class T> T* scratch(int slot, size_t count) {
+        scratch_[slot].ensure(count * sizeof(T));
+        return reinterpret_cast<T*>(scratch_[slot].ptr);
+    }
+    void release_scratch() { for (auto& b : scratch_) b.release(); }
+    // Host wall-clock of the phases of the last set_matrix / set_factors / iterate / get_factors sequence (ms):
+    // [0] matrix upload (+fp64->fp32), [1] device transpose + tr(AtA), [2] factor upload, [3] ALS loop, [4] factor download
+    double phase_ms[5] = {0, 0, 0, 0, 0};
 
     bool profiling = false;
     std::array<std::vector<std::pair<cudaEvent_t, cudaEvent_t>>, RCPPML_B200_NUM_SECTIONS> prof_events;

@@ -61,7 +61,19 @@ struct HalfStepParams {
     // X on the other GPUs (NVLink P2P stores), so the "all-gather" of the factor overlaps with the solve.
     float* peerX[7];
     int npeers;
+    int cslot;                         // c_solver slot holding this launch's diagonal blocks / reciprocals
 };
+
+// Warp-uniform solver operands (the 4x4 diagonal blocks and the pivot reciprocals) live in CONSTANT memory:
+// every lane reads the same address, and an LDS.128 of a broadcast address still costs four wavefronts of the
+// L1/shared data pipe — the pipe that bounds this kernel (ncu: l1tex__data_pipe_lsu_wavefronts 69-79 %). The
+// constant cache serves them off that pipe. One slot per engine instance (prepare_solver copies device->symbol).
+constexpr int kConstSlots = 8;
+struct SolverConsts {
+    float dblk[kMaxKP * 4];
+    float rcp[kMaxKP];
+};
+static __constant__ SolverConsts c_solver[kConstSlots];
 
 template <int LANES>
 __device__ __forceinline__ float gshfl(unsigned mask, float v, int src) {
@@ -72,6 +84,52 @@ __device__ __forceinline__ int gshfl(unsigned mask, int v, int src) {
     return __shfl_sync(mask, v, src, LANES);
 }
 
+#ifndef B200_SCALAR_FP32   // default: packed pairs (-DB200_SCALAR_FP32 selects the scalar FMUL + FADD form)
+// Blackwell packed fp32 pairs (FFMA2 / FADD2): two IEEE-rounded operations per issue slot. ptxas contracts
+// mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 even under --fmad=false, which would break the separately-rounded
+// contract, so the product is written as fma(a, b, +0): RN(a·b + 0) == RN(a·b) except that an exact-zero product
+// comes out as +0 instead of -0 — invisible here, because the accumulators it is added to / subtracted from
+// are never -0 (they start at +0, and RN(x + y) = -0 only when x = y = -0).
+__device__ __forceinline__ unsigned long long pk2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(unsigned long long p, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(p));
+}
+__device__ __forceinline__ unsigned long long mul2_rn(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(0ULL));
+    return r;
+}
+__device__ __forceinline__ unsigned long long add2_rn(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long sub2_rn(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ void axpy4(float (&acc)[4], float v, const float4& f) {
+    const unsigned long long vv = pk2(v, v);
+    unsigned long long a0 = pk2(acc[0], acc[1]), a1 = pk2(acc[2], acc[3]);
+    a0 = add2_rn(a0, mul2_rn(vv, pk2(f.x, f.y)));
+    a1 = add2_rn(a1, mul2_rn(vv, pk2(f.z, f.w)));
+    upk2(a0, acc[0], acc[1]);
+    upk2(a1, acc[2], acc[3]);
+}
+__device__ __forceinline__ void sub_scaled4(float (&b)[4], const float4& g, float s) {
+    const unsigned long long ss = pk2(s, s);
+    unsigned long long b0 = pk2(b[0], b[1]), b1 = pk2(b[2], b[3]);
+    b0 = sub2_rn(b0, mul2_rn(pk2(g.x, g.y), ss));
+    b1 = sub2_rn(b1, mul2_rn(pk2(g.z, g.w), ss));
+    upk2(b0, b[0], b[1]);
+    upk2(b1, b[2], b[3]);
+}
+#else
 // acc[e] = acc[e] + v*f[e], separately rounded (matches SSE2 Eigen `b += v * col`).
 __device__ __forceinline__ void axpy4(float (&acc)[4], float v, const float4& f) {
     acc[0] = __fadd_rn(acc[0], __fmul_rn(v, f.x));
@@ -86,6 +144,7 @@ __device__ __forceinline__ void sub_scaled4(float (&b)[4], const float4& g, floa
     b[2] = __fsub_rn(b[2], __fmul_rn(g.z, s));
     b[3] = __fsub_rn(b[3], __fmul_rn(g.w, s));
 }
+#endif
 
 // 128-bit load of a factor-row word on the read-only path. -DB200_GATHER_NOALLOC selects
 // ld.global.nc.L1::no_allocate (rows are used once per SM; don't let them evict the CSC segments).
@@ -223,7 +282,7 @@ __device__ __forceinline__ void warm_start_correct(const float* sG, int k, int g
 
 // cd_nnls_col_fixed (nnls_batch.hpp:71-132) with L1 = L2 = upper_bound = 0 as the fused path calls it.
 template <int LANES, int NV>
-__device__ __forceinline__ int cd_solve(const HalfStepParams& p, const float* sG, const float* sRcp, int gl,
+__device__ __forceinline__ int cd_solve(const HalfStepParams& p, const float* sG, const float* sDblk, const float* sRcp, int gl,
                                         unsigned gmask, float (&x)[NV][4], float (&b)[NV][4]) {
     constexpr int KP = LANES * 4 * NV;
     const float4* sG4 = reinterpret_cast<const float4*>(sG);
@@ -244,7 +303,7 @@ __device__ __forceinline__ int cd_solve(const HalfStepParams& p, const float* sG
                     const int i = i0 + e;
                     const float bi = gshfl<LANES>(gmask, b[nv][e], owner);
                     const float xi = gshfl<LANES>(gmask, x[nv][e], owner);
-                    const float gd = sG[i * KP + i];               // 0 for padded coordinates
+                    const float gd = sDblk[(i >> 2) * 16 + (i & 3) * 5];   // G_ii from the diagonal blocks (0 when padded)
                     float ad = 0.f, xn = xi;
                     if (gd > 0.f) {                                // :90
                         const float diff = div_exact(bi, gd, sRcp[i]);   // :92
@@ -383,7 +442,7 @@ __device__ __forceinline__ void chol_solve(const float* sLz, const float* sLTz, 
 #define B200_SOLVE_MIN_CTAS 3   // <= 85 registers: 3 CTAs (24 warps) per SM; 4 CTAs (64 regs) spills and is no faster
 #endif
 template <int LANES, int NV, int SOLVER, int BSRC, int OUT>
-__global__ void __launch_bounds__(256, B200_SOLVE_MIN_CTAS) half_step_kernel(const HalfStepParams p) {
+__global__ void __launch_bounds__(256, (NV >= 4) ? 2 : B200_SOLVE_MIN_CTAS) half_step_kernel(const HalfStepParams p) {
     constexpr int KP = LANES * 4 * NV;
     constexpr int GPW = 32 / LANES;   // groups per warp
     extern __shared__ __align__(16) float smem[];
@@ -391,9 +450,10 @@ __global__ void __launch_bounds__(256, B200_SOLVE_MIN_CTAS) half_step_kernel(con
 
     float* sM1 = smem;
     float* sM2 = smem + ((OUT == OUT_SOLVE) ? KP * KP : 0);
-    float* sDblk = sM2 + ((OUT == OUT_SOLVE && SOLVER == SOLVER_CHOL) ? KP * KP : 0);
-    float* sRcp = sDblk + KP * 4;
-    double* sRed = reinterpret_cast<double*>(sRcp + KP);     // [256/LANES][KP] norms + [256] cross; 8-byte aligned (KP % 16 == 0)
+    float* sEnd = sM2 + ((OUT == OUT_SOLVE && SOLVER == SOLVER_CHOL) ? KP * KP : 0);
+    const float* sDblk = c_solver[p.cslot].dblk;              // constant memory (see SolverConsts)
+    const float* sRcp = c_solver[p.cslot].rcp;
+    double* sRed = reinterpret_cast<double*>(sEnd);     // [256/LANES][KP] norms + [256] cross; 8-byte aligned (KP % 16 == 0)
 
     if (OUT == OUT_SOLVE) {
         const float4* g4 = reinterpret_cast<const float4*>(p.M1);
@@ -404,8 +464,6 @@ __global__ void __launch_bounds__(256, B200_SOLVE_MIN_CTAS) half_step_kernel(con
             float4* t4 = reinterpret_cast<float4*>(sM2);
             for (int t = threadIdx.x; t < KP * KP / 4; t += blockDim.x) t4[t] = l4[t];
         }
-        for (int t = threadIdx.x; t < KP * 4; t += blockDim.x) sDblk[t] = p.dblk[t];
-        for (int t = threadIdx.x; t < KP; t += blockDim.x) sRcp[t] = p.rcp[t];
     }
     __syncthreads();
 
@@ -492,7 +550,7 @@ __global__ void __launch_bounds__(256, B200_SOLVE_MIN_CTAS) half_step_kernel(con
                     x[nv][0] = xv.x; x[nv][1] = xv.y; x[nv][2] = xv.z; x[nv][3] = xv.w;
                 }
                 if (p.warm) warm_start_correct<LANES, NV>(sM1, p.k, gl, gmask, x, b);
-                my_sweeps += cd_solve<LANES, NV>(p, sM1, sRcp, gl, gmask, x, b);
+                my_sweeps += cd_solve<LANES, NV>(p, sM1, sDblk, sRcp, gl, gmask, x, b);
             } else {
                 chol_solve<LANES, NV>(sM1, sM2, sDblk, sRcp, p.k, gl, gmask, b);
 #pragma unroll
@@ -581,7 +639,7 @@ __global__ void __launch_bounds__(256, B200_SOLVE_MIN_CTAS) half_step_kernel(con
 template <int LANES, int NV, int SOLVER, int OUT>
 inline size_t half_step_smem_bytes() {
     constexpr int KP = LANES * 4 * NV;
-    size_t f = KP * 5;                                       // diagonal blocks + reciprocals
+    size_t f = 0;
     if (OUT == OUT_SOLVE) f += static_cast<size_t>(KP) * KP * (SOLVER == SOLVER_CHOL ? 2 : 1);
     return f * sizeof(float) + (static_cast<size_t>(256 / LANES) * KP + 256) * sizeof(double);
 }

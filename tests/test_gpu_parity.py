@@ -277,6 +277,54 @@ def test_reference_abi_unified_float(oracle):
     assert bad.status == -1 and np.array_equal(bad.W_T, W0)
 
 
+def test_reference_abi_zerocopy_and_cached_engine(oracle):
+    """rcppml_gpu_nmf_zerocopy_double (src/gpu_bridge_nmf.cu:879, R/gpu_backend.R:183): CSC arrays already on the
+    device, addresses passed as doubles. Also exercises the process-cached engine behind the reference entry
+    points: a big call, a small one, a masked one and a repeat must not leak state into each other."""
+    import ctypes as C
+    import torch
+    import rcppml_b200 as rb
+    from rcppml_b200 import _lib
+    m, n, k = 900, 600, 32
+    A = random_csc(m, n, 0.05, 77, counts=True)
+    W0, H0 = oracle.initialize_factors(k, m, n, 42)
+    ref = oracle.nmf_fit(A.indptr, A.indices, A.data, m, n, k, W0, H0, max_iter=6, tol=0.0, solver_mode=1,
+                         L1=(0.02, 0.01))
+    first = rb.bridge_nmf_sparse(A.indptr, A.indices, A.data, m, n, k, W0, H0, max_iter=6, tol=0.0, solver_mode=1,
+                                 L1=(0.02, 0.01))
+    assert first.status == 0 and rel_err(first.W_T, ref.W_T) <= RTOL and rel_err(first.H, ref.H) <= RTOL
+    # smaller problem, other rank, masked, through the same cached engine
+    m2, n2, k2 = 300, 200, 8
+    A2 = random_csc(m2, n2, 0.1, 51)
+    M2 = random_csc(m2, n2, 0.05, 52)
+    W2, H2 = oracle.initialize_factors(k2, m2, n2, 42)
+    ref2 = oracle.nmf_fit(A2.indptr, A2.indices, A2.data, m2, n2, k2, W2, H2, max_iter=4, tol=0.0, solver_mode=0,
+                          mask=(M2.indptr, M2.indices))
+    out2 = rb.bridge_nmf_sparse(A2.indptr, A2.indices, A2.data, m2, n2, k2, W2, H2, max_iter=4, tol=0.0, solver_mode=0,
+                                mask=(M2.indptr, M2.indices))
+    assert out2.status == 0 and rel_err(out2.W_T, ref2.W_T) <= RTOL and rel_err(out2.H, ref2.H) <= RTOL
+    # zero-copy: device-resident CSC (the mask of the previous call must be gone)
+    dp = torch.from_numpy(np.ascontiguousarray(A.indptr, np.int32)).cuda()
+    di = torch.from_numpy(np.ascontiguousarray(A.indices, np.int32)).cuda()
+    dx = torch.from_numpy(np.ascontiguousarray(A.data, np.float64)).cuda()
+    torch.cuda.synchronize()
+    zc = rb.gpu_nmf_zerocopy(dp.data_ptr(), di.data_ptr(), dx.data_ptr(), m, n, int(A.indptr[n]), k, W0, H0, maxit=6,
+                             tol=0.0, L1=(0.01, 0.02))            # this wrapper's pairs are (H, W)
+    assert zc.status == 0 and zc.iterations == 6
+    assert np.array_equal(zc.W_T, first.W_T) and np.array_equal(zc.H, first.H) and np.array_equal(zc.d, first.d)
+    assert zc.train_loss == first.train_loss
+    ph = (C.c_double * 5)()
+    lib = _lib.load()
+    assert lib.rcppml_b200_last_call_phases(ph) == 0 and ph[3] > 0.0
+    # host pointers are refused by the zero-copy entry; the cache survives a refused call and a release
+    bad = rb.gpu_nmf_zerocopy(A.indptr.ctypes.data, A.indices.ctypes.data, 0, m, n, int(A.indptr[n]), k, W0, H0, maxit=2)
+    assert bad.status == -1
+    assert lib.rcppml_b200_release_cache() == 0
+    again = rb.bridge_nmf_sparse(A.indptr, A.indices, A.data, m, n, k, W0, H0, max_iter=6, tol=0.0, solver_mode=1,
+                                 L1=(0.02, 0.01))
+    assert np.array_equal(again.W_T, first.W_T) and np.array_equal(again.H, first.H)
+
+
 def test_large_synthetic_properties(eng):
     """Full-width rows at reduced column count: size-independent properties (non-negativity,
     unit L1 row norms, monotone loss, determinism run to run)."""
