@@ -70,11 +70,21 @@ void launch_half_step(int lanes, int solver, int bsrc, int out, const HalfStepPa
 
 static void launch_normalize_gram(int KP, float* X, long long ncols, const float* d, int normalize, double* partials,
                                   const int* stop, int grid, cudaStream_t s) {
+#ifdef B200_GRAM_DFMA      // register-tiled DFMA version (kept for comparison; bound by shared-memory delivery)
     switch (KP) {
         case 16: normalize_gram_kernel<16, 64><<<grid, kGramThreads, 0, s>>>(X, ncols, d, normalize, partials, stop); break;
         case 32: normalize_gram_kernel<32, 64><<<grid, kGramThreads, 0, s>>>(X, ncols, d, normalize, partials, stop); break;
         case 64: normalize_gram_kernel<64, 32><<<grid, kGramThreads, 0, s>>>(X, ncols, d, normalize, partials, stop); break;
         case 128: normalize_gram_kernel<128, 32><<<grid, kGramThreads, 0, s>>>(X, ncols, d, normalize, partials, stop); break;
+        default: throw std::runtime_error("unsupported padded rank");
+    }
+    return;
+#endif
+    switch (KP) {
+        case 16: normalize_gram_mma_kernel<16, 64><<<grid, GramMmaGeom<16>::WARPS * 32, 0, s>>>(X, ncols, d, normalize, partials, stop); break;
+        case 32: normalize_gram_mma_kernel<32, 64><<<grid, GramMmaGeom<32>::WARPS * 32, 0, s>>>(X, ncols, d, normalize, partials, stop); break;
+        case 64: normalize_gram_mma_kernel<64, 32><<<grid, GramMmaGeom<64>::WARPS * 32, 0, s>>>(X, ncols, d, normalize, partials, stop); break;
+        case 128: normalize_gram_mma_kernel<128, 32><<<grid, GramMmaGeom<128>::WARPS * 32, 0, s>>>(X, ncols, d, normalize, partials, stop); break;
         default: throw std::runtime_error("unsupported padded rank");
     }
 }

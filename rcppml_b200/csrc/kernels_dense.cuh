@@ -133,6 +133,120 @@ static __global__ void __launch_bounds__(kGramThreads) normalize_gram_kernel(flo
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// normalize + Gram on the FP64 tensor cores (DMMA m8n8k4). Same contract as normalize_gram_kernel — exact
+// fp32xfp32 products accumulated in fp64, rounded once by gram_from_sums_kernel — but the operands reach the
+// math pipe as MMA fragments: one LDS.64 per lane feeds 256 FMAs, where the register-tiled DFMA version needs
+// 8 loads per 16 FMAs and is bound by shared-memory delivery (ncu r01c/r01g: l1tex 74 %, FP64 pipe 38 %).
+// G is cut into 8x8 tiles; only the NT(NT+1)/2 tiles of the lower triangle are computed, TPW per warp.
+// Fragment of tile-row t for the 4 staged columns c..c+3: lane l holds X[t*8 + l/4][c + l%4] — this is both
+// the A fragment (rows of G) and the col-major B fragment (columns of G). Staged rows are padded to
+// KP + 4 doubles so that the 16 lanes of a half-warp hit 16 distinct 8-byte banks.
+// ---------------------------------------------------------------------------------------------
+template <int KP> struct GramMmaGeom;
+template <> struct GramMmaGeom<16> { static constexpr int WARPS = 3, TPW = 1; };
+template <> struct GramMmaGeom<32> { static constexpr int WARPS = 5, TPW = 2; };
+template <> struct GramMmaGeom<64> { static constexpr int WARPS = 6, TPW = 6; };
+template <> struct GramMmaGeom<128> { static constexpr int WARPS = 8, TPW = 17; };
+
+template <int KP, int TC>
+static __global__ void __launch_bounds__(GramMmaGeom<KP>::WARPS * 32) normalize_gram_mma_kernel(
+    float* __restrict__ X, long long ncols, const float* __restrict__ d, int normalize, double* __restrict__ partials,
+    const int* __restrict__ stop_flag) {
+    constexpr int WARPS = GramMmaGeom<KP>::WARPS, TPW = GramMmaGeom<KP>::TPW, THREADS = WARPS * 32;
+    constexpr int NT = KP / 8;
+    static_assert(WARPS * TPW == NT * (NT + 1) / 2, "tiles of the lower triangle must split evenly over the warps");
+    constexpr int V4 = KP / 4;
+    constexpr int ROWD = KP + 4;
+    __shared__ __align__(16) double sX[TC][ROWD];
+    __shared__ float sD[KP];
+    if (*stop_flag) return;
+    for (int t = threadIdx.x; t < KP; t += blockDim.x) sD[t] = normalize ? d[t] : 1.f;
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // tile u of this warp: index e = warp*TPW + u in the row-major enumeration of the lower triangle
+    int fa[TPW], fb[TPW];                              // fragment offsets (doubles) inside a 4-column slab
+    int t_i[TPW], t_j[TPW];
+#pragma unroll
+    for (int u = 0; u < TPW; ++u) {
+        const int e = warp * TPW + u;
+        int ti = 0;
+        while ((ti + 1) * (ti + 2) / 2 <= e) ++ti;
+        const int tj = e - ti * (ti + 1) / 2;
+        t_i[u] = ti; t_j[u] = tj;
+        fa[u] = (lane & 3) * ROWD + ti * 8 + (lane >> 2);
+        fb[u] = (lane & 3) * ROWD + tj * 8 + (lane >> 2);
+    }
+    double acc[TPW][2];
+#pragma unroll
+    for (int u = 0; u < TPW; ++u) acc[u][0] = acc[u][1] = 0.0;
+
+    constexpr int PER = (TC * V4 + THREADS - 1) / THREADS;
+    const long long ntiles = (ncols + TC - 1) / TC;
+    float4 pre[PER];
+    auto fetch = [&](long long tile) {
+        const long long c0 = tile * TC;
+        const long long left = ncols - c0;
+        const int nc = left < TC ? static_cast<int>(left) : TC;
+        float4* X4 = reinterpret_cast<float4*>(X + c0 * KP);
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            const int t = threadIdx.x + u * THREADS;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (t < TC * V4 && t / V4 < nc) {
+                const int q = t % V4;
+                v = X4[t];
+                if (normalize) {                     // padded coordinates hold 0 and d = 1 there
+                    v.x = __fdiv_rn(v.x, sD[q * 4 + 0]);
+                    v.y = __fdiv_rn(v.y, sD[q * 4 + 1]);
+                    v.z = __fdiv_rn(v.z, sD[q * 4 + 2]);
+                    v.w = __fdiv_rn(v.w, sD[q * 4 + 3]);
+                    X4[t] = v;
+                }
+            }
+            pre[u] = v;
+        }
+    };
+    long long tile = blockIdx.x;
+    if (tile < ntiles) fetch(tile);
+    for (; tile < ntiles; tile += gridDim.x) {
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            const int t = threadIdx.x + u * THREADS;
+            if (t < TC * V4) {
+                const int c = t / V4, q = t % V4;
+                double2* dst = reinterpret_cast<double2*>(&sX[c][q * 4]);
+                dst[0] = make_double2(static_cast<double>(pre[u].x), static_cast<double>(pre[u].y));
+                dst[1] = make_double2(static_cast<double>(pre[u].z), static_cast<double>(pre[u].w));
+            }
+        }
+        __syncthreads();
+        if (tile + gridDim.x < ntiles) fetch(tile + gridDim.x);      // overlaps with the MMA loop below
+        const double* slab = &sX[0][0];
+#pragma unroll 2
+        for (int c = 0; c < TC; c += 4, slab += 4 * ROWD) {
+#pragma unroll
+            for (int u = 0; u < TPW; ++u) {
+                const double a = slab[fa[u]];
+                const double b = slab[fb[u]];
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                             : "+d"(acc[u][0]), "+d"(acc[u][1]) : "d"(a), "d"(b));
+            }
+        }
+        __syncthreads();
+    }
+    // C fragment: lane l holds C[l/4][2*(l%4) + {0,1}] of tile (ti, tj) -> G(i, j) stored at [j*KP + i]
+    double* out = partials + static_cast<size_t>(blockIdx.x) * KP * KP;
+#pragma unroll
+    for (int u = 0; u < TPW; ++u) {
+        const int i = t_i[u] * 8 + (lane >> 2);
+        const int j = t_j[u] * 8 + 2 * (lane & 3);
+        out[j * KP + i] = acc[u][0];
+        out[(j + 1) * KP + i] = acc[u][1];
+    }
+}
+
 // X[c][:] /= d for the columns c in [0, lo) and [hi, ncols): peer-memory sharded runs normalise the blocks the
 // OTHER ranks solved (pushed un-normalised into this rank's replica by their half_step_kernel) with the same
 // IEEE division normalize_gram_kernel applies to the own block. Pure HBM streaming.

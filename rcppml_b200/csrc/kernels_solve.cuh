@@ -184,10 +184,40 @@ __device__ __forceinline__ void gather_column(const HalfStepParams& p, int p0, i
         nidx = __ldg(p.rowidx + p0 + gl);
         nval = __ldg(p.vals + p0 + gl);
     }
+#ifdef B200_PREFETCH
+    // Two-deep index pipeline: segment s+2 of (idx, val) is requested while segment s is consumed, so that the
+    // row addresses of segment s+1 are known one whole segment early and can be prefetched
+    // (B200_PREFETCH=1: first half of the next segment into L1; =2: the whole next segment into L2).
+    int nnidx = 0;
+    float nnval = 0.f;
+    if (p0 + LANES + gl < p1) {
+        nnidx = __ldg(p.rowidx + p0 + LANES + gl);
+        nnval = __ldg(p.vals + p0 + LANES + gl);
+    }
+#endif
     const float4* Fl = reinterpret_cast<const float4*>(p.F) + gl;
     for (int base = p0; base < p1; base += LANES) {
         const int ridx = nidx;
         const float rval = nval;
+#ifdef B200_PREFETCH
+        nidx = nnidx;
+        nval = nnval;
+        const int nb = base + 2 * LANES + gl;        // request segment s+2
+        nnidx = 0;
+        nnval = 0.f;
+        if (nb < p1) {
+            nnidx = __ldg(p.rowidx + nb);
+            nnval = __ldg(p.vals + nb);
+        }
+        if (base + LANES + gl < p1 && (B200_PREFETCH == 2 || gl < LANES / 2)) {     // rows of segment s+1
+            const char* rowp = reinterpret_cast<const char*>(p.F) + static_cast<size_t>(nidx) * (KP * 4);
+#pragma unroll
+            for (int l = 0; l < KP * 4; l += 128) {
+                if (B200_PREFETCH == 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(rowp + l));
+                else asm volatile("prefetch.global.L1 [%0];" ::"l"(rowp + l));
+            }
+        }
+#else
         const int nb = base + LANES + gl;            // prefetch the next idx/val segment
         nidx = 0;
         nval = 0.f;
@@ -195,6 +225,7 @@ __device__ __forceinline__ void gather_column(const HalfStepParams& p, int p0, i
             nidx = __ldg(p.rowidx + nb);
             nval = __ldg(p.vals + nb);
         }
+#endif
         const int cnt = p1 - base;
         if (cnt >= LANES) {                          // full batch: no predication at all
 #pragma unroll
