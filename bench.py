@@ -251,6 +251,68 @@ def run_e2e(args, eng, steps):
                     "entry point is cached per process, so the timed call reuses the warm-up call's device buffers"}
 
 
+def run_e2e_sharded(args, eng, dist, steps, rank, world):
+    """N > 1: the same fit through the public sharded engine API from pinned HOST buffers on every rank — H2D of
+    this rank's column block and row block of A, device transpose, H2D of the initial factors, `steps` iterations,
+    D2H of the factors. Wall clock between barriers, max over ranks (the reference ABI has no multi-GPU entry)."""
+    import numpy as np
+    import scipy.sparse as sp
+    import torch
+    import rcppml_b200 as rb
+
+    m, n, k = args.m, eng.n, args.k
+    cp, ci, cx = eng.get_matrix()                         # A[:, J_g]  (CSC, global row ids)
+    tp, ti, tx = eng.get_matrix_t()                       # (A[I_g, :])^T as CSC over the block's rows
+    RB = sp.csc_matrix((tx, ti, tp), shape=(n, eng.m_loc)).T.tocsc()     # -> A[I_g, :] (n columns, local row ids)
+    RB.sort_indices()
+    W0, H0, _ = eng.get_factors()
+    keep = []
+
+    def pinned(a, dtype):
+        t = torch.empty(a.shape, dtype=dtype, pin_memory=True)
+        out = t.numpy()
+        out[...] = a
+        keep.append(t)
+        return out
+    cb = (pinned(cp, torch.int32), pinned(ci, torch.int32), pinned(cx, torch.float32))
+    rbk = (pinned(RB.indptr.astype(np.int32), torch.int32), pinned(RB.indices.astype(np.int32), torch.int32),
+           pinned(RB.data.astype(np.float32), torch.float32))
+    W0p, H0p = pinned(W0, torch.float32), pinned(H0, torch.float32)
+    cfg = rb.make_config(k, max_iter=steps, tol=0.0, solver_mode=solver_mode(args), cd_maxit=100,
+                         L1=(args.L1, args.L1), L2=(args.L2, args.L2))
+
+    def one_call(iters):
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        eng.set_matrix_sharded(m, n, cb, rbk)
+        eng.set_factors(W0p, H0p)
+        c = rb.make_config(k, max_iter=iters, tol=0.0, solver_mode=solver_mode(args), cd_maxit=100,
+                           L1=(args.L1, args.L1), L2=(args.L2, args.L2))
+        res = eng.fit(c)
+        out = eng.get_factors()
+        torch.cuda.synchronize()
+        dist.barrier()
+        secs = time.perf_counter() - t0
+        assert res.status == 0 and res.iterations == iters, res
+        return secs, out
+    warm_secs, _ = one_call(1)
+    secs, _ = one_call(steps)
+    t = torch.tensor([secs], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    secs = float(t.item())
+    h2d = sum(a.nbytes for a in cb) + sum(a.nbytes for a in rbk) + W0p.nbytes + H0p.nbytes
+    d2h = W0p.nbytes + H0p.nbytes + 4 * k
+    b = torch.tensor([h2d, d2h], dtype=torch.float64, device="cuda")
+    dist.all_reduce(b)
+    return {"value": eng.nnz_global * steps / secs, "unit": "nnz/s", "h2d_bytes_per_step": int(b[0].item()) // steps,
+            "d2h_bytes_per_step": int(b[1].item()) // steps, "seconds_total": secs, "warmup_call_seconds": warm_secs,
+            "iters_per_sec": steps / secs,
+            "note": f"sharded engine API on {world} ranks from pinned host buffers: H2D of each rank's column + row "
+                    f"block (fp32) and of the initial factors, device transpose, {steps} iterations, D2H of the "
+                    "factors on every rank; wall clock between barriers, max over ranks; bytes summed over ranks / steps"}
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
@@ -371,6 +433,9 @@ def main():
     if world == 1 and not args.no_e2e:
         eng.init_factors(k, SEED_INIT, 0)
         line["e2e"] = run_e2e(args, eng, args.steps)
+    elif world > 1 and not args.no_e2e:
+        eng.init_factors(k, SEED_INIT, 0)
+        line["e2e"] = run_e2e_sharded(args, eng, dist, args.steps, rank, world)
     else:
         line["e2e"] = None
     eng.close()

@@ -170,6 +170,9 @@ Engine::Engine(int dev) : device(dev) {
     B200_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
     num_sms = prop.multiProcessorCount;
     B200_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    B200_CUDA_CHECK(cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking));
+    B200_CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    B200_CUDA_CHECK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
     B200_CUDA_CHECK(cudaEventCreate(&ev_loop_begin));
     B200_CUDA_CHECK(cudaEventCreate(&ev_loop_end));
     state.ensure(1);
@@ -185,6 +188,10 @@ Engine::~Engine() {
     cudaStreamSynchronize(stream);
     for (auto& sec : prof_events)
         for (auto& pr : sec) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    cudaStreamSynchronize(side_stream);
+    cudaEventDestroy(ev_fork);
+    cudaEventDestroy(ev_join);
+    cudaStreamDestroy(side_stream);
     cudaEventDestroy(ev_loop_begin);
     cudaEventDestroy(ev_loop_end);
     if (h_state) cudaFreeHost(h_state);
@@ -216,6 +223,7 @@ void Engine::set_dims(int m_, int n_) {
     n_pad = ((n + world - 1) / world) * world;
     matrix_ready = false;
     factors_ready = false;
+    npanels[0] = npanels[1] = 1;
 }
 
 void Engine::finish_matrix() {
@@ -517,8 +525,9 @@ template void Engine::get_factors_host<float>(float*, float*, float*);
 template void Engine::get_factors_host<double>(double*, double*, double*);
 
 // ---- profiling sections -----------------------------------------------------------------------
-void Engine::sec_begin(int sec) {
+void Engine::sec_begin(int sec, cudaStream_t on) {
     if (!profiling) return;
+    if (!on) on = stream;
     auto& pool = prof_events[sec];
     if (prof_used[sec] == static_cast<int>(pool.size())) {
         cudaEvent_t a, b;
@@ -526,11 +535,12 @@ void Engine::sec_begin(int sec) {
         B200_CUDA_CHECK(cudaEventCreate(&b));
         pool.emplace_back(a, b);
     }
-    B200_CUDA_CHECK(cudaEventRecord(pool[prof_used[sec]].first, stream));
+    B200_CUDA_CHECK(cudaEventRecord(pool[prof_used[sec]].first, on));
 }
-void Engine::sec_end(int sec) {
+void Engine::sec_end(int sec, cudaStream_t on) {
     if (!profiling) return;
-    B200_CUDA_CHECK(cudaEventRecord(prof_events[sec][prof_used[sec]].second, stream));
+    if (!on) on = stream;
+    B200_CUDA_CHECK(cudaEventRecord(prof_events[sec][prof_used[sec]].second, on));
     ++prof_used[sec];
 }
 void Engine::collect_profile() {
@@ -558,12 +568,25 @@ void Engine::normalize_cfg(const rcppml_b200_config& c) {
 
 // Peer-memory sharding: the other ranks' half_step_kernel pushed their solved (un-normalised) columns into this
 // replica; divide them by d here (same IEEE division as the owner applies to its block).
+// Runs on the side stream, forked after `d` is final and joined before the next solve kernel gathers from X:
+// it overlaps with the Gram of the own block, the small all-reduces and the solver set-up on the main stream
+// (those touch only this rank's block of X and k x k data).
 void Engine::normalize_peer_blocks(float* X, long long ncols, long long lo, long long hi, bool normalize) {
     if (!normalize || ncols == hi - lo) return;
-    sec_begin(RCPPML_B200_SEC_COMM);
-    scale_columns_kernel<<<num_sms * 8, 256, 0, stream>>>(X, ncols, KP, d.ptr, lo, hi, &state.ptr->stop);
+    B200_CUDA_CHECK(cudaEventRecord(ev_fork, stream));
+    B200_CUDA_CHECK(cudaStreamWaitEvent(side_stream, ev_fork, 0));
+    sec_begin(RCPPML_B200_SEC_COMM, side_stream);
+    scale_columns_kernel<<<num_sms * 8, 256, 0, side_stream>>>(X, ncols, KP, d.ptr, lo, hi, &state.ptr->stop);
     launches[RCPPML_B200_SEC_COMM] += 1;
-    sec_end(RCPPML_B200_SEC_COMM);
+    sec_end(RCPPML_B200_SEC_COMM, side_stream);
+    B200_CUDA_CHECK(cudaEventRecord(ev_join, side_stream));
+    side_pending = true;
+}
+
+void Engine::join_side_stream() {
+    if (!side_pending) return;
+    B200_CUDA_CHECK(cudaStreamWaitEvent(stream, ev_join, 0));
+    side_pending = false;
 }
 
 void Engine::gram(float* X, long long ncols, bool normalize, float* G_out, int sec, bool reduce_over_ranks) {
@@ -654,17 +677,72 @@ HalfStepParams Engine::solve_params(int which, bool warm) const {
     return p;
 }
 
+// Row panels: when the factor a half-step gathers from is larger than what stays resident in the 126 MB L2
+// (C4: W_T is 256 MB; C5: both factors), nearly every round of row loads pays one DRAM miss. The rows of a
+// column are sorted, so the entries that fall in a panel of rows are a contiguous run: the half-step runs as P
+// launches, pass q touching only panel q of the factor (L2-resident after first touch) and carrying the running
+// right-hand sides in `carry`. RCPPML_B200_PANEL_MB sets the panel size (0 disables).
+void Engine::build_panels() {
+    // Measured on B200 (profiles/r01l_*, r01m_*): C5 (k = 128, factors 2.56 GB / 256 MB) 289.8 -> 147.8 ms per
+    // iteration with 40 MB panels; C4's H half-step (k = 64, W_T 256 MB, 72 % L2 hits) already runs at the L2
+    // throughput cap (14 TB/s) and gains nothing (1.718 vs 1.732 ms). Default rule: panels when the factor is
+    // > 4 x L2, or > 60 MB with 512-byte rows; an explicit RCPPML_B200_PANEL_MB overrides the rule.
+    double panel_mb = 40.0;
+    bool explicit_mb = false;
+    if (const char* env = std::getenv("RCPPML_B200_PANEL_MB")) { panel_mb = std::atof(env); explicit_mb = true; }
+    for (int which = 0; which < 2; ++which) {
+        const bool h = (which == 0);
+        const long long frows = h ? m : n;                                  // rows of the gathered factor
+        const long long ncols = h ? n_loc : m_loc;
+        const double fbytes = static_cast<double>(frows) * KP * sizeof(float);
+        int P = 1;
+        const bool wanted = explicit_mb || fbytes > 4.0 * 126.0 * 1048576.0 || KP >= 128;
+        if (wanted && panel_mb > 0.0 && fbytes > 1.5 * panel_mb * 1048576.0) P = static_cast<int>(std::ceil(fbytes / (panel_mb * 1048576.0)));
+        P = std::min(P, 64);
+        if (ncols <= 0 || (h ? nnz : nnz_w) == 0) P = 1;
+        npanels[which] = P;
+        if (P == 1) continue;
+        const int rows_per_panel = static_cast<int>((frows + P - 1) / P);
+        panel_bounds[which].ensure(static_cast<size_t>(P + 1) * ncols);
+        const long long total = static_cast<long long>(P + 1) * ncols;
+        panel_bounds_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+            h ? Ap.ptr : Atp.ptr, h ? Ai.ptr : Ati.ptr, static_cast<int>(ncols), P, rows_per_panel, panel_bounds[which].ptr);
+        B200_CUDA_CHECK(cudaGetLastError());
+        carry.ensure(static_cast<size_t>(std::max(n_loc, m_loc)) * KP);
+    }
+}
+
 void Engine::solve(int which, bool warm, int sec) {
     HalfStepParams p = solve_params(which, warm);
     const int solver = cfg.solver_mode == 0 ? SOLVER_CD : SOLVER_CHOL;
-    const int geom = geometry_for(which == 0 ? nnz : nnz_w, p.ncols);
+    const long long cnt = which == 0 ? nnz : nnz_w;
+    const int P = npanels[which];
+    const int geom = geometry_for(cnt, p.ncols);
     int grid = 0;
     launch_half_step(geom, solver, BSRC_GATHER, OUT_SOLVE, p, num_sms, stream, &grid);
     last_solve_grid = grid;
     sec_begin(sec);
-    B200_CUDA_CHECK(cudaMemsetAsync(p.work_counter, 0, sizeof(int), stream));
-    launch_half_step(geom, solver, BSRC_GATHER, OUT_SOLVE, p, num_sms, stream);
-    launches[sec] += 1;
+    if (P > 1) {
+        // passes 0..P-2 only gather (their segments are short: use the short-column geometry); the last pass
+        // gathers its segment on top of the carried sums and solves
+        const int geom_pass = geometry_for(cnt / P, p.ncols);
+        HalfStepParams q = p;
+        q.carry = carry.ptr;
+        q.cols_per_fetch = pick_cols_per_fetch(cnt / P, p.ncols, num_sms);
+        for (int pass = 0; pass < P; ++pass) {
+            q.seg_begin = panel_bounds[which].ptr + static_cast<size_t>(pass) * p.ncols;
+            q.seg_end = panel_bounds[which].ptr + static_cast<size_t>(pass + 1) * p.ncols;
+            q.carry_load = pass > 0 ? 1 : 0;
+            B200_CUDA_CHECK(cudaMemsetAsync(q.work_counter, 0, sizeof(int), stream));
+            if (pass + 1 < P) launch_half_step(geom_pass, SOLVER_CD, BSRC_GATHER, OUT_RHS, q, num_sms, stream);
+            else launch_half_step(geom, solver, BSRC_GATHER, OUT_SOLVE, q, num_sms, stream);
+            launches[sec] += 1;
+        }
+    } else {
+        B200_CUDA_CHECK(cudaMemsetAsync(p.work_counter, 0, sizeof(int), stream));
+        launch_half_step(geom, solver, BSRC_GATHER, OUT_SOLVE, p, num_sms, stream);
+        launches[sec] += 1;
+    }
     sec_end(sec);
 }
 
@@ -701,24 +779,26 @@ void Engine::enqueue_iteration() {
     // ---- H update (fit_cpu.hpp:488-645)
     if (iters_enqueued == 0) gram(Wblk, m_loc, false, G_w.ptr, RCPPML_B200_SEC_GRAM_H, sharded);   // :491
     prepare_solver(G_w.ptr, cfg.L2_H, RCPPML_B200_SEC_GRAM_H);              // :506
+    join_side_stream();                                                     // W_T fully normalised (peer blocks)
     solve(0, warm, RCPPML_B200_SEC_SOLVE_H);                                // :516-535 (+ :636 upper bound)
     scale_finalize(RCPPML_B200_SEC_SCALE_H, sharded);                       // :644 (p2p: also the barrier)
     // ---- W update (fit_cpu.hpp:713-893)
+    if (p2p) normalize_peer_blocks(H.ptr, n, col_begin, col_begin + n_loc, normalize);   // side stream
     gram(Hblk, n_loc, normalize, G_h.ptr, RCPPML_B200_SEC_GRAM_W, sharded); // :644 (normalise) + :715
-    if (p2p) normalize_peer_blocks(H.ptr, n, col_begin, col_begin + n_loc, normalize);
-    else if (sharded) allgather_rows(H.ptr, n_pad / world, RCPPML_B200_SEC_COMM);
+    if (sharded && !p2p) allgather_rows(H.ptr, n_pad / world, RCPPML_B200_SEC_COMM);
     prepare_solver(G_h.ptr, cfg.L2_W, RCPPML_B200_SEC_GRAM_W);              // :738
+    join_side_stream();
     solve(1, warm, RCPPML_B200_SEC_SOLVE_W);                                // :748-767 (+ :884)
     scale_finalize(RCPPML_B200_SEC_SCALE_W, sharded);                       // :892
     // ---- loss (fit_cpu.hpp:1729-1809): Gram of the new W_T doubles as next iteration's gram_H
+    if (p2p) normalize_peer_blocks(W_T.ptr, m, row_begin, row_begin + m_loc, normalize);   // side stream
     sec_begin(RCPPML_B200_SEC_LOSS);
     const bool was = profiling; profiling = false;                         // nested section: account under LOSS
     gram(Wblk, m_loc, normalize, G_w.ptr, RCPPML_B200_SEC_LOSS, sharded);   // :892 (normalise) + :1735
     profiling = was;
     loss(RCPPML_B200_SEC_LOSS);
     sec_end(RCPPML_B200_SEC_LOSS);
-    if (p2p) normalize_peer_blocks(W_T.ptr, m, row_begin, row_begin + m_loc, normalize);
-    else if (sharded) allgather_rows(W_T.ptr, m_pad / world, RCPPML_B200_SEC_COMM);
+    if (sharded && !p2p) allgather_rows(W_T.ptr, m_pad / world, RCPPML_B200_SEC_COMM);
     ++iters_enqueued;
 }
 
@@ -921,6 +1001,7 @@ void Engine::begin_fit(const rcppml_b200_config& c) {
     normalize_cfg(c);
     B200_REQUIRE(world == 1 || comm_ready(), "begin_fit: communicator not initialised");
     iters_enqueued = 0;
+    build_panels();
     loss_hist.ensure(static_cast<size_t>(std::max(cfg.max_iter, 1024)));
     DevState s0{};
     s0.prev_loss = 3.402823466e+38f;                                        // fit_cpu.hpp:281
@@ -930,6 +1011,12 @@ void Engine::begin_fit(const rcppml_b200_config& c) {
     B200_CUDA_CHECK(cudaMemcpyAsync(d.ptr, ones.data(), KP * sizeof(float), cudaMemcpyHostToDevice, stream));
     B200_CUDA_CHECK(cudaStreamSynchronize(stream));
     for (int s = 0; s < RCPPML_B200_NUM_SECTIONS; ++s) { prof_ms[s] = 0.0; launches[s] = 0; prof_used[s] = 0; }
+    // Peer-memory loop: no rank may push solved columns into a replica whose owner is still initialising it.
+    // One exchange (a k-independent barrier on the stream) orders every rank's set-up before any first solve.
+    if (world > 1 && peers_ready) {
+        red_small.ensure(KP + 1);
+        allreduce_f64(red_small.ptr, 1);
+    }
     fit_active = true;
     loop_ms = 0.0;
 }
@@ -949,6 +1036,7 @@ void Engine::iterate(int n_iters) {
             if (h_state->stop) break;
         }
     }
+    join_side_stream();
     B200_CUDA_CHECK(cudaEventRecord(ev_loop_end, stream));
     B200_CUDA_CHECK(cudaGetLastError());
     B200_CUDA_CHECK(cudaStreamSynchronize(stream));
@@ -964,6 +1052,7 @@ void Engine::half_step_only(const rcppml_b200_config& c, int which, bool warm, b
     B200_REQUIRE(matrix_ready && factors_ready, "half_step: matrix and factors must be set first");
     B200_REQUIRE(world == 1, "half_step: single-GPU diagnostic entry");
     normalize_cfg(c);
+    build_panels();
     DevState s0{};
     s0.prev_loss = 3.402823466e+38f;
     B200_CUDA_CHECK(cudaMemcpyAsync(state.ptr, &s0, sizeof(DevState), cudaMemcpyHostToDevice, stream));

@@ -98,6 +98,11 @@ public:
     int const_slot = 0;
     DeviceBuffer<double> gram_partials, solve_partials;   // per-CTA partials (fixed-order reductions)
     DeviceBuffer<double> red_gram, red_small;             // reduced sums: k×k Gram | k row sums + cross term
+    // row-panel passes for half-steps whose gathered factor exceeds L2 (build_panels, kernels_solve.cuh)
+    DeviceBuffer<int> panel_bounds[2];                    // [which][(P+1) x ncols]
+    int npanels[2] = {1, 1};
+    DeviceBuffer<float> carry;                            // [max(n_loc, m_loc)][KP] running right-hand sides
+    void build_panels();
     DeviceBuffer<int> counters;
     DeviceBuffer<unsigned long long> sweep_counter;
     DeviceBuffer<DevState> state;
@@ -155,8 +160,12 @@ private:
     void allgather_rows(float* buf, int rows_per_rank, int sec);
     void alloc_factors(int k);
     void normalize_cfg(const rcppml_b200_config& c);
-    void sec_begin(int sec);
-    void sec_end(int sec);
+    void sec_begin(int sec, cudaStream_t on = nullptr);
+    void sec_end(int sec, cudaStream_t on = nullptr);
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool side_pending = false;
+    void join_side_stream();
     void collect_profile();
     void gram(float* X, long long ncols, bool normalize, float* G_out, int sec, bool reduce_over_ranks = false);
     void normalize_peer_blocks(float* X, long long ncols, long long lo, long long hi, bool normalize);

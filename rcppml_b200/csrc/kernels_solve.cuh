@@ -62,6 +62,15 @@ struct HalfStepParams {
     float* peerX[7];
     int npeers;
     int cslot;                         // c_solver slot holding this launch's diagonal blocks / reciprocals
+    // Row-panel passes (engine.cu build_panels): when the gathered factor is larger than L2, a half-step runs as
+    // P launches; pass q gathers only the entries of every column whose rows fall in panel q (a contiguous run,
+    // rows are sorted), so the rows it touches stay L2-resident. The running right-hand side is carried between
+    // passes in `carry` ([ncols][KP], local column index) — the additions happen in exactly the CSC order of the
+    // single-pass kernel, so the result is bit-identical.
+    const int* __restrict__ seg_begin; // [ncols] first entry of this pass per column (nullptr: colptr[j])
+    const int* __restrict__ seg_end;   // [ncols] one past the last entry of this pass (nullptr: colptr[j+1])
+    float* __restrict__ carry;
+    int carry_load;                    // start from carry[j] instead of 0 (every pass but the first)
 };
 
 // Warp-uniform solver operands (the 4x4 diagonal blocks and the pivot reciprocals) live in CONSTANT memory:
@@ -173,10 +182,7 @@ __device__ __forceinline__ void gather_column(const HalfStepParams& p, int p0, i
 #endif
     constexpr int UNW = B200_GATHER_UN;                                          // 128-bit loads in flight per lane
     constexpr int UN = (LANES * NV <= UNW) ? LANES : (UNW / NV > 0 ? UNW / NV : 1);
-#pragma unroll
-    for (int nv = 0; nv < NV; ++nv)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) b[nv][e] = 0.f;
+    // b is initialised by the caller (zeros, or the running sums carried over from the previous row panel)
 
     int nidx = 0;
     float nval = 0.f;
@@ -526,8 +532,21 @@ __global__ void __launch_bounds__(256, (NV >= 4) ? 2 : B200_SOLVE_MIN_CTAS) half
 
             float b[NV][4];
             if (BSRC == BSRC_GATHER) {
-                const int p0 = __ldg(p.colptr + jl);    // the sparse operand is local to this rank
-                const int p1 = __ldg(p.colptr + jl + 1);
+                const int p0 = p.seg_begin ? __ldg(p.seg_begin + jl) : __ldg(p.colptr + jl);    // local to this rank
+                const int p1 = p.seg_end ? __ldg(p.seg_end + jl) : __ldg(p.colptr + jl + 1);
+                if (p.carry_load) {
+#pragma unroll
+                    for (int nv = 0; nv < NV; ++nv) {
+                        const float4 c = __ldcg(reinterpret_cast<const float4*>(p.carry + static_cast<size_t>(jl) * KP +
+                                                                                 (nv * LANES + gl) * 4));
+                        b[nv][0] = c.x; b[nv][1] = c.y; b[nv][2] = c.z; b[nv][3] = c.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int nv = 0; nv < NV; ++nv)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) b[nv][e] = 0.f;
+                }
                 gather_column<LANES, NV>(p, p0, p1, gl, gmask, b);
             } else {
                 const int jb = p.b_local_index ? jl : j;
@@ -549,11 +568,12 @@ __global__ void __launch_bounds__(256, (NV >= 4) ? 2 : B200_SOLVE_MIN_CTAS) half
                 }
             }
 
-            if (OUT == OUT_RHS) {
+            if (OUT == OUT_RHS) {                   // row-panel pass (carry) or raw right-hand side (B)
+                float* dst = p.carry ? p.carry + static_cast<size_t>(jl) * KP : p.B + static_cast<size_t>(j) * KP;
 #pragma unroll
                 for (int nv = 0; nv < NV; ++nv)
-                    *reinterpret_cast<float4*>(p.B + static_cast<size_t>(j) * KP + (nv * LANES + gl) * 4) =
-                        make_float4(b[nv][0], b[nv][1], b[nv][2], b[nv][3]);
+                    __stcg(reinterpret_cast<float4*>(dst + (nv * LANES + gl) * 4),
+                           make_float4(b[nv][0], b[nv][1], b[nv][2], b[nv][3]));
                 continue;
             }
 

@@ -119,4 +119,22 @@ static __global__ void __launch_bounds__(256) synth_column_kernel(int m, int n_l
     }
 }
 
+// Row-panel boundaries inside every column: out[q*ncols + j] = first entry of column j whose row is
+// >= q*rows_per_panel (q = 0..P), by binary search over the sorted row indices. out[0][j] = colptr[j],
+// out[P][j] = colptr[j+1]. One thread per (q, j).
+static __global__ void panel_bounds_kernel(const int* __restrict__ colptr, const int* __restrict__ rowidx, int ncols,
+                                           int npanels, int rows_per_panel, int* __restrict__ out) {
+    const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= static_cast<long long>(npanels + 1) * ncols) return;
+    const int q = static_cast<int>(t / ncols), j = static_cast<int>(t % ncols);
+    int lo = colptr[j], hi = colptr[j + 1];
+    if (q == npanels) { out[t] = hi; return; }
+    const long long bound = static_cast<long long>(q) * rows_per_panel;
+    while (lo < hi) {                                  // first position with rowidx >= bound
+        const int mid = lo + ((hi - lo) >> 1);
+        if (rowidx[mid] < bound) lo = mid + 1; else hi = mid;
+    }
+    out[t] = lo;
+}
+
 }  // namespace b200

@@ -325,6 +325,33 @@ def test_reference_abi_zerocopy_and_cached_engine(oracle):
     assert np.array_equal(again.W_T, first.W_T) and np.array_equal(again.H, first.H)
 
 
+@pytest.mark.parametrize("k,solver", [(6, 0), (20, 1), (64, 1), (64, 0), (128, 1)])
+def test_row_panel_passes_are_bit_identical(eng, oracle, k, solver, monkeypatch):
+    """Row-panel passes (engine.cu build_panels): the half-step split into P launches over row panels of the
+    gathered factor must reproduce the single-launch fit bit for bit (same additions in the same CSC order),
+    including empty segments, ragged columns and panels that split a column many times."""
+    import rcppml_b200 as rb
+    m, n = 1500, 700
+    A = random_csc(m, n, 0.05, 300 + k, ragged=True)
+    eng.set_matrix(m, n, A.indptr, A.indices, A.data)
+    cfg = rb.make_config(k, max_iter=4, tol=0.0, solver_mode=solver, L1=(0.01, 0.0), L2=(0.0, 0.02))
+    outs = []
+    for panel_mb in ("0", "0.02", "0.004"):
+        monkeypatch.setenv("RCPPML_B200_PANEL_MB", panel_mb)
+        eng.init_factors(k, 42)
+        res = eng.fit(cfg)
+        assert res.status == 0 and res.iterations == 4
+        outs.append(eng.get_factors() + (eng.loss_history(4),))
+    monkeypatch.delenv("RCPPML_B200_PANEL_MB")
+    for other in outs[1:]:
+        for a, b in zip(outs[0], other):
+            assert np.array_equal(a, b)
+    W0, H0 = oracle.initialize_factors(k, m, n, 42)
+    ref = oracle.nmf_fit(A.indptr, A.indices, A.data, m, n, k, W0, H0, max_iter=4, tol=0.0, solver_mode=solver,
+                         L1=(0.01, 0.0), L2=(0.0, 0.02))
+    assert rel_err(outs[1][0], ref.W_T) <= RTOL and rel_err(outs[1][1], ref.H) <= RTOL
+
+
 def test_large_synthetic_properties(eng):
     """Full-width rows at reduced column count: size-independent properties (non-negativity,
     unit L1 row norms, monotone loss, determinism run to run)."""
