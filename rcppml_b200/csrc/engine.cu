@@ -57,14 +57,58 @@ static void launch_half_step_l(int lanes, const HalfStepParams& p, int num_sms, 
 // grid_out != nullptr: only report the grid this configuration would use (for buffer sizing).
 void launch_half_step(int lanes, int solver, int bsrc, int out, const HalfStepParams& p, int num_sms,
                       cudaStream_t s, int* grid_out) {
+    B200_REQUIRE(bsrc == BSRC_GATHER, "right-hand sides are always gathered in-kernel");
     if (out == OUT_RHS) {
         launch_half_step_l<SOLVER_CD, BSRC_GATHER, OUT_RHS>(lanes, p, num_sms, s, grid_out);
-    } else if (bsrc == BSRC_GATHER) {
+    } else {
         if (solver == SOLVER_CD) launch_half_step_l<SOLVER_CD, BSRC_GATHER, OUT_SOLVE>(lanes, p, num_sms, s, grid_out);
         else launch_half_step_l<SOLVER_CHOL, BSRC_GATHER, OUT_SOLVE>(lanes, p, num_sms, s, grid_out);
-    } else {
-        if (solver == SOLVER_CD) launch_half_step_l<SOLVER_CD, BSRC_LOAD, OUT_SOLVE>(lanes, p, num_sms, s, grid_out);
-        else launch_half_step_l<SOLVER_CHOL, BSRC_LOAD, OUT_SOLVE>(lanes, p, num_sms, s, grid_out);
+    }
+}
+
+// The coordinate-descent kernel (kernels_cd.cuh): narrow lane groups, blocked pivots.
+template <int LANES, int NV>
+static void launch_cd_t(const HalfStepParams& p, int num_sms, cudaStream_t stream, int* grid_out) {
+    auto kern = cd_half_step_kernel<LANES, NV>;
+    const int wc = p.want_cross ? 1 : 0;
+    const size_t smem = cd_half_step_smem_bytes<LANES, NV>(wc != 0);
+    static thread_local int cached_occ[2] = {-1, -1};
+    if (cached_occ[wc] < 0) {
+        B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(cd_half_step_smem_bytes<LANES, NV>(true))));
+        int occ = 0;
+        B200_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));
+        B200_REQUIRE(occ > 0, "cd_half_step_kernel does not fit on an SM");
+        cached_occ[wc] = occ;
+    }
+    const int grid = num_sms * cached_occ[wc];
+    if (grid_out) { *grid_out = grid; return; }
+    kern<<<grid, 256, smem, stream>>>(p);
+}
+
+// `geom` encodes (LANES, NV) as LANES + 100*(NV-1), LANES*4*NV == KP.
+void launch_cd_half_step(int geom, const HalfStepParams& p, int num_sms, cudaStream_t s, int* grid_out) {
+    switch (geom) {
+        case 102: launch_cd_t<2, 2>(p, num_sms, s, grid_out); break;     // KP = 16
+        case 4: launch_cd_t<4, 1>(p, num_sms, s, grid_out); break;
+        case 302: launch_cd_t<2, 4>(p, num_sms, s, grid_out); break;     // KP = 32
+        case 104: launch_cd_t<4, 2>(p, num_sms, s, grid_out); break;
+        case 702: launch_cd_t<2, 8>(p, num_sms, s, grid_out); break;     // KP = 64
+        case 304: launch_cd_t<4, 4>(p, num_sms, s, grid_out); break;
+        case 108: launch_cd_t<8, 2>(p, num_sms, s, grid_out); break;
+        case 704: launch_cd_t<4, 8>(p, num_sms, s, grid_out); break;     // KP = 128
+        case 308: launch_cd_t<8, 4>(p, num_sms, s, grid_out); break;
+        case 116: launch_cd_t<16, 2>(p, num_sms, s, grid_out); break;
+        default: throw std::runtime_error("unsupported coordinate-descent lane-group geometry");
+    }
+}
+
+static bool cd_geometry_matches(int geom, int KP) {
+    const int lanes = geom % 100, nv = geom / 100 + 1;
+    switch (geom) {
+        case 102: case 4: case 302: case 104: case 702: case 304: case 108: case 704: case 308: case 116:
+            return lanes * 4 * nv == KP;
+        default: return false;
     }
 }
 
@@ -429,6 +473,15 @@ void Engine::alloc_factors(int k_) {
     if (const char* env = std::getenv("RCPPML_B200_NV")) nv_override = std::atoi(env);   // tuning knobs (1, 2 or 4)
     nv_short_override = 0;
     if (const char* env = std::getenv("RCPPML_B200_NV_SHORT")) nv_short_override = std::atoi(env);
+    // Coordinate descent runs in its own kernel with narrow lane groups (kernels_cd.cuh). RCPPML_B200_CD_GEOM
+    // selects another geometry (LANES + 100*(NV-1)); RCPPML_B200_CD_KERNEL=1 falls back to half_step_kernel<CD>.
+    cd_geom = (KP == 16) ? 102 : (KP == 32) ? 302 : (KP == 64) ? 702 : 308;
+    if (const char* env = std::getenv("RCPPML_B200_CD_GEOM")) {
+        const int g = std::atoi(env);
+        B200_REQUIRE(cd_geometry_matches(g, KP), "RCPPML_B200_CD_GEOM does not match the padded rank");
+        cd_geom = g;
+    }
+    if (const char* env = std::getenv("RCPPML_B200_CD_KERNEL")) { if (std::atoi(env) == 1) cd_geom = 0; }
     if (peers_ready && (static_cast<size_t>(m_pad) * KP > W_T.count || static_cast<size_t>(n_pad) * KP > H.count ||
                         KP * KP > xchg_ne_max))
         comm_ipc_close();                                 // the mapped buffers are about to move: back to NCCL
@@ -452,6 +505,14 @@ void Engine::alloc_factors(int k_) {
         for (int geom : {LANES, (KP == 64 || KP == 128) ? 100 + KP / 8 : LANES, (KP == 64 || KP == 128) ? 300 + KP / 16 : LANES}) {
             int g = 0;
             launch_half_step(geom, solver, BSRC_GATHER, OUT_SOLVE, dummy, num_sms, stream, &g);
+            gmax = std::max(gmax, g);
+        }
+    }
+    if (cd_geom) {
+        for (int wc = 0; wc < 2; ++wc) {
+            int g = 0;
+            dummy.want_cross = wc;
+            launch_cd_half_step(cd_geom, dummy, num_sms, stream, &g);
             gmax = std::max(gmax, g);
         }
     }
@@ -712,14 +773,20 @@ void Engine::build_panels() {
     }
 }
 
+void Engine::launch_solver(int geom, int solver, const HalfStepParams& p, int* grid_out) {
+    if (solver == SOLVER_CD && cd_geom) launch_cd_half_step(cd_geom, p, num_sms, stream, grid_out);
+    else launch_half_step(geom, solver, BSRC_GATHER, OUT_SOLVE, p, num_sms, stream, grid_out);
+}
+
 void Engine::solve(int which, bool warm, int sec) {
     HalfStepParams p = solve_params(which, warm);
     const int solver = cfg.solver_mode == 0 ? SOLVER_CD : SOLVER_CHOL;
     const long long cnt = which == 0 ? nnz : nnz_w;
     const int P = npanels[which];
     const int geom = geometry_for(cnt, p.ncols);
+    if (solver == SOLVER_CD && cd_geom) p.cols_per_fetch = 1;      // a CD column is thousands of instructions
     int grid = 0;
-    launch_half_step(geom, solver, BSRC_GATHER, OUT_SOLVE, p, num_sms, stream, &grid);
+    launch_solver(geom, solver, p, &grid);
     last_solve_grid = grid;
     sec_begin(sec);
     if (P > 1) {
@@ -728,19 +795,23 @@ void Engine::solve(int which, bool warm, int sec) {
         const int geom_pass = geometry_for(cnt / P, p.ncols);
         HalfStepParams q = p;
         q.carry = carry.ptr;
-        q.cols_per_fetch = pick_cols_per_fetch(cnt / P, p.ncols, num_sms);
         for (int pass = 0; pass < P; ++pass) {
             q.seg_begin = panel_bounds[which].ptr + static_cast<size_t>(pass) * p.ncols;
             q.seg_end = panel_bounds[which].ptr + static_cast<size_t>(pass + 1) * p.ncols;
             q.carry_load = pass > 0 ? 1 : 0;
             B200_CUDA_CHECK(cudaMemsetAsync(q.work_counter, 0, sizeof(int), stream));
-            if (pass + 1 < P) launch_half_step(geom_pass, SOLVER_CD, BSRC_GATHER, OUT_RHS, q, num_sms, stream);
-            else launch_half_step(geom, solver, BSRC_GATHER, OUT_SOLVE, q, num_sms, stream);
+            if (pass + 1 < P) {
+                q.cols_per_fetch = pick_cols_per_fetch(cnt / P, p.ncols, num_sms);
+                launch_half_step(geom_pass, SOLVER_CD, BSRC_GATHER, OUT_RHS, q, num_sms, stream);
+            } else {
+                q.cols_per_fetch = (solver == SOLVER_CD && cd_geom) ? 1 : pick_cols_per_fetch(cnt / P, p.ncols, num_sms);
+                launch_solver(geom, solver, q);
+            }
             launches[sec] += 1;
         }
     } else {
         B200_CUDA_CHECK(cudaMemsetAsync(p.work_counter, 0, sizeof(int), stream));
-        launch_half_step(geom, solver, BSRC_GATHER, OUT_SOLVE, p, num_sms, stream);
+        launch_solver(geom, solver, p);
         launches[sec] += 1;
     }
     sec_end(sec);

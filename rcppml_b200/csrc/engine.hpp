@@ -7,6 +7,7 @@
 #include "kernels_masked.cuh"
 #include "kernels_cv.cuh"
 #include "kernels_solve.cuh"
+#include "kernels_cd.cuh"
 #include "kernels_sparse.cuh"
 
 #include <array>
@@ -23,6 +24,7 @@ extern thread_local std::string g_last_error;
 // grid_out != nullptr: only report the persistent grid this instantiation uses (buffer sizing).
 void launch_half_step(int lanes, int solver, int bsrc, int out, const HalfStepParams& p, int num_sms,
                       cudaStream_t s, int* grid_out = nullptr);
+void launch_cd_half_step(int geom, const HalfStepParams& p, int num_sms, cudaStream_t s, int* grid_out = nullptr);
 
 class Engine {
 public:
@@ -93,6 +95,8 @@ public:
 
     int k = 0, KP = 0, LANES = 0, nv_override = 0, nv_short_override = 0;
     int geometry_for(long long nnz, long long ncols) const;
+    int cd_geom = 0;                        // lane-group geometry of cd_half_step_kernel (0: use half_step_kernel<CD>)
+    void launch_solver(int geom, int solver, const HalfStepParams& p, int* grid_out = nullptr);
     DeviceBuffer<float> W_T, H, d;
     DeviceBuffer<float> G_w, G_h, M1, M2, dblk;     // dblk: SolverConsts image (diagonal blocks, then reciprocals)
     int const_slot = 0;

@@ -352,6 +352,46 @@ def test_row_panel_passes_are_bit_identical(eng, oracle, k, solver, monkeypatch)
     assert rel_err(outs[1][0], ref.W_T) <= RTOL and rel_err(outs[1][1], ref.H) <= RTOL
 
 
+CD_GEOMS = {16: (102, 4), 32: (302, 104), 64: (702, 304, 108), 128: (704, 308, 116)}
+
+
+@pytest.mark.parametrize("k", [5, 16, 20, 32, 50, 64, 100, 128])
+def test_cd_kernel_geometries_are_bit_identical(eng, oracle, k, monkeypatch):
+    """The coordinate-descent kernel (kernels_cd.cuh: narrow lane groups, pivots blocked by 4, branch-free
+    steps, tolerance quotients split over lanes) must reproduce half_step_kernel<CD> bit for bit in every
+    lane-group geometry — factors, d, loss history AND the total number of CD sweeps — and match the oracle."""
+    import rcppml_b200 as rb
+    m, n = 1100, 600
+    A = random_csc(m, n, 0.05, 500 + k, ragged=True)
+    eng.set_matrix(m, n, A.indptr, A.indices, A.data)
+    kw = dict(solver_mode=0, L1=(0.01, 0.005), L2=(0.0, 0.01), cd_maxit=100)
+    iters = 5
+    cfg = rb.make_config(k, max_iter=iters, tol=0.0, **kw)
+    kp = 16 if k <= 16 else 32 if k <= 32 else 64 if k <= 64 else 128
+    outs = []
+    monkeypatch.setenv("RCPPML_B200_CD_KERNEL", "1")            # the original kernel
+    eng.init_factors(k, 42)
+    res = eng.fit(cfg)
+    assert res.status == 0 and res.iterations == iters
+    outs.append(eng.get_factors() + (eng.loss_history(iters), eng.cd_sweeps()))
+    monkeypatch.delenv("RCPPML_B200_CD_KERNEL")
+    for geom in CD_GEOMS[kp]:
+        monkeypatch.setenv("RCPPML_B200_CD_GEOM", str(geom))
+        eng.init_factors(k, 42)
+        res = eng.fit(cfg)
+        assert res.status == 0 and res.iterations == iters
+        outs.append(eng.get_factors() + (eng.loss_history(iters), eng.cd_sweeps()))
+    monkeypatch.delenv("RCPPML_B200_CD_GEOM")
+    for gi, other in enumerate(outs[1:]):
+        for a, b in zip(outs[0][:4], other[:4]):
+            assert np.array_equal(a, b), (k, CD_GEOMS[kp][gi])
+        assert outs[0][4] == other[4], (k, CD_GEOMS[kp][gi], outs[0][4], other[4])
+    W0, H0 = oracle.initialize_factors(k, m, n, 42)
+    ref = oracle.nmf_fit(A.indptr, A.indices, A.data, m, n, k, W0, H0, max_iter=iters, tol=0.0, **kw)
+    assert rel_err(outs[1][0], ref.W_T) <= RTOL and rel_err(outs[1][1], ref.H) <= RTOL
+    assert outs[1][4] == ref.cd_sweeps
+
+
 def test_large_synthetic_properties(eng):
     """Full-width rows at reduced column count: size-independent properties (non-negativity,
     unit L1 row norms, monotone loss, determinism run to run)."""
