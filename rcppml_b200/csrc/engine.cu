@@ -70,18 +70,16 @@ void launch_half_step(int lanes, int solver, int bsrc, int out, const HalfStepPa
 template <int LANES, int NV>
 static void launch_cd_t(const HalfStepParams& p, int num_sms, cudaStream_t stream, int* grid_out) {
     auto kern = cd_half_step_kernel<LANES, NV>;
-    const int wc = p.want_cross ? 1 : 0;
-    const size_t smem = cd_half_step_smem_bytes<LANES, NV>(wc != 0);
-    static thread_local int cached_occ[2] = {-1, -1};
-    if (cached_occ[wc] < 0) {
-        B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             static_cast<int>(cd_half_step_smem_bytes<LANES, NV>(true))));
+    const size_t smem = cd_half_step_smem_bytes<LANES, NV>();
+    static thread_local int cached_occ = -1;
+    if (cached_occ < 0) {
+        B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         int occ = 0;
         B200_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));
         B200_REQUIRE(occ > 0, "cd_half_step_kernel does not fit on an SM");
-        cached_occ[wc] = occ;
+        cached_occ = occ;
     }
-    const int grid = num_sms * cached_occ[wc];
+    const int grid = num_sms * cached_occ;
     if (grid_out) { *grid_out = grid; return; }
     kern<<<grid, 256, smem, stream>>>(p);
 }
@@ -89,9 +87,11 @@ static void launch_cd_t(const HalfStepParams& p, int num_sms, cudaStream_t strea
 // `geom` encodes (LANES, NV) as LANES + 100*(NV-1), LANES*4*NV == KP.
 void launch_cd_half_step(int geom, const HalfStepParams& p, int num_sms, cudaStream_t s, int* grid_out) {
     switch (geom) {
-        case 102: launch_cd_t<2, 2>(p, num_sms, s, grid_out); break;     // KP = 16
+        case 301: launch_cd_t<1, 4>(p, num_sms, s, grid_out); break;     // KP = 16
+        case 102: launch_cd_t<2, 2>(p, num_sms, s, grid_out); break;
         case 4: launch_cd_t<4, 1>(p, num_sms, s, grid_out); break;
-        case 302: launch_cd_t<2, 4>(p, num_sms, s, grid_out); break;     // KP = 32
+        case 701: launch_cd_t<1, 8>(p, num_sms, s, grid_out); break;     // KP = 32
+        case 302: launch_cd_t<2, 4>(p, num_sms, s, grid_out); break;
         case 104: launch_cd_t<4, 2>(p, num_sms, s, grid_out); break;
         case 702: launch_cd_t<2, 8>(p, num_sms, s, grid_out); break;     // KP = 64
         case 304: launch_cd_t<4, 4>(p, num_sms, s, grid_out); break;
@@ -106,7 +106,7 @@ void launch_cd_half_step(int geom, const HalfStepParams& p, int num_sms, cudaStr
 static bool cd_geometry_matches(int geom, int KP) {
     const int lanes = geom % 100, nv = geom / 100 + 1;
     switch (geom) {
-        case 102: case 4: case 302: case 104: case 702: case 304: case 108: case 704: case 308: case 116:
+        case 301: case 102: case 4: case 701: case 302: case 104: case 702: case 304: case 108: case 704: case 308: case 116:
             return lanes * 4 * nv == KP;
         default: return false;
     }
@@ -230,6 +230,7 @@ Engine::Engine(int dev) : device(dev) {
 Engine::~Engine() {
     cudaSetDevice(device);
     cudaStreamSynchronize(stream);
+    if (iter_graph) cudaGraphExecDestroy(iter_graph);
     for (auto& sec : prof_events)
         for (auto& pr : sec) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     cudaStreamSynchronize(side_stream);
@@ -260,6 +261,8 @@ static void block_of(int total, int world, int rank, int* begin, int* count) {
 
 void Engine::set_dims(int m_, int n_) {
     B200_REQUIRE(m_ > 0 && n_ > 0, "set_matrix: bad dimensions");
+    drop_iteration_graph();
+    fit_active = false;                                   // a fit in flight does not survive a new matrix
     m = m_; n = n_;
     block_of(n, world, rank, &col_begin, &n_loc);
     block_of(m, world, rank, &row_begin, &m_loc);
@@ -466,6 +469,8 @@ void Engine::set_matrix_synthetic_sharded(int m_, int n_, double density, uint64
 void Engine::alloc_factors(int k_) {
     B200_REQUIRE(matrix_ready, "set a matrix before the factors");
     B200_REQUIRE(k_ >= 1 && k_ <= kMaxKP, "rank must be in [1, 128]");
+    drop_iteration_graph();
+    fit_active = false;                                   // a fit in flight does not survive new factors
     k = k_;
     LANES = lanes_for_rank(k);
     KP = padded_rank(k);
@@ -475,13 +480,16 @@ void Engine::alloc_factors(int k_) {
     if (const char* env = std::getenv("RCPPML_B200_NV_SHORT")) nv_short_override = std::atoi(env);
     // Coordinate descent runs in its own kernel with narrow lane groups (kernels_cd.cuh). RCPPML_B200_CD_GEOM
     // selects another geometry (LANES + 100*(NV-1)); RCPPML_B200_CD_KERNEL=1 falls back to half_step_kernel<CD>.
-    cd_geom = (KP == 16) ? 102 : (KP == 32) ? 302 : (KP == 64) ? 702 : 308;
+    // Measured at C4 (profiles/r01p_cd_geometries.json): the narrowest group wins wherever the solve dominates
+    // (short columns: the W half-step); long columns (the H half-step, 1000 non-zeros) gather better one step wider.
+    cd_geom = (KP == 16) ? 301 : (KP == 32) ? 701 : (KP == 64) ? 702 : 704;
+    cd_geom_long = (KP == 16) ? 102 : (KP == 32) ? 302 : (KP == 64) ? 304 : 704;
     if (const char* env = std::getenv("RCPPML_B200_CD_GEOM")) {
         const int g = std::atoi(env);
         B200_REQUIRE(cd_geometry_matches(g, KP), "RCPPML_B200_CD_GEOM does not match the padded rank");
-        cd_geom = g;
+        cd_geom = cd_geom_long = g;
     }
-    if (const char* env = std::getenv("RCPPML_B200_CD_KERNEL")) { if (std::atoi(env) == 1) cd_geom = 0; }
+    if (const char* env = std::getenv("RCPPML_B200_CD_KERNEL")) { if (std::atoi(env) == 1) cd_geom = cd_geom_long = 0; }
     if (peers_ready && (static_cast<size_t>(m_pad) * KP > W_T.count || static_cast<size_t>(n_pad) * KP > H.count ||
                         KP * KP > xchg_ne_max))
         comm_ipc_close();                                 // the mapped buffers are about to move: back to NCCL
@@ -509,10 +517,9 @@ void Engine::alloc_factors(int k_) {
         }
     }
     if (cd_geom) {
-        for (int wc = 0; wc < 2; ++wc) {
+        for (int geom : {cd_geom, cd_geom_long}) {
             int g = 0;
-            dummy.want_cross = wc;
-            launch_cd_half_step(cd_geom, dummy, num_sms, stream, &g);
+            launch_cd_half_step(geom, dummy, num_sms, stream, &g);
             gmax = std::max(gmax, g);
         }
     }
@@ -666,7 +673,11 @@ void Engine::prepare_solver(const float* G, float L2, int sec) {
     sec_begin(sec);
     const int solver = cfg.solver_mode == 0 ? SOLVER_CD : SOLVER_CHOL;
     const size_t smem = static_cast<size_t>(2) * KP * KP * sizeof(float);
-    B200_CUDA_CHECK(cudaFuncSetAttribute(prepare_solver_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 128 * 128 * 4));
+    static thread_local bool attr_set = false;
+    if (!attr_set) {
+        B200_CUDA_CHECK(cudaFuncSetAttribute(prepare_solver_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 128 * 128 * 4));
+        attr_set = true;
+    }
     prepare_solver_kernel<<<1, kPrepThreads, smem, stream>>>(G, KP, k, L2, solver, M1.ptr, M2.ptr, dblk.ptr, dblk.ptr + kMaxKP * 4, state.ptr);
     // warp-uniform operands -> this engine's constant-memory slot (kernels_solve.cuh SolverConsts); rcp follows
     // dblk in one device buffer, laid out like the struct
@@ -774,7 +785,7 @@ void Engine::build_panels() {
 }
 
 void Engine::launch_solver(int geom, int solver, const HalfStepParams& p, int* grid_out) {
-    if (solver == SOLVER_CD && cd_geom) launch_cd_half_step(cd_geom, p, num_sms, stream, grid_out);
+    if (solver == SOLVER_CD && cd_geom) launch_cd_half_step(geom, p, num_sms, stream, grid_out);
     else launch_half_step(geom, solver, BSRC_GATHER, OUT_SOLVE, p, num_sms, stream, grid_out);
 }
 
@@ -783,8 +794,16 @@ void Engine::solve(int which, bool warm, int sec) {
     const int solver = cfg.solver_mode == 0 ? SOLVER_CD : SOLVER_CHOL;
     const long long cnt = which == 0 ? nnz : nnz_w;
     const int P = npanels[which];
-    const int geom = geometry_for(cnt, p.ncols);
-    if (solver == SOLVER_CD && cd_geom) p.cols_per_fetch = 1;      // a CD column is thousands of instructions
+    int geom = geometry_for(cnt, p.ncols);
+    if (solver == SOLVER_CD && cd_geom) {
+        const double avg = p.ncols > 0 ? static_cast<double>(cnt) / static_cast<double>(p.ncols) : 0.0;
+        geom = avg >= 400.0 ? cd_geom_long : cd_geom;
+        p.cols_per_fetch = 1;                                      // a CD column is thousands of instructions
+        if (p.want_cross) {                                        // parking space for the pre-L1 right-hand sides
+            carry.ensure(static_cast<size_t>(std::max(n_loc, m_loc)) * KP);
+            p.braw = carry.ptr;                                    // (a panel pass reads carry[j] before it parks there)
+        }
+    }
     int grid = 0;
     launch_solver(geom, solver, p, &grid);
     last_solve_grid = grid;
@@ -1072,6 +1091,9 @@ void Engine::begin_fit(const rcppml_b200_config& c) {
     normalize_cfg(c);
     B200_REQUIRE(world == 1 || comm_ready(), "begin_fit: communicator not initialised");
     iters_enqueued = 0;
+    drop_iteration_graph();                                                 // new configuration / buffers
+    graphs_enabled = true;
+    if (const char* env = std::getenv("RCPPML_B200_GRAPH")) graphs_enabled = std::atoi(env) != 0;
     build_panels();
     loss_hist.ensure(static_cast<size_t>(std::max(cfg.max_iter, 1024)));
     DevState s0{};
@@ -1092,6 +1114,41 @@ void Engine::begin_fit(const rcppml_b200_config& c) {
     loop_ms = 0.0;
 }
 
+void Engine::drop_iteration_graph() {
+    if (iter_graph) cudaGraphExecDestroy(iter_graph);
+    iter_graph = nullptr;
+}
+
+// Capture one steady-state iteration (warm start, Gram of W_T carried over) into a graph. Every launcher has
+// run once by now (iteration 0), so no attribute / occupancy query or allocation happens inside the capture.
+void Engine::capture_iteration_graph() {
+    const auto before = launches;
+    const int it0 = iters_enqueued;
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        graphs_enabled = false;
+        return;
+    }
+    bool ok = true;
+    try {
+        enqueue_iteration();
+    } catch (...) {
+        ok = false;
+    }
+    if (cudaStreamEndCapture(stream, &graph) != cudaSuccess || !graph) ok = false;
+    iters_enqueued = it0;                                                   // nothing has executed
+    for (int s = 0; s < RCPPML_B200_NUM_SECTIONS; ++s) graph_launches[s] = launches[s] - before[s];
+    launches = before;
+    if (ok && cudaGraphInstantiate(&iter_graph, graph, 0) != cudaSuccess) { iter_graph = nullptr; ok = false; }
+    if (graph) cudaGraphDestroy(graph);
+    if (!ok) {                                                              // fall back to plain launches
+        cudaGetLastError();
+        drop_iteration_graph();
+        graphs_enabled = false;
+    }
+}
+
 void Engine::iterate(int n_iters) {
     use_device();
     B200_REQUIRE(fit_active, "iterate: call begin_fit first");
@@ -1100,7 +1157,13 @@ void Engine::iterate(int n_iters) {
     // kernels enqueued after `stop` return immediately. Every 8 iterations the host peeks at the
     // flag only to avoid enqueuing a long tail of no-op launches.
     for (int it = 0; it < n_iters; ++it) {
-        if (cv_active) enqueue_iteration_cv(); else if (has_mask) enqueue_iteration_masked(); else enqueue_iteration();
+        const bool graphable = graphs_enabled && !cv_active && !has_mask && world == 1 && !profiling && iters_enqueued >= 1;
+        if (graphable && !iter_graph) capture_iteration_graph();
+        if (graphable && iter_graph) {
+            B200_CUDA_CHECK(cudaGraphLaunch(iter_graph, stream));
+            for (int s = 0; s < RCPPML_B200_NUM_SECTIONS; ++s) launches[s] += graph_launches[s];
+            ++iters_enqueued;
+        } else if (cv_active) enqueue_iteration_cv(); else if (has_mask) enqueue_iteration_masked(); else enqueue_iteration();
         if ((it & 7) == 7 && (cfg.tol > 0.f || cv_active)) {
             B200_CUDA_CHECK(cudaMemcpyAsync(h_state, state.ptr, sizeof(DevState), cudaMemcpyDeviceToHost, stream));
             B200_CUDA_CHECK(cudaStreamSynchronize(stream));
@@ -1123,6 +1186,8 @@ void Engine::half_step_only(const rcppml_b200_config& c, int which, bool warm, b
     B200_REQUIRE(matrix_ready && factors_ready, "half_step: matrix and factors must be set first");
     B200_REQUIRE(world == 1, "half_step: single-GPU diagnostic entry");
     normalize_cfg(c);
+    drop_iteration_graph();
+    fit_active = false;
     build_panels();
     DevState s0{};
     s0.prev_loss = 3.402823466e+38f;

@@ -95,7 +95,8 @@ public:
 
     int k = 0, KP = 0, LANES = 0, nv_override = 0, nv_short_override = 0;
     int geometry_for(long long nnz, long long ncols) const;
-    int cd_geom = 0;                        // lane-group geometry of cd_half_step_kernel (0: use half_step_kernel<CD>)
+    int cd_geom = 0, cd_geom_long = 0;      // lane-group geometry of cd_half_step_kernel for short / long columns
+                                            // (0: use half_step_kernel<CD>)
     void launch_solver(int geom, int solver, const HalfStepParams& p, int* grid_out = nullptr);
     DeviceBuffer<float> W_T, H, d;
     DeviceBuffer<float> G_w, G_h, M1, M2, dblk;     // dblk: SolverConsts image (diagonal blocks, then reciprocals)
@@ -115,6 +116,14 @@ public:
     int gram_grid = 0, solve_grid_max = 0, last_solve_grid = 0;
 
     rcppml_b200_config cfg{};
+    // Steady-state iteration (iteration >= 1, single GPU, plain path) captured once per fit as a CUDA graph and
+    // replayed: on small matrices (C2/C3) an iteration is ~20 launches of a few microseconds each and the loop is
+    // launch bound. RCPPML_B200_GRAPH=0 disables. Not used while per-section profiling records events.
+    cudaGraphExec_t iter_graph = nullptr;
+    bool graphs_enabled = true;
+    std::array<int, RCPPML_B200_NUM_SECTIONS> graph_launches{};
+    void capture_iteration_graph();
+    void drop_iteration_graph();
     int iters_enqueued = 0;
     double loop_ms = 0.0;
     unsigned long long cd_sweeps = 0;

@@ -71,6 +71,7 @@ struct HalfStepParams {
     const int* __restrict__ seg_end;   // [ncols] one past the last entry of this pass (nullptr: colptr[j+1])
     float* __restrict__ carry;
     int carry_load;                    // start from carry[j] instead of 0 (every pass but the first)
+    float* __restrict__ braw;          // cd_half_step_kernel, want_cross: [ncols][KP] parking space for the pre-L1 RHS
 };
 
 // Warp-uniform solver operands (the 4x4 diagonal blocks and the pivot reciprocals) live in CONSTANT memory:

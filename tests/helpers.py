@@ -63,3 +63,22 @@ def load_pbmc3k_block():
     import os
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pbmc3k_500x200.npz"))
     return sp.csc_matrix((g["data"], g["indices"], g["indptr"]), shape=(500, 200))
+
+
+def load_movielens():
+    """tests/golden/movielens.npz: the reference's data/movielens.rda (Matrix::dgCMatrix, 3867 x 610, 75 238 ratings
+    1..5) read without R by tests/golden/rdx3.py — BASELINE.json configs[1]. Returns (csc, frozen oracle outputs)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "movielens.npz"))
+    A = sp.csc_matrix((g["data"], g["indices"], g["indptr"]), shape=(int(g["m"]), int(g["n"])))
+    return A, g
+
+
+def load_aml_as_csc():
+    """tests/golden/aml.npz: the reference's data/aml.rda (dense 824 x 135 methylation matrix, BASELINE.json
+    configs[0], the quick-start) as CSC with its 232 exact zeros dropped — the sparse path's view of it."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "aml.npz"))
+    A = sp.csc_matrix(g["A"])
+    A.sort_indices()
+    return A

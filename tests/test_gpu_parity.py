@@ -223,27 +223,51 @@ def test_pbmc3k_full_k32(eng, oracle):
         assert zero_pattern_equal(W, ref.W_T) and zero_pattern_equal(H, ref.H)
 
 
-def test_movielens_shaped_k20_l1(eng, oracle):
-    """BASELINE.json configs[1] stand-in: data/movielens.rda is an R serialisation (RDX3) that cannot be read
-    without R, so this is a DECLARED SYNTHETIC matrix of movielens' shape and density (3867 x 610, ~4 %, ratings
-    0.5..5 in steps of 0.5), k=20, L1=(0.01, 0.01), CD."""
+def test_movielens_k20_l1(eng, oracle):
+    """BASELINE.json configs[1]: the reference's movielens ratings matrix (data/movielens.rda, read without R by
+    tests/golden/rdx3.py), k=20, L1=(0.01, 0.01); CD (what R selects for the GPU at k <= 32) and Cholesky."""
     import rcppml_b200 as rb
-    rng = np.random.default_rng(610)
-    import scipy.sparse as sp
-    A = sp.random(3867, 610, density=0.043, format="csc", random_state=rng, dtype=np.float32)
-    A.data = (np.ceil(A.data * 10) / 2).astype(np.float32)
-    A.sort_indices()
-    m, n, k, iters = 3867, 610, 20, 6
+    from helpers import load_movielens
+    A, frozen = load_movielens()
+    m, n, k, iters = A.shape[0], A.shape[1], 20, 6
+    assert (m, n, A.nnz) == (3867, 610, 75238)
     W0, H0 = oracle.initialize_factors(k, m, n, 42)
-    kw = dict(L1=(0.01, 0.01), solver_mode=0)
-    ref = oracle.nmf_fit(A.indptr, A.indices, A.data, m, n, k, W0, H0, max_iter=iters, tol=0.0, **kw)
     eng.set_matrix(m, n, A.indptr, A.indices, A.data)
-    eng.set_factors(W0, H0)
-    eng.fit(rb.make_config(k, max_iter=iters, tol=0.0, **kw))
-    W, H, d = eng.get_factors()
-    errs = dict(W=rel_err(W, ref.W_T), H=rel_err(H, ref.H), d=rel_err(d, ref.d))
-    assert max(errs.values()) <= RTOL, errs
-    assert eng.cd_sweeps() == ref.cd_sweeps
+    for solver in (0, 1):
+        kw = dict(L1=(0.01, 0.01), solver_mode=solver)
+        ref = oracle.nmf_fit(A.indptr, A.indices, A.data, m, n, k, W0, H0, max_iter=iters, tol=0.0, **kw)
+        eng.set_factors(W0, H0)
+        res = eng.fit(rb.make_config(k, max_iter=iters, tol=0.0, **kw))
+        W, H, d = eng.get_factors()
+        errs = dict(W=rel_err(W, ref.W_T), H=rel_err(H, ref.H), d=rel_err(d, ref.d),
+                    loss=rel_err(eng.loss_history(iters), ref.loss_history),
+                    loss_frozen=rel_err(eng.loss_history(iters), frozen[f"loss_{solver}"]))
+        print("movielens k=20 solver", solver, errs, "loop ms/iter", res.loop_ms / iters)
+        assert max(errs.values()) <= RTOL, errs
+        assert zero_pattern_equal(W, ref.W_T) and zero_pattern_equal(H, ref.H)
+        if solver == 0:
+            assert eng.cd_sweeps() == ref.cd_sweeps == int(frozen["sweeps_0"])
+
+
+def test_aml_k6_through_the_sparse_path(eng, oracle):
+    """BASELINE.json configs[0]: the reference quick-start matrix (data/aml.rda, dense 824 x 135), k=6, MSE. The
+    reference runs it through its dense CPU path (out of scope here); this feeds the same numbers to the sparse
+    kernels as CSC — every column is (almost) full, the opposite extreme of C4."""
+    import rcppml_b200 as rb
+    from helpers import load_aml_as_csc
+    A = load_aml_as_csc()
+    m, n, k, iters = 824, 135, 6, 10
+    W0, H0 = oracle.initialize_factors(k, m, n, 42)
+    eng.set_matrix(m, n, A.indptr, A.indices, A.data)
+    for solver in (0, 1):
+        ref = oracle.nmf_fit(A.indptr, A.indices, A.data, m, n, k, W0, H0, max_iter=iters, tol=0.0, solver_mode=solver)
+        eng.set_factors(W0, H0)
+        eng.fit(rb.make_config(k, max_iter=iters, tol=0.0, solver_mode=solver))
+        W, H, d = eng.get_factors()
+        errs = dict(W=rel_err(W, ref.W_T), H=rel_err(H, ref.H), d=rel_err(d, ref.d),
+                    loss=rel_err(eng.loss_history(iters), ref.loss_history))
+        assert max(errs.values()) <= RTOL, (solver, errs)
+        assert zero_pattern_equal(W, ref.W_T) and zero_pattern_equal(H, ref.H)
 
 
 def test_convergence_and_patience(eng, oracle):
@@ -352,7 +376,7 @@ def test_row_panel_passes_are_bit_identical(eng, oracle, k, solver, monkeypatch)
     assert rel_err(outs[1][0], ref.W_T) <= RTOL and rel_err(outs[1][1], ref.H) <= RTOL
 
 
-CD_GEOMS = {16: (102, 4), 32: (302, 104), 64: (702, 304, 108), 128: (704, 308, 116)}
+CD_GEOMS = {16: (301, 102, 4), 32: (701, 302, 104), 64: (702, 304, 108), 128: (704, 308, 116)}
 
 
 @pytest.mark.parametrize("k", [5, 16, 20, 32, 50, 64, 100, 128])
@@ -390,6 +414,40 @@ def test_cd_kernel_geometries_are_bit_identical(eng, oracle, k, monkeypatch):
     ref = oracle.nmf_fit(A.indptr, A.indices, A.data, m, n, k, W0, H0, max_iter=iters, tol=0.0, **kw)
     assert rel_err(outs[1][0], ref.W_T) <= RTOL and rel_err(outs[1][1], ref.H) <= RTOL
     assert outs[1][4] == ref.cd_sweeps
+
+
+@pytest.mark.parametrize("solver", [0, 1])
+def test_cuda_graph_iterations_are_bit_identical(eng, oracle, solver, monkeypatch):
+    """iterate() replays the steady-state iteration as a CUDA graph (engine.cu capture_iteration_graph). Same kernels,
+    same order: factors, loss history, iteration count and the device-side convergence stop must be bit-identical
+    to plain launches — with tol = 0 and with early stopping in the middle of the replayed iterations."""
+    import rcppml_b200 as rb
+    m, n, k = 900, 400, 20
+    A = random_csc(m, n, 0.05, 77, ragged=True)
+    eng.set_matrix(m, n, A.indptr, A.indices, A.data)
+    for tol, iters in ((0.0, 12), (3e-3, 60)):
+        cfg = rb.make_config(k, max_iter=iters, tol=tol, solver_mode=solver, L1=(0.01, 0.01), patience=2)
+        outs = []
+        for graph in ("0", "1"):
+            monkeypatch.setenv("RCPPML_B200_GRAPH", graph)
+            eng.init_factors(k, 42)
+            res = eng.fit(cfg)
+            assert res.status == 0
+            outs.append(eng.get_factors() + (eng.loss_history(res.iterations), res.iterations, res.converged, res.gpu_launches))
+        monkeypatch.delenv("RCPPML_B200_GRAPH")
+        for a, b in zip(outs[0][:4], outs[1][:4]):
+            assert np.array_equal(a, b)
+        assert outs[0][4:] == outs[1][4:], (outs[0][4:], outs[1][4:])
+        if tol > 0:
+            assert outs[0][5] and outs[0][4] < iters        # stopped early, on the device
+    # a second fit on new factors must not replay the previous fit's graph
+    W0, H0 = oracle.initialize_factors(k, m, n, 7)
+    eng.set_factors(W0, H0)
+    cfg = rb.make_config(k, max_iter=6, tol=0.0, solver_mode=solver)
+    res = eng.fit(cfg)
+    ref = oracle.nmf_fit(A.indptr, A.indices, A.data, m, n, k, W0, H0, max_iter=6, tol=0.0, solver_mode=solver)
+    W, H, d = eng.get_factors()
+    assert res.iterations == 6 and rel_err(W, ref.W_T) <= RTOL and rel_err(H, ref.H) <= RTOL
 
 
 def test_large_synthetic_properties(eng):

@@ -224,3 +224,41 @@ def test_golden_fixture_regression(oracle):
                            L2=(0.0, 0.01), threads=1)
         assert np.array_equal(r.W_T, g[f"W_{solver}"]) and np.array_equal(r.H, g[f"H_{solver}"])
         assert np.array_equal(r.d, g[f"d_{solver}"]) and np.array_equal(r.loss_history, g[f"loss_{solver}"])
+
+
+# ---- the reference's own datasets (BASELINE.json configs[0], configs[1]) --------------------------
+def test_oracle_on_movielens_matches_frozen_outputs(oracle):
+    """tests/golden/movielens.npz holds the reference's data/movielens.rda (read without R, tests/golden/rdx3.py)
+    and what the oracle produced on it when the fixture was made: an edit of oracle/nmf_oracle.cpp that changes
+    a single rounding shows up here (loss history, d, CD sweep total are compared exactly)."""
+    from helpers import load_movielens
+    A, g = load_movielens()
+    m, n, k, iters = A.shape[0], A.shape[1], 20, 6
+    assert (m, n, A.nnz) == (3867, 610, 75238)
+    assert set(np.unique(A.data).tolist()) <= {1.0, 2.0, 3.0, 4.0, 5.0}
+    W0, H0 = oracle.initialize_factors(k, m, n, 42)
+    for solver in (0, 1):
+        r = oracle.nmf_fit(A.indptr, A.indices, A.data, m, n, k, W0, H0, max_iter=iters, tol=0.0, solver_mode=solver,
+                           L1=(0.01, 0.01), threads=1)
+        assert np.array_equal(r.loss_history, g[f"loss_{solver}"])
+        assert np.array_equal(r.d, g[f"d_{solver}"])
+        assert r.cd_sweeps == int(g[f"sweeps_{solver}"])
+        assert np.all(np.diff(r.loss_history) <= 1e-5 * np.abs(r.loss_history[:-1]))    # test_loss_monotonicity.R
+
+
+def test_rda_reader_against_the_reference_files():
+    """tests/golden/rdx3.py on the reference's .rda files (only where /root/reference exists: the build container)."""
+    import os
+    import sys
+    if not os.path.exists("/root/reference/data/movielens.rda"):
+        pytest.skip("reference tree not present (GPU box)")
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import rdx3
+    from helpers import load_aml_as_csc, load_movielens
+    p, i, x, (m, n) = rdx3.as_csc(rdx3.read_rda("/root/reference/data/movielens.rda")["movielens"])
+    A, _ = load_movielens()
+    assert (m, n) == A.shape and np.array_equal(p, A.indptr) and np.array_equal(i, A.indices)
+    assert np.array_equal(x.astype(np.float32), A.data)
+    aml = rdx3.read_rda("/root/reference/data/aml.rda")["aml"]
+    dense = np.asarray(aml.value).reshape((135, 824)).T.astype(np.float32)
+    assert np.array_equal(load_aml_as_csc().toarray(), dense)

@@ -37,9 +37,9 @@ def main():
     eng = rb.Engine(0)
     eng.set_matrix_synthetic_sharded(args.m, args.n, args.density, 20260101)
     kp = 16 if args.k <= 16 else 32 if args.k <= 32 else 64 if args.k <= 64 else 128
-    geoms = {16: (102, 4), 32: (302, 104), 64: (702, 304, 108), 128: (704, 308, 116)}[kp]
+    geoms = {16: (301, 102, 4), 32: (701, 302, 104), 64: (702, 304, 108), 128: (704, 308, 116)}[kp]
     if args.solver == 0:
-        variants = [("v2_geom%d" % g, {"RCPPML_B200_CD_GEOM": str(g)}) for g in geoms]
+        variants = [("default", {})] + [("v2_geom%d" % g, {"RCPPML_B200_CD_GEOM": str(g)}) for g in geoms]
         variants += [("v1_nv%d" % nv, {"RCPPML_B200_CD_KERNEL": "1", "RCPPML_B200_NV": str(nv)})
                      for nv in ((1, 2, 4) if kp >= 64 else (1,))]
     else:
