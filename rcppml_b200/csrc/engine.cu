@@ -103,6 +103,41 @@ void launch_cd_half_step(int geom, const HalfStepParams& p, int num_sms, cudaStr
     }
 }
 
+template <int GL, int GNV, int SL, int SNV, int SOLVER>
+static void launch_tiled_t(const HalfStepParams& p, int num_sms, cudaStream_t stream, int* grid_out) {
+    auto kern = tiled_half_step_kernel<GL, GNV, SL, SNV, SOLVER>;
+    const size_t smem = tiled_smem_bytes<GL, GNV, SL, SNV, SOLVER>();
+    static thread_local int cached_occ = -1;
+    if (cached_occ < 0) {
+        B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        int occ = 0;
+        B200_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));
+        B200_REQUIRE(occ > 0, "tiled_half_step_kernel does not fit on an SM");
+        cached_occ = occ;
+    }
+    const int grid = num_sms * cached_occ;
+    if (grid_out) { *grid_out = grid; return; }
+    kern<<<grid, 256, smem, stream>>>(p);
+}
+
+template <int SOLVER>
+static void launch_tiled_s(int gather_geom, const HalfStepParams& p, int num_sms, cudaStream_t s, int* grid_out) {
+    switch (gather_geom) {                          // gather (LANES + 100*(NV-1)); the solve geometry follows from KP
+        case 4: launch_tiled_t<4, 1, 1, 4, SOLVER>(p, num_sms, s, grid_out); break;       // KP = 16
+        case 8: launch_tiled_t<8, 1, 1, 8, SOLVER>(p, num_sms, s, grid_out); break;       // KP = 32
+        case 16: launch_tiled_t<16, 1, 2, 8, SOLVER>(p, num_sms, s, grid_out); break;     // KP = 64
+        case 108: launch_tiled_t<8, 2, 2, 8, SOLVER>(p, num_sms, s, grid_out); break;
+        case 32: launch_tiled_t<32, 1, 4, 8, SOLVER>(p, num_sms, s, grid_out); break;     // KP = 128
+        case 116: launch_tiled_t<16, 2, 4, 8, SOLVER>(p, num_sms, s, grid_out); break;
+        default: throw std::runtime_error("unsupported gather geometry for the tiled kernel");
+    }
+}
+
+void launch_tiled_half_step(int gather_geom, int solver, const HalfStepParams& p, int num_sms, cudaStream_t s, int* grid_out) {
+    if (solver == SOLVER_CD) launch_tiled_s<SOLVER_CD>(gather_geom, p, num_sms, s, grid_out);
+    else launch_tiled_s<SOLVER_CHOL>(gather_geom, p, num_sms, s, grid_out);
+}
+
 static bool cd_geometry_matches(int geom, int KP) {
     const int lanes = geom % 100, nv = geom / 100 + 1;
     switch (geom) {
@@ -490,6 +525,13 @@ void Engine::alloc_factors(int k_) {
         cd_geom = cd_geom_long = g;
     }
     if (const char* env = std::getenv("RCPPML_B200_CD_KERNEL")) { if (std::atoi(env) == 1) cd_geom = cd_geom_long = 0; }
+    tiled_mode = 1;
+    if (const char* env = std::getenv("RCPPML_B200_TILED")) tiled_mode = std::atoi(env);
+    tiled_min_batches = 1.5;
+    if (const char* env = std::getenv("RCPPML_B200_TILED_MIN_BATCHES")) tiled_min_batches = std::atof(env);
+    narrow_min_cols = 8.0 * num_sms * 24;
+    if (std::getenv("RCPPML_B200_CD_GEOM")) narrow_min_cols = 0.0;           // an explicit geometry applies to every size
+    if (const char* env = std::getenv("RCPPML_B200_NARROW_MIN_COLS")) narrow_min_cols = std::atof(env);
     if (peers_ready && (static_cast<size_t>(m_pad) * KP > W_T.count || static_cast<size_t>(n_pad) * KP > H.count ||
                         KP * KP > xchg_ne_max))
         comm_ipc_close();                                 // the mapped buffers are about to move: back to NCCL
@@ -522,6 +564,14 @@ void Engine::alloc_factors(int k_) {
             launch_cd_half_step(geom, dummy, num_sms, stream, &g);
             gmax = std::max(gmax, g);
         }
+    }
+    if (tiled_mode) {
+        for (int solver = 0; solver < 2; ++solver)
+            for (int geom : {LANES, (KP == 64 || KP == 128) ? 100 + KP / 8 : LANES}) {
+                int g = 0;
+                launch_tiled_half_step(geom, solver, dummy, num_sms, stream, &g);
+                gmax = std::max(gmax, g);
+            }
     }
     { int g = 0; MaskedParams md{}; launch_masked(KP, md, num_sms, stream, &g); gmax = std::max(gmax, g); }
     { int g = 0; CvParams cd{}; launch_cv(KP, cd, num_sms, stream, &g); gmax = std::max(gmax, g); }
@@ -784,8 +834,40 @@ void Engine::build_panels() {
     }
 }
 
-void Engine::launch_solver(int geom, int solver, const HalfStepParams& p, int* grid_out) {
-    if (solver == SOLVER_CD && cd_geom) launch_cd_half_step(geom, p, num_sms, stream, grid_out);
+// Kernel selection for a half-step (all choices give bit-identical results; measured in profiles/r01p_*):
+//   * few columns (< narrow_min_cols, default 8 per resident warp): the one-geometry kernel with WIDE lane groups.
+//     Narrow groups put 16-32 columns in a warp; with few columns most of the machine idles and each column is
+//     slower (pbmc3k k=32 CD: 1.7 ms/iteration wide, 4.2 ms narrow; Cholesky 0.49 vs 1.2 ms);
+//   * coordinate descent otherwise: narrow groups — the tiled kernel (robust to skewed column lengths; long
+//     columns gather wide), or cd_half_step_kernel with RCPPML_B200_TILED=0;
+//   * Cholesky with short columns and >= tiled_min_batches batches per resident warp: the tiled kernel
+//     (C4 W half-step 2.64 -> 2.46 ms); long columns (C4 H half-step) are gather bound and stay one-geometry.
+bool Engine::use_narrow_cd(long long ncols) const {
+    return cd_geom != 0 && static_cast<double>(ncols) >= narrow_min_cols;
+}
+
+bool Engine::use_tiled(int solver, long long cnt, long long ncols) const {
+    if (tiled_mode == 0) return false;
+    if (tiled_mode == 2) return true;
+    if (solver == SOLVER_CD) return use_narrow_cd(ncols);
+    const int cb = (KP == 64) ? 16 : (KP == 128) ? 8 : 32;
+    const long long resident_warps = static_cast<long long>(num_sms) * 24;
+    if (static_cast<double>(ncols) < tiled_min_batches * static_cast<double>(cb) * static_cast<double>(resident_warps)) return false;
+    const double avg = ncols > 0 ? static_cast<double>(cnt) / static_cast<double>(ncols) : 0.0;
+    return avg < 400.0 && KP < 128;
+}
+
+int Engine::tiled_gather_geom(long long cnt, long long ncols) const {
+    const int g = geometry_for(cnt, ncols);                     // LANES + 100*(NV-1), NV in {1, 2, 4}
+    if (g >= 300) return 100 + KP / 8;                          // NV = 4 is not instantiated for the tiled kernel
+    return g;
+}
+
+// kind 0: half_step_kernel (one geometry, wide groups); 1: cd_half_step_kernel (one geometry, narrow groups);
+// 2: tiled_half_step_kernel (geom = gather geometry).
+void Engine::launch_solver(int kind, int geom, int solver, const HalfStepParams& p, int* grid_out) {
+    if (kind == 2) launch_tiled_half_step(geom, solver, p, num_sms, stream, grid_out);
+    else if (kind == 1) launch_cd_half_step(geom, p, num_sms, stream, grid_out);
     else launch_half_step(geom, solver, BSRC_GATHER, OUT_SOLVE, p, num_sms, stream, grid_out);
 }
 
@@ -795,17 +877,22 @@ void Engine::solve(int which, bool warm, int sec) {
     const long long cnt = which == 0 ? nnz : nnz_w;
     const int P = npanels[which];
     int geom = geometry_for(cnt, p.ncols);
-    if (solver == SOLVER_CD && cd_geom) {
+    const bool tiled = use_tiled(solver, cnt, p.ncols);
+    const bool narrow_cd = !tiled && solver == SOLVER_CD && use_narrow_cd(p.ncols);
+    const int kind = tiled ? 2 : (narrow_cd ? 1 : 0);
+    if (tiled) {
+        geom = tiled_gather_geom(cnt, p.ncols);
+    } else if (narrow_cd) {
         const double avg = p.ncols > 0 ? static_cast<double>(cnt) / static_cast<double>(p.ncols) : 0.0;
         geom = avg >= 400.0 ? cd_geom_long : cd_geom;
         p.cols_per_fetch = 1;                                      // a CD column is thousands of instructions
-        if (p.want_cross) {                                        // parking space for the pre-L1 right-hand sides
-            carry.ensure(static_cast<size_t>(std::max(n_loc, m_loc)) * KP);
-            p.braw = carry.ptr;                                    // (a panel pass reads carry[j] before it parks there)
-        }
+    }
+    if ((tiled || narrow_cd) && p.want_cross) {                    // parking space for the pre-L1 right-hand sides
+        carry.ensure(static_cast<size_t>(std::max(n_loc, m_loc)) * KP);
+        p.braw = carry.ptr;                                        // (a panel pass reads carry[j] before it parks there)
     }
     int grid = 0;
-    launch_solver(geom, solver, p, &grid);
+    launch_solver(kind, geom, solver, p, &grid);
     last_solve_grid = grid;
     sec_begin(sec);
     if (P > 1) {
@@ -823,14 +910,14 @@ void Engine::solve(int which, bool warm, int sec) {
                 q.cols_per_fetch = pick_cols_per_fetch(cnt / P, p.ncols, num_sms);
                 launch_half_step(geom_pass, SOLVER_CD, BSRC_GATHER, OUT_RHS, q, num_sms, stream);
             } else {
-                q.cols_per_fetch = (solver == SOLVER_CD && cd_geom) ? 1 : pick_cols_per_fetch(cnt / P, p.ncols, num_sms);
-                launch_solver(geom, solver, q);
+                q.cols_per_fetch = narrow_cd ? 1 : pick_cols_per_fetch(cnt / P, p.ncols, num_sms);
+                launch_solver(kind, geom, solver, q);
             }
             launches[sec] += 1;
         }
     } else {
         B200_CUDA_CHECK(cudaMemsetAsync(p.work_counter, 0, sizeof(int), stream));
-        launch_solver(geom, solver, p);
+        launch_solver(kind, geom, solver, p);
         launches[sec] += 1;
     }
     sec_end(sec);

@@ -8,6 +8,7 @@
 #include "kernels_cv.cuh"
 #include "kernels_solve.cuh"
 #include "kernels_cd.cuh"
+#include "kernels_tiled.cuh"
 #include "kernels_sparse.cuh"
 
 #include <array>
@@ -25,6 +26,8 @@ extern thread_local std::string g_last_error;
 void launch_half_step(int lanes, int solver, int bsrc, int out, const HalfStepParams& p, int num_sms,
                       cudaStream_t s, int* grid_out = nullptr);
 void launch_cd_half_step(int geom, const HalfStepParams& p, int num_sms, cudaStream_t s, int* grid_out = nullptr);
+void launch_tiled_half_step(int gather_geom, int solver, const HalfStepParams& p, int num_sms, cudaStream_t s,
+                            int* grid_out = nullptr);
 
 class Engine {
 public:
@@ -97,7 +100,14 @@ public:
     int geometry_for(long long nnz, long long ncols) const;
     int cd_geom = 0, cd_geom_long = 0;      // lane-group geometry of cd_half_step_kernel for short / long columns
                                             // (0: use half_step_kernel<CD>)
-    void launch_solver(int geom, int solver, const HalfStepParams& p, int* grid_out = nullptr);
+    void launch_solver(int kind, int geom, int solver, const HalfStepParams& p, int* grid_out = nullptr);
+    // kernels_tiled.cuh (wide gather -> shared-memory tile -> narrow solve). 0: never, 1: CD always and Cholesky
+    // for short columns (default), 2: always. RCPPML_B200_TILED overrides.
+    int tiled_mode = 1;
+    double tiled_min_batches = 1.5, narrow_min_cols = 0.0;
+    bool use_narrow_cd(long long ncols) const;
+    bool use_tiled(int solver, long long cnt, long long ncols) const;
+    int tiled_gather_geom(long long cnt, long long ncols) const;
     DeviceBuffer<float> W_T, H, d;
     DeviceBuffer<float> G_w, G_h, M1, M2, dblk;     // dblk: SolverConsts image (diagonal blocks, then reciprocals)
     int const_slot = 0;

@@ -31,7 +31,11 @@ def main():
     cases = [(64, 1, {}), (64, 0, dict(L1=(0.01, 0.01))), (20, 0, dict(L2=(0.01, 0.01))),
              (128, 1, dict(L1=(0.01, 0.01), L2=(0.01, 0.01)))]
     # every case with the peer-memory loop (no NCCL call inside the iteration) and with the NCCL loop
-    for p2p, (k, solver, kw) in [(a, b) for a in (True, False) for b in cases]:
+    # ... and the peer-memory loop once more with the tiled kernels forced (kernels_tiled.cuh stores whole rows into
+    # the peer replicas; the default policy keeps operands this thin on the one-geometry kernels)
+    combos = [(a, b, "1") for a in (True, False) for b in cases] + [(True, b, "2") for b in cases]
+    for p2p, (k, solver, kw), tiled in combos:
+        os.environ["RCPPML_B200_TILED"] = tiled
         iters = 4
         eng = rb.Engine(local)
         uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
@@ -77,7 +81,7 @@ def main():
         exact = bool(np.array_equal(W, W1) and np.array_equal(H, H1) and np.array_equal(d, d1))
         worst = max(worst, *errs.values())
         if rank == 0:
-            print(f"k={k} solver={solver} world={world} p2p={p2p}: bit-identical={exact} {errs}", flush=True)
+            print(f"k={k} solver={solver} world={world} p2p={p2p} tiled={tiled}: bit-identical={exact} {errs}", flush=True)
         assert max(errs.values()) <= 1e-5, errs
     dist.barrier()
     if rank == 0:

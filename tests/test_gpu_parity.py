@@ -376,6 +376,45 @@ def test_row_panel_passes_are_bit_identical(eng, oracle, k, solver, monkeypatch)
     assert rel_err(outs[1][0], ref.W_T) <= RTOL and rel_err(outs[1][1], ref.H) <= RTOL
 
 
+@pytest.mark.parametrize("k", [5, 16, 20, 32, 50, 64, 100, 128])
+@pytest.mark.parametrize("solver", [0, 1])
+def test_tiled_kernel_is_bit_identical(eng, oracle, k, solver, monkeypatch):
+    """kernels_tiled.cuh (wide gather -> shared-memory tile -> narrow solve -> whole-row stores) against the
+    one-geometry kernels: factors, d and the loss history bit for bit (CD: sweep totals too), for ragged columns,
+    L1/L2, an upper bound, both norms, short and long columns, and with row panels on top."""
+    import rcppml_b200 as rb
+    outs = {}
+    for (m, n, dens) in ((1100, 600, 0.05), (300, 2100, 0.2)):            # W-update columns: ~30 / ~420 non-zeros
+        A = random_csc(m, n, dens, 900 + k, ragged=True)
+        eng.set_matrix(m, n, A.indptr, A.indices, A.data)
+        for kw in (dict(L1=(0.01, 0.005), L2=(0.0, 0.01)), dict(upper_bound=(0.05, 0.08), norm_type=1)):
+            cfg = rb.make_config(k, max_iter=4, tol=0.0, solver_mode=solver, cd_maxit=100, **kw)
+            res = []
+            for tiled, panel in (("0", None), ("2", None), ("2", "0.02")):
+                monkeypatch.setenv("RCPPML_B200_TILED", tiled)
+                if panel:
+                    monkeypatch.setenv("RCPPML_B200_PANEL_MB", panel)
+                eng.init_factors(k, 42)
+                r = eng.fit(cfg)
+                assert r.status == 0 and r.iterations == 4
+                res.append(eng.get_factors() + (eng.loss_history(4), eng.cd_sweeps()))
+                if panel:
+                    monkeypatch.delenv("RCPPML_B200_PANEL_MB")
+            monkeypatch.delenv("RCPPML_B200_TILED")
+            for other in res[1:]:
+                for a, b in zip(res[0][:4], other[:4]):
+                    assert np.array_equal(a, b), (k, solver, m, kw)
+                assert res[0][4] == other[4]
+            outs[(m, tuple(kw))] = res[1]
+    m, n = 1100, 600
+    A = random_csc(m, n, 0.05, 900 + k, ragged=True)
+    W0, H0 = oracle.initialize_factors(k, m, n, 42)
+    ref = oracle.nmf_fit(A.indptr, A.indices, A.data, m, n, k, W0, H0, max_iter=4, tol=0.0, solver_mode=solver,
+                         L1=(0.01, 0.005), L2=(0.0, 0.01))
+    got = outs[(1100, ("L1", "L2"))]
+    assert rel_err(got[0], ref.W_T) <= RTOL and rel_err(got[1], ref.H) <= RTOL and rel_err(got[2], ref.d) <= RTOL
+
+
 CD_GEOMS = {16: (301, 102, 4), 32: (701, 302, 104), 64: (702, 304, 108), 128: (704, 308, 116)}
 
 
@@ -393,6 +432,7 @@ def test_cd_kernel_geometries_are_bit_identical(eng, oracle, k, monkeypatch):
     cfg = rb.make_config(k, max_iter=iters, tol=0.0, **kw)
     kp = 16 if k <= 16 else 32 if k <= 32 else 64 if k <= 64 else 128
     outs = []
+    monkeypatch.setenv("RCPPML_B200_TILED", "0")                # this test is about cd_half_step_kernel
     monkeypatch.setenv("RCPPML_B200_CD_KERNEL", "1")            # the original kernel
     eng.init_factors(k, 42)
     res = eng.fit(cfg)
@@ -406,6 +446,7 @@ def test_cd_kernel_geometries_are_bit_identical(eng, oracle, k, monkeypatch):
         assert res.status == 0 and res.iterations == iters
         outs.append(eng.get_factors() + (eng.loss_history(iters), eng.cd_sweeps()))
     monkeypatch.delenv("RCPPML_B200_CD_GEOM")
+    monkeypatch.delenv("RCPPML_B200_TILED")
     for gi, other in enumerate(outs[1:]):
         for a, b in zip(outs[0][:4], other[:4]):
             assert np.array_equal(a, b), (k, CD_GEOMS[kp][gi])

@@ -39,17 +39,19 @@ def main():
     kp = 16 if args.k <= 16 else 32 if args.k <= 32 else 64 if args.k <= 64 else 128
     geoms = {16: (301, 102, 4), 32: (701, 302, 104), 64: (702, 304, 108), 128: (704, 308, 116)}[kp]
     if args.solver == 0:
-        variants = [("default", {})] + [("v2_geom%d" % g, {"RCPPML_B200_CD_GEOM": str(g)}) for g in geoms]
+        variants = [("default", {}), ("untiled", {"RCPPML_B200_TILED": "0"})]
+        variants += [("v2_geom%d" % g, {"RCPPML_B200_CD_GEOM": str(g), "RCPPML_B200_TILED": "0"}) for g in geoms]
         variants += [("v1_nv%d" % nv, {"RCPPML_B200_CD_KERNEL": "1", "RCPPML_B200_NV": str(nv)})
                      for nv in ((1, 2, 4) if kp >= 64 else (1,))]
     else:
-        variants = [("chol_default", {})]
+        variants = [("chol_default", {}), ("chol_untiled", {"RCPPML_B200_TILED": "0"}), ("chol_tiled_both", {"RCPPML_B200_TILED": "2"})]
         if kp >= 64:
-            variants += [("chol_nvshort%d" % nv, {"RCPPML_B200_NV_SHORT": str(nv)}) for nv in (1, 4)]
+            variants += [("chol_untiled_nvshort%d" % nv, {"RCPPML_B200_NV_SHORT": str(nv), "RCPPML_B200_TILED": "0"}) for nv in (1, 4)]
+            variants += [("chol_tiled_gather16x1", {"RCPPML_B200_NV_SHORT": "1"})]
     if args.variants:
         keep = set(args.variants.split(","))
         variants = [v for v in variants if v[0] in keep]
-    knobs = ("RCPPML_B200_CD_GEOM", "RCPPML_B200_CD_KERNEL", "RCPPML_B200_NV", "RCPPML_B200_NV_SHORT")
+    knobs = ("RCPPML_B200_CD_GEOM", "RCPPML_B200_CD_KERNEL", "RCPPML_B200_NV", "RCPPML_B200_NV_SHORT", "RCPPML_B200_TILED")
     lines = []
     for name, env in variants:
         for kname in knobs:

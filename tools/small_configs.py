@@ -21,6 +21,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=200)
     ap.add_argument("--out", default="")
+    ap.add_argument("--kernel-variants", action="store_true",
+                    help="also time the other kernel selections (RCPPML_B200_TILED / _CD_KERNEL knobs)")
     args = ap.parse_args()
     import torch
     import rcppml_b200 as rb
@@ -53,6 +55,21 @@ def main():
                     best = cur if best is None or cur[0] < best[0] else best
                 row["graph" if graph == "1" else "plain"] = {"device_ms_per_iter": best[0], "wall_ms_per_iter": best[1]}
             row["nnz_per_sec_graph"] = A.nnz / (row["graph"]["device_ms_per_iter"] / 1e3)
+            if args.kernel_variants:
+                os.environ["RCPPML_B200_GRAPH"] = "1"
+                variants = {"tiled_always": {"RCPPML_B200_TILED": "2"}, "untiled": {"RCPPML_B200_TILED": "0"}}
+                if solver == 0:
+                    variants["untiled_wide_cd"] = {"RCPPML_B200_TILED": "0", "RCPPML_B200_CD_KERNEL": "1"}
+                for vname, env in variants.items():
+                    os.environ.update(env)
+                    best = None
+                    for rep in range(2):
+                        eng.init_factors(k, 42)
+                        res = eng.fit(rb.make_config(k, max_iter=args.iters, tol=0.0, solver_mode=solver, **kw))
+                        best = res.loop_ms / args.iters if best is None else min(best, res.loop_ms / args.iters)
+                    row[vname] = best
+                    for kn in env:
+                        os.environ.pop(kn, None)
             lines.append(row)
             print(json.dumps(row), flush=True)
     os.environ.pop("RCPPML_B200_GRAPH", None)
