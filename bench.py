@@ -395,7 +395,7 @@ def main():
     per_launch_bytes = (bh + bw) / 2.0 / world
     achieved = per_launch_bytes / (solve_ms / max(1, solve_launches) / 1e3) / 1e9
     traffic = ncu_traffic(args, world)
-    roofline = {"bound": "hbm", "kernel": "half_step_kernel (fused gather + NNLS solve; H- and W-update launches)",
+    roofline = {"bound": "hbm", "kernel": "fused gather + NNLS solve, two launches per iteration: half_step_kernel (H half-step, long columns) and tiled_half_step_kernel (W half-step, short columns)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": (traffic or {}).get("bytes_per_launch_mean"), "traffic_detail": traffic,
                 "peak_source": peak_src,
                 "per_launch_algorithmic_bytes": per_launch_bytes,
@@ -432,7 +432,7 @@ def main():
         line["solver_mode_0"] = {"ms_per_step": ms2 / st, "value": nnz_total * st / (ms2 / 1e3), "unit": "nnz/s",
                                  "iters_per_sec": st / (ms2 / 1e3), "steps": st, "warmup": wu,
                                  "cd_sweeps_total_incl_warmup": sweeps, "gpu_launches": l2,
-                                 "kernel": "cd_half_step_kernel (kernels_cd.cuh)",
+                                 "kernel": "tiled_half_step_kernel<.., SOLVER_CD> (kernels_tiled.cuh + the blocked CD of kernels_cd.cuh)",
                                  "sections_ms_per_step": {kk: v / st for kk, v in pm2.items()}}
 
     if world == 1 and not args.no_e2e:
