@@ -362,6 +362,7 @@ def main():
         eng.begin_fit(cfg)
         eng.iterate(warmup)
         launches0 = eng.result().gpu_launches
+        _, prof_launch0 = eng.profile()                      # per-section launch counts so far (warm-up iterations)
         eng.set_profiling(True)
         if dist is not None:
             dist.barrier()
@@ -381,6 +382,8 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         prof_ms, prof_launch = eng.profile()
+        # section times cover the timed steps only: count only the launches of the timed steps against them
+        prof_launch = {kk: v - prof_launch0.get(kk, 0) for kk, v in prof_launch.items()}
         assert res.iterations == steps + warmup and res.status == 0, res
         return ms, res.gpu_launches - launches0, prof_ms, prof_launch, clocks, eng.cd_sweeps()
 
