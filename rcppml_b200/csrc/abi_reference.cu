@@ -110,8 +110,7 @@ void rcppml_gpu_nmf_cv_unified_float(
         if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) { warn("no CUDA device"); return; }
         EngineLease lease(0);
         b200::Engine& E = lease.get();
-        E.set_matrix_host<double>(*m, *n, static_cast<int64_t>(*nnz), col_ptr, row_idx, values);
-        E.set_factors_host<double>(*k, W, H);
+        E.set_matrix_and_factors_host<double, double>(*m, *n, static_cast<int64_t>(*nnz), col_ptr, row_idx, values, *k, W, H);
         rcppml_b200_config cfg{};
         cfg.k = *k; cfg.max_iter = *max_iter; cfg.tol = static_cast<float>(*tol);
         cfg.L1_H = static_cast<float>(*L1_H); cfg.L1_W = static_cast<float>(*L1_W);
@@ -388,9 +387,13 @@ static void nmf_unified_impl(
 
         EngineLease lease(0);
         b200::Engine& E = lease.get();
-        E.set_matrix_host<double>(*m, *n, static_cast<int64_t>(*nnz), col_ptr, row_idx, values);
-        if (mask_p && mask_i && mask_nnz && *mask_nnz > 0) E.set_mask(*mask_nnz, mask_p, mask_i);
-        E.set_factors_host<double>(*k, W, H);
+        if (mask_p && mask_i && mask_nnz && *mask_nnz > 0) {
+            E.set_matrix_host<double>(*m, *n, static_cast<int64_t>(*nnz), col_ptr, row_idx, values);
+            E.set_mask(*mask_nnz, mask_p, mask_i);
+            E.set_factors_host<double>(*k, W, H);
+        } else {
+            E.set_matrix_and_factors_host<double, double>(*m, *n, static_cast<int64_t>(*nnz), col_ptr, row_idx, values, *k, W, H);
+        }
 
         rcppml_b200_config cfg{};
         cfg.k = *k;

@@ -51,6 +51,11 @@ public:
 
     // factors
     template <class T> void set_factors_host(int k, const T* W_T, const T* H);
+    // Host matrix + host factors in one call (the reference entry points): the factor H2D copies run on the copy
+    // engine while the device transposes A, instead of after it.
+    template <class ValT, class T>
+    void set_matrix_and_factors_host(int m, int n, int64_t nnz, const int* col_ptr, const int* row_idx, const ValT* values,
+                                     int k, const T* W_T, const T* H);
     template <class T> void get_factors_host(T* W_T, T* H, T* d);
     void init_factors(int k, uint32_t seed, int h_col_begin);
 
