@@ -8,12 +8,24 @@
 // reference leg may build, load or call this file. The product path
 // (rcppml_b200/csrc) never links or calls it.
 //
-// PARITY STATUS: **parity unpinned** for W/d/H values. The reference cannot be
-// compiled here (every hot-path header needs Eigen; no Eigen/R/Rcpp in the
-// image) and its test-suite holds no golden W/d/H vectors.
-// What IS pinned (tests/test_oracle_kats.py): the known-answer tests of
-// tests/cpp/test_nnls.cpp, test_gram.cpp, test_rng.cpp and the published
-// SplitMix64 reference vectors.
+// PARITY STATUS: pinned against the reference's OWN SOURCE for everything that
+// source decides, **parity unpinned** only for the rounding inside Eigen.
+//  * The reference's hot-path headers (rng.hpp, nnls_batch.hpp, fused_nnls.hpp,
+//    cholesky_clip.hpp, gram.hpp, primitives.hpp, constants.hpp) compile
+//    unmodified from /root/reference against a minimal stand-in for the Eigen
+//    types they use (oracle/ref_hotpath, `make -C oracle ref_hotpath` ->
+//    oracle/_ref/libref_hotpath.so); tests/test_reference_sources.py holds this
+//    file against that library BIT FOR BIT: SplitMix64 / hash / is_holdout /
+//    fill_uniform / factor initialisation, cd_nnls_col_fixed with every switch
+//    (sweep counts included), nnls_batch, the fused CD and Cholesky column loops
+//    (L1, warm start, clip, bound), the Gram wrapper.
+//  * Eigen itself (and R/Rcpp) is not in the image, so the whole nmf_fit<> cannot
+//    be built and the reference's test-suite holds no golden W/d/H vectors
+//    (SURVEY.md §8c): the order of the reductions INSIDE Eigen (rankUpdate, gemv,
+//    LLT, dot) is this file's definition (below), which the stand-in shares.
+//  * Also pinned (tests/test_oracle_kats.py): the known-answer tests of
+//    tests/cpp/test_nnls.cpp, test_gram.cpp, test_rng.cpp, the published
+//    SplitMix64 vectors, and frozen outputs on the reference's movielens matrix.
 //
 // Arithmetic conventions of this restatement (documented in DESIGN.md §3):
 //  * fp32 everywhere the reference is fp32; compiled with -ffp-contract=off

@@ -1,0 +1,136 @@
+// C entry points over the REFERENCE'S OWN hot-path headers, compiled from /root/reference where they lie against the
+// minimal Eigen stand-in in shim/ (Eigen itself is not in this image). TEST INFRASTRUCTURE ONLY: the library is
+// built into oracle/_ref/ (git-ignored) and loaded by tests/test_reference_sources.py, which holds the oracle's
+// restatement (oracle/nmf_oracle.cpp) against it bit for bit.
+//
+//   make -C oracle ref_hotpath
+//
+// Reference sources compiled here (nothing is copied into this repository):
+//   inst/include/FactorNet/rng/rng.hpp                      SplitMix64, uniform, hash, is_holdout, fill_uniform
+//   inst/include/FactorNet/primitives/cpu/nnls_batch.hpp     cd_nnls_col_fixed, nnls_batch<CPU,float|double>
+//   inst/include/FactorNet/primitives/cpu/fused_nnls.hpp     fused_rhs_nnls_sparse, fused_rhs_cholesky_sparse,
+//                                                            loss_cross_term_sparse_via_At
+//   inst/include/FactorNet/primitives/cpu/cholesky_clip.hpp  cholesky_clip_col
+//   inst/include/FactorNet/primitives/cpu/gram.hpp           gram<CPU,float|double>
+//   inst/include/FactorNet/primitives/primitives.hpp         trace_AtA
+//   inst/include/FactorNet/core/constants.hpp                tiny_num, CD_TOL, CD_MAXIT, CD_ABS_TOL, NMF_PATIENCE
+#ifndef FACTORNET_HOST_DEVICE
+#define FACTORNET_HOST_DEVICE
+#endif
+#include <Eigen/Dense>
+#include <Eigen/Sparse>
+namespace Eigen { template <class D> struct DenseBase; }   // named by a fill_uniform overload that is never instantiated
+
+#include <FactorNet/rng/rng.hpp>
+#include <FactorNet/primitives/cpu/gram.hpp>
+#include <FactorNet/primitives/cpu/fused_nnls.hpp>
+
+#include <cstdint>
+#include <cstring>
+
+using namespace FactorNet;
+using FactorNet::primitives::CPU;
+using SpF = Eigen::SparseMatrix<float, Eigen::ColMajor, int>;
+
+template <class S>
+static DenseMatrix<S> dense_from(const S* p, long rows, long cols) {
+    DenseMatrix<S> M(rows, cols);
+    std::memcpy(M.data(), p, sizeof(S) * static_cast<size_t>(rows * cols));
+    return M;
+}
+
+extern "C" {
+
+// ---- rng/rng.hpp
+void ref_splitmix_next(uint64_t seed, int count, uint64_t* out) {
+    rng::SplitMix64 g(seed);
+    for (int i = 0; i < count; ++i) out[i] = g.next();
+}
+uint64_t ref_splitmix_hash(uint64_t seed, uint32_t i, uint32_t j) { return rng::SplitMix64::hash(seed, i, j); }
+int ref_is_holdout(uint64_t seed, uint32_t i, uint32_t j, uint64_t inv_prob) { return rng::SplitMix64::is_holdout(seed, i, j, inv_prob) ? 1 : 0; }
+void ref_fill_uniform_f32(uint64_t seed, float* data, int rows, int cols) { rng::SplitMix64 g(seed); g.fill_uniform(data, rows, cols); }
+void ref_fill_uniform_f64(uint64_t seed, double* data, int rows, int cols) { rng::SplitMix64 g(seed); g.fill_uniform(data, rows, cols); }
+// nmf/nmf_init.hpp:173-181 draws W_T (k x m) then H (k x n) from ONE stream — two fill_uniform calls on one generator
+void ref_init_factors_f32(uint64_t seed, int k, int m, int n, float* W_T, float* H) {
+    rng::SplitMix64 g(seed);
+    g.fill_uniform(W_T, k, m);
+    g.fill_uniform(H, k, n);
+}
+
+// ---- core/constants.hpp
+void ref_constants(double* out) {
+    out[0] = static_cast<double>(tiny_num<float>());
+    out[1] = tiny_num<double>();
+    out[2] = CD_TOL;
+    out[3] = static_cast<double>(CD_MAXIT);
+    out[4] = CD_ABS_TOL;
+    out[5] = static_cast<double>(NMF_PATIENCE);
+}
+
+// ---- primitives/cpu/nnls_batch.hpp
+int ref_cd_nnls_col_fixed_f32(const float* G, float* b, float* x, int k, float L1, float L2, int nonneg, int maxit,
+                              float ub, float cd_tol) {
+    const DenseMatrix<float> Gm = dense_from(G, k, k);
+    return primitives::detail::cd_nnls_col_fixed<float>(Gm, b, x, k, L1, L2, nonneg != 0, maxit, ub, cd_tol);
+}
+int ref_cd_nnls_col_fixed_f64(const double* G, double* b, double* x, int k, double L1, double L2, int nonneg, int maxit,
+                              double ub, double cd_tol) {
+    const DenseMatrix<double> Gm = dense_from(G, k, k);
+    return primitives::detail::cd_nnls_col_fixed<double>(Gm, b, x, k, L1, L2, nonneg != 0, maxit, ub, cd_tol);
+}
+void ref_nnls_batch_f64(const double* G, double* B, double* X, int k, long n, int cd_maxit, double cd_tol, double L1,
+                        double L2, int nonneg, double ub, int warm_start) {
+    const DenseMatrix<double> Gm = dense_from(G, k, k);
+    DenseMatrix<double> Bm = dense_from(B, k, n), Xm = dense_from(X, k, n);
+    primitives::nnls_batch<CPU, double>(Gm, Bm, Xm, cd_maxit, cd_tol, L1, L2, nonneg != 0, 1, ub, warm_start != 0);
+    std::memcpy(B, Bm.data(), sizeof(double) * static_cast<size_t>(k) * n);
+    std::memcpy(X, Xm.data(), sizeof(double) * static_cast<size_t>(k) * n);
+}
+
+// ---- primitives/cpu/gram.hpp (F is k x ncols col-major)
+void ref_gram_f32(const float* F, int k, long ncols, float* G) {
+    const DenseMatrix<float> Fm = dense_from(F, k, ncols);
+    DenseMatrix<float> Gm;
+    primitives::gram<CPU, float>(Fm, Gm);
+    std::memcpy(G, Gm.data(), sizeof(float) * static_cast<size_t>(k) * k);
+}
+
+// ---- primitives/cpu/fused_nnls.hpp (A: CSC m x n; Factor k x m; X k x n, in/out)
+void ref_fused_rhs_nnls_sparse_f32(const int* Ap, const int* Ai, const float* Ax, long m, long n, const float* Factor,
+                                   const float* G, float* X, int k, int cd_maxit, float cd_tol, float L1, int nonneg,
+                                   int warm_start, float ub) {
+    const SpF A(m, n, Ap, Ai, Ax);
+    const DenseMatrix<float> Fm = dense_from(Factor, k, m), Gm = dense_from(G, k, k);
+    DenseMatrix<float> Xm = dense_from(X, k, n);
+    primitives::fused_rhs_nnls_sparse<SpF, float>(A, Fm, Gm, Xm, cd_maxit, cd_tol, L1, nonneg != 0, 1, warm_start != 0, ub);
+    std::memcpy(X, Xm.data(), sizeof(float) * static_cast<size_t>(k) * n);
+}
+void ref_fused_rhs_cholesky_sparse_f32(const int* Ap, const int* Ai, const float* Ax, long m, long n, const float* Factor,
+                                       const float* G, float* X, int k, int solver_mode, float L1, int nonneg, float ub) {
+    const SpF A(m, n, Ap, Ai, Ax);
+    const DenseMatrix<float> Fm = dense_from(Factor, k, m), Gm = dense_from(G, k, k);
+    DenseMatrix<float> Xm = dense_from(X, k, n);
+    primitives::fused_rhs_cholesky_sparse<SpF, float>(A, Fm, Gm, Xm, solver_mode, L1, nonneg != 0, 1, false, ub);
+    std::memcpy(X, Xm.data(), sizeof(float) * static_cast<size_t>(k) * n);
+}
+// At: CSC n x m (the transpose of A); W_T k x m; H k x n
+float ref_loss_cross_term_via_At_f32(const int* Atp, const int* Ati, const float* Atx, long n, long m, const float* W_T,
+                                     const float* H, const float* d, int k) {
+    const SpF At(n, m, Atp, Ati, Atx);
+    const DenseMatrix<float> Wm = dense_from(W_T, k, m), Hm = dense_from(H, k, n);
+    DenseVector<float> dv(k);
+    for (int i = 0; i < k; ++i) dv(i) = d[i];
+    return primitives::loss_cross_term_sparse_via_At<SpF, float>(At, Wm, Hm, dv, 1);
+}
+float ref_trace_AtA_f32(const int* Ap, const int* Ai, const float* Ax, long m, long n) {
+    const SpF A(m, n, Ap, Ai, Ax);
+    return primitives::trace_AtA<CPU, float>(A);
+}
+
+// ---- primitives/cpu/cholesky_clip.hpp
+void ref_cholesky_clip_col_f32(const float* G, float* b, float* x, int k, float L1, float L2, int nonneg, float ub) {
+    const DenseMatrix<float> Gm = dense_from(G, k, k);
+    primitives::detail::cholesky_clip_col<float>(Gm, b, x, k, L1, L2, nonneg != 0, 0, 0.f, ub);
+}
+
+}  // extern "C"
