@@ -14,6 +14,10 @@
 //   inst/include/FactorNet/primitives/cpu/gram.hpp           gram<CPU,float|double>
 //   inst/include/FactorNet/primitives/primitives.hpp         trace_AtA
 //   inst/include/FactorNet/core/constants.hpp                tiny_num, CD_TOL, CD_MAXIT, CD_ABS_TOL, NMF_PATIENCE
+//   inst/include/FactorNet/nmf/masked_nnls.hpp               masked_nnls_h / masked_nnls_w / masked_loss (+ core/config.hpp)
+//   inst/include/FactorNet/nmf/variant_helpers.hpp           extract_scaling
+//   inst/include/FactorNet/features/bounds.hpp               apply_upper_bound
+//   inst/include/FactorNet/nmf/speckled_cv.hpp               LazySpeckledMask (seed / inv_prob conventions)
 #ifndef FACTORNET_HOST_DEVICE
 #define FACTORNET_HOST_DEVICE
 #endif
@@ -21,9 +25,15 @@
 #include <Eigen/Sparse>
 namespace Eigen { template <class D> struct DenseBase; }   // named by a fill_uniform overload that is never instantiated
 
+namespace Eigen { template <class M> class SelfAdjointEigenSolver; }   // named by a projective-NMF helper, never instantiated
+
 #include <FactorNet/rng/rng.hpp>
 #include <FactorNet/primitives/cpu/gram.hpp>
 #include <FactorNet/primitives/cpu/fused_nnls.hpp>
+#include <FactorNet/features/bounds.hpp>
+#include <FactorNet/nmf/masked_nnls.hpp>
+#include <FactorNet/nmf/speckled_cv.hpp>
+#include <FactorNet/nmf/variant_helpers.hpp>
 
 #include <cstdint>
 #include <cstring>
@@ -131,6 +141,68 @@ float ref_trace_AtA_f32(const int* Ap, const int* Ai, const float* Ax, long m, l
 void ref_cholesky_clip_col_f32(const float* G, float* b, float* x, int k, float L1, float L2, int nonneg, float ub) {
     const DenseMatrix<float> Gm = dense_from(G, k, k);
     primitives::detail::cholesky_clip_col<float>(Gm, b, x, k, L1, L2, nonneg != 0, 0, 0.f, ub);
+}
+
+// ---- nmf/masked_nnls.hpp. A: CSC m x n; mask: CSC pattern m x n of the masked entries (values 1); F = W_T (k x m);
+//      X = H (k x n). The W half-step is the same call on the transposes (masked_nnls_w over At, mask_T).
+static NMFConfig<float> masked_cfg(float L1, float L2, int nonneg, int cd_maxit, float cd_tol, int solver_mode, bool for_w) {
+    NMFConfig<float> c;
+    c.cd_max_iter = cd_maxit; c.cd_tol = cd_tol; c.solver_mode = solver_mode;
+    auto& f = for_w ? c.W : c.H;
+    f.L1 = L1; f.L2 = L2; f.nonneg = nonneg != 0;
+    return c;
+}
+void ref_masked_nnls_h_f32(const int* Ap, const int* Ai, const float* Ax, long m, long n, const float* W_T, const float* G,
+                           float* H, int k, const int* Mp, const int* Mi, float L1, float L2, int nonneg, int cd_maxit,
+                           float cd_tol, int solver_mode, int warm_start) {
+    const SpF A(m, n, Ap, Ai, Ax);
+    std::vector<float> ones(static_cast<size_t>(Mp[n]) + 1, 1.f);
+    const SpF M(m, n, Mp, Mi, ones.data());
+    const DenseMatrix<float> Wm = dense_from(W_T, k, m), Gm = dense_from(G, k, k);
+    DenseMatrix<float> Hm = dense_from(H, k, n);
+    nmf::mask_detail::masked_nnls_h<float, SpF>(A, Wm, Gm, Hm, M, masked_cfg(L1, L2, nonneg, cd_maxit, cd_tol, solver_mode, false), 1, warm_start != 0);
+    std::memcpy(H, Hm.data(), sizeof(float) * static_cast<size_t>(k) * n);
+}
+void ref_masked_nnls_w_f32(const int* Atp, const int* Ati, const float* Atx, long n, long m, const float* H, const float* G,
+                           float* W_T, int k, const int* MTp, const int* MTi, float L1, float L2, int nonneg, int cd_maxit,
+                           float cd_tol, int solver_mode, int warm_start) {
+    const SpF At(n, m, Atp, Ati, Atx);
+    std::vector<float> ones(static_cast<size_t>(MTp[m]) + 1, 1.f);
+    const SpF MT(n, m, MTp, MTi, ones.data());
+    const DenseMatrix<float> Hm = dense_from(H, k, n), Gm = dense_from(G, k, k);
+    DenseMatrix<float> Wm = dense_from(W_T, k, m);
+    nmf::mask_detail::masked_nnls_w<float, SpF>(At, Hm, Gm, Wm, MT, masked_cfg(L1, L2, nonneg, cd_maxit, cd_tol, solver_mode, true), 1, warm_start != 0);
+    std::memcpy(W_T, Wm.data(), sizeof(float) * static_cast<size_t>(k) * m);
+}
+float ref_masked_loss_f32(const int* Ap, const int* Ai, const float* Ax, long m, long n, const float* W_Td, const float* H,
+                          int k, const int* Mp, const int* Mi) {
+    const SpF A(m, n, Ap, Ai, Ax);
+    std::vector<float> ones(static_cast<size_t>(Mp[n]) + 1, 1.f);
+    const SpF M(m, n, Mp, Mi, ones.data());
+    const DenseMatrix<float> Wm = dense_from(W_Td, k, m), Hm = dense_from(H, k, n);
+    LossConfig<float> lc{};
+    return nmf::mask_detail::masked_loss<float, SpF>(A, Wm, Hm, M, lc, 1);
+}
+
+// ---- nmf/variant_helpers.hpp:287-305 and features/bounds.hpp:38 (X is k x n col-major, in place)
+void ref_extract_scaling_f32(float* X, int k, long n, float* d, int norm_type) {
+    DenseMatrix<float> Xm = dense_from(X, k, n);
+    DenseVector<float> dv(k);
+    nmf::variant::extract_scaling<float>(Xm, dv, norm_type == 0 ? NormType::L1 : norm_type == 1 ? NormType::L2 : NormType::None);
+    std::memcpy(X, Xm.data(), sizeof(float) * static_cast<size_t>(k) * n);
+    for (int i = 0; i < k; ++i) d[i] = dv(i);
+}
+void ref_apply_upper_bound_f32(float* X, int k, long n, float ub) {
+    DenseMatrix<float> Xm = dense_from(X, k, n);
+    features::apply_upper_bound<float>(Xm, ub);
+    std::memcpy(X, Xm.data(), sizeof(float) * static_cast<size_t>(k) * n);
+}
+
+// ---- nmf/speckled_cv.hpp: LazySpeckledMask(n_rows, n_cols, nnz, holdout_fraction, seed, mask_zeros).is_holdout(i, j)
+void ref_speckled_mask_f32(int n_rows, int n_cols, double holdout_fraction, uint64_t seed, const int* ii, const int* jj,
+                           int count, int* out) {
+    nmf::LazySpeckledMask<float> mask(n_rows, n_cols, 0, holdout_fraction, seed, true);
+    for (int t = 0; t < count; ++t) out[t] = mask.is_holdout(ii[t], jj[t]) ? 1 : 0;
 }
 
 }  // extern "C"

@@ -1,7 +1,8 @@
 """CPU: the oracle's restatement against the REFERENCE'S OWN hot-path source.
 
 oracle/_ref/libref_hotpath.so is the reference's headers — rng/rng.hpp, primitives/cpu/{nnls_batch, fused_nnls,
-cholesky_clip, gram}.hpp, primitives/primitives.hpp, core/constants.hpp — compiled unmodified from /root/reference
+cholesky_clip, gram}.hpp, primitives/primitives.hpp, core/constants.hpp, nmf/masked_nnls.hpp (with core/config.hpp),
+nmf/variant_helpers.hpp, features/bounds.hpp, nmf/speckled_cv.hpp — compiled unmodified from /root/reference
 (`make -C oracle ref_hotpath`) against a minimal stand-in for the Eigen types they use (Eigen is not in this image).
 Everything the reference's source decides — the SplitMix64 generator and hash, the CD solver with its skip rules,
 clamps and convergence formula, where L1 / the warm-start correction / the clip / the upper bound sit in the fused
@@ -31,6 +32,7 @@ def ref():
     lib.ref_is_holdout.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64]
     lib.ref_loss_cross_term_via_At_f32.restype = C.c_float
     lib.ref_trace_AtA_f32.restype = C.c_float
+    lib.ref_masked_loss_f32.restype = C.c_float
     return lib
 
 
@@ -175,3 +177,92 @@ def test_loss_terms_match(ref, oracle):
                                             _p(W, C.c_float), _p(H, C.c_float), _p(d, C.c_float), k)
     c2 = oracle.loss_cross_term(Tp, Ti, Tx, W, H, d)
     assert abs(c1 - c2) <= 2e-5 * abs(c2), (c1, c2)
+
+
+def _mask_pattern(rng, m, n, frac):
+    import scipy.sparse as sp
+    M = sp.random(m, n, density=frac, format="csc", random_state=rng, dtype=np.float32)
+    M.data[:] = 1
+    M.sort_indices()
+    return M
+
+
+@pytest.mark.parametrize("k,solver", [(5, 0), (5, 1), (20, 0), (32, 1)])
+def test_masked_path_bit_exact(ref, oracle, k, solver):
+    """nmf/masked_nnls.hpp (explicit user mask): masked_nnls_h and masked_nnls_w — the per-column Gram downdate over the
+    masked rows, L1 on b and L2 on the local diagonal, cold / warm start, CD or the per-column LLT — bit for bit;
+    masked_loss to fp32 accumulation error (the reference sums in fp32, the oracle in fp64)."""
+    m, n = 160, 90
+    rng = np.random.default_rng(100 + k)
+    A = random_csc(m, n, 0.12, 70 + k, ragged=True)
+    M = _mask_pattern(rng, m, n, 0.05)
+    Ap, Ai, Ax = A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data.astype(np.float32)
+    Mp, Mi = M.indptr.astype(np.int32), M.indices.astype(np.int32)
+    W = rng.random((m, k)).astype(np.float32)
+    H0 = rng.random((n, k)).astype(np.float32)
+    G = oracle.gram(W)
+    for warm in (False, True):
+        H1, H2 = H0.copy(), H0.copy()
+        ref.ref_masked_nnls_h_f32(_p(Ap, C.c_int), _p(Ai, C.c_int), _p(Ax, C.c_float), C.c_long(m), C.c_long(n),
+                                  _p(W, C.c_float), _p(G, C.c_float), _p(H1, C.c_float), k, _p(Mp, C.c_int), _p(Mi, C.c_int),
+                                  C.c_float(0.01), C.c_float(0.02), 1, 25, C.c_float(1e-8), solver, int(warm))
+        oracle.masked_nnls(Ap, Ai, Ax, m, W, G, H2, Mp, Mi, L1=0.01, L2=0.02, nonneg=True, cd_maxit=25, cd_tol=1e-8,
+                           solver_mode=solver, warm_start=warm)
+        assert np.array_equal(H1, H2), (k, solver, warm)
+    # W half-step: the same kernel on the transposes
+    Tp, Ti, Tx = oracle.transpose_csc(Ap, Ai, Ax, m, n)
+    MT = M.T.tocsc()
+    MT.sort_indices()
+    MTp, MTi = MT.indptr.astype(np.int32), MT.indices.astype(np.int32)
+    Gh = oracle.gram(H0)
+    W1, W2 = W.copy(), W.copy()
+    ref.ref_masked_nnls_w_f32(_p(Tp, C.c_int), _p(Ti, C.c_int), _p(Tx, C.c_float), C.c_long(n), C.c_long(m),
+                              _p(H0, C.c_float), _p(Gh, C.c_float), _p(W1, C.c_float), k, _p(MTp, C.c_int), _p(MTi, C.c_int),
+                              C.c_float(0.0), C.c_float(0.01), 1, 25, C.c_float(1e-8), solver, 1)
+    oracle.masked_nnls(Tp, Ti, Tx, n, H0, Gh, W2, MTp, MTi, L1=0.0, L2=0.01, nonneg=True, cd_maxit=25, cd_tol=1e-8,
+                       solver_mode=solver, warm_start=True)
+    assert np.array_equal(W1, W2), (k, solver)
+    # masked loss through a full masked fit of the oracle (one iteration): compare its loss with the reference's sum
+    d = rng.random(k).astype(np.float32)
+    WTd = (W * d).astype(np.float32)
+    l_ref = ref.ref_masked_loss_f32(_p(Ap, C.c_int), _p(Ai, C.c_int), _p(Ax, C.c_float), C.c_long(m), C.c_long(n),
+                                    _p(WTd, C.c_float), _p(H0, C.c_float), k, _p(Mp, C.c_int), _p(Mi, C.c_int))
+    mask_dense = M.toarray() != 0
+    pred = WTd.astype(np.float64) @ H0.astype(np.float64).T
+    Ad = A.toarray()
+    sel = (Ad != 0) & ~mask_dense
+    want = float(((Ad - pred)[sel] ** 2).sum())
+    assert abs(l_ref - want) <= 1e-4 * want, (l_ref, want)
+
+
+def test_extract_scaling_and_bounds_bit_exact(ref, oracle):
+    rng = np.random.default_rng(8)
+    for k, n in ((6, 200), (20, 1000), (64, 77)):
+        X0 = (rng.random((n, k)) * (rng.random((n, k)) < 0.6)).astype(np.float32)
+        for norm_type in (0, 1, 2):
+            X1, X2 = X0.copy(), X0.copy()
+            d1 = np.zeros(k, np.float32)
+            ref.ref_extract_scaling_f32(_p(X1, C.c_float), k, C.c_long(n), _p(d1, C.c_float), norm_type)
+            d2 = oracle.extract_scaling(X2, norm_type)
+            assert np.array_equal(d1, d2) and np.array_equal(X1, X2), (k, norm_type)
+        X1 = X0.copy()
+        ref.ref_apply_upper_bound_f32(_p(X1, C.c_float), k, C.c_long(n), C.c_float(0.3))
+        assert np.array_equal(X1, np.minimum(X0, np.float32(0.3)))
+
+
+def test_speckled_mask_conventions(ref, oracle):
+    """LazySpeckledMask: the seed is truncated to 32 bits with 0 -> 12345, inv_prob = uint64(1 / double(fraction)) — the
+    reference passes the FLOAT fraction, so 0.1f gives 9 (11.1 % held out), 0.25f gives 4, 0.2f gives 4 (not 5)."""
+    rng = np.random.default_rng(5)
+    ii = rng.integers(0, 50000, 4000).astype(np.int32)
+    jj = rng.integers(0, 9000, 4000).astype(np.int32)
+    for frac, inv in ((0.1, 9), (0.25, 4), (0.2, 4), (0.05, 19), (0.5, 2)):
+        for seed in (0, 42, 2**32 + 7, 2**32):
+            out = np.zeros(4000, np.int32)
+            ref.ref_speckled_mask_f32(50000, 9000, C.c_double(float(np.float32(frac))), C.c_uint64(seed),
+                                      _p(ii, C.c_int), _p(jj, C.c_int), 4000, _p(out, C.c_int))
+            s32 = seed & 0xFFFFFFFF
+            eff = 12345 if s32 == 0 else s32
+            want = np.array([oracle.is_holdout(eff, int(i), int(j), inv) for i, j in zip(ii, jj)], dtype=np.int32)
+            assert np.array_equal(out, want), (frac, seed)
+            assert 0.5 / inv < out.mean() < 1.5 / inv
