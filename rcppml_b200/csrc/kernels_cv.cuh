@@ -55,12 +55,12 @@ struct CvParams {
 };
 
 template <int KP>
-__global__ void __launch_bounds__(256) cv_half_step_kernel(const CvParams p) {   // blockDim = WARPS*32
+__global__ void __launch_bounds__(384, 1) cv_half_step_kernel(const CvParams p) {   // blockDim = WARPS*32
     constexpr int NC = (KP + 31) / 32;
     constexpr int LD = KP + 1;
-    constexpr int WARPS = (KP <= 64) ? 8 : 3;
+    constexpr int WARPS = (KP <= 64) ? 12 : 3;      // 12 x 16.9 KB of per-warp Gram copies at k = 64 (one CTA per SM)
     extern __shared__ __align__(16) float smem[];
-    __shared__ double sred[8][KP + 1];
+    __shared__ double sred[12][KP + 1];
     if (p.state->stop) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* Gl = smem + static_cast<size_t>(warp) * (KP * LD + KP);
@@ -109,8 +109,10 @@ __global__ void __launch_bounds__(256) cv_half_step_kernel(const CvParams p) {  
                 for (int t = 0; t < cnt; ++t) {
                     const int rt = __shfl_sync(0xffffffffu, r, t);
                     const float vt = __shfl_sync(0xffffffffu, v, t);
-                    if ((hb >> t) & 1u) warp_rank1_downdate<KP>(Gl, sf, p.F + static_cast<size_t>(rt) * KP, k, lane);
-                    else accumulate(b, vt, rt);
+                    if ((hb >> t) & 1u) {
+                        if (p.solver == 1) warp_rank1_downdate_lower<KP>(Gl, sf, p.F + static_cast<size_t>(rt) * KP, k, lane);
+                        else warp_rank1_downdate<KP>(Gl, sf, p.F + static_cast<size_t>(rt) * KP, k, lane);
+                    } else accumulate(b, vt, rt);
                 }
             }
         } else {                                                    // every (row, column) cell is hashed
@@ -127,7 +129,8 @@ __global__ void __launch_bounds__(256) cv_half_step_kernel(const CvParams p) {  
                     if (row == 0x7fffffff) break;
                     const bool is_h = (row == nh);
                     if (is_h) {
-                        warp_rank1_downdate<KP>(Gl, sf, p.F + static_cast<size_t>(row) * KP, k, lane);
+                        if (p.solver == 1) warp_rank1_downdate_lower<KP>(Gl, sf, p.F + static_cast<size_t>(row) * KP, k, lane);
+                        else warp_rank1_downdate<KP>(Gl, sf, p.F + static_cast<size_t>(row) * KP, k, lane);
                         rest &= rest - 1;
                         if (row == nz) ++e;                         // held-out non-zero: skipped in b
                     } else {

@@ -63,21 +63,32 @@ __device__ __forceinline__ int warp_cd_solve(const float* Gl, float (&b)[(KP + 3
     return maxit;
 }
 
-// Eigen::LLT restated (oracle order): in-place left-looking factorisation of Gl, then x := L⁻ᵀ L⁻¹ b by
-// column-oriented substitution with IEEE division. b holds the rhs on entry and x on exit. Returns the
-// first non-positive pivot index + 1 (0 = ok).
+// Eigen::LLT restated (oracle order): L(i,j) = (G(i,j) − t_ij) / L(j,j), t_ij = Σ_{p<j} L(i,p)·L(j,p) accumulated
+// sequentially in p (separately rounded mul and add), L(j,j) = sqrt(G(j,j) − t_jj); then x := L⁻ᵀ L⁻¹ b by
+// column-oriented substitution with IEEE division. b holds the rhs on entry and x on exit. Returns the first
+// non-positive pivot index + 1 (0 = ok).
+// The dots are kept as RUNNING sums (like prepare_solver_kernel): finished column j adds L(i,j)·L(c,j) to T(i,c) for
+// every pair j < c <= i at once — the same additions in the same order as the left-looking loop, but the k³/6
+// updates are independent of each other instead of forming k²/2 dependent chains of length j (the left-looking
+// form made a warp wait ~130 K cycles per column on those chains). Only the lower triangle of Gl is read by the
+// factorisation and the substitutions, so T lives in the unused upper triangle: T(i,c), i > c, at Gl[i*LD + c];
+// T(c,c) in the padding row, Gl[c*LD + KP].
 template <int KP>
 __device__ __forceinline__ int warp_chol_solve(float* Gl, float (&b)[(KP + 31) / 32], int k, int lane) {
     constexpr int NC = (KP + 31) / 32;
     constexpr int LD = KP + 1;
     int fail = 0;
-    for (int jj = 0; jj < k; ++jj) {
-        float s = 0.f;
-        for (int pp = 0; pp < jj; ++pp) {
-            const float l = Gl[pp * LD + jj];
-            s = __fadd_rn(s, __fmul_rn(l, l));
+    for (int c = 0; c < k; ++c) {                                   // T = 0
+#pragma unroll
+        for (int t = 0; t < NC; ++t) {
+            const int i = lane + 32 * t;
+            if (i > c && i < k) Gl[i * LD + c] = 0.f;
+            else if (i == c) Gl[c * LD + KP] = 0.f;
         }
-        const float xx = __fsub_rn(Gl[jj * LD + jj], s);
+    }
+    __syncwarp();
+    for (int jj = 0; jj < k; ++jj) {
+        const float xx = __fsub_rn(Gl[jj * LD + jj], Gl[jj * LD + KP]);
         float ljj = 0.f;
         if (!(xx > 0.f)) { if (!fail) fail = jj + 1; } else ljj = __fsqrt_rn(xx);
         float lij[NC];
@@ -85,20 +96,29 @@ __device__ __forceinline__ int warp_chol_solve(float* Gl, float (&b)[(KP + 31) /
         for (int t = 0; t < NC; ++t) {
             const int i = lane + 32 * t;
             lij[t] = 0.f;
-            if (i > jj && i < k) {
-                float tt = 0.f;
-                for (int pp = 0; pp < jj; ++pp) tt = __fadd_rn(tt, __fmul_rn(Gl[pp * LD + i], Gl[pp * LD + jj]));
-                lij[t] = __fdiv_rn(__fsub_rn(Gl[jj * LD + i], tt), ljj);
-            }
+            if (i > jj && i < k) lij[t] = __fdiv_rn(__fsub_rn(Gl[jj * LD + i], Gl[i * LD + jj]), ljj);
         }
-        __syncwarp();
+        __syncwarp();                                               // every lane has read G(jj,jj)
 #pragma unroll
         for (int t = 0; t < NC; ++t) {
             const int i = lane + 32 * t;
             if (i > jj && i < k) Gl[jj * LD + i] = lij[t];
-            if (i == jj) Gl[jj * LD + jj] = ljj;
+            if (i == jj) { Gl[jj * LD + jj] = ljj; lij[t] = ljj; }
         }
-        __syncwarp();
+        __syncwarp();                                               // L(:, jj) visible
+        for (int c = jj + 1; c < k; ++c) {                          // T(i,c) += L(i,jj)·L(c,jj), c <= i
+            const float lc = Gl[jj * LD + c];
+#pragma unroll
+            for (int t = 0; t < NC; ++t) {
+                if (32 * t + 31 < c) continue;                      // warp-uniform: no row of this pass reaches c
+                const int i = lane + 32 * t;
+                if (i >= c && i < k) {
+                    float* tp = (i == c) ? (Gl + c * LD + KP) : (Gl + i * LD + c);
+                    *tp = __fadd_rn(*tp, __fmul_rn(lij[t], lc));
+                }
+            }
+        }
+        __syncwarp();                                               // T(jj+1, jj+1) visible to every lane
     }
     for (int pp = 0; pp < k; ++pp) {
         const int owner = pp & 31, slot = pp >> 5;
@@ -148,6 +168,30 @@ __device__ __forceinline__ void warp_rank1_downdate(float* Gl, float* sf, const 
     __syncwarp();
 }
 
+// The same downdate restricted to the lower triangle (rows >= column) — all a per-column LLT reads
+// (cv_detail.hpp:80-84 updates the Lower view and mirrors it). Same products, same roundings.
+template <int KP>
+__device__ __forceinline__ void warp_rank1_downdate_lower(float* Gl, float* sf, const float* __restrict__ f, int k, int lane) {
+    constexpr int NC = (KP + 31) / 32;
+    constexpr int LD = KP + 1;
+    __syncwarp();
+    for (int c = lane; c < KP; c += 32) sf[c] = __ldg(f + c);
+    __syncwarp();
+    float fr[NC];
+#pragma unroll
+    for (int t = 0; t < NC; ++t) fr[t] = (lane + 32 * t < KP) ? sf[lane + 32 * t] : 0.f;
+    for (int col = 0; col < k; ++col) {
+        const float fc = sf[col];
+#pragma unroll
+        for (int t = 0; t < NC; ++t) {
+            if (32 * t + 31 < col) continue;
+            const int row = lane + 32 * t;
+            if (row >= col && row < k) Gl[col * LD + row] = __fsub_rn(Gl[col * LD + row], __fmul_rn(fr[t], fc));
+        }
+    }
+    __syncwarp();
+}
+
 struct MaskedParams {
     const int* __restrict__ colptr;    // sparse operand (A or Aᵀ), CSC
     const int* __restrict__ rowidx;
@@ -172,10 +216,10 @@ struct MaskedParams {
 };
 
 template <int KP>
-__global__ void __launch_bounds__(256) masked_half_step_kernel(const MaskedParams p) {   // blockDim = WARPS*32
+__global__ void __launch_bounds__(384, 1) masked_half_step_kernel(const MaskedParams p) {   // blockDim = WARPS*32
     constexpr int NC = (KP + 31) / 32;            // coordinates per lane
     constexpr int LD = KP + 1;                     // padded leading dimension: row reads are conflict-free
-    constexpr int WARPS = (KP <= 64) ? 8 : 3;
+    constexpr int WARPS = (KP <= 64) ? 12 : 3;      // 12 x 16.9 KB of per-warp Gram copies at k = 64 (one CTA per SM)
     extern __shared__ __align__(16) float smem[];
     if (p.state->stop) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -218,7 +262,8 @@ __global__ void __launch_bounds__(256) masked_half_step_kernel(const MaskedParam
         for (int e = lane; e < KP * KP; e += 32) Gl[(e / KP) * LD + (e % KP)] = p.G[e];
         __syncwarp();
         for (int e = mb; e < me; ++e)
-            warp_rank1_downdate<KP>(Gl, sf, p.F + static_cast<size_t>(__ldg(p.midx + e)) * KP, k, lane);
+            if (p.solver == 0) warp_rank1_downdate<KP>(Gl, sf, p.F + static_cast<size_t>(__ldg(p.midx + e)) * KP, k, lane);
+            else warp_rank1_downdate_lower<KP>(Gl, sf, p.F + static_cast<size_t>(__ldg(p.midx + e)) * KP, k, lane);
         // ---- L1 / L2 (masked_nnls.hpp:141-144): unconditional, like the reference
 #pragma unroll
         for (int t = 0; t < NC; ++t) {
@@ -265,7 +310,7 @@ __global__ void __launch_bounds__(256) masked_half_step_kernel(const MaskedParam
         }
     }
     // per-CTA partial row sums in a fixed order
-    __shared__ double sred[8][KP];
+    __shared__ double sred[12][KP];
 #pragma unroll
     for (int t = 0; t < NC; ++t) {
         const int c = lane + 32 * t;
@@ -283,7 +328,7 @@ __global__ void __launch_bounds__(256) masked_half_step_kernel(const MaskedParam
 }
 
 template <int KP>
-inline int masked_warps() { return (KP <= 64) ? 8 : 3; }
+inline int masked_warps() { return (KP <= 64) ? 12 : 3; }
 template <int KP>
 inline size_t masked_smem_bytes() {
     return static_cast<size_t>(masked_warps<KP>()) * (KP * (KP + 1) + KP) * sizeof(float);
