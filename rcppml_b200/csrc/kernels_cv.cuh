@@ -106,13 +106,36 @@ __global__ void __launch_bounds__(384, 1) cv_half_step_kernel(const CvParams p) 
                 if (e < p1) { r = __ldg(p.rowidx + e); v = __ldg(p.vals + e); h = held(r, j); }
                 const unsigned hb = __ballot_sync(0xffffffffu, h);
                 const int cnt = min(32, p1 - e0);
-                for (int t = 0; t < cnt; ++t) {
-                    const int rt = __shfl_sync(0xffffffffu, r, t);
-                    const float vt = __shfl_sync(0xffffffffu, v, t);
-                    if ((hb >> t) & 1u) {
-                        if (p.solver == 1) warp_rank1_downdate_lower<KP>(Gl, sf, p.F + static_cast<size_t>(rt) * KP, k, lane);
-                        else warp_rank1_downdate<KP>(Gl, sf, p.F + static_cast<size_t>(rt) * KP, k, lane);
-                    } else accumulate(b, vt, rt);
+                // The factor rows of 8 entries are requested together before any of them is consumed: a train
+                // entry and a held-out entry both need their row, and one L2 round trip per entry, taken one
+                // after the other, was what a column spent most of its time on.
+                constexpr int PF = 8;
+                for (int t0 = 0; t0 < cnt; t0 += PF) {
+                    float fr[PF][NC];
+#pragma unroll
+                    for (int u = 0; u < PF; ++u) {
+                        const int rt = __shfl_sync(0xffffffffu, r, (t0 + u) & 31);
+                        const float* f = p.F + static_cast<size_t>(rt) * KP;
+#pragma unroll
+                        for (int t = 0; t < NC; ++t) {
+                            const int c = lane + 32 * t;
+                            fr[u][t] = (t0 + u < cnt && c < KP) ? __ldg(f + c) : 0.f;
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < PF; ++u) {
+                        if (t0 + u >= cnt) break;
+                        const float vt = __shfl_sync(0xffffffffu, v, t0 + u);
+                        if ((hb >> (t0 + u)) & 1u) {
+                            warp_stage_row<KP>(sf, fr[u], lane);
+                            if (p.solver == 1) warp_rank1_downdate_staged<KP, true>(Gl, sf, fr[u], k, lane);
+                            else warp_rank1_downdate_staged<KP, false>(Gl, sf, fr[u], k, lane);
+                        } else {
+#pragma unroll
+                            for (int t = 0; t < NC; ++t)
+                                if (lane + 32 * t < KP) b[t] = __fadd_rn(b[t], __fmul_rn(vt, fr[u][t]));
+                        }
+                    }
                 }
             }
         } else {                                                    // every (row, column) cell is hashed

@@ -168,6 +168,32 @@ __device__ __forceinline__ void warp_rank1_downdate(float* Gl, float* sf, const 
     __syncwarp();
 }
 
+// Stage a factor row that is already in registers (a lane holds coordinates lane, lane+32, ...) into sf.
+template <int KP>
+__device__ __forceinline__ void warp_stage_row(float* sf, const float (&fr)[(KP + 31) / 32], int lane) {
+    constexpr int NC = (KP + 31) / 32;
+    __syncwarp();
+#pragma unroll
+    for (int t = 0; t < NC; ++t) if (lane + 32 * t < KP) sf[lane + 32 * t] = fr[t];
+    __syncwarp();
+}
+// Gl -= f fᵀ with f already staged in sf (full square / lower triangle only).
+template <int KP, bool LOWER>
+__device__ __forceinline__ void warp_rank1_downdate_staged(float* Gl, const float* sf, const float (&fr)[(KP + 31) / 32], int k, int lane) {
+    constexpr int NC = (KP + 31) / 32;
+    constexpr int LD = KP + 1;
+    for (int col = 0; col < k; ++col) {
+        const float fc = sf[col];
+#pragma unroll
+        for (int t = 0; t < NC; ++t) {
+            if (LOWER && 32 * t + 31 < col) continue;
+            const int row = lane + 32 * t;
+            if (row < k && (!LOWER || row >= col)) Gl[col * LD + row] = __fsub_rn(Gl[col * LD + row], __fmul_rn(fr[t], fc));
+        }
+    }
+    __syncwarp();
+}
+
 // The same downdate restricted to the lower triangle (rows >= column) — all a per-column LLT reads
 // (cv_detail.hpp:80-84 updates the Lower view and mirrors it). Same products, same roundings.
 template <int KP>
