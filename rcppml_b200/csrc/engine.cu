@@ -812,7 +812,7 @@ HalfStepParams Engine::solve_params(int which, bool warm) const {
     p.F = h ? W_T.ptr : H.ptr;                          // full (replicated) factor being gathered
     p.X = h ? H.ptr : W_T.ptr;                          // full factor being solved; this rank owns a block of it
     p.M1 = M1.ptr; p.M2 = M2.ptr; p.dblk = dblk.ptr; p.rcp = dblk.ptr + kMaxKP * 4; p.cslot = const_slot;
-    p.B = nullptr; p.nslots = 0; p.slot_stride = 0; p.b_local_index = 0;
+    p.B = nullptr;
     p.ncols = h ? n_loc : m_loc;
     p.col_offset = h ? col_begin : row_begin;
     p.k = k;

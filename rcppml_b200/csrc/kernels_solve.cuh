@@ -19,7 +19,7 @@
 namespace b200 {
 
 enum : int { SOLVER_CD = 0, SOLVER_CHOL = 1 };
-enum : int { BSRC_GATHER = 0, BSRC_LOAD = 1 };
+enum : int { BSRC_GATHER = 0 };   // right-hand sides are always gathered in-kernel (an exchanged-RHS variant existed once)
 enum : int { OUT_SOLVE = 0, OUT_RHS = 1 };
 
 struct HalfStepParams {
@@ -35,10 +35,8 @@ struct HalfStepParams {
     const float* __restrict__ M2;      // CHOL: LTz[p*KP+i] = L(p,i) for i<p
     const float* __restrict__ dblk;    // [KP/4][4][4] diagonal blocks (CD: of G; CHOL: of L incl. diagonal)
     const float* __restrict__ rcp;     // [KP] RN(1/diag) (0 where the diagonal is <= 0)
-    // BSRC_LOAD / OUT_RHS: dense right-hand sides [nslots][ncols][KP]
+    // OUT_RHS without a carry buffer: raw right-hand sides [ncols][KP] (diagnostics)
     float* __restrict__ B;
-    int nslots;
-    long long slot_stride;
     int ncols;
     int col_offset;                    // X row of local column 0 (this rank's block of the replicated factor)
     int k;
@@ -54,7 +52,6 @@ struct HalfStepParams {
     int cols_per_fetch;
     int* work_counter;
     double* partials;                  // [gridDim.x][KP+1]: Σ|x| (or Σx²) per coordinate, then <x, b_raw>
-    int b_local_index;                 // BSRC_LOAD: B is indexed by the local column (row-block solves)
     const int* stop_flag;
     unsigned long long* sweep_counter; // optional: total CD sweeps (diagnostics)
     // Sharded runs with peer-mapped factors: every solved column is ALSO stored straight into the replicas of
@@ -472,8 +469,7 @@ __device__ __forceinline__ void chol_solve(const float* sLz, const float* sLTz, 
 // ---------------------------------------------------------------------------------------------
 // The kernel. Persistent CTAs; a warp pulls batches of columns from a global counter; each
 // LANES-wide lane group handles one column at a time.
-//   BSRC_GATHER: b gathered from the CSC operand (single-GPU fused path)
-//   BSRC_LOAD  : b = Σ_slots B[slot][col] in slot order (multi-GPU: partial RHS from every rank)
+//   BSRC_GATHER: b gathered from the CSC operand
 //   OUT_SOLVE  : solve and write X;  OUT_RHS: write the raw gathered b to B[0] (partial RHS)
 // ---------------------------------------------------------------------------------------------
 #ifndef B200_SOLVE_MIN_CTAS
@@ -483,6 +479,7 @@ template <int LANES, int NV, int SOLVER, int BSRC, int OUT>
 __global__ void __launch_bounds__(256, (NV >= 4) ? 2 : B200_SOLVE_MIN_CTAS) half_step_kernel(const HalfStepParams p) {
     constexpr int KP = LANES * 4 * NV;
     constexpr int GPW = 32 / LANES;   // groups per warp
+    static_assert(BSRC == BSRC_GATHER, "right-hand sides are gathered in-kernel");
     extern __shared__ __align__(16) float smem[];
     if (*p.stop_flag) return;
 
@@ -549,24 +546,6 @@ __global__ void __launch_bounds__(256, (NV >= 4) ? 2 : B200_SOLVE_MIN_CTAS) half
                         for (int e = 0; e < 4; ++e) b[nv][e] = 0.f;
                 }
                 gather_column<LANES, NV>(p, p0, p1, gl, gmask, b);
-            } else {
-                const int jb = p.b_local_index ? jl : j;
-#pragma unroll
-                for (int nv = 0; nv < NV; ++nv) {
-                    const float4 v0 = *reinterpret_cast<const float4*>(p.B + static_cast<size_t>(jb) * KP +
-                                                                       (nv * LANES + gl) * 4);
-                    b[nv][0] = v0.x; b[nv][1] = v0.y; b[nv][2] = v0.z; b[nv][3] = v0.w;
-                }
-                for (int s = 1; s < p.nslots; ++s) {   // fixed slot (rank) order -> deterministic sum
-#pragma unroll
-                    for (int nv = 0; nv < NV; ++nv) {
-                        const float4 v = *reinterpret_cast<const float4*>(
-                            p.B + static_cast<size_t>(s) * p.slot_stride + static_cast<size_t>(jb) * KP +
-                            (nv * LANES + gl) * 4);
-                        b[nv][0] = __fadd_rn(b[nv][0], v.x); b[nv][1] = __fadd_rn(b[nv][1], v.y);
-                        b[nv][2] = __fadd_rn(b[nv][2], v.z); b[nv][3] = __fadd_rn(b[nv][3], v.w);
-                    }
-                }
             }
 
             if (OUT == OUT_RHS) {                   // row-panel pass (carry) or raw right-hand side (B)
