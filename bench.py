@@ -182,6 +182,38 @@ def run_cpu_reference(args, steps, warmup, budget_s):
             "iters_per_sec": timed / secs, "ms_per_step": 1e3 * secs / timed, "steps": timed, "nnz": nnz_s}
 
 
+def cpu_reference_native_row(args, budget_s):
+    """SURVEY.md §8d asks for a second, labelled CPU row: the same restatement built with -O3 -march=native (the
+    package itself builds with plain -O2, no -march: src/Makevars:6). Built ON THIS BOX (a -march=native object from
+    the build container may not run here) and timed in a child process, so that nothing it does — a failed build,
+    an illegal instruction — can take the bench line down. Returns a dict or None."""
+    import shutil
+    tmp = tempfile.mkdtemp(prefix="oracle_native_")
+    try:
+        so = os.path.join(tmp, "liboracle_native.so")
+        cc = ["/usr/bin/g++", "-std=c++17", "-O3", "-march=native", "-fopenmp", "-ffp-contract=off", "-fPIC", "-shared",
+              "-o", so, os.path.join(ROOT, "oracle", "nmf_oracle.cpp")]
+        if subprocess.run(cc, capture_output=True, timeout=120).returncode != 0:
+            return None
+        code = ("import json,sys; sys.argv=['bench.py','--m','%d','--n','%d','--density','%r','--k','%d','--solver','%s'];"
+                "sys.path.insert(0,%r); import bench; a=bench.parse_args();"
+                "r=bench.run_cpu_reference(a, steps=3, warmup=1, budget_s=%r); print('NATIVE_ROW '+json.dumps(r))"
+                % (args.m, args.n, args.density, args.k, args.solver, ROOT, budget_s))
+        env = dict(os.environ, RCPPML_ORACLE_LIB=so)
+        out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env)
+        for ln in out.stdout.splitlines():
+            if ln.startswith("NATIVE_ROW "):
+                r = json.loads(ln[len("NATIVE_ROW "):])
+                return {"value": r["value"], "unit": "nnz/s", "cores": r["cores"], "iters_per_sec": r["iters_per_sec"],
+                        "flags": "-O3 -march=native -fopenmp -ffp-contract=off (built on this box)",
+                        "sample": r["sample"].replace("-O2 -fopenmp", "-O3 -march=native -fopenmp")}
+        return None
+    except Exception:
+        return None
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def print_reference_line(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -452,6 +484,10 @@ def main():
         cpu = run_cpu_reference(args, steps=3, warmup=1, budget_s=args.cpu_budget_s)
         line["cpu_baseline"] = {kk: cpu[kk] for kk in ("value", "unit", "cores", "kind", "sample")}
         line["cpu_baseline"]["iters_per_sec"] = cpu["iters_per_sec"]
+        line["cpu_baseline"]["flags"] = "-O2 -fopenmp -ffp-contract=off (the package's flags: no -march, no FMA)"
+        native = cpu_reference_native_row(args, args.cpu_budget_s)
+        if native is not None:
+            line["cpu_baseline"]["O3_march_native"] = native
     if rank == 0:
         print(json.dumps(line), flush=True)
     if dist is not None:

@@ -14,11 +14,15 @@ from dataclasses import dataclass, field
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "liboracle.so")
+# RCPPML_ORACLE_LIB: an alternative build of nmf_oracle.cpp (bench.py times an -O3 -march=native build beside the
+# package-flags build; the checker itself always uses the default library).
+_LIB_PATH = os.environ.get("RCPPML_ORACLE_LIB") or os.path.join(_HERE, "liboracle.so")
 
 
 def build(force: bool = False) -> str:
     src = os.path.join(_HERE, "nmf_oracle.cpp")
+    if os.environ.get("RCPPML_ORACLE_LIB"):
+        return _LIB_PATH
     if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
         subprocess.check_call(["make", "-C", _HERE, "-B" if force else "-s"], stdout=subprocess.DEVNULL)
     return _LIB_PATH
