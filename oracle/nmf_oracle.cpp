@@ -18,7 +18,9 @@
 //    file against that library BIT FOR BIT: SplitMix64 / hash / is_holdout /
 //    fill_uniform / factor initialisation, cd_nnls_col_fixed with every switch
 //    (sweep counts included), nnls_batch, the fused CD and Cholesky column loops
-//    (L1, warm start, clip, bound), the Gram wrapper.
+//    (L1, warm start, clip, bound), the Gram wrapper, the explicit-mask half-steps,
+//    extract_scaling, apply_upper_bound, LazySpeckledMask, and the CV building
+//    blocks compute_train_rhs / compute_train_rhs_W / apply_gram_correction.
 //  * Eigen itself (and R/Rcpp) is not in the image, so the whole nmf_fit<> cannot
 //    be built and the reference's test-suite holds no golden W/d/H vectors
 //    (SURVEY.md §8c): the order of the reductions INSIDE Eigen (rankUpdate, gemv,
@@ -906,6 +908,37 @@ typedef struct {
     long n_test;                 // held-out entries (last evaluation)
 } orc_cv_result;
 
+// nmf/cv_detail.hpp:305-340 (compute_train_rhs: operand A, column j, mask(i = inner, j)) and :357-405
+// (compute_train_rhs_W: operand Aᵀ, column i, mask(i, col = inner)). Train entries accumulate into b in ascending
+// inner order; held-out entries are listed (index and stored value, 0 for a structural zero) in the same order.
+// mask_zeros: only the stored entries can be held out; otherwise every cell of the column is hashed.
+extern "C++" {
+template <class Held>
+static void cv_train_rhs(const int* Cp, const int* Ci, const float* Cx, long n_inner, long col, const float* F, int k,
+                         bool transposed, bool mz, const Held& held, float* b, std::vector<int>& test,
+                         std::vector<float>& tval) {
+    std::fill(b, b + k, 0.f);
+    test.clear();
+    tval.clear();
+    auto is_held = [&](long inner) { return transposed ? held(col, inner) : held(inner, col); };
+    if (mz) {
+        for (long p = Cp[col]; p < Cp[col + 1]; ++p) {
+            if (is_held(Ci[p])) { test.push_back(Ci[p]); tval.push_back(Cx[p]); }
+            else { const float v = Cx[p]; const float* f = F + static_cast<long>(Ci[p]) * k;
+                   for (int t = 0; t < k; ++t) b[t] += v * f[t]; }
+        }
+    } else {
+        long p = Cp[col];
+        for (long c = 0; c < n_inner; ++c) {
+            float v = 0.f;
+            if (p < Cp[col + 1] && Ci[p] == c) { v = Cx[p]; ++p; }
+            if (is_held(c)) { test.push_back(static_cast<int>(c)); tval.push_back(v); }
+            else if (v != 0.f) { const float* f = F + c * k; for (int t = 0; t < k; ++t) b[t] += v * f[t]; }
+        }
+    }
+}
+}  // extern "C++"
+
 static void cv_solve_col(const float* G, const float* F, const std::vector<int>& test, int k, float* Gl, float* Lc,
                          float* b, float* x, float L1, bool nonneg, int cd_maxit, int solver_mode) {
     std::copy(G, G + static_cast<long>(k) * k, Gl);                              // cv_detail.hpp:74
@@ -922,6 +955,30 @@ static void cv_solve_col(const float* G, const float* F, const std::vector<int>&
         if (nonneg) for (int i = 0; i < k; ++i) x[i] = std::max(x[i], 0.f);
     } else {                                                                     // fit_cv.hpp:469-472: no cd_tol
         orc::cd_nnls_col_fixed(Gl, b, x, k, L1, 0.f, nonneg, cd_maxit, 0.f, 0.f);
+    }
+}
+
+// The two per-column building blocks of the CV path on their own (tests/test_reference_sources.py holds them against
+// the reference's compute_train_rhs / compute_train_rhs_W / apply_gram_correction). Returns the number of held-out
+// entries; test_idx must have room for every candidate (n_inner).
+long orc_cv_train_rhs_f32(const int* Cp, const int* Ci, const float* Cx, long n_inner, long col, const float* F, int k,
+                          int transposed, int mask_zeros, uint64_t seed, uint64_t inv_prob, float* b, int* test_idx) {
+    auto held = [&](long i, long j) {
+        return orc::SplitMix64::is_holdout(seed, static_cast<uint32_t>(i), static_cast<uint32_t>(j), inv_prob);
+    };
+    std::vector<int> test;
+    std::vector<float> tval;
+    cv_train_rhs(Cp, Ci, Cx, n_inner, col, F, k, transposed != 0, mask_zeros != 0, held, b, test, tval);
+    for (size_t q = 0; q < test.size(); ++q) test_idx[q] = test[q];
+    return static_cast<long>(test.size());
+}
+// G_local = G − Σ_{r in test} f_r f_rᵀ (cv_detail.hpp:67-85, restated as sequential fp32 downdates in test order)
+void orc_cv_gram_correction_f32(const float* G, const float* F, const int* test_idx, long n_test, int k, float* Gl) {
+    std::copy(G, G + static_cast<long>(k) * k, Gl);
+    for (long q = 0; q < n_test; ++q) {
+        const float* f = F + static_cast<long>(test_idx[q]) * k;
+        for (int c = 0; c < k; ++c)
+            for (int a = 0; a < k; ++a) Gl[static_cast<long>(c) * k + a] -= f[a] * f[c];
     }
 }
 
@@ -968,25 +1025,10 @@ int orc_nmf_fit_cv_f32(const int* Ap, const int* Ai, const float* Ax, long m, lo
         {
             std::vector<float> b(k), x(k), Gl(static_cast<size_t>(k) * k), Lc(Gl.size());
             std::vector<int> test;
+            std::vector<float> tval;
 #pragma omp for schedule(dynamic, 64)
             for (long j = 0; j < n; ++j) {
-                std::fill(b.begin(), b.end(), 0.f);                              // cv_detail.hpp:305-340
-                test.clear();
-                if (mz) {
-                    for (long p = Ap[j]; p < Ap[j + 1]; ++p) {
-                        if (held(Ai[p], j)) test.push_back(Ai[p]);
-                        else { const float v = Ax[p]; const float* f = W_T + static_cast<long>(Ai[p]) * k;
-                               for (int t = 0; t < k; ++t) b[t] += v * f[t]; }
-                    }
-                } else {
-                    long p = Ap[j];
-                    for (long i = 0; i < m; ++i) {
-                        float v = 0.f;
-                        if (p < Ap[j + 1] && Ai[p] == i) { v = Ax[p]; ++p; }
-                        if (held(i, j)) test.push_back(static_cast<int>(i));
-                        else if (v != 0.f) { const float* f = W_T + i * k; for (int t = 0; t < k; ++t) b[t] += v * f[t]; }
-                    }
-                }
+                cv_train_rhs(Ap, Ai, Ax, m, j, W_T, k, false, mz, held, b.data(), test, tval);   // cv_detail.hpp:305-340
                 std::copy(H + j * k, H + (j + 1) * k, x.begin());                // :460 x_local = H.col(j)
                 cv_solve_col(G.data(), W_T, test, k, Gl.data(), Lc.data(), b.data(), x.data(), cfg->L1_H,
                              cfg->nonneg_H != 0, cfg->cd_maxit, cfg->solver_mode);
@@ -1008,23 +1050,7 @@ int orc_nmf_fit_cv_f32(const int* Ap, const int* Ai, const float* Ax, long m, lo
             std::vector<float> tval;
 #pragma omp for schedule(dynamic, 64)
             for (long i = 0; i < m; ++i) {
-                std::fill(b.begin(), b.end(), 0.f);                              // cv_detail.hpp:357-405
-                test.clear(); tval.clear();
-                if (mz) {
-                    for (long p = Atp[i]; p < Atp[i + 1]; ++p) {
-                        if (held(i, Ati[p])) { test.push_back(Ati[p]); tval.push_back(Atx[p]); }
-                        else { const float v = Atx[p]; const float* f = H + static_cast<long>(Ati[p]) * k;
-                               for (int t = 0; t < k; ++t) b[t] += v * f[t]; }
-                    }
-                } else {
-                    long p = Atp[i];
-                    for (long c = 0; c < n; ++c) {
-                        float v = 0.f;
-                        if (p < Atp[i + 1] && Ati[p] == c) { v = Atx[p]; ++p; }
-                        if (held(i, c)) { test.push_back(static_cast<int>(c)); tval.push_back(v); }
-                        else if (v != 0.f) { const float* f = H + c * k; for (int t = 0; t < k; ++t) b[t] += v * f[t]; }
-                    }
-                }
+                cv_train_rhs(Atp.data(), Ati.data(), Atx.data(), n, i, H, k, true, mz, held, b.data(), test, tval);   // cv_detail.hpp:357-405
                 bf = b;                                                          // :609-653 full RHS (train, then test entries)
                 for (size_t q = 0; q < test.size(); ++q)
                     if (tval[q] != 0.f) { const float* f = H + static_cast<long>(test[q]) * k;

@@ -18,6 +18,7 @@
 //   inst/include/FactorNet/nmf/variant_helpers.hpp           extract_scaling
 //   inst/include/FactorNet/features/bounds.hpp               apply_upper_bound
 //   inst/include/FactorNet/nmf/speckled_cv.hpp               LazySpeckledMask (seed / inv_prob conventions)
+//   inst/include/FactorNet/nmf/cv_detail.hpp                 compute_train_rhs, compute_train_rhs_W, apply_gram_correction
 #ifndef FACTORNET_HOST_DEVICE
 #define FACTORNET_HOST_DEVICE
 #endif
@@ -34,6 +35,7 @@ namespace Eigen { template <class M> class SelfAdjointEigenSolver; }   // named 
 #include <FactorNet/nmf/masked_nnls.hpp>
 #include <FactorNet/nmf/speckled_cv.hpp>
 #include <FactorNet/nmf/variant_helpers.hpp>
+#include <FactorNet/nmf/cv_detail.hpp>
 
 #include <cstdint>
 #include <cstring>
@@ -203,6 +205,32 @@ void ref_speckled_mask_f32(int n_rows, int n_cols, double holdout_fraction, uint
                            int count, int* out) {
     nmf::LazySpeckledMask<float> mask(n_rows, n_cols, 0, holdout_fraction, seed, true);
     for (int t = 0; t < count; ++t) out[t] = mask.is_holdout(ii[t], jj[t]) ? 1 : 0;
+}
+
+// ---- nmf/cv_detail.hpp. C = A (CSC m x n) with F = W_T for the H side (transposed = 0), C = Aᵀ (CSC n x m) with F = H
+//      for the W side (transposed = 1). Returns the number of held-out entries of column `col`, listed in test_idx.
+long ref_cv_train_rhs_f32(const int* Cp, const int* Ci, const float* Cx, long n_inner, long n_cols, long col, const float* F,
+                          int k, int transposed, int mask_zeros, double holdout_fraction, uint64_t seed, float* b, int* test_idx) {
+    const SpF Cm(n_inner, n_cols, Cp, Ci, Cx);
+    const DenseMatrix<float> Fm = dense_from(F, k, n_inner);
+    // LazySpeckledMask(n_rows, n_cols, ...) is indexed (row of A, column of A) on both sides
+    const nmf::LazySpeckledMask<float> mask(transposed ? static_cast<int>(n_cols) : static_cast<int>(n_inner),
+                                            transposed ? static_cast<int>(n_inner) : static_cast<int>(n_cols), 0,
+                                            holdout_fraction, seed, mask_zeros != 0);
+    DenseVector<float> bv(k);
+    std::vector<int> test;
+    if (transposed) nmf::detail::compute_train_rhs_W<float, SpF>(Cm, Fm, static_cast<int>(col), mask, bv, test, mask_zeros != 0, static_cast<int>(n_inner));
+    else nmf::detail::compute_train_rhs<float, SpF>(Cm, Fm, static_cast<int>(col), mask, bv, test, mask_zeros != 0, static_cast<int>(n_inner));
+    for (int i = 0; i < k; ++i) b[i] = bv(i);
+    for (size_t q = 0; q < test.size(); ++q) test_idx[q] = test[q];
+    return static_cast<long>(test.size());
+}
+void ref_cv_gram_correction_f32(const float* G, const float* F, long n_rows, const int* test_idx, long n_test, int k, float* Gl) {
+    const DenseMatrix<float> Gm = dense_from(G, k, k), Fm = dense_from(F, k, n_rows);
+    DenseMatrix<float> Gl_m(k, k), buf(k, n_test > 0 ? n_test : 1);
+    const std::vector<int> test(test_idx, test_idx + n_test);
+    nmf::detail::apply_gram_correction<float>(Gm, Fm, test, Gl_m, buf);
+    std::memcpy(Gl, Gl_m.data(), sizeof(float) * static_cast<size_t>(k) * k);
 }
 
 }  // extern "C"

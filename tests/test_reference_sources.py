@@ -2,7 +2,8 @@
 
 oracle/_ref/libref_hotpath.so is the reference's headers — rng/rng.hpp, primitives/cpu/{nnls_batch, fused_nnls,
 cholesky_clip, gram}.hpp, primitives/primitives.hpp, core/constants.hpp, nmf/masked_nnls.hpp (with core/config.hpp),
-nmf/variant_helpers.hpp, features/bounds.hpp, nmf/speckled_cv.hpp — compiled unmodified from /root/reference
+nmf/variant_helpers.hpp, features/bounds.hpp, nmf/speckled_cv.hpp, nmf/cv_detail.hpp — compiled unmodified from
+/root/reference
 (`make -C oracle ref_hotpath`) against a minimal stand-in for the Eigen types they use (Eigen is not in this image).
 Everything the reference's source decides — the SplitMix64 generator and hash, the CD solver with its skip rules,
 clamps and convergence formula, where L1 / the warm-start correction / the clip / the upper bound sit in the fused
@@ -266,3 +267,44 @@ def test_speckled_mask_conventions(ref, oracle):
             want = np.array([oracle.is_holdout(eff, int(i), int(j), inv) for i, j in zip(ii, jj)], dtype=np.int32)
             assert np.array_equal(out, want), (frac, seed)
             assert 0.5 / inv < out.mean() < 1.5 / inv
+
+
+@pytest.mark.parametrize("mask_zeros", [True, False])
+def test_cv_building_blocks_bit_exact(ref, oracle, mask_zeros):
+    """nmf/cv_detail.hpp: compute_train_rhs (H side: operand A, mask(row, col)), compute_train_rhs_W (W side: operand
+    Aᵀ, mask(row of A = column of Aᵀ, col = inner)) and apply_gram_correction — which entries are held out, in which
+    order, what accumulates into b (mask_zeros: only stored entries can be held out; otherwise every cell of the
+    column is hashed and a held-out structural zero counts too), and the corrected Gram."""
+    from oracle.oracle import lib as olib
+    L = olib()
+    L.orc_cv_train_rhs_f32.restype = C.c_long
+    ref.ref_cv_train_rhs_f32.restype = C.c_long
+    m, n, k = 140, 60, 9
+    A = random_csc(m, n, 0.15, 31, ragged=True)
+    Ap, Ai, Ax = A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data.astype(np.float32)
+    Tp, Ti, Tx = oracle.transpose_csc(Ap, Ai, Ax, m, n)
+    rng = np.random.default_rng(12)
+    W = rng.random((m, k)).astype(np.float32)
+    H = rng.random((n, k)).astype(np.float32)
+    frac = float(np.float32(0.2))                       # the reference holds the fraction as a float: inv_prob = 4
+    seed, inv_prob = 77, 4
+    for transposed, (Cp, Ci, Cx, n_inner, n_cols, F) in ((0, (Ap, Ai, Ax, m, n, W)), (1, (Tp, Ti, Tx, n, m, H))):
+        G = oracle.gram(F)
+        for col in range(0, n_cols, 7):
+            b1, b2 = np.zeros(k, np.float32), np.zeros(k, np.float32)
+            t1, t2 = np.zeros(n_inner + 1, np.int32), np.zeros(n_inner + 1, np.int32)
+            c1 = ref.ref_cv_train_rhs_f32(_p(Cp, C.c_int), _p(Ci, C.c_int), _p(Cx, C.c_float), C.c_long(n_inner),
+                                          C.c_long(n_cols), C.c_long(col), _p(F, C.c_float), k, transposed,
+                                          int(mask_zeros), C.c_double(frac), C.c_uint64(seed), _p(b1, C.c_float), _p(t1, C.c_int))
+            c2 = L.orc_cv_train_rhs_f32(_p(Cp, C.c_int), _p(Ci, C.c_int), _p(Cx, C.c_float), C.c_long(n_inner),
+                                        C.c_long(col), _p(F, C.c_float), k, transposed, int(mask_zeros),
+                                        C.c_uint64(seed), C.c_uint64(inv_prob), _p(b2, C.c_float), _p(t2, C.c_int))
+            assert c1 == c2 and np.array_equal(t1[:c1], t2[:c2]), (transposed, col, c1, c2)
+            assert np.array_equal(b1, b2), (transposed, col)
+            G1, G2 = np.zeros((k, k), np.float32), np.zeros((k, k), np.float32)
+            ref.ref_cv_gram_correction_f32(_p(G, C.c_float), _p(F, C.c_float), C.c_long(n_inner), _p(t1, C.c_int),
+                                           C.c_long(c1), k, _p(G1, C.c_float))
+            L.orc_cv_gram_correction_f32(_p(G, C.c_float), _p(F, C.c_float), _p(t2, C.c_int), C.c_long(c2), k, _p(G2, C.c_float))
+            assert np.array_equal(G1, G2), (transposed, col)
+        if not mask_zeros:
+            assert c1 > 0                                # with every cell hashed a column of 60+ cells has hold-outs
