@@ -114,3 +114,27 @@ def test_synth_numpy_twin_matches_oracle_generator(oracle):
     assert x.min() >= 0.5 and x.max() < 1.5 and np.all(i < 100000)
     for j in range(50):
         assert np.all(np.diff(i[p[j]:p[j + 1]]) > 0)                   # sorted, unique rows
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm) on a small matrix: one JSON line
+    with the contract's keys, cpu_baseline describing the run, e2e repeating the line's own value with no copies."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--m", "20000", "--n", "2000",
+                          "--density", "0.005", "--k", "16", "--steps", "2", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["unit"] == "nnz/s" and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "nnz/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"]
