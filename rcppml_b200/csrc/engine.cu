@@ -527,7 +527,7 @@ void Engine::alloc_factors(int k_) {
     if (const char* env = std::getenv("RCPPML_B200_CD_KERNEL")) { if (std::atoi(env) == 1) cd_geom = cd_geom_long = 0; }
     tiled_mode = 1;
     if (const char* env = std::getenv("RCPPML_B200_TILED")) tiled_mode = std::atoi(env);
-    tiled_min_batches = 1.5;
+    tiled_min_batches = 0.5;
     if (const char* env = std::getenv("RCPPML_B200_TILED_MIN_BATCHES")) tiled_min_batches = std::atof(env);
     narrow_min_cols = 8.0 * num_sms * 24;
     if (std::getenv("RCPPML_B200_CD_GEOM")) narrow_min_cols = 0.0;           // an explicit geometry applies to every size
@@ -879,8 +879,9 @@ void Engine::build_panels() {
 //     slower (pbmc3k k=32 CD: 1.7 ms/iteration wide, 4.2 ms narrow; Cholesky 0.49 vs 1.2 ms);
 //   * coordinate descent otherwise: narrow groups — the tiled kernel (robust to skewed column lengths; long
 //     columns gather wide), or cd_half_step_kernel with RCPPML_B200_TILED=0;
-//   * Cholesky with short columns and >= tiled_min_batches batches per resident warp: the tiled kernel
-//     (C4 W half-step 2.64 -> 2.46 ms); long columns (C4 H half-step) are gather bound and stay one-geometry.
+//   * Cholesky with >= tiled_min_batches batches per resident warp: the tiled kernel for short columns (C4 W
+//     half-step 2.64 -> 2.35 ms; every pass of a row-panelled half-step is "short": C5 147 -> 114 ms) and for long
+//     columns at k = 32 / 128; long columns at k = 64 / 16 (C4 H half-step) stay one-geometry.
 bool Engine::use_narrow_cd(long long ncols) const {
     return cd_geom != 0 && static_cast<double>(ncols) >= narrow_min_cols;
 }
@@ -889,11 +890,19 @@ bool Engine::use_tiled(int solver, long long cnt, long long ncols) const {
     if (tiled_mode == 0) return false;
     if (tiled_mode == 2) return true;
     if (solver == SOLVER_CD) return use_narrow_cd(ncols);
-    const int cb = (KP == 64) ? 16 : (KP == 128) ? 8 : 32;
-    const long long resident_warps = static_cast<long long>(num_sms) * 24;
+    // Cholesky. `cnt` is the non-zero count of the pass that ends in the solve (one row panel's share when the
+    // half-step is split into panel passes).
+    const int cb = (KP == 64) ? 16 : (KP == 128) ? 8 : 32;                       // columns per warp batch
+    const long long resident_warps = static_cast<long long>(num_sms) * ((KP == 128) ? 8 : 24);
+    // fewer than ~half a batch per resident warp: the narrow solve geometry starves the machine (pbmc3k, 0.12
+    // batches per warp: 0.49 -> 1.2 ms); from ~0.9 batches per warp on the tiled kernel is ahead (k = 32, 100 K columns)
     if (static_cast<double>(ncols) < tiled_min_batches * static_cast<double>(cb) * static_cast<double>(resident_warps)) return false;
     const double avg = ncols > 0 ? static_cast<double>(cnt) / static_cast<double>(ncols) : 0.0;
-    return avg < 400.0 && KP < 128;
+    if (avg < 400.0) return true;                 // short columns: the solve dominates at every rank
+    // Long columns (measured on the C4 shape, 1000 non-zeros per column, profiles/r01r_chol_kernel_selection.json):
+    // k = 128: 4.48 -> 3.61 ms and k = 32: 1.11 -> 0.84 ms with the tiled kernel, but k = 64: 1.73 -> 3.87 ms and
+    // k = 16: 0.70 -> 0.76 ms — those stay on the one-geometry kernel.
+    return KP == 128 || KP == 32;
 }
 
 int Engine::tiled_gather_geom(long long cnt, long long ncols) const {
@@ -916,7 +925,7 @@ void Engine::solve(int which, bool warm, int sec) {
     const long long cnt = which == 0 ? nnz : nnz_w;
     const int P = npanels[which];
     int geom = geometry_for(cnt, p.ncols);
-    const bool tiled = use_tiled(solver, cnt, p.ncols);
+    const bool tiled = use_tiled(solver, cnt / std::max(1, P), p.ncols);
     const bool narrow_cd = !tiled && solver == SOLVER_CD && use_narrow_cd(p.ncols);
     const int kind = tiled ? 2 : (narrow_cd ? 1 : 0);
     if (tiled) {

@@ -109,7 +109,7 @@ public:
     // kernels_tiled.cuh (wide gather -> shared-memory tile -> narrow solve). 0: never, 1: CD always and Cholesky
     // for short columns (default), 2: always. RCPPML_B200_TILED overrides.
     int tiled_mode = 1;
-    double tiled_min_batches = 1.5, narrow_min_cols = 0.0;
+    double tiled_min_batches = 0.5, narrow_min_cols = 0.0;
     bool use_narrow_cd(long long ncols) const;
     bool use_tiled(int solver, long long cnt, long long ncols) const;
     int tiled_gather_geom(long long cnt, long long ncols) const;
