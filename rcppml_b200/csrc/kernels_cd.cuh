@@ -1,6 +1,9 @@
 // kernels_cd.cuh — the fused half-step kernel specialised for the coordinate-descent solver
 // (solver_mode 0): same gather, same arithmetic contract and same results (bit for bit, sweep counts
 // included) as half_step_kernel<.., SOLVER_CD, ..> in kernels_solve.cuh, re-cut for what bounds CD.
+// cd_solve_blocked() below is also the CD solver of tiled_half_step_kernel (kernels_tiled.cuh), which is what a fit
+// runs by default when columns are plentiful; cd_half_step_kernel (one narrow geometry for gather and solve) remains
+// selectable with RCPPML_B200_TILED=0.
 //
 // Replaces (reference): primitives/cpu/fused_nnls.hpp:71-134 and primitives/cpu/nnls_batch.hpp:71-132.
 //
@@ -19,7 +22,9 @@
 //     formed as fma(g, Δ, +0) = +0, and x − (+0) = x for every x including −0), so executing it is the
 //     reference's `continue`;
 //   * the sweep's convergence sum Σ|Δ|/(|x|+1e-15) keeps its order (coordinate order, fp32) but the four
-//     IEEE divisions of a block are spread over the lanes of the group and brought back by shuffle;
+//     IEEE divisions of a block are spread over the lanes of the group and brought back by shuffle; and since
+//     the sum of non-negative terms only grows under monotone rounding, once tol_sum/k >= cd_tol the sweep-end
+//     test is decided and the quotients are skipped for the rest of the sweep (exact, not a heuristic);
 //   * registers hold only the lane's words of b (32 at k = 64): x lives in shared memory (it is touched once per
 //     block), the fp64 row sums are per-warp shared-memory arrays, and the pre-L1 right-hand side kept for the
 //     loss cross term is parked in global memory (L2) — 3 CTAs per SM instead of 2;
