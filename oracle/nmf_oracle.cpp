@@ -8,8 +8,12 @@
 // reference leg may build, load or call this file. The product path
 // (rcppml_b200/csrc) never links or calls it.
 //
-// PARITY STATUS: pinned against the reference's OWN SOURCE for everything that
-// source decides, **parity unpinned** only for the rounding inside Eigen.
+// PARITY STATUS: pinned against the reference's OWN nmf_fit — fit_cpu.hpp compiled
+// unmodified against an Eigen stand-in (oracle/ref_hotpath/ref_fit.cpp ->
+// oracle/_ref/libref_fit.so); tests/test_reference_fit.py: W, d, H of this file are
+// bit-identical to it (CD / Cholesky, L1/L2, bounds, norms, masks, sorting,
+// patience). **parity unpinned** only for the rounding inside Eigen (the stand-in
+// shares this file's definitions) and for the fp32-vs-fp64 loss accumulation.
 //  * The reference's hot-path headers (rng.hpp, nnls_batch.hpp, fused_nnls.hpp,
 //    cholesky_clip.hpp, gram.hpp, primitives.hpp, constants.hpp) compile
 //    unmodified from /root/reference against a minimal stand-in for the Eigen
