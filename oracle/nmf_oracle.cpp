@@ -8,8 +8,8 @@
 // reference leg may build, load or call this file. The product path
 // (rcppml_b200/csrc) never links or calls it.
 //
-// PARITY STATUS: pinned against the reference's OWN nmf_fit — fit_cpu.hpp compiled
-// unmodified against an Eigen stand-in (oracle/ref_hotpath/ref_fit.cpp ->
+// PARITY STATUS: pinned against the reference's OWN nmf_fit and nmf_fit_cv —
+// fit_cpu.hpp / fit_cv.hpp compiled unmodified against an Eigen stand-in (oracle/ref_hotpath/ref_fit.cpp ->
 // oracle/_ref/libref_fit.so); tests/test_reference_fit.py: W, d, H of this file are
 // bit-identical to it (CD / Cholesky, L1/L2, bounds, norms, masks, sorting,
 // patience). **parity unpinned** only for the rounding inside Eigen (the stand-in

@@ -1,4 +1,4 @@
-"""CPU: the oracle against THE REFERENCE'S OWN ALS LOOP.
+"""CPU: the oracle against THE REFERENCE'S OWN ALS LOOPS (nmf_fit and, at the end of the file, nmf_fit_cv).
 
 oracle/_ref/libref_fit.so is the reference's nmf/fit_cpu.hpp — nmf_fit<CPU, float, SparseMatrix<float>>, 1855 lines,
 with every header it pulls in — compiled unmodified from /root/reference (`make -C oracle ref_hotpath`) against the
@@ -143,3 +143,48 @@ def test_reference_fit_convergence_and_patience(reffit, oracle):
         assert np.array_equal(W, ref.W_T) and np.array_equal(H, ref.H) and np.array_equal(d, ref.d)
         # the relative change is a difference of nearly equal losses that the two sides accumulate in fp32 / fp64
         assert abs(res.final_tol - ref.final_tol) <= 2e-2 * abs(ref.final_tol) + 1e-9
+
+
+# ---- the cross-validation orchestrator: nmf/fit_cv.hpp, nmf_fit_cv<CPU, float, SparseMatrix<float>> ----------------
+class CP(C.Structure):
+    _fields_ = [("holdout_fraction", C.c_float), ("cv_seed", C.c_uint), ("mask_zeros", C.c_int), ("cv_patience", C.c_int)]
+
+
+class CR(C.Structure):
+    _fields_ = [("test_loss", C.c_float), ("best_test_loss", C.c_float), ("best_iter", C.c_int), ("n_test_hist", C.c_int)]
+
+
+CV_CASES = [(7, 1, True, dict(L1=(0.01, 0.0), L2=(0.0, 0.01))), (7, 0, True, {}), (5, 1, False, {}),
+            (12, 0, False, dict(L1=(0.0, 0.01))), (20, 1, True, dict(upper_bound=(0.5, 0.5))), (6, 0, True, dict(norm_type=1))]
+
+
+@pytest.mark.parametrize("k,solver,mask_zeros,kw", CV_CASES, ids=[f"k{c[0]}_s{c[1]}_mz{int(c[2])}" for c in CV_CASES])
+def test_oracle_reproduces_the_reference_cv_fit_bit_for_bit(reffit, oracle, k, solver, mask_zeros, kw):
+    """Speckled-mask cross-validation: W, d, H bit for bit, same best iteration; train / test losses to 1e-5 (the
+    reference sums them in fp32, the oracle in fp64)."""
+    m, n, iters = 260, 180, 6
+    A = random_csc(m, n, 0.12, 3 + k, ragged=True)
+    W0, H0 = oracle.initialize_factors(k, m, n, 42)
+    L1, L2, ub = kw.get("L1", (0.0, 0.0)), kw.get("L2", (0.0, 0.0)), kw.get("upper_bound", (0.0, 0.0))
+    q = P(k=k, max_iter=iters, tol=0.0, L1_W=L1[0], L1_H=L1[1], L2_W=L2[0], L2_H=L2[1], ub_W=ub[0], ub_H=ub[1],
+          nonneg_W=1, nonneg_H=1, cd_maxit=15, cd_tol=1e-8, norm_type=kw.get("norm_type", 0), solver_mode=solver,
+          patience=5, threads=1, sort_model=0, seed=42)
+    cq = CP(holdout_fraction=0.1, cv_seed=7, mask_zeros=int(mask_zeros), cv_patience=5)
+    Ap, Ai, Ax = A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data.astype(np.float32)
+    W_in, H_in = np.ascontiguousarray(W0.T), np.ascontiguousarray(H0)
+    W_out, H_out, d = np.zeros((k, m), np.float32), np.zeros((n, k), np.float32), np.zeros(k, np.float32)
+    tr, te = np.zeros(iters, np.float32), np.zeros(iters, np.float32)
+    res, cres, err = R(), CR(), C.create_string_buffer(300)
+    rc = reffit.reffit_nmf_cv_sparse_f32(_p(Ap, C.c_int), _p(Ai, C.c_int), _p(Ax, C.c_float), m, n, C.byref(q), C.byref(cq),
+                                         _p(W_in, C.c_float), _p(H_in, C.c_float), _p(W_out, C.c_float),
+                                         _p(H_out, C.c_float), _p(d, C.c_float), _p(tr, C.c_float), _p(te, C.c_float),
+                                         C.byref(res), C.byref(cres), err, 300)
+    assert rc == 0, err.value.decode()
+    ref = oracle.nmf_fit_cv(A.indptr, A.indices, A.data, m, n, k, W0, H0, max_iter=iters, tol=0.0, solver_mode=solver,
+                            cd_maxit=15, holdout_fraction=0.1, cv_seed=7, seed=42, mask_zeros=mask_zeros, threads=1, **kw)
+    assert res.iterations == ref.iterations and cres.best_iter == ref.best_iter
+    assert np.array_equal(W_out.T, ref.W_T), float(np.abs(W_out.T - ref.W_T).max())
+    assert np.array_equal(H_out, ref.H) and np.array_equal(d, ref.d)
+    assert np.allclose(te[:cres.n_test_hist], ref.test_history, rtol=1e-5, atol=0)
+    assert np.allclose(tr[:res.n_loss], ref.train_history, rtol=1e-5, atol=0)
+    assert abs(cres.best_test_loss - ref.best_test_loss) <= 1e-5 * abs(ref.best_test_loss)
