@@ -14,7 +14,9 @@ metric = processed non-zeros per second = nnz x iterations / seconds (iterations
 * roofline   : the fused gather+solve kernel (two launches per iteration), algorithmic bytes per launch
                 / mean CUDA-event duration of those launches, against MEASURED_PEAKS.json.
 * cpu_baseline / --impl reference : the CPU restatement of the reference algorithm (oracle/, OpenMP, all
-               host cores) on the same matrix, bounded in wall time.
+               host cores) on the same matrix, bounded in wall time. (oracle/_ref/libref_fit.so — the reference's own
+               nmf_fit compiled against an Eigen stand-in — reproduces the same factors bit for bit but is a checker,
+               8x slower than the port because the stand-in's linear algebra is not optimised; it is not timed.)
 """
 from __future__ import annotations
 
