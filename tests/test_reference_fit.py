@@ -188,3 +188,31 @@ def test_oracle_reproduces_the_reference_cv_fit_bit_for_bit(reffit, oracle, k, s
     assert np.allclose(te[:cres.n_test_hist], ref.test_history, rtol=1e-5, atol=0)
     assert np.allclose(tr[:res.n_loss], ref.train_history, rtol=1e-5, atol=0)
     assert abs(cres.best_test_loss - ref.best_test_loss) <= 1e-5 * abs(ref.best_test_loss)
+
+
+# ---- the GPU engine against the reference's own fit, directly ----------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", [c for c in CASES if "sorted" not in c[0]], ids=[c[0] for c in CASES if "sorted" not in c[0]])
+def test_gpu_engine_matches_the_reference_fit(reffit, oracle, case):
+    """north_star: "W, d, H match the reference CPU path within 1e-5 relative fp32 tolerance" — here the reference CPU
+    path is the reference's own nmf_fit (libref_fit.so), not the restatement. (sort_model is not on the GPU wire.)"""
+    import rcppml_b200 as rb
+    from helpers import RTOL, rel_err, zero_pattern_equal
+    name, m, n, dens, k, kw = case
+    iters = 7
+    A = random_csc(m, n, dens, 17, counts=("L1" in name), ragged=True)
+    W0, H0 = oracle.initialize_factors(k, m, n, 42)
+    W, H, d, hist, res = _ref_fit(reffit, A, k, W0, H0, max_iter=iters, **kw)
+    eng = rb.Engine(0)
+    try:
+        eng.set_matrix(m, n, A.indptr, A.indices, A.data)
+        eng.set_factors(W0, H0)
+        out = eng.fit(rb.make_config(k, max_iter=iters, tol=0.0, **kw))
+        Wg, Hg, dg = eng.get_factors()
+        lg = eng.loss_history(iters)
+    finally:
+        eng.close()
+    assert out.status == 0 and out.iterations == iters
+    errs = dict(W=rel_err(Wg, W), H=rel_err(Hg, H), d=rel_err(dg, d), loss=rel_err(lg, hist))
+    assert max(errs.values()) <= RTOL, (name, errs)
+    assert zero_pattern_equal(Wg, W) and zero_pattern_equal(Hg, H)
