@@ -1,0 +1,424 @@
+"""Host mirror of the reference's `nmf()` front end for the path this repository replaces.
+
+Argument names, defaults, meaning and error messages follow R/nmf_thin.R:219-1315 (`nmf`), R/parse_dots.R:5-96
+(`.parse_nmf_dots`) and R/nmf_validation.R:64-240; the R -> config mapping follows
+src/RcppFunctions_nmf.cpp:23-95, 335-455 (`build_config_from_params`, `Rcpp_nmf_full`: data and W_init are cast to
+float) and the call reaches the GPU exactly as `nmf::nmf` does with plan = GPU (nmf/fit.hpp:97-117, 187-203):
+through the dlsym bridge's packing (gpu/bridge_nmf.hpp:199-393; rcppml_b200/bridge.py is its ctypes twin) into
+`rcppml_gpu_nmf_unified_float` / `rcppml_gpu_nmf_cv_unified_float` of RcppML_gpu.so.
+
+What is mirrored: sparse `data`, scalar `k`, `tol`, `maxit`, `L1`, `L2`, `seed` (NULL / integer / W matrix),
+`mask` (NULL / "zeros" / pattern matrix / list("zeros", matrix)), `nonneg`, `test_fraction`, and from `...`:
+`upper_bound`, `norm`, `solver`, `cd_maxit`, `cd_tol`, `h_init`, `w_init`, `cv_seed`, `patience`, `sort_model`,
+`resource`, `threads`. Everything the reference routes elsewhere (non-MSE losses, robust/zi, L21 / angular / graph /
+target penalties, projective / symmetric, rank vectors and k = "auto", SVD-based init strings, streaming .spz,
+multi-init seed lists, dense input) raises NotImplementedError naming the argument: SURVEY.md §2 marks them out of
+scope and there is NO CPU fallback behind this function — where the reference would fall back to its CPU loop
+(nmf/fit.hpp:118-127), this one raises `NativeLibraryError`.
+
+Two points where the GPU route of the reference loses information and this mirror does not:
+  * an explicit `mask` is not carried by the bridge signature — here it goes to the ABI
+    extension `rcppml_gpu_nmf_masked_unified_float`;
+  * `sort_model` is not transmitted either (core/config.hpp:358), so the reference returns unsorted factors from
+    the GPU route; here `sort_model=True` (the R default) applies `NMFResult::sort` (core/result.hpp:169-189) on
+    the host, which is what the reference's CPU route returns.
+"""
+from __future__ import annotations
+
+import time
+import warnings
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib
+from .bridge import bridge_nmf_cv_sparse, bridge_nmf_sparse, gpu_detect
+
+_INT_MAX = 2147483647          # .Machine$integer.max
+
+# .parse_nmf_dots defaults (R/parse_dots.R:6-58)
+_DOT_DEFAULTS = dict(
+    L21=(0, 0), angular=(0, 0), upper_bound=(0, 0), graph_W=None, graph_H=None, graph_lambda=(0, 0),
+    target_H=None, target_lambda=(0, 0), dispersion="per_row", theta_init=0.1, theta_max=5.0, theta_min=0.0,
+    nb_size_init=10.0, nb_size_max=1e6, nb_size_min=0.01, gamma_phi_init=1.0, gamma_phi_max=1e4,
+    gamma_phi_min=1e-6, tweedie_power=1.5, irls_max_iter=5, irls_tol=1e-4, huber_delta=1.0, zi_em_iters=1,
+    solver="auto", cd_tol=1e-8, cd_maxit=100, h_init=None, w_init=None, cv_seed=None, patience=5,
+    cv_k_range=(2, 50), track_train_loss=True, threads=0, resource="auto", norm="L1", sort_model=True,
+    streaming="auto", panel_cols=0, dispatch=None, on_iteration=None, profile=False, convergence="loss",
+    sparse=False)
+
+
+# ------------------------------------------------------------------------------------------------ R's RNG ----
+class RRandom:
+    """R's default generator (Mersenne-Twister + inversion), enough of it for `set.seed(s); runif(n)` — what
+    nmf() draws W from (R/nmf_thin.R:794-795). R-4 src/main/RNG.c: `RNG_Init` scrambles the seed with
+    `seed = 69069 * seed + 1` 50 times, fills dummy[0..624] with the next 625 values of that LCG, `FixupSeeds`
+    sets dummy[0] = mti = 624; `MT_genrand` is the standard MT19937 tempering, scaled by 2.3283064365386963e-10
+    and clamped into (0, 1) by `fixup`. Pinned by the well-known values of set.seed(42) / (1) / (123) in
+    tests/test_nmf_api.py."""
+
+    _I2_32M1 = 2.328306437080797e-10
+
+    def __init__(self, seed: int):
+        s = int(seed) & 0xFFFFFFFF
+        for _ in range(50):
+            s = (69069 * s + 1) & 0xFFFFFFFF
+        words = np.empty(625, np.uint32)
+        for j in range(625):
+            s = (69069 * s + 1) & 0xFFFFFFFF
+            words[j] = s
+        self._bg = np.random.MT19937()
+        st = self._bg.state
+        st["state"]["key"] = words[1:].copy()
+        st["state"]["pos"] = 624
+        self._bg.state = st
+
+    def runif(self, n: int) -> np.ndarray:
+        u = self._bg.random_raw(int(n)).astype(np.float64) * 2.3283064365386963e-10
+        u[u <= 0.0] = 0.5 * self._I2_32M1
+        u[(1.0 - u) <= 0.0] = 1.0 - 0.5 * self._I2_32M1
+        return u
+
+
+# ------------------------------------------------------------------------------------ SplitMix64 (rng.hpp) ----
+_GAMMA = 0x9E3779B97F4A7C15
+
+
+def splitmix_fill_uniform_f64(seed: int, count: int) -> np.ndarray:
+    """`SplitMix64(seed).fill_uniform(double*, ...)` (rng/rng.hpp:73, 89-104, 195-201): element e of the stream is
+    mix(state0 + (e+1)·γ); uniform<double>() = double(next()) / double(UINT64_MAX) (= 2^64 after rounding)."""
+    s0 = 12345 if (seed & 0xFFFFFFFFFFFFFFFF) == 0 else (seed & 0xFFFFFFFFFFFFFFFF)
+    with np.errstate(over="ignore"):
+        z = np.uint64(s0) + np.arange(1, count + 1, dtype=np.uint64) * np.uint64(_GAMMA)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return z.astype(np.float64) / 18446744073709551616.0
+
+
+def bridge_h_init(seed: int, k: int, n: int) -> np.ndarray:
+    """H as the bridge draws it when no h_init is given (gpu/bridge_nmf.hpp:226-229): a fresh double stream seeded
+    `config.seed + 0x9E3779B9u` (32-bit unsigned wrap). Returned as (n, k): row j = column j of the k x n H."""
+    return splitmix_fill_uniform_f64((int(seed) + 0x9E3779B9) & 0xFFFFFFFF, k * n).reshape(n, k)
+
+
+def bridge_w_init(seed: int, k: int, m: int) -> np.ndarray:
+    """W_T when neither seed nor w_init yields a matrix (gpu/bridge_nmf.hpp:216-218). R always sends one, so this is
+    reached only with an SVD-init string, which this mirror refuses; kept for direct callers."""
+    return splitmix_fill_uniform_f64(int(seed) & 0xFFFFFFFF, k * m).reshape(m, k)
+
+
+# -------------------------------------------------------------------------------------------- validation ----
+def _pair(value, name):
+    """validate_penalty (R/nmf_validation.R:64-76)."""
+    v = np.atleast_1d(np.asarray(value, dtype=np.float64))
+    if v.size == 1:
+        v = np.repeat(v, 2)
+    elif v.size != 2:
+        raise ValueError(f"'{name}' must be length 1 or 2 for c(w, h)")
+    if (v < 0).any():
+        raise ValueError(f"'{name}' values must be non-negative")
+    return float(v[0]), float(v[1])
+
+
+def _parse_dots(dots: dict) -> dict:
+    unknown = [k for k in dots if k not in _DOT_DEFAULTS]
+    if unknown:
+        raise TypeError("Unknown parameter(s) passed to nmf(): " + ", ".join(f"'{u}'" for u in unknown)
+                        + ". See ?nmf for valid parameters.")
+    out = dict(_DOT_DEFAULTS)
+    out.update(dots)
+    for name, choices in (("solver", ("auto", "cholesky", "cd")), ("norm", ("L1", "L2", "none"))):
+        if out[name] not in choices:
+            raise ValueError(f"'{name}' should be one of " + ", ".join(f"'{c}'" for c in choices))
+    return out
+
+
+def _refuse(name, why="outside the ALS hot path this library replaces (SURVEY.md §2); use the reference's CPU route"):
+    raise NotImplementedError(f"nmf(): '{name}' is {why}")
+
+
+def _as_csc(data):
+    import scipy.sparse as sp
+    if isinstance(data, str):
+        _refuse("data = <file path>", "file input (.spz streaming and loaders) is outside this library's scope")
+    if isinstance(data, (list, tuple, dict)):
+        _refuse("data = <list>", "multi-modal input (factor_net) is outside this library's scope")
+    if not sp.issparse(data):
+        arr = np.asarray(data)
+        if arr.ndim != 2 or not np.issubdtype(arr.dtype, np.number):
+            raise ValueError("'data' was not coercible to a numeric matrix")
+        _refuse("dense data", "the dense-A path (rcppml_gpu_nmf_dense_unified_float) is out of scope; pass a "
+                              "scipy.sparse matrix (the dgCMatrix route)")
+    A = data.tocsc().astype(np.float32)          # Rcpp_nmf_full: A_mapped.cast<float>()
+    A.sort_indices()
+    if np.isnan(A.data).any():
+        _refuse("NA values in data", "the NA-mask route is not mirrored; pass an explicit mask")
+    return A
+
+
+def _mask_pattern(mask, shape):
+    """validate_mask (R/nmf_validation.R:173-216) -> (pattern CSC or None, mask_zeros)."""
+    import scipy.sparse as sp
+    if mask is None:
+        return None, False
+    if isinstance(mask, (list, tuple)) and not sp.issparse(mask):
+        if len(mask) < 2 or not isinstance(mask[0], str) or mask[0] != "zeros":
+            raise ValueError("'mask' list must be list(\"zeros\", <matrix>)")
+        pat, _ = _mask_pattern(mask[1], shape)
+        return pat, True
+    if isinstance(mask, str):
+        if mask == "zeros":
+            return None, True
+        if mask == "NA":
+            return None, False
+        raise ValueError("'mask' must be NULL, 'zeros', 'NA', a matrix, or list(\"zeros\", <matrix>)")
+    try:
+        M = sp.csc_matrix(mask)
+    except Exception as exc:        # noqa: BLE001
+        raise ValueError("could not coerce the value of 'mask' to a sparse pattern matrix (dgCMatrix)") from exc
+    if M.shape != tuple(shape):
+        raise ValueError("'mask' dimensions must match 'data'")
+    M.eliminate_zeros()
+    M.sort_indices()
+    return (M if M.nnz > 0 else None), False          # has_mask() is false for an empty matrix (core/config.hpp:254)
+
+
+def sort_by_d(w, d, h):
+    """NMFResult::sort (core/result.hpp:169-189): factors in decreasing order of d."""
+    order = np.argsort(-np.asarray(d, dtype=np.float64), kind="stable")
+    return w[:, order], d[order], h[order, :]
+
+
+# ------------------------------------------------------------------------------------------------- result ----
+@dataclass
+class NMFModel:
+    """The reference's S4 class `nmf`: w (m x k), d (k), h (k x n), misc (R/nmf_thin.R:1225-1313)."""
+    w: np.ndarray
+    d: np.ndarray
+    h: np.ndarray
+    misc: dict = field(default_factory=dict)
+
+    def __iter__(self):                      # w, d, h = model
+        return iter((self.w, self.d, self.h))
+
+    def reconstruct(self):
+        return (self.w * self.d) @ self.h
+
+    def predict(self, data, *, L1=0.0, L2=0.0, upper_bound=0.0):
+        """R/predict_nmf.R:48 — project new columns onto w (GPU, fp64)."""
+        from .project import predict
+        return predict(self.w, data, L1=L1, L2=L2, upper_bound=upper_bound)
+
+    def evaluate(self, data, *, mask=None):
+        """R/nmf_methods.R:356 with loss = "mse": mean squared error (over the non-zeros when mask = "zeros")."""
+        from .project import evaluate
+        if mask is not None and mask != "zeros":
+            _refuse("evaluate(mask = <matrix>)", "not mirrored; only NULL and \"zeros\"")
+        return evaluate(data, self.w, self.d, self.h, mask_zeros=(mask == "zeros"))
+
+
+# --------------------------------------------------------------------------------------------------- nmf ----
+def nmf(data, k, tol=1e-4, maxit=100, L1=(0, 0), L2=(0, 0), seed=None, mask=None, loss="mse", nonneg=(True, True),
+        test_fraction=0, verbose=False, projective=False, symmetric=False, zi="none", robust=False, **dots) -> NMFModel:
+    """Non-negative matrix factorisation A ~ w diag(d) h on the GPU (see the module docstring for the mapping)."""
+    start = time.time()
+    p = _parse_dots(dots)
+
+    # ---- arguments whose code paths live outside the hot path (R/nmf_thin.R:278-420) ----
+    if loss != "mse":
+        if loss not in ("gp", "nb", "gamma", "inverse_gaussian", "tweedie"):
+            raise ValueError("'loss' should be one of 'mse', 'gp', 'nb', 'gamma', 'inverse_gaussian', 'tweedie'")
+        _refuse(f"loss = '{loss}'")
+    if zi != "none":
+        if zi not in ("row", "col"):
+            raise ValueError("'zi' should be one of 'none', 'row', 'col'")
+        raise ValueError("zi != 'none' requires loss='gp' or loss='nb'.")
+    if robust is not False and robust != 0:
+        _refuse("robust")
+    if bool(projective) and bool(symmetric):
+        raise ValueError("'projective' and 'symmetric' cannot both be TRUE")
+    if projective:
+        _refuse("projective")
+    if symmetric:
+        _refuse("symmetric")
+    for name in ("graph_W", "graph_H", "target_H", "on_iteration", "dispatch"):
+        if p[name] is not None:
+            _refuse(name)
+    if p["streaming"] is True or p["panel_cols"]:
+        _refuse("streaming")
+    if p["sparse"]:
+        _refuse("sparse")
+    if p["resource"] not in ("auto", "cpu", "gpu"):
+        raise ValueError("'resource' must be \"auto\", \"cpu\", or \"gpu\"")
+    if p["resource"] == "cpu":
+        _refuse("resource = 'cpu'", "not available: this library is the GPU route and has no CPU fallback")
+
+    A = _as_csc(data)
+    m, n = A.shape
+
+    # ---- penalties (validate_all_penalties, R/nmf_validation.R:78-111) ----
+    L1 = _pair(L1, "L1")
+    if max(L1) >= 1 or min(L1) < 0:
+        raise ValueError("L1 penalties must be strictly in the range [0,1)")
+    L2 = _pair(L2, "L2")
+    if max(_pair(p["L21"], "L21")) > 0:
+        _refuse("L21")
+    if max(_pair(p["angular"], "angular")) > 0:
+        _refuse("angular")
+    _pair(p["graph_lambda"], "graph_lambda")
+    upper_bound = _pair(p["upper_bound"], "upper_bound")
+
+    # ---- validate_simple_params / validate_cv_params ----
+    sort_model = p["sort_model"]
+    if not isinstance(sort_model, (bool, np.bool_)):
+        raise ValueError("'sort_model' must be a single logical value")
+    nn = np.atleast_1d(np.asarray(nonneg))
+    if nn.dtype != np.bool_:
+        raise ValueError("'nonneg' must be logical")
+    if nn.size == 1:
+        nn = np.repeat(nn, 2)
+    if nn.size != 2:
+        raise ValueError("'nonneg' must be length 1 or 2 with no NA values")
+    nonneg = (bool(nn[0]), bool(nn[1]))
+    if not np.isscalar(test_fraction) or isinstance(test_fraction, (str, bool)):
+        raise ValueError("'test_fraction' must be a single numeric value")
+    if test_fraction < 0 or test_fraction >= 1:
+        raise ValueError("'test_fraction' must be in the range [0, 1)")
+    patience = p["patience"]
+    if not np.isscalar(patience) or isinstance(patience, str):
+        raise ValueError("'patience' must be a single numeric value")
+
+    mask_pat, mask_zeros = _mask_pattern(mask, (m, n))
+
+    # ---- k ----
+    if isinstance(k, str):
+        if k == "auto":
+            _refuse("k = 'auto'", "rank search is outside this library's scope")
+        raise ValueError("'k' must be a positive integer")
+    if np.size(k) != 1:
+        _refuse("k = <vector>", "multi-rank cross-validation sweeps are outside this library's scope")
+    k = int(np.asarray(k).reshape(-1)[0])
+    if k < 1:
+        raise ValueError("'k' must be a positive integer")
+
+    # ---- solver (R/nmf_thin.R:362-388; the GPU branch of "auto") ----
+    solver = p["solver"]
+    if solver == "auto":
+        solver = "cd" if k <= 32 else "cholesky"
+    solver_mode = {"cd": 0, "cholesky": 1}[solver]
+
+    # ---- seed -> w_init + seed_int (R/nmf_thin.R:723-827) ----
+    w_init = None
+    seed_int = 0
+    if isinstance(seed, str):
+        if seed == "random":
+            seed = None
+        elif seed in ("lanczos", "irlba", "randomized", "svd"):
+            _refuse(f"seed = '{seed}'", "SVD-based initialisation is outside this library's scope")
+        else:
+            raise ValueError(f"Unknown seed string '{seed}'. Valid: NULL, integer, matrix, "
+                             "'lanczos', 'irlba', 'randomized', 'svd'")
+    if seed is None:
+        # R draws from the session's current RNG state; the host equivalent is numpy's global-free default_rng()
+        w_init = np.random.default_rng().random((m, k))
+        head = w_init.T.reshape(-1)[:min(10, w_init.size)]               # R's column-major w_init_mat[1:10]
+        seed_int = int(abs(head.sum() * 1e8) % _INT_MAX)
+    elif isinstance(seed, (list, tuple)):
+        _refuse("seed = <list>", "multiple initialisations are outside this library's scope")
+    elif isinstance(seed, np.ndarray) and seed.ndim == 2:
+        actual_k = seed.shape[1] if seed.shape[0] == m else seed.shape[0]
+        if actual_k != k:
+            raise ValueError(f"Rank mismatch: k={k} specified but custom initialization has rank {actual_k}.")
+        if seed.shape[0] == m:
+            w_init = np.asarray(seed, np.float64)
+        elif seed.shape[1] == m:
+            w_init = np.asarray(seed, np.float64).T
+        else:
+            raise ValueError("Custom init matrix dimensions incompatible with data")
+        seed_int = abs(int(float(np.sum(seed * 1e6)) % _INT_MAX))
+    elif np.size(seed) > 1:
+        _refuse("seed = <vector>", "multiple initialisations are outside this library's scope")
+    elif isinstance(seed, (int, float, np.integer, np.floating)):
+        seed_int = int(seed)
+        w_init = RRandom(seed_int).runif(m * k).reshape(k, m).T          # matrix(runif(m*k), m, k): column-major
+    else:
+        raise ValueError("'seed' must be NULL, an integer, or a matrix")
+
+    if p["w_init"] is not None:
+        wi = np.asarray(p["w_init"], np.float64)
+        if wi.ndim != 2:
+            raise ValueError("w_init must be a matrix")
+        if wi.shape == (m, k):
+            w_init = wi
+        elif wi.shape == (k, m):
+            w_init = wi.T
+        else:
+            raise ValueError("w_init dimensions incompatible with data and k")
+        if seed_int == 0:
+            head = w_init.T.reshape(-1)[:min(10, w_init.size)]
+            seed_int = abs(int(head.sum() * 1e8) % _INT_MAX)
+
+    # Rcpp_nmf_full casts W_init / H_init to float before the bridge widens them again (:419-433)
+    W_T0 = np.ascontiguousarray(w_init, dtype=np.float32)                 # (m, k): row = column of the k x m W_T
+    if p["h_init"] is not None:
+        hi = np.asarray(p["h_init"], np.float64)
+        if hi.shape != (k, n):                                            # bridge_nmf.hpp:221 ignores other shapes
+            raise ValueError("h_init must be a k x n matrix")
+        H0 = np.ascontiguousarray(hi.T, dtype=np.float32)
+    elif test_fraction > 0:
+        H0 = None                                                         # the CV bridge always draws H (:437-440)
+    else:
+        H0 = bridge_h_init(seed_int, k, n)
+
+    # ---- config scalars (build_config_from_params, src/RcppFunctions_nmf.cpp:74-76) ----
+    cd_maxit = int(p["cd_maxit"]) if int(p["cd_maxit"]) > 0 else 10
+    if p["cd_tol"] > 0 and p["cd_tol"] != 1e-8:
+        warnings.warn("cd_tol is not carried by the GPU bridge (gpu/bridge_nmf.hpp:39-75); the engine uses 1e-8",
+                      stacklevel=2)
+    norm_type = {"L1": 0, "L2": 1, "none": 2}[p["norm"]]
+
+    det = gpu_detect()
+    if det["status"] != 0 or det["num_gpus"] < 1:
+        raise _lib.NativeLibraryError("nmf(): no CUDA device (rcppml_gpu_detect) and no CPU fallback in this library")
+
+    misc = dict(loss_type=loss, w_init=w_init, solver_mode=solver_mode, L1=L1, L2=L2, nonneg=nonneg,
+                upper_bound=upper_bound, backend="gpu", seed_int=seed_int)
+
+    if test_fraction > 0:
+        # nmf::nmf -> dispatch_cv -> bridge_nmf_cv_sparse (nmf/fit.hpp:187-203)
+        if mask_pat is not None:
+            _refuse("mask = <matrix> with test_fraction > 0", "not carried by the CV entry (gpu/bridge_nmf.hpp:78-99)")
+        if max(upper_bound) > 0:
+            warnings.warn("upper_bound is not carried by the CV bridge (gpu/bridge_nmf.hpp:78-99) and is ignored",
+                          stacklevel=2)
+        cv_seed = 0 if p["cv_seed"] is None else int(np.atleast_1d(p["cv_seed"])[0])   # cv_seeds.empty() ? 0u
+        if p["h_init"] is not None:
+            warnings.warn("h_init is ignored by the CV bridge (gpu/bridge_nmf.hpp:437-440)", stacklevel=2)
+        H0cv = bridge_h_init(seed_int, k, n)
+        r = bridge_nmf_cv_sparse(A.indptr, A.indices, A.data, m, n, k, W_T0, H0cv, max_iter=int(maxit), tol=tol, L1=L1,
+                                 L2=L2, nonneg=nonneg, cd_maxit=cd_maxit, verbose=verbose, seed=seed_int,
+                                 holdout_fraction=float(np.float32(test_fraction)), cv_seed=cv_seed,
+                                 mask_zeros=mask_zeros, norm_type=norm_type, solver_mode=solver_mode)
+        if r.status != 0:
+            raise _lib.NativeLibraryError("GPU CV NMF bridge call failed (status != 0)")
+        misc.update(train_loss=r.train_loss, test_loss=r.best_test_loss, best_iter=r.best_iter + 1, loss=r.train_loss,
+                    iter=r.iterations, tol=float("nan"), converged=r.converged)
+    else:
+        kw = dict(max_iter=int(maxit), tol=tol, L1=L1, L2=L2, upper_bound=upper_bound, nonneg=nonneg,
+                  cd_maxit=cd_maxit, verbose=verbose, seed=seed_int, patience=5, norm_type=norm_type,
+                  solver_mode=solver_mode)
+        if mask_pat is not None:
+            kw["mask"] = (mask_pat.indptr, mask_pat.indices)
+        r = bridge_nmf_sparse(A.indptr, A.indices, A.data, m, n, k, W_T0, H0, **kw)
+        if r.status != 0:
+            raise _lib.NativeLibraryError("GPU NMF bridge call failed (status != 0)")
+        misc.update(loss=r.train_loss, iter=r.iterations, tol=r.final_tol, converged=r.converged)
+
+    w = r.W_T.astype(np.float64)              # result_to_list casts to double (src/RcppFunctions_nmf.cpp:109-111)
+    h = r.H.astype(np.float64).T.copy()
+    d = r.d.astype(np.float64)
+    if sort_model:
+        w, d, h = sort_by_d(w, d, h)
+    misc["runtime"] = time.time() - start
+    return NMFModel(np.ascontiguousarray(w), d, np.ascontiguousarray(h), misc)
