@@ -6,7 +6,7 @@ reference interface for this path.
 """
 from .engine import Engine, FitResult, make_config, nccl_unique_id  # noqa: F401
 from .bridge import bridge_nmf_cv_sparse, bridge_nmf_sparse, gpu_detect, gpu_nmf_zerocopy  # noqa: F401
-from .nmf import NMFModel, nmf  # noqa: F401
-from .project import evaluate, nnls, predict  # noqa: F401
+from .nmf import NMFModel, nmf, nnls  # noqa: F401
+from .project import evaluate, predict  # noqa: F401
 
 __all__ = ["Engine", "FitResult", "make_config", "nccl_unique_id", "bridge_nmf_sparse", "bridge_nmf_cv_sparse", "gpu_detect", "gpu_nmf_zerocopy", "nmf", "NMFModel", "nnls", "predict", "evaluate"]

@@ -205,17 +205,55 @@ class NMFModel:
     def reconstruct(self):
         return (self.w * self.d) @ self.h
 
-    def predict(self, data, *, L1=0.0, L2=0.0, upper_bound=0.0):
-        """R/predict_nmf.R:48 — project new columns onto w (GPU, fp64)."""
+    def predict(self, data, L1=None, L2=None, mask=None, upper_bound=None, threads=0, verbose=False):
+        """`predict(object, data, ...)` (R/predict_nmf.R:48-98): project new columns onto w (GPU, fp64). Penalties
+        default to the model's own h-side values; returns a new model with the projected h, misc = {projected}.
+        `mask` is validated and then unused, as in the reference (Rcpp_predict never reads it)."""
         from .project import predict
-        return predict(self.w, data, L1=L1, L2=L2, upper_bound=upper_bound)
+        import scipy.sparse as sp
+        if L1 is None:
+            L1 = self.misc["L1"][1] if self.misc.get("L1") is not None else 0
+        if L2 is None:
+            L2 = self.misc["L2"][1] if self.misc.get("L2") is not None else 0
+        if upper_bound is None:
+            upper_bound = self.misc["upper_bound"][1] if self.misc.get("upper_bound") is not None else 0
+        if np.size(L1) != 1:
+            raise ValueError("'L1' must be a single value giving the penalty on 'h'")
+        if L1 >= 1 or L1 < 0:
+            raise ValueError("L1 penalty must be strictly in the range [0,1)")
+        if np.size(L2) != 1:
+            raise ValueError("'L2' must be a single value giving the penalty on 'h'")
+        if L2 < 0:
+            raise ValueError("L2 penalty must be strictly >= 0")
+        A = data.tocsc() if sp.issparse(data) else sp.csc_matrix(np.asarray(data, np.float64))
+        _mask_pattern(mask, A.shape)
+        w = self.w
+        if not (w.shape[0] == A.shape[0]) and w.shape[1] == A.shape[0]:
+            w = w.T
+        if w.shape[0] != A.shape[0]:
+            raise ValueError("dimensions of 'object@w' and 'A' are not compatible")
+        h = predict(w, A, L1=float(L1), L2=float(L2), upper_bound=float(upper_bound))
+        return NMFModel(self.w, self.d, h, dict(projected=True))
 
-    def evaluate(self, data, *, mask=None):
-        """R/nmf_methods.R:356 with loss = "mse": mean squared error (over the non-zeros when mask = "zeros")."""
+    def evaluate(self, data, mask=None, missing_only=False, loss="mse", test_fraction=0, test_seed=None, eval_set="all",
+                 threads=0, verbose=False):
+        """`evaluate(x, data, mask, ...)` (R/nmf_methods.R:332-440 -> Rcpp_evaluate_loss) with loss = "mse": mean
+        squared error over all entries, or over the non-zeros when mask = "zeros" (GPU, fp64, no dense m x n
+        reconstruction). Explicit masks, missing_only and test-set evaluation are not mirrored."""
         from .project import evaluate
-        if mask is not None and mask != "zeros":
+        if eval_set not in ("all", "test", "train"):
+            raise ValueError("'eval_set' should be one of 'all', 'test', 'train'")
+        if missing_only and mask is None:
+            raise ValueError("a mask matrix must be specified to set 'missing_only = TRUE'")
+        if loss not in ("mse", "gp"):
+            raise ValueError("'loss' should be one of 'mse', 'gp'")
+        if loss != "mse":
+            _refuse("evaluate(loss = 'gp')")
+        if test_fraction > 0 or test_seed is not None or eval_set != "all":
+            _refuse("evaluate(test_fraction / test_seed / eval_set)", "not mirrored")
+        if mask is not None and not (isinstance(mask, str) and mask == "zeros"):
             _refuse("evaluate(mask = <matrix>)", "not mirrored; only NULL and \"zeros\"")
-        return evaluate(data, self.w, self.d, self.h, mask_zeros=(mask == "zeros"))
+        return evaluate(data, self.w, self.d, self.h, mask_zeros=(mask is not None))
 
 
 # --------------------------------------------------------------------------------------------------- nmf ----
@@ -422,3 +460,85 @@ def nmf(data, k, tol=1e-4, maxit=100, L1=(0, 0), L2=(0, 0), seed=None, mask=None
         w, d, h = sort_by_d(w, d, h)
     misc["runtime"] = time.time() - start
     return NMFModel(np.ascontiguousarray(w), d, np.ascontiguousarray(h), misc)
+
+
+# -------------------------------------------------------------------------------------------------- nnls ----
+def nnls(w=None, h=None, A=None, L1=(0, 0), L2=(0, 0), loss="mse", upper_bound=(0, 0), nonneg=(True, True), threads=0,
+         verbose=False, **dots):
+    """Mirror of the reference's `nnls()` (R/solve.R:60-360) over `rcppml_gpu_nnls_double` (c_nnls,
+    src/RcppFunctions_utils.cpp:314-366; fp64 like the reference).
+
+    Exactly one of `w` (m x k: solve A ~ w h for h, k x n) or `h` (k x n: solve for w, m x k, as the transposed problem
+    `c_nnls(t(h), t(A))`) is given. Pairs are c(w, h): solving for h uses the second element, solving for w the first
+    (R/solve.R:305-309, 330-334). A factor passed in the other orientation is transposed automatically (:236-247).
+    `...`: cd_maxit (100), cd_tol (1e-8), warm_start. Non-MSE losses, L21, angular and targets go through a one-iteration
+    nmf() in the reference (:136-184) and are refused here."""
+    from . import project
+    import scipy.sparse as sp
+    known = dict(L21=(0, 0), angular=(0, 0), cd_maxit=100, cd_tol=1e-8, warm_start=None, target_H=None,
+                 target_lambda=(0, 0))
+    unknown = [k for k in dots if k not in known]
+    if unknown:
+        raise TypeError("Unknown parameter(s) passed to nnls(): " + ", ".join(f"'{u}'" for u in unknown)
+                        + ". See ?nnls for valid parameters.")
+    known.update(dots)
+    if w is not None and h is not None and A is None:                 # deprecated nnls(w, A) positional form (:79-87)
+        warnings.warn("nnls(w, A) 2-positional-arg form is deprecated.\nUse nnls(w = ..., A = ...) to solve for H, or "
+                      "nnls(h = ..., A = ...) to solve for W.", DeprecationWarning, stacklevel=2)
+        A, h = h, None
+    if w is None and h is None:
+        raise ValueError("Either 'w' or 'h' must be provided (not both NULL)")
+    if w is not None and h is not None:
+        raise ValueError("Exactly one of 'w' or 'h' must be NULL (cannot provide both)")
+    if A is None:
+        raise ValueError("argument \"A\" is missing, with no default")
+    solve_for_h = w is not None
+    rep2 = lambda v: tuple(np.repeat(np.atleast_1d(v), 2)) if np.size(v) == 1 else tuple(np.atleast_1d(v))
+    L1, L2, upper_bound, nonneg = rep2(L1), rep2(L2), rep2(upper_bound), rep2(nonneg)
+    if loss != "mse" or any(np.asarray(rep2(known["L21"])) != 0) or any(np.asarray(rep2(known["angular"])) != 0) or (
+            known["target_H"] is not None and any(np.asarray(rep2(known["target_lambda"])) != 0)):
+        _refuse("nnls(loss / L21 / angular / target_H)")
+    if isinstance(A, str):
+        _refuse("A = <file path>", "file input is outside this library's scope")
+    if any(v < 0 for v in L1) or any(v >= 1 for v in L1):
+        raise ValueError("L1 penalty must be in range [0, 1)")
+    if any(v < 0 for v in L2):
+        raise ValueError("L2 penalty must be >= 0")
+    if any(v < 0 for v in upper_bound):
+        raise ValueError("upper_bound must be >= 0")
+    A = A.tocsc() if sp.issparse(A) else sp.csc_matrix(np.asarray(A, np.float64))   # zeros add nothing to w^T a_j
+    F = np.asarray(w if solve_for_h else h, np.float64)
+    if F.ndim != 2:
+        raise ValueError("factor matrix must be a matrix")
+    m, n = A.shape
+    if solve_for_h:
+        if F.shape[0] != m and F.shape[1] == m:
+            F = F.T
+        if F.shape[0] != m:
+            raise ValueError(f"Incompatible dimensions: nrow(w) = {F.shape[0]} but nrow(A) = {m} and no rownames/colnames "
+                             "available for matching")
+    else:
+        if F.shape[1] != n and F.shape[0] == n:
+            F = F.T
+        if F.shape[1] != n:
+            raise ValueError(f"Incompatible dimensions: ncol(h) = {F.shape[1]} but ncol(A) = {n} and no rownames/colnames "
+                             "available for matching")
+    ws = known["warm_start"]
+    kw = dict(cd_maxit=int(known["cd_maxit"]), cd_tol=float(known["cd_tol"]))
+    if solve_for_h:
+        if ws is not None:
+            ws = np.asarray(ws, np.float64)
+            if ws.shape != (F.shape[1], n):
+                raise ValueError(f"warm_start dimensions ({ws.shape[0]} x {ws.shape[1]}) don't match expected output "
+                                 f"dimensions ({F.shape[1]} x {n})")
+        return project.nnls(F, A, L1=float(L1[1]), L2=float(L2[1]), upper_bound=float(upper_bound[1]),
+                            nonneg=bool(nonneg[1]), warm_start=ws, **kw)
+    if ws is not None:
+        # R/solve.R:291-292 expects nrow(A) x ncol(h) (= m x n) here and hands its transpose to c_nnls, whose
+        # `G * h` then has mismatched shapes: the reference's warm start is not usable when solving for w.
+        _refuse("warm_start with h = ...", "not usable in the reference either (R/solve.R:291-298 vs c_nnls)")
+    At = A.T.tocsc()
+    At.sort_indices()
+    w_T = project.nnls(np.ascontiguousarray(F.T), At, L1=float(L1[0]), L2=float(L2[0]), upper_bound=float(upper_bound[0]),
+                       nonneg=bool(nonneg[0]), **kw)
+    return w_T.T.copy()

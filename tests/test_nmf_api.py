@@ -102,6 +102,32 @@ def test_sort_by_d_is_result_sort():
     assert np.array_equal(ws, w[:, [1, 0, 2]]) and np.array_equal(hs, h[[1, 0, 2], :])
 
 
+def test_nnls_argument_validation_uses_the_reference_messages():
+    """R/solve.R:89-96, 211-213, 282-298."""
+    import rcppml_b200 as rb
+    A = random_csc(30, 20, 0.3, 1)
+    w, h = np.ones((30, 4)), np.ones((4, 20))
+    cases = [
+        (dict(A=A), ValueError, "Either 'w' or 'h' must be provided (not both NULL)"),
+        (dict(w=w, h=h, A=A), ValueError, "Exactly one of 'w' or 'h' must be NULL (cannot provide both)"),
+        (dict(w=w, A=A, L1=1.0), ValueError, "L1 penalty must be in range [0, 1)"),
+        (dict(w=w, A=A, L2=(-1, 0)), ValueError, "L2 penalty must be >= 0"),
+        (dict(w=w, A=A, upper_bound=-1), ValueError, "upper_bound must be >= 0"),
+        (dict(w=np.ones((7, 4)), A=A), ValueError, "Incompatible dimensions: nrow(w) = 7 but nrow(A) = 30"),
+        (dict(h=np.ones((4, 7)), A=A), ValueError, "Incompatible dimensions: ncol(h) = 7 but ncol(A) = 20"),
+        (dict(w=w, A=A, warm_start=np.ones((3, 20))), ValueError, "warm_start dimensions (3 x 20) don't match expected "
+                                                                 "output dimensions (4 x 20)"),
+        (dict(w=w, A=A, bogus=1), TypeError, "Unknown parameter(s) passed to nnls(): 'bogus'"),
+        (dict(w=w, A=A, loss="gp"), NotImplementedError, "nnls(loss"),
+        (dict(w=w, A=A, L21=0.1), NotImplementedError, "nnls(loss"),
+        (dict(h=h, A=A, warm_start=np.ones((30, 4))), NotImplementedError, "warm_start with h"),
+    ]
+    for kw, exc, msg in cases:
+        with pytest.raises(exc) as e:
+            rb.nnls(**kw)
+        assert msg in str(e.value), (kw, str(e.value))
+
+
 # ------------------------------------------------------------------------------------------------ GPU ----
 def _oracle_twin(oracle, A, k, seed, **kw):
     """What the reference's CPU loop computes from the inputs nmf() hands to the bridge."""
@@ -180,8 +206,10 @@ def test_nmf_invariants_of_the_reference_tests():
     mse = m1.evaluate(A)
     dense = A.toarray().astype(np.float64)
     assert abs(mse - np.mean((dense - m1.reconstruct()) ** 2)) <= 1e-6 * max(mse, 1e-12)
-    hp = m1.predict(A)
-    assert hp.shape == (6, 150) and hp.min() >= 0
+    proj = m1.predict(A)
+    assert proj.h.shape == (6, 150) and proj.h.min() >= 0 and proj.misc == dict(projected=True) and proj.w is m1.w
+    mz = np.mean((dense - m1.reconstruct())[dense != 0] ** 2)
+    assert abs(m1.evaluate(A, mask="zeros") - mz) <= 1e-6 * mz
 
 
 @pytest.mark.gpu
@@ -224,3 +252,33 @@ def test_nmf_test_fraction_runs_the_cv_entry(oracle, mask, solver):
     assert rel_err(model.w, ref.W_T) <= RTOL and rel_err(model.h, ref.H.T) <= RTOL and rel_err(model.d, ref.d) <= RTOL
     assert abs(model.misc["test_loss"] - ref.best_test_loss) <= 1e-5 * abs(ref.best_test_loss)
     assert abs(model.misc["train_loss"] - ref.train_loss) <= 1e-5 * abs(ref.train_loss)
+
+
+@pytest.mark.gpu
+def test_nnls_solves_for_h_and_for_w(oracle):
+    """nnls(w =, A =) and nnls(h =, A =) (R/solve.R:300-360): c_nnls on A, resp. on the transposed problem with the
+    w-side penalties; factor orientation is fixed up automatically; the old positional form still works."""
+    import rcppml_b200 as rb
+    m, n, k = 260, 170, 9
+    A = random_csc(m, n, 0.1, 41, counts=True, ragged=True)
+    rng = np.random.default_rng(3)
+    w, h = rng.random((m, k)), rng.random((k, n))
+    Ax = A.data.astype(np.float64)
+    ref_h = oracle.project_f64(A.indptr, A.indices, Ax, m, n, w, L1=0.02, L2=0.1, upper_bound=0.5)          # (n, k)
+    got_h = rb.nnls(w=w, A=A, L1=(0.3, 0.02), L2=(0.0, 0.1), upper_bound=(0.0, 0.5))
+    assert got_h.shape == (k, n) and rel_err(got_h.T, ref_h) <= 1e-9
+    assert np.array_equal(rb.nnls(w=w.T.copy(), A=A, L1=(0.3, 0.02), L2=(0.0, 0.1), upper_bound=(0.0, 0.5)), got_h)
+    with pytest.warns(DeprecationWarning):
+        old = rb.nnls(w, A)
+    assert rel_err(old.T, oracle.project_f64(A.indptr, A.indices, Ax, m, n, w)) <= 1e-9
+    dense = rb.nnls(w=w, A=A.toarray())
+    assert np.array_equal(dense, old)
+    At = A.T.tocsc()
+    At.sort_indices()
+    ref_w = oracle.project_f64(At.indptr, At.indices, At.data.astype(np.float64), n, m, np.ascontiguousarray(h.T),
+                               L1=0.05, nonneg=False)                                                      # (m, k)
+    got_w = rb.nnls(h=h, A=A, L1=(0.05, 0.4), nonneg=(False, True))
+    assert got_w.shape == (m, k) and rel_err(got_w, ref_w) <= 1e-9
+    h0 = rng.random((k, n)) * 0.1
+    ref_ws = oracle.project_f64(A.indptr, A.indices, Ax, m, n, w, warm_start=h0.T, cd_maxit=5)
+    assert rel_err(rb.nnls(w=w, A=A, warm_start=h0, cd_maxit=5).T, ref_ws) <= 1e-9
