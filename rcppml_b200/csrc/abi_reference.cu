@@ -7,6 +7,9 @@
 #include <cstdlib>
 #include <memory>
 #include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
 
 namespace {
 
@@ -47,6 +50,93 @@ struct EngineLease {
     }
     b200::Engine& get() { return *e; }
 };
+
+// ---- RCPPML_NUM_GPUS: multi-GPU behind the single-process reference caller (SURVEY.md §8b "Multi-GPU knob", §8e) ----
+// The bridge signature has no device-count argument and R calls it from one thread of one process, so the knob is an
+// environment variable read here (default 1; "all" or 0 = every usable device, capped at 8). With G > 1 the call runs
+// the same sharded ALS as the one-process-per-GPU path (engine.cu: column block of H + row block of W_T per device,
+// solved columns stored straight into every replica over NVLink, one-shot peer-memory all-reduces), with one Engine
+// per device and one host thread per Engine inside this process; peers are plain device pointers after
+// cudaDeviceEnablePeerAccess — no NCCL, no IPC. Every device receives the whole matrix over its own PCIe link and
+// slices its two operands out of the device transpose. Results are bit-identical to one GPU.
+// STATUS (round 1): compiled and reviewed, NOT yet run on a multi-GPU box (tools/gpu_jobs/round2_inprocess_multigpu.sh).
+int usable_devices(int* ids, int cap) {
+    int count = 0, usable = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) return 0;
+    for (int dev = 0; dev < count && usable < cap; ++dev) {
+        cudaDeviceProp prop{};
+        if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess && prop.major >= 10) ids[usable++] = dev;
+    }
+    return usable;
+}
+
+int requested_gpus() {
+    const char* env = std::getenv("RCPPML_NUM_GPUS");
+    if (!env || !env[0]) return 1;
+    if (std::string(env) == "all") return 8;
+    const int v = std::atoi(env);
+    return v <= 0 ? 8 : std::min(v, 8);
+}
+
+// Returns false (after warn) on any failure; fills res / W / H / d from rank 0 on success.
+bool fit_in_process_multi_gpu(int G, const int* devices, int m, int n, int64_t nnz, const int* col_ptr, const int* row_idx,
+                              const double* values, int k, double* W, double* H, double* d, const rcppml_b200_config& cfg,
+                              rcppml_b200_result* res) {
+    std::vector<std::unique_ptr<b200::Engine>> eng(G);
+    std::vector<std::string> err(G);
+    auto run_all = [&](auto&& body) {
+        std::vector<std::thread> th;
+        for (int g = 0; g < G; ++g)
+            th.emplace_back([&, g] {
+                try { body(g); }
+                catch (const std::exception& ex) { err[g] = ex.what()[0] ? ex.what() : "error"; }
+                catch (...) { err[g] = "unknown error"; }
+            });
+        for (auto& t : th) t.join();
+        for (int g = 0; g < G; ++g)
+            if (!err[g].empty()) { warn(("multi-GPU rank " + std::to_string(g) + ": " + err[g]).c_str()); return false; }
+        return true;
+    };
+    bool ok = run_all([&](int g) {                             // phase 1: data on every device, exchange buffers
+        eng[g].reset(new b200::Engine(devices[g]));
+        eng[g]->comm_init_local(g, G);
+        eng[g]->set_matrix_host_shard<double>(m, n, nnz, col_ptr, row_idx, values);
+        eng[g]->set_factors_host<double>(k, W, H);
+        eng[g]->comm_prepare_local(devices);
+    });
+    if (ok) {
+        std::vector<b200::Engine*> all(G);
+        for (int g = 0; g < G; ++g) all[g] = eng[g].get();
+        try { for (int g = 0; g < G; ++g) eng[g]->comm_attach_local(all.data()); }
+        catch (const std::exception& ex) { warn(ex.what()); ok = false; }
+    }
+    std::vector<rcppml_b200_result> rr(G);
+    if (ok) ok = run_all([&](int g) {                          // phase 2: the loop (peers meet in the exchange kernels)
+        eng[g]->begin_fit(cfg);
+        eng[g]->iterate(cfg.max_iter);
+        eng[g]->get_result(&rr[g]);
+        if (g == 0 && rr[0].status == 0) eng[0]->get_factors_host<double>(W, H, d);
+    });
+    if (ok)
+        for (int g = 0; g < G; ++g)
+            if (rr[g].status != 0) {
+                warn(rr[g].status == 2 ? "multi-GPU exchange timed out (a peer stopped)" : "Gram matrix not positive definite (Cholesky pivot <= 0)");
+                ok = false;
+                break;
+            }
+    if (ok) {
+        *res = rr[0];
+        for (int i = 0; i < 5; ++i) g_phases[i] = eng[0]->phase_ms[i];
+    }
+    for (int g = 0; g < G; ++g) {                              // destroy on the owning device, peers still alive
+        if (!eng[g]) continue;
+        cudaSetDevice(devices[g]);
+        cudaDeviceSynchronize();
+    }
+    eng.clear();
+    cudaSetDevice(0);
+    return ok;
+}
 
 }  // namespace
 
@@ -385,16 +475,6 @@ static void nmf_unified_impl(
         int count = 0;
         if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) { warn("no CUDA device"); return; }
 
-        EngineLease lease(0);
-        b200::Engine& E = lease.get();
-        if (mask_p && mask_i && mask_nnz && *mask_nnz > 0) {
-            E.set_matrix_host<double>(*m, *n, static_cast<int64_t>(*nnz), col_ptr, row_idx, values);
-            E.set_mask(*mask_nnz, mask_p, mask_i);
-            E.set_factors_host<double>(*k, W, H);
-        } else {
-            E.set_matrix_and_factors_host<double, double>(*m, *n, static_cast<int64_t>(*nnz), col_ptr, row_idx, values, *k, W, H);
-        }
-
         rcppml_b200_config cfg{};
         cfg.k = *k;
         cfg.max_iter = *max_iter;
@@ -410,12 +490,33 @@ static void nmf_unified_impl(
         cfg.patience = *patience;
         cfg.verbose = *verbose;
 
-        E.begin_fit(cfg);
-        E.iterate(cfg.max_iter);
+        const bool masked = mask_p && mask_i && mask_nnz && *mask_nnz > 0;
+        int devices[8];
+        int G = 1;                                                      // masked path: single GPU
+        if (!masked && requested_gpus() > 1) G = std::min(requested_gpus(), usable_devices(devices, 8));
         rcppml_b200_result res{};
-        E.get_result(&res);
-        if (res.status != 0) { warn("Gram matrix not positive definite (Cholesky pivot <= 0)"); return; }
-        E.get_factors_host<double>(W, H, d);
+        std::unique_ptr<EngineLease> lease_holder;
+        if (G > 1) {
+            std::lock_guard<std::mutex> guard(g_mu);
+            if (!fit_in_process_multi_gpu(G, devices, *m, *n, static_cast<int64_t>(*nnz), col_ptr, row_idx, values, *k, W, H, d,
+                                          cfg, &res))
+                return;
+        } else {
+            lease_holder.reset(new EngineLease(0));
+            b200::Engine& E = lease_holder->get();
+            if (masked) {
+                E.set_matrix_host<double>(*m, *n, static_cast<int64_t>(*nnz), col_ptr, row_idx, values);
+                E.set_mask(*mask_nnz, mask_p, mask_i);
+                E.set_factors_host<double>(*k, W, H);
+            } else {
+                E.set_matrix_and_factors_host<double, double>(*m, *n, static_cast<int64_t>(*nnz), col_ptr, row_idx, values, *k, W, H);
+            }
+            E.begin_fit(cfg);
+            E.iterate(cfg.max_iter);
+            E.get_result(&res);
+            if (res.status != 0) { warn("Gram matrix not positive definite (Cholesky pivot <= 0)"); return; }
+            E.get_factors_host<double>(W, H, d);
+        }
 
         if (out_theta_len) *out_theta_len = 0;
         if (out_iter) *out_iter = res.iterations;
@@ -425,7 +526,7 @@ static void nmf_unified_impl(
         if (*verbose)
             std::fprintf(stderr, "[RcppML_gpu/b200] %d iterations, loss %.6g, loop %.3f ms, %d launches\n",
                          res.iterations, res.train_loss, res.loop_ms, res.gpu_launches);
-        lease.commit();
+        if (lease_holder) lease_holder->commit();
         *out_status = 0;
     } catch (const std::exception& ex) {
         warn(ex.what());

@@ -41,13 +41,56 @@ void Engine::comm_init(int rank_, int world_, const char* id128) {
 void Engine::comm_ipc_close() {
     if (!peers_ready) return;
     cudaStreamSynchronize(stream);
-    for (int r = 0; r < world; ++r) {
+    for (int r = 0; r < world && !peers_local; ++r) {
         if (r == rank) continue;
         cudaIpcCloseMemHandle(peer_W[r]);
         cudaIpcCloseMemHandle(peer_H[r]);
         cudaIpcCloseMemHandle(peer_x[r]);
     }
     peers_ready = false;
+    peers_local = false;
+}
+
+// ---- in-process multi-GPU (abi_reference.cu: RCPPML_NUM_GPUS) ------------------------------------------------
+void Engine::comm_init_local(int rank_, int world_) {
+    use_device();
+    B200_REQUIRE(world_ >= 1 && world_ <= 8 && rank_ >= 0 && rank_ < world_, "comm_init_local: bad rank/world");
+    B200_REQUIRE(!matrix_ready && !factors_ready, "comm_init_local must come first: blocks and padding depend on (rank, world)");
+    rank = rank_;
+    world = world_;
+}
+
+void Engine::comm_prepare_local(const int* devices) {
+    use_device();
+    B200_REQUIRE(world > 1 && factors_ready, "comm_prepare_local: needs comm_init_local and allocated factors");
+    comm_ipc_close();
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) continue;
+        int can = 0;
+        B200_CUDA_CHECK(cudaDeviceCanAccessPeer(&can, device, devices[r]));
+        B200_REQUIRE(can, "comm_prepare_local: no peer access between the selected devices (NVLink / NVSwitch required)");
+        const cudaError_t e = cudaDeviceEnablePeerAccess(devices[r], 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+        else B200_CUDA_CHECK(e);
+    }
+    xchg_ne_max = KP * KP;
+    xbuf.ensure(static_cast<size_t>(2) * world * xchg_ne_max + 16);
+    B200_CUDA_CHECK(cudaMemsetAsync(xbuf.ptr, 0, xbuf.bytes(), stream));
+    B200_CUDA_CHECK(cudaStreamSynchronize(stream));
+    xchg_seq = 0;
+}
+
+void Engine::comm_attach_local(Engine* const* all) {
+    B200_REQUIRE(world > 1 && xbuf.ptr != nullptr, "comm_attach_local: call comm_prepare_local on every engine first");
+    for (int r = 0; r < world; ++r) {
+        B200_REQUIRE(all[r] && all[r]->world == world && all[r]->rank == r && all[r]->KP == KP && all[r]->xbuf.ptr,
+                     "comm_attach_local: engines do not form one group");
+        peer_W[r] = all[r]->W_T.ptr;
+        peer_H[r] = all[r]->H.ptr;
+        peer_x[r] = all[r]->xbuf.ptr;
+    }
+    peers_local = true;
+    peers_ready = true;
 }
 
 void Engine::comm_destroy() {

@@ -308,18 +308,21 @@ void Engine::set_dims(int m_, int n_) {
     npanels[0] = npanels[1] = 1;
 }
 
-void Engine::finish_matrix() {
-    // tr(AᵀA) in fp64 (primitives/primitives.hpp:101-115) over this rank's column block, then over ranks
+void Engine::finish_matrix() { finish_matrix_from(Ax.ptr, nnz, world > 1); }
+
+void Engine::finish_matrix_from(const float* vals, int64_t vcnt, bool reduce_over_ranks) {
+    // tr(AᵀA) in fp64 (primitives/primitives.hpp:101-115) over the given values (this rank's column block, then
+    // summed over ranks — or the whole matrix when every device holds it, set_matrix_host_shard)
     const int nb = 1024;
     struct { double* ptr; } part{scratch<double>(6, nb)};
-    sumsq_kernel<<<nb, 256, 0, stream>>>(Ax.ptr, nnz, part.ptr);
+    sumsq_kernel<<<nb, 256, 0, stream>>>(vals, vcnt, part.ptr);
     std::vector<double> hp(nb);
     B200_CUDA_CHECK(cudaMemcpyAsync(hp.data(), part.ptr, nb * sizeof(double), cudaMemcpyDeviceToHost, stream));
     B200_CUDA_CHECK(cudaStreamSynchronize(stream));
     double s = 0.0;
     for (double v : hp) s += v;
-    double cnt = static_cast<double>(nnz);
-    if (world > 1) {
+    double cnt = static_cast<double>(vcnt);
+    if (reduce_over_ranks) {
         DeviceBuffer<double> t;
         t.ensure(2);
         const double h[2] = {s, cnt};
@@ -437,6 +440,50 @@ void Engine::set_matrix_sharded(int m_, int n_, const int* cb_ptr, const int* cb
 }
 template void Engine::set_matrix_sharded<float>(int, int, const int*, const int*, const float*, const int*, const int*, const float*);
 template void Engine::set_matrix_sharded<double>(int, int, const int*, const int*, const double*, const int*, const int*, const double*);
+
+// In-process multi-GPU: every device receives the whole host matrix (its own PCIe link), transposes it on the device
+// and keeps two contiguous slices — columns J of A and columns I of Aᵀ (= rows I of A, inner = global column id,
+// ascending: the same operand set_matrix_sharded builds from a host-extracted row block). tr(AᵀA) is taken over the
+// whole matrix with the single-GPU reduction, so it is bit-identical to a one-GPU fit without any exchange.
+__global__ void rebase_pointers_kernel(const int* __restrict__ src, int count, int base, int* __restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) dst[i] = src[i] - base;
+}
+
+template <class ValT>
+void Engine::set_matrix_host_shard(int m_, int n_, int64_t nnz_, const int* col_ptr, const int* row_idx, const ValT* values) {
+    use_device();
+    B200_REQUIRE(world > 1, "set_matrix_host_shard: needs comm_init / comm_init_local first");
+    set_dims(m_, n_);
+    DeviceBuffer<int> fp, fi, tp, ti;
+    DeviceBuffer<float> fx, tx;
+    upload_csc<ValT>(n, nnz_, col_ptr, row_idx, values, fp, fi, fx);
+    transpose_csc(fp.ptr, fi.ptr, fx.ptr, n, m, nnz_, tp, ti, tx, 0);
+    auto slice = [&](const DeviceBuffer<int>& sp, const DeviceBuffer<int>& si, const DeviceBuffer<float>& sx, int first,
+                     int count, DeviceBuffer<int>& dp, DeviceBuffer<int>& di, DeviceBuffer<float>& dx) -> int64_t {
+        int ends[2] = {0, 0};
+        B200_CUDA_CHECK(cudaMemcpyAsync(&ends[0], sp.ptr + first, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        B200_CUDA_CHECK(cudaMemcpyAsync(&ends[1], sp.ptr + first + count, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        B200_CUDA_CHECK(cudaStreamSynchronize(stream));
+        const int64_t cnt = static_cast<int64_t>(ends[1]) - ends[0];
+        dp.ensure(static_cast<size_t>(std::max(count, 1)) + 1);
+        di.ensure(std::max<int64_t>(cnt, 1) + 4);
+        dx.ensure(std::max<int64_t>(cnt, 1) + 4);
+        rebase_pointers_kernel<<<(count + 1 + 255) / 256, 256, 0, stream>>>(sp.ptr + first, count + 1, ends[0], dp.ptr);
+        if (cnt > 0) {
+            B200_CUDA_CHECK(cudaMemcpyAsync(di.ptr, si.ptr + ends[0], cnt * sizeof(int), cudaMemcpyDeviceToDevice, stream));
+            B200_CUDA_CHECK(cudaMemcpyAsync(dx.ptr, sx.ptr + ends[0], cnt * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+        }
+        B200_CUDA_CHECK(cudaGetLastError());
+        return cnt;
+    };
+    nnz = slice(fp, fi, fx, col_begin, n_loc, Ap, Ai, Ax);
+    nnz_w = slice(tp, ti, tx, row_begin, m_loc, Atp, Ati, Atx);
+    finish_matrix_from(fx.ptr, nnz_, false);               // host-synchronised at its end: the temporaries may go
+    has_mask = false;
+}
+template void Engine::set_matrix_host_shard<float>(int, int, int64_t, const int*, const int*, const float*);
+template void Engine::set_matrix_host_shard<double>(int, int, int64_t, const int*, const int*, const double*);
 
 // SURVEY.md §8d generator. Columns [c0, c0+nc), rows kept in [r0, r1) and stored relative to r0.
 void Engine::synth_block(int m_, int c0, int nc, int r0, int r1, double density, uint64_t seed, DeviceBuffer<int>& dp,
@@ -1224,7 +1271,7 @@ void Engine::begin_fit(const rcppml_b200_config& c) {
     use_device();
     B200_REQUIRE(matrix_ready && factors_ready, "begin_fit: matrix and factors must be set first");
     normalize_cfg(c);
-    B200_REQUIRE(world == 1 || comm_ready(), "begin_fit: communicator not initialised");
+    B200_REQUIRE(world == 1 || comm_ready() || peers_ready, "begin_fit: communicator not initialised");
     iters_enqueued = 0;
     drop_iteration_graph();                                                 // new configuration / buffers
     graphs_enabled = true;

@@ -75,6 +75,16 @@ public:
     void comm_ipc_export(char* handles192);
     void comm_ipc_import(const char* all_handles /* world x 192 bytes, rank-major */);
     void comm_ipc_close();
+    // In-process multi-GPU (RCPPML_NUM_GPUS behind the reference entry points, abi_reference.cu): one Engine per
+    // device inside ONE process, each driven by its own host thread. No NCCL and no IPC: the peers' buffers are
+    // plain device pointers once peer access is enabled, and the peer-memory loop is the only loop.
+    void comm_init_local(int rank, int world);
+    void comm_prepare_local(const int* devices);          // exchange buffer + cudaDeviceEnablePeerAccess to every peer
+    void comm_attach_local(Engine* const* all);           // after EVERY engine ran comm_prepare_local
+    // The whole host matrix goes to this device; the engine keeps its column block and its row block of the device
+    // transpose (both are contiguous slices), so no host-side transposition or extraction is needed.
+    template <class ValT>
+    void set_matrix_host_shard(int m, int n, int64_t nnz, const int* col_ptr, const int* row_idx, const ValT* values);
 
     // ---- state (public: the C ABI shims read it) ------------------------------------------
     int device = 0;
@@ -166,6 +176,7 @@ public:
     ncclComm* comm = nullptr;
     int rank = 0, world = 1;
     bool peers_ready = false;
+    bool peers_local = false;         // peers live in this process (comm_attach_local): nothing to IPC-close
     float* peer_W[8] = {};            // every rank's W_T / H / exchange buffer (own pointers at [rank])
     float* peer_H[8] = {};
     double* peer_x[8] = {};
@@ -178,6 +189,7 @@ private:
 
     void set_dims(int m, int n);
     void finish_matrix();
+    void finish_matrix_from(const float* vals, int64_t cnt, bool reduce_over_ranks);
     void transpose_csc(const int* sp, const int* si, const float* sx, int ncols, int nrows, int64_t cnt,
                        DeviceBuffer<int>& dp, DeviceBuffer<int>& di, DeviceBuffer<float>& dx, int col_id_offset);
     template <class ValT>

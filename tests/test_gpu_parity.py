@@ -618,3 +618,37 @@ def test_cv_reference_abi(oracle):
     assert rel_err(out.W_T, ref.W_T) <= RTOL and rel_err(out.H, ref.H) <= RTOL and rel_err(out.d, ref.d) <= RTOL
     assert abs(out.test_loss - ref.test_loss) <= 1e-5 * abs(ref.test_loss)
     assert abs(out.best_test_loss - ref.best_test_loss) <= 1e-5 * abs(ref.best_test_loss)
+
+
+def test_in_process_multi_gpu_behind_the_reference_entry_is_bit_identical():
+    """RCPPML_NUM_GPUS (SURVEY.md §8b "Multi-GPU knob"): the single-process reference caller gets the sharded
+    peer-memory loop with one engine + one host thread per device (abi_reference.cu). Needs >= 2 GPUs with peer
+    access; run in a child process so that a failure cannot wedge the suite."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    code = r'''
+import os, sys, numpy as np
+sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
+import rcppml_b200 as rb
+from helpers import random_csc
+for (m, n, k, solver, kw) in [(900, 500, 16, 0, {}), (1201, 777, 64, 1, dict(L1=(0.01, 0.02), L2=(0.0, 0.01))), (640, 333, 8, 1, dict(upper_bound=(0.2, 0.3)))]:
+    A = random_csc(m, n, 0.05, 5 + k, ragged=True)
+    rng = np.random.default_rng(k)
+    W0, H0 = rng.random((m, k)), rng.random((n, k))
+    os.environ.pop("RCPPML_NUM_GPUS", None)
+    one = rb.bridge_nmf_sparse(A.indptr, A.indices, A.data, m, n, k, W0, H0, max_iter=7, tol=0.0, solver_mode=solver, **kw)
+    for G in ("2", "all"):
+        os.environ["RCPPML_NUM_GPUS"] = G
+        many = rb.bridge_nmf_sparse(A.indptr, A.indices, A.data, m, n, k, W0, H0, max_iter=7, tol=0.0, solver_mode=solver, **kw)
+        assert one.status == 0 and many.status == 0, (G, one.status, many.status)
+        assert np.array_equal(one.W_T, many.W_T) and np.array_equal(one.H, many.H) and np.array_equal(one.d, many.d), (G, m, n, k)
+        assert one.iterations == many.iterations and one.train_loss == many.train_loss
+print("INPROCESS_MULTIGPU_OK")
+'''
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600,
+                         cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert out.returncode == 0 and "INPROCESS_MULTIGPU_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
