@@ -78,11 +78,23 @@ int requested_gpus() {
     return v <= 0 ? 8 : std::min(v, 8);
 }
 
-// Returns false (after warn) on any failure; fills res / W / H / d from rank 0 on success.
+// The engines of the last multi-GPU call are kept (grow-only device buffers, like the single-GPU cache) and reused
+// when the next call asks for the same devices; any failure drops them. Guarded by g_mu.
+std::vector<std::unique_ptr<b200::Engine>> g_multi;
+std::vector<int> g_multi_devices;
+
+// Returns false (after warn) on any failure; fills res / W / H / d from rank 0 on success. Caller holds g_mu.
 bool fit_in_process_multi_gpu(int G, const int* devices, int m, int n, int64_t nnz, const int* col_ptr, const int* row_idx,
                               const double* values, int k, double* W, double* H, double* d, const rcppml_b200_config& cfg,
                               rcppml_b200_result* res) {
-    std::vector<std::unique_ptr<b200::Engine>> eng(G);
+    const char* env = std::getenv("RCPPML_B200_CACHE");
+    const bool cache = !(env && env[0] == '0');
+    if (!(cache && static_cast<int>(g_multi.size()) == G && g_multi_devices == std::vector<int>(devices, devices + G))) {
+        g_multi.clear();
+        g_multi.resize(G);
+        g_multi_devices.assign(devices, devices + G);
+    }
+    std::vector<std::unique_ptr<b200::Engine>>& eng = g_multi;
     std::vector<std::string> err(G);
     auto run_all = [&](auto&& body) {
         std::vector<std::thread> th;
@@ -98,8 +110,10 @@ bool fit_in_process_multi_gpu(int G, const int* devices, int m, int n, int64_t n
         return true;
     };
     bool ok = run_all([&](int g) {                             // phase 1: data on every device, exchange buffers
-        eng[g].reset(new b200::Engine(devices[g]));
-        eng[g]->comm_init_local(g, G);
+        if (!eng[g]) {
+            eng[g].reset(new b200::Engine(devices[g]));
+            eng[g]->comm_init_local(g, G);
+        }
         eng[g]->set_matrix_host_shard<double>(m, n, nnz, col_ptr, row_idx, values);
         eng[g]->set_factors_host<double>(k, W, H);
         eng[g]->comm_prepare_local(devices);
@@ -128,12 +142,15 @@ bool fit_in_process_multi_gpu(int G, const int* devices, int m, int n, int64_t n
         *res = rr[0];
         for (int i = 0; i < 5; ++i) g_phases[i] = eng[0]->phase_ms[i];
     }
-    for (int g = 0; g < G; ++g) {                              // destroy on the owning device, peers still alive
+    for (int g = 0; g < G; ++g) {                              // every device idle before anything is reused or freed
         if (!eng[g]) continue;
         cudaSetDevice(devices[g]);
         cudaDeviceSynchronize();
     }
-    eng.clear();
+    if (!ok || !cache) {                                       // never reuse engines in an unknown state
+        g_multi.clear();
+        g_multi_devices.clear();
+    }
     cudaSetDevice(0);
     return ok;
 }
@@ -541,6 +558,8 @@ static void nmf_unified_impl(
 int rcppml_b200_release_cache(void) {
     std::lock_guard<std::mutex> g(g_mu);
     g_engine.reset();
+    g_multi.clear();
+    g_multi_devices.clear();
     return 0;
 }
 // Host wall-clock (ms) of the phases of the last reference-ABI call: matrix upload (+fp64->fp32), device
