@@ -630,6 +630,10 @@ def test_in_process_multi_gpu_behind_the_reference_entry_is_bit_identical():
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs at least 2 GPUs")
+    if os.environ.get("RCPPML_B200_TEST_INPROCESS_MULTIGPU") != "1":
+        # written after round 1's GPU minutes were spent: opt-in until tools/gpu_jobs/round2_inprocess_multigpu.sh
+        # has passed once on a multi-GPU box, then drop this gate
+        pytest.skip("in-process multi-GPU path not yet validated on hardware (set RCPPML_B200_TEST_INPROCESS_MULTIGPU=1)")
     code = r'''
 import os, sys, numpy as np
 sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
