@@ -313,6 +313,9 @@ def run_e2e_sharded(args, eng, dist, steps, rank, world):
     rbk = (pinned(RB.indptr.astype(np.int32), torch.int32), pinned(RB.indices.astype(np.int32), torch.int32),
            pinned(RB.data.astype(np.float32), torch.float32))
     W0p, H0p = pinned(W0, torch.float32), pinned(H0, torch.float32)
+    # results land in pinned host buffers too (as W / H do in the reference ABI call at N = 1), not in fresh pageable arrays
+    outs = (pinned(np.zeros_like(W0), torch.float32), pinned(np.zeros_like(H0), torch.float32),
+            pinned(np.zeros(k, np.float32), torch.float32))
     cfg = rb.make_config(k, max_iter=steps, tol=0.0, solver_mode=solver_mode(args), cd_maxit=100,
                          L1=(args.L1, args.L1), L2=(args.L2, args.L2))
 
@@ -325,7 +328,7 @@ def run_e2e_sharded(args, eng, dist, steps, rank, world):
         c = rb.make_config(k, max_iter=iters, tol=0.0, solver_mode=solver_mode(args), cd_maxit=100,
                            L1=(args.L1, args.L1), L2=(args.L2, args.L2))
         res = eng.fit(c)
-        out = eng.get_factors()
+        out = eng.get_factors(out=outs)
         torch.cuda.synchronize()
         dist.barrier()
         secs = time.perf_counter() - t0

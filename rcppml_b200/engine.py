@@ -151,10 +151,19 @@ class Engine:
         _lib.check(self._lib.rcppml_b200_init_factors(self._h, k, seed, h_col_begin), "init_factors")
         self.k = k
 
-    def get_factors(self):
-        W_T = np.empty((self.m, self.k), np.float32)
-        H = np.empty((self.n, self.k), np.float32)
-        d = np.empty(self.k, np.float32)
+    def get_factors(self, out=None):
+        """Returns (W_T (m, k), H (n, k), d (k)) as float32. `out`: optional preallocated (W_T, H, d) C-contiguous
+        float32 arrays of those shapes (e.g. pinned memory) that receive the copies instead of fresh arrays."""
+        if out is not None:
+            W_T, H, d = out
+            for a, shape in ((W_T, (self.m, self.k)), (H, (self.n, self.k)), (d, (self.k,))):
+                if not (isinstance(a, np.ndarray) and a.dtype == np.float32 and a.shape == shape
+                        and a.flags.c_contiguous and a.flags.writeable):
+                    raise ValueError(f"get_factors(out=...): expected a writeable C-contiguous float32 array of shape {shape}")
+        else:
+            W_T = np.empty((self.m, self.k), np.float32)
+            H = np.empty((self.n, self.k), np.float32)
+            d = np.empty(self.k, np.float32)
         _lib.check(self._lib.rcppml_b200_get_factors_f32(self._h, _p(W_T, C.c_float), _p(H, C.c_float),
                                                          _p(d, C.c_float)), "get_factors")
         return W_T, H, d
