@@ -36,7 +36,10 @@ void rcppml_gpu_detect(int* num_gpus, double* total_mem_mb, double* free_mem_mb,
  * Supported: loss_type 0 (MSE), solver_mode 0 (CD) / !=0 (Cholesky+clip), L1/L2, upper
  * bounds, nonneg flags, norm_type 0/1/2. Anything else (L21, ortho, graph, guides,
  * projective, symmetric, non-MSE loss, k > 128) sets *out_status = -1 so that the
- * reference gateway (nmf/fit.hpp:125-133) takes its CPU path; there is no CPU fallback here. */
+ * reference gateway (nmf/fit.hpp:125-133) takes its CPU path; there is no CPU fallback here.
+ * Environment: RCPPML_NUM_GPUS = G | "all" (default 1) runs the fit sharded over G devices inside this
+ * one call (one engine + host thread per device, NVLink peer memory); the signature carries no device
+ * count (core/config.hpp:86 `max_gpus` is dead). Same results, bit for bit. */
 void rcppml_gpu_nmf_unified_float(
     const int* col_ptr, const int* row_idx, const double* values,
     int* m, int* n, int* nnz, int* k,
