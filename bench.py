@@ -52,6 +52,9 @@ def parse_args():
     ap.add_argument("--L1", type=float, default=0.0, help="L1 penalty on both factors (C5: 0.01)")
     ap.add_argument("--L2", type=float, default=0.0, help="L2 penalty on both factors (C5: 0.01)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-blocks", action="store_true",
+                    help="N > 1: block-wise factor I/O in the e2e leg (each rank moves only its own blocks over PCIe; "
+                         "experiment, off by default until measured)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--also-cd", action="store_true", help="(default now) append the secondary solver_mode=0 measurement")
     ap.add_argument("--no-cd", action="store_true", help="skip the secondary solver_mode=0 (coordinate descent) measurement")
@@ -314,7 +317,11 @@ def run_e2e_sharded(args, eng, dist, steps, rank, world):
            pinned(RB.data.astype(np.float32), torch.float32))
     W0p, H0p = pinned(W0, torch.float32), pinned(H0, torch.float32)
     # results land in pinned host buffers too (as W / H do in the reference ABI call at N = 1), not in fresh pageable arrays
-    outs = (pinned(np.zeros_like(W0), torch.float32), pinned(np.zeros_like(H0), torch.float32),
+    blocks = bool(getattr(args, "e2e_blocks", False))
+    if blocks:                                            # only this rank's rows of W_T / H cross PCIe, both ways
+        W0p = pinned(W0[eng.row_begin:eng.row_begin + eng.m_loc], torch.float32)
+        H0p = pinned(H0[eng.col_begin:eng.col_begin + eng.n_loc], torch.float32)
+    outs = (pinned(np.zeros_like(W0p), torch.float32), pinned(np.zeros_like(H0p), torch.float32),
             pinned(np.zeros(k, np.float32), torch.float32))
     cfg = rb.make_config(k, max_iter=steps, tol=0.0, solver_mode=solver_mode(args), cd_maxit=100,
                          L1=(args.L1, args.L1), L2=(args.L2, args.L2))
@@ -324,11 +331,11 @@ def run_e2e_sharded(args, eng, dist, steps, rank, world):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         eng.set_matrix_sharded(m, n, cb, rbk)
-        eng.set_factors(W0p, H0p)
+        (eng.set_factor_blocks if blocks else eng.set_factors)(W0p, H0p)
         c = rb.make_config(k, max_iter=iters, tol=0.0, solver_mode=solver_mode(args), cd_maxit=100,
                            L1=(args.L1, args.L1), L2=(args.L2, args.L2))
         res = eng.fit(c)
-        out = eng.get_factors(out=outs)
+        out = (eng.get_factor_blocks if blocks else eng.get_factors)(out=outs)
         torch.cuda.synchronize()
         dist.barrier()
         secs = time.perf_counter() - t0
@@ -348,7 +355,9 @@ def run_e2e_sharded(args, eng, dist, steps, rank, world):
             "iters_per_sec": steps / secs,
             "note": f"sharded engine API on {world} ranks from pinned host buffers: H2D of each rank's column + row "
                     f"block (fp32) and of the initial factors, device transpose, {steps} iterations, D2H of the "
-                    "factors on every rank; wall clock between barriers, max over ranks; bytes summed over ranks / steps"}
+                    "factors on every rank; wall clock between barriers, max over ranks; bytes summed over ranks / steps"
+                    + ("; --e2e-blocks: every rank moves only its own factor blocks, replicas completed by an NVLink "
+                       "all-gather" if blocks else "")}
 
 
 def main():

@@ -278,6 +278,12 @@ int rcppml_b200_set_factors_f64(rcppml_b200_engine* e, int k, const double* W_T,
 int rcppml_b200_init_factors(rcppml_b200_engine* e, int k, uint32_t seed, int h_col_begin);
 int rcppml_b200_get_factors_f32(rcppml_b200_engine* e, float* W_T, float* H, float* d);
 int rcppml_b200_get_factors_f64(rcppml_b200_engine* e, double* W_T, double* H, double* d);
+/* Sharded fits: only this rank's blocks cross PCIe — W_blk is k x m_loc (rows [row_begin, row_begin + m_loc) of W_T),
+ * H_blk is k x n_loc (columns [col_begin, col_begin + n_loc) of H), see rcppml_b200_get_shard. set_: the replicas on
+ * every rank are completed by one all-gather per factor over NVLink (every rank must call it). With one rank the
+ * blocks are the whole factors. */
+int rcppml_b200_set_factor_blocks_f32(rcppml_b200_engine* e, int k, const float* W_blk, const float* H_blk);
+int rcppml_b200_get_factor_blocks_f32(rcppml_b200_engine* e, float* W_blk, float* H_blk, float* d);
 
 /* nmf_fit loop (nmf/fit_cpu.hpp:444-1825). begin_fit resets iteration state (iter = 0);
  * iterate enqueues up to n_iters further ALS iterations and returns after they finished. */

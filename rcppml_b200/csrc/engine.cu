@@ -728,6 +728,57 @@ void Engine::get_factors_host(T* W_T_host, T* H_host, T* d_host) {
 template void Engine::get_factors_host<float>(float*, float*, float*);
 template void Engine::get_factors_host<double>(double*, double*, double*);
 
+// Block-wise factor I/O for sharded fits (world > 1; with world == 1 the blocks are the whole factors). Upload: own
+// blocks into place in the zero-filled replicas, then one in-place all-gather per factor (equal padded blocks, NCCL).
+template <class T>
+void Engine::set_factor_blocks_host(int k_, const T* W_blk, const T* H_blk) {
+    use_device();
+    B200_REQUIRE(world == 1 || comm_ready(), "set_factor_blocks: needs the communicator (comm_init)");
+    alloc_factors(k_);
+    const auto t0 = std::chrono::steady_clock::now();
+    auto upload = [&](const T* src, float* dst, long long ncols) {
+        if (ncols <= 0) return;
+        struct { T* ptr; } tmp{scratch<T>(0, static_cast<size_t>(ncols) * k)};
+        B200_CUDA_CHECK(cudaMemcpyAsync(tmp.ptr, src, static_cast<size_t>(ncols) * k * sizeof(T), cudaMemcpyHostToDevice, stream));
+        const long long total = ncols * KP;
+        pad_convert_kernel<T><<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(tmp.ptr, dst, ncols, k, KP);
+        B200_CUDA_CHECK(cudaStreamSynchronize(stream));
+        h2d_bytes += static_cast<size_t>(ncols) * k * sizeof(T);
+    };
+    upload(W_blk, W_T.ptr + static_cast<size_t>(row_begin) * KP, m_loc);
+    upload(H_blk, H.ptr + static_cast<size_t>(col_begin) * KP, n_loc);
+    if (world > 1) {
+        allgather_rows(W_T.ptr, m_pad / world, RCPPML_B200_SEC_COMM);
+        allgather_rows(H.ptr, n_pad / world, RCPPML_B200_SEC_COMM);
+        B200_CUDA_CHECK(cudaStreamSynchronize(stream));
+    }
+    phase_ms[2] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+template void Engine::set_factor_blocks_host<float>(int, const float*, const float*);
+template void Engine::set_factor_blocks_host<double>(int, const double*, const double*);
+
+template <class T>
+void Engine::get_factor_blocks_host(T* W_blk, T* H_blk, T* d_host) {
+    use_device();
+    B200_REQUIRE(factors_ready, "no factors");
+    const auto t0 = std::chrono::steady_clock::now();
+    auto download = [&](const float* src, T* dst, long long ncols) {
+        if (!dst || ncols <= 0) return;
+        struct { T* ptr; } tmp{scratch<T>(0, static_cast<size_t>(ncols) * k)};
+        const long long total = ncols * k;
+        unpad_convert_kernel<T><<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(src, tmp.ptr, ncols, k, KP);
+        B200_CUDA_CHECK(cudaMemcpyAsync(dst, tmp.ptr, static_cast<size_t>(total) * sizeof(T), cudaMemcpyDeviceToHost, stream));
+        B200_CUDA_CHECK(cudaStreamSynchronize(stream));
+        d2h_bytes += static_cast<size_t>(total) * sizeof(T);
+    };
+    download(W_T.ptr + static_cast<size_t>(row_begin) * KP, W_blk, m_loc);
+    download(H.ptr + static_cast<size_t>(col_begin) * KP, H_blk, n_loc);
+    download(d.ptr, d_host, 1);
+    phase_ms[4] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+template void Engine::get_factor_blocks_host<float>(float*, float*, float*);
+template void Engine::get_factor_blocks_host<double>(double*, double*, double*);
+
 // ---- profiling sections -----------------------------------------------------------------------
 void Engine::sec_begin(int sec, cudaStream_t on) {
     if (!profiling) return;
@@ -1506,6 +1557,12 @@ int rcppml_b200_get_factors_f32(rcppml_b200_engine* e, float* W_T, float* H, flo
 }
 int rcppml_b200_get_factors_f64(rcppml_b200_engine* e, double* W_T, double* H, double* d) {
     B200_API_BEGIN e->impl.get_factors_host<double>(W_T, H, d); B200_API_END
+}
+int rcppml_b200_set_factor_blocks_f32(rcppml_b200_engine* e, int k, const float* W_blk, const float* H_blk) {
+    B200_API_BEGIN e->impl.set_factor_blocks_host<float>(k, W_blk, H_blk); B200_API_END
+}
+int rcppml_b200_get_factor_blocks_f32(rcppml_b200_engine* e, float* W_blk, float* H_blk, float* d) {
+    B200_API_BEGIN e->impl.get_factor_blocks_host<float>(W_blk, H_blk, d); B200_API_END
 }
 int rcppml_b200_begin_fit(rcppml_b200_engine* e, const rcppml_b200_config* cfg) {
     B200_API_BEGIN e->impl.begin_fit(*cfg); B200_API_END

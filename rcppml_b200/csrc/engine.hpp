@@ -57,6 +57,10 @@ public:
     void set_matrix_and_factors_host(int m, int n, int64_t nnz, const int* col_ptr, const int* row_idx, const ValT* values,
                                      int k, const T* W_T, const T* H);
     template <class T> void get_factors_host(T* W_T, T* H, T* d);
+    // Sharded fits: move only this rank's blocks over PCIe — rows [row_begin, row_begin + m_loc) of W_T and columns
+    // [col_begin, col_begin + n_loc) of H; the replicas are completed by one all-gather per factor over NVLink.
+    template <class T> void set_factor_blocks_host(int k, const T* W_blk, const T* H_blk);
+    template <class T> void get_factor_blocks_host(T* W_blk, T* H_blk, T* d);
     void init_factors(int k, uint32_t seed, int h_col_begin);
 
     // fit

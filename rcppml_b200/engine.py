@@ -168,6 +168,34 @@ class Engine:
                                                          _p(d, C.c_float)), "get_factors")
         return W_T, H, d
 
+    def set_factor_blocks(self, W_blk, H_blk):
+        """Sharded fits: upload only this rank's rows of W_T ((m_loc, k), rows row_begin..) and of H ((n_loc, k),
+        columns col_begin..); the library completes the replicas with one all-gather per factor over NVLink.
+        Collective: every rank must call it."""
+        W_blk = np.ascontiguousarray(W_blk, dtype=np.float32)
+        H_blk = np.ascontiguousarray(H_blk, dtype=np.float32)
+        if W_blk.shape[0] != self.m_loc or H_blk.shape[0] != self.n_loc or W_blk.shape[1] != H_blk.shape[1]:
+            raise ValueError(f"set_factor_blocks: expected ({self.m_loc}, k) and ({self.n_loc}, k)")
+        self.k = W_blk.shape[1]
+        _lib.check(self._lib.rcppml_b200_set_factor_blocks_f32(self._h, self.k, _p(W_blk, C.c_float),
+                                                               _p(H_blk, C.c_float)), "set_factor_blocks")
+
+    def get_factor_blocks(self, out=None):
+        """This rank's blocks of the fitted factors: (W_T[row_begin : row_begin + m_loc], H[col_begin : col_begin +
+        n_loc], d). `out` as in get_factors."""
+        shapes = ((self.m_loc, self.k), (self.n_loc, self.k), (self.k,))
+        if out is not None:
+            for a, shape in zip(out, shapes):
+                if not (isinstance(a, np.ndarray) and a.dtype == np.float32 and a.shape == shape
+                        and a.flags.c_contiguous and a.flags.writeable):
+                    raise ValueError(f"get_factor_blocks(out=...): expected a writeable C-contiguous float32 array of shape {shape}")
+            W_blk, H_blk, d = out
+        else:
+            W_blk, H_blk, d = (np.empty(s_, np.float32) for s_ in shapes)
+        _lib.check(self._lib.rcppml_b200_get_factor_blocks_f32(self._h, _p(W_blk, C.c_float), _p(H_blk, C.c_float),
+                                                               _p(d, C.c_float)), "get_factor_blocks")
+        return W_blk, H_blk, d
+
     # ---- fit
     def begin_fit(self, cfg: Config):
         _lib.check(self._lib.rcppml_b200_begin_fit(self._h, C.byref(cfg)), "begin_fit")

@@ -83,6 +83,40 @@ def main():
         if rank == 0:
             print(f"k={k} solver={solver} world={world} p2p={p2p} tiled={tiled}: bit-identical={exact} {errs}", flush=True)
         assert max(errs.values()) <= 1e-5, errs
+    if os.environ.get("RCPPML_B200_TEST_ROUND2") == "1":
+        # block-wise factor I/O (written after round 1's GPU minutes were spent; opt-in until it has passed once):
+        # a fit started from set_factor_blocks equals one started from set_factors, bit for bit, and get_factor_blocks
+        # returns this rank's slices of the replicated factors.
+        os.environ["RCPPML_B200_TILED"] = "1"
+        k, iters = 20, 3
+        cfg = rb.make_config(k, max_iter=iters, tol=0.0, solver_mode=0)
+        rng = np.random.default_rng(7)
+        W0, H0 = rng.random((m, k), dtype=np.float32), rng.random((n, k), dtype=np.float32)
+        outs = []
+        for blocks in (False, True):
+            eng = rb.Engine(local)
+            uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                uid.copy_(torch.frombuffer(bytearray(rb.nccl_unique_id()), dtype=torch.uint8))
+            dist.broadcast(uid, 0)
+            eng.comm_init(rank, world, uid.cpu().numpy().tobytes())
+            eng.set_matrix_synthetic_sharded(m, n, dens, synth.SEED_A)
+            if blocks:
+                eng.set_factor_blocks(W0[eng.row_begin:eng.row_begin + eng.m_loc], H0[eng.col_begin:eng.col_begin + eng.n_loc])
+            else:
+                eng.set_factors(W0, H0)
+            assert eng.comm_enable_p2p(dist)
+            res = eng.fit(cfg)
+            assert res.iterations == iters and res.status == 0
+            W, H, d = eng.get_factors()
+            Wb, Hb, db = eng.get_factor_blocks()
+            assert np.array_equal(Wb, W[eng.row_begin:eng.row_begin + eng.m_loc])
+            assert np.array_equal(Hb, H[eng.col_begin:eng.col_begin + eng.n_loc]) and np.array_equal(db, d)
+            eng.close()
+            outs.append((W, H, d))
+        assert all(np.array_equal(a, b) for a, b in zip(outs[0], outs[1])), "set_factor_blocks changes the fit"
+        if rank == 0:
+            print("block-wise factor I/O: bit-identical", flush=True)
     dist.barrier()
     if rank == 0:
         print(f"MULTIGPU_CHECK_OK world={world} worst_rel_err={worst:.3e}", flush=True)

@@ -630,10 +630,10 @@ def test_in_process_multi_gpu_behind_the_reference_entry_is_bit_identical():
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs at least 2 GPUs")
-    if os.environ.get("RCPPML_B200_TEST_INPROCESS_MULTIGPU") != "1":
+    if os.environ.get("RCPPML_B200_TEST_ROUND2") != "1":
         # written after round 1's GPU minutes were spent: opt-in until tools/gpu_jobs/round2_inprocess_multigpu.sh
         # has passed once on a multi-GPU box, then drop this gate
-        pytest.skip("in-process multi-GPU path not yet validated on hardware (set RCPPML_B200_TEST_INPROCESS_MULTIGPU=1)")
+        pytest.skip("in-process multi-GPU path not yet validated on hardware (set RCPPML_B200_TEST_ROUND2=1)")
     code = r'''
 import os, sys, numpy as np
 sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
@@ -656,3 +656,26 @@ print("INPROCESS_MULTIGPU_OK")
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600,
                          cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert out.returncode == 0 and "INPROCESS_MULTIGPU_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_factor_blocks_on_one_gpu_are_the_whole_factors(oracle):
+    """rcppml_b200_set/get_factor_blocks_f32 with a single rank: the blocks are the whole factors, so the fit and the
+    round trip must equal set_factors / get_factors bit for bit. (The multi-rank case lives in tests/multigpu_check.py.)"""
+    import os
+    import rcppml_b200 as rb
+    if os.environ.get("RCPPML_B200_TEST_ROUND2") != "1":
+        pytest.skip("block-wise factor I/O not yet validated on hardware (set RCPPML_B200_TEST_ROUND2=1)")
+    m, n, k = 500, 300, 12
+    A = random_csc(m, n, 0.05, 17, ragged=True)
+    W0, H0 = oracle.initialize_factors(k, m, n, 42)
+    outs = []
+    for blocks in (False, True):
+        e = rb.Engine(0)
+        try:
+            e.set_matrix(m, n, A.indptr, A.indices, A.data)
+            (e.set_factor_blocks if blocks else e.set_factors)(W0, H0)
+            e.fit(rb.make_config(k, max_iter=4, tol=0.0, solver_mode=1))
+            outs.append(e.get_factor_blocks() if blocks else e.get_factors())
+        finally:
+            e.close()
+    assert all(np.array_equal(a, b) for a, b in zip(outs[0], outs[1]))
