@@ -54,9 +54,12 @@ class PackedCall:
                  cd_maxit=100, verbose=False, seed=42, loss_every=1, patience=5, loss_type=0, norm_type=0,
                  projective=False, symmetric=False, solver_mode=0, mask=None):
         lib = _lib.load()
-        assert col_ptr.dtype == np.int32 and row_idx.dtype == np.int32
-        assert values.dtype == np.float64 and W.dtype == np.float64 and H.dtype == np.float64
-        assert W.shape == (m, k) and H.shape == (n, k) and W.flags.c_contiguous and H.flags.c_contiguous
+        if col_ptr.dtype != np.int32 or row_idx.dtype != np.int32:
+            raise TypeError("PackedCall: col_ptr / row_idx must be int32 (the wire format, bridge_nmf.hpp:39-41)")
+        if values.dtype != np.float64 or W.dtype != np.float64 or H.dtype != np.float64:
+            raise TypeError("PackedCall: values / W / H must be float64 (the wire format)")
+        if W.shape != (m, k) or H.shape != (n, k) or not (W.flags.c_contiguous and H.flags.c_contiguous):
+            raise ValueError(f"PackedCall: W must be C-contiguous ({m}, {k}) and H ({n}, {k})")
         nnz = int(col_ptr[n])
         self.W, self.H = W, H
         self.d = np.ones(k, dtype=np.float64)                                 # :208
@@ -224,7 +227,8 @@ def gpu_nmf_zerocopy(col_ptr_addr: int, row_idx_addr: int, values_addr: int, m, 
     lib = _lib.load()
     W = np.array(W_T0, dtype=np.float64, order="C")
     H = np.array(H0, dtype=np.float64, order="C")
-    assert W.shape == (m, k) and H.shape == (n, k)
+    if W.shape != (m, k) or H.shape != (n, k):
+        raise ValueError(f"gpu_nmf_zerocopy: W_T0 must be ({m}, {k}) and H0 ({n}, {k})")
     d = np.ones(k, dtype=np.float64)
     I, D = C.c_int, C.c_double
     dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))

@@ -142,7 +142,8 @@ class Engine:
     def set_factors(self, W_T, H):
         W_T = np.ascontiguousarray(W_T, dtype=np.float32)
         H = np.ascontiguousarray(H, dtype=np.float32)
-        assert W_T.shape[0] == self.m and H.shape[0] == self.n and W_T.shape[1] == H.shape[1]
+        if W_T.ndim != 2 or H.ndim != 2 or W_T.shape[0] != self.m or H.shape[0] != self.n or W_T.shape[1] != H.shape[1]:
+            raise ValueError(f"set_factors: expected W_T ({self.m}, k) and H ({self.n}, k)")
         self.k = W_T.shape[1]
         _lib.check(self._lib.rcppml_b200_set_factors_f32(self._h, self.k, _p(W_T, C.c_float), _p(H, C.c_float)),
                    "set_factors")

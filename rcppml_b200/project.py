@@ -32,11 +32,13 @@ def nnls(w, A, *, L1=0.0, L2=0.0, upper_bound=0.0, nonneg=True, cd_maxit=100, cd
     lib = _lib.load()
     indptr, indices, data, (m, n) = _csc(A)
     w_T = np.ascontiguousarray(np.asarray(w, np.float64))           # (m, k) C-order == k x m column-major
-    assert w_T.shape[0] == m
+    if w_T.ndim != 2 or w_T.shape[0] != m:
+        raise ValueError(f"nnls: w must have {m} rows (one per row of A)")
     k = w_T.shape[1]
     if warm_start is not None:
         h = np.ascontiguousarray(np.asarray(warm_start, np.float64).T).copy()     # (n, k)
-        assert h.shape == (n, k)
+        if h.shape != (n, k):
+            raise ValueError(f"nnls: warm_start must be ({k}, {n})")
     else:
         h = np.zeros((n, k), np.float64)
     if indices.size == 0:
@@ -69,7 +71,8 @@ def evaluate(A, w, d, h, *, mask_zeros=False):
     hh = np.ascontiguousarray(np.asarray(h, np.float64).T)
     dd = np.ascontiguousarray(np.asarray(d, np.float64))
     k = w_T.shape[1]
-    assert w_T.shape == (m, k) and hh.shape == (n, k) and dd.shape == (k,)
+    if w_T.shape != (m, k) or hh.shape != (n, k) or dd.shape != (k,):
+        raise ValueError(f"evaluate: expected w ({m}, k), d (k,), h (k, {n})")
     if indices.size == 0:
         indices, data = np.zeros(1, np.int32), np.zeros(1, np.float64)
     I, D = C.c_int, C.c_double
