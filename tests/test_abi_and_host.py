@@ -138,3 +138,83 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "nnz/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]
+
+
+def test_bench_sharded_e2e_host_logic(monkeypatch):
+    """bench.run_e2e_sharded (the N > 1 end-to-end leg) with a stand-in engine and process group: the host code path the
+    driver's scaling run takes — pinned staging of the blocks, result buffers handed to get_factors(out=...), byte
+    accounting — for the default and the --e2e-blocks variant. No CUDA: pinned allocation and device tensors are mapped
+    to plain host ones for the duration of the test."""
+    import sys
+    import types
+    import scipy.sparse as sp
+    import torch
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    import bench
+    real_empty, real_tensor = torch.empty, torch.tensor
+    monkeypatch.setattr(torch, "empty", lambda *a, **k: real_empty(*a, **{x: y for x, y in k.items() if x != "pin_memory"}))
+    monkeypatch.setattr(torch, "tensor", lambda *a, **k: real_tensor(*a, **{x: y for x, y in k.items() if x != "device"}))
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    m, n, k = 60, 40, 4
+    A = sp.random(m, n, density=0.2, format="csc", dtype=np.float32, random_state=np.random.default_rng(0))
+    A.sort_indices()
+    T = A[:30, :].tocsc().T.tocsc()
+    T.sort_indices()
+    calls = []
+
+    class Eng:
+        n, m, m_loc, n_loc, row_begin, col_begin, nnz_global = 40, 60, 30, 20, 0, 20, A.nnz
+
+        def get_matrix(self):
+            return A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data
+
+        def get_matrix_t(self):
+            return T.indptr.astype(np.int32), T.indices.astype(np.int32), T.data
+
+        def get_factors(self, out=None):
+            if out is None:
+                return np.ones((m, k), np.float32), np.ones((n, k), np.float32), np.ones(k, np.float32)
+            assert [o.shape for o in out] == [(m, k), (n, k), (k,)] and all(o.dtype == np.float32 for o in out)
+            calls.append("get_factors")
+            return out
+
+        def get_factor_blocks(self, out=None):
+            assert [o.shape for o in out] == [(30, k), (20, k), (k,)]
+            calls.append("get_factor_blocks")
+            return out
+
+        def set_matrix_sharded(self, m_, n_, cb, rbk):
+            assert len(cb) == 3 and len(rbk) == 3 and rbk[0].shape == (n + 1,)
+
+        def set_factors(self, W, H):
+            calls.append(("set_factors", W.shape, H.shape))
+
+        def set_factor_blocks(self, W, H):
+            calls.append(("set_factor_blocks", W.shape, H.shape))
+
+        def fit(self, c):
+            return types.SimpleNamespace(status=0, iterations=c.max_iter)
+
+    class Dist:
+        class ReduceOp:
+            MAX = 0
+
+        def barrier(self):
+            pass
+
+        def all_reduce(self, t, op=None):
+            pass
+
+    for blocks in (False, True):
+        calls.clear()
+        args = types.SimpleNamespace(m=m, k=k, L1=0.0, L2=0.0, solver="cholesky", e2e_blocks=blocks)
+        r = bench.run_e2e_sharded(args, Eng(), Dist(), 3, 0, 2)
+        assert r["value"] > 0 and r["unit"] == "nnz/s" and r["h2d_bytes_per_step"] > 0 and r["d2h_bytes_per_step"] > 0
+        if blocks:
+            assert calls == [("set_factor_blocks", (30, k), (20, k)), "get_factor_blocks"] * 2
+            assert r["d2h_bytes_per_step"] == (30 * k * 4 + 20 * k * 4 + 4 * k) // 3
+        else:
+            assert calls == [("set_factors", (m, k), (n, k)), "get_factors"] * 2
+            assert r["d2h_bytes_per_step"] == (m * k * 4 + n * k * 4 + 4 * k) // 3
