@@ -7,12 +7,13 @@ float) and the call reaches the GPU exactly as `nmf::nmf` does with plan = GPU (
 through the dlsym bridge's packing (gpu/bridge_nmf.hpp:199-393; rcppml_b200/bridge.py is its ctypes twin) into
 `rcppml_gpu_nmf_unified_float` / `rcppml_gpu_nmf_cv_unified_float` of RcppML_gpu.so.
 
-What is mirrored: sparse `data`, scalar `k`, `tol`, `maxit`, `L1`, `L2`, `seed` (NULL / integer / W matrix),
+What is mirrored: sparse `data`, scalar `k`, `tol`, `maxit`, `L1`, `L2`, `seed` (NULL / integer / W matrix / vector of
+seeds or list of W matrices = several initialisations, best loss kept),
 `mask` (NULL / "zeros" / pattern matrix / list("zeros", matrix)), `nonneg`, `test_fraction`, and from `...`:
 `upper_bound`, `norm`, `solver`, `cd_maxit`, `cd_tol`, `h_init`, `w_init`, `cv_seed`, `patience`, `sort_model`,
 `resource`, `threads`. Everything the reference routes elsewhere (non-MSE losses, robust/zi, L21 / angular / graph /
 target penalties, projective / symmetric, rank vectors and k = "auto", SVD-based init strings, streaming .spz,
-multi-init seed lists, dense input) raises NotImplementedError naming the argument: SURVEY.md §2 marks them out of
+dense input) raises NotImplementedError naming the argument: SURVEY.md §2 marks them out of
 scope and there is NO CPU fallback behind this function — where the reference would fall back to its CPU loop
 (nmf/fit.hpp:118-127), this one raises `NativeLibraryError`.
 
@@ -109,6 +110,11 @@ def bridge_w_init(seed: int, k: int, m: int) -> np.ndarray:
 
 
 # -------------------------------------------------------------------------------------------- validation ----
+class _SeedOnly(int):
+    """config.seed for one run of a multi-initialisation fit: the W matrix comes through `w_init`, so the scalar-seed
+    branch must not draw one (R/nmf_thin.R:839-853: `seed = seed_int + i - 1L, w_init_sexp = w_init_list[[i]]`)."""
+
+
 def _pair(value, name):
     """validate_penalty (R/nmf_validation.R:64-76)."""
     v = np.atleast_1d(np.asarray(value, dtype=np.float64))
@@ -256,12 +262,33 @@ class NMFModel:
         return evaluate(data, self.w, self.d, self.h, mask_zeros=(mask is not None))
 
 
+def _multi_init(w_init_list, seed_int, start, test_fraction, call_args):
+    """Multiple initialisations: run each, keep the lowest loss (R/nmf_thin.R:829-925). Run i (0-based) gets
+    config.seed = seed_int + i — hence its own H stream — and w_init_list[i]."""
+    if test_fraction > 0:
+        raise ValueError("Multiple initializations are not compatible with cross-validation. Use a single seed or matrix.")
+    args = dict(call_args)
+    args.pop("w_init", None)
+    best, best_idx, losses = None, 0, []
+    for i, w0 in enumerate(w_init_list):
+        model = nmf(seed=_SeedOnly(seed_int + i), w_init=w0, **args)
+        losses.append(model.misc["loss"])
+        if best is None or model.misc["loss"] < best.misc["loss"]:
+            best, best_idx = model, i
+    best.misc = dict(tol=best.misc["tol"], iter=best.misc["iter"], loss_type=best.misc["loss_type"], loss=best.misc["loss"],
+                     runtime=time.time() - start, w_init=w_init_list[best_idx],
+                     all_inits=[dict(init=i + 1, loss=v, selected=(i == best_idx)) for i, v in enumerate(losses)])
+    return best
+
+
 # --------------------------------------------------------------------------------------------------- nmf ----
 def nmf(data, k, tol=1e-4, maxit=100, L1=(0, 0), L2=(0, 0), seed=None, mask=None, loss="mse", nonneg=(True, True),
         test_fraction=0, verbose=False, projective=False, symmetric=False, zi="none", robust=False, **dots) -> NMFModel:
     """Non-negative matrix factorisation A ~ w diag(d) h on the GPU (see the module docstring for the mapping)."""
     start = time.time()
     p = _parse_dots(dots)
+    call_args = dict(data=data, k=k, tol=tol, maxit=maxit, L1=L1, L2=L2, mask=mask, loss=loss, nonneg=nonneg,
+                     verbose=False, projective=projective, symmetric=symmetric, zi=zi, robust=robust, **dots)
 
     # ---- arguments whose code paths live outside the hot path (R/nmf_thin.R:278-420) ----
     if loss != "mse":
@@ -362,8 +389,24 @@ def nmf(data, k, tol=1e-4, maxit=100, L1=(0, 0), L2=(0, 0), seed=None, mask=None
         w_init = np.random.default_rng().random((m, k))
         head = w_init.T.reshape(-1)[:min(10, w_init.size)]               # R's column-major w_init_mat[1:10]
         seed_int = int(abs(head.sum() * 1e8) % _INT_MAX)
-    elif isinstance(seed, (list, tuple)):
-        _refuse("seed = <list>", "multiple initialisations are outside this library's scope")
+    elif isinstance(seed, (list, tuple)) and len(seed) and all(isinstance(x, np.ndarray) for x in seed):
+        w_init_list = []                                                  # list of custom W matrices (:745-757)
+        for x in seed:
+            if x.ndim != 2:
+                raise ValueError("Each element of seed list must be a matrix")
+            actual_k = x.shape[1] if x.shape[0] == m else x.shape[0]
+            if actual_k != k:
+                raise ValueError(f"Rank mismatch: k={k} specified but custom initialization has rank {actual_k}.")
+            if x.shape[0] == m:
+                w_init_list.append(np.asarray(x, np.float64))
+            elif x.shape[1] == m:
+                w_init_list.append(np.asarray(x, np.float64).T)
+            else:
+                raise ValueError("Custom init matrix dimensions incompatible with data")
+        seed_int = abs(int(float(np.sum(seed[0] * 1e6)) % _INT_MAX))
+        if len(w_init_list) > 1:
+            return _multi_init(w_init_list, seed_int, start, test_fraction, call_args)
+        w_init = bridge_w_init(seed_int, k, m)              # a one-element list leaves w_init_mat NULL: bridge_nmf.hpp:216
     elif isinstance(seed, np.ndarray) and seed.ndim == 2:
         actual_k = seed.shape[1] if seed.shape[0] == m else seed.shape[0]
         if actual_k != k:
@@ -376,7 +419,11 @@ def nmf(data, k, tol=1e-4, maxit=100, L1=(0, 0), L2=(0, 0), seed=None, mask=None
             raise ValueError("Custom init matrix dimensions incompatible with data")
         seed_int = abs(int(float(np.sum(seed * 1e6)) % _INT_MAX))
     elif np.size(seed) > 1:
-        _refuse("seed = <vector>", "multiple initialisations are outside this library's scope")
+        svec = [int(x) for x in np.asarray(seed).reshape(-1)]            # vector of seeds for multi-init (:772-791)
+        w_init_list = [RRandom(sv).runif(m * k).reshape(k, m).T for sv in svec]
+        return _multi_init(w_init_list, svec[0], start, test_fraction, call_args)
+    elif isinstance(seed, _SeedOnly):
+        seed_int = int(seed)
     elif isinstance(seed, (int, float, np.integer, np.floating)):
         seed_int = int(seed)
         w_init = RRandom(seed_int).runif(m * k).reshape(k, m).T          # matrix(runif(m*k), m, k): column-major
@@ -393,10 +440,12 @@ def nmf(data, k, tol=1e-4, maxit=100, L1=(0, 0), L2=(0, 0), seed=None, mask=None
             w_init = wi.T
         else:
             raise ValueError("w_init dimensions incompatible with data and k")
-        if seed_int == 0:
+        if seed_int == 0 and not isinstance(seed, _SeedOnly):
             head = w_init.T.reshape(-1)[:min(10, w_init.size)]
             seed_int = abs(int(head.sum() * 1e8) % _INT_MAX)
 
+    if w_init is None:                                                    # no matrix from R: the bridge draws W (:216-218)
+        w_init = bridge_w_init(seed_int, k, m)
     # Rcpp_nmf_full casts W_init / H_init to float before the bridge widens them again (:419-433)
     W_T0 = np.ascontiguousarray(w_init, dtype=np.float32)                 # (m, k): row = column of the k x m W_T
     if p["h_init"] is not None:

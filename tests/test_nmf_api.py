@@ -58,6 +58,9 @@ def test_nmf_argument_validation_uses_the_reference_messages():
         (dict(zi="row"), ValueError, "zi != 'none' requires loss='gp' or loss='nb'."),
         (dict(solver="qr"), ValueError, "'solver' should be one of"),
         (dict(w_init=np.ones((7, 7))), ValueError, "w_init dimensions incompatible with data and k"),
+        (dict(seed=[1, 2, 3], test_fraction=0.1), ValueError, "Multiple initializations are not compatible with cross-validation"),
+        (dict(seed=[np.ones((30, 3)), np.ones(3)]), ValueError, "Each element of seed list must be a matrix"),
+        (dict(seed=[np.ones((30, 3)), np.ones((30, 4))]), ValueError, "Rank mismatch: k=3 specified but custom initialization has rank 4."),
     ]
     for kw, exc, msg in cases:
         with pytest.raises(exc) as e:
@@ -70,7 +73,7 @@ def test_nmf_refuses_what_is_outside_the_hot_path():
     A = random_csc(30, 20, 0.3, 1)
     for kw in (dict(loss="gp"), dict(robust=True), dict(projective=True), dict(symmetric=True), dict(L21=0.1),
                dict(angular=(0.0, 0.2)), dict(graph_W=sp.identity(30)), dict(target_H=np.ones((3, 20))),
-               dict(seed="lanczos"), dict(seed=[1, 2, 3]), dict(resource="cpu"), dict(streaming=True)):
+               dict(seed="lanczos"), dict(resource="cpu"), dict(streaming=True)):
         with pytest.raises(NotImplementedError):
             rb.nmf(A, 3, **kw)
     with pytest.raises(NotImplementedError):
@@ -282,3 +285,24 @@ def test_nnls_solves_for_h_and_for_w(oracle):
     h0 = rng.random((k, n)) * 0.1
     ref_ws = oracle.project_f64(A.indptr, A.indices, Ax, m, n, w, warm_start=h0.T, cd_maxit=5)
     assert rel_err(rb.nnls(w=w, A=A, warm_start=h0, cd_maxit=5).T, ref_ws) <= 1e-9
+
+
+@pytest.mark.gpu
+def test_nmf_multiple_initialisations_keep_the_best():
+    """seed = c(5, 6, 7) / list(W1, W2) (R/nmf_thin.R:772-791, 829-925): one fit per initialisation — run i with
+    config.seed = seed[1] + i - 1 — and the lowest loss wins; misc$all_inits lists them."""
+    import rcppml_b200 as rb
+    A = random_csc(150, 90, 0.12, 51, counts=True)
+    kw = dict(maxit=4, tol=0.0, L1=0.01)
+    singles = [rb.nmf(A, 5, seed=s, **kw) for s in (5, 6, 7)]
+    multi = rb.nmf(A, 5, seed=[5, 6, 7], **kw)
+    losses = [s.misc["loss"] for s in singles]
+    best = int(np.argmin(losses))
+    assert [r["loss"] for r in multi.misc["all_inits"]] == losses
+    assert [r["selected"] for r in multi.misc["all_inits"]] == [i == best for i in range(3)]
+    assert np.array_equal(multi.w, singles[best].w) and np.array_equal(multi.h, singles[best].h)
+    assert np.array_equal(multi.misc["w_init"], singles[best].misc["w_init"]) and multi.misc["loss"] == min(losses)
+    Ws = [s.misc["w_init"] for s in singles[:2]]
+    from_list = rb.nmf(A, 5, seed=[Ws[0], Ws[1].T.copy()], **kw)
+    assert len(from_list.misc["all_inits"]) == 2 and from_list.w.shape == (150, 5)
+    assert from_list.misc["loss"] == min(r["loss"] for r in from_list.misc["all_inits"])

@@ -70,6 +70,9 @@ def test_nmf_host_plumbing(oracle_backed_native_calls, oracle):
     assert sent and all(c[1]["solver_mode"] == 1 and c[1]["seed"] == 123 and c[1]["cd_maxit"] == 100 for c in sent)
     T.test_nmf_seed_forms_and_reproducibility()
     T.test_nmf_invariants_of_the_reference_tests()
+    calls.clear()
+    T.test_nmf_multiple_initialisations_keep_the_best()
+    assert [c[1]["seed"] for c in calls[3:6]] == [5, 6, 7]             # config.seed = seed[1] + i - 1
 
 
 def test_nmf_mask_and_cv_routing(oracle_backed_native_calls, oracle):
