@@ -12,6 +12,7 @@
 //                                                            loss_cross_term_sparse_via_At
 //   inst/include/FactorNet/primitives/cpu/cholesky_clip.hpp  cholesky_clip_col
 //   inst/include/FactorNet/primitives/cpu/gram.hpp           gram<CPU,float|double>
+//   inst/include/FactorNet/primitives/cpu/rhs.hpp            rhs<CPU,double> (sparse) — with gram + nnls_batch: the body of c_nnls / Rcpp_predict
 //   inst/include/FactorNet/primitives/primitives.hpp         trace_AtA
 //   inst/include/FactorNet/core/constants.hpp                tiny_num, CD_TOL, CD_MAXIT, CD_ABS_TOL, NMF_PATIENCE
 //   inst/include/FactorNet/nmf/masked_nnls.hpp               masked_nnls_h / masked_nnls_w / masked_loss (+ core/config.hpp)
@@ -31,6 +32,7 @@ namespace Eigen { template <class M> class SelfAdjointEigenSolver; }   // named 
 #include <FactorNet/rng/rng.hpp>
 #include <FactorNet/primitives/cpu/gram.hpp>
 #include <FactorNet/primitives/cpu/fused_nnls.hpp>
+#include <FactorNet/primitives/cpu/rhs.hpp>
 #include <FactorNet/features/bounds.hpp>
 #include <FactorNet/nmf/masked_nnls.hpp>
 #include <FactorNet/nmf/speckled_cv.hpp>
@@ -97,6 +99,31 @@ void ref_nnls_batch_f64(const double* G, double* B, double* X, int k, long n, in
     primitives::nnls_batch<CPU, double>(Gm, Bm, Xm, cd_maxit, cd_tol, L1, L2, nonneg != 0, 1, ub, warm_start != 0);
     std::memcpy(B, Bm.data(), sizeof(double) * static_cast<size_t>(k) * n);
     std::memcpy(X, Xm.data(), sizeof(double) * static_cast<size_t>(k) * n);
+}
+
+// ---- c_nnls / Rcpp_predict (src/RcppFunctions_utils.cpp:314-366, 23-53): those two functions need Rcpp, but their
+// bodies are these calls into the reference's own primitives, in this order, in double. w_T: k x m, h: k x n in/out.
+void ref_c_nnls_sparse_f64(const int* Ap, const int* Ai, const double* Ax, long m, long n, const double* w_T, int k, double* h,
+                           int cd_maxit, double cd_tol, double L1, double L2, double ub, int nonneg, int warm_start) {
+    using SpD = Eigen::SparseMatrix<double, Eigen::ColMajor, int>;
+    const SpD A(m, n, Ap, Ai, Ax);
+    const DenseMatrix<double> Wm = dense_from(w_T, k, m);
+    DenseMatrix<double> G(k, k);
+    primitives::gram<CPU, double>(Wm, G);                                             // :326 / :33
+    for (int i = 0; i < k; ++i) G(i, i) += tiny_num<double>();                          // :327
+    if (L2 > 0) for (int i = 0; i < k; ++i) G(i, i) += L2;                              // :328
+    DenseMatrix<double> B;
+    B.resize(k, n);
+    primitives::rhs<CPU, double>(A, Wm, B);                                           // :338
+    DenseMatrix<double> hm = dense_from(h, k, n);
+    if (warm_start) {                                                                   // :347-356
+        B.noalias() -= G * hm;
+        for (long j = 0; j < n; ++j)
+            primitives::detail::cd_nnls_col_fixed(G, B.col(j).data(), hm.col(j).data(), k, L1, 0.0, nonneg != 0, cd_maxit, ub);
+    } else {                                                                            // :358-360
+        primitives::nnls_batch<CPU, double>(G, B, hm, cd_maxit, cd_tol, L1, 0.0, nonneg != 0, 1, ub);
+    }
+    std::memcpy(h, hm.data(), sizeof(double) * static_cast<size_t>(k) * n);
 }
 
 // ---- primitives/cpu/gram.hpp (F is k x ncols col-major)

@@ -1,7 +1,7 @@
 """CPU: the oracle's restatement against the REFERENCE'S OWN hot-path source.
 
 oracle/_ref/libref_hotpath.so is the reference's headers — rng/rng.hpp, primitives/cpu/{nnls_batch, fused_nnls,
-cholesky_clip, gram}.hpp, primitives/primitives.hpp, core/constants.hpp, nmf/masked_nnls.hpp (with core/config.hpp),
+cholesky_clip, gram, rhs}.hpp, primitives/primitives.hpp, core/constants.hpp, nmf/masked_nnls.hpp (with core/config.hpp),
 nmf/variant_helpers.hpp, features/bounds.hpp, nmf/speckled_cv.hpp, nmf/cv_detail.hpp — compiled unmodified from
 /root/reference
 (`make -C oracle ref_hotpath`) against a minimal stand-in for the Eigen types they use (Eigen is not in this image).
@@ -308,3 +308,30 @@ def test_cv_building_blocks_bit_exact(ref, oracle, mask_zeros):
             assert np.array_equal(G1, G2), (transposed, col)
         if not mask_zeros:
             assert c1 > 0                                # with every cell hashed a column of 60+ cells has hold-outs
+
+
+@pytest.mark.parametrize("k", [5, 20, 64])
+def test_predict_nnls_pipeline_bit_exact(ref, oracle, k):
+    """predict() / nnls(): the bodies of c_nnls / Rcpp_predict (src/RcppFunctions_utils.cpp:314-366,
+    23-53 — gram<CPU,double>, + tiny_num, + L2, rhs<CPU,double>, nnls_batch<CPU,double> or the warm-started CD loop)
+    assembled from the reference's own primitives, against the oracle's project_f64 — the checker of the GPU entry
+    rcppml_gpu_nnls_double."""
+    if not hasattr(ref, "ref_c_nnls_sparse_f64"):
+        pytest.skip("oracle/_ref/libref_hotpath.so predates ref_c_nnls_sparse_f64 (rebuild: make -C oracle ref_hotpath)")
+    m, n = 300, 120
+    A = random_csc(m, n, 0.08, 90 + k, counts=True, ragged=True)
+    Ap, Ai, Ax = A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data.astype(np.float64)
+    rng = np.random.default_rng(k)
+    w = rng.random((m, k))                                                 # (m, k) C-order == k x m column-major
+    cases = [dict(), dict(L1=0.05, L2=0.1), dict(upper_bound=0.3), dict(nonneg=False, L2=0.01), dict(cd_maxit=3),
+             dict(warm_start=rng.random((n, k)) * 0.1, cd_maxit=7), dict(warm_start=rng.random((n, k)), L1=0.02, upper_bound=0.5)]
+    for kw in cases:
+        got = oracle.project_f64(Ap, Ai, Ax, m, n, w, **kw)               # (n, k)
+        ws = kw.get("warm_start")
+        h = np.zeros((n, k)) if ws is None else np.array(ws, np.float64, order="C")
+        ref.ref_c_nnls_sparse_f64(_p(Ap, C.c_int), _p(Ai, C.c_int), _p(Ax, C.c_double), C.c_long(m), C.c_long(n),
+                                  _p(w, C.c_double), k, _p(h, C.c_double), kw.get("cd_maxit", 100),
+                                  C.c_double(kw.get("cd_tol", 1e-8)), C.c_double(kw.get("L1", 0.0)),
+                                  C.c_double(kw.get("L2", 0.0)), C.c_double(kw.get("upper_bound", 0.0)),
+                                  int(kw.get("nonneg", True)), int(ws is not None))
+        assert np.array_equal(got, h), (k, {a: b for a, b in kw.items() if a != "warm_start"}, float(np.abs(got - h).max()))
