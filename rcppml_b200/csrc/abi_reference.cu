@@ -98,12 +98,17 @@ bool fit_in_process_multi_gpu(int G, const int* devices, int m, int n, int64_t n
     std::vector<std::string> err(G);
     auto run_all = [&](auto&& body) {
         std::vector<std::thread> th;
-        for (int g = 0; g < G; ++g)
-            th.emplace_back([&, g] {
-                try { body(g); }
-                catch (const std::exception& ex) { err[g] = ex.what()[0] ? ex.what() : "error"; }
-                catch (...) { err[g] = "unknown error"; }
-            });
+        th.reserve(G);
+        try {
+            for (int g = 0; g < G; ++g)
+                th.emplace_back([&, g] {
+                    try { body(g); }
+                    catch (const std::exception& ex) { err[g] = ex.what()[0] ? ex.what() : "error"; }
+                    catch (...) { err[g] = "unknown error"; }
+                });
+        } catch (...) {                                        // thread creation failed: the ranks that did start will
+            err[G - 1] = "could not start a host thread";      // time out in their first exchange (2 s) and return
+        }
         for (auto& t : th) t.join();
         for (int g = 0; g < G; ++g)
             if (!err[g].empty()) { warn(("multi-GPU rank " + std::to_string(g) + ": " + err[g]).c_str()); return false; }
