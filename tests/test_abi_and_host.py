@@ -218,3 +218,30 @@ def test_bench_sharded_e2e_host_logic(monkeypatch):
         else:
             assert calls == [("set_factors", (m, k), (n, k)), "get_factors"] * 2
             assert r["d2h_bytes_per_step"] == (m * k * 4 + n * k * 4 + 4 * k) // 3
+
+
+def test_row_block_operand_is_a_column_slice_of_the_transpose():
+    """The premise of Engine::set_matrix_host_shard (in-process multi-GPU): the W half-step operand of rank g —
+    (A[I_g, :])ᵀ as CSC with ascending global column ids, which set_matrix_sharded builds from a host-extracted row
+    block — is the contiguous column range I_g of the full transpose with its pointers rebased; and the H half-step
+    operand is the column range J_g of A itself."""
+    import scipy.sparse as sp
+    from rcppml_b200 import shard
+    from helpers import random_csc
+    m, n, world = 203, 117, 4
+    A = random_csc(m, n, 0.07, 12, ragged=True)
+    At = A.T.tocsc()
+    At.sort_indices()
+    for rank in range(world):
+        r0, rc = shard.block_of(m, world, rank)
+        rp, ri, rx = shard.extract_row_block(A.indptr, A.indices, A.data, r0, rc)       # A[I, :], local row ids
+        ref = sp.csc_matrix((rx, ri, rp), shape=(rc, n)).T.tocsc()                       # what the engine transposes
+        ref.sort_indices()
+        lo, hi = At.indptr[r0], At.indptr[r0 + rc]
+        assert np.array_equal(ref.indptr, At.indptr[r0:r0 + rc + 1] - lo)                # rebase_pointers_kernel
+        assert np.array_equal(ref.indices, At.indices[lo:hi]) and np.array_equal(ref.data, At.data[lo:hi])
+        c0, cc = shard.block_of(n, world, rank)
+        cp, ci, cx = shard.extract_shard(A.indptr, A.indices, A.data, c0, cc)
+        lo, hi = A.indptr[c0], A.indptr[c0 + cc]
+        assert np.array_equal(cp, A.indptr[c0:c0 + cc + 1] - lo)
+        assert np.array_equal(ci, A.indices[lo:hi]) and np.array_equal(cx, A.data[lo:hi])
