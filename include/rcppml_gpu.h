@@ -260,6 +260,14 @@ int rcppml_b200_set_matrix_sharded_f32(rcppml_b200_engine* e, int m, int n, cons
                                        const int* rowblk_idx, const float* rowblk_val);
 int rcppml_b200_get_shard(rcppml_b200_engine* e, int* col_begin, int* n_loc, int* row_begin, int* m_loc,
                           int64_t* nnz_global);
+/* Explicit partition for the following set_matrix_* calls (after comm_init, same cuts on every rank): rank r owns
+ * columns [col_cuts[r], col_cuts[r+1]) of H and rows [row_cuts[r], row_cuts[r+1]) of W_T; world+1 ascending cuts
+ * each, 0 .. n and 0 .. m. NULL restores equal blocks. Contiguous ranges balanced by work:
+ * rcppml_b200/shard.py balanced_cuts. */
+int rcppml_b200_set_partition(rcppml_b200_engine* e, const int* col_cuts, const int* row_cuts);
+/* 64-bit checksums of the logical factors {W_T, H, d} (padding excluded), computed on the device: equal
+ * checksums <=> bit-identical factors. Used to compare sharded fits with the one-GPU fit of the same seed. */
+int rcppml_b200_factor_checksum(rcppml_b200_engine* e, uint64_t* out3);
 /* Copies the device CSC operands back (for checking the generator / transpose). Pass NULL to skip an array.
  * get_matrix: A[:, J] (n_loc columns); get_matrix_t: A[I, :]^T (m_loc columns, global column ids). */
 int rcppml_b200_get_matrix(rcppml_b200_engine* e, int64_t* nnz, int* col_ptr, int* row_idx, float* values);

@@ -90,6 +90,8 @@ def load() -> C.CDLL:
     lib.rcppml_b200_set_matrix_synthetic_sharded.argtypes = [E, C.c_int, C.c_int, C.c_double, C.c_uint64]
     lib.rcppml_b200_set_matrix_sharded_f32.argtypes = [E, C.c_int, C.c_int, ip, ip, fp, ip, ip, fp]
     lib.rcppml_b200_get_shard.argtypes = [E, ip, ip, ip, ip, C.POINTER(C.c_int64)]
+    lib.rcppml_b200_set_partition.argtypes = [E, ip, ip]
+    lib.rcppml_b200_factor_checksum.argtypes = [E, C.POINTER(C.c_uint64)]
     lib.rcppml_b200_get_matrix.argtypes = [E, C.POINTER(C.c_int64), ip, ip, fp]
     lib.rcppml_b200_get_matrix_t.argtypes = [E, ip, ip, fp]
     lib.rcppml_b200_set_mask.argtypes = [E, C.c_int64, ip, ip]
@@ -98,6 +100,8 @@ def load() -> C.CDLL:
     lib.rcppml_b200_init_factors.argtypes = [E, C.c_int, C.c_uint32, C.c_int]
     lib.rcppml_b200_get_factors_f32.argtypes = [E, fp, fp, fp]
     lib.rcppml_b200_get_factors_f64.argtypes = [E, dp, dp, dp]
+    lib.rcppml_b200_set_factor_blocks_f32.argtypes = [E, C.c_int, fp, fp]
+    lib.rcppml_b200_get_factor_blocks_f32.argtypes = [E, fp, fp, fp]
     lib.rcppml_b200_begin_fit.argtypes = [E, C.POINTER(Config)]
     lib.rcppml_b200_iterate.argtypes = [E, C.c_int]
     lib.rcppml_b200_fit.argtypes = [E, C.POINTER(Config)]

@@ -218,9 +218,9 @@ void rcppml_gpu_nmf_cv_unified_float(
         else if (*k < 1 || *k > b200::kMaxKP) refuse = "rank must be in [1, 128] on the B200 CV path";
         else if (*max_iter <= 0) refuse = "max_iter must be positive";
         if (refuse) { warn(refuse); return; }
-        int count = 0;
-        if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) { warn("no CUDA device"); return; }
-        EngineLease lease(0);
+        int dev0 = 0;
+        if (usable_devices(&dev0, 1) < 1) { warn("no sm_100+ CUDA device"); return; }
+        EngineLease lease(dev0);
         b200::Engine& E = lease.get();
         E.set_matrix_and_factors_host<double, double>(*m, *n, static_cast<int64_t>(*nnz), col_ptr, row_idx, values, *k, W, H);
         rcppml_b200_config cfg{};
@@ -494,8 +494,8 @@ static void nmf_unified_impl(
         else if (*max_iter <= 0) refuse = "max_iter must be positive";
         if (refuse) { warn(refuse); return; }
 
-        int count = 0;
-        if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) { warn("no CUDA device"); return; }
+        int dev0 = 0;
+        if (usable_devices(&dev0, 1) < 1) { warn("no sm_100+ CUDA device"); return; }
 
         rcppml_b200_config cfg{};
         cfg.k = *k;
@@ -524,7 +524,7 @@ static void nmf_unified_impl(
                                           cfg, &res))
                 return;
         } else {
-            lease_holder.reset(new EngineLease(0));
+            lease_holder.reset(new EngineLease(dev0));
             b200::Engine& E = lease_holder->get();
             if (masked) {
                 E.set_matrix_host<double>(*m, *n, static_cast<int64_t>(*nnz), col_ptr, row_idx, values);

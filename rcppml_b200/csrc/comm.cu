@@ -155,12 +155,22 @@ void Engine::comm_ipc_import(const char* all) {
     peers_ready = true;
 }
 
-// In-place all-gather of equal row blocks of a replicated factor: rank g contributes rows
-// [g*rows_per_rank, (g+1)*rows_per_rank).
-void Engine::allgather_rows(float* buf, int rows_per_rank, int sec) {
+// In-place all-gather of the row blocks of a replicated factor: rank r contributes rows [cuts[r], cuts[r+1]).
+// Equal (padded) blocks go through ncclAllGather; an explicit partition through grouped per-rank broadcasts.
+void Engine::allgather_rows(float* buf, const std::vector<int>& cuts, int rows_padded, int sec) {
     sec_begin(sec);
-    const size_t cnt = static_cast<size_t>(rows_per_rank) * KP;
-    B200_NCCL_CHECK(ncclAllGather(buf + static_cast<size_t>(rank) * cnt, buf, cnt, ncclFloat, as_comm(comm), stream));
+    if (equal_partition) {
+        const size_t cnt = static_cast<size_t>(rows_padded / world) * KP;
+        B200_NCCL_CHECK(ncclAllGather(buf + static_cast<size_t>(rank) * cnt, buf, cnt, ncclFloat, as_comm(comm), stream));
+    } else {
+        B200_NCCL_CHECK(ncclGroupStart());
+        for (int r = 0; r < world; ++r) {
+            const size_t cnt = static_cast<size_t>(cuts[r + 1] - cuts[r]) * KP;
+            float* blk = buf + static_cast<size_t>(cuts[r]) * KP;
+            if (cnt > 0) B200_NCCL_CHECK(ncclBroadcast(blk, blk, cnt, ncclFloat, r, as_comm(comm), stream));
+        }
+        B200_NCCL_CHECK(ncclGroupEnd());
+    }
     sec_end(sec);
 }
 

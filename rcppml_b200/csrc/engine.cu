@@ -17,6 +17,29 @@ namespace b200 {
 
 thread_local std::string g_last_error;
 
+// Opt-in shared memory (cudaFuncSetAttribute) and the occupancy of a kernel are properties of the (kernel, DEVICE)
+// pair, so they are cached per device — a host thread may drive engines on several devices (zero-copy entry,
+// Engine(1) after Engine(0)), and the in-process multi-GPU path runs one thread per device.
+constexpr int kMaxDevices = 64;
+struct OccCache {
+    std::atomic<int> v[kMaxDevices];
+    OccCache() { for (auto& x : v) x.store(-1); }
+};
+template <class Kern>
+static int cached_occupancy(OccCache& cache, Kern kern, int threads, size_t smem, const char* what) {
+    int dev = 0;
+    B200_CUDA_CHECK(cudaGetDevice(&dev));
+    B200_REQUIRE(dev >= 0 && dev < kMaxDevices, "device ordinal out of range");
+    int occ = cache.v[dev].load(std::memory_order_acquire);
+    if (occ < 0) {
+        B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        B200_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+        B200_REQUIRE(occ > 0, what);
+        cache.v[dev].store(occ, std::memory_order_release);
+    }
+    return occ;
+}
+
 // ---------------------------------------------------------------------------------------------
 // kernel dispatch by padded rank
 // ---------------------------------------------------------------------------------------------
@@ -24,14 +47,8 @@ template <int LANES, int NV, int SOLVER, int BSRC, int OUT>
 static void launch_half_step_t(const HalfStepParams& p, int num_sms, cudaStream_t stream, int* grid_out) {
     auto kern = half_step_kernel<LANES, NV, SOLVER, BSRC, OUT>;
     const size_t smem = half_step_smem_bytes<LANES, NV, SOLVER, OUT>();
-    static thread_local int cached_occ = -1;
-    if (cached_occ < 0) {
-        B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        int occ = 0;
-        B200_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));
-        B200_REQUIRE(occ > 0, "half_step_kernel does not fit on an SM");
-        cached_occ = occ;
-    }
+    static OccCache cache;
+    const int cached_occ = cached_occupancy(cache, kern, 256, smem, "half_step_kernel does not fit on an SM");
     // Persistent grid: a multiple of the SM count (148 on B200) x resident CTAs per SM.
     const int grid = num_sms * cached_occ;
     if (grid_out) { *grid_out = grid; return; }
@@ -71,14 +88,8 @@ template <int LANES, int NV>
 static void launch_cd_t(const HalfStepParams& p, int num_sms, cudaStream_t stream, int* grid_out) {
     auto kern = cd_half_step_kernel<LANES, NV>;
     const size_t smem = cd_half_step_smem_bytes<LANES, NV>();
-    static thread_local int cached_occ = -1;
-    if (cached_occ < 0) {
-        B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        int occ = 0;
-        B200_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));
-        B200_REQUIRE(occ > 0, "cd_half_step_kernel does not fit on an SM");
-        cached_occ = occ;
-    }
+    static OccCache cache;
+    const int cached_occ = cached_occupancy(cache, kern, 256, smem, "cd_half_step_kernel does not fit on an SM");
     const int grid = num_sms * cached_occ;
     if (grid_out) { *grid_out = grid; return; }
     kern<<<grid, 256, smem, stream>>>(p);
@@ -107,14 +118,8 @@ template <int GL, int GNV, int SL, int SNV, int SOLVER>
 static void launch_tiled_t(const HalfStepParams& p, int num_sms, cudaStream_t stream, int* grid_out) {
     auto kern = tiled_half_step_kernel<GL, GNV, SL, SNV, SOLVER>;
     const size_t smem = tiled_smem_bytes<GL, GNV, SL, SNV, SOLVER>();
-    static thread_local int cached_occ = -1;
-    if (cached_occ < 0) {
-        B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        int occ = 0;
-        B200_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));
-        B200_REQUIRE(occ > 0, "tiled_half_step_kernel does not fit on an SM");
-        cached_occ = occ;
-    }
+    static OccCache cache;
+    const int cached_occ = cached_occupancy(cache, kern, 256, smem, "tiled_half_step_kernel does not fit on an SM");
     const int grid = num_sms * cached_occ;
     if (grid_out) { *grid_out = grid; return; }
     kern<<<grid, 256, smem, stream>>>(p);
@@ -122,6 +127,14 @@ static void launch_tiled_t(const HalfStepParams& p, int num_sms, cudaStream_t st
 
 template <int SOLVER>
 static void launch_tiled_s(int gather_geom, const HalfStepParams& p, int num_sms, cudaStream_t s, int* grid_out) {
+    // gather_geom = LANES + 100*(NV-1) of the gather phase (+ 1000 * solve lanes when the solve geometry is not the
+    // default narrowest one: k = 64 with 4 lanes x 4 words = batches of 8 columns instead of 16 — fewer columns per
+    // warp batch quantise better when a rank holds few columns, Engine::tiled_solve_lanes)
+    switch (gather_geom) {
+        case 4016: launch_tiled_t<16, 1, 4, 4, SOLVER>(p, num_sms, s, grid_out); return;  // KP = 64, 8-column batches
+        case 4108: launch_tiled_t<8, 2, 4, 4, SOLVER>(p, num_sms, s, grid_out); return;
+        default: break;
+    }
     switch (gather_geom) {                          // gather (LANES + 100*(NV-1)); the solve geometry follows from KP
         case 4: launch_tiled_t<4, 1, 1, 4, SOLVER>(p, num_sms, s, grid_out); break;       // KP = 16
         case 8: launch_tiled_t<8, 1, 1, 8, SOLVER>(p, num_sms, s, grid_out); break;       // KP = 32
@@ -173,14 +186,8 @@ static void launch_masked_t(const MaskedParams& p, int num_sms, cudaStream_t s, 
     auto kern = masked_half_step_kernel<KP>;
     const size_t smem = masked_smem_bytes<KP>();
     const int threads = masked_warps<KP>() * 32;
-    static thread_local int cached_occ = -1;
-    if (cached_occ < 0) {
-        B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        int occ = 0;
-        B200_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
-        B200_REQUIRE(occ > 0, "masked_half_step_kernel does not fit on an SM");
-        cached_occ = occ;
-    }
+    static OccCache cache;
+    const int cached_occ = cached_occupancy(cache, kern, threads, smem, "masked_half_step_kernel does not fit on an SM");
     const int grid = num_sms * cached_occ;
     if (grid_out) { *grid_out = grid; return; }
     kern<<<grid, threads, smem, s>>>(p);
@@ -200,14 +207,8 @@ static void launch_cv_t(const CvParams& p, int num_sms, cudaStream_t s, int* gri
     auto kern = cv_half_step_kernel<KP>;
     const size_t smem = masked_smem_bytes<KP>();
     const int threads = masked_warps<KP>() * 32;
-    static thread_local int cached_occ = -1;
-    if (cached_occ < 0) {
-        B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        int occ = 0;
-        B200_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
-        B200_REQUIRE(occ > 0, "cv_half_step_kernel does not fit on an SM");
-        cached_occ = occ;
-    }
+    static OccCache cache;
+    const int cached_occ = cached_occupancy(cache, kern, threads, smem, "cv_half_step_kernel does not fit on an SM");
     const int grid = num_sms * cached_occ;
     if (grid_out) { *grid_out = grid; return; }
     kern<<<grid, threads, smem, s>>>(p);
@@ -240,10 +241,30 @@ static __global__ void cv_prepare_gram_kernel(const float* __restrict__ G, int K
 // ---------------------------------------------------------------------------------------------
 // Engine
 // ---------------------------------------------------------------------------------------------
-static std::atomic<int> g_engine_counter{0};
+// __constant__ SolverConsts slots (kernels_solve.cuh) are per device: a live engine owns one slot of ITS device, so
+// two engines running on their own streams can never overwrite each other's diagonal blocks / reciprocals.
+static std::mutex g_slot_mu;
+static bool g_slot_used[kMaxDevices][kConstSlots] = {};
 
 Engine::Engine(int dev) : device(dev) {
-    const_slot = g_engine_counter.fetch_add(1) % kConstSlots;
+    B200_REQUIRE(dev >= 0 && dev < kMaxDevices, "device ordinal out of range");
+    {
+        std::lock_guard<std::mutex> g(g_slot_mu);
+        const_slot = -1;
+        for (int s = 0; s < kConstSlots && const_slot < 0; ++s)
+            if (!g_slot_used[dev][s]) { g_slot_used[dev][s] = true; const_slot = s; }
+    }
+    B200_REQUIRE(const_slot >= 0, "too many live engines on this device (8 constant-memory solver slots); destroy one first");
+    try {
+        init_device_objects();
+    } catch (...) {
+        std::lock_guard<std::mutex> g(g_slot_mu);
+        g_slot_used[dev][const_slot] = false;
+        throw;
+    }
+}
+
+void Engine::init_device_objects() {
     B200_CUDA_CHECK(cudaSetDevice(device));
     cudaDeviceProp prop{};
     B200_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
@@ -277,6 +298,8 @@ Engine::~Engine() {
     if (h_state) cudaFreeHost(h_state);
     comm_destroy();
     cudaStreamDestroy(stream);
+    std::lock_guard<std::mutex> g(g_slot_mu);
+    if (const_slot >= 0) g_slot_used[device][const_slot] = false;
 }
 
 void Engine::use_device() const { B200_CUDA_CHECK(cudaSetDevice(device)); }
@@ -299,13 +322,46 @@ void Engine::set_dims(int m_, int n_) {
     drop_iteration_graph();
     fit_active = false;                                   // a fit in flight does not survive a new matrix
     m = m_; n = n_;
-    block_of(n, world, rank, &col_begin, &n_loc);
-    block_of(m, world, rank, &row_begin, &m_loc);
+    equal_partition = true;
+    auto fill = [&](std::vector<int>& cuts, const std::vector<int>& pending, int total, const char* what) {
+        if (!pending.empty()) {
+            B200_REQUIRE(static_cast<int>(pending.size()) == world + 1 && pending.front() == 0 && pending.back() == total, what);
+            for (int r = 0; r < world; ++r) B200_REQUIRE(pending[r] <= pending[r + 1], what);
+            cuts = pending;
+            equal_partition = false;
+            return;
+        }
+        cuts.assign(world + 1, total);
+        for (int r = 0; r < world; ++r) { int lo = 0, cnt = 0; block_of(total, world, r, &lo, &cnt); cuts[r] = lo; }
+    };
+    fill(col_cuts, pending_col_cuts, n, "set_partition: the column cuts do not cover this matrix (need world+1 ascending cuts, 0 .. n)");
+    fill(row_cuts, pending_row_cuts, m, "set_partition: the row cuts do not cover this matrix (need world+1 ascending cuts, 0 .. m)");
+    col_begin = col_cuts[rank]; n_loc = col_cuts[rank + 1] - col_cuts[rank];
+    row_begin = row_cuts[rank]; m_loc = row_cuts[rank + 1] - row_cuts[rank];
     m_pad = ((m + world - 1) / world) * world;
     n_pad = ((n + world - 1) / world) * world;
     matrix_ready = false;
     factors_ready = false;
     npanels[0] = npanels[1] = 1;
+}
+
+void Engine::set_partition(const int* cc, const int* rc) {
+    pending_col_cuts.clear();
+    pending_row_cuts.clear();
+    if (cc) pending_col_cuts.assign(cc, cc + world + 1);
+    if (rc) pending_row_cuts.assign(rc, rc + world + 1);
+}
+
+void Engine::factor_checksum(unsigned long long* out3) {
+    use_device();
+    B200_REQUIRE(factors_ready, "no factors");
+    unsigned long long* acc = scratch<unsigned long long>(6, 4);
+    B200_CUDA_CHECK(cudaMemsetAsync(acc, 0, 4 * sizeof(unsigned long long), stream));
+    checksum_kernel<<<num_sms * 8, 256, 0, stream>>>(W_T.ptr, m, k, KP, acc);
+    checksum_kernel<<<num_sms * 8, 256, 0, stream>>>(H.ptr, n, k, KP, acc + 1);
+    checksum_kernel<<<1, 256, 0, stream>>>(d.ptr, 1, k, KP, acc + 2);
+    B200_CUDA_CHECK(cudaMemcpyAsync(out3, acc, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+    B200_CUDA_CHECK(cudaStreamSynchronize(stream));
 }
 
 void Engine::finish_matrix() { finish_matrix_from(Ax.ptr, nnz, world > 1); }
@@ -576,6 +632,10 @@ void Engine::alloc_factors(int k_) {
     if (const char* env = std::getenv("RCPPML_B200_TILED")) tiled_mode = std::atoi(env);
     tiled_min_batches = 0.5;
     if (const char* env = std::getenv("RCPPML_B200_TILED_MIN_BATCHES")) tiled_min_batches = std::atof(env);
+    tiled_sl_override = 0;
+    if (const char* env = std::getenv("RCPPML_B200_TILED_SL")) tiled_sl_override = std::atoi(env);
+    tiled_sl4_below = 0.0;                                    // auto rule off until measured (profiles/r02*)
+    if (const char* env = std::getenv("RCPPML_B200_TILED_SL4_BELOW")) tiled_sl4_below = std::atof(env);
     narrow_min_cols = 8.0 * num_sms * 24;
     if (std::getenv("RCPPML_B200_CD_GEOM")) narrow_min_cols = 0.0;           // an explicit geometry applies to every size
     if (const char* env = std::getenv("RCPPML_B200_NARROW_MIN_COLS")) narrow_min_cols = std::atof(env);
@@ -614,7 +674,7 @@ void Engine::alloc_factors(int k_) {
     }
     if (tiled_mode) {
         for (int solver = 0; solver < 2; ++solver)
-            for (int geom : {LANES, (KP == 64 || KP == 128) ? 100 + KP / 8 : LANES}) {
+            for (int geom : {LANES, (KP == 64 || KP == 128) ? 100 + KP / 8 : LANES, KP == 64 ? 4016 : LANES, KP == 64 ? 4108 : LANES}) {
                 int g = 0;
                 launch_tiled_half_step(geom, solver, dummy, num_sms, stream, &g);
                 gmax = std::max(gmax, g);
@@ -748,8 +808,8 @@ void Engine::set_factor_blocks_host(int k_, const T* W_blk, const T* H_blk) {
     upload(W_blk, W_T.ptr + static_cast<size_t>(row_begin) * KP, m_loc);
     upload(H_blk, H.ptr + static_cast<size_t>(col_begin) * KP, n_loc);
     if (world > 1) {
-        allgather_rows(W_T.ptr, m_pad / world, RCPPML_B200_SEC_COMM);
-        allgather_rows(H.ptr, n_pad / world, RCPPML_B200_SEC_COMM);
+        allgather_rows(W_T.ptr, row_cuts, m_pad, RCPPML_B200_SEC_COMM);
+        allgather_rows(H.ptr, col_cuts, n_pad, RCPPML_B200_SEC_COMM);
         B200_CUDA_CHECK(cudaStreamSynchronize(stream));
     }
     phase_ms[2] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -860,11 +920,9 @@ void Engine::prepare_solver(const float* G, float L2, int sec) {
     sec_begin(sec);
     const int solver = cfg.solver_mode == 0 ? SOLVER_CD : SOLVER_CHOL;
     const size_t smem = static_cast<size_t>(2) * KP * KP * sizeof(float);
-    static thread_local bool attr_set = false;
-    if (!attr_set) {
-        B200_CUDA_CHECK(cudaFuncSetAttribute(prepare_solver_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 128 * 128 * 4));
-        attr_set = true;
-    }
+    static OccCache cache;                                   // per device (see cached_occupancy)
+    cached_occupancy(cache, prepare_solver_kernel, kPrepThreads, static_cast<size_t>(2) * 128 * 128 * 4,
+                     "prepare_solver_kernel does not fit on an SM");
     prepare_solver_kernel<<<1, kPrepThreads, smem, stream>>>(G, KP, k, L2, solver, M1.ptr, M2.ptr, dblk.ptr, dblk.ptr + kMaxKP * 4, state.ptr);
     // warp-uniform operands -> this engine's constant-memory slot (kernels_solve.cuh SolverConsts); rcp follows
     // dblk in one device buffer, laid out like the struct
@@ -1004,8 +1062,19 @@ bool Engine::use_tiled(int solver, long long cnt, long long ncols) const {
 }
 
 int Engine::tiled_gather_geom(long long cnt, long long ncols) const {
-    const int g = geometry_for(cnt, ncols);                     // LANES + 100*(NV-1), NV in {1, 2, 4}
-    if (g >= 300) return 100 + KP / 8;                          // NV = 4 is not instantiated for the tiled kernel
+    int g = geometry_for(cnt, ncols);                           // LANES + 100*(NV-1), NV in {1, 2, 4}
+    if (g >= 300) g = 100 + KP / 8;                             // NV = 4 is not instantiated for the tiled kernel
+    // k = 64: batches of 8 columns (4 lanes x 4 words per column) instead of 16 when this rank holds few batches per
+    // resident warp (sharded runs: 125 K rows on 8 GPUs are 2.2 sixteen-column batches per warp — one warp in five
+    // works a third batch while the others idle). RCPPML_B200_TILED_SL = 2 / 4 forces a geometry.
+    if (KP == 64) {
+        int sl = tiled_sl_override;
+        if (sl == 0) {
+            const double batches16 = static_cast<double>(ncols) / (16.0 * num_sms * 24);
+            sl = (batches16 < tiled_sl4_below) ? 4 : 2;
+        }
+        if (sl == 4) g += 4000;
+    }
     return g;
 }
 
@@ -1108,7 +1177,7 @@ void Engine::enqueue_iteration() {
     // ---- W update (fit_cpu.hpp:713-893)
     if (p2p) normalize_peer_blocks(H.ptr, n, col_begin, col_begin + n_loc, normalize);   // side stream
     gram(Hblk, n_loc, normalize, G_h.ptr, RCPPML_B200_SEC_GRAM_W, sharded); // :644 (normalise) + :715
-    if (sharded && !p2p) allgather_rows(H.ptr, n_pad / world, RCPPML_B200_SEC_COMM);
+    if (sharded && !p2p) allgather_rows(H.ptr, col_cuts, n_pad, RCPPML_B200_SEC_COMM);
     prepare_solver(G_h.ptr, cfg.L2_W, RCPPML_B200_SEC_GRAM_W);              // :738
     join_side_stream();
     solve(1, warm, RCPPML_B200_SEC_SOLVE_W);                                // :748-767 (+ :884)
@@ -1121,7 +1190,7 @@ void Engine::enqueue_iteration() {
     profiling = was;
     loss(RCPPML_B200_SEC_LOSS);
     sec_end(RCPPML_B200_SEC_LOSS);
-    if (sharded && !p2p) allgather_rows(W_T.ptr, m_pad / world, RCPPML_B200_SEC_COMM);
+    if (sharded && !p2p) allgather_rows(W_T.ptr, row_cuts, m_pad, RCPPML_B200_SEC_COMM);
     ++iters_enqueued;
 }
 
@@ -1329,6 +1398,10 @@ void Engine::begin_fit(const rcppml_b200_config& c) {
     if (const char* env = std::getenv("RCPPML_B200_GRAPH")) graphs_enabled = std::atoi(env) != 0;
     build_panels();
     loss_hist.ensure(static_cast<size_t>(std::max(cfg.max_iter, 1024)));
+    // Every buffer the loop touches exists before the first iteration is enqueued: a cudaMalloc inside the loop would
+    // synchronise the device against peers that are already spinning in an exchange kernel (sharded fits).
+    carry.ensure(static_cast<size_t>(std::max(std::max(n_loc, m_loc), 1)) * KP);
+    loss_partials.ensure(static_cast<size_t>(num_sms) * 4 * 2);
     DevState s0{};
     s0.prev_loss = 3.402823466e+38f;                                        // fit_cpu.hpp:281
     B200_CUDA_CHECK(cudaMemcpyAsync(state.ptr, &s0, sizeof(DevState), cudaMemcpyHostToDevice, stream));
@@ -1397,10 +1470,11 @@ void Engine::iterate(int n_iters) {
             for (int s = 0; s < RCPPML_B200_NUM_SECTIONS; ++s) launches[s] += graph_launches[s];
             ++iters_enqueued;
         } else if (cv_active) enqueue_iteration_cv(); else if (has_mask) enqueue_iteration_masked(); else enqueue_iteration();
-        if ((it & 7) == 7 && (cfg.tol > 0.f || cv_active)) {
+        // (sharded fits poll as well, less often: a peer-memory exchange that timed out sets comm_error + stop)
+        if (((it & 7) == 7 && (cfg.tol > 0.f || cv_active)) || ((it & 31) == 31 && world > 1)) {
             B200_CUDA_CHECK(cudaMemcpyAsync(h_state, state.ptr, sizeof(DevState), cudaMemcpyDeviceToHost, stream));
             B200_CUDA_CHECK(cudaStreamSynchronize(stream));
-            if (h_state->stop) break;
+            if (h_state->stop || h_state->comm_error) break;
         }
     }
     join_side_stream();
@@ -1505,6 +1579,17 @@ int rcppml_b200_set_matrix_synthetic_sharded(rcppml_b200_engine* e, int m, int n
 int rcppml_b200_set_matrix_sharded_f32(rcppml_b200_engine* e, int m, int n, const int* cb_ptr, const int* cb_idx,
                                        const float* cb_val, const int* rb_ptr, const int* rb_idx, const float* rb_val) {
     B200_API_BEGIN e->impl.set_matrix_sharded<float>(m, n, cb_ptr, cb_idx, cb_val, rb_ptr, rb_idx, rb_val); B200_API_END
+}
+int rcppml_b200_set_partition(rcppml_b200_engine* e, const int* col_cuts, const int* row_cuts) {
+    B200_API_BEGIN e->impl.set_partition(col_cuts, row_cuts); B200_API_END
+}
+int rcppml_b200_factor_checksum(rcppml_b200_engine* e, uint64_t* out3) {
+    B200_API_BEGIN
+    B200_REQUIRE(out3 != nullptr, "factor_checksum: null output");
+    unsigned long long h[3] = {0, 0, 0};
+    e->impl.factor_checksum(h);
+    for (int i = 0; i < 3; ++i) out3[i] = static_cast<uint64_t>(h[i]);
+    B200_API_END
 }
 int rcppml_b200_get_shard(rcppml_b200_engine* e, int* col_begin, int* n_loc, int* row_begin, int* m_loc, int64_t* nnz_global) {
     B200_API_BEGIN

@@ -99,6 +99,14 @@ public:
     int col_begin = 0, n_loc = 0;           // this rank's column block J (H half-step)
     int row_begin = 0, m_loc = 0;           // this rank's row block I (W half-step)
     int m_pad = 0, n_pad = 0;               // m, n rounded up to a multiple of world (equal all-gather blocks)
+    // Partition over the ranks: rank r owns columns [col_cuts[r], col_cuts[r+1]) of H and rows [row_cuts[r],
+    // row_cuts[r+1]) of W_T. Default: equal blocks of ceil(total/world). set_partition installs explicit cuts
+    // (contiguous ranges balanced by work) for the following set_matrix_* calls; nullptr restores
+    // the default. Every rank must install the same cuts.
+    std::vector<int> col_cuts, row_cuts, pending_col_cuts, pending_row_cuts;
+    bool equal_partition = true;
+    void set_partition(const int* col_cuts_in, const int* row_cuts_in);
+    void factor_checksum(unsigned long long* out3);
     int64_t nnz = 0, nnz_w = 0, nnz_global = 0;   // nnz of A[:,J], of A[I,:], of A
     bool matrix_ready = false, factors_ready = false, fit_active = false;
     DeviceBuffer<int> Ap, Ai, Atp, Ati;
@@ -124,6 +132,8 @@ public:
     // for short columns (default), 2: always. RCPPML_B200_TILED overrides.
     int tiled_mode = 1;
     double tiled_min_batches = 0.5, narrow_min_cols = 0.0;
+    int tiled_sl_override = 0;              // k = 64 tiled kernel: solve lanes per column (0: rule, 2: 16-column batches, 4: 8)
+    double tiled_sl4_below = 0.0;
     bool use_narrow_cd(long long ncols) const;
     bool use_tiled(int solver, long long cnt, long long ncols) const;
     int tiled_gather_geom(long long cnt, long long ncols) const;
@@ -190,6 +200,7 @@ public:
 
 private:
     cudaEvent_t ev_loop_begin = nullptr, ev_loop_end = nullptr;
+    void init_device_objects();
 
     void set_dims(int m, int n);
     void finish_matrix();
@@ -201,7 +212,7 @@ private:
                     DeviceBuffer<int>& dp, DeviceBuffer<int>& di, DeviceBuffer<float>& dx);
     void synth_block(int m, int c0, int nc, int r0, int r1, double density, uint64_t seed, DeviceBuffer<int>& dp,
                      DeviceBuffer<int>& di, DeviceBuffer<float>& dx, int64_t* cnt_out);
-    void allgather_rows(float* buf, int rows_per_rank, int sec);
+    void allgather_rows(float* buf, const std::vector<int>& cuts, int rows_padded, int sec);
     void alloc_factors(int k);
     void normalize_cfg(const rcppml_b200_config& c);
     void sec_begin(int sec, cudaStream_t on = nullptr);

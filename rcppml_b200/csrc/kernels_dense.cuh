@@ -335,7 +335,9 @@ static __global__ void __launch_bounds__(1024) xchg_allreduce_kernel(const doubl
         for (;;) {
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
             if (v >= x.seq) break;
-            if (clock64() - t0 > 4000000000LL) { st->comm_error = 1; break; }     // ~2 s: never hang the GPU
+            // ~2 s: never hang the GPU. `stop` turns every later kernel of this fit into a no-op, so a dead peer costs
+            // one time-out, not one per exchange; the host sees comm_error at its next poll (Engine::iterate).
+            if (clock64() - t0 > 4000000000LL) { st->comm_error = 1; st->stop = 1; break; }
         }
     }
     __syncthreads();
@@ -559,6 +561,26 @@ static __global__ void init_uniform_kernel(float* __restrict__ dst, long long nc
     const unsigned long long idx = first_elem + static_cast<unsigned long long>(c) * k + i;
     const unsigned long long state = state0 + (idx + 1ULL) * 0x9e3779b97f4a7c15ULL;
     dst[e] = u64_to_unit_float(splitmix_mix(state));
+}
+
+// 64-bit checksum of the logical k x ncols factor (padding excluded), independent of the launch geometry: the sum
+// (mod 2^64) over elements of mix(position) ^ mix(bits). Equal checksums <=> bit-identical factors (up to 2^-64);
+// bench.py and the multi-GPU checks compare sharded fits with the one-GPU fit of the same seed this way.
+static __global__ void __launch_bounds__(256) checksum_kernel(const float* __restrict__ X, long long ncols, int k, int KP,
+                                                              unsigned long long* __restrict__ out) {
+    unsigned long long acc = 0;
+    const long long total = ncols * k;
+    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
+         e += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long c = e / k;
+        const int i = static_cast<int>(e % k);
+        const unsigned bits = __float_as_uint(X[c * KP + i]);
+        acc += splitmix_mix(static_cast<unsigned long long>(e + 1) * 0x9e3779b97f4a7c15ULL) ^
+               splitmix_mix(0x5851f42d4c957f2dULL + bits);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
 }
 
 // tr(AᵀA) partials (primitives/primitives.hpp:101-115) in fp64; reduced on the host.

@@ -10,13 +10,40 @@ namespace {
 
 using b200::DeviceBuffer;
 
+// First sm_100+ device (this library carries sm_100a code only; rcppml_gpu_detect counts the same devices), made
+// current; its SM count sizes the grids. Throws when there is none.
+int select_device(int* num_sms) {
+    int count = 0;
+    B200_REQUIRE(cudaGetDeviceCount(&count) == cudaSuccess && count > 0, "no CUDA device");
+    for (int dev = 0; dev < count; ++dev) {
+        cudaDeviceProp prop{};
+        if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess && prop.major >= 10) {
+            B200_CUDA_CHECK(cudaSetDevice(dev));
+            if (num_sms) *num_sms = prop.multiProcessorCount;
+            return dev;
+        }
+    }
+    throw std::runtime_error("no sm_100+ device");
+}
+
+// The stream of one entry-point call: destroyed on every exit path (a thrown B200_REQUIRE / CUDA error included).
+struct ScopedStream {
+    cudaStream_t s = nullptr;
+    ScopedStream() { B200_CUDA_CHECK(cudaStreamCreate(&s)); }
+    ~ScopedStream() { if (s) cudaStreamDestroy(s); }
+    ScopedStream(const ScopedStream&) = delete;
+    ScopedStream& operator=(const ScopedStream&) = delete;
+};
+
+int g_num_sms = b200::kNumSMs;     // of the device select_device() made current (entry points are synchronous)
+
 template <int KP>
 void launch_gram_f64(const double* F, long long ncols, double* partials, int grid, cudaStream_t s) {
     b200::gram_f64_kernel<KP><<<grid, 256, 0, s>>>(F, ncols, partials);
 }
 void gram_f64(int KP, int k, const double* F, long long ncols, double add1, double add2, double add3, double* G,
               cudaStream_t s) {
-    const int grid = 148 * 2;
+    const int grid = g_num_sms * 2;
     DeviceBuffer<double> partials;
     partials.ensure(static_cast<size_t>(grid) * KP * KP);
     switch (KP) {
@@ -38,7 +65,7 @@ void launch_project(const b200::ProjectParams& p, cudaStream_t s) {
     int occ = 0;
     B200_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, b200::project_f64_kernel<KP>, 256, smem));
     B200_REQUIRE(occ > 0, "project_f64_kernel does not fit on an SM");
-    b200::project_f64_kernel<KP><<<148 * occ, 256, smem, s>>>(p);
+    b200::project_f64_kernel<KP><<<g_num_sms * occ, 256, smem, s>>>(p);
 }
 
 struct DeviceCsc64 {
@@ -86,11 +113,9 @@ void rcppml_gpu_nnls_double(const int* col_ptr, const int* row_idx, const double
     try {
         B200_REQUIRE(*k >= 1 && *k <= b200::kMaxKP, "rank must be in [1, 128]");
         B200_REQUIRE(*m > 0 && *n > 0 && *nnz >= 0 && *cd_maxit > 0, "bad dimensions");
-        int count = 0;
-        B200_REQUIRE(cudaGetDeviceCount(&count) == cudaSuccess && count > 0, "no CUDA device");
-        B200_CUDA_CHECK(cudaSetDevice(0));
-        cudaStream_t s;
-        B200_CUDA_CHECK(cudaStreamCreate(&s));
+        select_device(&g_num_sms);
+        ScopedStream stream_guard;
+        cudaStream_t s = stream_guard.s;
         const int KP = b200::padded_rank(*k);
         DeviceCsc64 A;
         A.upload(*n, *nnz, col_ptr, row_idx, values, s);
@@ -123,7 +148,6 @@ void rcppml_gpu_nnls_double(const int* col_ptr, const int* row_idx, const double
         b200::unpad_f64_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(H.ptr, out.ptr, *n, *k, KP);
         B200_CUDA_CHECK(cudaMemcpyAsync(h, out.ptr, total * sizeof(double), cudaMemcpyDeviceToHost, s));
         B200_CUDA_CHECK(cudaStreamSynchronize(s));
-        cudaStreamDestroy(s);
         *out_status = 0;
     } catch (const std::exception& ex) {
         warn(ex.what());
@@ -143,11 +167,9 @@ void rcppml_gpu_evaluate_double(const int* col_ptr, const int* row_idx, const do
     *out_status = -1;
     try {
         B200_REQUIRE(*k >= 1 && *k <= b200::kMaxKP, "rank must be in [1, 128]");
-        int count = 0;
-        B200_REQUIRE(cudaGetDeviceCount(&count) == cudaSuccess && count > 0, "no CUDA device");
-        B200_CUDA_CHECK(cudaSetDevice(0));
-        cudaStream_t s;
-        B200_CUDA_CHECK(cudaStreamCreate(&s));
+        select_device(&g_num_sms);
+        ScopedStream stream_guard;
+        cudaStream_t s = stream_guard.s;
         const int KP = b200::padded_rank(*k);
         DeviceCsc64 A;
         A.upload(*n, *nnz, col_ptr, row_idx, values, s);
@@ -155,7 +177,7 @@ void rcppml_gpu_evaluate_double(const int* col_ptr, const int* row_idx, const do
         upload_padded(w_T, *m, *k, KP, W, s);
         upload_padded(h, *n, *k, KP, H, s);
         upload_padded(d, 1, *k, KP, D, s);
-        const int grid = 148 * 4;
+        const int grid = g_num_sms * 4;
         part.ensure(static_cast<size_t>(grid) * 3);
         b200::eval_nnz_kernel<<<grid, 256, 0, s>>>(A.p.ptr, A.i.ptr, A.x.ptr, *n, KP, *k, W.ptr, H.ptr, D.ptr, part.ptr);
         std::vector<double> hp(static_cast<size_t>(grid) * 3);
@@ -179,7 +201,6 @@ void rcppml_gpu_evaluate_double(const int* col_ptr, const int* row_idx, const do
                 for (int j = 0; j < *k; ++j) recon += d[i] * d[j] * gw[static_cast<size_t>(j) * KP + i] * gh[static_cast<size_t>(j) * KP + i];
             *out_loss = (aa - 2.0 * cross + recon) / (static_cast<double>(*m) * static_cast<double>(*n));
         }
-        cudaStreamDestroy(s);
         *out_status = 0;
     } catch (const std::exception& ex) {
         warn(ex.what());

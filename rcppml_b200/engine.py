@@ -109,6 +109,19 @@ class Engine:
             _p(arrs[3], C.c_int), _p(arrs[4], C.c_int), _p(arrs[5], C.c_float)), "set_matrix_sharded")
         self._refresh_shard(m, n)
 
+    def set_partition(self, col_cuts=None, row_cuts=None):
+        """Explicit partition for the following set_matrix_* calls (same cuts on every rank): world+1 ascending cuts
+        0 .. n / 0 .. m (rcppml_b200.shard.balanced_cuts); None restores equal blocks."""
+        cc = None if col_cuts is None else np.ascontiguousarray(col_cuts, np.int32)
+        rc = None if row_cuts is None else np.ascontiguousarray(row_cuts, np.int32)
+        _lib.check(self._lib.rcppml_b200_set_partition(self._h, _p(cc, C.c_int), _p(rc, C.c_int)), "set_partition")
+
+    def factor_checksum(self):
+        """64-bit device-side checksums (W_T, H, d) of the logical factors: equal <=> bit-identical."""
+        out = (C.c_uint64 * 3)()
+        _lib.check(self._lib.rcppml_b200_factor_checksum(self._h, out), "factor_checksum")
+        return int(out[0]), int(out[1]), int(out[2])
+
     def get_matrix(self):
         p = np.empty(self.n_loc + 1, np.int32)
         i = np.empty(self.nnz, np.int32)

@@ -30,6 +30,23 @@ def shard_columns_by_nnz(indptr, world: int):
     return [(bounds[r], bounds[r + 1] - bounds[r]) for r in range(world)]
 
 
+def balanced_cuts(counts, world: int, per_item: float = 0.0):
+    """Contiguous ranges balanced by WORK (SURVEY.md §8e "contiguous column ranges balanced by nnz"): item j costs
+    counts[j] + per_item (the gather is proportional to its non-zeros, the k x k solve is a constant per column; the
+    engine's in-process path uses per_item = k). Returns world+1 ascending cuts, cuts[0] = 0, cuts[world] = len(counts):
+    cut r is the first position whose work prefix reaches r/world of the total (csrc/engine.cu balanced_cuts_host)."""
+    counts = np.asarray(counts, dtype=np.float64)
+    total_items = counts.size
+    prefix = np.concatenate([[0.0], np.cumsum(counts + per_item)])
+    cuts = [0]
+    for r in range(1, world):
+        target = prefix[-1] * r / world
+        j = int(np.searchsorted(prefix, target, side="left"))
+        cuts.append(min(max(j, cuts[-1]), total_items))
+    cuts.append(total_items)
+    return np.asarray(cuts, dtype=np.int32)
+
+
 def extract_row_block(indptr, indices, data, first: int, count: int):
     """CSC of A[first:first+count, :] over ALL columns, row ids relative to the block (the W half-step
     operand of the rank owning those rows)."""

@@ -143,7 +143,7 @@ def test_bench_reference_arm_prints_the_contract_line():
 def test_bench_sharded_e2e_host_logic(monkeypatch):
     """bench.run_e2e_sharded (the N > 1 end-to-end leg) with a stand-in engine and process group: the host code path the
     driver's scaling run takes — pinned staging of the blocks, result buffers handed to get_factors(out=...), byte
-    accounting — for the default and the --e2e-blocks variant. No CUDA: pinned allocation and device tensors are mapped
+    accounting (--e2e-sharded variant, block-wise factor I/O). No CUDA: pinned allocation and device tensors are mapped
     to plain host ones for the duration of the test."""
     import sys
     import types
@@ -207,17 +207,13 @@ def test_bench_sharded_e2e_host_logic(monkeypatch):
         def all_reduce(self, t, op=None):
             pass
 
-    for blocks in (False, True):
-        calls.clear()
-        args = types.SimpleNamespace(m=m, k=k, L1=0.0, L2=0.0, solver="cholesky", e2e_blocks=blocks)
-        r = bench.run_e2e_sharded(args, Eng(), Dist(), 3, 0, 2)
-        assert r["value"] > 0 and r["unit"] == "nnz/s" and r["h2d_bytes_per_step"] > 0 and r["d2h_bytes_per_step"] > 0
-        if blocks:
-            assert calls == [("set_factor_blocks", (30, k), (20, k)), "get_factor_blocks"] * 2
-            assert r["d2h_bytes_per_step"] == (30 * k * 4 + 20 * k * 4 + 4 * k) // 3
-        else:
-            assert calls == [("set_factors", (m, k), (n, k)), "get_factors"] * 2
-            assert r["d2h_bytes_per_step"] == (m * k * 4 + n * k * 4 + 4 * k) // 3
+    calls.clear()
+    args = types.SimpleNamespace(m=m, k=k, L1=0.0, L2=0.0, solver="cholesky")
+    r = bench.run_e2e_sharded(args, Eng(), Dist(), 3, 0, 2)
+    assert r["value"] > 0 and r["unit"] == "nnz/s" and r["h2d_bytes_per_step"] > 0 and r["d2h_bytes_per_step"] > 0
+    # block-wise factor I/O: only this rank's rows of W_T / H cross PCIe, both ways (warm-up call + timed call)
+    assert calls == [("set_factor_blocks", (30, k), (20, k)), "get_factor_blocks"] * 2
+    assert r["d2h_bytes_per_step"] == (30 * k * 4 + 20 * k * 4 + 4 * k) // 3
 
 
 def test_row_block_operand_is_a_column_slice_of_the_transpose():
