@@ -659,7 +659,10 @@ def main():
     cpu = None
     if world == 1:
         if not args.no_cpu:
-            cpu = run_cpu_reference(args, steps=3, warmup=1, budget_s=args.cpu_budget_s, keep_fit=not args.no_parity)
+            # the FULL benchmark matrix (1 warm-up + 3 timed iterations: ~7 s of 16 cores at C4) unless that would take
+            # longer than 90 s — parity is then checked on the object that was timed
+            cpu = run_cpu_reference(args, steps=3, warmup=1, budget_s=args.cpu_budget_s, keep_fit=not args.no_parity,
+                                    prefer_full=True, hard_cap_s=90.0)
             if not args.no_parity:
                 parity = parity_vs_oracle(args, eng, cpu, mode)
     elif not args.no_parity:

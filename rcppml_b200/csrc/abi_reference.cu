@@ -3,6 +3,8 @@
 #include "engine.hpp"
 
 #include <algorithm>
+#include <chrono>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <memory>
@@ -57,9 +59,12 @@ struct EngineLease {
 // the same sharded ALS as the one-process-per-GPU path (engine.cu: column block of H + row block of W_T per device,
 // solved columns stored straight into every replica over NVLink, one-shot peer-memory all-reduces), with one Engine
 // per device and one host thread per Engine inside this process; peers are plain device pointers after
-// cudaDeviceEnablePeerAccess — no NCCL, no IPC. Every device receives the whole matrix over its own PCIe link and
-// slices its two operands out of the device transpose. Results are bit-identical to one GPU.
-// STATUS (round 1): compiled and reviewed, NOT yet run on a multi-GPU box (tools/gpu_jobs/round2_inprocess_multigpu.sh).
+// cudaDeviceEnablePeerAccess — no NCCL, no IPC.
+// Ingest is sharded too: device g pulls only A[:, J_g] (nnz/G entries) and its blocks of W / H over ITS PCIe link; the
+// row blocks A[I_g, :] are assembled from the peers' column blocks over NVLink (Engine::assemble_row_block), the factor
+// replicas are completed by peer copies, and every device writes its own blocks of the result straight into the
+// caller's W / H. Partition: contiguous ranges balanced by work (non-zeros + k per column).
+// Results are bit-identical to one GPU (same per-column arithmetic; fp64 reductions only re-associate).
 int usable_devices(int* ids, int cap) {
     int count = 0, usable = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess) return 0;
@@ -78,15 +83,63 @@ int requested_gpus() {
     return v <= 0 ? 8 : std::min(v, 8);
 }
 
+// Host-side barrier of the per-device threads. fail() releases everybody: wait() then returns false on every thread,
+// so one device's exception can never leave the others blocked.
+struct PhaseBarrier {
+    std::mutex mu;
+    std::condition_variable cv;
+    int n = 0, waiting = 0;
+    unsigned gen = 0;
+    bool failed = false;
+    explicit PhaseBarrier(int n_) : n(n_) {}
+    bool wait() {
+        std::unique_lock<std::mutex> l(mu);
+        if (failed) return false;
+        const unsigned g = gen;
+        if (++waiting == n) {
+            waiting = 0;
+            ++gen;
+            cv.notify_all();
+            return true;
+        }
+        cv.wait(l, [&] { return gen != g || failed; });
+        return !failed;
+    }
+    void fail() {
+        std::lock_guard<std::mutex> l(mu);
+        failed = true;
+        cv.notify_all();
+    }
+};
+
+// Contiguous column ranges balanced by work = non-zeros + per_item per column, straight from the host col_ptr
+// (rcppml_b200/shard.py balanced_cuts: cut r = smallest j with prefix(j) >= total * r / G).
+void balanced_col_cuts(const int* col_ptr, int n, int G, int per_item, int* cuts) {
+    auto prefix = [&](int j) { return static_cast<double>(col_ptr[j]) + static_cast<double>(per_item) * j; };
+    const double total = prefix(n);
+    cuts[0] = 0;
+    for (int r = 1; r < G; ++r) {
+        const double target = total * r / G;
+        int lo = 0, hi = n;
+        while (lo < hi) {
+            const int mid = lo + ((hi - lo) >> 1);
+            if (prefix(mid) < target) lo = mid + 1; else hi = mid;
+        }
+        cuts[r] = std::max(lo, cuts[r - 1]);
+    }
+    cuts[G] = n;
+}
+
 // The engines of the last multi-GPU call are kept (grow-only device buffers, like the single-GPU cache) and reused
 // when the next call asks for the same devices; any failure drops them. Guarded by g_mu.
 std::vector<std::unique_ptr<b200::Engine>> g_multi;
 std::vector<int> g_multi_devices;
 
-// Returns false (after warn) on any failure; fills res / W / H / d from rank 0 on success. Caller holds g_mu.
+// Returns false (after warn) on any failure; fills res / W / H / d on success. Caller holds g_mu.
 bool fit_in_process_multi_gpu(int G, const int* devices, int m, int n, int64_t nnz, const int* col_ptr, const int* row_idx,
                               const double* values, int k, double* W, double* H, double* d, const rcppml_b200_config& cfg,
                               rcppml_b200_result* res) {
+    const auto t_call = std::chrono::steady_clock::now();
     const char* env = std::getenv("RCPPML_B200_CACHE");
     const bool cache = !(env && env[0] == '0');
     if (!(cache && static_cast<int>(g_multi.size()) == G && g_multi_devices == std::vector<int>(devices, devices + G))) {
@@ -95,47 +148,78 @@ bool fit_in_process_multi_gpu(int G, const int* devices, int m, int n, int64_t n
         g_multi_devices.assign(devices, devices + G);
     }
     std::vector<std::unique_ptr<b200::Engine>>& eng = g_multi;
+    // RCPPML_B200_BALANCE=0: equal blocks (the partition of the one-process-per-GPU path's default)
+    const char* benv = std::getenv("RCPPML_B200_BALANCE");
+    const bool balance = !(benv && benv[0] == '0');
+    std::vector<int> col_cuts(G + 1, 0), row_cuts(G + 1, 0);
+    if (balance) balanced_col_cuts(col_ptr, n, G, k, col_cuts.data());
+    std::vector<b200::Engine*> all(G, nullptr);
+    std::vector<double> sumsq(G, 0.0);
+    std::vector<rcppml_b200_result> rr(G);
     std::vector<std::string> err(G);
-    auto run_all = [&](auto&& body) {
-        std::vector<std::thread> th;
-        th.reserve(G);
-        try {
-            for (int g = 0; g < G; ++g)
-                th.emplace_back([&, g] {
-                    try { body(g); }
-                    catch (const std::exception& ex) { err[g] = ex.what()[0] ? ex.what() : "error"; }
-                    catch (...) { err[g] = "unknown error"; }
-                });
-        } catch (...) {                                        // thread creation failed: the ranks that did start will
-            err[G - 1] = "could not start a host thread";      // time out in their first exchange (2 s) and return
-        }
-        for (auto& t : th) t.join();
-        for (int g = 0; g < G; ++g)
-            if (!err[g].empty()) { warn(("multi-GPU rank " + std::to_string(g) + ": " + err[g]).c_str()); return false; }
-        return true;
-    };
-    bool ok = run_all([&](int g) {                             // phase 1: data on every device, exchange buffers
+    PhaseBarrier bar(G);
+    double marks[6] = {0, 0, 0, 0, 0, 0};                     // rank 0's wall clock at the phase boundaries (ms)
+    auto since = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count(); };
+
+    auto body = [&](int g) {
         if (!eng[g]) {
             eng[g].reset(new b200::Engine(devices[g]));
             eng[g]->comm_init_local(g, G);
         }
-        eng[g]->set_matrix_host_shard<double>(m, n, nnz, col_ptr, row_idx, values);
-        eng[g]->set_factors_host<double>(k, W, H);
-        eng[g]->comm_prepare_local(devices);
-    });
-    if (ok) {
-        std::vector<b200::Engine*> all(G);
-        for (int g = 0; g < G; ++g) all[g] = eng[g].get();
-        try { for (int g = 0; g < G; ++g) eng[g]->comm_attach_local(all.data()); }
-        catch (const std::exception& ex) { warn(ex.what()); ok = false; }
+        b200::Engine& E = *eng[g];
+        all[g] = &E;
+        E.enable_peer_access(devices);
+        E.set_partition(balance ? col_cuts.data() : nullptr, nullptr);
+        E.upload_col_block_host<double>(m, n, col_ptr, row_idx, values);     // own column block + row histogram
+        if (!bar.wait()) return;                                             // A: every column block is resident
+        if (g == 0) {
+            marks[0] = since();
+            if (balance) E.balanced_row_cuts(all.data(), k, row_cuts.data());
+            else row_cuts = E.row_cuts;                                      // equal blocks from set_dims
+        }
+        if (!bar.wait()) return;                                             // B: row cuts known
+        sumsq[g] = E.assemble_row_block(all.data(), row_cuts.data());        // NVLink pulls + local transpose
+        if (!bar.wait()) return;                                             // C: nobody reads a peer's column block any more
+        if (g == 0) marks[1] = since();
+        double s = 0.0;
+        for (int r = 0; r < G; ++r) s += sumsq[r];                           // rank order: identical on every device
+        E.finish_matrix_local(s, nnz);
+        E.upload_factor_blocks_host<double>(k, W, H);                        // own rows of W_T, own columns of H
+        E.comm_prepare_local(devices);
+        if (!bar.wait()) return;                                             // D: every replica buffer exists, own blocks in place
+        E.comm_attach_local(all.data());
+        E.pull_factor_blocks_from_peers();
+        if (g == 0) marks[2] = since();
+        E.begin_fit(cfg);                                                    // (its first exchange orders the pulls against the peers' first stores)
+        E.iterate(cfg.max_iter);
+        E.get_result(&rr[g]);
+        if (g == 0) marks[3] = since();
+        if (rr[g].status == 0)
+            E.get_factor_blocks_host<double>(W + static_cast<size_t>(E.row_begin) * k, H + static_cast<size_t>(E.col_begin) * k,
+                                             g == 0 ? d : nullptr);
+        if (g == 0) marks[4] = since();
+    };
+    {
+        std::vector<std::thread> th;
+        th.reserve(G);
+        auto guarded = [&](int g) {
+            try { body(g); }
+            catch (const std::exception& ex) { err[g] = ex.what()[0] ? ex.what() : "error"; bar.fail(); }
+            catch (...) { err[g] = "unknown error"; bar.fail(); }
+        };
+        try {
+            for (int g = 1; g < G; ++g) th.emplace_back(guarded, g);
+        } catch (...) {                                        // thread creation failed: release the ranks that did start
+            err[G - 1] = "could not start a host thread";
+            bar.fail();
+        }
+        if (err[G - 1].empty()) guarded(0);                    // the calling thread drives device 0
+        for (auto& t : th) t.join();
     }
-    std::vector<rcppml_b200_result> rr(G);
-    if (ok) ok = run_all([&](int g) {                          // phase 2: the loop (peers meet in the exchange kernels)
-        eng[g]->begin_fit(cfg);
-        eng[g]->iterate(cfg.max_iter);
-        eng[g]->get_result(&rr[g]);
-        if (g == 0 && rr[0].status == 0) eng[0]->get_factors_host<double>(W, H, d);
-    });
+    bool ok = true;
+    for (int g = 0; g < G && ok; ++g)
+        if (!err[g].empty()) { warn(("multi-GPU rank " + std::to_string(g) + ": " + err[g]).c_str()); ok = false; }
+    if (ok && bar.failed) { warn("multi-GPU: a rank stopped early"); ok = false; }
     if (ok)
         for (int g = 0; g < G; ++g)
             if (rr[g].status != 0) {
@@ -145,7 +229,13 @@ bool fit_in_process_multi_gpu(int G, const int* devices, int m, int n, int64_t n
             }
     if (ok) {
         *res = rr[0];
-        for (int i = 0; i < 5; ++i) g_phases[i] = eng[0]->phase_ms[i];
+        // phases of the call as rank 0 saw them: column-block upload | row-block assembly + transpose | factor blocks
+        // up + replicas | ALS loop (CUDA events) | factor blocks down
+        g_phases[0] = marks[0];
+        g_phases[1] = marks[1] - marks[0];
+        g_phases[2] = marks[2] - marks[1];
+        g_phases[3] = rr[0].loop_ms;
+        g_phases[4] = marks[4] - marks[3];
     }
     for (int g = 0; g < G; ++g) {                              // every device idle before anything is reused or freed
         if (!eng[g]) continue;
@@ -156,7 +246,7 @@ bool fit_in_process_multi_gpu(int G, const int* devices, int m, int n, int64_t n
         g_multi.clear();
         g_multi_devices.clear();
     }
-    cudaSetDevice(0);
+    cudaSetDevice(devices[0]);
     return ok;
 }
 
@@ -516,6 +606,7 @@ static void nmf_unified_impl(
         int devices[8];
         int G = 1;                                                      // masked path: single GPU
         if (!masked && requested_gpus() > 1) G = std::min(requested_gpus(), usable_devices(devices, 8));
+        while (G > 1 && (*n < 64 * G || *m < 64 * G)) --G;             // every device needs a real block of each factor
         rcppml_b200_result res{};
         std::unique_ptr<EngineLease> lease_holder;
         if (G > 1) {

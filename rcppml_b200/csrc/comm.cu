@@ -60,24 +60,30 @@ void Engine::comm_init_local(int rank_, int world_) {
     world = world_;
 }
 
-void Engine::comm_prepare_local(const int* devices) {
+void Engine::enable_peer_access(const int* devices) {
     use_device();
-    B200_REQUIRE(world > 1 && factors_ready, "comm_prepare_local: needs comm_init_local and allocated factors");
-    comm_ipc_close();
+    if (peer_access_enabled) return;
     for (int r = 0; r < world; ++r) {
         if (r == rank) continue;
         int can = 0;
         B200_CUDA_CHECK(cudaDeviceCanAccessPeer(&can, device, devices[r]));
-        B200_REQUIRE(can, "comm_prepare_local: no peer access between the selected devices (NVLink / NVSwitch required)");
+        B200_REQUIRE(can, "no peer access between the selected devices (NVLink / NVSwitch required)");
         const cudaError_t e = cudaDeviceEnablePeerAccess(devices[r], 0);
         if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
         else B200_CUDA_CHECK(e);
     }
+    peer_access_enabled = true;
+}
+
+void Engine::comm_prepare_local(const int* devices) {
+    use_device();
+    B200_REQUIRE(world > 1 && factors_ready, "comm_prepare_local: needs comm_init_local and allocated factors");
+    comm_ipc_close();
+    enable_peer_access(devices);
     xchg_ne_max = KP * KP;
-    xbuf.ensure(static_cast<size_t>(2) * world * xchg_ne_max + 16);
+    xbuf.ensure(static_cast<size_t>(2) * world * xchg_ne_max + kXchgTailWords);
     B200_CUDA_CHECK(cudaMemsetAsync(xbuf.ptr, 0, xbuf.bytes(), stream));
     B200_CUDA_CHECK(cudaStreamSynchronize(stream));
-    xchg_seq = 0;
 }
 
 void Engine::comm_attach_local(Engine* const* all) {
@@ -107,8 +113,6 @@ void Engine::allreduce_f64(double* buf, size_t count) {
         XchgParams x{};
         for (int r = 0; r < world; ++r) x.peer[r] = peer_x[r];
         x.rank = rank; x.world = world; x.ne_max = xchg_ne_max;
-        x.seq = ++xchg_seq;
-        x.phase = static_cast<int>(x.seq & 1ULL);
         xchg_allreduce_kernel<<<1, 1024, 0, stream>>>(buf, static_cast<int>(count), buf, x, state.ptr);
         launches[RCPPML_B200_SEC_COMM] += 1;
         return;
@@ -122,11 +126,10 @@ void Engine::comm_ipc_export(char* handles192) {
     B200_REQUIRE(world > 1 && factors_ready, "comm_ipc_export: needs a communicator and allocated factors");
     comm_ipc_close();
     xchg_ne_max = KP * KP;
-    const size_t doubles = static_cast<size_t>(2) * world * xchg_ne_max + 16;
+    const size_t doubles = static_cast<size_t>(2) * world * xchg_ne_max + kXchgTailWords;
     xbuf.ensure(doubles);
     B200_CUDA_CHECK(cudaMemsetAsync(xbuf.ptr, 0, xbuf.bytes(), stream));
     B200_CUDA_CHECK(cudaStreamSynchronize(stream));
-    xchg_seq = 0;
     cudaIpcMemHandle_t hs[3];
     B200_CUDA_CHECK(cudaIpcGetMemHandle(&hs[0], W_T.ptr));
     B200_CUDA_CHECK(cudaIpcGetMemHandle(&hs[1], H.ptr));

@@ -497,49 +497,147 @@ void Engine::set_matrix_sharded(int m_, int n_, const int* cb_ptr, const int* cb
 template void Engine::set_matrix_sharded<float>(int, int, const int*, const int*, const float*, const int*, const int*, const float*);
 template void Engine::set_matrix_sharded<double>(int, int, const int*, const int*, const double*, const int*, const int*, const double*);
 
-// In-process multi-GPU: every device receives the whole host matrix (its own PCIe link), transposes it on the device
-// and keeps two contiguous slices — columns J of A and columns I of Aᵀ (= rows I of A, inner = global column id,
-// ascending: the same operand set_matrix_sharded builds from a host-extracted row block). tr(AᵀA) is taken over the
-// whole matrix with the single-GPU reduction, so it is bit-identical to a one-GPU fit without any exchange.
-__global__ void rebase_pointers_kernel(const int* __restrict__ src, int count, int base, int* __restrict__ dst) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < count) dst[i] = src[i] - base;
+// ---- in-process multi-GPU ingest (abi_reference.cu: RCPPML_NUM_GPUS) ------------------------------------------------
+// Each device receives ONLY its column block of the host matrix over its own PCIe link (nnz/G entries instead of nnz);
+// the row block it needs for the W half-step is assembled from all devices' column blocks over NVLink
+// (assemble_row_block). The steps are separate methods because the host threads meet at barriers between them.
+
+// Step 1: dimensions + column partition (pending cuts, set_partition), own column block up. Host-synchronised.
+template <class ValT>
+void Engine::upload_col_block_host(int m_, int n_, const int* col_ptr, const int* row_idx, const ValT* values) {
+    use_device();
+    B200_REQUIRE(world > 1, "upload_col_block_host: needs comm_init_local first");
+    const auto t0 = std::chrono::steady_clock::now();
+    set_dims(m_, n_);
+    const int64_t p0 = col_ptr[col_begin], p1 = col_ptr[col_begin + n_loc];
+    nnz = p1 - p0;
+    upload_csc<ValT>(n_loc, nnz, col_ptr + col_begin, row_idx + p0, values + p0, Ap, Ai, Ax);
+    if (p0 != 0) rebase_int_kernel<<<(n_loc + 1 + 255) / 256, 256, 0, stream>>>(Ap.ptr, n_loc + 1, static_cast<int>(p0));
+    // row work of this block (balanced row partition): hist[r] = entries of row r in A[:, J]
+    row_hist.ensure(static_cast<size_t>(m));
+    B200_CUDA_CHECK(cudaMemsetAsync(row_hist.ptr, 0, static_cast<size_t>(m) * sizeof(int), stream));
+    if (nnz > 0) row_histogram_kernel<<<num_sms * 8, 256, 0, stream>>>(Ai.ptr, nnz, row_hist.ptr);
+    B200_CUDA_CHECK(cudaGetLastError());
+    B200_CUDA_CHECK(cudaStreamSynchronize(stream));
+    phase_ms[0] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+template void Engine::upload_col_block_host<float>(int, int, const int*, const int*, const float*);
+template void Engine::upload_col_block_host<double>(int, int, const int*, const int*, const double*);
+
+// Step 2 (one device, after every device finished step 1): row cuts balanced by work = non-zeros of the row +
+// per_item (the k x k solve is a constant per row), from the sum of all devices' histograms. cuts_out: world + 1 ints.
+void Engine::balanced_row_cuts(Engine* const* all, int per_item, int* cuts_out) {
+    use_device();
+    HistPtrs hp{};
+    for (int g = 0; g < world; ++g) hp.p[g] = all[g]->row_hist.ptr;
+    long long* work = scratch<long long>(8, static_cast<size_t>(m));
+    long long* inc = scratch<long long>(9, static_cast<size_t>(m));
+    sum_histograms_kernel<<<(m + 255) / 256, 256, 0, stream>>>(hp, world, m, per_item, work);
+    size_t temp_bytes = 0;
+    cub::DeviceScan::InclusiveSum(nullptr, temp_bytes, work, inc, m, stream);
+    unsigned char* temp = scratch<unsigned char>(5, temp_bytes);
+    B200_CUDA_CHECK(cub::DeviceScan::InclusiveSum(temp, temp_bytes, work, inc, m, stream));
+    int* dcuts = scratch<int>(10, 16);
+    balanced_cuts_kernel<<<1, 32, 0, stream>>>(inc, m, world, dcuts);
+    B200_CUDA_CHECK(cudaMemcpyAsync(cuts_out, dcuts, (world + 1) * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    B200_CUDA_CHECK(cudaStreamSynchronize(stream));
 }
 
-template <class ValT>
-void Engine::set_matrix_host_shard(int m_, int n_, int64_t nnz_, const int* col_ptr, const int* row_idx, const ValT* values) {
+// Step 3: install the row cuts, pull the runs of every column that fall into this device's rows out of all column
+// blocks (peer reads), transpose the row block locally. Returns this device's share of tr(AtA) (over its column block).
+double Engine::assemble_row_block(Engine* const* all, const int* row_cuts_in) {
     use_device();
-    B200_REQUIRE(world > 1, "set_matrix_host_shard: needs comm_init / comm_init_local first");
-    set_dims(m_, n_);
-    DeviceBuffer<int> fp, fi, tp, ti;
-    DeviceBuffer<float> fx, tx;
-    upload_csc<ValT>(n, nnz_, col_ptr, row_idx, values, fp, fi, fx);
-    transpose_csc(fp.ptr, fi.ptr, fx.ptr, n, m, nnz_, tp, ti, tx, 0);
-    auto slice = [&](const DeviceBuffer<int>& sp, const DeviceBuffer<int>& si, const DeviceBuffer<float>& sx, int first,
-                     int count, DeviceBuffer<int>& dp, DeviceBuffer<int>& di, DeviceBuffer<float>& dx) -> int64_t {
-        int ends[2] = {0, 0};
-        B200_CUDA_CHECK(cudaMemcpyAsync(&ends[0], sp.ptr + first, sizeof(int), cudaMemcpyDeviceToHost, stream));
-        B200_CUDA_CHECK(cudaMemcpyAsync(&ends[1], sp.ptr + first + count, sizeof(int), cudaMemcpyDeviceToHost, stream));
-        B200_CUDA_CHECK(cudaStreamSynchronize(stream));
-        const int64_t cnt = static_cast<int64_t>(ends[1]) - ends[0];
-        dp.ensure(static_cast<size_t>(std::max(count, 1)) + 1);
-        di.ensure(std::max<int64_t>(cnt, 1) + 4);
-        dx.ensure(std::max<int64_t>(cnt, 1) + 4);
-        rebase_pointers_kernel<<<(count + 1 + 255) / 256, 256, 0, stream>>>(sp.ptr + first, count + 1, ends[0], dp.ptr);
-        if (cnt > 0) {
-            B200_CUDA_CHECK(cudaMemcpyAsync(di.ptr, si.ptr + ends[0], cnt * sizeof(int), cudaMemcpyDeviceToDevice, stream));
-            B200_CUDA_CHECK(cudaMemcpyAsync(dx.ptr, sx.ptr + ends[0], cnt * sizeof(float), cudaMemcpyDeviceToDevice, stream));
-        }
-        B200_CUDA_CHECK(cudaGetLastError());
-        return cnt;
-    };
-    nnz = slice(fp, fi, fx, col_begin, n_loc, Ap, Ai, Ax);
-    nnz_w = slice(tp, ti, tx, row_begin, m_loc, Atp, Ati, Atx);
-    finish_matrix_from(fx.ptr, nnz_, false);               // host-synchronised at its end: the temporaries may go
+    const auto t0 = std::chrono::steady_clock::now();
+    row_cuts.assign(row_cuts_in, row_cuts_in + world + 1);
+    B200_REQUIRE(row_cuts.front() == 0 && row_cuts.back() == m, "assemble_row_block: the row cuts do not cover the matrix");
+    row_begin = row_cuts[rank]; m_loc = row_cuts[rank + 1] - row_cuts[rank];
+    equal_partition = false;
+    int* rstart = scratch<int>(8, static_cast<size_t>(n) + 1);
+    int* rcnt = scratch<int>(9, static_cast<size_t>(n) + 1);
+    int* rp = scratch<int>(10, static_cast<size_t>(n) + 1);
+    for (int g = 0; g < world; ++g) {
+        const Engine& P = *all[g];
+        B200_REQUIRE(P.col_begin == col_cuts[g] && P.n_loc == col_cuts[g + 1] - col_cuts[g], "assemble_row_block: peers disagree on the column partition");
+        if (P.n_loc > 0)
+            rowblock_count_kernel<<<(P.n_loc + 255) / 256, 256, 0, stream>>>(P.Ap.ptr, P.Ai.ptr, P.n_loc, row_begin, row_begin + m_loc,
+                                                                             rstart + P.col_begin, rcnt + P.col_begin);
+    }
+    B200_CUDA_CHECK(cudaMemsetAsync(rcnt + n, 0, sizeof(int), stream));
+    size_t temp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, temp_bytes, rcnt, rp, n + 1, stream);
+    unsigned char* temp = scratch<unsigned char>(5, temp_bytes);
+    B200_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(temp, temp_bytes, rcnt, rp, n + 1, stream));
+    int total = 0;
+    B200_CUDA_CHECK(cudaMemcpyAsync(&total, rp + n, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    // tr(AtA) share of the own column block meanwhile (fixed-order fp64 partials, summed on the host below)
+    const int nb = 1024;
+    double* part = scratch<double>(6, nb);
+    sumsq_kernel<<<nb, 256, 0, stream>>>(Ax.ptr, nnz, part);
+    std::vector<double> hp(nb);
+    B200_CUDA_CHECK(cudaMemcpyAsync(hp.data(), part, nb * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    B200_CUDA_CHECK(cudaStreamSynchronize(stream));
+    B200_REQUIRE(total >= 0, "assemble_row_block: nnz overflowed int32");
+    nnz_w = total;
+    int* ri = scratch<int>(11, static_cast<size_t>(std::max(total, 1)) + 4);
+    float* rx = scratch<float>(12, static_cast<size_t>(std::max(total, 1)) + 4);
+    for (int g = 0; g < world; ++g) {
+        const Engine& P = *all[g];
+        if (P.n_loc > 0)
+            rowblock_copy_kernel<<<num_sms * 8, 256, 0, stream>>>(P.Ai.ptr, P.Ax.ptr, P.n_loc, rstart + P.col_begin, rp + P.col_begin,
+                                                                  row_begin, ri, rx);
+    }
+    B200_CUDA_CHECK(cudaGetLastError());
+    transpose_csc(rp, ri, rx, n, std::max(m_loc, 1), nnz_w, Atp, Ati, Atx, 0);      // host-synchronised at its end
+    double s = 0.0;
+    for (double v : hp) s += v;
+    phase_ms[1] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return s;
+}
+
+// Step 4 (after every device finished step 3 — nobody reads this device's column block any more): tr(AtA) and nnz
+// of the whole matrix as summed by the caller in rank order.
+void Engine::finish_matrix_local(double sumsq_total, int64_t nnz_total) {
+    trAtA = static_cast<float>(sumsq_total);
+    nnz_global = nnz_total;
+    matrix_ready = true;
     has_mask = false;
 }
-template void Engine::set_matrix_host_shard<float>(int, int, int64_t, const int*, const int*, const float*);
-template void Engine::set_matrix_host_shard<double>(int, int, int64_t, const int*, const int*, const double*);
+
+// Step 5: own factor blocks up (rows [row_begin, +m_loc) of the full host W_T, columns [col_begin, +n_loc) of H).
+template <class T>
+void Engine::upload_factor_blocks_host(int k_, const T* W_full, const T* H_full) {
+    use_device();
+    alloc_factors(k_);
+    const auto t0 = std::chrono::steady_clock::now();
+    const size_t wcount = static_cast<size_t>(m_loc) * k, hcount = static_cast<size_t>(n_loc) * k;
+    T* stage = scratch<T>(7, wcount + hcount + 1);
+    if (wcount) B200_CUDA_CHECK(cudaMemcpyAsync(stage, W_full + static_cast<size_t>(row_begin) * k, wcount * sizeof(T), cudaMemcpyHostToDevice, stream));
+    if (hcount) B200_CUDA_CHECK(cudaMemcpyAsync(stage + wcount, H_full + static_cast<size_t>(col_begin) * k, hcount * sizeof(T), cudaMemcpyHostToDevice, stream));
+    if (wcount) pad_convert_kernel<T><<<static_cast<unsigned>((static_cast<long long>(m_loc) * KP + 255) / 256), 256, 0, stream>>>(
+        stage, W_T.ptr + static_cast<size_t>(row_begin) * KP, m_loc, k, KP);
+    if (hcount) pad_convert_kernel<T><<<static_cast<unsigned>((static_cast<long long>(n_loc) * KP + 255) / 256), 256, 0, stream>>>(
+        stage + wcount, H.ptr + static_cast<size_t>(col_begin) * KP, n_loc, k, KP);
+    B200_CUDA_CHECK(cudaGetLastError());
+    B200_CUDA_CHECK(cudaStreamSynchronize(stream));
+    h2d_bytes += (wcount + hcount) * sizeof(T);
+    phase_ms[2] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+template void Engine::upload_factor_blocks_host<float>(int, const float*, const float*);
+template void Engine::upload_factor_blocks_host<double>(int, const double*, const double*);
+
+// Step 6 (after comm_attach_local on every engine): complete the replicas with the peers' blocks over NVLink.
+void Engine::pull_factor_blocks_from_peers() {
+    use_device();
+    B200_REQUIRE(peers_ready && peers_local, "pull_factor_blocks_from_peers: peers not attached");
+    for (int g = 0; g < world; ++g) {
+        if (g == rank) continue;
+        const size_t wo = static_cast<size_t>(row_cuts[g]) * KP, wc = static_cast<size_t>(row_cuts[g + 1] - row_cuts[g]) * KP;
+        const size_t ho = static_cast<size_t>(col_cuts[g]) * KP, hc = static_cast<size_t>(col_cuts[g + 1] - col_cuts[g]) * KP;
+        if (wc) B200_CUDA_CHECK(cudaMemcpyAsync(W_T.ptr + wo, peer_W[g] + wo, wc * sizeof(float), cudaMemcpyDefault, stream));
+        if (hc) B200_CUDA_CHECK(cudaMemcpyAsync(H.ptr + ho, peer_H[g] + ho, hc * sizeof(float), cudaMemcpyDefault, stream));
+    }
+    B200_CUDA_CHECK(cudaStreamSynchronize(stream));
+}
 
 // SURVEY.md §8d generator. Columns [c0, c0+nc), rows kept in [r0, r1) and stored relative to r0.
 void Engine::synth_block(int m_, int c0, int nc, int r0, int r1, double density, uint64_t seed, DeviceBuffer<int>& dp,
@@ -634,7 +732,9 @@ void Engine::alloc_factors(int k_) {
     if (const char* env = std::getenv("RCPPML_B200_TILED_MIN_BATCHES")) tiled_min_batches = std::atof(env);
     tiled_sl_override = 0;
     if (const char* env = std::getenv("RCPPML_B200_TILED_SL")) tiled_sl_override = std::atoi(env);
-    tiled_sl4_below = 0.0;                                    // auto rule off until measured (profiles/r02*)
+    // measured per rank shape on one B200 (profiles/r02a_rank_shapes.jsonl, C4 W half-step, ms): N = 2: 1.227 -> 1.138,
+    // N = 4: 0.657 -> 0.603, N = 8: 0.378 -> 0.341 (one-geometry kernel: 1.339 / 0.685 / 0.357)
+    tiled_sl4_below = 12.0;
     if (const char* env = std::getenv("RCPPML_B200_TILED_SL4_BELOW")) tiled_sl4_below = std::atof(env);
     narrow_min_cols = 8.0 * num_sms * 24;
     if (std::getenv("RCPPML_B200_CD_GEOM")) narrow_min_cols = 0.0;           // an explicit geometry applies to every size
@@ -1168,9 +1268,13 @@ void Engine::enqueue_iteration() {
     const bool p2p = sharded && peers_ready;
     float* Hblk = H.ptr + static_cast<size_t>(col_begin) * KP;
     float* Wblk = W_T.ptr + static_cast<size_t>(row_begin) * KP;
-    // ---- H update (fit_cpu.hpp:488-645)
-    if (iters_enqueued == 0) gram(Wblk, m_loc, false, G_w.ptr, RCPPML_B200_SEC_GRAM_H, sharded);   // :491
-    prepare_solver(G_w.ptr, cfg.L2_H, RCPPML_B200_SEC_GRAM_H);              // :506
+    // ---- H update (fit_cpu.hpp:488-645). The Gram of W_T and the solver operands built from it are produced at the END
+    // of the previous iteration (the Gram doubles as the loss's; the LLT then runs while the side stream still
+    // normalises the peers' blocks of W_T), so a steady-state iteration starts directly with the solve.
+    if (iters_enqueued == 0) {
+        gram(Wblk, m_loc, false, G_w.ptr, RCPPML_B200_SEC_GRAM_H, sharded);   // :491
+        prepare_solver(G_w.ptr, cfg.L2_H, RCPPML_B200_SEC_GRAM_H);            // :506
+    }
     join_side_stream();                                                     // W_T fully normalised (peer blocks)
     solve(0, warm, RCPPML_B200_SEC_SOLVE_H);                                // :516-535 (+ :636 upper bound)
     scale_finalize(RCPPML_B200_SEC_SCALE_H, sharded);                       // :644 (p2p: also the barrier)
@@ -1191,6 +1295,8 @@ void Engine::enqueue_iteration() {
     loss(RCPPML_B200_SEC_LOSS);
     sec_end(RCPPML_B200_SEC_LOSS);
     if (sharded && !p2p) allgather_rows(W_T.ptr, row_cuts, m_pad, RCPPML_B200_SEC_COMM);
+    prepare_solver(G_w.ptr, cfg.L2_H, RCPPML_B200_SEC_GRAM_H);              // next iteration's :506 (no-op once stopped)
+    if (capturing) join_side_stream();                                      // a captured graph has no dangling branch
     ++iters_enqueued;
 }
 
@@ -1431,17 +1537,20 @@ void Engine::capture_iteration_graph() {
     const auto before = launches;
     const int it0 = iters_enqueued;
     cudaGraph_t graph = nullptr;
+    join_side_stream();                                                     // nothing of a plain iteration dangles into the capture
     if (cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
         cudaGetLastError();
         graphs_enabled = false;
         return;
     }
     bool ok = true;
+    capturing = true;
     try {
         enqueue_iteration();
     } catch (...) {
         ok = false;
     }
+    capturing = false;
     if (cudaStreamEndCapture(stream, &graph) != cudaSuccess || !graph) ok = false;
     iters_enqueued = it0;                                                   // nothing has executed
     for (int s = 0; s < RCPPML_B200_NUM_SECTIONS; ++s) graph_launches[s] = launches[s] - before[s];
@@ -1463,7 +1572,10 @@ void Engine::iterate(int n_iters) {
     // kernels enqueued after `stop` return immediately. Every 8 iterations the host peeks at the
     // flag only to avoid enqueuing a long tail of no-op launches.
     for (int it = 0; it < n_iters; ++it) {
-        const bool graphable = graphs_enabled && !cv_active && !has_mask && world == 1 && !profiling && iters_enqueued >= 1;
+        // (sharded fits: only the peer-memory loop — its exchange kernels carry no per-call argument; the NCCL loop
+        // is launched plainly)
+        const bool graphable = graphs_enabled && !cv_active && !has_mask && (world == 1 || peers_ready) && !profiling &&
+                               iters_enqueued >= 1;
         if (graphable && !iter_graph) capture_iteration_graph();
         if (graphable && iter_graph) {
             B200_CUDA_CHECK(cudaGraphLaunch(iter_graph, stream));

@@ -85,10 +85,17 @@ public:
     void comm_init_local(int rank, int world);
     void comm_prepare_local(const int* devices);          // exchange buffer + cudaDeviceEnablePeerAccess to every peer
     void comm_attach_local(Engine* const* all);           // after EVERY engine ran comm_prepare_local
-    // The whole host matrix goes to this device; the engine keeps its column block and its row block of the device
-    // transpose (both are contiguous slices), so no host-side transposition or extraction is needed.
+    void enable_peer_access(const int* devices);          // cudaDeviceEnablePeerAccess to every peer (idempotent)
+    // Sharded ingest of a HOST matrix (engine.cu, "in-process multi-GPU ingest"): every device uploads only its column
+    // block; row blocks are assembled from the peers' column blocks over NVLink; factors travel block-wise.
     template <class ValT>
-    void set_matrix_host_shard(int m, int n, int64_t nnz, const int* col_ptr, const int* row_idx, const ValT* values);
+    void upload_col_block_host(int m, int n, const int* col_ptr, const int* row_idx, const ValT* values);
+    void balanced_row_cuts(Engine* const* all, int per_item, int* cuts_out);
+    double assemble_row_block(Engine* const* all, const int* row_cuts_in);
+    void finish_matrix_local(double sumsq_total, int64_t nnz_total);
+    template <class T> void upload_factor_blocks_host(int k, const T* W_full, const T* H_full);
+    void pull_factor_blocks_from_peers();
+    DeviceBuffer<int> row_hist;                           // [m] entries per row of the own column block
 
     // ---- state (public: the C ABI shims read it) ------------------------------------------
     int device = 0;
@@ -160,6 +167,7 @@ public:
     // launch bound. RCPPML_B200_GRAPH=0 disables. Not used while per-section profiling records events.
     cudaGraphExec_t iter_graph = nullptr;
     bool graphs_enabled = true;
+    bool capturing = false;
     std::array<int, RCPPML_B200_NUM_SECTIONS> graph_launches{};
     void capture_iteration_graph();
     void drop_iteration_graph();
@@ -170,7 +178,7 @@ public:
 
     // Grow-only staging buffers (fp64 wire copies, transpose temporaries): a cached engine (abi_reference.cu)
     // makes its second and later calls without a single cudaMalloc / cudaFree.
-    std::array<DeviceBuffer<unsigned char>, 8> scratch_;
+    std::array<DeviceBuffer<unsigned char>, 13> scratch_;
     template <class T> T* scratch(int slot, size_t count) {
         scratch_[slot].ensure(count * sizeof(T));
         return reinterpret_cast<T*>(scratch_[slot].ptr);
@@ -191,12 +199,12 @@ public:
     int rank = 0, world = 1;
     bool peers_ready = false;
     bool peers_local = false;         // peers live in this process (comm_attach_local): nothing to IPC-close
+    bool peer_access_enabled = false; // in-process peers: cudaDeviceEnablePeerAccess done for this engine's device
     float* peer_W[8] = {};            // every rank's W_T / H / exchange buffer (own pointers at [rank])
     float* peer_H[8] = {};
     double* peer_x[8] = {};
-    DeviceBuffer<double> xbuf;        // data[2][world][ne_max] + flags[2][8]
+    DeviceBuffer<double> xbuf;        // data[2][world][ne_max] + flags[2][8] + sequence counter (kXchgTailWords)
     int xchg_ne_max = 0;
-    unsigned long long xchg_seq = 0;
 
 private:
     cudaEvent_t ev_loop_begin = nullptr, ev_loop_end = nullptr;

@@ -307,19 +307,33 @@ struct XchgParams {
     double* peer[8];                 // exchange buffer base of every rank (peer[rank] = own)
     int rank, world;
     int ne_max;
-    unsigned long long seq;          // strictly increasing per call, same on every rank
-    int phase;                       // seq & 1
 };
+// The sequence number of an exchange lives in the rank's own exchange buffer (u64 slot 16 behind the flags) and is
+// advanced by the kernel itself: every rank runs the same sequence of exchanges, so the counters stay in lock-step,
+// and a launch carries no per-call argument — the sharded iteration can be captured once as a CUDA graph and replayed.
+constexpr int kXchgTailWords = 24;   // flags[2][8] + sequence counter (+ padding), in 8-byte words
 
 __device__ __forceinline__ unsigned long long* xchg_flags(double* base, int world, int ne_max, int phase) {
     return reinterpret_cast<unsigned long long*>(base + static_cast<size_t>(2) * world * ne_max) + phase * 8;
+}
+__device__ __forceinline__ unsigned long long* xchg_seq_counter(double* base, int world, int ne_max) {
+    return reinterpret_cast<unsigned long long*>(base + static_cast<size_t>(2) * world * ne_max) + 16;
 }
 
 static __global__ void __launch_bounds__(1024) xchg_allreduce_kernel(const double* __restrict__ local, int nelem,
                                                                      double* __restrict__ out, const XchgParams x,
                                                                      DevState* __restrict__ st) {
     if (st->stop) return;            // identical on every rank (convergence is decided from all-reduced data)
-    const size_t slot = (static_cast<size_t>(x.phase) * x.world + x.rank) * x.ne_max;
+    __shared__ unsigned long long s_seq;
+    if (threadIdx.x == 0) {
+        unsigned long long* ctr = xchg_seq_counter(x.peer[x.rank], x.world, x.ne_max);
+        s_seq = *ctr + 1ULL;
+        *ctr = s_seq;
+    }
+    __syncthreads();
+    const unsigned long long seq = s_seq;
+    const int phase = static_cast<int>(seq & 1ULL);
+    const size_t slot = (static_cast<size_t>(phase) * x.world + x.rank) * x.ne_max;
     for (int r = 0; r < x.world; ++r) {
         double* dst = x.peer[r] + slot;
         for (int e = threadIdx.x; e < nelem; e += blockDim.x) dst[e] = local[e];
@@ -327,21 +341,21 @@ static __global__ void __launch_bounds__(1024) xchg_allreduce_kernel(const doubl
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x < x.world) {
-        unsigned long long* f = xchg_flags(x.peer[threadIdx.x], x.world, x.ne_max, x.phase) + x.rank;
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(x.seq) : "memory");
-        const unsigned long long* mine = xchg_flags(x.peer[x.rank], x.world, x.ne_max, x.phase) + threadIdx.x;
+        unsigned long long* f = xchg_flags(x.peer[threadIdx.x], x.world, x.ne_max, phase) + x.rank;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(seq) : "memory");
+        const unsigned long long* mine = xchg_flags(x.peer[x.rank], x.world, x.ne_max, phase) + threadIdx.x;
         unsigned long long v = 0;
         const long long t0 = clock64();
         for (;;) {
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
-            if (v >= x.seq) break;
+            if (v >= seq) break;
             // ~2 s: never hang the GPU. `stop` turns every later kernel of this fit into a no-op, so a dead peer costs
             // one time-out, not one per exchange; the host sees comm_error at its next poll (Engine::iterate).
             if (clock64() - t0 > 4000000000LL) { st->comm_error = 1; st->stop = 1; break; }
         }
     }
     __syncthreads();
-    const double* base = x.peer[x.rank] + static_cast<size_t>(x.phase) * x.world * x.ne_max;
+    const double* base = x.peer[x.rank] + static_cast<size_t>(phase) * x.world * x.ne_max;
     for (int e = threadIdx.x; e < nelem; e += blockDim.x) {
         double s = 0.0;
         for (int r = 0; r < x.world; ++r) s += __ldcg(base + static_cast<size_t>(r) * x.ne_max + e);
@@ -377,6 +391,7 @@ static __global__ void __launch_bounds__(kPrepThreads) prepare_solver_kernel(con
                                                             float* __restrict__ M2, float* __restrict__ dblk,
                                                             float* __restrict__ rcp, DevState* __restrict__ st) {
     extern __shared__ float sL[];          // KP*KP col-major working copy, then KP*KP running dot products T
+    __shared__ float sDiag[kMaxKP];        // L(j,j) (the diagonal of the working copy keeps G(j,j): it is read by every row)
     if (st->stop) return;
     const int tid = threadIdx.x;
     float* sT = sL + KP * KP;
@@ -387,35 +402,46 @@ static __global__ void __launch_bounds__(kPrepThreads) prepare_solver_kernel(con
         sL[e] = v;
         if (solver != 0) sT[e] = 0.f;
     }
+    if (tid < KP) sDiag[tid] = 0.f;
     __syncthreads();
     if (solver != 0) {
         // LLT in the oracle's operation order: L(i,j) = (G(i,j) - t_ij) / L(j,j) with the dot product
         // t_ij = sum_{p<j} L(i,p)·L(j,p) accumulated sequentially in p (separately rounded mul and add), and
         // L(j,j) = sqrt(G(j,j) - t_jj). The dots are kept as RUNNING sums T(i,j) that every finished column p
         // updates for all pairs (i >= j > p) at once — the same additions in the same order as the left-looking
-        // loop, but k steps of O(1) depth instead of k dependent dots of length j (≈65 us -> ≈6 us at k = 64).
+        // loop, but k steps of O(1) depth instead of k dependent dots of length j.
+        // Synchronisation per column (was three CTA-wide barriers): thread (ti, tj0) always updates T(ti, c) for
+        // c = j+1+tj0 (+ multiples of blockDim/KP), so T(:, j+1) — all the NEXT column needs — is written by the
+        // threads with tj0 == 0, the same `tid < KP` threads that turn it into L(:, j+1). Those warps meet at a
+        // narrow named barrier (A), everyone meets once at the CTA barrier (B) that publishes L(:, j). The pivot is
+        // recomputed by every row from G(j,j) and T(j,j), so the in-place overwrite needs no barrier of its own.
         const int ti = tid % KP, tj0 = tid / KP, tjs = blockDim.x / KP;
+        const int front = (KP < 32) ? 32 : KP;              // threads of the warps that own a row (whole warps)
         for (int j = 0; j < k; ++j) {
-            // column j from G and T (thread i owns row i; every thread recomputes the pivot: broadcast reads)
-            const float x = __fsub_rn(sL[j * KP + j], sT[j * KP + j]);
-            float ljj = 0.f;
-            if (!(x > 0.f)) {
-                if (tid == 0 && st->chol_fail == 0) st->chol_fail = j + 1;
-            } else {
-                ljj = __fsqrt_rn(x);
+            if (tid < front) {
+                if (j > 0) {                                // (A) T(:, j) complete: written by these warps in step j-1
+                    if (front == 32) __syncwarp();
+                    else asm volatile("bar.sync 1, %0;" ::"r"(front) : "memory");
+                }
+                const float x = __fsub_rn(sL[j * KP + j], sT[j * KP + j]);
+                float ljj = 0.f;
+                if (!(x > 0.f)) {
+                    if (tid == 0 && st->chol_fail == 0) st->chol_fail = j + 1;
+                } else {
+                    ljj = __fsqrt_rn(x);
+                }
+                if (tid > j && tid < k) sL[j * KP + tid] = __fdiv_rn(__fsub_rn(sL[j * KP + tid], sT[j * KP + tid]), ljj);
+                if (tid == j) sDiag[j] = ljj;
             }
-            float lij = 0.f;
-            if (tid > j && tid < k) lij = __fdiv_rn(__fsub_rn(sL[j * KP + tid], sT[j * KP + tid]), ljj);
-            __syncthreads();                   // all reads of column j (as G) done
-            if (tid > j && tid < k) sL[j * KP + tid] = lij;
-            if (tid == j) sL[j * KP + j] = ljj;
-            __syncthreads();
+            __syncthreads();                                // (B) L(:, j) published
             // T(i,c) += L(i,j)·L(c,j) for j < c <= i < k
             const float li = sL[j * KP + ti];
             for (int c = j + 1 + tj0; c < k; c += tjs)
                 if (ti >= c && ti < k) sT[c * KP + ti] = __fadd_rn(sT[c * KP + ti], __fmul_rn(li, sL[j * KP + c]));
-            __syncthreads();                   // T(:,j+1) complete before the next column reads it
         }
+        __syncthreads();
+        for (int j = tid; j < k; j += blockDim.x) sL[j * KP + j] = sDiag[j];
+        __syncthreads();
     }
     for (int e = tid; e < KP * KP; e += blockDim.x) {
         const int i = e % KP, j = e / KP;                  // e = j*KP + i  -> element (row i, col j)

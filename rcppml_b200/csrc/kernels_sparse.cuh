@@ -137,4 +137,88 @@ static __global__ void panel_bounds_kernel(const int* __restrict__ colptr, const
     out[t] = lo;
 }
 
+// --------------------------------------------------------------------------------------------
+// In-process multi-GPU ingest (abi_reference.cu, Engine::assemble_row_block): every device uploads only its own
+// column block A[:, J_g]; the row block A[I_g, :] each device needs for the W half-step is assembled from the
+// column blocks of ALL devices over NVLink peer memory. Rows are ascending inside a CSC column, so the entries of
+// column j that fall in rows [r0, r1) are ONE contiguous run, found by two binary searches.
+// --------------------------------------------------------------------------------------------
+// Per column j of a (peer's) column block: start[j] = first entry with row >= r0, cnt[j] = entries with row in [r0, r1).
+static __global__ void rowblock_count_kernel(const int* __restrict__ sp, const int* __restrict__ si, int ncols, int r0,
+                                             int r1, int* __restrict__ start, int* __restrict__ cnt) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ncols) return;
+    const int p0 = sp[j], p1 = sp[j + 1];
+    int lo = p0, hi = p1;
+    while (lo < hi) {                                  // first position with row >= r0
+        const int mid = lo + ((hi - lo) >> 1);
+        if (si[mid] < r0) lo = mid + 1; else hi = mid;
+    }
+    const int first = lo;
+    hi = p1;
+    while (lo < hi) {                                  // first position with row >= r1
+        const int mid = lo + ((hi - lo) >> 1);
+        if (si[mid] < r1) lo = mid + 1; else hi = mid;
+    }
+    start[j] = first;
+    cnt[j] = lo - first;
+}
+
+// One warp per column: copies the run found above into the row block's CSC (row ids relative to r0).
+static __global__ void __launch_bounds__(256) rowblock_copy_kernel(const int* __restrict__ si, const float* __restrict__ sx,
+                                                                   int ncols, const int* __restrict__ start,
+                                                                   const int* __restrict__ dst_ptr, int r0,
+                                                                   int* __restrict__ di, float* __restrict__ dx) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < ncols; j += warps) {
+        const int d0 = dst_ptr[j], cnt = dst_ptr[j + 1] - d0, s0 = start[j];
+        for (int e = lane; e < cnt; e += 32) {
+            di[d0 + e] = si[s0 + e] - r0;
+            dx[d0 + e] = sx[s0 + e];
+        }
+    }
+}
+
+// hist[row] += 1 per stored entry (row work of the W half-step, for the balanced row partition)
+static __global__ void row_histogram_kernel(const int* __restrict__ si, long long nnz, int* __restrict__ hist) {
+    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < nnz;
+         e += static_cast<long long>(gridDim.x) * blockDim.x)
+        atomicAdd(hist + si[e], 1);
+}
+
+// work[i] = per_item + sum over devices of hist_g[i]   (hist pointers are peer memory)
+struct HistPtrs { const int* p[8]; };
+static __global__ void sum_histograms_kernel(HistPtrs h, int ndev, int m, int per_item, long long* __restrict__ work) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    long long s = per_item;
+    for (int g = 0; g < ndev; ++g) s += h.p[g][i];
+    work[i] = s;
+}
+
+// cuts[r] (r = 1..world-1) = smallest j in [0, m] with prefix(j) >= total*r/world, prefix(j) = work of items < j
+// (inc is the INCLUSIVE scan: prefix(j) = inc[j-1]); the rule of rcppml_b200/shard.py balanced_cuts. cuts[0] = 0,
+// cuts[world] = m. One thread per cut; monotone by construction.
+static __global__ void balanced_cuts_kernel(const long long* __restrict__ inc, int m, int world, int* __restrict__ cuts) {
+    const int r = threadIdx.x;
+    if (r > world) return;
+    if (r == 0) { cuts[0] = 0; return; }
+    if (r == world) { cuts[world] = m; return; }
+    const double total = static_cast<double>(inc[m - 1]);
+    const double target = total * static_cast<double>(r) / static_cast<double>(world);
+    int lo = 0, hi = m;                                // smallest j with prefix(j) >= target
+    while (lo < hi) {
+        const int mid = lo + ((hi - lo) >> 1);
+        const double pm = (mid == 0) ? 0.0 : static_cast<double>(inc[mid - 1]);
+        if (pm < target) lo = mid + 1; else hi = mid;
+    }
+    cuts[r] = lo;
+}
+
+static __global__ void rebase_int_kernel(int* __restrict__ x, int count, int base) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) x[i] -= base;
+}
+
 }  // namespace b200

@@ -650,7 +650,8 @@ for (m, n, k, solver, kw) in [(900, 500, 16, 0, {}), (1201, 777, 64, 1, dict(L1=
         many = rb.bridge_nmf_sparse(A.indptr, A.indices, A.data, m, n, k, W0, H0, max_iter=7, tol=0.0, solver_mode=solver, **kw)
         assert one.status == 0 and many.status == 0, (G, one.status, many.status)
         assert np.array_equal(one.W_T, many.W_T) and np.array_equal(one.H, many.H) and np.array_equal(one.d, many.d), (G, m, n, k)
-        assert one.iterations == many.iterations and one.train_loss == many.train_loss
+        # (tr(AtA) is summed per device, then over devices: the loss may differ in its last bit, the factors may not)
+        assert one.iterations == many.iterations and abs(one.train_loss - many.train_loss) <= 1e-6 * abs(one.train_loss)
 print("INPROCESS_MULTIGPU_OK")
 '''
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600,
