@@ -340,6 +340,8 @@ int rcppml_b200_comm_ipc_import(rcppml_b200_engine* e, const char* all_handles);
  * [0] matrix upload (+fp64->fp32) [1] device transpose + tr(AtA) [2] factor upload [3] ALS loop [4] factor download. */
 int rcppml_b200_release_cache(void);
 int rcppml_b200_last_call_phases(double* ms5);
+/* Wall clock (ms) of the last rcppml_gpu_nmf_unified_float call, entry to return, measured inside the library. */
+double rcppml_b200_last_call_wall_ms(void);
 
 #ifdef __cplusplus
 }

@@ -26,6 +26,7 @@ void warn(const char* what) { std::fprintf(stderr, "[RcppML_gpu/b200] %s\n", wha
 std::mutex g_mu;
 std::unique_ptr<b200::Engine> g_engine;
 double g_phases[5] = {0, 0, 0, 0, 0};
+double g_call_wall_ms = 0.0;                     // wall clock of the last part-1 call, entry to return, measured in here
 
 struct EngineLease {
     std::unique_lock<std::mutex> lock;
@@ -158,7 +159,7 @@ bool fit_in_process_multi_gpu(int G, const int* devices, int m, int n, int64_t n
     std::vector<rcppml_b200_result> rr(G);
     std::vector<std::string> err(G);
     PhaseBarrier bar(G);
-    double marks[6] = {0, 0, 0, 0, 0, 0};                     // rank 0's wall clock at the phase boundaries (ms)
+    double marks[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};        // rank 0's wall clock at the phase boundaries (ms)
     auto since = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count(); };
 
     auto body = [&](int g) {
@@ -191,6 +192,7 @@ bool fit_in_process_multi_gpu(int G, const int* devices, int m, int n, int64_t n
         E.pull_factor_blocks_from_peers();
         if (g == 0) marks[2] = since();
         E.begin_fit(cfg);                                                    // (its first exchange orders the pulls against the peers' first stores)
+        if (g == 0) marks[5] = since();
         E.iterate(cfg.max_iter);
         E.get_result(&rr[g]);
         if (g == 0) marks[3] = since();
@@ -237,6 +239,7 @@ bool fit_in_process_multi_gpu(int G, const int* devices, int m, int n, int64_t n
         g_phases[3] = rr[0].loop_ms;
         g_phases[4] = marks[4] - marks[3];
     }
+    marks[6] = since();
     for (int g = 0; g < G; ++g) {                              // every device idle before anything is reused or freed
         if (!eng[g]) continue;
         cudaSetDevice(devices[g]);
@@ -247,6 +250,12 @@ bool fit_in_process_multi_gpu(int G, const int* devices, int m, int n, int64_t n
         g_multi_devices.clear();
     }
     cudaSetDevice(devices[0]);
+    if (std::getenv("RCPPML_B200_TRACE"))
+        std::fprintf(stderr, "[RcppML_gpu/b200] multi-GPU call (G=%d), rank-0 wall clock ms: col blocks up %.2f | row blocks %.2f | "
+                             "factor blocks + replicas %.2f | begin_fit %.2f | iterate+result %.2f (loop events %.2f) | blocks down %.2f | "
+                             "threads joined %.2f | end %.2f\n",
+                     G, marks[0], marks[1] - marks[0], marks[2] - marks[1], marks[5] - marks[2], marks[3] - marks[5], rr[0].loop_ms,
+                     marks[4] - marks[3], marks[6], since());
     return ok;
 }
 
@@ -569,6 +578,11 @@ static void nmf_unified_impl(
 {
     if (!out_status) return;
     *out_status = -1;
+    const auto t_entry = std::chrono::steady_clock::now();
+    struct WallClock {
+        std::chrono::steady_clock::time_point t0;
+        ~WallClock() { g_call_wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+    } wall_clock{t_entry};
     try {
         // Features outside the sparse-MSE ALS path are refused, not emulated: the caller
         // (nmf/fit.hpp:125-133) owns the CPU fallback.
@@ -665,5 +679,6 @@ int rcppml_b200_last_call_phases(double* ms5) {
     for (int i = 0; i < 5; ++i) ms5[i] = g_phases[i];
     return 0;
 }
+double rcppml_b200_last_call_wall_ms(void) { return g_call_wall_ms; }
 
 }  // extern "C"

@@ -732,10 +732,6 @@ void Engine::alloc_factors(int k_) {
     if (const char* env = std::getenv("RCPPML_B200_TILED_MIN_BATCHES")) tiled_min_batches = std::atof(env);
     tiled_sl_override = 0;
     if (const char* env = std::getenv("RCPPML_B200_TILED_SL")) tiled_sl_override = std::atoi(env);
-    // measured per rank shape on one B200 (profiles/r02a_rank_shapes.jsonl, C4 W half-step, ms): N = 2: 1.227 -> 1.138,
-    // N = 4: 0.657 -> 0.603, N = 8: 0.378 -> 0.341 (one-geometry kernel: 1.339 / 0.685 / 0.357)
-    tiled_sl4_below = 12.0;
-    if (const char* env = std::getenv("RCPPML_B200_TILED_SL4_BELOW")) tiled_sl4_below = std::atof(env);
     narrow_min_cols = 8.0 * num_sms * 24;
     if (std::getenv("RCPPML_B200_CD_GEOM")) narrow_min_cols = 0.0;           // an explicit geometry applies to every size
     if (const char* env = std::getenv("RCPPML_B200_NARROW_MIN_COLS")) narrow_min_cols = std::atof(env);
@@ -1161,18 +1157,18 @@ bool Engine::use_tiled(int solver, long long cnt, long long ncols) const {
     return KP == 128 || KP == 32;
 }
 
-int Engine::tiled_gather_geom(long long cnt, long long ncols) const {
+int Engine::tiled_gather_geom(long long cnt, long long ncols, int solver) const {
     int g = geometry_for(cnt, ncols);                           // LANES + 100*(NV-1), NV in {1, 2, 4}
     if (g >= 300) g = 100 + KP / 8;                             // NV = 4 is not instantiated for the tiled kernel
-    // k = 64: batches of 8 columns (4 lanes x 4 words per column) instead of 16 when this rank holds few batches per
-    // resident warp (sharded runs: 125 K rows on 8 GPUs are 2.2 sixteen-column batches per warp — one warp in five
-    // works a third batch while the others idle). RCPPML_B200_TILED_SL = 2 / 4 forces a geometry.
+    // k = 64, Cholesky: batches of 8 columns (4 lanes x 4 words per column) instead of 16. Measured on the C4 W half-step
+    // (profiles/r02a_rank_shapes.jsonl, r02b_rank_shapes_n1.jsonl; ms, 16- vs 8-column batches): one GPU 2.355 -> 2.215;
+    // per-rank shapes of N = 2 / 4 / 8: 1.227 -> 1.138, 0.657 -> 0.603, 0.378 -> 0.341 (a rank with 125 K rows holds only
+    // 2.2 sixteen-column batches per resident warp: one warp in five works a third batch while the others idle).
+    // Coordinate descent keeps the narrowest groups (its cost is the group-uniform part of every coordinate step).
+    // RCPPML_B200_TILED_SL = 2 / 4 forces a geometry.
     if (KP == 64) {
         int sl = tiled_sl_override;
-        if (sl == 0) {
-            const double batches16 = static_cast<double>(ncols) / (16.0 * num_sms * 24);
-            sl = (batches16 < tiled_sl4_below) ? 4 : 2;
-        }
+        if (sl == 0) sl = (solver == SOLVER_CHOL) ? 4 : 2;
         if (sl == 4) g += 4000;
     }
     return g;
@@ -1196,7 +1192,7 @@ void Engine::solve(int which, bool warm, int sec) {
     const bool narrow_cd = !tiled && solver == SOLVER_CD && use_narrow_cd(p.ncols);
     const int kind = tiled ? 2 : (narrow_cd ? 1 : 0);
     if (tiled) {
-        geom = tiled_gather_geom(cnt, p.ncols);
+        geom = tiled_gather_geom(cnt, p.ncols, solver);
     } else if (narrow_cd) {
         const double avg = p.ncols > 0 ? static_cast<double>(cnt) / static_cast<double>(p.ncols) : 0.0;
         geom = avg >= 400.0 ? cd_geom_long : cd_geom;
@@ -1307,18 +1303,44 @@ void Engine::enqueue_iteration() {
 void Engine::set_mask(int64_t mnnz, const int* mask_ptr, const int* mask_idx) {
     use_device();
     B200_REQUIRE(matrix_ready, "set_mask: set the matrix first");
-    B200_REQUIRE(world == 1, "set_mask: the masked path is single-GPU");
     has_mask = false;
     if (mnnz <= 0) return;
-    Mp.ensure(static_cast<size_t>(n) + 1);
-    Mi.ensure(mnnz + 4);
-    B200_CUDA_CHECK(cudaMemcpyAsync(Mp.ptr, mask_ptr, (static_cast<size_t>(n) + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
-    B200_CUDA_CHECK(cudaMemcpyAsync(Mi.ptr, mask_idx, mnnz * sizeof(int), cudaMemcpyHostToDevice, stream));
+    // Every rank receives the WHOLE pattern (index arrays only; masks are small next to A), transposes it on the
+    // device and — sharded — keeps two contiguous slices: columns J of the pattern (H half-step) and columns I of its
+    // transpose (= rows I, W half-step), pointers rebased; exactly the two operands it holds of A itself.
+    DeviceBuffer<int> fp, fi, tp, ti;
     DeviceBuffer<float> ones, onesT;
+    DeviceBuffer<int>& Fp = (world == 1) ? Mp : fp;
+    DeviceBuffer<int>& Fi = (world == 1) ? Mi : fi;
+    DeviceBuffer<int>& Tp = (world == 1) ? MTp : tp;
+    DeviceBuffer<int>& Ti = (world == 1) ? MTi : ti;
+    Fp.ensure(static_cast<size_t>(n) + 1);
+    Fi.ensure(mnnz + 4);
+    B200_CUDA_CHECK(cudaMemcpyAsync(Fp.ptr, mask_ptr, (static_cast<size_t>(n) + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
+    B200_CUDA_CHECK(cudaMemcpyAsync(Fi.ptr, mask_idx, mnnz * sizeof(int), cudaMemcpyHostToDevice, stream));
     ones.ensure(mnnz + 4);
     B200_CUDA_CHECK(cudaMemsetAsync(ones.ptr, 0, (mnnz + 4) * sizeof(float), stream));
     B200_CUDA_CHECK(cudaStreamSynchronize(stream));
-    transpose_csc(Mp.ptr, Mi.ptr, ones.ptr, n, m, mnnz, MTp, MTi, onesT, 0);
+    transpose_csc(Fp.ptr, Fi.ptr, ones.ptr, n, m, mnnz, Tp, Ti, onesT, 0);
+    if (world > 1) {
+        auto slice = [&](const DeviceBuffer<int>& sp, const DeviceBuffer<int>& si, int first, int count, DeviceBuffer<int>& dp,
+                         DeviceBuffer<int>& di) {
+            int ends[2] = {0, 0};
+            B200_CUDA_CHECK(cudaMemcpyAsync(&ends[0], sp.ptr + first, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            B200_CUDA_CHECK(cudaMemcpyAsync(&ends[1], sp.ptr + first + count, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            B200_CUDA_CHECK(cudaStreamSynchronize(stream));
+            const int64_t cnt = static_cast<int64_t>(ends[1]) - ends[0];
+            dp.ensure(static_cast<size_t>(std::max(count, 1)) + 1);
+            di.ensure(std::max<int64_t>(cnt, 1) + 4);
+            B200_CUDA_CHECK(cudaMemcpyAsync(dp.ptr, sp.ptr + first, (static_cast<size_t>(count) + 1) * sizeof(int), cudaMemcpyDeviceToDevice, stream));
+            rebase_int_kernel<<<(count + 1 + 255) / 256, 256, 0, stream>>>(dp.ptr, count + 1, ends[0]);
+            if (cnt > 0) B200_CUDA_CHECK(cudaMemcpyAsync(di.ptr, si.ptr + ends[0], cnt * sizeof(int), cudaMemcpyDeviceToDevice, stream));
+            B200_CUDA_CHECK(cudaGetLastError());
+        };
+        slice(fp, fi, col_begin, n_loc, Mp, Mi);
+        slice(tp, ti, row_begin, m_loc, MTp, MTi);
+        B200_CUDA_CHECK(cudaStreamSynchronize(stream));
+    }
     mask_nnz = mnnz;
     has_mask = true;
 }
@@ -1334,7 +1356,12 @@ void Engine::masked_solve(int which, bool warm, const float* G, int sec) {
     p.F = h ? W_T.ptr : H.ptr;
     p.X = h ? H.ptr : W_T.ptr;
     p.G = G;
-    p.ncols = h ? n : m;
+    p.ncols = h ? n_loc : m_loc;
+    p.col_offset = h ? col_begin : row_begin;
+    p.npeers = 0;
+    if (peers_ready)
+        for (int r = 0; r < world; ++r)
+            if (r != rank) p.peerX[p.npeers++] = h ? peer_H[r] : peer_W[r];
     p.k = k;
     p.L1 = h ? cfg.L1_H : cfg.L1_W;
     p.L2 = h ? cfg.L2_H : cfg.L2_W;
@@ -1361,27 +1388,42 @@ void Engine::masked_solve(int which, bool warm, const float* G, int sec) {
     sec_end(sec);
 }
 
-// fit_cpu.hpp with use_mask: :560-564 (H), :799-810 (W), :1686-1691 (loss).
+// fit_cpu.hpp with use_mask: :560-564 (H), :799-810 (W), :1686-1691 (loss). Sharded like enqueue_iteration: every rank
+// solves its column block of H and its row block of W_T with its slices of A and of the mask pattern; Grams, row
+// sums and the explicit loss are all-reduced in fp64.
 void Engine::enqueue_iteration_masked() {
     const bool warm = iters_enqueued > 0;
     const bool normalize = cfg.norm_type != 2;
-    if (iters_enqueued == 0) gram(W_T.ptr, m, false, G_w.ptr, RCPPML_B200_SEC_GRAM_H);   // :562 rebuilt unmodified
+    const bool sharded = world > 1;
+    const bool p2p = sharded && peers_ready;
+    float* Hblk = H.ptr + static_cast<size_t>(col_begin) * KP;
+    float* Wblk = W_T.ptr + static_cast<size_t>(row_begin) * KP;
+    if (iters_enqueued == 0) gram(Wblk, m_loc, false, G_w.ptr, RCPPML_B200_SEC_GRAM_H, sharded);   // :562 rebuilt unmodified
+    join_side_stream();
     masked_solve(0, warm, G_w.ptr, RCPPML_B200_SEC_SOLVE_H);
-    scale_finalize(RCPPML_B200_SEC_SCALE_H);
-    gram(H.ptr, n, normalize, G_h.ptr, RCPPML_B200_SEC_GRAM_W);                           // :644 + :801
+    scale_finalize(RCPPML_B200_SEC_SCALE_H, sharded);
+    if (p2p) normalize_peer_blocks(H.ptr, n, col_begin, col_begin + n_loc, normalize);
+    gram(Hblk, n_loc, normalize, G_h.ptr, RCPPML_B200_SEC_GRAM_W, sharded);                       // :644 + :801
+    if (sharded && !p2p) allgather_rows(H.ptr, col_cuts, n_pad, RCPPML_B200_SEC_COMM);
+    join_side_stream();
     masked_solve(1, warm, G_h.ptr, RCPPML_B200_SEC_SOLVE_W);
-    scale_finalize(RCPPML_B200_SEC_SCALE_W);
+    scale_finalize(RCPPML_B200_SEC_SCALE_W, sharded);
+    if (p2p) normalize_peer_blocks(W_T.ptr, m, row_begin, row_begin + m_loc, normalize);
     sec_begin(RCPPML_B200_SEC_LOSS);
     const bool was = profiling; profiling = false;
-    gram(W_T.ptr, m, normalize, G_w.ptr, RCPPML_B200_SEC_LOSS);                           // normalise + next gram_H
+    gram(Wblk, m_loc, normalize, G_w.ptr, RCPPML_B200_SEC_LOSS, sharded);                         // normalise + next gram_H
     profiling = was;
+    if (sharded && !p2p) allgather_rows(W_T.ptr, row_cuts, m_pad, RCPPML_B200_SEC_COMM);
+    join_side_stream();                                                     // the loss reads every row of W_T
     const int lgrid = num_sms * 4;
-    if (loss_partials.count < static_cast<size_t>(lgrid)) loss_partials.ensure(lgrid);
-    masked_loss_kernel<<<lgrid, 256, 0, stream>>>(Ap.ptr, Ai.ptr, Ax.ptr, Mp.ptr, Mi.ptr, n, KP, k, W_T.ptr, H.ptr, d.ptr,
-                                                  loss_partials.ptr, &state.ptr->stop);
-    masked_loss_finalize_kernel<<<1, 32, 0, stream>>>(loss_partials.ptr, lgrid, cfg.tol, cfg.patience, loss_hist.ptr,
+    masked_loss_kernel<<<lgrid, 256, 0, stream>>>(Ap.ptr, Ai.ptr, Ax.ptr, Mp.ptr, Mi.ptr, n_loc, col_begin, KP, k, W_T.ptr, H.ptr,
+                                                  d.ptr, loss_partials.ptr, &state.ptr->stop);
+    // fixed-order sum of the per-CTA partials, then (sharded) over the ranks' column blocks
+    sum_partials_kernel<<<1, dim3(32, 8), 0, stream>>>(loss_partials.ptr, lgrid, 1, red_small.ptr, &state.ptr->stop);
+    if (sharded) allreduce_f64(red_small.ptr, 1);
+    masked_loss_finalize_kernel<<<1, 32, 0, stream>>>(red_small.ptr, 1, cfg.tol, cfg.patience, loss_hist.ptr,
                                                       static_cast<int>(loss_hist.count), state.ptr);
-    launches[RCPPML_B200_SEC_LOSS] += 2;
+    launches[RCPPML_B200_SEC_LOSS] += 3;
     sec_end(RCPPML_B200_SEC_LOSS);
     ++iters_enqueued;
 }
@@ -1396,8 +1438,13 @@ void Engine::cv_solve(int which, int sec) {
     p.F = h ? W_T.ptr : H.ptr;
     p.X = h ? H.ptr : W_T.ptr;
     p.G = M1.ptr;
-    p.ncols = h ? n : m;
+    p.ncols = h ? n_loc : m_loc;
     p.nrows = h ? m : n;
+    p.col_offset = h ? col_begin : row_begin;
+    p.npeers = 0;
+    if (peers_ready)
+        for (int r = 0; r < world; ++r)
+            if (r != rank) p.peerX[p.npeers++] = h ? peer_H[r] : peer_W[r];
     p.k = k;
     p.transposed = h ? 0 : 1;
     p.mask_zeros = cv.mask_zeros;
@@ -1427,37 +1474,49 @@ void Engine::cv_solve(int which, int sec) {
 
 void Engine::enqueue_iteration_cv() {
     const bool normalize = cfg.norm_type != 2;
+    const bool sharded = world > 1;
+    const bool p2p = sharded && peers_ready;
+    float* Hblk = H.ptr + static_cast<size_t>(col_begin) * KP;
+    float* Wblk = W_T.ptr + static_cast<size_t>(row_begin) * KP;
     const int ge = (KP * KP + 255) / 256;
-    if (iters_enqueued == 0) gram(W_T.ptr, m, false, G_w.ptr, RCPPML_B200_SEC_GRAM_H);      // fit_cv.hpp:413
+    if (iters_enqueued == 0) gram(Wblk, m_loc, false, G_w.ptr, RCPPML_B200_SEC_GRAM_H, sharded);   // fit_cv.hpp:413
     cv_prepare_gram_kernel<<<ge, 256, 0, stream>>>(G_w.ptr, KP, k, cfg.L2_H, M1.ptr, &state.ptr->stop);   // :414-417
+    join_side_stream();
     cv_solve(0, RCPPML_B200_SEC_SOLVE_H);                                                    // :431-476, :528
-    scale_finalize(RCPPML_B200_SEC_SCALE_H);                                                 // :536-548
-    gram(H.ptr, n, normalize, G_h.ptr, RCPPML_B200_SEC_GRAM_W);                              // :570 (= G_H_saved)
+    scale_finalize(RCPPML_B200_SEC_SCALE_H, sharded);                                        // :536-548
+    if (p2p) normalize_peer_blocks(H.ptr, n, col_begin, col_begin + n_loc, normalize);
+    gram(Hblk, n_loc, normalize, G_h.ptr, RCPPML_B200_SEC_GRAM_W, sharded);                  // :570 (= G_H_saved)
+    if (sharded && !p2p) allgather_rows(H.ptr, col_cuts, n_pad, RCPPML_B200_SEC_COMM);
     cv_prepare_gram_kernel<<<ge, 256, 0, stream>>>(G_h.ptr, KP, k, cfg.L2_W, M1.ptr, &state.ptr->stop);   // :578-581
+    join_side_stream();
     cv_solve(1, RCPPML_B200_SEC_SOLVE_W);                                                    // :598-735, :843
-    scale_finalize(RCPPML_B200_SEC_SCALE_W);                                                 // :849-858
+    scale_finalize(RCPPML_B200_SEC_SCALE_W, sharded);                                        // :849-858 (+ cross term)
+    if (p2p) normalize_peer_blocks(W_T.ptr, m, row_begin, row_begin + m_loc, normalize);
     sec_begin(RCPPML_B200_SEC_LOSS);
     const bool was = profiling; profiling = false;
-    gram(W_T.ptr, m, normalize, G_w.ptr, RCPPML_B200_SEC_LOSS);                              // normalise + :1518
+    gram(Wblk, m_loc, normalize, G_w.ptr, RCPPML_B200_SEC_LOSS, sharded);                    // normalise + :1518
     profiling = was;
+    if (sharded && !p2p) allgather_rows(W_T.ptr, row_cuts, m_pad, RCPPML_B200_SEC_COMM);
+    join_side_stream();                                                     // the test loss reads every row of W_T
     const int lgrid = num_sms * 4;
-    if (loss_partials.count < static_cast<size_t>(lgrid) * 2) loss_partials.ensure(static_cast<size_t>(lgrid) * 2);
-    cv_test_loss_kernel<<<lgrid, 256, 0, stream>>>(Ap.ptr, Ai.ptr, Ax.ptr, n, m, KP, k, cv.mask_zeros, cv_seed_state,
+    cv_test_loss_kernel<<<lgrid, 256, 0, stream>>>(Ap.ptr, Ai.ptr, Ax.ptr, n_loc, col_begin, m, KP, k, cv.mask_zeros, cv_seed_state,
                                                    cv_threshold, cv_inv_prob != 0, W_T.ptr, H.ptr, d.ptr,
                                                    loss_partials.ptr, &state.ptr->stop);
+    // {sum, count} of the held-out entries: fixed-order over the CTAs, then (sharded) over the ranks' column blocks
+    sum_partials_kernel<<<1, dim3(32, 8), 0, stream>>>(loss_partials.ptr, lgrid, 2, red_gram.ptr, &state.ptr->stop);
+    if (sharded) allreduce_f64(red_gram.ptr, 2);
     const long long total_entries = cv.mask_zeros ? nnz_global : static_cast<long long>(m) * n;
-    cv_loss_finalize_kernel<<<1, 256, 0, stream>>>(G_w.ptr, G_h.ptr, d.ptr, KP, k, red_small.ptr + KP, loss_partials.ptr,
-                                                   lgrid, trAtA, total_entries, cfg.tol, cv.cv_patience, loss_hist.ptr,
+    cv_loss_finalize_kernel<<<1, 256, 0, stream>>>(G_w.ptr, G_h.ptr, d.ptr, KP, k, red_small.ptr + KP, red_gram.ptr,
+                                                   1, trAtA, total_entries, cfg.tol, cv.cv_patience, loss_hist.ptr,
                                                    test_hist.ptr, static_cast<int>(loss_hist.count), state.ptr,
                                                    cv_state.ptr);
-    launches[RCPPML_B200_SEC_GRAM_H] += 1; launches[RCPPML_B200_SEC_GRAM_W] += 1; launches[RCPPML_B200_SEC_LOSS] += 2;
+    launches[RCPPML_B200_SEC_GRAM_H] += 1; launches[RCPPML_B200_SEC_GRAM_W] += 1; launches[RCPPML_B200_SEC_LOSS] += 3;
     sec_end(RCPPML_B200_SEC_LOSS);
     ++iters_enqueued;
 }
 
 void Engine::fit_cv(const rcppml_b200_config& c, const rcppml_b200_cv_config& cvc) {
     use_device();
-    B200_REQUIRE(world == 1, "fit_cv: the cross-validation path is single-GPU");
     B200_REQUIRE(!has_mask, "fit_cv: a user mask together with the speckled mask is not supported");
     B200_REQUIRE(cvc.holdout_fraction >= 0.f && cvc.holdout_fraction < 1.f, "holdout_fraction must be in [0, 1)");   // core/config.hpp:428
     B200_REQUIRE(c.max_iter > 0, "max_iter must be positive");

@@ -140,10 +140,9 @@ public:
     int tiled_mode = 1;
     double tiled_min_batches = 0.5, narrow_min_cols = 0.0;
     int tiled_sl_override = 0;              // k = 64 tiled kernel: solve lanes per column (0: rule, 2: 16-column batches, 4: 8)
-    double tiled_sl4_below = 0.0;
     bool use_narrow_cd(long long ncols) const;
     bool use_tiled(int solver, long long cnt, long long ncols) const;
-    int tiled_gather_geom(long long cnt, long long ncols) const;
+    int tiled_gather_geom(long long cnt, long long ncols, int solver) const;
     DeviceBuffer<float> W_T, H, d;
     DeviceBuffer<float> G_w, G_h, M1, M2, dblk;     // dblk: SolverConsts image (diagonal blocks, then reciprocals)
     int const_slot = 0;

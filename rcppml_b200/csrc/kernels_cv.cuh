@@ -52,6 +52,11 @@ struct CvParams {
     int* work_counter;
     double* partials;                  // [gridDim.x][KP+1]
     DevState* state;
+    // sharded fits: local column j is column / row j + col_offset of the whole matrix (the hold-out hash takes GLOBAL
+    // indices) and row j + col_offset of the replicated factor X; solved columns also go into the peers' replicas
+    int col_offset;
+    float* peerX[7];
+    int npeers;
 };
 
 template <int KP>
@@ -92,6 +97,7 @@ __global__ void __launch_bounds__(384, 1) cv_half_step_kernel(const CvParams p) 
         j = __shfl_sync(0xffffffffu, j, 0);
         if (j >= p.ncols) break;
         const int p0 = p.colptr[j], p1 = p.colptr[j + 1];
+        const int jg = j + p.col_offset;                            // global column (H update) / row (W update) index
 
         for (int e = lane; e < KP * KP; e += 32) Gl[(e / KP) * LD + (e % KP)] = p.G[e];      // cv_detail.hpp:74
         float b[NC];
@@ -103,7 +109,7 @@ __global__ void __launch_bounds__(384, 1) cv_half_step_kernel(const CvParams p) 
             for (int e0 = p0; e0 < p1; e0 += 32) {
                 const int e = e0 + lane;
                 int r = 0; float v = 0.f; bool h = false;
-                if (e < p1) { r = __ldg(p.rowidx + e); v = __ldg(p.vals + e); h = held(r, j); }
+                if (e < p1) { r = __ldg(p.rowidx + e); v = __ldg(p.vals + e); h = held(r, jg); }
                 const unsigned hb = __ballot_sync(0xffffffffu, h);
                 const int cnt = min(32, p1 - e0);
                 // The factor rows of 8 entries are requested together before any of them is consumed: a train
@@ -142,7 +148,7 @@ __global__ void __launch_bounds__(384, 1) cv_half_step_kernel(const CvParams p) 
             int e = p0;
             for (int i0 = 0; i0 < p.nrows; i0 += 32) {
                 const int i = i0 + lane;
-                const unsigned hb = __ballot_sync(0xffffffffu, i < p.nrows && held(i, j));
+                const unsigned hb = __ballot_sync(0xffffffffu, i < p.nrows && held(i, jg));
                 unsigned rest = hb;
                 for (;;) {                                          // merge held-out rows and non-zero rows of this chunk
                     const int nh = rest ? i0 + __ffs(rest) - 1 : 0x7fffffff;
@@ -171,7 +177,7 @@ __global__ void __launch_bounds__(384, 1) cv_half_step_kernel(const CvParams p) 
 #pragma unroll
             for (int t = 0; t < NC; ++t) btrain[t] = b[t];
         }
-        float* xcol = p.X + static_cast<size_t>(j) * KP;
+        float* xcol = p.X + static_cast<size_t>(jg) * KP;
         float x[NC];
         if (p.solver == 1) {                                        // cholesky_clip_col(G_local, b, x, k, L1, 0, nonneg, ...)
             if (p.L1 > 0.f) {
@@ -195,6 +201,7 @@ __global__ void __launch_bounds__(384, 1) cv_half_step_kernel(const CvParams p) 
                 if (p.ub > 0.f) v = fminf(v, p.ub);                 // fit_cv.hpp:528 / :843 (post-hoc)
                 x[t] = v;
                 xcol[c] = v;
+                for (int q2 = 0; q2 < p.npeers; ++q2) p.peerX[q2][static_cast<size_t>(jg) * KP + c] = v;
                 if (p.norm_type == 0) rs[t] += static_cast<double>(fabsf(v));
                 else if (p.norm_type == 1) rs[t] += static_cast<double>(v) * static_cast<double>(v);
             }
@@ -205,7 +212,7 @@ __global__ void __launch_bounds__(384, 1) cv_half_step_kernel(const CvParams p) 
                 for (int e0 = p0; e0 < p1; e0 += 32) {
                     const int e = e0 + lane;
                     int r = 0; float v = 0.f; bool h = false;
-                    if (e < p1) { r = __ldg(p.rowidx + e); v = __ldg(p.vals + e); h = held(r, j); }
+                    if (e < p1) { r = __ldg(p.rowidx + e); v = __ldg(p.vals + e); h = held(r, jg); }
                     unsigned hb = __ballot_sync(0xffffffffu, h);
                     while (hb) {
                         const int t = __ffs(hb) - 1;
@@ -217,7 +224,7 @@ __global__ void __launch_bounds__(384, 1) cv_half_step_kernel(const CvParams p) 
                 for (int e = p0; e < p1; ++e) {
                     const int r = __ldg(p.rowidx + e);
                     const float v = __ldg(p.vals + e);
-                    if (held(r, j) && v != 0.f) accumulate(btrain, v, r);
+                    if (held(r, jg) && v != 0.f) accumulate(btrain, v, r);
                 }
             }
             double s = 0.0;
@@ -246,8 +253,8 @@ __global__ void __launch_bounds__(384, 1) cv_half_step_kernel(const CvParams p) 
 // One CTA per column (grid-stride). partials[cta] = {sum, count}.
 static __global__ void __launch_bounds__(256) cv_test_loss_kernel(const int* __restrict__ colptr,
                                                                   const int* __restrict__ rowidx,
-                                                                  const float* __restrict__ vals, int ncols, int nrows,
-                                                                  int KP, int k, int mask_zeros,
+                                                                  const float* __restrict__ vals, int ncols, int col_offset,
+                                                                  int nrows, int KP, int k, int mask_zeros,
                                                                   unsigned long long seed, unsigned long long threshold,
                                                                   int holdout_enabled, const float* __restrict__ W_T,
                                                                   const float* __restrict__ H,
@@ -267,8 +274,9 @@ static __global__ void __launch_bounds__(256) cv_test_loss_kernel(const int* __r
         const float df = __fsub_rn(a, static_cast<float>(s));
         return static_cast<double>(__fmul_rn(df, df));
     };
-    for (int j = blockIdx.x; j < ncols; j += gridDim.x) {
-        const int p0 = colptr[j], p1 = colptr[j + 1];
+    for (int jl = blockIdx.x; jl < ncols; jl += gridDim.x) {
+        const int p0 = colptr[jl], p1 = colptr[jl + 1];
+        const int j = jl + col_offset;                              // global column: hash argument and row of H
         if (mask_zeros) {
             for (int e = p0 + threadIdx.x; e < p1; e += blockDim.x) {
                 const int i = rowidx[e];

@@ -239,6 +239,11 @@ struct MaskedParams {
     double* partials;                  // [gridDim.x][KP+1] (norm sums; slot KP unused here)
     DevState* state;
     unsigned long long* sweep_counter;
+    // sharded fits: local column j is row j + col_offset of the replicated factor X; solved columns are also stored
+    // into the peers' replicas (NVLink P2P), like half_step_kernel does
+    int col_offset;
+    float* peerX[7];
+    int npeers;
 };
 
 template <int KP>
@@ -301,7 +306,7 @@ __global__ void __launch_bounds__(384, 1) masked_half_step_kernel(const MaskedPa
         }
         __syncwarp();
 
-        float* xcol = p.X + static_cast<size_t>(j) * KP;
+        float* xcol = p.X + static_cast<size_t>(j + p.col_offset) * KP;
         float x[NC];
         if (p.solver == 0) {
             // ---- cd_nnls_col_fixed(G_local, b, x, k, 0, 0, nonneg, maxit, 0, cd_tol)  (masked_nnls.hpp:62-65)
@@ -330,6 +335,7 @@ __global__ void __launch_bounds__(384, 1) masked_half_step_kernel(const MaskedPa
                 float v = (c < k) ? x[t] : 0.f;
                 if (p.ub > 0.f) v = fminf(v, p.ub);                         // fit_cpu.hpp:636 / :884 (post-hoc)
                 xcol[c] = v;
+                for (int q2 = 0; q2 < p.npeers; ++q2) p.peerX[q2][static_cast<size_t>(j + p.col_offset) * KP + c] = v;
                 if (p.norm_type == 0) rs[t] += static_cast<double>(fabsf(v));
                 else if (p.norm_type == 1) rs[t] += static_cast<double>(v) * static_cast<double>(v);
             }
@@ -366,8 +372,8 @@ static __global__ void __launch_bounds__(256) masked_loss_kernel(const int* __re
                                                                  const int* __restrict__ rowidx,
                                                                  const float* __restrict__ vals,
                                                                  const int* __restrict__ mptr,
-                                                                 const int* __restrict__ midx, int ncols, int KP, int k,
-                                                                 const float* __restrict__ W_T,
+                                                                 const int* __restrict__ midx, int ncols, int col_offset,
+                                                                 int KP, int k, const float* __restrict__ W_T,
                                                                  const float* __restrict__ H,
                                                                  const float* __restrict__ d,
                                                                  double* __restrict__ partials,
@@ -377,7 +383,7 @@ static __global__ void __launch_bounds__(256) masked_loss_kernel(const int* __re
     double acc = 0.0;
     for (int j = blockIdx.x; j < ncols; j += gridDim.x) {
         const int p0 = colptr[j], p1 = colptr[j + 1], mb = mptr[j], me = mptr[j + 1];
-        const float* h = H + static_cast<size_t>(j) * KP;
+        const float* h = H + static_cast<size_t>(j + col_offset) * KP;
         for (int e = p0 + threadIdx.x; e < p1; e += blockDim.x) {
             const int r = rowidx[e];
             int lo = mb, hi = me;                               // binary search of r in the mask column

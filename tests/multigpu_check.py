@@ -83,10 +83,9 @@ def main():
         if rank == 0:
             print(f"k={k} solver={solver} world={world} p2p={p2p} tiled={tiled}: bit-identical={exact} {errs}", flush=True)
         assert max(errs.values()) <= 1e-5, errs
-    if os.environ.get("RCPPML_B200_TEST_ROUND2") == "1":
-        # block-wise factor I/O (written after round 1's GPU minutes were spent; opt-in until it has passed once):
-        # a fit started from set_factor_blocks equals one started from set_factors, bit for bit, and get_factor_blocks
-        # returns this rank's slices of the replicated factors.
+    if True:
+        # block-wise factor I/O: a fit started from set_factor_blocks equals one started from set_factors, bit for bit,
+        # and get_factor_blocks returns this rank's slices of the replicated factors.
         os.environ["RCPPML_B200_TILED"] = "1"
         k, iters = 20, 3
         cfg = rb.make_config(k, max_iter=iters, tol=0.0, solver_mode=0)
@@ -117,6 +116,70 @@ def main():
         assert all(np.array_equal(a, b) for a, b in zip(outs[0], outs[1])), "set_factor_blocks changes the fit"
         if rank == 0:
             print("block-wise factor I/O: bit-identical", flush=True)
+    # ---- explicit user mask and speckled-mask cross-validation, sharded (peer-memory loop and NCCL loop) vs one GPU
+    os.environ["RCPPML_B200_TILED"] = "1"
+    import scipy.sparse as sp
+    ms, ns = 30_011, 4_003
+    hp, hi, hx = synth.synth_csc(ms, ns, 0, 4e-3, synth.SEED_A)
+    rng = np.random.default_rng(11)
+    M = sp.random(ms, ns, density=2e-3, format="csc", random_state=rng, dtype=np.float32)
+    M.sort_indices()
+    mask = (M.indptr.astype(np.int32), M.indices.astype(np.int32))
+
+    def sharded_engine(p2p):
+        e = rb.Engine(local)
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(rb.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        e.comm_init(rank, world, uid.cpu().numpy().tobytes())
+        lo, cnt = shard.block_of(ns, world, rank)
+        r0, rc = shard.block_of(ms, world, rank)
+        e.set_matrix_sharded(ms, ns, shard.extract_shard(hp, hi, hx, lo, cnt), shard.extract_row_block(hp, hi, hx, r0, rc))
+        return e
+
+    for k, solver in ((16, 0), (64, 1)):
+        cfg = rb.make_config(k, max_iter=4, tol=0.0, solver_mode=solver, L1=(0.01, 0.0), L2=(0.0, 0.01), cd_maxit=20)
+        one = rb.Engine(local)
+        one.set_matrix(ms, ns, hp, hi, hx)
+        one.set_mask(*mask)
+        one.init_factors(k, 42, 0)
+        one.fit(cfg)
+        ref_m = one.get_factors() + (one.loss_history(4),)
+        one.set_mask()
+        one.init_factors(k, 42, 0)
+        _, cv1 = one.fit_cv(cfg, holdout_fraction=0.1, cv_seed=7, seed=42, mask_zeros=True, cv_patience=0)
+        ref_c = one.get_factors() + (cv1["test_history"], cv1["train_history"])
+        n_test1 = cv1["n_test"]
+        one.close()
+        for p2p in (True, False):
+            e = sharded_engine(p2p)
+            e.set_mask(*mask)
+            e.init_factors(k, 42, 0)
+            if p2p:
+                assert e.comm_enable_p2p(dist)
+            e.fit(cfg)
+            got = e.get_factors() + (e.loss_history(4),)
+            errs = [rel_err(a, b) for a, b in zip(got, ref_m)]
+            exact = all(np.array_equal(a, b) for a, b in zip(got[:3], ref_m[:3]))
+            assert max(errs) <= 1e-5, ("masked", k, solver, p2p, errs)
+            worst = max(worst, *errs)
+            if rank == 0:
+                print(f"masked k={k} solver={solver} world={world} p2p={p2p}: bit-identical={exact} max_rel_err={max(errs):.2e}", flush=True)
+            e.set_mask()
+            e.init_factors(k, 42, 0)
+            if p2p:
+                assert e.comm_enable_p2p(dist)
+            _, cv = e.fit_cv(cfg, holdout_fraction=0.1, cv_seed=7, seed=42, mask_zeros=True, cv_patience=0)
+            got = e.get_factors() + (cv["test_history"], cv["train_history"])
+            errs = [rel_err(a, b) for a, b in zip(got, ref_c)]
+            exact = all(np.array_equal(a, b) for a, b in zip(got[:3], ref_c[:3]))
+            assert cv["n_test"] == n_test1, (cv["n_test"], n_test1)
+            assert max(errs) <= 1e-5, ("cv", k, solver, p2p, errs)
+            worst = max(worst, *errs)
+            if rank == 0:
+                print(f"cv k={k} solver={solver} world={world} p2p={p2p}: bit-identical={exact} n_test={cv['n_test']} max_rel_err={max(errs):.2e}", flush=True)
+            e.close()
     dist.barrier()
     if rank == 0:
         print(f"MULTIGPU_CHECK_OK world={world} worst_rel_err={worst:.3e}", flush=True)

@@ -630,10 +630,6 @@ def test_in_process_multi_gpu_behind_the_reference_entry_is_bit_identical():
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs at least 2 GPUs")
-    if os.environ.get("RCPPML_B200_TEST_ROUND2") != "1":
-        # written after round 1's GPU minutes were spent: opt-in until tools/gpu_jobs/round2_inprocess_multigpu.sh
-        # has passed once on a multi-GPU box, then drop this gate
-        pytest.skip("in-process multi-GPU path not yet validated on hardware (set RCPPML_B200_TEST_ROUND2=1)")
     code = r'''
 import os, sys, numpy as np
 sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
@@ -664,8 +660,6 @@ def test_factor_blocks_on_one_gpu_are_the_whole_factors(oracle):
     round trip must equal set_factors / get_factors bit for bit. (The multi-rank case lives in tests/multigpu_check.py.)"""
     import os
     import rcppml_b200 as rb
-    if os.environ.get("RCPPML_B200_TEST_ROUND2") != "1":
-        pytest.skip("block-wise factor I/O not yet validated on hardware (set RCPPML_B200_TEST_ROUND2=1)")
     m, n, k = 500, 300, 12
     A = random_csc(m, n, 0.05, 17, ragged=True)
     W0, H0 = oracle.initialize_factors(k, m, n, 42)

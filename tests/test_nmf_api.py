@@ -290,9 +290,6 @@ def test_nnls_solves_for_h_and_for_w(oracle):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("RCPPML_B200_TEST_ROUND2") != "1",
-                    reason="added after round 1's GPU minutes were spent (host logic is covered on CPU by "
-                           "test_nmf_api_host.py); opt-in until it has passed once on hardware")
 def test_nmf_multiple_initialisations_keep_the_best():
     """seed = c(5, 6, 7) / list(W1, W2) (R/nmf_thin.R:772-791, 829-925): one fit per initialisation — run i with
     config.seed = seed[1] + i - 1 — and the lowest loss wins; misc$all_inits lists them."""
