@@ -66,13 +66,21 @@ struct EngineLease {
 // replicas are completed by peer copies, and every device writes its own blocks of the result straight into the
 // caller's W / H. Partition: contiguous ranges balanced by work (non-zeros + k per column).
 // Results are bit-identical to one GPU (same per-column arithmetic; fp64 reductions only re-associate).
+// The sm_100+ devices of this process, found once (cudaGetDeviceProperties costs milliseconds per call; the entry
+// points are called once per nmf()).
 int usable_devices(int* ids, int cap) {
-    int count = 0, usable = 0;
-    if (cudaGetDeviceCount(&count) != cudaSuccess) return 0;
-    for (int dev = 0; dev < count && usable < cap; ++dev) {
-        cudaDeviceProp prop{};
-        if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess && prop.major >= 10) ids[usable++] = dev;
-    }
+    static std::once_flag once;
+    static std::vector<int> found;
+    std::call_once(once, [] {
+        int count = 0;
+        if (cudaGetDeviceCount(&count) != cudaSuccess) { cudaGetLastError(); return; }
+        for (int dev = 0; dev < count; ++dev) {
+            int major = 0;
+            if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) == cudaSuccess && major >= 10) found.push_back(dev);
+        }
+    });
+    int usable = 0;
+    for (size_t i = 0; i < found.size() && usable < cap; ++i) ids[usable++] = found[i];
     return usable;
 }
 

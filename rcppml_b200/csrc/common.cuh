@@ -39,6 +39,24 @@ inline int lanes_for_rank(int k) {
 }
 inline int padded_rank(int k) { return lanes_for_rank(k) * 4; }
 
+// IEEE-exact a/d from a correctly rounded reciprocal r = RN(1/d): two FMA correction steps
+// (Markstein): after the first q is faithful, after the second it is the correctly rounded
+// quotient. 5 instructions instead of the ~15 (MUFU + slow path) of a generic __fdiv_rn; the
+// guard hands results outside the comfortable exponent range to __fdiv_rn. Verified bit for bit
+// against __fdiv_rn by rcppml_b200_selftest_division (tests/test_gpu_parity.py).
+__device__ __forceinline__ float div_exact(float a, float d, float r) {
+    float q = __fmul_rn(a, r);
+    float e = __fmaf_rn(-d, q, a);
+    q = __fmaf_rn(e, r, q);
+    e = __fmaf_rn(-d, q, a);
+    q = __fmaf_rn(e, r, q);
+    const float aq = fabsf(q);
+    if (!(aq > 1e-30f && aq < 1e30f)) {
+        if (a != 0.f) q = __fdiv_rn(a, d);
+    }
+    return q;
+}
+
 template <class T>
 struct DeviceBuffer {
     T* ptr = nullptr;

@@ -1002,9 +1002,13 @@ void Engine::join_side_stream() {
 
 void Engine::gram(float* X, long long ncols, bool normalize, float* G_out, int sec, bool reduce_over_ranks) {
     sec_begin(sec);
-    launch_normalize_gram(KP, X, ncols, d.ptr, normalize ? 1 : 0, gram_partials.ptr, &state.ptr->stop, gram_grid, stream);
+    // one CTA per column tile at most: a rank's block of a sharded factor can be a few hundred tiles, and every CTA's
+    // k x k fp64 partial is summed afterwards (592 partials of 32 KB at k = 64)
+    const long long tc = (KP >= 64) ? 32 : 64;
+    const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(gram_grid, (ncols + tc - 1) / tc)));
+    launch_normalize_gram(KP, X, ncols, d.ptr, normalize ? 1 : 0, gram_partials.ptr, &state.ptr->stop, grid, stream);
     const int nelem = KP * KP;
-    sum_partials_kernel<<<(nelem + 31) / 32, dim3(32, 8), 0, stream>>>(gram_partials.ptr, gram_grid, nelem, red_gram.ptr, &state.ptr->stop);
+    sum_partials_kernel<<<(nelem + 31) / 32, dim3(32, 8), 0, stream>>>(gram_partials.ptr, grid, nelem, red_gram.ptr, &state.ptr->stop);
     launches[sec] += 2;
     if (reduce_over_ranks && world > 1) allreduce_f64(red_gram.ptr, nelem);
     gram_from_sums_kernel<<<(nelem + 255) / 256, 256, 0, stream>>>(red_gram.ptr, KP, k, G_out, &state.ptr->stop);
@@ -1012,14 +1016,27 @@ void Engine::gram(float* X, long long ncols, bool normalize, float* G_out, int s
     sec_end(sec);
 }
 
+template <int KP>
+static void launch_prepare_solver(const float* G, int k, float L2, int solver, float* M1, float* M2, float* dblk, float* rcp,
+                                  DevState* st, cudaStream_t stream) {
+    auto kern = prepare_solver_kernel<KP>;
+    const size_t smem = static_cast<size_t>(KP) * KP * sizeof(float);
+    static OccCache cache;                                   // per device (see cached_occupancy)
+    cached_occupancy(cache, kern, kPrepThreads, smem, "prepare_solver_kernel does not fit on an SM");
+    kern<<<1, kPrepThreads, smem, stream>>>(G, k, L2, solver, M1, M2, dblk, rcp, st);
+}
+
 void Engine::prepare_solver(const float* G, float L2, int sec) {
     sec_begin(sec);
     const int solver = cfg.solver_mode == 0 ? SOLVER_CD : SOLVER_CHOL;
-    const size_t smem = static_cast<size_t>(2) * KP * KP * sizeof(float);
-    static OccCache cache;                                   // per device (see cached_occupancy)
-    cached_occupancy(cache, prepare_solver_kernel, kPrepThreads, static_cast<size_t>(2) * 128 * 128 * 4,
-                     "prepare_solver_kernel does not fit on an SM");
-    prepare_solver_kernel<<<1, kPrepThreads, smem, stream>>>(G, KP, k, L2, solver, M1.ptr, M2.ptr, dblk.ptr, dblk.ptr + kMaxKP * 4, state.ptr);
+    float* rcp = dblk.ptr + kMaxKP * 4;
+    switch (KP) {
+        case 16: launch_prepare_solver<16>(G, k, L2, solver, M1.ptr, M2.ptr, dblk.ptr, rcp, state.ptr, stream); break;
+        case 32: launch_prepare_solver<32>(G, k, L2, solver, M1.ptr, M2.ptr, dblk.ptr, rcp, state.ptr, stream); break;
+        case 64: launch_prepare_solver<64>(G, k, L2, solver, M1.ptr, M2.ptr, dblk.ptr, rcp, state.ptr, stream); break;
+        case 128: launch_prepare_solver<128>(G, k, L2, solver, M1.ptr, M2.ptr, dblk.ptr, rcp, state.ptr, stream); break;
+        default: throw std::runtime_error("unsupported padded rank");
+    }
     // warp-uniform operands -> this engine's constant-memory slot (kernels_solve.cuh SolverConsts); rcp follows
     // dblk in one device buffer, laid out like the struct
     B200_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_solver, dblk.ptr, sizeof(SolverConsts), sizeof(SolverConsts) * const_slot,

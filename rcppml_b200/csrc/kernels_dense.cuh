@@ -386,64 +386,75 @@ static __global__ void gram_from_sums_kernel(const double* __restrict__ sums, in
 //         (lower triangle incl. diagonal, [q][row][col]); rcp = RN(1/L_pp).
 // Padded pivots get dblk diagonal 1 (CHOL) / 0 (CD) so that they solve to 0 / are skipped.
 constexpr int kPrepThreads = 1024;
-static __global__ void __launch_bounds__(kPrepThreads) prepare_solver_kernel(const float* __restrict__ G, int KP, int k, float L2,
+template <int KP>
+static __global__ void __launch_bounds__(kPrepThreads) prepare_solver_kernel(const float* __restrict__ G, int k, float L2,
                                                             int solver, float* __restrict__ M1,
                                                             float* __restrict__ M2, float* __restrict__ dblk,
                                                             float* __restrict__ rcp, DevState* __restrict__ st) {
-    extern __shared__ float sL[];          // KP*KP col-major working copy, then KP*KP running dot products T
-    __shared__ float sDiag[kMaxKP];        // L(j,j) (the diagonal of the working copy keeps G(j,j): it is read by every row)
+    extern __shared__ float sL[];          // KP*KP col-major: G (+L2·I), overwritten column by column with L (below the diagonal)
+    __shared__ float sDiag[KP];            // L(j,j) (the diagonal of the working copy keeps G(j,j): every row reads it)
     if (st->stop) return;
     const int tid = threadIdx.x;
-    float* sT = sL + KP * KP;
-    for (int e = tid; e < KP * KP; e += blockDim.x) {
+    for (int e = tid; e < KP * KP; e += kPrepThreads) {
         float v = G[e];
         const int i = e % KP, j = e / KP;
         if (i == j && i < k && L2 > 0.f) v = __fadd_rn(v, L2);
         sL[e] = v;
-        if (solver != 0) sT[e] = 0.f;
     }
     if (tid < KP) sDiag[tid] = 0.f;
     __syncthreads();
     if (solver != 0) {
         // LLT in the oracle's operation order: L(i,j) = (G(i,j) - t_ij) / L(j,j) with the dot product
         // t_ij = sum_{p<j} L(i,p)·L(j,p) accumulated sequentially in p (separately rounded mul and add), and
-        // L(j,j) = sqrt(G(j,j) - t_jj). The dots are kept as RUNNING sums T(i,j) that every finished column p
-        // updates for all pairs (i >= j > p) at once — the same additions in the same order as the left-looking
-        // loop, but k steps of O(1) depth instead of k dependent dots of length j.
-        // Synchronisation per column (was three CTA-wide barriers): thread (ti, tj0) always updates T(ti, c) for
-        // c = j+1+tj0 (+ multiples of blockDim/KP), so T(:, j+1) — all the NEXT column needs — is written by the
-        // threads with tj0 == 0, the same `tid < KP` threads that turn it into L(:, j+1). Those warps meet at a
-        // narrow named barrier (A), everyone meets once at the CTA barrier (B) that publishes L(:, j). The pivot is
-        // recomputed by every row from G(j,j) and T(j,j), so the in-place overwrite needs no barrier of its own.
-        const int ti = tid % KP, tj0 = tid / KP, tjs = blockDim.x / KP;
-        const int front = (KP < 32) ? 32 : KP;              // threads of the warps that own a row (whole warps)
+        // L(j,j) = sqrt(G(j,j) - t_jj). The dots are RUNNING sums that every finished column p updates for all pairs
+        // (i >= c > p) at once — the same additions in the same order as the left-looking loop, k steps of O(1) depth.
+        // Thread (ti, tq) OWNS the running dots T(ti, c) of the columns c = tq, tq + TJS, ... in registers, and — so that
+        // no pivot has to be broadcast — its own copy of the diagonal dots T(c, c) of those columns (the multiplier
+        // L(c,p) it reads for T(ti,c) += L(ti,p)·L(c,p) is all that needs: T(c,c) += L(c,p)·L(c,p), the very
+        // operation the owner of row c performs). Column j is then finished by the threads with tq == j mod TJS from
+        // registers alone, and ONE CTA barrier per column publishes it (round 1: three barriers and the dots in shared
+        // memory, ~45 us at k = 64). IEEE division through div_exact with RN(1/L(j,j)) — bit-identical to __fdiv_rn
+        // (rcppml_b200_selftest_division).
+        constexpr int TJS = kPrepThreads / KP;             // column stride between a thread's columns
+        constexpr int NU = (KP + TJS - 1) / TJS;           // columns per thread
+        const int ti = tid % KP, tq = tid / KP;
+        float T[NU], Td[NU];
+#pragma unroll
+        for (int u = 0; u < NU; ++u) T[u] = Td[u] = 0.f;
         for (int j = 0; j < k; ++j) {
-            if (tid < front) {
-                if (j > 0) {                                // (A) T(:, j) complete: written by these warps in step j-1
-                    if (front == 32) __syncwarp();
-                    else asm volatile("bar.sync 1, %0;" ::"r"(front) : "memory");
-                }
-                const float x = __fsub_rn(sL[j * KP + j], sT[j * KP + j]);
+            if (tq == j % TJS) {
+                const int uj = j / TJS;
+                float t = 0.f, td = 0.f;
+#pragma unroll
+                for (int u = 0; u < NU; ++u)
+                    if (u == uj) { t = T[u]; td = Td[u]; }
+                const float x = __fsub_rn(sL[j * KP + j], td);
                 float ljj = 0.f;
                 if (!(x > 0.f)) {
-                    if (tid == 0 && st->chol_fail == 0) st->chol_fail = j + 1;
+                    if (ti == 0 && st->chol_fail == 0) st->chol_fail = j + 1;
                 } else {
                     ljj = __fsqrt_rn(x);
                 }
-                if (tid > j && tid < k) sL[j * KP + tid] = __fdiv_rn(__fsub_rn(sL[j * KP + tid], sT[j * KP + tid]), ljj);
-                if (tid == j) sDiag[j] = ljj;
+                if (ti > j && ti < k) sL[j * KP + ti] = div_exact(__fsub_rn(sL[j * KP + ti], t), ljj, __frcp_rn(ljj));
+                if (ti == j) sDiag[j] = ljj;
             }
-            __syncthreads();                                // (B) L(:, j) published
-            // T(i,c) += L(i,j)·L(c,j) for j < c <= i < k
-            const float li = sL[j * KP + ti];
-            for (int c = j + 1 + tj0; c < k; c += tjs)
-                if (ti >= c && ti < k) sT[c * KP + ti] = __fadd_rn(sT[c * KP + ti], __fmul_rn(li, sL[j * KP + c]));
+            __syncthreads();                                // L(:, j) published
+            const float li = sL[j * KP + ti];               // (rows <= j read G or garbage: their dots are never used)
+#pragma unroll
+            for (int u = 0; u < NU; ++u) {
+                const int c = tq + u * TJS;
+                if (c > j && c < k) {
+                    const float lc = sL[j * KP + c];
+                    T[u] = __fadd_rn(T[u], __fmul_rn(li, lc));
+                    Td[u] = __fadd_rn(Td[u], __fmul_rn(lc, lc));
+                }
+            }
         }
         __syncthreads();
-        for (int j = tid; j < k; j += blockDim.x) sL[j * KP + j] = sDiag[j];
+        for (int j = tid; j < k; j += kPrepThreads) sL[j * KP + j] = sDiag[j];
         __syncthreads();
     }
-    for (int e = tid; e < KP * KP; e += blockDim.x) {
+    for (int e = tid; e < KP * KP; e += kPrepThreads) {
         const int i = e % KP, j = e / KP;                  // e = j*KP + i  -> element (row i, col j)
         const bool in_block = (i / 4) == (j / 4);
         if (solver == 0) {
@@ -454,7 +465,7 @@ static __global__ void __launch_bounds__(kPrepThreads) prepare_solver_kernel(con
             M2[e] = (i < j && j < k && !in_block) ? sL[i * KP + j] : 0.f;
         }
     }
-    for (int e = tid; e < KP * 4; e += blockDim.x) {        // dblk[q][a][b] = M(4q+a, 4q+b)
+    for (int e = tid; e < KP * 4; e += kPrepThreads) {     // dblk[q][a][b] = M(4q+a, 4q+b)
         const int q = e / 16, a = (e / 4) % 4, b = e % 4;
         const int i = q * 4 + a, j = q * 4 + b;
         float v;
@@ -462,7 +473,7 @@ static __global__ void __launch_bounds__(kPrepThreads) prepare_solver_kernel(con
         else v = (i < k && j < k) ? ((j <= i) ? sL[j * KP + i] : 0.f) : ((i == j) ? 1.f : 0.f);
         dblk[e] = v;
     }
-    for (int i = tid; i < KP; i += blockDim.x) {
+    for (int i = tid; i < KP; i += kPrepThreads) {
         const float dg = (i < k) ? sL[i * KP + i] : ((solver == 0) ? 0.f : 1.f);
         rcp[i] = (dg > 0.f) ? __frcp_rn(dg) : 0.f;
     }
