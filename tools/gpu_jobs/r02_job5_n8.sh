@@ -1,0 +1,33 @@
+#!/bin/bash
+# Round 2, GPU call 5 (8 GPUs): BASELINE configs[3] (C4) and configs[4] (C5: 5M x 500K, k = 128, L1 = L2 = 0.01) on 8 GPUs
+# with parity (sharded fit == one-GPU fit, device checksums) and the e2e leg through the reference ABI with
+# RCPPML_NUM_GPUS=8; the sharded-vs-one-GPU check of every path; C4 in CD mode.
+#   gpurun --gpus 8 --timeout 720 -- bash tools/gpu_jobs/r02_job5_n8.sh
+set -u
+mkdir -p gpurun_out
+tr() { # name timeout port args...
+    local name=$1 to=$2 port=$3; shift 3
+    RCPPML_B200_TRACE=1 timeout $to python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port $port \
+        bench.py --gpus 8 "$@" > gpurun_out/${name}.json 2> gpurun_out/${name}.err
+    echo "== ${name}: rc=$?"; grep "RcppML_gpu" gpurun_out/${name}.err | tail -2
+}
+tr r02e_bench_c4_n8 240 29541 --steps 20 --warmup 5
+tr r02e_bench_c5_n8 330 29542 --steps 5 --warmup 3 --rows 5000000 --cols 500000 --density 5e-4 --rank 128 --L1 0.01 --L2 0.01
+echo "== multigpu_check n8"
+timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29543 tests/multigpu_check.py > gpurun_out/r02e_multigpu_check_n8.txt 2>&1; echo "rc=$?"; grep -v "^W\|^\*\*\*\|OMP_NUM" gpurun_out/r02e_multigpu_check_n8.txt | tail -8
+tr r02e_bench_c4_cd_n8 150 29544 --steps 10 --warmup 3 --solver cd --no-e2e
+python - <<'PY'
+import json
+for f in ('r02e_bench_c4_n8', 'r02e_bench_c5_n8', 'r02e_bench_c4_cd_n8'):
+    try:
+        d=json.loads([l for l in open('gpurun_out/%s.json' % f) if l.startswith('{')][-1])
+        print(f, round(d['ms_per_step'],4), d['value'], d['gpu_launches'])
+        print(' sections', {k: round(v,3) for k,v in d['roofline']['sections_ms_per_step'].items()})
+        o=d['roofline']['over_ranks']; print(' over_ranks', o['loop_ms_per_step'], o['profiled_loop_ms_per_step'])
+        print(' sections min/max', {k: (round(v['min'],3), round(v['max'],3)) for k,v in o['sections_ms_per_step'].items()})
+        e=d['e2e']
+        if e: print(' e2e', e['value'], e['seconds_total'], e.get('phases'), e.get('factors_bit_identical_to_sharded_engine'), e.get('warmup_call_seconds'))
+        print(' parity', d['parity'])
+    except Exception as ex:
+        print(f, 'parse failed', ex)
+PY
