@@ -332,6 +332,21 @@ int rcppml_b200_comm_init(rcppml_b200_engine* e, int rank, int world, const char
  * that sum in rank order (bit-identical on every rank). Without these two calls the loop uses NCCL. */
 int rcppml_b200_comm_ipc_export(rcppml_b200_engine* e, char* handles192);
 int rcppml_b200_comm_ipc_import(rcppml_b200_engine* e, const char* all_handles);
+/* NVSwitch multicast replication (NVLS; preferred over the unicast peer stores where the devices support it and
+ * RCPPML_B200_MC != 0 — comm_mc_wanted says so after comm_init): the factors are VMM allocations bound to two
+ * multicast objects, and the kernel that normalises a freshly solved block writes it into EVERY replica with one
+ * multimem.st per word. Same call pattern as the IPC pair: export a 128-byte blob per rank after the factors exist,
+ * all-gather the blobs (rank-major, world x 128 bytes), import on every rank, check that every rank succeeded, bind, barrier, finish. The blobs carry POSIX
+ * file descriptors that a peer duplicates with pidfd_getfd (same user). On failure: last_error, and the loop falls
+ * back to NCCL. */
+int rcppml_b200_comm_mc_wanted(rcppml_b200_engine* e);
+int rcppml_b200_comm_mc_ready(rcppml_b200_engine* e);
+int rcppml_b200_comm_mc_export(rcppml_b200_engine* e, char* blob128);
+int rcppml_b200_comm_mc_import(rcppml_b200_engine* e, const char* all_blobs);
+int rcppml_b200_comm_mc_bind(rcppml_b200_engine* e);      /* after import succeeded on EVERY rank (binding blocks until all joined) */
+int rcppml_b200_comm_mc_finish(rcppml_b200_engine* e);
+/* Drops every peer mapping (IPC or multicast): the loop falls back to NCCL until the next export / import. */
+int rcppml_b200_comm_p2p_close(rcppml_b200_engine* e);
 
 /* The engine behind the reference entry points (part 1) is cached per process: device buffers and staging areas
  * are grow-only, so repeated calls make no cudaMalloc / cudaFree (the reference builds its GPUContext per call,

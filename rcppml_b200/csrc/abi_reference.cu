@@ -167,6 +167,8 @@ bool fit_in_process_multi_gpu(int G, const int* devices, int m, int n, int64_t n
     std::vector<rcppml_b200_result> rr(G);
     std::vector<std::string> err(G);
     PhaseBarrier bar(G);
+    CUmemGenericAllocationHandle mc_handles[2] = {0, 0};
+    bool mc_created = false;
     double marks[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};        // rank 0's wall clock at the phase boundaries (ms)
     auto since = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count(); };
 
@@ -197,6 +199,22 @@ bool fit_in_process_multi_gpu(int G, const int* devices, int m, int n, int64_t n
         E.comm_prepare_local(devices);
         if (!bar.wait()) return;                                             // D: every replica buffer exists, own blocks in place
         E.comm_attach_local(all.data());
+        // NVSwitch multicast (vmm.hpp): device 0's thread creates the two multicast objects, every device joins, binds
+        // its replicas and maps them — from then on a normalised block is written once and lands in all replicas
+        bool want_mc = true;
+        for (int r = 0; r < G; ++r) want_mc = want_mc && all[r]->mc_wanted && all[r]->W_T.vmm && all[r]->H.vmm;
+        if (want_mc) {
+            if (g == 0) {
+                try { E.mc_create(&mc_handles[0], &mc_handles[1], false); mc_created = true; }
+                catch (const std::exception& ex) { warn((std::string("multicast unavailable, unicast peer stores instead: ") + ex.what()).c_str()); }
+            }
+            if (!bar.wait()) return;                                         // E1: the objects exist (or not)
+            if (mc_created) {
+                E.mc_add_device(mc_handles[0], mc_handles[1]);
+                if (!bar.wait()) return;                                     // E2: every device joined
+                E.mc_bind_and_map(mc_handles[0], mc_handles[1], g == 0);
+            }
+        }
         E.pull_factor_blocks_from_peers();
         if (g == 0) marks[2] = since();
         E.begin_fit(cfg);                                                    // (its first exchange orders the pulls against the peers' first stores)
@@ -259,10 +277,10 @@ bool fit_in_process_multi_gpu(int G, const int* devices, int m, int n, int64_t n
     }
     cudaSetDevice(devices[0]);
     if (std::getenv("RCPPML_B200_TRACE"))
-        std::fprintf(stderr, "[RcppML_gpu/b200] multi-GPU call (G=%d), rank-0 wall clock ms: col blocks up %.2f | row blocks %.2f | "
+        std::fprintf(stderr, "[RcppML_gpu/b200] multi-GPU call (G=%d, %s), rank-0 wall clock ms: col blocks up %.2f | row blocks %.2f | "
                              "factor blocks + replicas %.2f | begin_fit %.2f | iterate+result %.2f (loop events %.2f) | blocks down %.2f | "
                              "threads joined %.2f | end %.2f\n",
-                     G, marks[0], marks[1] - marks[0], marks[2] - marks[1], marks[5] - marks[2], marks[3] - marks[5], rr[0].loop_ms,
+                     G, (eng.size() && eng[0] && eng[0]->mc_ready) ? "multicast replication" : "unicast peer stores", marks[0], marks[1] - marks[0], marks[2] - marks[1], marks[5] - marks[2], marks[3] - marks[5], rr[0].loop_ms,
                      marks[4] - marks[3], marks[6], since());
     return ok;
 }

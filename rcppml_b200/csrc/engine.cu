@@ -161,22 +161,22 @@ static bool cd_geometry_matches(int geom, int KP) {
 }
 
 static void launch_normalize_gram(int KP, float* X, long long ncols, const float* d, int normalize, double* partials,
-                                  const int* stop, int grid, cudaStream_t s) {
+                                  const int* stop, int grid, cudaStream_t s, float* mcX) {
 #ifdef B200_GRAM_DFMA      // register-tiled DFMA version (kept for comparison; bound by shared-memory delivery)
     switch (KP) {
-        case 16: normalize_gram_kernel<16, 64><<<grid, kGramThreads, 0, s>>>(X, ncols, d, normalize, partials, stop); break;
-        case 32: normalize_gram_kernel<32, 64><<<grid, kGramThreads, 0, s>>>(X, ncols, d, normalize, partials, stop); break;
-        case 64: normalize_gram_kernel<64, 32><<<grid, kGramThreads, 0, s>>>(X, ncols, d, normalize, partials, stop); break;
-        case 128: normalize_gram_kernel<128, 32><<<grid, kGramThreads, 0, s>>>(X, ncols, d, normalize, partials, stop); break;
+        case 16: normalize_gram_kernel<16, 64><<<grid, kGramThreads, 0, s>>>(X, ncols, d, normalize, partials, stop, mcX); break;
+        case 32: normalize_gram_kernel<32, 64><<<grid, kGramThreads, 0, s>>>(X, ncols, d, normalize, partials, stop, mcX); break;
+        case 64: normalize_gram_kernel<64, 32><<<grid, kGramThreads, 0, s>>>(X, ncols, d, normalize, partials, stop, mcX); break;
+        case 128: normalize_gram_kernel<128, 32><<<grid, kGramThreads, 0, s>>>(X, ncols, d, normalize, partials, stop, mcX); break;
         default: throw std::runtime_error("unsupported padded rank");
     }
     return;
 #endif
     switch (KP) {
-        case 16: normalize_gram_mma_kernel<16, 64><<<grid, GramMmaGeom<16>::WARPS * 32, 0, s>>>(X, ncols, d, normalize, partials, stop); break;
-        case 32: normalize_gram_mma_kernel<32, 64><<<grid, GramMmaGeom<32>::WARPS * 32, 0, s>>>(X, ncols, d, normalize, partials, stop); break;
-        case 64: normalize_gram_mma_kernel<64, 32><<<grid, GramMmaGeom<64>::WARPS * 32, 0, s>>>(X, ncols, d, normalize, partials, stop); break;
-        case 128: normalize_gram_mma_kernel<128, 32><<<grid, GramMmaGeom<128>::WARPS * 32, 0, s>>>(X, ncols, d, normalize, partials, stop); break;
+        case 16: normalize_gram_mma_kernel<16, 64><<<grid, GramMmaGeom<16>::WARPS * 32, 0, s>>>(X, ncols, d, normalize, partials, stop, mcX); break;
+        case 32: normalize_gram_mma_kernel<32, 64><<<grid, GramMmaGeom<32>::WARPS * 32, 0, s>>>(X, ncols, d, normalize, partials, stop, mcX); break;
+        case 64: normalize_gram_mma_kernel<64, 32><<<grid, GramMmaGeom<64>::WARPS * 32, 0, s>>>(X, ncols, d, normalize, partials, stop, mcX); break;
+        case 128: normalize_gram_mma_kernel<128, 32><<<grid, GramMmaGeom<128>::WARPS * 32, 0, s>>>(X, ncols, d, normalize, partials, stop, mcX); break;
         default: throw std::runtime_error("unsupported padded rank");
     }
 }
@@ -735,8 +735,10 @@ void Engine::alloc_factors(int k_) {
     narrow_min_cols = 8.0 * num_sms * 24;
     if (std::getenv("RCPPML_B200_CD_GEOM")) narrow_min_cols = 0.0;           // an explicit geometry applies to every size
     if (const char* env = std::getenv("RCPPML_B200_NARROW_MIN_COLS")) narrow_min_cols = std::atof(env);
-    if (peers_ready && (static_cast<size_t>(m_pad) * KP > W_T.count || static_cast<size_t>(n_pad) * KP > H.count ||
-                        KP * KP > xchg_ne_max))
+    W_T.want_vmm = H.want_vmm = mc_wanted;
+    if ((peers_ready || mc_ready) &&
+        (static_cast<size_t>(m_pad) * KP > W_T.count || static_cast<size_t>(n_pad) * KP > H.count || KP * KP > xchg_ne_max ||
+         W_T.vmm != W_T.want_vmm || H.vmm != H.want_vmm))
         comm_ipc_close();                                 // the mapped buffers are about to move: back to NCCL
     W_T.ensure(static_cast<size_t>(m_pad) * KP);          // padded to equal row / column blocks (all-gather)
     H.ensure(static_cast<size_t>(n_pad) * KP);
@@ -1000,13 +1002,16 @@ void Engine::join_side_stream() {
     side_pending = false;
 }
 
-void Engine::gram(float* X, long long ncols, bool normalize, float* G_out, int sec, bool reduce_over_ranks) {
+void Engine::gram(float* X, long long ncols, bool normalize, float* G_out, int sec, bool reduce_over_ranks, bool replicate) {
     sec_begin(sec);
     // one CTA per column tile at most: a rank's block of a sharded factor can be a few hundred tiles, and every CTA's
     // k x k fp64 partial is summed afterwards (592 partials of 32 KB at k = 64)
     const long long tc = (KP >= 64) ? 32 : 64;
     const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(gram_grid, (ncols + tc - 1) / tc)));
-    launch_normalize_gram(KP, X, ncols, d.ptr, normalize ? 1 : 0, gram_partials.ptr, &state.ptr->stop, grid, stream);
+    // replicate: X is this rank's freshly solved block of a replicated factor and the factors are multicast-bound —
+    // the kernel writes the normalised block into every replica (multimem.st) instead of only this one
+    float* mcX = (replicate && mc_ready) ? mc_alias(X) : nullptr;
+    launch_normalize_gram(KP, X, ncols, d.ptr, normalize ? 1 : 0, gram_partials.ptr, &state.ptr->stop, grid, stream, mcX);
     const int nelem = KP * KP;
     sum_partials_kernel<<<(nelem + 31) / 32, dim3(32, 8), 0, stream>>>(gram_partials.ptr, grid, nelem, red_gram.ptr, &state.ptr->stop);
     launches[sec] += 2;
@@ -1100,7 +1105,7 @@ HalfStepParams Engine::solve_params(int which, bool warm) const {
     p.stop_flag = &state.ptr->stop;
     p.sweep_counter = sweep_counter.ptr;
     p.npeers = 0;
-    if (peers_ready) {
+    if (peers_ready && !mc_ready) {                     // multicast mode: the normalising Gram kernel replicates the block
         for (int r = 0; r < world; ++r)
             if (r != rank) p.peerX[p.npeers++] = h ? peer_H[r] : peer_W[r];
     }
@@ -1279,6 +1284,8 @@ void Engine::enqueue_iteration() {
     // other GPUs' copies while they run, the small all-reduces are one-shot peer-memory kernels, and each
     // rank normalises the whole replicated factor locally: no NCCL call in the loop, no exposed all-gather.
     const bool p2p = sharded && peers_ready;
+    const bool ucast = p2p && !mc_ready;                                    // unicast peer stores + local re-normalisation
+    const bool repl = p2p && mc_ready;                                      // multicast replication by the Gram kernel
     float* Hblk = H.ptr + static_cast<size_t>(col_begin) * KP;
     float* Wblk = W_T.ptr + static_cast<size_t>(row_begin) * KP;
     // ---- H update (fit_cpu.hpp:488-645). The Gram of W_T and the solver operands built from it are produced at the END
@@ -1292,18 +1299,18 @@ void Engine::enqueue_iteration() {
     solve(0, warm, RCPPML_B200_SEC_SOLVE_H);                                // :516-535 (+ :636 upper bound)
     scale_finalize(RCPPML_B200_SEC_SCALE_H, sharded);                       // :644 (p2p: also the barrier)
     // ---- W update (fit_cpu.hpp:713-893)
-    if (p2p) normalize_peer_blocks(H.ptr, n, col_begin, col_begin + n_loc, normalize);   // side stream
-    gram(Hblk, n_loc, normalize, G_h.ptr, RCPPML_B200_SEC_GRAM_W, sharded); // :644 (normalise) + :715
+    if (ucast) normalize_peer_blocks(H.ptr, n, col_begin, col_begin + n_loc, normalize);   // side stream
+    gram(Hblk, n_loc, normalize, G_h.ptr, RCPPML_B200_SEC_GRAM_W, sharded, repl); // :644 (normalise) + :715
     if (sharded && !p2p) allgather_rows(H.ptr, col_cuts, n_pad, RCPPML_B200_SEC_COMM);
     prepare_solver(G_h.ptr, cfg.L2_W, RCPPML_B200_SEC_GRAM_W);              // :738
     join_side_stream();
     solve(1, warm, RCPPML_B200_SEC_SOLVE_W);                                // :748-767 (+ :884)
     scale_finalize(RCPPML_B200_SEC_SCALE_W, sharded);                       // :892
     // ---- loss (fit_cpu.hpp:1729-1809): Gram of the new W_T doubles as next iteration's gram_H
-    if (p2p) normalize_peer_blocks(W_T.ptr, m, row_begin, row_begin + m_loc, normalize);   // side stream
+    if (ucast) normalize_peer_blocks(W_T.ptr, m, row_begin, row_begin + m_loc, normalize);   // side stream
     sec_begin(RCPPML_B200_SEC_LOSS);
     const bool was = profiling; profiling = false;                         // nested section: account under LOSS
-    gram(Wblk, m_loc, normalize, G_w.ptr, RCPPML_B200_SEC_LOSS, sharded);   // :892 (normalise) + :1735
+    gram(Wblk, m_loc, normalize, G_w.ptr, RCPPML_B200_SEC_LOSS, sharded, repl);   // :892 (normalise) + :1735
     profiling = was;
     loss(RCPPML_B200_SEC_LOSS);
     sec_end(RCPPML_B200_SEC_LOSS);
@@ -1376,7 +1383,7 @@ void Engine::masked_solve(int which, bool warm, const float* G, int sec) {
     p.ncols = h ? n_loc : m_loc;
     p.col_offset = h ? col_begin : row_begin;
     p.npeers = 0;
-    if (peers_ready)
+    if (peers_ready && !mc_ready)
         for (int r = 0; r < world; ++r)
             if (r != rank) p.peerX[p.npeers++] = h ? peer_H[r] : peer_W[r];
     p.k = k;
@@ -1413,22 +1420,24 @@ void Engine::enqueue_iteration_masked() {
     const bool normalize = cfg.norm_type != 2;
     const bool sharded = world > 1;
     const bool p2p = sharded && peers_ready;
+    const bool ucast = p2p && !mc_ready;                                    // unicast peer stores + local re-normalisation
+    const bool repl = p2p && mc_ready;                                      // multicast replication by the Gram kernel
     float* Hblk = H.ptr + static_cast<size_t>(col_begin) * KP;
     float* Wblk = W_T.ptr + static_cast<size_t>(row_begin) * KP;
     if (iters_enqueued == 0) gram(Wblk, m_loc, false, G_w.ptr, RCPPML_B200_SEC_GRAM_H, sharded);   // :562 rebuilt unmodified
     join_side_stream();
     masked_solve(0, warm, G_w.ptr, RCPPML_B200_SEC_SOLVE_H);
     scale_finalize(RCPPML_B200_SEC_SCALE_H, sharded);
-    if (p2p) normalize_peer_blocks(H.ptr, n, col_begin, col_begin + n_loc, normalize);
-    gram(Hblk, n_loc, normalize, G_h.ptr, RCPPML_B200_SEC_GRAM_W, sharded);                       // :644 + :801
+    if (ucast) normalize_peer_blocks(H.ptr, n, col_begin, col_begin + n_loc, normalize);
+    gram(Hblk, n_loc, normalize, G_h.ptr, RCPPML_B200_SEC_GRAM_W, sharded, repl);                       // :644 + :801
     if (sharded && !p2p) allgather_rows(H.ptr, col_cuts, n_pad, RCPPML_B200_SEC_COMM);
     join_side_stream();
     masked_solve(1, warm, G_h.ptr, RCPPML_B200_SEC_SOLVE_W);
     scale_finalize(RCPPML_B200_SEC_SCALE_W, sharded);
-    if (p2p) normalize_peer_blocks(W_T.ptr, m, row_begin, row_begin + m_loc, normalize);
+    if (ucast) normalize_peer_blocks(W_T.ptr, m, row_begin, row_begin + m_loc, normalize);
     sec_begin(RCPPML_B200_SEC_LOSS);
     const bool was = profiling; profiling = false;
-    gram(Wblk, m_loc, normalize, G_w.ptr, RCPPML_B200_SEC_LOSS, sharded);                         // normalise + next gram_H
+    gram(Wblk, m_loc, normalize, G_w.ptr, RCPPML_B200_SEC_LOSS, sharded, repl);                         // normalise + next gram_H
     profiling = was;
     if (sharded && !p2p) allgather_rows(W_T.ptr, row_cuts, m_pad, RCPPML_B200_SEC_COMM);
     join_side_stream();                                                     // the loss reads every row of W_T
@@ -1459,7 +1468,7 @@ void Engine::cv_solve(int which, int sec) {
     p.nrows = h ? m : n;
     p.col_offset = h ? col_begin : row_begin;
     p.npeers = 0;
-    if (peers_ready)
+    if (peers_ready && !mc_ready)
         for (int r = 0; r < world; ++r)
             if (r != rank) p.peerX[p.npeers++] = h ? peer_H[r] : peer_W[r];
     p.k = k;
@@ -1493,6 +1502,8 @@ void Engine::enqueue_iteration_cv() {
     const bool normalize = cfg.norm_type != 2;
     const bool sharded = world > 1;
     const bool p2p = sharded && peers_ready;
+    const bool ucast = p2p && !mc_ready;                                    // unicast peer stores + local re-normalisation
+    const bool repl = p2p && mc_ready;                                      // multicast replication by the Gram kernel
     float* Hblk = H.ptr + static_cast<size_t>(col_begin) * KP;
     float* Wblk = W_T.ptr + static_cast<size_t>(row_begin) * KP;
     const int ge = (KP * KP + 255) / 256;
@@ -1501,17 +1512,17 @@ void Engine::enqueue_iteration_cv() {
     join_side_stream();
     cv_solve(0, RCPPML_B200_SEC_SOLVE_H);                                                    // :431-476, :528
     scale_finalize(RCPPML_B200_SEC_SCALE_H, sharded);                                        // :536-548
-    if (p2p) normalize_peer_blocks(H.ptr, n, col_begin, col_begin + n_loc, normalize);
-    gram(Hblk, n_loc, normalize, G_h.ptr, RCPPML_B200_SEC_GRAM_W, sharded);                  // :570 (= G_H_saved)
+    if (ucast) normalize_peer_blocks(H.ptr, n, col_begin, col_begin + n_loc, normalize);
+    gram(Hblk, n_loc, normalize, G_h.ptr, RCPPML_B200_SEC_GRAM_W, sharded, repl);                  // :570 (= G_H_saved)
     if (sharded && !p2p) allgather_rows(H.ptr, col_cuts, n_pad, RCPPML_B200_SEC_COMM);
     cv_prepare_gram_kernel<<<ge, 256, 0, stream>>>(G_h.ptr, KP, k, cfg.L2_W, M1.ptr, &state.ptr->stop);   // :578-581
     join_side_stream();
     cv_solve(1, RCPPML_B200_SEC_SOLVE_W);                                                    // :598-735, :843
     scale_finalize(RCPPML_B200_SEC_SCALE_W, sharded);                                        // :849-858 (+ cross term)
-    if (p2p) normalize_peer_blocks(W_T.ptr, m, row_begin, row_begin + m_loc, normalize);
+    if (ucast) normalize_peer_blocks(W_T.ptr, m, row_begin, row_begin + m_loc, normalize);
     sec_begin(RCPPML_B200_SEC_LOSS);
     const bool was = profiling; profiling = false;
-    gram(Wblk, m_loc, normalize, G_w.ptr, RCPPML_B200_SEC_LOSS, sharded);                    // normalise + :1518
+    gram(Wblk, m_loc, normalize, G_w.ptr, RCPPML_B200_SEC_LOSS, sharded, repl);                    // normalise + :1518
     profiling = was;
     if (sharded && !p2p) allgather_rows(W_T.ptr, row_cuts, m_pad, RCPPML_B200_SEC_COMM);
     join_side_stream();                                                     // the test loss reads every row of W_T

@@ -3,6 +3,7 @@
 
 #include "../../include/rcppml_gpu.h"
 #include "common.cuh"
+#include "vmm.hpp"
 #include "kernels_dense.cuh"
 #include "kernels_masked.cuh"
 #include "kernels_cv.cuh"
@@ -143,7 +144,8 @@ public:
     bool use_narrow_cd(long long ncols) const;
     bool use_tiled(int solver, long long cnt, long long ncols) const;
     int tiled_gather_geom(long long cnt, long long ncols, int solver) const;
-    DeviceBuffer<float> W_T, H, d;
+    FactorBuffer W_T, H;                    // replicated factors (VMM-backed + multicast-bound in sharded fits, vmm.hpp)
+    DeviceBuffer<float> d;
     DeviceBuffer<float> G_w, G_h, M1, M2, dblk;     // dblk: SolverConsts image (diagonal blocks, then reciprocals)
     int const_slot = 0;
     DeviceBuffer<double> gram_partials, solve_partials;   // per-CTA partials (fixed-order reductions)
@@ -199,11 +201,33 @@ public:
     bool peers_ready = false;
     bool peers_local = false;         // peers live in this process (comm_attach_local): nothing to IPC-close
     bool peer_access_enabled = false; // in-process peers: cudaDeviceEnablePeerAccess done for this engine's device
+    bool peers_vmm = false;           // cross-process peers mapped from imported VMM handles (multicast path), not cudaIpc
     float* peer_W[8] = {};            // every rank's W_T / H / exchange buffer (own pointers at [rank])
     float* peer_H[8] = {};
     double* peer_x[8] = {};
     DeviceBuffer<double> xbuf;        // data[2][world][ne_max] + flags[2][8] + sequence counter (kXchgTailWords)
     int xchg_ne_max = 0;
+    // NVSwitch multicast (NVLS) replication of the factors. mc_wanted is decided with the communicator (device support,
+    // RCPPML_B200_MC != 0): the factors are then VMM allocations. Once every rank has bound its W_T / H to the two
+    // multicast objects (mc_ready), the kernel that NORMALISES a freshly solved block (normalize_gram_*) writes it with
+    // multimem.st — one store per word lands in all N replicas through the switch — and the solve kernels stop pushing
+    // unicast copies; the "every rank re-normalises the peers' blocks" pass disappears with them.
+    bool mc_wanted = false, mc_ready = false;
+    MappedHandle mcW, mcH;            // the multicast objects mapped on this device
+    bool mc_owner = false;            // this engine created the multicast objects (it releases the handles last)
+    MappedHandle peer_map_W[8], peer_map_H[8];   // cross-process: the peers' physical allocations mapped here
+    int mc_export_fds[4] = {-1, -1, -1, -1};
+    void mc_decide();                                        // after rank / world are known
+    void mc_grant_local_access(const int* devices);          // in-process: every device of the group may access W_T / H
+    void mc_create(CUmemGenericAllocationHandle* hW, CUmemGenericAllocationHandle* hH, bool shareable);
+    void mc_add_device(CUmemGenericAllocationHandle hW, CUmemGenericAllocationHandle hH);
+    void mc_bind_and_map(CUmemGenericAllocationHandle hW, CUmemGenericAllocationHandle hH, bool owner);
+    void mc_close();
+    void comm_mc_export(char* blob128);                      // cross-process (one process per GPU)
+    void comm_mc_import(const char* all_blobs);
+    void comm_mc_bind();
+    void comm_mc_finish();
+    float* mc_alias(const float* replica_ptr) const;         // multicast address of a word of W_T / H (nullptr: not ready)
 
 private:
     cudaEvent_t ev_loop_begin = nullptr, ev_loop_end = nullptr;
@@ -229,7 +253,8 @@ private:
     bool side_pending = false;
     void join_side_stream();
     void collect_profile();
-    void gram(float* X, long long ncols, bool normalize, float* G_out, int sec, bool reduce_over_ranks = false);
+    void gram(float* X, long long ncols, bool normalize, float* G_out, int sec, bool reduce_over_ranks = false,
+              bool replicate = false);
     void normalize_peer_blocks(float* X, long long ncols, long long lo, long long hi, bool normalize);
     void loss(int sec);
     void allreduce_f64(double* buf, size_t count);

@@ -26,6 +26,13 @@ struct DevState {
     float train_loss;
 };
 
+// One 128-bit store into EVERY replica bound to the multicast object behind `mc` (NVSwitch multicast, NVLS): the
+// switch replicates the packet, the sender's NVLink egress carries it once.
+__device__ __forceinline__ void multimem_store4(float4* mc, const float4& v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // normalize + Gram. X is [ncols][KP] (row c = column c of the reference's k×ncols matrix).
 // G is symmetric: of the 16×16 grid of R×R tiles (R = KP/16) only the lower triangle is needed. A warp owns
@@ -41,7 +48,7 @@ template <int KP, int TC>
 static __global__ void __launch_bounds__(kGramThreads) normalize_gram_kernel(float* __restrict__ X, long long ncols,
                                                              const float* __restrict__ d, int normalize,
                                                              double* __restrict__ partials,
-                                                             const int* __restrict__ stop_flag) {
+                                                             const int* __restrict__ stop_flag, float* __restrict__ mcX) {
     constexpr int R = KP / 16;
     constexpr int V4 = KP / 4;                       // float4 per column
     constexpr int ROWD = KP + (KP / 16) * 2;         // doubles per staged row incl. padding (2 doubles per 16)
@@ -88,8 +95,11 @@ static __global__ void __launch_bounds__(kGramThreads) normalize_gram_kernel(flo
                     v.y = __fdiv_rn(v.y, sD[q * 4 + 1]);
                     v.z = __fdiv_rn(v.z, sD[q * 4 + 2]);
                     v.w = __fdiv_rn(v.w, sD[q * 4 + 3]);
-                    X4[t] = v;
+                    if (!mcX) X4[t] = v;
                 }
+                // sharded fits with multicast-bound factors: the (normalised) block goes into ALL replicas, this rank's
+                // included, with one store per word
+                if (mcX) multimem_store4(reinterpret_cast<float4*>(mcX + c0 * KP) + t, v);
             }
             pre[u] = v;
         }
@@ -152,7 +162,7 @@ template <> struct GramMmaGeom<128> { static constexpr int WARPS = 8, TPW = 17; 
 template <int KP, int TC>
 static __global__ void __launch_bounds__(GramMmaGeom<KP>::WARPS * 32) normalize_gram_mma_kernel(
     float* __restrict__ X, long long ncols, const float* __restrict__ d, int normalize, double* __restrict__ partials,
-    const int* __restrict__ stop_flag) {
+    const int* __restrict__ stop_flag, float* __restrict__ mcX) {
     constexpr int WARPS = GramMmaGeom<KP>::WARPS, TPW = GramMmaGeom<KP>::TPW, THREADS = WARPS * 32;
     constexpr int NT = KP / 8;
     static_assert(WARPS * TPW == NT * (NT + 1) / 2, "tiles of the lower triangle must split evenly over the warps");
@@ -202,8 +212,11 @@ static __global__ void __launch_bounds__(GramMmaGeom<KP>::WARPS * 32) normalize_
                     v.y = __fdiv_rn(v.y, sD[q * 4 + 1]);
                     v.z = __fdiv_rn(v.z, sD[q * 4 + 2]);
                     v.w = __fdiv_rn(v.w, sD[q * 4 + 3]);
-                    X4[t] = v;
+                    if (!mcX) X4[t] = v;
                 }
+                // sharded fits with multicast-bound factors: the (normalised) block goes into ALL replicas, this rank's
+                // included, with one store per word
+                if (mcX) multimem_store4(reinterpret_cast<float4*>(mcX + c0 * KP) + t, v);
             }
             pre[u] = v;
         }

@@ -273,22 +273,51 @@ class Engine:
         _lib.check(self._lib.rcppml_b200_comm_init(self._h, rank, world, unique_id), "comm_init")
 
     def comm_enable_p2p(self, dist) -> bool:
-        """Peer-memory fast path (include/rcppml_gpu.h: comm_ipc_export/import). `dist` is an initialised
-        torch.distributed (only used to all-gather the 192-byte IPC handle triples). Call on every rank after
-        the factors exist. Returns False (and leaves the NCCL path active) when RCPPML_B200_P2P=0."""
+        """Peer-memory fast path (include/rcppml_gpu.h). `dist` is an initialised torch.distributed (only used to
+        all-gather the per-rank handle blobs). Call on every rank after the factors exist. Two flavours, chosen by the
+        library at comm_init: NVSwitch MULTICAST (comm_mc_export/import: the factors are VMM allocations bound to
+        multicast objects; a normalised block is written into every replica with one multimem.st per word) where the
+        devices support it and RCPPML_B200_MC != 0, else unicast peer stores over CUDA IPC mappings
+        (comm_ipc_export/import). Returns False (and leaves the NCCL loop active) when RCPPML_B200_P2P=0 or the
+        set-up failed on any rank."""
         import os
         import torch
+        self.p2p_mode = "nccl"
         if os.environ.get("RCPPML_B200_P2P", "1") == "0":
             return False
         world = dist.get_world_size()
+        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+
+        def all_ok(rc):
+            t = torch.tensor([1 if rc == 0 else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            return bool(t.item() == 1)
+
+        def gather(raw):
+            mine = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
+            allb = torch.empty(world * len(raw), dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(allb, mine)
+            return allb.cpu().numpy().tobytes()
+
+        if self._lib.rcppml_b200_comm_mc_wanted(self._h):
+            buf = C.create_string_buffer(128)
+            ok = all_ok(self._lib.rcppml_b200_comm_mc_export(self._h, buf))
+            if ok:
+                ok = all_ok(self._lib.rcppml_b200_comm_mc_import(self._h, gather(buf.raw)))
+            if ok:                                           # every device joined: binding cannot block any more
+                ok = all_ok(self._lib.rcppml_b200_comm_mc_bind(self._h))
+            dist.barrier()                                   # every rank duplicated the descriptors it needs
+            self._lib.rcppml_b200_comm_mc_finish(self._h)
+            if ok:
+                self.p2p_mode = "multicast"
+                return True
+            self._lib.rcppml_b200_comm_p2p_close(self._h)   # (VMM factors cannot go through CUDA IPC: NCCL loop)
+            return False
         buf = C.create_string_buffer(192)
         _lib.check(self._lib.rcppml_b200_comm_ipc_export(self._h, buf), "comm_ipc_export")
-        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
-        mine = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).to(dev)
-        allh = torch.empty(world * 192, dtype=torch.uint8, device=dev)
-        dist.all_gather_into_tensor(allh, mine)
-        _lib.check(self._lib.rcppml_b200_comm_ipc_import(self._h, allh.cpu().numpy().tobytes()), "comm_ipc_import")
+        _lib.check(self._lib.rcppml_b200_comm_ipc_import(self._h, gather(buf.raw)), "comm_ipc_import")
         dist.barrier()
+        self.p2p_mode = "unicast"
         return True
 
 

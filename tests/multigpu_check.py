@@ -33,9 +33,12 @@ def main():
     # every case with the peer-memory loop (no NCCL call inside the iteration) and with the NCCL loop
     # ... and the peer-memory loop once more with the tiled kernels forced (kernels_tiled.cuh stores whole rows into
     # the peer replicas; the default policy keeps operands this thin on the one-geometry kernels)
-    combos = [(a, b, "1") for a in (True, False) for b in cases] + [(True, b, "2") for b in cases]
+    # p2p: "mc" = NVSwitch multicast replication (multimem.st from the normalising Gram kernel), "uc" = unicast peer stores
+    # from the solve kernels (RCPPML_B200_MC=0), False = NCCL loop
+    combos = [(a, b, "1") for a in ("mc", "uc", False) for b in cases] + [(a, b, "2") for a in ("mc", "uc") for b in cases]
     for p2p, (k, solver, kw), tiled in combos:
         os.environ["RCPPML_B200_TILED"] = tiled
+        os.environ["RCPPML_B200_MC"] = "0" if p2p == "uc" else "1"
         iters = 4
         eng = rb.Engine(local)
         uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
@@ -55,6 +58,9 @@ def main():
         eng.init_factors(k, 42, 0)
         if p2p:
             assert eng.comm_enable_p2p(dist), "peer-memory path not enabled"
+            mode = eng.p2p_mode
+        else:
+            mode = "nccl"
         cfg = rb.make_config(k, max_iter=iters, tol=0.0, solver_mode=solver, **kw)
         res = eng.fit(cfg)
         W, H, d = eng.get_factors()
@@ -81,7 +87,7 @@ def main():
         exact = bool(np.array_equal(W, W1) and np.array_equal(H, H1) and np.array_equal(d, d1))
         worst = max(worst, *errs.values())
         if rank == 0:
-            print(f"k={k} solver={solver} world={world} p2p={p2p} tiled={tiled}: bit-identical={exact} {errs}", flush=True)
+            print(f"k={k} solver={solver} world={world} p2p={p2p} ({mode}) tiled={tiled}: bit-identical={exact} {errs}", flush=True)
         assert max(errs.values()) <= 1e-5, errs
     if True:
         # block-wise factor I/O: a fit started from set_factor_blocks equals one started from set_factors, bit for bit,
@@ -152,7 +158,8 @@ def main():
         ref_c = one.get_factors() + (cv1["test_history"], cv1["train_history"])
         n_test1 = cv1["n_test"]
         one.close()
-        for p2p in (True, False):
+        for p2p in ("mc", "uc", False):
+            os.environ["RCPPML_B200_MC"] = "0" if p2p == "uc" else "1"
             e = sharded_engine(p2p)
             e.set_mask(*mask)
             e.init_factors(k, 42, 0)
@@ -180,6 +187,7 @@ def main():
             if rank == 0:
                 print(f"cv k={k} solver={solver} world={world} p2p={p2p}: bit-identical={exact} n_test={cv['n_test']} max_rel_err={max(errs):.2e}", flush=True)
             e.close()
+    os.environ.pop("RCPPML_B200_MC", None)
     dist.barrier()
     if rank == 0:
         print(f"MULTIGPU_CHECK_OK world={world} worst_rel_err={worst:.3e}", flush=True)

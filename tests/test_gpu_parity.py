@@ -634,6 +634,7 @@ def test_in_process_multi_gpu_behind_the_reference_entry_is_bit_identical():
 import os, sys, numpy as np
 sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
 import rcppml_b200 as rb
+from rcppml_b200 import _lib
 from helpers import random_csc
 for (m, n, k, solver, kw) in [(900, 500, 16, 0, {}), (1201, 777, 64, 1, dict(L1=(0.01, 0.02), L2=(0.0, 0.01))), (640, 333, 8, 1, dict(upper_bound=(0.2, 0.3)))]:
     A = random_csc(m, n, 0.05, 5 + k, ragged=True)
@@ -641,11 +642,17 @@ for (m, n, k, solver, kw) in [(900, 500, 16, 0, {}), (1201, 777, 64, 1, dict(L1=
     W0, H0 = rng.random((m, k)), rng.random((n, k))
     os.environ.pop("RCPPML_NUM_GPUS", None)
     one = rb.bridge_nmf_sparse(A.indptr, A.indices, A.data, m, n, k, W0, H0, max_iter=7, tol=0.0, solver_mode=solver, **kw)
-    for G in ("2", "all"):
+    # RCPPML_B200_MC: NVSwitch multicast replication ("1", where supported) / unicast peer stores ("0"); the engines
+    # behind the entry point are cached, so the cache is dropped when the mode changes
+    for G, mc in (("2", "1"), ("all", "1"), ("2", "0"), ("all", "0")):
         os.environ["RCPPML_NUM_GPUS"] = G
+        os.environ["RCPPML_B200_MC"] = mc
+        _lib.load().rcppml_b200_release_cache()
         many = rb.bridge_nmf_sparse(A.indptr, A.indices, A.data, m, n, k, W0, H0, max_iter=7, tol=0.0, solver_mode=solver, **kw)
-        assert one.status == 0 and many.status == 0, (G, one.status, many.status)
-        assert np.array_equal(one.W_T, many.W_T) and np.array_equal(one.H, many.H) and np.array_equal(one.d, many.d), (G, m, n, k)
+        many2 = rb.bridge_nmf_sparse(A.indptr, A.indices, A.data, m, n, k, W0, H0, max_iter=7, tol=0.0, solver_mode=solver, **kw)
+        assert one.status == 0 and many.status == 0 and many2.status == 0, (G, mc, one.status, many.status, many2.status)
+        assert np.array_equal(one.W_T, many.W_T) and np.array_equal(one.H, many.H) and np.array_equal(one.d, many.d), (G, mc, m, n, k)
+        assert np.array_equal(many2.W_T, many.W_T) and np.array_equal(many2.H, many.H), "second call on the cached engines differs"
         # (tr(AtA) is summed per device, then over devices: the loss may differ in its last bit, the factors may not)
         assert one.iterations == many.iterations and abs(one.train_loss - many.train_loss) <= 1e-6 * abs(one.train_loss)
 print("INPROCESS_MULTIGPU_OK")
