@@ -143,6 +143,22 @@ void balanced_col_cuts(const int* col_ptr, int n, int G, int per_item, int* cuts
 // when the next call asks for the same devices; any failure drops them. Guarded by g_mu.
 std::vector<std::unique_ptr<b200::Engine>> g_multi;
 std::vector<int> g_multi_devices;
+// The two multicast objects (W_T, H) of the cached in-process group: created by device 0's thread, shared by all
+// engines, released here once every engine has unbound (engine destruction or mc_close).
+CUmemGenericAllocationHandle g_mc_handles[2] = {0, 0};
+bool g_mc_valid = false;
+void release_group_multicast() {
+    if (!g_mc_valid) return;
+    const b200::DriverApi& drv = b200::DriverApi::get();
+    if (drv.ok) { drv.MemRelease(g_mc_handles[0]); drv.MemRelease(g_mc_handles[1]); }
+    g_mc_handles[0] = g_mc_handles[1] = 0;
+    g_mc_valid = false;
+}
+void drop_group() {                                            // engines first (they unmap / unbind), then the objects
+    g_multi.clear();
+    g_multi_devices.clear();
+    release_group_multicast();
+}
 
 // Returns false (after warn) on any failure; fills res / W / H / d on success. Caller holds g_mu.
 bool fit_in_process_multi_gpu(int G, const int* devices, int m, int n, int64_t nnz, const int* col_ptr, const int* row_idx,
@@ -152,7 +168,7 @@ bool fit_in_process_multi_gpu(int G, const int* devices, int m, int n, int64_t n
     const char* env = std::getenv("RCPPML_B200_CACHE");
     const bool cache = !(env && env[0] == '0');
     if (!(cache && static_cast<int>(g_multi.size()) == G && g_multi_devices == std::vector<int>(devices, devices + G))) {
-        g_multi.clear();
+        drop_group();
         g_multi.resize(G);
         g_multi_devices.assign(devices, devices + G);
     }
@@ -167,8 +183,6 @@ bool fit_in_process_multi_gpu(int G, const int* devices, int m, int n, int64_t n
     std::vector<rcppml_b200_result> rr(G);
     std::vector<std::string> err(G);
     PhaseBarrier bar(G);
-    CUmemGenericAllocationHandle mc_handles[2] = {0, 0};
-    bool mc_created = false;
     double marks[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};        // rank 0's wall clock at the phase boundaries (ms)
     auto since = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count(); };
 
@@ -201,19 +215,28 @@ bool fit_in_process_multi_gpu(int G, const int* devices, int m, int n, int64_t n
         E.comm_attach_local(all.data());
         // NVSwitch multicast (vmm.hpp): device 0's thread creates the two multicast objects, every device joins, binds
         // its replicas and maps them — from then on a normalised block is written once and lands in all replicas
-        bool want_mc = true;
-        for (int r = 0; r < G; ++r) want_mc = want_mc && all[r]->mc_wanted && all[r]->W_T.vmm && all[r]->H.vmm;
-        if (want_mc) {
+        bool want_mc = true, have_mc = true;
+        for (int r = 0; r < G; ++r) {
+            want_mc = want_mc && all[r]->mc_wanted && all[r]->W_T.vmm && all[r]->H.vmm;
+            have_mc = have_mc && all[r]->mc_ready;
+        }
+        if (!bar.wait()) return;                                             // F: every thread sampled the same state
+        if (want_mc && !have_mc) {                                           // (a cached group keeps its mappings)
+            E.mc_close();
+            if (!bar.wait()) return;                                         // E0: nobody is bound to the old objects
             if (g == 0) {
-                try { E.mc_create(&mc_handles[0], &mc_handles[1], false); mc_created = true; }
+                release_group_multicast();
+                try { E.mc_create(&g_mc_handles[0], &g_mc_handles[1], false); g_mc_valid = true; }
                 catch (const std::exception& ex) { warn((std::string("multicast unavailable, unicast peer stores instead: ") + ex.what()).c_str()); }
             }
             if (!bar.wait()) return;                                         // E1: the objects exist (or not)
-            if (mc_created) {
-                E.mc_add_device(mc_handles[0], mc_handles[1]);
+            if (g_mc_valid) {
+                E.mc_add_device(g_mc_handles[0], g_mc_handles[1]);
                 if (!bar.wait()) return;                                     // E2: every device joined
-                E.mc_bind_and_map(mc_handles[0], mc_handles[1], g == 0);
+                E.mc_bind_and_map(g_mc_handles[0], g_mc_handles[1], g == 0);
             }
+        } else if (!want_mc && E.mc_ready) {
+            E.mc_close();
         }
         E.pull_factor_blocks_from_peers();
         if (g == 0) marks[2] = since();
@@ -271,10 +294,7 @@ bool fit_in_process_multi_gpu(int G, const int* devices, int m, int n, int64_t n
         cudaSetDevice(devices[g]);
         cudaDeviceSynchronize();
     }
-    if (!ok || !cache) {                                       // never reuse engines in an unknown state
-        g_multi.clear();
-        g_multi_devices.clear();
-    }
+    if (!ok || !cache) drop_group();                           // never reuse engines in an unknown state
     cudaSetDevice(devices[0]);
     if (std::getenv("RCPPML_B200_TRACE"))
         std::fprintf(stderr, "[RcppML_gpu/b200] multi-GPU call (G=%d, %s), rank-0 wall clock ms: col blocks up %.2f | row blocks %.2f | "
@@ -694,8 +714,7 @@ static void nmf_unified_impl(
 int rcppml_b200_release_cache(void) {
     std::lock_guard<std::mutex> g(g_mu);
     g_engine.reset();
-    g_multi.clear();
-    g_multi_devices.clear();
+    drop_group();
     return 0;
 }
 // Host wall-clock (ms) of the phases of the last reference-ABI call: matrix upload (+fp64->fp32), device

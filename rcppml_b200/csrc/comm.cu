@@ -136,6 +136,7 @@ void Engine::mc_bind_and_map(CUmemGenericAllocationHandle hW, CUmemGenericAlloca
     use_device();
     const DriverApi& drv = DriverApi::get();
     mc_owner = owner;
+    mc_local = peers_local;
     mcW.handle = hW; mcW.size = W_T.phys_size; mcW.device = device;
     mcH.handle = hH; mcH.size = H.phys_size; mcH.device = device;
     B200_CU_CHECK(drv.MulticastBindMem(hW, 0, W_T.phys, 0, W_T.phys_size, 0));
@@ -151,9 +152,10 @@ void Engine::mc_bind_and_map(CUmemGenericAllocationHandle hW, CUmemGenericAlloca
 void Engine::mc_close() {
     if (!mcW.handle && !mcH.handle) { mc_ready = false; return; }
     cudaSetDevice(device);
-    // in-process groups share one handle: only the creator releases it (after its own unmap / unbind)
-    mcW.release(mc_owner || !peers_local);
-    mcH.release(mc_owner || !peers_local);
+    // in-process groups share one handle per factor, owned by the orchestrator (abi_reference.cu): an engine only
+    // unmaps and unbinds. Cross-process: every rank holds its own (created or imported) handle and releases it.
+    mcW.release(!mc_local);
+    mcH.release(!mc_local);
     mc_ready = false;
     mc_owner = false;
 }
@@ -301,7 +303,9 @@ void Engine::enable_peer_access(const int* devices) {
 void Engine::comm_prepare_local(const int* devices) {
     use_device();
     B200_REQUIRE(world > 1 && factors_ready, "comm_prepare_local: needs comm_init_local and allocated factors");
-    comm_ipc_close();
+    // (a cached in-process group keeps its peer pointers and multicast mappings from call to call: alloc_factors
+    // closes them when a buffer moved, comm_attach_local refreshes the pointers)
+    if (!peers_local) comm_ipc_close();
     enable_peer_access(devices);
     mc_grant_local_access(devices);
     xchg_ne_max = KP * KP;

@@ -286,6 +286,8 @@ void Engine::init_device_objects() {
 Engine::~Engine() {
     cudaSetDevice(device);
     cudaStreamSynchronize(stream);
+    cudaStreamSynchronize(side_stream);
+    comm_destroy();                                       // peer / multicast mappings go first (needs both streams alive)
     if (iter_graph) cudaGraphExecDestroy(iter_graph);
     for (auto& sec : prof_events)
         for (auto& pr : sec) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
@@ -296,7 +298,6 @@ Engine::~Engine() {
     cudaEventDestroy(ev_loop_begin);
     cudaEventDestroy(ev_loop_end);
     if (h_state) cudaFreeHost(h_state);
-    comm_destroy();
     cudaStreamDestroy(stream);
     std::lock_guard<std::mutex> g(g_slot_mu);
     if (const_slot >= 0) g_slot_used[device][const_slot] = false;

@@ -214,7 +214,8 @@ public:
     // unicast copies; the "every rank re-normalises the peers' blocks" pass disappears with them.
     bool mc_wanted = false, mc_ready = false;
     MappedHandle mcW, mcH;            // the multicast objects mapped on this device
-    bool mc_owner = false;            // this engine created the multicast objects (it releases the handles last)
+    bool mc_owner = false;            // this engine created the multicast objects
+    bool mc_local = false;            // in-process group: the handles are shared and owned by the orchestrator
     MappedHandle peer_map_W[8], peer_map_H[8];   // cross-process: the peers' physical allocations mapped here
     int mc_export_fds[4] = {-1, -1, -1, -1};
     void mc_decide();                                        // after rank / world are known
