@@ -75,6 +75,7 @@ void Engine::mc_decide() {
     if (world <= 1) return;
     const char* env = std::getenv("RCPPML_B200_MC");
     if (env && env[0] == '0') return;
+    mc_mode = (env && env[0] == '1') ? 1 : 2;
     if (!multicast_supported(device)) return;
     try {
         const size_t g = multicast_granularity(world);

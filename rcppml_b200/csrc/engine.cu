@@ -1106,7 +1106,10 @@ HalfStepParams Engine::solve_params(int which, bool warm) const {
     p.stop_flag = &state.ptr->stop;
     p.sweep_counter = sweep_counter.ptr;
     p.npeers = 0;
-    if (peers_ready && !mc_ready) {                     // multicast mode: the normalising Gram kernel replicates the block
+    p.mcX = nullptr;
+    if (peers_ready && mc_ready) {                      // multicast: mode 1 — the normalising Gram kernel replicates the
+        if (mc_mode == 2) p.mcX = mc_alias(p.X);        // block; mode 2 — this kernel's stores go through the multicast alias
+    } else if (peers_ready) {
         for (int r = 0; r < world; ++r)
             if (r != rank) p.peerX[p.npeers++] = h ? peer_H[r] : peer_W[r];
     }
@@ -1285,8 +1288,9 @@ void Engine::enqueue_iteration() {
     // other GPUs' copies while they run, the small all-reduces are one-shot peer-memory kernels, and each
     // rank normalises the whole replicated factor locally: no NCCL call in the loop, no exposed all-gather.
     const bool p2p = sharded && peers_ready;
-    const bool ucast = p2p && !mc_ready;                                    // unicast peer stores + local re-normalisation
-    const bool repl = p2p && mc_ready;                                      // multicast replication by the Gram kernel
+    const bool repl = p2p && mc_ready && mc_mode == 1;                      // multicast replication by the Gram kernel
+    const bool ucast = p2p && !repl;                                        // the solve kernel replicates (unicast peer stores or
+                                                                            // multicast), every rank re-normalises the peers' blocks
     float* Hblk = H.ptr + static_cast<size_t>(col_begin) * KP;
     float* Wblk = W_T.ptr + static_cast<size_t>(row_begin) * KP;
     // ---- H update (fit_cpu.hpp:488-645). The Gram of W_T and the solver operands built from it are produced at the END
@@ -1384,9 +1388,13 @@ void Engine::masked_solve(int which, bool warm, const float* G, int sec) {
     p.ncols = h ? n_loc : m_loc;
     p.col_offset = h ? col_begin : row_begin;
     p.npeers = 0;
-    if (peers_ready && !mc_ready)
+    p.mcX = nullptr;
+    if (peers_ready && mc_ready) {
+        if (mc_mode == 2) p.mcX = mc_alias(p.X);
+    } else if (peers_ready) {
         for (int r = 0; r < world; ++r)
             if (r != rank) p.peerX[p.npeers++] = h ? peer_H[r] : peer_W[r];
+    }
     p.k = k;
     p.L1 = h ? cfg.L1_H : cfg.L1_W;
     p.L2 = h ? cfg.L2_H : cfg.L2_W;
@@ -1421,8 +1429,9 @@ void Engine::enqueue_iteration_masked() {
     const bool normalize = cfg.norm_type != 2;
     const bool sharded = world > 1;
     const bool p2p = sharded && peers_ready;
-    const bool ucast = p2p && !mc_ready;                                    // unicast peer stores + local re-normalisation
-    const bool repl = p2p && mc_ready;                                      // multicast replication by the Gram kernel
+    const bool repl = p2p && mc_ready && mc_mode == 1;                      // multicast replication by the Gram kernel
+    const bool ucast = p2p && !repl;                                        // the solve kernel replicates (unicast peer stores or
+                                                                            // multicast), every rank re-normalises the peers' blocks
     float* Hblk = H.ptr + static_cast<size_t>(col_begin) * KP;
     float* Wblk = W_T.ptr + static_cast<size_t>(row_begin) * KP;
     if (iters_enqueued == 0) gram(Wblk, m_loc, false, G_w.ptr, RCPPML_B200_SEC_GRAM_H, sharded);   // :562 rebuilt unmodified
@@ -1469,9 +1478,13 @@ void Engine::cv_solve(int which, int sec) {
     p.nrows = h ? m : n;
     p.col_offset = h ? col_begin : row_begin;
     p.npeers = 0;
-    if (peers_ready && !mc_ready)
+    p.mcX = nullptr;
+    if (peers_ready && mc_ready) {
+        if (mc_mode == 2) p.mcX = mc_alias(p.X);
+    } else if (peers_ready) {
         for (int r = 0; r < world; ++r)
             if (r != rank) p.peerX[p.npeers++] = h ? peer_H[r] : peer_W[r];
+    }
     p.k = k;
     p.transposed = h ? 0 : 1;
     p.mask_zeros = cv.mask_zeros;
@@ -1503,8 +1516,9 @@ void Engine::enqueue_iteration_cv() {
     const bool normalize = cfg.norm_type != 2;
     const bool sharded = world > 1;
     const bool p2p = sharded && peers_ready;
-    const bool ucast = p2p && !mc_ready;                                    // unicast peer stores + local re-normalisation
-    const bool repl = p2p && mc_ready;                                      // multicast replication by the Gram kernel
+    const bool repl = p2p && mc_ready && mc_mode == 1;                      // multicast replication by the Gram kernel
+    const bool ucast = p2p && !repl;                                        // the solve kernel replicates (unicast peer stores or
+                                                                            // multicast), every rank re-normalises the peers' blocks
     float* Hblk = H.ptr + static_cast<size_t>(col_begin) * KP;
     float* Wblk = W_T.ptr + static_cast<size_t>(row_begin) * KP;
     const int ge = (KP * KP + 255) / 256;

@@ -213,6 +213,9 @@ public:
     // multimem.st — one store per word lands in all N replicas through the switch — and the solve kernels stop pushing
     // unicast copies; the "every rank re-normalises the peers' blocks" pass disappears with them.
     bool mc_wanted = false, mc_ready = false;
+    int mc_mode = 2;                  // 1: the normalising Gram kernel writes the block into every replica (no peer-side
+                                      // re-normalisation); 2: the solve kernel's stores go through the multicast alias
+                                      // (overlapped with the solve; peers re-normalise as with unicast). RCPPML_B200_MC.
     MappedHandle mcW, mcH;            // the multicast objects mapped on this device
     bool mc_owner = false;            // this engine created the multicast objects
     bool mc_local = false;            // in-process group: the handles are shared and owned by the orchestrator

@@ -57,6 +57,7 @@ struct CvParams {
     int col_offset;
     float* peerX[7];
     int npeers;
+    float* mcX;                        // multicast alias of X (see HalfStepParams::mcX); nullptr: local store
 };
 
 template <int KP>
@@ -200,7 +201,8 @@ __global__ void __launch_bounds__(384, 1) cv_half_step_kernel(const CvParams p) 
                 float v = (c < k) ? x[t] : 0.f;
                 if (p.ub > 0.f) v = fminf(v, p.ub);                 // fit_cv.hpp:528 / :843 (post-hoc)
                 x[t] = v;
-                xcol[c] = v;
+                if (p.mcX) multimem_store1(p.mcX + static_cast<size_t>(jg) * KP + c, v);
+                else xcol[c] = v;
                 for (int q2 = 0; q2 < p.npeers; ++q2) p.peerX[q2][static_cast<size_t>(jg) * KP + c] = v;
                 if (p.norm_type == 0) rs[t] += static_cast<double>(fabsf(v));
                 else if (p.norm_type == 1) rs[t] += static_cast<double>(v) * static_cast<double>(v);

@@ -33,6 +33,10 @@ __device__ __forceinline__ void multimem_store4(float4* mc, const float4& v) {
                  : "memory");
 }
 
+__device__ __forceinline__ void multimem_store1(float* mc, float v) {
+    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(mc), "f"(v) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // normalize + Gram. X is [ncols][KP] (row c = column c of the reference's k×ncols matrix).
 // G is symmetric: of the 16×16 grid of R×R tiles (R = KP/16) only the lower triangle is needed. A warp owns

@@ -35,10 +35,12 @@ def main():
     # the peer replicas; the default policy keeps operands this thin on the one-geometry kernels)
     # p2p: "mc" = NVSwitch multicast replication (multimem.st from the normalising Gram kernel), "uc" = unicast peer stores
     # from the solve kernels (RCPPML_B200_MC=0), False = NCCL loop
-    combos = [(a, b, "1") for a in ("mc", "uc", False) for b in cases] + [(a, b, "2") for a in ("mc", "uc") for b in cases]
+    # (RCPPML_B200_MC: 1 = the Gram kernel replicates the normalised block, 2 = the solve kernel's stores are multicast)
+    MC_ENV = {"mc": "1", "mc2": "2", "uc": "0", False: "0"}
+    combos = [(a, b, "1") for a in ("mc", "mc2", "uc", False) for b in cases] + [(a, b, "2") for a in ("mc2", "uc") for b in cases]
     for p2p, (k, solver, kw), tiled in combos:
         os.environ["RCPPML_B200_TILED"] = tiled
-        os.environ["RCPPML_B200_MC"] = "0" if p2p == "uc" else "1"
+        os.environ["RCPPML_B200_MC"] = MC_ENV[p2p]
         iters = 4
         eng = rb.Engine(local)
         uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
@@ -158,8 +160,8 @@ def main():
         ref_c = one.get_factors() + (cv1["test_history"], cv1["train_history"])
         n_test1 = cv1["n_test"]
         one.close()
-        for p2p in ("mc", "uc", False):
-            os.environ["RCPPML_B200_MC"] = "0" if p2p == "uc" else "1"
+        for p2p in ("mc", "mc2", "uc", False):
+            os.environ["RCPPML_B200_MC"] = MC_ENV[p2p]
             e = sharded_engine(p2p)
             e.set_mask(*mask)
             e.init_factors(k, 42, 0)

@@ -642,9 +642,10 @@ for (m, n, k, solver, kw) in [(900, 500, 16, 0, {}), (1201, 777, 64, 1, dict(L1=
     W0, H0 = rng.random((m, k)), rng.random((n, k))
     os.environ.pop("RCPPML_NUM_GPUS", None)
     one = rb.bridge_nmf_sparse(A.indptr, A.indices, A.data, m, n, k, W0, H0, max_iter=7, tol=0.0, solver_mode=solver, **kw)
-    # RCPPML_B200_MC: NVSwitch multicast replication ("1", where supported) / unicast peer stores ("0"); the engines
+    # RCPPML_B200_MC: NVSwitch multicast replication ("2": from the solve kernel, "1": from the Gram kernel; where
+    # supported) / unicast peer stores ("0"); the engines
     # behind the entry point are cached, so the cache is dropped when the mode changes
-    for G, mc in (("2", "1"), ("all", "1"), ("2", "0"), ("all", "0")):
+    for G, mc in (("2", "2"), ("all", "2"), ("2", "1"), ("all", "1"), ("2", "0"), ("all", "0")):
         os.environ["RCPPML_NUM_GPUS"] = G
         os.environ["RCPPML_B200_MC"] = mc
         _lib.load().rcppml_b200_release_cache()
