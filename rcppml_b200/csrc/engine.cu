@@ -269,8 +269,14 @@ void Engine::init_device_objects() {
     cudaDeviceProp prop{};
     B200_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
     num_sms = prop.multiProcessorCount;
-    B200_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-    B200_CUDA_CHECK(cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking));
+    // The main stream carries the critical path (solve -> exchange -> Gram -> exchange -> LLT); the side stream only
+    // re-normalises the peers' blocks of a replicated factor (pure HBM streaming with a machine-filling grid). With
+    // priorities the Gram kernel's CTAs are placed first and the streaming kernel fills what is left, instead of the
+    // Gram waiting for a full wave of it (N = 8: the "loss" section was 0.19 ms of a 1.14 ms iteration).
+    int prio_lo = 0, prio_hi = 0;
+    B200_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));     // lo = least (numerically greatest)
+    B200_CUDA_CHECK(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, prio_hi));
+    B200_CUDA_CHECK(cudaStreamCreateWithPriority(&side_stream, cudaStreamNonBlocking, prio_lo));
     B200_CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
     B200_CUDA_CHECK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
     B200_CUDA_CHECK(cudaEventCreate(&ev_loop_begin));
@@ -985,9 +991,18 @@ void Engine::normalize_cfg(const rcppml_b200_config& c) {
 // Runs on the side stream, forked after `d` is final and joined before the next solve kernel gathers from X:
 // it overlaps with the Gram of the own block, the small all-reduces and the solver set-up on the main stream
 // (those touch only this rank's block of X and k x k data).
-void Engine::normalize_peer_blocks(float* X, long long ncols, long long lo, long long hi, bool normalize) {
-    if (!normalize || ncols == hi - lo) return;
+void Engine::fork_side_stream() {
     B200_CUDA_CHECK(cudaEventRecord(ev_fork, stream));
+    side_forked = true;
+}
+
+// Enqueued AFTER the main-stream work it overlaps with (fork_side_stream marks the point in the main stream it
+// depends on), so that the main stream's kernels reach the hardware queues first.
+void Engine::normalize_peer_blocks(float* X, long long ncols, long long lo, long long hi, bool normalize) {
+    const bool forked = side_forked;
+    side_forked = false;
+    if (!normalize || ncols == hi - lo) return;
+    if (!forked) B200_CUDA_CHECK(cudaEventRecord(ev_fork, stream));
     B200_CUDA_CHECK(cudaStreamWaitEvent(side_stream, ev_fork, 0));
     sec_begin(RCPPML_B200_SEC_COMM, side_stream);
     scale_columns_kernel<<<num_sms * 8, 256, 0, side_stream>>>(X, ncols, KP, d.ptr, lo, hi, &state.ptr->stop);
@@ -1304,19 +1319,21 @@ void Engine::enqueue_iteration() {
     solve(0, warm, RCPPML_B200_SEC_SOLVE_H);                                // :516-535 (+ :636 upper bound)
     scale_finalize(RCPPML_B200_SEC_SCALE_H, sharded);                       // :644 (p2p: also the barrier)
     // ---- W update (fit_cpu.hpp:713-893)
-    if (ucast) normalize_peer_blocks(H.ptr, n, col_begin, col_begin + n_loc, normalize);   // side stream
+    if (ucast) fork_side_stream();                                          // d is final from here on
     gram(Hblk, n_loc, normalize, G_h.ptr, RCPPML_B200_SEC_GRAM_W, sharded, repl); // :644 (normalise) + :715
+    if (ucast) normalize_peer_blocks(H.ptr, n, col_begin, col_begin + n_loc, normalize);   // side stream, behind the Gram in the queues
     if (sharded && !p2p) allgather_rows(H.ptr, col_cuts, n_pad, RCPPML_B200_SEC_COMM);
     prepare_solver(G_h.ptr, cfg.L2_W, RCPPML_B200_SEC_GRAM_W);              // :738
     join_side_stream();
     solve(1, warm, RCPPML_B200_SEC_SOLVE_W);                                // :748-767 (+ :884)
     scale_finalize(RCPPML_B200_SEC_SCALE_W, sharded);                       // :892
     // ---- loss (fit_cpu.hpp:1729-1809): Gram of the new W_T doubles as next iteration's gram_H
-    if (ucast) normalize_peer_blocks(W_T.ptr, m, row_begin, row_begin + m_loc, normalize);   // side stream
+    if (ucast) fork_side_stream();                                          // d is final from here on
     sec_begin(RCPPML_B200_SEC_LOSS);
     const bool was = profiling; profiling = false;                         // nested section: account under LOSS
     gram(Wblk, m_loc, normalize, G_w.ptr, RCPPML_B200_SEC_LOSS, sharded, repl);   // :892 (normalise) + :1735
     profiling = was;
+    if (ucast) normalize_peer_blocks(W_T.ptr, m, row_begin, row_begin + m_loc, normalize);   // side stream, behind the Gram in the queues
     loss(RCPPML_B200_SEC_LOSS);
     sec_end(RCPPML_B200_SEC_LOSS);
     if (sharded && !p2p) allgather_rows(W_T.ptr, row_cuts, m_pad, RCPPML_B200_SEC_COMM);
@@ -1438,17 +1455,19 @@ void Engine::enqueue_iteration_masked() {
     join_side_stream();
     masked_solve(0, warm, G_w.ptr, RCPPML_B200_SEC_SOLVE_H);
     scale_finalize(RCPPML_B200_SEC_SCALE_H, sharded);
-    if (ucast) normalize_peer_blocks(H.ptr, n, col_begin, col_begin + n_loc, normalize);
+    if (ucast) fork_side_stream();                                          // d is final from here on
     gram(Hblk, n_loc, normalize, G_h.ptr, RCPPML_B200_SEC_GRAM_W, sharded, repl);                       // :644 + :801
+    if (ucast) normalize_peer_blocks(H.ptr, n, col_begin, col_begin + n_loc, normalize);   // side stream, behind the Gram in the queues
     if (sharded && !p2p) allgather_rows(H.ptr, col_cuts, n_pad, RCPPML_B200_SEC_COMM);
     join_side_stream();
     masked_solve(1, warm, G_h.ptr, RCPPML_B200_SEC_SOLVE_W);
     scale_finalize(RCPPML_B200_SEC_SCALE_W, sharded);
-    if (ucast) normalize_peer_blocks(W_T.ptr, m, row_begin, row_begin + m_loc, normalize);
+    if (ucast) fork_side_stream();                                          // d is final from here on
     sec_begin(RCPPML_B200_SEC_LOSS);
     const bool was = profiling; profiling = false;
     gram(Wblk, m_loc, normalize, G_w.ptr, RCPPML_B200_SEC_LOSS, sharded, repl);                         // normalise + next gram_H
     profiling = was;
+    if (ucast) normalize_peer_blocks(W_T.ptr, m, row_begin, row_begin + m_loc, normalize);   // side stream, behind the Gram in the queues
     if (sharded && !p2p) allgather_rows(W_T.ptr, row_cuts, m_pad, RCPPML_B200_SEC_COMM);
     join_side_stream();                                                     // the loss reads every row of W_T
     const int lgrid = num_sms * 4;
@@ -1527,18 +1546,20 @@ void Engine::enqueue_iteration_cv() {
     join_side_stream();
     cv_solve(0, RCPPML_B200_SEC_SOLVE_H);                                                    // :431-476, :528
     scale_finalize(RCPPML_B200_SEC_SCALE_H, sharded);                                        // :536-548
-    if (ucast) normalize_peer_blocks(H.ptr, n, col_begin, col_begin + n_loc, normalize);
+    if (ucast) fork_side_stream();                                          // d is final from here on
     gram(Hblk, n_loc, normalize, G_h.ptr, RCPPML_B200_SEC_GRAM_W, sharded, repl);                  // :570 (= G_H_saved)
+    if (ucast) normalize_peer_blocks(H.ptr, n, col_begin, col_begin + n_loc, normalize);   // side stream, behind the Gram in the queues
     if (sharded && !p2p) allgather_rows(H.ptr, col_cuts, n_pad, RCPPML_B200_SEC_COMM);
     cv_prepare_gram_kernel<<<ge, 256, 0, stream>>>(G_h.ptr, KP, k, cfg.L2_W, M1.ptr, &state.ptr->stop);   // :578-581
     join_side_stream();
     cv_solve(1, RCPPML_B200_SEC_SOLVE_W);                                                    // :598-735, :843
     scale_finalize(RCPPML_B200_SEC_SCALE_W, sharded);                                        // :849-858 (+ cross term)
-    if (ucast) normalize_peer_blocks(W_T.ptr, m, row_begin, row_begin + m_loc, normalize);
+    if (ucast) fork_side_stream();                                          // d is final from here on
     sec_begin(RCPPML_B200_SEC_LOSS);
     const bool was = profiling; profiling = false;
     gram(Wblk, m_loc, normalize, G_w.ptr, RCPPML_B200_SEC_LOSS, sharded, repl);                    // normalise + :1518
     profiling = was;
+    if (ucast) normalize_peer_blocks(W_T.ptr, m, row_begin, row_begin + m_loc, normalize);   // side stream, behind the Gram in the queues
     if (sharded && !p2p) allgather_rows(W_T.ptr, row_cuts, m_pad, RCPPML_B200_SEC_COMM);
     join_side_stream();                                                     // the test loss reads every row of W_T
     const int lgrid = num_sms * 4;

@@ -254,7 +254,8 @@ private:
     void sec_end(int sec, cudaStream_t on = nullptr);
     cudaStream_t side_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    bool side_pending = false;
+    bool side_pending = false, side_forked = false;
+    void fork_side_stream();
     void join_side_stream();
     void collect_profile();
     void gram(float* X, long long ncols, bool normalize, float* G_out, int sec, bool reduce_over_ranks = false,
