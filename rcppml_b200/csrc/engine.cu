@@ -737,6 +737,8 @@ void Engine::alloc_factors(int k_) {
     if (const char* env = std::getenv("RCPPML_B200_TILED")) tiled_mode = std::atoi(env);
     tiled_min_batches = 0.5;
     if (const char* env = std::getenv("RCPPML_B200_TILED_MIN_BATCHES")) tiled_min_batches = std::atof(env);
+    side_ctas_per_sm = 2;
+    if (const char* env = std::getenv("RCPPML_B200_SIDE_CTAS")) side_ctas_per_sm = std::max(1, std::atoi(env));
     tiled_sl_override = 0;
     if (const char* env = std::getenv("RCPPML_B200_TILED_SL")) tiled_sl_override = std::atoi(env);
     narrow_min_cols = 8.0 * num_sms * 24;
@@ -1005,7 +1007,7 @@ void Engine::normalize_peer_blocks(float* X, long long ncols, long long lo, long
     if (!forked) B200_CUDA_CHECK(cudaEventRecord(ev_fork, stream));
     B200_CUDA_CHECK(cudaStreamWaitEvent(side_stream, ev_fork, 0));
     sec_begin(RCPPML_B200_SEC_COMM, side_stream);
-    scale_columns_kernel<<<num_sms * 8, 256, 0, side_stream>>>(X, ncols, KP, d.ptr, lo, hi, &state.ptr->stop);
+    scale_columns_kernel<<<num_sms * side_ctas_per_sm, 256, 0, side_stream>>>(X, ncols, KP, d.ptr, lo, hi, &state.ptr->stop);
     launches[RCPPML_B200_SEC_COMM] += 1;
     sec_end(RCPPML_B200_SEC_COMM, side_stream);
     B200_CUDA_CHECK(cudaEventRecord(ev_join, side_stream));

@@ -277,16 +277,30 @@ static __global__ void __launch_bounds__(256) scale_columns_kernel(float* __rest
     const int V4 = KP / 4;
     const long long head = lo * V4, skip = (hi - lo) * V4, total = (ncols - (hi - lo)) * V4;
     float4* X4 = reinterpret_cast<float4*>(X);
-    for (long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; t < total;
-         t += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const long long w = t < head ? t : t + skip;
-        const int q = static_cast<int>(w % V4);
-        float4 v = X4[w];
-        v.x = __fdiv_rn(v.x, sD[q * 4 + 0]);
-        v.y = __fdiv_rn(v.y, sD[q * 4 + 1]);
-        v.z = __fdiv_rn(v.z, sD[q * 4 + 2]);
-        v.w = __fdiv_rn(v.w, sD[q * 4 + 3]);
-        X4[w] = v;
+    // Few CTAs, four independent 128-bit loads in flight per thread: the kernel runs BESIDE the Gram chain of the main
+    // stream (it is on the low-priority side stream) and must leave it the issue slots — HBM streaming needs bytes in
+    // flight, not resident warps.
+    constexpr int UN = 4;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long t0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; t0 < total; t0 += stride * UN) {
+        float4 v[UN];
+        long long w[UN];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const long long t = t0 + u * stride;
+            w[u] = t < head ? t : t + skip;
+            if (t < total) v[u] = X4[w[u]];
+        }
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            if (t0 + u * stride >= total) break;
+            const int q = static_cast<int>(w[u] % V4);
+            v[u].x = __fdiv_rn(v[u].x, sD[q * 4 + 0]);
+            v[u].y = __fdiv_rn(v[u].y, sD[q * 4 + 1]);
+            v[u].z = __fdiv_rn(v[u].z, sD[q * 4 + 2]);
+            v[u].w = __fdiv_rn(v[u].w, sD[q * 4 + 3]);
+            X4[w[u]] = v[u];
+        }
     }
 }
 
