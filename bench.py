@@ -641,10 +641,10 @@ def main():
                    "solver_mode": mode, "solver": args.solver, "cd_maxit": 100, "L1": args.L1, "L2": args.L2,
                    "seed_A": SEED_A,
                    "seed_init": SEED_INIT,
-                   "parallelism": ((f"column blocks of H + row blocks of W over {world} GPUs; every normalised block is "
-                                    f"written into all replicas by the Gram kernel with NVSwitch multicast stores "
-                                    f"(multimem.st), one-shot peer-memory fp64 all-reduce of Grams/norms (no NCCL call in "
-                                    f"the loop)")
+                   "parallelism": ((f"column blocks of H + row blocks of W over {world} GPUs; solved columns stored into "
+                                    f"every replica by the solve kernel with NVSwitch multicast stores (multimem.st: one "
+                                    f"store per word, the switch replicates), one-shot peer-memory fp64 all-reduce of "
+                                    f"Grams/norms (no NCCL call in the loop)")
                                    if (p2p and getattr(eng, "p2p_mode", "") == "multicast") else
                                    (f"column blocks of H + row blocks of W over {world} GPUs; solved columns stored "
                                     f"into every replica over NVLink peer memory by the solve kernel, one-shot "

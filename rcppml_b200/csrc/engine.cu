@@ -737,7 +737,9 @@ void Engine::alloc_factors(int k_) {
     if (const char* env = std::getenv("RCPPML_B200_TILED")) tiled_mode = std::atoi(env);
     tiled_min_batches = 0.5;
     if (const char* env = std::getenv("RCPPML_B200_TILED_MIN_BATCHES")) tiled_min_batches = std::atof(env);
-    side_ctas_per_sm = 2;
+    // measured on 8 GPUs (profiles/r02k_bench_c4_n8*.json): 8 CTAs/SM 1.067 ms per iteration, 2 CTAs/SM 1.120 ms — the
+    // throttled kernel no longer fits under the Gram chain and the next solve waits for it
+    side_ctas_per_sm = 8;
     if (const char* env = std::getenv("RCPPML_B200_SIDE_CTAS")) side_ctas_per_sm = std::max(1, std::atoi(env));
     tiled_sl_override = 0;
     if (const char* env = std::getenv("RCPPML_B200_TILED_SL")) tiled_sl_override = std::atoi(env);

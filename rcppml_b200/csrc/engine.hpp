@@ -140,7 +140,7 @@ public:
     // for short columns (default), 2: always. RCPPML_B200_TILED overrides.
     int tiled_mode = 1;
     double tiled_min_batches = 0.5, narrow_min_cols = 0.0;
-    int side_ctas_per_sm = 2;               // grid of the peers' re-normalisation kernel (side stream), CTAs per SM
+    int side_ctas_per_sm = 8;               // grid of the peers' re-normalisation kernel (side stream), CTAs per SM
     int tiled_sl_override = 0;              // k = 64 tiled kernel: solve lanes per column (0: rule, 2: 16-column batches, 4: 8)
     bool use_narrow_cd(long long ncols) const;
     bool use_tiled(int solver, long long cnt, long long ncols) const;

@@ -277,9 +277,8 @@ static __global__ void __launch_bounds__(256) scale_columns_kernel(float* __rest
     const int V4 = KP / 4;
     const long long head = lo * V4, skip = (hi - lo) * V4, total = (ncols - (hi - lo)) * V4;
     float4* X4 = reinterpret_cast<float4*>(X);
-    // Few CTAs, four independent 128-bit loads in flight per thread: the kernel runs BESIDE the Gram chain of the main
-    // stream (it is on the low-priority side stream) and must leave it the issue slots — HBM streaming needs bytes in
-    // flight, not resident warps.
+    // Four independent 128-bit loads in flight per thread. The kernel runs BESIDE the Gram chain of the main stream, on
+    // the low-priority side stream (grid: Engine::side_ctas_per_sm CTAs per SM).
     constexpr int UN = 4;
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
     for (long long t0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; t0 < total; t0 += stride * UN) {
