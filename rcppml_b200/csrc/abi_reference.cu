@@ -203,13 +203,15 @@ bool fit_in_process_multi_gpu(int G, const int* devices, int m, int n, int64_t n
             else row_cuts = E.row_cuts;                                      // equal blocks from set_dims
         }
         if (!bar.wait()) return;                                             // B: row cuts known
-        sumsq[g] = E.assemble_row_block(all.data(), row_cuts.data());        // NVLink pulls + local transpose
+        E.install_row_cuts(row_cuts.data());
+        E.start_factor_block_upload<double>(k, W, H);                        // copy engine, behind the row-block assembly
+        sumsq[g] = E.assemble_row_block(all.data());                         // NVLink pulls + local transpose
         if (!bar.wait()) return;                                             // C: nobody reads a peer's column block any more
         if (g == 0) marks[1] = since();
         double s = 0.0;
         for (int r = 0; r < G; ++r) s += sumsq[r];                           // rank order: identical on every device
         E.finish_matrix_local(s, nnz);
-        E.upload_factor_blocks_host<double>(k, W, H);                        // own rows of W_T, own columns of H
+        E.finish_factor_block_upload<double>(k);                             // own rows of W_T, own columns of H into place
         E.comm_prepare_local(devices);
         if (!bar.wait()) return;                                             // D: every replica buffer exists, own blocks in place
         E.comm_attach_local(all.data());

@@ -172,11 +172,21 @@ static void launch_normalize_gram(int KP, float* X, long long ncols, const float
     }
     return;
 #endif
+    if (mcX) {                                        // multicast replication by the Gram kernel (Engine::mc_mode 1)
+        switch (KP) {
+            case 16: normalize_gram_mma_kernel<16, 64, true><<<grid, GramMmaGeom<16>::WARPS * 32, 0, s>>>(X, ncols, d, normalize, partials, stop, mcX); break;
+            case 32: normalize_gram_mma_kernel<32, 64, true><<<grid, GramMmaGeom<32>::WARPS * 32, 0, s>>>(X, ncols, d, normalize, partials, stop, mcX); break;
+            case 64: normalize_gram_mma_kernel<64, 32, true><<<grid, GramMmaGeom<64>::WARPS * 32, 0, s>>>(X, ncols, d, normalize, partials, stop, mcX); break;
+            case 128: normalize_gram_mma_kernel<128, 32, true><<<grid, GramMmaGeom<128>::WARPS * 32, 0, s>>>(X, ncols, d, normalize, partials, stop, mcX); break;
+            default: throw std::runtime_error("unsupported padded rank");
+        }
+        return;
+    }
     switch (KP) {
-        case 16: normalize_gram_mma_kernel<16, 64><<<grid, GramMmaGeom<16>::WARPS * 32, 0, s>>>(X, ncols, d, normalize, partials, stop, mcX); break;
-        case 32: normalize_gram_mma_kernel<32, 64><<<grid, GramMmaGeom<32>::WARPS * 32, 0, s>>>(X, ncols, d, normalize, partials, stop, mcX); break;
-        case 64: normalize_gram_mma_kernel<64, 32><<<grid, GramMmaGeom<64>::WARPS * 32, 0, s>>>(X, ncols, d, normalize, partials, stop, mcX); break;
-        case 128: normalize_gram_mma_kernel<128, 32><<<grid, GramMmaGeom<128>::WARPS * 32, 0, s>>>(X, ncols, d, normalize, partials, stop, mcX); break;
+        case 16: normalize_gram_mma_kernel<16, 64><<<grid, GramMmaGeom<16>::WARPS * 32, 0, s>>>(X, ncols, d, normalize, partials, stop, nullptr); break;
+        case 32: normalize_gram_mma_kernel<32, 64><<<grid, GramMmaGeom<32>::WARPS * 32, 0, s>>>(X, ncols, d, normalize, partials, stop, nullptr); break;
+        case 64: normalize_gram_mma_kernel<64, 32><<<grid, GramMmaGeom<64>::WARPS * 32, 0, s>>>(X, ncols, d, normalize, partials, stop, nullptr); break;
+        case 128: normalize_gram_mma_kernel<128, 32><<<grid, GramMmaGeom<128>::WARPS * 32, 0, s>>>(X, ncols, d, normalize, partials, stop, nullptr); break;
         default: throw std::runtime_error("unsupported padded rank");
     }
 }
@@ -552,13 +562,17 @@ void Engine::balanced_row_cuts(Engine* const* all, int per_item, int* cuts_out) 
 
 // Step 3: install the row cuts, pull the runs of every column that fall into this device's rows out of all column
 // blocks (peer reads), transpose the row block locally. Returns this device's share of tr(AtA) (over its column block).
-double Engine::assemble_row_block(Engine* const* all, const int* row_cuts_in) {
-    use_device();
-    const auto t0 = std::chrono::steady_clock::now();
+void Engine::install_row_cuts(const int* row_cuts_in) {
     row_cuts.assign(row_cuts_in, row_cuts_in + world + 1);
-    B200_REQUIRE(row_cuts.front() == 0 && row_cuts.back() == m, "assemble_row_block: the row cuts do not cover the matrix");
+    B200_REQUIRE(row_cuts.front() == 0 && row_cuts.back() == m, "install_row_cuts: the row cuts do not cover the matrix");
+    for (int r = 0; r < world; ++r) B200_REQUIRE(row_cuts[r] <= row_cuts[r + 1], "install_row_cuts: cuts must ascend");
     row_begin = row_cuts[rank]; m_loc = row_cuts[rank + 1] - row_cuts[rank];
     equal_partition = false;
+}
+
+double Engine::assemble_row_block(Engine* const* all) {
+    use_device();
+    const auto t0 = std::chrono::steady_clock::now();
     int* rstart = scratch<int>(8, static_cast<size_t>(n) + 1);
     int* rcnt = scratch<int>(9, static_cast<size_t>(n) + 1);
     int* rp = scratch<int>(10, static_cast<size_t>(n) + 1);
@@ -610,27 +624,42 @@ void Engine::finish_matrix_local(double sumsq_total, int64_t nnz_total) {
     has_mask = false;
 }
 
-// Step 5: own factor blocks up (rows [row_begin, +m_loc) of the full host W_T, columns [col_begin, +n_loc) of H).
+// Step 5: own factor blocks up (rows [row_begin, +m_loc) of the full host W_T, columns [col_begin, +n_loc) of H), in two
+// halves: the H2D copies into a staging buffer start on the side stream as soon as the row cuts are installed and run
+// on the copy engine WHILE the main stream assembles and transposes the row block (NVLink + SMs); padding / conversion
+// into the replicas follows once the matrix is complete.
 template <class T>
-void Engine::upload_factor_blocks_host(int k_, const T* W_full, const T* H_full) {
+void Engine::start_factor_block_upload(int k_, const T* W_full, const T* H_full) {
+    use_device();
+    B200_REQUIRE(k_ >= 1 && k_ <= kMaxKP, "rank must be in [1, 128]");
+    const size_t wcount = static_cast<size_t>(m_loc) * k_, hcount = static_cast<size_t>(n_loc) * k_;
+    T* stage = scratch<T>(7, wcount + hcount + 1);
+    if (wcount) B200_CUDA_CHECK(cudaMemcpyAsync(stage, W_full + static_cast<size_t>(row_begin) * k_, wcount * sizeof(T), cudaMemcpyHostToDevice, side_stream));
+    if (hcount) B200_CUDA_CHECK(cudaMemcpyAsync(stage + wcount, H_full + static_cast<size_t>(col_begin) * k_, hcount * sizeof(T), cudaMemcpyHostToDevice, side_stream));
+    B200_CUDA_CHECK(cudaEventRecord(ev_join, side_stream));
+    h2d_bytes += (wcount + hcount) * sizeof(T);
+}
+template void Engine::start_factor_block_upload<float>(int, const float*, const float*);
+template void Engine::start_factor_block_upload<double>(int, const double*, const double*);
+
+template <class T>
+void Engine::finish_factor_block_upload(int k_) {
     use_device();
     alloc_factors(k_);
     const auto t0 = std::chrono::steady_clock::now();
     const size_t wcount = static_cast<size_t>(m_loc) * k, hcount = static_cast<size_t>(n_loc) * k;
-    T* stage = scratch<T>(7, wcount + hcount + 1);
-    if (wcount) B200_CUDA_CHECK(cudaMemcpyAsync(stage, W_full + static_cast<size_t>(row_begin) * k, wcount * sizeof(T), cudaMemcpyHostToDevice, stream));
-    if (hcount) B200_CUDA_CHECK(cudaMemcpyAsync(stage + wcount, H_full + static_cast<size_t>(col_begin) * k, hcount * sizeof(T), cudaMemcpyHostToDevice, stream));
+    T* stage = scratch<T>(7, wcount + hcount + 1);                           // (same size as in start_: no reallocation)
+    B200_CUDA_CHECK(cudaStreamWaitEvent(stream, ev_join, 0));
     if (wcount) pad_convert_kernel<T><<<static_cast<unsigned>((static_cast<long long>(m_loc) * KP + 255) / 256), 256, 0, stream>>>(
         stage, W_T.ptr + static_cast<size_t>(row_begin) * KP, m_loc, k, KP);
     if (hcount) pad_convert_kernel<T><<<static_cast<unsigned>((static_cast<long long>(n_loc) * KP + 255) / 256), 256, 0, stream>>>(
         stage + wcount, H.ptr + static_cast<size_t>(col_begin) * KP, n_loc, k, KP);
     B200_CUDA_CHECK(cudaGetLastError());
     B200_CUDA_CHECK(cudaStreamSynchronize(stream));
-    h2d_bytes += (wcount + hcount) * sizeof(T);
     phase_ms[2] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 }
-template void Engine::upload_factor_blocks_host<float>(int, const float*, const float*);
-template void Engine::upload_factor_blocks_host<double>(int, const double*, const double*);
+template void Engine::finish_factor_block_upload<float>(int);
+template void Engine::finish_factor_block_upload<double>(int);
 
 // Step 6 (after comm_attach_local on every engine): complete the replicas with the peers' blocks over NVLink.
 void Engine::pull_factor_blocks_from_peers() {

@@ -92,9 +92,11 @@ public:
     template <class ValT>
     void upload_col_block_host(int m, int n, const int* col_ptr, const int* row_idx, const ValT* values);
     void balanced_row_cuts(Engine* const* all, int per_item, int* cuts_out);
-    double assemble_row_block(Engine* const* all, const int* row_cuts_in);
+    void install_row_cuts(const int* row_cuts_in);
+    double assemble_row_block(Engine* const* all);
     void finish_matrix_local(double sumsq_total, int64_t nnz_total);
-    template <class T> void upload_factor_blocks_host(int k, const T* W_full, const T* H_full);
+    template <class T> void start_factor_block_upload(int k, const T* W_full, const T* H_full);
+    template <class T> void finish_factor_block_upload(int k);
     void pull_factor_blocks_from_peers();
     DeviceBuffer<int> row_hist;                           // [m] entries per row of the own column block
 

@@ -29,12 +29,13 @@ struct DevState {
 // One 128-bit store into EVERY replica bound to the multicast object behind `mc` (NVSwitch multicast, NVLS): the
 // switch replicates the packet, the sender's NVLink egress carries it once.
 __device__ __forceinline__ void multimem_store4(float4* mc, const float4& v) {
-    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
-                 : "memory");
+    // (no "memory" clobber: it would be a compiler barrier in every kernel that merely CONTAINS the store — measured:
+    // the Gram kernel lost its load/MMA overlap, 0.32 -> 0.52 ms, with the multicast path not even taken)
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
 }
 
 __device__ __forceinline__ void multimem_store1(float* mc, float v) {
-    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(mc), "f"(v) : "memory");
+    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(mc), "f"(v));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -163,7 +164,10 @@ template <> struct GramMmaGeom<32> { static constexpr int WARPS = 5, TPW = 2; };
 template <> struct GramMmaGeom<64> { static constexpr int WARPS = 6, TPW = 6; };
 template <> struct GramMmaGeom<128> { static constexpr int WARPS = 8, TPW = 17; };
 
-template <int KP, int TC>
+// REPL: also write the (normalised) block into every replica through the multicast alias mcX (Engine::mc_mode 1) — a
+// separate instantiation, so that the common kernel keeps its 80 registers (4 CTAs/SM; with the extra pointer
+// arithmetic it needed 94 and lost a resident CTA: 0.32 -> 0.52 ms).
+template <int KP, int TC, bool REPL = false>
 static __global__ void __launch_bounds__(GramMmaGeom<KP>::WARPS * 32) normalize_gram_mma_kernel(
     float* __restrict__ X, long long ncols, const float* __restrict__ d, int normalize, double* __restrict__ partials,
     const int* __restrict__ stop_flag, float* __restrict__ mcX) {
@@ -216,11 +220,11 @@ static __global__ void __launch_bounds__(GramMmaGeom<KP>::WARPS * 32) normalize_
                     v.y = __fdiv_rn(v.y, sD[q * 4 + 1]);
                     v.z = __fdiv_rn(v.z, sD[q * 4 + 2]);
                     v.w = __fdiv_rn(v.w, sD[q * 4 + 3]);
-                    if (!mcX) X4[t] = v;
+                    if (!REPL) X4[t] = v;
                 }
-                // sharded fits with multicast-bound factors: the (normalised) block goes into ALL replicas, this rank's
-                // included, with one store per word
-                if (mcX) multimem_store4(reinterpret_cast<float4*>(mcX + c0 * KP) + t, v);
+                // sharded fits with multicast-bound factors (REPL): the (normalised) block goes into ALL replicas, this
+                // rank's included, with one store per word
+                if (REPL) multimem_store4(reinterpret_cast<float4*>(mcX + c0 * KP) + t, v);
             }
             pre[u] = v;
         }
