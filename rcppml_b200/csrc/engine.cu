@@ -4,6 +4,8 @@
 // rcppml_b200_* C ABI declared in include/rcppml_gpu.h.
 #include "engine.hpp"
 
+#include <nvtx3/nvToolsExt.h>      // header-only NVTX v3: ranges are no-ops unless a profiler injects itself
+
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -978,7 +980,13 @@ template void Engine::get_factor_blocks_host<float>(float*, float*, float*);
 template void Engine::get_factor_blocks_host<double>(double*, double*, double*);
 
 // ---- profiling sections -----------------------------------------------------------------------
+// Sections of an iteration, named as the reference's own profiling sections — also the NVTX ranges a
+// profiler sees around the enqueue of each section's kernels (host side; nested for the Gram inside the loss section).
+static const char* const kSectionNames[RCPPML_B200_NUM_SECTIONS] = {"gram_H", "fused_rhs_nnls_H", "scaling_H", "gram_W",
+                                                                     "fused_rhs_nnls_W", "scaling_W", "loss", "comm"};
+
 void Engine::sec_begin(int sec, cudaStream_t on) {
+    nvtxRangePushA(kSectionNames[sec]);
     if (!profiling) return;
     if (!on) on = stream;
     auto& pool = prof_events[sec];
@@ -991,6 +999,7 @@ void Engine::sec_begin(int sec, cudaStream_t on) {
     B200_CUDA_CHECK(cudaEventRecord(pool[prof_used[sec]].first, on));
 }
 void Engine::sec_end(int sec, cudaStream_t on) {
+    nvtxRangePop();
     if (!profiling) return;
     if (!on) on = stream;
     B200_CUDA_CHECK(cudaEventRecord(prof_events[sec][prof_used[sec]].second, on));

@@ -279,23 +279,22 @@ __global__ void __launch_bounds__(256, B200_CD_MIN_CTAS) cd_half_step_kernel(con
 #pragma unroll
                         for (int e = 0; e < 4; ++e) x[nv][e] = fminf(x[nv][e], p.ub);
                 }
-                if (p.mcX) {                                                // every replica at once (NVSwitch multicast)
-                    float* mc = p.mcX + static_cast<size_t>(j) * KP;
 #pragma unroll
-                    for (int nv = 0; nv < NV; ++nv)
-                        multimem_store4(reinterpret_cast<float4*>(mc + (nv * LANES + gl) * 4), make_float4(x[nv][0], x[nv][1], x[nv][2], x[nv][3]));
-                } else {
-#pragma unroll
-                    for (int nv = 0; nv < NV; ++nv)
-                        *reinterpret_cast<float4*>(xcol + (nv * LANES + gl) * 4) =
-                            make_float4(x[nv][0], x[nv][1], x[nv][2], x[nv][3]);
-                }
+                for (int nv = 0; nv < NV; ++nv)
+                    *reinterpret_cast<float4*>(xcol + (nv * LANES + gl) * 4) =
+                        make_float4(x[nv][0], x[nv][1], x[nv][2], x[nv][3]);
                 for (int q = 0; q < p.npeers; ++q) {                        // replicate to the peers' copies of X
                     float* pc = p.peerX[q] + static_cast<size_t>(j) * KP;
 #pragma unroll
                     for (int nv = 0; nv < NV; ++nv)
                         *reinterpret_cast<float4*>(pc + (nv * LANES + gl) * 4) =
                             make_float4(x[nv][0], x[nv][1], x[nv][2], x[nv][3]);
+                }
+                if (p.mcX) {                                                // ... or to every replica at once (multicast)
+                    float* mc = p.mcX + static_cast<size_t>(j) * KP;
+#pragma unroll
+                    for (int nv = 0; nv < NV; ++nv)
+                        multimem_store4(reinterpret_cast<float4*>(mc + (nv * LANES + gl) * 4), make_float4(x[nv][0], x[nv][1], x[nv][2], x[nv][3]));
                 }
                 if (p.want_cross) {                                         // Σ_i x_i · b_raw,i
                     const float* br = p.braw + static_cast<size_t>(jl) * KP;

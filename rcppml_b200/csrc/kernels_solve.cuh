@@ -59,8 +59,9 @@ struct HalfStepParams {
     float* peerX[7];
     int npeers;
     // ... or, with multicast-bound factors (vmm.hpp, Engine::mc_mode 2): ONE multimem.st per word through mcX, the
-    // multicast alias of X, lands in every replica (this rank's included) — the sender's NVLink egress carries the
-    // block once instead of N-1 times. nullptr: plain local store (+ the unicast peer stores above).
+    // multicast alias of X, lands in every replica — the sender's NVLink egress carries the block once instead of
+    // N-1 times. (The local store stays unconditional: the copy that loops back into this rank's replica carries the
+    // same bits, and the hot path of a one-GPU fit keeps its instruction schedule.) nullptr: no multicast.
     float* mcX;
     int cslot;                         // c_solver slot holding this launch's diagonal blocks / reciprocals
     // Row-panel passes (engine.cu build_panels): when the gathered factor is larger than L2, a half-step runs as
@@ -585,23 +586,22 @@ __global__ void __launch_bounds__(256, (NV >= 4) ? 2 : B200_SOLVE_MIN_CTAS) half
 #pragma unroll
                     for (int e = 0; e < 4; ++e) x[nv][e] = fminf(x[nv][e], p.ub);
             }
-            if (p.mcX) {                                            // every replica at once (NVSwitch multicast)
-                float* mc = p.mcX + static_cast<size_t>(j) * KP;
 #pragma unroll
-                for (int nv = 0; nv < NV; ++nv)
-                    multimem_store4(reinterpret_cast<float4*>(mc + (nv * LANES + gl) * 4), make_float4(x[nv][0], x[nv][1], x[nv][2], x[nv][3]));
-            } else {
-#pragma unroll
-                for (int nv = 0; nv < NV; ++nv)
-                    *reinterpret_cast<float4*>(xcol + (nv * LANES + gl) * 4) =
-                        make_float4(x[nv][0], x[nv][1], x[nv][2], x[nv][3]);
-            }
+            for (int nv = 0; nv < NV; ++nv)
+                *reinterpret_cast<float4*>(xcol + (nv * LANES + gl) * 4) =
+                    make_float4(x[nv][0], x[nv][1], x[nv][2], x[nv][3]);
             for (int q = 0; q < p.npeers; ++q) {                    // replicate to the peers' copies of X
                 float* pc = p.peerX[q] + static_cast<size_t>(j) * KP;
 #pragma unroll
                 for (int nv = 0; nv < NV; ++nv)
                     *reinterpret_cast<float4*>(pc + (nv * LANES + gl) * 4) =
                         make_float4(x[nv][0], x[nv][1], x[nv][2], x[nv][3]);
+            }
+            if (p.mcX) {                                            // ... or to every replica at once (NVSwitch multicast; the
+                float* mc = p.mcX + static_cast<size_t>(j) * KP;    // copy that loops back into this replica carries the same bits)
+#pragma unroll
+                for (int nv = 0; nv < NV; ++nv)
+                    multimem_store4(reinterpret_cast<float4*>(mc + (nv * LANES + gl) * 4), make_float4(x[nv][0], x[nv][1], x[nv][2], x[nv][3]));
             }
 
             if (p.norm_type == 0) {

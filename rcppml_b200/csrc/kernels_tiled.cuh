@@ -331,9 +331,9 @@ __global__ void __launch_bounds__(256, (GL * 4 * GNV >= 128) ? (SOLVER == SOLVER
             if (row < CB && jr < p.ncols) {
                 const float4 v = *reinterpret_cast<const float4*>(tile + row * PITCH + sw * 4);
                 const size_t off = static_cast<size_t>(jr + p.col_offset) * KP + sw * 4;
-                if (p.mcX) multimem_store4(reinterpret_cast<float4*>(p.mcX + off), v);      // every replica at once
-                else *reinterpret_cast<float4*>(p.X + off) = v;
+                *reinterpret_cast<float4*>(p.X + off) = v;
                 for (int q = 0; q < p.npeers; ++q) *reinterpret_cast<float4*>(p.peerX[q] + off) = v;
+                if (p.mcX) multimem_store4(reinterpret_cast<float4*>(p.mcX + off), v);      // ... or every replica at once
                 if (p.norm_type != 2) {
                     double2 a0 = myrs[0], a1 = myrs[1];
                     if (p.norm_type == 0) {
