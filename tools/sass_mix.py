@@ -1,7 +1,8 @@
 """Static instruction mix of the shipped kernels: `cuobjdump -sass` of rcppml_b200/lib/RcppML_gpu.so, opcode counts per
 kernel (no GPU needed). Backs the statements of DESIGN.md §4 about the code that actually ships — packed fp32 pairs
 (FFMA2 / FADD2), 128-bit global and shared accesses, FP64 tensor-core Gram (DMMA), constant-memory operands (LDC) —
-and shows what is NOT there (no UBLKCP / UTMALDG bulk copies, no tcgen05 / UTCxMMA: DESIGN.md §5 says why).
+and shows what is NOT there (no UBLKCP / UTMALDG bulk copies, no tcgen05 / UTCxMMA: DESIGN.md §5 says why). Round 2: the
+system-scope strong stores of the solve kernels are the NVSwitch multicast stores (PTX multimem.st, kernels_dense.cuh).
 
     python tools/sass_mix.py [--match half_step_kernel --match normalize_gram_mma] [--out profiles/r01t_sass_mix.json]
 """
@@ -49,6 +50,10 @@ for block in sass.split("Function : ")[1:]:
         ops[base] += 1
         if base in ("LDG", "STG", "LDS", "STS") and ".128" in op:
             wide[base + ".128"] += 1
+        # multimem.st.relaxed.sys (NVSwitch multicast store through the multicast alias of a factor) has no mnemonic of its
+        # own in this disassembler: it shows as a system-scope strong store
+        if base == "STG" and ".STRONG.SYS" in op:
+            wide["STG.STRONG.SYS (multimem.st / peer flag stores)"] += 1
     row = {"kernel": re.sub(r"\(.*", "", name)[:140], "sass_instructions": n}
     row.update({k: ops[k] for k in KEYS if ops[k]})
     row.update(wide)
