@@ -116,15 +116,15 @@ void launch_cd_half_step(int geom, const HalfStepParams& p, int num_sms, cudaStr
     }
 }
 
-template <int GL, int GNV, int SL, int SNV, int SOLVER>
+template <int GL, int GNV, int SL, int SNV, int SOLVER, int WARPS = 8, bool HYB = false>
 static void launch_tiled_t(const HalfStepParams& p, int num_sms, cudaStream_t stream, int* grid_out) {
-    auto kern = tiled_half_step_kernel<GL, GNV, SL, SNV, SOLVER>;
-    const size_t smem = tiled_smem_bytes<GL, GNV, SL, SNV, SOLVER>();
+    auto kern = tiled_half_step_kernel<GL, GNV, SL, SNV, SOLVER, WARPS, HYB>;
+    const size_t smem = tiled_smem_bytes<GL, GNV, SL, SNV, SOLVER, WARPS, HYB>();
     static OccCache cache;
-    const int cached_occ = cached_occupancy(cache, kern, 256, smem, "tiled_half_step_kernel does not fit on an SM");
+    const int cached_occ = cached_occupancy(cache, kern, WARPS * 32, smem, "tiled_half_step_kernel does not fit on an SM");
     const int grid = num_sms * cached_occ;
     if (grid_out) { *grid_out = grid; return; }
-    kern<<<grid, 256, smem, stream>>>(p);
+    kern<<<grid, WARPS * 32, smem, stream>>>(p);
 }
 
 template <int SOLVER>
@@ -135,6 +135,10 @@ static void launch_tiled_s(int gather_geom, const HalfStepParams& p, int num_sms
     switch (gather_geom) {
         case 4016: launch_tiled_t<16, 1, 4, 4, SOLVER>(p, num_sms, s, grid_out); return;  // KP = 64, 8-column batches
         case 4108: launch_tiled_t<8, 2, 4, 4, SOLVER>(p, num_sms, s, grid_out); return;
+        // + 10000: one 768-thread CTA per SM (L / Lᵀ once per SM); + 20000: the same with the hybrid register +
+        // cp.async-ring gather (kernels_tiled.cuh) — Cholesky, short columns; Engine::tiled_gather_geom
+        case 14108: if (SOLVER == SOLVER_CHOL) { launch_tiled_t<8, 2, 4, 4, SOLVER_CHOL, 24, false>(p, num_sms, s, grid_out); return; } break;
+        case 24108: if (SOLVER == SOLVER_CHOL) { launch_tiled_t<8, 2, 4, 4, SOLVER_CHOL, 24, true>(p, num_sms, s, grid_out); return; } break;
         default: break;
     }
     switch (gather_geom) {                          // gather (LANES + 100*(NV-1)); the solve geometry follows from KP
@@ -774,6 +778,8 @@ void Engine::alloc_factors(int k_) {
     if (const char* env = std::getenv("RCPPML_B200_SIDE_CTAS")) side_ctas_per_sm = std::max(1, std::atoi(env));
     tiled_sl_override = 0;
     if (const char* env = std::getenv("RCPPML_B200_TILED_SL")) tiled_sl_override = std::atoi(env);
+    tiled_cta_mode = 0;
+    if (const char* env = std::getenv("RCPPML_B200_TILED_CTA")) tiled_cta_mode = std::max(0, std::min(2, std::atoi(env)));
     narrow_min_cols = 8.0 * num_sms * 24;
     if (std::getenv("RCPPML_B200_CD_GEOM")) narrow_min_cols = 0.0;           // an explicit geometry applies to every size
     if (const char* env = std::getenv("RCPPML_B200_NARROW_MIN_COLS")) narrow_min_cols = std::atof(env);
@@ -814,7 +820,8 @@ void Engine::alloc_factors(int k_) {
     }
     if (tiled_mode) {
         for (int solver = 0; solver < 2; ++solver)
-            for (int geom : {LANES, (KP == 64 || KP == 128) ? 100 + KP / 8 : LANES, KP == 64 ? 4016 : LANES, KP == 64 ? 4108 : LANES}) {
+            for (int geom : {LANES, (KP == 64 || KP == 128) ? 100 + KP / 8 : LANES, KP == 64 ? 4016 : LANES, KP == 64 ? 4108 : LANES,
+                             (KP == 64 && solver == SOLVER_CHOL) ? 14108 : LANES, (KP == 64 && solver == SOLVER_CHOL) ? 24108 : LANES}) {
                 int g = 0;
                 launch_tiled_half_step(geom, solver, dummy, num_sms, stream, &g);
                 gmax = std::max(gmax, g);
@@ -1253,6 +1260,8 @@ int Engine::tiled_gather_geom(long long cnt, long long ncols, int solver) const 
         int sl = tiled_sl_override;
         if (sl == 0) sl = (solver == SOLVER_CHOL) ? 4 : 2;
         if (sl == 4) g += 4000;
+        // RCPPML_B200_TILED_CTA: 1 = one 768-thread CTA per SM, 2 = that + hybrid gather (Cholesky, 8 lanes x 2 words)
+        if (g == 4108 && solver == SOLVER_CHOL && tiled_cta_mode > 0) g += 10000 * tiled_cta_mode;
     }
     return g;
 }

@@ -143,6 +143,8 @@ public:
     int tiled_mode = 1;
     double tiled_min_batches = 0.5, narrow_min_cols = 0.0;
     int side_ctas_per_sm = 8;               // grid of the peers' re-normalisation kernel (side stream), CTAs per SM
+    int tiled_cta_mode = 0;                 // k = 64 Cholesky tiled kernel: 0 = 3 x 256-thread CTAs per SM, 1 = one 768-thread CTA,
+                                            // 2 = one 768-thread CTA + hybrid register / cp.async-ring gather (RCPPML_B200_TILED_CTA)
     int tiled_sl_override = 0;              // k = 64 tiled kernel: solve lanes per column (0: rule, 2: 16-column batches, 4: 8)
     bool use_narrow_cd(long long ncols) const;
     bool use_tiled(int solver, long long cnt, long long ncols) const;

@@ -142,12 +142,95 @@ __device__ __forceinline__ void chol_solve_rolled(const float* sLz, const float*
 #undef B200_UPDATE
 }
 
-template <int GL, int GNV, int SL, int SNV, int SOLVER>
+// ---------------------------------------------------------------------------------------------
+// Hybrid gather (tiled kernel, WARPS = 24 variant): twice the factor rows in flight per lane group without a register
+// more. Of every segment of GL (index, value) pairs the first half of the rows is requested into registers (LDG.128)
+// as in gather_column, the second half is requested AT THE SAME TIME into a per-group shared-memory ring with cp.async
+// (LDGSTS, 16 bytes per lane, L1 bypassed) — landing space the one-CTA-per-SM layout frees by keeping L / Lᵀ once per
+// SM instead of three times. A lane copies exactly the words it later consumes, so no cross-lane synchronisation is
+// needed: cp.async.wait_group makes its own copies visible to it. The accumulation order is the CSC order of
+// gather_column (entries 0 .. GL-1 of a segment in turn): bit-identical.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+template <int GL, int GNV>
+__device__ __forceinline__ void gather_column_hybrid(const HalfStepParams& p, int p0, int p1, int gl, unsigned gmask,
+                                                     float* ring /* this group's [GL/2][KP] floats */, float (&b)[GNV][4]) {
+    constexpr int KP = GL * 4 * GNV;
+    constexpr int HALF = GL / 2;
+    static_assert(GL >= 2 && HALF * GNV <= 8, "register half must stay within 8 loads per lane");
+    int nidx = 0;
+    float nval = 0.f;
+    if (p0 + gl < p1) {
+        nidx = __ldg(p.rowidx + p0 + gl);
+        nval = __ldg(p.vals + p0 + gl);
+    }
+    const float4* Fl = reinterpret_cast<const float4*>(p.F) + gl;
+    float4* ringl = reinterpret_cast<float4*>(ring) + gl;
+    for (int base = p0; base < p1; base += GL) {
+        const int ridx = nidx;
+        const float rval = nval;
+        const int nb = base + GL + gl;               // prefetch the next idx/val segment
+        nidx = 0;
+        nval = 0.f;
+        if (nb < p1) {
+            nidx = __ldg(p.rowidx + nb);
+            nval = __ldg(p.vals + nb);
+        }
+        const int cnt = p1 - base;
+        if (cnt >= GL) {
+            float4 f[HALF][GNV];
+            float v[GL];
+#pragma unroll
+            for (int u = 0; u < HALF; ++u) {         // first half: registers
+                const int r = gshfl<GL>(gmask, ridx, u);
+                v[u] = gshfl<GL>(gmask, rval, u);
+                const float4* row = Fl + static_cast<size_t>(r) * (KP / 4);
+#pragma unroll
+                for (int nv = 0; nv < GNV; ++nv) f[u][nv] = ldg_row(row + nv * GL);
+            }
+#pragma unroll
+            for (int u = HALF; u < GL; ++u) {        // second half: shared-memory ring, in flight together with the first
+                const int r = gshfl<GL>(gmask, ridx, u);
+                v[u] = gshfl<GL>(gmask, rval, u);
+                const float4* row = Fl + static_cast<size_t>(r) * (KP / 4);
+#pragma unroll
+                for (int nv = 0; nv < GNV; ++nv) cp_async16(ringl + (u - HALF) * (KP / 4) + nv * GL, row + nv * GL);
+            }
+#pragma unroll
+            for (int u = 0; u < HALF; ++u)
+#pragma unroll
+                for (int nv = 0; nv < GNV; ++nv) axpy4(b[nv], v[u], f[u][nv]);
+            cp_async_commit_wait_all();
+#pragma unroll
+            for (int u = HALF; u < GL; ++u)
+#pragma unroll
+                for (int nv = 0; nv < GNV; ++nv) axpy4(b[nv], v[u], ringl[(u - HALF) * (KP / 4) + nv * GL]);
+        } else {                                     // ragged tail (< GL entries), element by element
+            for (int s2 = 0; s2 < cnt; ++s2) {
+                const int r = gshfl<GL>(gmask, ridx, s2);
+                const float v = gshfl<GL>(gmask, rval, s2);
+                const float4* row = Fl + static_cast<size_t>(r) * (KP / 4);
+#pragma unroll
+                for (int nv = 0; nv < GNV; ++nv) axpy4(b[nv], v, __ldg(row + nv * GL));
+            }
+        }
+    }
+}
+
+template <int GL, int GNV, int SL, int SNV, int SOLVER, int WARPS = 8, bool HYB = false>
 inline size_t tiled_smem_bytes() {
     constexpr int KP = GL * 4 * GNV;
     constexpr int CB = 32 / SL;
     return static_cast<size_t>(KP) * KP * sizeof(float) * (SOLVER == SOLVER_CHOL ? 2 : 1) +
-           static_cast<size_t>(8) * CB * (KP + 4) * sizeof(float) + static_cast<size_t>(8) * 128 * sizeof(double);
+           static_cast<size_t>(WARPS) * CB * (KP + 4) * sizeof(float) + static_cast<size_t>(WARPS) * 128 * sizeof(double) +
+           (HYB ? static_cast<size_t>(WARPS) * (32 / GL) * (GL / 2) * KP * sizeof(float) : 0);
     // (k = 64, Cholesky: 32 KB + 34 KB + 8 KB = 74 KB -> three CTAs per SM; the 256 fp64 cross partials of the
     // final reduction reuse the tile)
 }
@@ -155,8 +238,10 @@ inline size_t tiled_smem_bytes() {
 #ifndef B200_TILED_MIN_CTAS
 #define B200_TILED_MIN_CTAS 3
 #endif
-template <int GL, int GNV, int SL, int SNV, int SOLVER>
-__global__ void __launch_bounds__(256, (GL * 4 * GNV >= 128) ? (SOLVER == SOLVER_CHOL ? 1 : 2) : B200_TILED_MIN_CTAS) tiled_half_step_kernel(const HalfStepParams p) {
+// WARPS = 8 (default): 256-thread CTAs, three per SM at k = 64. WARPS = 24: ONE 768-thread CTA per SM — L / Lᵀ exist once
+// per SM (32 KB instead of 96), which is what pays for the shared-memory ring of the hybrid gather (HYB).
+template <int GL, int GNV, int SL, int SNV, int SOLVER, int WARPS = 8, bool HYB = false>
+__global__ void __launch_bounds__(WARPS * 32, (WARPS > 8) ? 1 : ((GL * 4 * GNV >= 128) ? (SOLVER == SOLVER_CHOL ? 1 : 2) : B200_TILED_MIN_CTAS)) tiled_half_step_kernel(const HalfStepParams p) {
     constexpr int KP = GL * 4 * GNV;
     static_assert(KP == SL * 4 * SNV, "gather and solve geometries must cover the same padded rank");
     constexpr int GGPW = 32 / GL;                 // gather groups (columns per gather round) per warp
@@ -172,22 +257,24 @@ __global__ void __launch_bounds__(256, (GL * 4 * GNV >= 128) ? (SOLVER == SOLVER
 
     float* sM1 = smem;
     float* sM2 = sM1 + KP * KP;
-    float* sTile = sM2 + (SOLVER == SOLVER_CHOL ? KP * KP : 0);                     // [8][CB][PITCH]
-    double* sRS = reinterpret_cast<double*>(sTile + 8 * CB * PITCH);                // [8][RPI][KP]  (RPI*KP = 128)
-    double* sCross = reinterpret_cast<double*>(sTile);                              // [256], after the main loop only
+    constexpr int THREADS = WARPS * 32;
+    float* sTile = sM2 + (SOLVER == SOLVER_CHOL ? KP * KP : 0);                     // [WARPS][CB][PITCH]
+    double* sRS = reinterpret_cast<double*>(sTile + WARPS * CB * PITCH);            // [WARPS][RPI][KP]  (RPI*KP = 128)
+    float* sRing = reinterpret_cast<float*>(sRS + WARPS * 128);                     // HYB: [WARPS][GGPW][GL/2][KP]
+    double* sCross = reinterpret_cast<double*>(sTile);                              // [THREADS], after the main loop only
     const float* cD = c_solver[p.cslot].dblk;
     const float* cR = c_solver[p.cslot].rcp;
     const int tid = threadIdx.x;
     {
         const float4* g4 = reinterpret_cast<const float4*>(p.M1);
         float4* s4 = reinterpret_cast<float4*>(sM1);
-        for (int t = tid; t < KP * KP / 4; t += 256) s4[t] = g4[t];
+        for (int t = tid; t < KP * KP / 4; t += THREADS) s4[t] = g4[t];
         if (SOLVER == SOLVER_CHOL) {
             const float4* l4 = reinterpret_cast<const float4*>(p.M2);
             float4* t4 = reinterpret_cast<float4*>(sM2);
-            for (int t = tid; t < KP * KP / 4; t += 256) t4[t] = l4[t];
+            for (int t = tid; t < KP * KP / 4; t += THREADS) t4[t] = l4[t];
         }
-        for (int t = tid; t < 8 * 128; t += 256) sRS[t] = 0.0;
+        for (int t = tid; t < WARPS * 128; t += THREADS) sRS[t] = 0.0;
     }
     __syncthreads();
 
@@ -232,7 +319,8 @@ __global__ void __launch_bounds__(256, (GL * 4 * GNV >= 128) ? (SOLVER == SOLVER
                         b[nv][0] = cv.x; b[nv][1] = cv.y; b[nv][2] = cv.z; b[nv][3] = cv.w;
                     }
                 }
-                gather_column<GL, GNV>(p, p0, p1, ggl, ggmask, b);
+                if constexpr (HYB) gather_column_hybrid<GL, GNV>(p, p0, p1, ggl, ggmask, sRing + ((warp * GGPW + ggw) * (GL / 2)) * KP, b);
+                else gather_column<GL, GNV>(p, p0, p1, ggl, ggmask, b);
             }
 #pragma unroll
             for (int nv = 0; nv < GNV; ++nv)
@@ -357,16 +445,16 @@ __global__ void __launch_bounds__(256, (GL * 4 * GNV >= 128) ? (SOLVER == SOLVER
     __syncthreads();                                                                // every warp is done with its tile
     sCross[tid] = cross;
     __syncthreads();
-    for (int t = tid; t < KP; t += 256) {
+    for (int t = tid; t < KP; t += THREADS) {
         double s = 0.0;
         if (p.norm_type != 2)
-            for (int g = 0; g < 8 * RPI; ++g) s += sRS[g * KP + t];
+            for (int g = 0; g < WARPS * RPI; ++g) s += sRS[g * KP + t];
         p.partials[static_cast<size_t>(blockIdx.x) * (KP + 1) + t] = s;
     }
     if (tid == 0) {
         double s = 0.0;
         if (p.want_cross)
-            for (int t = 0; t < 256; ++t) s += sCross[t];
+            for (int t = 0; t < THREADS; ++t) s += sCross[t];
         p.partials[static_cast<size_t>(blockIdx.x) * (KP + 1) + KP] = s;
     }
 }

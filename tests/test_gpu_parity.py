@@ -415,6 +415,32 @@ def test_tiled_kernel_is_bit_identical(eng, oracle, k, solver, monkeypatch):
     assert rel_err(got[0], ref.W_T) <= RTOL and rel_err(got[1], ref.H) <= RTOL and rel_err(got[2], ref.d) <= RTOL
 
 
+@pytest.mark.parametrize("k", [40, 64])
+def test_tiled_cta768_and_hybrid_gather_are_bit_identical(eng, k, monkeypatch):
+    """RCPPML_B200_TILED_CTA: the tiled Cholesky kernel as ONE 768-thread CTA per SM (L / Lt once per SM), and that layout
+    with the hybrid gather (half of every segment's factor rows in registers, half through a cp.async shared-memory ring)
+    must reproduce the default 256-thread kernel bit for bit — ragged short columns, both half-steps, L1/L2, a bound."""
+    import rcppml_b200 as rb
+    for (m, n, dens) in ((1500, 700, 0.04), (4000, 900, 0.03)):
+        A = random_csc(m, n, dens, 1200 + k, ragged=True)
+        eng.set_matrix(m, n, A.indptr, A.indices, A.data)
+        for kw in (dict(L1=(0.01, 0.005), L2=(0.0, 0.01)), dict(upper_bound=(0.05, 0.08), norm_type=1)):
+            cfg = rb.make_config(k, max_iter=4, tol=0.0, solver_mode=1, **kw)
+            res = []
+            monkeypatch.setenv("RCPPML_B200_TILED", "2")
+            for mode in ("0", "1", "2"):
+                monkeypatch.setenv("RCPPML_B200_TILED_CTA", mode)
+                eng.init_factors(k, 42)
+                r = eng.fit(cfg)
+                assert r.status == 0 and r.iterations == 4
+                res.append(eng.get_factors() + (eng.loss_history(4),))
+            monkeypatch.delenv("RCPPML_B200_TILED_CTA")
+            monkeypatch.delenv("RCPPML_B200_TILED")
+            for other in res[1:]:
+                for a, b in zip(res[0], other):
+                    assert np.array_equal(a, b), (k, m, kw)
+
+
 CD_GEOMS = {16: (301, 102, 4), 32: (701, 302, 104), 64: (702, 304, 108), 128: (704, 308, 116)}
 
 

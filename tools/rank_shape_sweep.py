@@ -20,7 +20,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-KNOBS = ("RCPPML_B200_TILED", "RCPPML_B200_TILED_SL", "RCPPML_B200_NV", "RCPPML_B200_NV_SHORT", "RCPPML_B200_CD_GEOM",
+KNOBS = ("RCPPML_B200_TILED", "RCPPML_B200_TILED_SL", "RCPPML_B200_TILED_CTA", "RCPPML_B200_NV", "RCPPML_B200_NV_SHORT", "RCPPML_B200_CD_GEOM",
          "RCPPML_B200_CD_KERNEL", "RCPPML_B200_TILED_MIN_BATCHES", "RCPPML_B200_NARROW_MIN_COLS", "RCPPML_B200_PANEL_MB")
 
 
@@ -35,6 +35,8 @@ def main():
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--out", default="")
+    ap.add_argument("--variants", default="", help="comma-separated subset of the variant names")
+    ap.add_argument("--half-steps", default="H,W")
     args = ap.parse_args()
 
     import torch
@@ -44,12 +46,19 @@ def main():
     variants = [("untiled", {"RCPPML_B200_TILED": "0"}),
                 ("tiled16", {"RCPPML_B200_TILED": "2", "RCPPML_B200_TILED_SL": "2"}),
                 ("tiled8", {"RCPPML_B200_TILED": "2", "RCPPML_B200_TILED_SL": "4"}),
+                ("tiled8_cta768", {"RCPPML_B200_TILED": "2", "RCPPML_B200_TILED_SL": "4", "RCPPML_B200_TILED_CTA": "1"}),
+                ("tiled8_cta768_hybrid", {"RCPPML_B200_TILED": "2", "RCPPML_B200_TILED_SL": "4", "RCPPML_B200_TILED_CTA": "2"}),
                 ("untiled_nv1", {"RCPPML_B200_TILED": "0", "RCPPML_B200_NV": "1"}),
                 ("untiled_nv2", {"RCPPML_B200_TILED": "0", "RCPPML_B200_NV": "2"}),
                 ("default", {})]
+    if args.variants:
+        keep = set(args.variants.split(","))
+        variants = [v for v in variants if v[0] in keep]
     lines = []
     for N in [int(x) for x in args.ns.split(",")]:
         for which, (m_s, n_s) in (("H", (args.m, args.n // N)), ("W", (args.m // N, args.n))):
+            if which not in args.half_steps.split(","):
+                continue
             eng = rb.Engine(0)
             # columns [0, n_s) / all columns of the generator with m_s rows: same column statistics as the rank's operand
             eng.set_matrix_synthetic(m_s, n_s, 0, args.density, 20260101)
