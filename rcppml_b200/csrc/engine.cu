@@ -133,6 +133,7 @@ static void launch_tiled_s(int gather_geom, const HalfStepParams& p, int num_sms
     // default narrowest one: k = 64 with 4 lanes x 4 words = batches of 8 columns instead of 16 — fewer columns per
     // warp batch quantise better when a rank holds few columns, Engine::tiled_solve_lanes)
     switch (gather_geom) {
+        case 8108: launch_tiled_t<8, 2, 8, 2, SOLVER>(p, num_sms, s, grid_out); return;   // KP = 64, 4-column batches (experiment)
         case 4016: launch_tiled_t<16, 1, 4, 4, SOLVER>(p, num_sms, s, grid_out); return;  // KP = 64, 8-column batches
         case 4108: launch_tiled_t<8, 2, 4, 4, SOLVER>(p, num_sms, s, grid_out); return;
         // + 10000: one 768-thread CTA per SM (L / Lᵀ once per SM); + 20000: the same with the hybrid register +
@@ -1260,6 +1261,7 @@ int Engine::tiled_gather_geom(long long cnt, long long ncols, int solver) const 
         int sl = tiled_sl_override;
         if (sl == 0) sl = (solver == SOLVER_CHOL) ? 4 : 2;
         if (sl == 4) g += 4000;
+        if (sl == 8 && g == 108) g += 8000;
         // RCPPML_B200_TILED_CTA: 1 = one 768-thread CTA per SM, 2 = that + hybrid gather (Cholesky, 8 lanes x 2 words)
         if (g == 4108 && solver == SOLVER_CHOL && tiled_cta_mode > 0) g += 10000 * tiled_cta_mode;
     }

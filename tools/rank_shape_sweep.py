@@ -46,6 +46,7 @@ def main():
     variants = [("untiled", {"RCPPML_B200_TILED": "0"}),
                 ("tiled16", {"RCPPML_B200_TILED": "2", "RCPPML_B200_TILED_SL": "2"}),
                 ("tiled8", {"RCPPML_B200_TILED": "2", "RCPPML_B200_TILED_SL": "4"}),
+                ("tiled4", {"RCPPML_B200_TILED": "2", "RCPPML_B200_TILED_SL": "8"}),
                 ("tiled8_cta768", {"RCPPML_B200_TILED": "2", "RCPPML_B200_TILED_SL": "4", "RCPPML_B200_TILED_CTA": "1"}),
                 ("tiled8_cta768_hybrid", {"RCPPML_B200_TILED": "2", "RCPPML_B200_TILED_SL": "4", "RCPPML_B200_TILED_CTA": "2"}),
                 ("untiled_nv1", {"RCPPML_B200_TILED": "0", "RCPPML_B200_NV": "1"}),
