@@ -357,6 +357,9 @@ int rcppml_b200_release_cache(void);
 int rcppml_b200_last_call_phases(double* ms5);
 /* Wall clock (ms) of the last rcppml_gpu_nmf_unified_float call, entry to return, measured inside the library. */
 double rcppml_b200_last_call_wall_ms(void);
+/* The column partition of the in-process multi-GPU path (RCPPML_NUM_GPUS), host only: world + 1 ascending cuts of the n
+ * columns, balanced by work = non-zeros + per_item per column (rcppml_b200/shard.py balanced_cuts). */
+int rcppml_b200_balanced_col_cuts(const int* col_ptr, int n, int world, int per_item, int* cuts);
 
 #ifdef __cplusplus
 }

@@ -117,6 +117,7 @@ def load() -> C.CDLL:
     lib.rcppml_b200_cd_sweeps.restype = C.c_int64
     lib.rcppml_b200_selftest_division.argtypes = [C.c_int64, C.c_uint64, C.POINTER(C.c_int64)]
     lib.rcppml_b200_get_counters.argtypes = [E, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.rcppml_b200_balanced_col_cuts.argtypes = [ip, C.c_int, C.c_int, C.c_int, ip]
     lib.rcppml_b200_last_call_wall_ms.restype = C.c_double
     lib.rcppml_b200_last_call_wall_ms.argtypes = []
     lib.rcppml_b200_nccl_unique_id.argtypes = [C.c_char_p]

@@ -727,5 +727,12 @@ int rcppml_b200_last_call_phases(double* ms5) {
     return 0;
 }
 double rcppml_b200_last_call_wall_ms(void) { return g_call_wall_ms; }
+// The column partition the in-process multi-GPU path uses (host only, no device work): world + 1 ascending cuts of the
+// n columns of a CSC matrix, balanced by work = non-zeros + per_item per column.
+int rcppml_b200_balanced_col_cuts(const int* col_ptr, int n, int world, int per_item, int* cuts) {
+    if (!col_ptr || !cuts || n < 0 || world < 1) return -1;
+    balanced_col_cuts(col_ptr, n, world, per_item, cuts);
+    return 0;
+}
 
 }  // extern "C"

@@ -218,6 +218,8 @@ void Engine::comm_mc_export(char* blob128) {
 void Engine::comm_mc_import(const char* all) {
     use_device();
     B200_REQUIRE(world > 1 && world <= 8 && xbuf.ptr != nullptr, "comm_mc_import: call comm_mc_export first (world <= 8)");
+    // (test hook: exercise the fall-back of the host launcher — VMM-backed factors on the NCCL loop)
+    B200_REQUIRE(!std::getenv("RCPPML_B200_MC_TEST_FAIL"), "comm_mc_import: failure requested by RCPPML_B200_MC_TEST_FAIL");
     const DriverApi& drv = DriverApi::get();
     std::vector<McBlob> blobs(world);
     for (int r = 0; r < world; ++r) std::memcpy(&blobs[r], all + static_cast<size_t>(r) * 128, sizeof(McBlob));

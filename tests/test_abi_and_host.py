@@ -241,3 +241,36 @@ def test_row_block_operand_is_a_column_slice_of_the_transpose():
         lo, hi = A.indptr[c0], A.indptr[c0 + cc]
         assert np.array_equal(cp, A.indptr[c0:c0 + cc + 1] - lo)
         assert np.array_equal(ci, A.indices[lo:hi]) and np.array_equal(cx, A.data[lo:hi])
+
+
+def test_balanced_cuts_host_logic_and_library_agree():
+    """Work-balanced contiguous partitions: rcppml_b200.shard.balanced_cuts — ascending cuts covering
+    0 .. n, every block within one item's weight of the ideal share — and the library's own column cuts (the ones the
+    in-process multi-GPU path takes from the caller's col_ptr) equal to it, on the reference's skewed datasets."""
+    import ctypes as C
+    from rcppml_b200 import _lib, shard
+    lib = _lib.load()
+    root = os.path.dirname(os.path.abspath(__file__))
+    cases = []
+    for name in ("pbmc3k_500x200.npz", "movielens.npz"):
+        g = np.load(os.path.join(root, "golden", name))
+        key = "indptr" if "indptr" in g.files else [f for f in g.files if f.endswith("p") or "ptr" in f][0]
+        cases.append(np.asarray(g[key], dtype=np.int32))
+    rng = np.random.default_rng(3)
+    cases.append(np.concatenate([[0], np.cumsum(rng.integers(0, 2000, size=777))]).astype(np.int32))
+    for indptr in cases:
+        n = indptr.size - 1
+        counts = np.diff(indptr)
+        for world in (2, 3, 8):
+            for per_item in (0, 16, 64):
+                cuts = shard.balanced_cuts(counts, world, per_item=per_item)
+                assert cuts[0] == 0 and cuts[-1] == n and np.all(np.diff(cuts) >= 0) and cuts.size == world + 1
+                work = counts.astype(np.float64) + per_item
+                ideal = work.sum() / world
+                for r in range(world):
+                    blk = work[cuts[r]:cuts[r + 1]].sum()
+                    assert abs(blk - ideal) <= 2 * work.max() + 1e-9, (world, per_item, r, blk, ideal)
+                out = np.zeros(world + 1, np.int32)
+                assert lib.rcppml_b200_balanced_col_cuts(indptr.ctypes.data_as(C.POINTER(C.c_int)), n, world, per_item,
+                                                         out.ctypes.data_as(C.POINTER(C.c_int))) == 0
+                assert np.array_equal(out, cuts), (world, per_item, out, cuts)

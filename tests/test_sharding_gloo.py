@@ -29,11 +29,16 @@ def _allgather_rows(block, first, total):
     return _allreduce(full)
 
 
-def _sharded_fit(rank, world, A, m, n, k, W0, H0, iters, solver, L1, L2):
+def _sharded_fit(rank, world, A, m, n, k, W0, H0, iters, solver, L1, L2, cuts=None):
+    """cuts = (col_cuts, row_cuts): explicit partition (rcppml_b200.shard.balanced_cuts); None = equal blocks."""
     from oracle import oracle as O
     from rcppml_b200 import shard
-    lo, cnt = shard.block_of(n, world, rank)          # my columns of H
-    r0, rc = shard.block_of(m, world, rank)           # my rows of W
+    if cuts is None:
+        lo, cnt = shard.block_of(n, world, rank)          # my columns of H
+        r0, rc = shard.block_of(m, world, rank)           # my rows of W
+    else:
+        lo, cnt = int(cuts[0][rank]), int(cuts[0][rank + 1] - cuts[0][rank])
+        r0, rc = int(cuts[1][rank]), int(cuts[1][rank + 1] - cuts[1][rank])
     Ap, Ai, Ax = shard.extract_shard(A.indptr, A.indices, A.data, lo, cnt)
     Ai, Ax = np.ascontiguousarray(Ai, np.int32), np.ascontiguousarray(Ax, np.float32)
     Rp, Ri, Rx = shard.extract_row_block(A.indptr, A.indices, A.data, r0, rc)
@@ -95,6 +100,22 @@ def _worker(rank, world, port, q):
                     loss=rel_err(hist, ref.loss_history))
         msgs.append((solver, errs))
         ok = ok and max(errs.values()) <= 1e-5
+    # The reference's own skewed data (pbmc3k block: gene rows with 0 .. 200 non-zeros) under the work-balanced
+    # partition the engine's in-process multi-GPU path uses (contiguous ranges cut on the prefix sum of nnz + k).
+    from rcppml_b200 import shard
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pbmc3k_500x200.npz"))
+    m, n, k, iters = 500, 200, 8, 4
+    import scipy.sparse as sp
+    A = sp.csc_matrix((g["data"].astype(np.float32), g["indices"], g["indptr"]), shape=(m, n))
+    A.sort_indices()
+    col_cuts = shard.balanced_cuts(np.diff(A.indptr), world, per_item=k)
+    row_cuts = shard.balanced_cuts(np.bincount(A.indices, minlength=m), world, per_item=k)
+    W0, H0 = O.initialize_factors(k, m, n, 42)
+    ref = O.nmf_fit(A.indptr, A.indices, A.data, m, n, k, W0, H0, max_iter=iters, tol=0.0, solver_mode=1, threads=1)
+    W_T, H, d, hist, _ = _sharded_fit(rank, world, A, m, n, k, W0, H0, iters, 1, (0.0, 0.0), (0.0, 0.0), cuts=(col_cuts, row_cuts))
+    errs = dict(W=rel_err(W_T, ref.W_T), H=rel_err(H, ref.H), d=rel_err(d, ref.d), loss=rel_err(hist, ref.loss_history))
+    msgs.append(("pbmc3k balanced", errs, col_cuts.tolist(), row_cuts.tolist()))
+    ok = ok and max(errs.values()) <= 1e-5 and row_cuts[1] != m // 2                  # skew: the balanced cut is not the middle
     q.put((rank, ok, msgs))
     dist.destroy_process_group()
 
