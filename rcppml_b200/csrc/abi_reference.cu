@@ -161,9 +161,13 @@ void drop_group() {                                            // engines first 
 }
 
 // Returns false (after warn) on any failure; fills res / W / H / d on success. Caller holds g_mu.
+// Optional: cv / cv_res — the speckled-mask cross-validation fit (nmf_fit_cv) instead of the plain one; mask_* — the
+// explicit user mask (CSC pattern of the whole matrix; every device keeps its two slices).
 bool fit_in_process_multi_gpu(int G, const int* devices, int m, int n, int64_t nnz, const int* col_ptr, const int* row_idx,
                               const double* values, int k, double* W, double* H, double* d, const rcppml_b200_config& cfg,
-                              rcppml_b200_result* res) {
+                              rcppml_b200_result* res, const rcppml_b200_cv_config* cv = nullptr,
+                              rcppml_b200_cv_result* cv_res = nullptr, int64_t mask_nnz = 0, const int* mask_p = nullptr,
+                              const int* mask_i = nullptr) {
     const auto t_call = std::chrono::steady_clock::now();
     const char* env = std::getenv("RCPPML_B200_CACHE");
     const bool cache = !(env && env[0] == '0');
@@ -211,6 +215,7 @@ bool fit_in_process_multi_gpu(int G, const int* devices, int m, int n, int64_t n
         double s = 0.0;
         for (int r = 0; r < G; ++r) s += sumsq[r];                           // rank order: identical on every device
         E.finish_matrix_local(s, nnz);
+        if (mask_nnz > 0) E.set_mask(mask_nnz, mask_p, mask_i);
         E.finish_factor_block_upload<double>(k);                             // own rows of W_T, own columns of H into place
         E.comm_prepare_local(devices);
         if (!bar.wait()) return;                                             // D: every replica buffer exists, own blocks in place
@@ -242,9 +247,14 @@ bool fit_in_process_multi_gpu(int G, const int* devices, int m, int n, int64_t n
         }
         E.pull_factor_blocks_from_peers();
         if (g == 0) marks[2] = since();
-        E.begin_fit(cfg);                                                    // (its first exchange orders the pulls against the peers' first stores)
-        if (g == 0) marks[5] = since();
-        E.iterate(cfg.max_iter);
+        if (cv) {
+            E.fit_cv(cfg, *cv);                                              // begin_fit + iterations + d absorbed into H
+            if (g == 0) { marks[5] = since(); E.get_cv_result(cv_res); }
+        } else {
+            E.begin_fit(cfg);                                                // (its first exchange orders the pulls against the peers' first stores)
+            if (g == 0) marks[5] = since();
+            E.iterate(cfg.max_iter);
+        }
         E.get_result(&rr[g]);
         if (g == 0) marks[3] = since();
         if (rr[g].status == 0)
@@ -367,9 +377,6 @@ void rcppml_gpu_nmf_cv_unified_float(
         if (refuse) { warn(refuse); return; }
         int dev0 = 0;
         if (usable_devices(&dev0, 1) < 1) { warn("no sm_100+ CUDA device"); return; }
-        EngineLease lease(dev0);
-        b200::Engine& E = lease.get();
-        E.set_matrix_and_factors_host<double, double>(*m, *n, static_cast<int64_t>(*nnz), col_ptr, row_idx, values, *k, W, H);
         rcppml_b200_config cfg{};
         cfg.k = *k; cfg.max_iter = *max_iter; cfg.tol = static_cast<float>(*tol);
         cfg.L1_H = static_cast<float>(*L1_H); cfg.L1_W = static_cast<float>(*L1_W);
@@ -383,20 +390,35 @@ void rcppml_gpu_nmf_cv_unified_float(
         cv.seed = static_cast<uint32_t>(*seed);
         cv.mask_zeros = *mask_zeros != 0;
         cv.cv_patience = 5;                                              // core/config.hpp:257, not on the wire
-        E.fit_cv(cfg, cv);
         rcppml_b200_result res{};
-        E.get_result(&res);
-        if (res.status != 0) { warn("Gram matrix not positive definite (Cholesky pivot <= 0)"); return; }
         rcppml_b200_cv_result cr{};
-        E.get_cv_result(&cr);
-        E.get_factors_host<double>(W, H, d);
+        int devices[8];
+        int G = 1;                                                       // RCPPML_NUM_GPUS, as for the standard entry
+        if (requested_gpus() > 1) G = std::min(requested_gpus(), usable_devices(devices, 8));
+        while (G > 1 && (*n < 64 * G || *m < 64 * G)) --G;
+        std::unique_ptr<EngineLease> lease_holder;
+        if (G > 1) {
+            std::lock_guard<std::mutex> guard(g_mu);
+            if (!fit_in_process_multi_gpu(G, devices, *m, *n, static_cast<int64_t>(*nnz), col_ptr, row_idx, values, *k, W, H, d,
+                                          cfg, &res, &cv, &cr))
+                return;
+        } else {
+            lease_holder.reset(new EngineLease(dev0));
+            b200::Engine& E = lease_holder->get();
+            E.set_matrix_and_factors_host<double, double>(*m, *n, static_cast<int64_t>(*nnz), col_ptr, row_idx, values, *k, W, H);
+            E.fit_cv(cfg, cv);
+            E.get_result(&res);
+            if (res.status != 0) { warn("Gram matrix not positive definite (Cholesky pivot <= 0)"); return; }
+            E.get_cv_result(&cr);
+            E.get_factors_host<double>(W, H, d);
+        }
         if (out_iter) *out_iter = res.iterations;
         if (out_converged) *out_converged = res.converged;
         if (out_train_loss) *out_train_loss = cr.train_loss;
         if (out_test_loss) *out_test_loss = cr.test_loss;
         if (out_best_test) *out_best_test = cr.best_test_loss;
         if (out_best_iter) *out_best_iter = cr.best_iter;
-        lease.commit();
+        if (lease_holder) lease_holder->commit();
         *out_status = 0;
     } catch (const std::exception& ex) {
         warn(ex.what());
@@ -666,15 +688,15 @@ static void nmf_unified_impl(
 
         const bool masked = mask_p && mask_i && mask_nnz && *mask_nnz > 0;
         int devices[8];
-        int G = 1;                                                      // masked path: single GPU
-        if (!masked && requested_gpus() > 1) G = std::min(requested_gpus(), usable_devices(devices, 8));
+        int G = 1;
+        if (requested_gpus() > 1) G = std::min(requested_gpus(), usable_devices(devices, 8));
         while (G > 1 && (*n < 64 * G || *m < 64 * G)) --G;             // every device needs a real block of each factor
         rcppml_b200_result res{};
         std::unique_ptr<EngineLease> lease_holder;
         if (G > 1) {
             std::lock_guard<std::mutex> guard(g_mu);
             if (!fit_in_process_multi_gpu(G, devices, *m, *n, static_cast<int64_t>(*nnz), col_ptr, row_idx, values, *k, W, H, d,
-                                          cfg, &res))
+                                          cfg, &res, nullptr, nullptr, masked ? *mask_nnz : 0, mask_p, mask_i))
                 return;
         } else {
             lease_holder.reset(new EngineLease(dev0));

@@ -682,6 +682,30 @@ for (m, n, k, solver, kw) in [(900, 500, 16, 0, {}), (1201, 777, 64, 1, dict(L1=
         assert np.array_equal(many2.W_T, many.W_T) and np.array_equal(many2.H, many.H), "second call on the cached engines differs"
         # (tr(AtA) is summed per device, then over devices: the loss may differ in its last bit, the factors may not)
         assert one.iterations == many.iterations and abs(one.train_loss - many.train_loss) <= 1e-6 * abs(one.train_loss)
+# the cross-validation entry (51 pointers) and the masked extension entry shard behind the same knob
+import scipy.sparse as sp
+m, n, k = 1500, 900, 16
+A = random_csc(m, n, 0.05, 77, ragged=True)
+rng = np.random.default_rng(5)
+W0, H0 = rng.random((m, k)), rng.random((n, k))
+M = sp.random(m, n, density=0.01, format="csc", random_state=rng, dtype=np.float32); M.sort_indices()
+mask = (M.indptr.astype(np.int32), M.indices.astype(np.int32))
+os.environ.pop("RCPPML_NUM_GPUS", None); os.environ.pop("RCPPML_B200_MC", None)
+_lib.load().rcppml_b200_release_cache()
+for solver in (0, 1):
+    cv1 = rb.bridge_nmf_cv_sparse(A.indptr, A.indices, A.data, m, n, k, W0, H0, max_iter=6, tol=0.0, solver_mode=solver, cd_maxit=15, holdout_fraction=0.1, cv_seed=3)
+    mk1 = rb.bridge_nmf_sparse(A.indptr, A.indices, A.data, m, n, k, W0, H0, max_iter=5, tol=0.0, solver_mode=solver, mask=mask)
+    for mc in ("2", "0"):
+        os.environ["RCPPML_NUM_GPUS"] = "2"; os.environ["RCPPML_B200_MC"] = mc
+        _lib.load().rcppml_b200_release_cache()
+        cv2 = rb.bridge_nmf_cv_sparse(A.indptr, A.indices, A.data, m, n, k, W0, H0, max_iter=6, tol=0.0, solver_mode=solver, cd_maxit=15, holdout_fraction=0.1, cv_seed=3)
+        mk2 = rb.bridge_nmf_sparse(A.indptr, A.indices, A.data, m, n, k, W0, H0, max_iter=5, tol=0.0, solver_mode=solver, mask=mask)
+        assert cv1.status == 0 and cv2.status == 0 and mk1.status == 0 and mk2.status == 0
+        assert np.array_equal(cv1.W_T, cv2.W_T) and np.array_equal(cv1.H, cv2.H) and np.array_equal(cv1.d, cv2.d), ("cv", solver, mc)
+        assert cv1.best_iter == cv2.best_iter and abs(cv1.test_loss - cv2.test_loss) <= 1e-6 * abs(cv1.test_loss)
+        assert np.array_equal(mk1.W_T, mk2.W_T) and np.array_equal(mk1.H, mk2.H) and np.array_equal(mk1.d, mk2.d), ("masked", solver, mc)
+    os.environ.pop("RCPPML_NUM_GPUS", None); os.environ.pop("RCPPML_B200_MC", None)
+    _lib.load().rcppml_b200_release_cache()
 print("INPROCESS_MULTIGPU_OK")
 '''
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600,
