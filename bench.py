@@ -456,6 +456,10 @@ def parity_vs_oracle(args, eng, cpu, mode):
     zero_w = bool(np.array_equal(W == 0, ref.W_T == 0))
     zero_h = bool(np.array_equal(H == 0, ref.H == 0))
     out = {"against": "oracle (oracle/nmf_oracle.cpp, the cpu_baseline run)", "matrix": cpu["sample"].split(",")[0],
+           "oracle_pinning": "the oracle reproduces the reference's own nmf_fit (nmf/fit_cpu.hpp compiled unmodified against an "
+                             "Eigen stand-in) bit for bit (tests/test_reference_fit.py); the rounding INSIDE Eigen — notably its "
+                             "fp32 rankUpdate for the Gram, here fp64-accumulated and rounded once — is the stand-in's "
+                             "definition and cannot be pinned without Eigen (DESIGN.md section 3)",
            "matrix_identical_to_oracle_generator": same_matrix, "iterations": iters, "rows_compared_W": int(W.shape[0]),
            "rows_compared_H": int(H.shape[0]), "rel_err": errs, "max_rel_err": max(errs.values()),
            "zero_pattern_equal": zero_w and zero_h, "bit_identical_W": bool(np.array_equal(W, ref.W_T)),

@@ -538,6 +538,37 @@ def test_large_synthetic_properties(eng):
         assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("solver,density", [(1, 4e-3), (0, 1e-3)])
+def test_c4_shaped_fit_matches_oracle_with_the_default_kernel_policy(eng, oracle, solver, density):
+    """The configuration the headline is quoted on, at a quarter of its rows and columns and with NOTHING forced:
+    250 K x 25 K, k = 64; Cholesky with C4's column statistics (1000 non-zeros per column, ~100 per row: 2.5e7 non-zeros —
+    the H half-step on half_step_kernel<16,1>, the W half-step on the tiled kernel with 8-column batches, the dynamic
+    work counters, CUDA-graph replay), coordinate descent on a quarter of that density (the CPU side of a CD fit is what
+    bounds the test) — against the oracle on the same generator matrix: W, H, d, loss history to 1e-5 (in practice
+    bit for bit), equal zero patterns, and in CD mode equal sweep totals. (bench.py makes the same comparison on the
+    full 1e8-non-zero matrix.)"""
+    import rcppml_b200 as rb
+    from rcppml_b200 import synth
+    m, n, k, iters = 250_000, 25_000, 64, 3
+    eng.set_matrix_synthetic(m, n, 0, density, synth.SEED_A)
+    Ap, Ai, Ax = eng.get_matrix()
+    hp, hi, hx = oracle.synth_csc(m, n, 0, density, synth.SEED_A)
+    assert np.array_equal(Ap, hp) and np.array_equal(Ai, hi) and np.array_equal(Ax, hx)
+    eng.init_factors(k, 42)
+    W0, H0 = oracle.initialize_factors(k, m, n, 42)
+    cfg = rb.make_config(k, max_iter=iters, tol=0.0, solver_mode=solver, cd_maxit=100)
+    res = eng.fit(cfg)
+    W, H, d = eng.get_factors()
+    hist = eng.loss_history(iters)
+    ref = oracle.nmf_fit(hp, hi, hx, m, n, k, W0, H0, max_iter=iters, tol=0.0, solver_mode=solver, cd_maxit=100)
+    assert res.status == 0 and res.iterations == iters
+    assert rel_err(W, ref.W_T) <= RTOL and rel_err(H, ref.H) <= RTOL and rel_err(d, ref.d) <= RTOL
+    assert rel_err(hist, ref.loss_history) <= RTOL
+    assert np.array_equal(W == 0, ref.W_T == 0) and np.array_equal(H == 0, ref.H == 0)
+    if solver == 0:
+        assert eng.cd_sweeps() == ref.cd_sweeps
+
+
 def test_multi_gpu_matches_single_gpu():
     """Column-sharded fit over NCCL (tests/multigpu_check.py) — needs >= 2 GPUs on the box."""
     import os
