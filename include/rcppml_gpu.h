@@ -273,7 +273,7 @@ int rcppml_b200_factor_checksum(rcppml_b200_engine* e, uint64_t* out3);
 int rcppml_b200_get_matrix(rcppml_b200_engine* e, int64_t* nnz, int* col_ptr, int* row_idx, float* values);
 int rcppml_b200_get_matrix_t(rcppml_b200_engine* e, int* col_ptr, int* row_idx, float* values);
 
-/* Explicit user mask (single GPU): CSC pattern (m x n) of the masked entries; mask_nnz = 0 clears it.
+/* Explicit user mask: CSC pattern (m x n, the WHOLE pattern on every rank of a sharded fit) of the masked entries; mask_nnz = 0 clears it.
  * With a mask set, fits follow the reference's masked path (nmf/masked_nnls.hpp). */
 int rcppml_b200_set_mask(rcppml_b200_engine* e, int64_t mask_nnz, const int* mask_col_ptr, const int* mask_row_idx);
 
@@ -299,7 +299,7 @@ int rcppml_b200_begin_fit(rcppml_b200_engine* e, const rcppml_b200_config* cfg);
 int rcppml_b200_iterate(rcppml_b200_engine* e, int n_iters);
 int rcppml_b200_fit(rcppml_b200_engine* e, const rcppml_b200_config* cfg);   /* begin_fit + iterate(max_iter) */
 int rcppml_b200_get_result(rcppml_b200_engine* e, rcppml_b200_result* out);
-/* nmf_fit_cv (single GPU): MSE, standard variant, no user mask. On return H has d absorbed (fit_cv.hpp:1639-1641),
+/* nmf_fit_cv (one GPU or sharded): MSE, standard variant, no user mask. On return H has d absorbed (fit_cv.hpp:1639-1641),
  * get_result gives iterations / converged / final_tol, get_cv_result the losses. */
 int rcppml_b200_fit_cv(rcppml_b200_engine* e, const rcppml_b200_config* cfg, const rcppml_b200_cv_config* cv);
 int rcppml_b200_get_cv_result(rcppml_b200_engine* e, rcppml_b200_cv_result* out);
