@@ -345,6 +345,9 @@ int rcppml_b200_comm_mc_export(rcppml_b200_engine* e, char* blob128);
 int rcppml_b200_comm_mc_import(rcppml_b200_engine* e, const char* all_blobs);
 int rcppml_b200_comm_mc_bind(rcppml_b200_engine* e);      /* after import succeeded on EVERY rank (binding blocks until all joined) */
 int rcppml_b200_comm_mc_finish(rcppml_b200_engine* e);
+/* The multicast set-up failed on some rank: give multicast up for this engine, keeping the factors (they move into plain
+ * allocations that the IPC pair can export). Call on every rank, then use comm_ipc_export / import. */
+int rcppml_b200_comm_mc_disable(rcppml_b200_engine* e);
 /* Drops every peer mapping (IPC or multicast): the loop falls back to NCCL until the next export / import. */
 int rcppml_b200_comm_p2p_close(rcppml_b200_engine* e);
 

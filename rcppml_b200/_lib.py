@@ -125,7 +125,7 @@ def load() -> C.CDLL:
     lib.rcppml_b200_comm_ipc_export.argtypes = [E, C.c_char_p]
     lib.rcppml_b200_comm_ipc_import.argtypes = [E, C.c_char_p]
     for name in ("rcppml_b200_comm_mc_wanted", "rcppml_b200_comm_mc_ready", "rcppml_b200_comm_mc_finish", "rcppml_b200_comm_p2p_close",
-                 "rcppml_b200_comm_mc_bind"):
+                 "rcppml_b200_comm_mc_bind", "rcppml_b200_comm_mc_disable"):
         getattr(lib, name).argtypes = [E]
     lib.rcppml_b200_comm_mc_export.argtypes = [E, C.c_char_p]
     lib.rcppml_b200_comm_mc_import.argtypes = [E, C.c_char_p]

@@ -52,12 +52,13 @@ void Engine::comm_ipc_close() {
         cudaStreamSynchronize(side_stream);
     }
     mc_close();
+    for (int r = 0; r < 8; ++r) {                            // imported VMM mappings (also of an import that failed half-way)
+        if (peer_map_W[r].va || peer_map_W[r].handle) peer_map_W[r].release();
+        if (peer_map_H[r].va || peer_map_H[r].handle) peer_map_H[r].release();
+    }
     for (int r = 0; r < world && peers_ready && !peers_local; ++r) {
         if (r == rank) continue;
-        if (peers_vmm) {                                     // multicast path: the peers' physical allocations were mapped here
-            peer_map_W[r].release();
-            peer_map_H[r].release();
-        } else {
+        if (!peers_vmm) {
             cudaIpcCloseMemHandle(peer_W[r]);
             cudaIpcCloseMemHandle(peer_H[r]);
         }
@@ -270,6 +271,31 @@ void Engine::comm_mc_bind() {
     mc_bind_and_map(mcW.handle, mcH.handle, rank == 0);
 }
 
+// Fall-back of the host launcher when the multicast set-up failed on some rank: give up multicast for this engine but
+// KEEP the factors — they move (device to device) from the VMM allocations into plain cudaMalloc buffers, which the
+// CUDA-IPC path (unicast peer stores) can export. Every rank must call it (same decision on all ranks).
+void Engine::mc_disable_keep_factors() {
+    use_device();
+    comm_ipc_close();
+    mc_wanted = false;
+    if (!factors_ready) return;
+    auto move = [&](FactorBuffer& buf) {
+        if (!buf.vmm || !buf.ptr) return;
+        const size_t n_floats = buf.count;
+        float* plain = nullptr;
+        B200_CUDA_CHECK(cudaMalloc(&plain, n_floats * sizeof(float)));
+        B200_CUDA_CHECK(cudaMemcpyAsync(plain, buf.ptr, n_floats * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+        B200_CUDA_CHECK(cudaStreamSynchronize(stream));
+        buf.want_vmm = false;
+        buf.release();                                       // unmaps and frees the VMM allocation
+        buf.ptr = plain;
+        buf.count = n_floats;
+    };
+    drop_iteration_graph();
+    move(W_T);
+    move(H);
+}
+
 // After every rank imported (a barrier of the host launcher): the exported descriptors are no longer needed.
 void Engine::comm_mc_finish() {
     for (int& fd : mc_export_fds) {
@@ -435,6 +461,10 @@ int rcppml_b200_comm_mc_import(rcppml_b200_engine* e, const char* all_blobs) {
 }
 int rcppml_b200_comm_mc_bind(rcppml_b200_engine* e) {
     try { e->impl.comm_mc_bind(); return 0; }
+    catch (const std::exception& ex) { b200::g_last_error = ex.what(); return -1; }
+}
+int rcppml_b200_comm_mc_disable(rcppml_b200_engine* e) {
+    try { e->impl.mc_disable_keep_factors(); return 0; }
     catch (const std::exception& ex) { b200::g_last_error = ex.what(); return -1; }
 }
 int rcppml_b200_comm_p2p_close(rcppml_b200_engine* e) {

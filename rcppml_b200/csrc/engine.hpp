@@ -236,6 +236,7 @@ public:
     void comm_mc_import(const char* all_blobs);
     void comm_mc_bind();
     void comm_mc_finish();
+    void mc_disable_keep_factors();                          // multicast set-up failed somewhere: plain buffers, same contents
     float* mc_alias(const float* replica_ptr) const;         // multicast address of a word of W_T / H (nullptr: not ready)
 
 private:

@@ -278,8 +278,8 @@ class Engine:
         library at comm_init: NVSwitch MULTICAST (comm_mc_export/import: the factors are VMM allocations bound to
         multicast objects; a normalised block is written into every replica with one multimem.st per word) where the
         devices support it and RCPPML_B200_MC != 0, else unicast peer stores over CUDA IPC mappings
-        (comm_ipc_export/import). Returns False (and leaves the NCCL loop active) when RCPPML_B200_P2P=0 or the
-        set-up failed on any rank."""
+        (comm_ipc_export/import) — also the fall-back when the multicast set-up fails on any rank. Returns False (and
+        leaves the NCCL loop active) when RCPPML_B200_P2P=0."""
         import os
         import torch
         self.p2p_mode = "nccl"
@@ -311,8 +311,10 @@ class Engine:
             if ok:
                 self.p2p_mode = "multicast"
                 return True
-            self._lib.rcppml_b200_comm_p2p_close(self._h)   # (VMM factors cannot go through CUDA IPC: NCCL loop)
-            return False
+            # fall back to unicast peer stores: the factors move into plain allocations that CUDA IPC can export
+            if not all_ok(self._lib.rcppml_b200_comm_mc_disable(self._h)):
+                self._lib.rcppml_b200_comm_p2p_close(self._h)
+                return False
         buf = C.create_string_buffer(192)
         _lib.check(self._lib.rcppml_b200_comm_ipc_export(self._h, buf), "comm_ipc_export")
         _lib.check(self._lib.rcppml_b200_comm_ipc_import(self._h, gather(buf.raw)), "comm_ipc_import")

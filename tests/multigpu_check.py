@@ -36,8 +36,8 @@ def main():
     # p2p: "mc" = NVSwitch multicast replication (multimem.st from the normalising Gram kernel), "uc" = unicast peer stores
     # from the solve kernels (RCPPML_B200_MC=0), False = NCCL loop
     # (RCPPML_B200_MC: 1 = the Gram kernel replicates the normalised block, 2 = the solve kernel's stores are multicast)
-    # "mcfail": the multicast set-up is made to fail on import (RCPPML_B200_MC_TEST_FAIL): comm_enable_p2p must return
-    # False on every rank and the fit must run on the NCCL loop with the VMM-backed factors it already allocated
+    # "mcfail": the multicast set-up is made to fail on import (RCPPML_B200_MC_TEST_FAIL): comm_enable_p2p must fall back
+    # to unicast peer stores on every rank, moving the VMM-backed factors it already holds into plain allocations
     MC_ENV = {"mc": "1", "mc2": "2", "uc": "0", False: "0", "mcfail": "2"}
     combos = [(a, b, "1") for a in ("mc", "mc2", "uc", False) for b in cases] + [(a, b, "2") for a in ("mc2", "uc") for b in cases]
     combos += [("mcfail", cases[0], "1"), ("mcfail", cases[1], "1")]
@@ -65,8 +65,8 @@ def main():
             eng.set_matrix_synthetic_sharded(m, n, dens, synth.SEED_A)
         eng.init_factors(k, 42, 0)
         if p2p == "mcfail":
-            assert not eng.comm_enable_p2p(dist), "the failed multicast set-up must fall back"
-            mode = "nccl after a failed multicast set-up"
+            assert eng.comm_enable_p2p(dist) and eng.p2p_mode == "unicast", "the failed multicast set-up must fall back to unicast peer stores"
+            mode = "unicast after a failed multicast set-up"
             os.environ.pop("RCPPML_B200_MC_TEST_FAIL", None)
         elif p2p:
             assert eng.comm_enable_p2p(dist), "peer-memory path not enabled"
