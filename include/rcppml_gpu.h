@@ -337,8 +337,8 @@ int rcppml_b200_comm_ipc_import(rcppml_b200_engine* e, const char* all_handles);
  * multicast objects, and the kernel that normalises a freshly solved block writes it into EVERY replica with one
  * multimem.st per word. Same call pattern as the IPC pair: export a 128-byte blob per rank after the factors exist,
  * all-gather the blobs (rank-major, world x 128 bytes), import on every rank, check that every rank succeeded, bind, barrier, finish. The blobs carry POSIX
- * file descriptors that a peer duplicates with pidfd_getfd (same user). On failure: last_error, and the loop falls
- * back to NCCL. */
+ * file descriptors that a peer duplicates with pidfd_getfd (same user). On failure on any rank: last_error, then
+ * comm_mc_disable on every rank and the IPC pair (unicast peer stores) instead. */
 int rcppml_b200_comm_mc_wanted(rcppml_b200_engine* e);
 int rcppml_b200_comm_mc_ready(rcppml_b200_engine* e);
 int rcppml_b200_comm_mc_export(rcppml_b200_engine* e, char* blob128);
