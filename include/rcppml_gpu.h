@@ -245,6 +245,15 @@ int rcppml_b200_set_matrix_f32(rcppml_b200_engine* e, int m, int n, int64_t nnz,
                                const int* row_idx, const float* values);
 int rcppml_b200_set_matrix_f64(rcppml_b200_engine* e, int m, int n, int64_t nnz, const int* col_ptr,
                                const int* row_idx, const double* values);
+/* The caller already holds CSC(A^T) with ascending column ids per row — e.g. a StreamPress .spz file written with
+ * include_transpose and decoded by the package's own reader (streampress/sparsepress_v2.hpp:58, :652, :1318; SURVEY.md
+ * 8f-4): both operands are uploaded as they are, the device transpose is skipped. Single GPU. */
+int rcppml_b200_set_matrix_with_transpose_f32(rcppml_b200_engine* e, int m, int n, int64_t nnz, const int* col_ptr,
+                                              const int* row_idx, const float* values, const int* t_col_ptr,
+                                              const int* t_row_idx, const float* t_values);
+int rcppml_b200_set_matrix_with_transpose_f64(rcppml_b200_engine* e, int m, int n, int64_t nnz, const int* col_ptr,
+                                              const int* row_idx, const double* values, const int* t_col_ptr,
+                                              const int* t_row_idx, const double* t_values);
 /* Synthetic generator of SURVEY.md §8d, on the device. Columns [col_begin, col_begin+n_local)
  * of the m x n_global matrix; per column round(m*density) candidate rows
  * SplitMix64::hash(seed, t, j) mod m, sorted + deduplicated; value 0.5 + uniform<float>(seed+1, r, j). */

@@ -86,6 +86,8 @@ def load() -> C.CDLL:
     ip, fp, dp = C.POINTER(C.c_int), C.POINTER(C.c_float), C.POINTER(C.c_double)
     lib.rcppml_b200_set_matrix_f32.argtypes = [E, C.c_int, C.c_int, C.c_int64, ip, ip, fp]
     lib.rcppml_b200_set_matrix_f64.argtypes = [E, C.c_int, C.c_int, C.c_int64, ip, ip, dp]
+    lib.rcppml_b200_set_matrix_with_transpose_f32.argtypes = [E, C.c_int, C.c_int, C.c_int64, ip, ip, fp, ip, ip, fp]
+    lib.rcppml_b200_set_matrix_with_transpose_f64.argtypes = [E, C.c_int, C.c_int, C.c_int64, ip, ip, dp, ip, ip, dp]
     lib.rcppml_b200_set_matrix_synthetic.argtypes = [E, C.c_int, C.c_int, C.c_int, C.c_double, C.c_uint64]
     lib.rcppml_b200_set_matrix_synthetic_sharded.argtypes = [E, C.c_int, C.c_int, C.c_double, C.c_uint64]
     lib.rcppml_b200_set_matrix_sharded_f32.argtypes = [E, C.c_int, C.c_int, ip, ip, fp, ip, ip, fp]

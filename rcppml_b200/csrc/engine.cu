@@ -502,6 +502,30 @@ void Engine::set_matrix_host(int m_, int n_, int64_t nnz_, const int* col_ptr, c
 template void Engine::set_matrix_host<float>(int, int, int64_t, const int*, const int*, const float*);
 template void Engine::set_matrix_host<double>(int, int, int64_t, const int*, const int*, const double*);
 
+// The caller already holds CSC(Aᵀ) — e.g. a StreamPress .spz file written with include_transpose, decoded by the package's
+// own reader (streampress/sparsepress_v2.hpp:58, :652, :1318): both operands are uploaded as they are and
+// the device transpose (radix sort, 6 ms at C4) is skipped. The transpose must list, for every row of A, its entries
+// with ascending column indices (what Eigen's transpose() and the .spz writer produce); it is trusted, like A itself.
+template <class ValT>
+void Engine::set_matrix_host_with_transpose(int m_, int n_, int64_t nnz_, const int* col_ptr, const int* row_idx,
+                                            const ValT* values, const int* t_col_ptr, const int* t_row_idx, const ValT* t_values) {
+    use_device();
+    B200_REQUIRE(world == 1, "set_matrix_with_transpose: single-GPU entry (sharded fits slice their operands themselves)");
+    B200_REQUIRE(col_ptr[n_] == nnz_ && t_col_ptr[m_] == nnz_, "set_matrix_with_transpose: A and its transpose disagree on nnz");
+    set_dims(m_, n_);
+    nnz = nnz_w = nnz_;
+    const auto t0 = std::chrono::steady_clock::now();
+    upload_csc<ValT>(n, nnz, col_ptr, row_idx, values, Ap, Ai, Ax);
+    upload_csc<ValT>(m, nnz, t_col_ptr, t_row_idx, t_values, Atp, Ati, Atx);
+    const auto t1 = std::chrono::steady_clock::now();
+    finish_matrix();
+    has_mask = false;
+    phase_ms[0] = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    phase_ms[1] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();
+}
+template void Engine::set_matrix_host_with_transpose<float>(int, int, int64_t, const int*, const int*, const float*, const int*, const int*, const float*);
+template void Engine::set_matrix_host_with_transpose<double>(int, int, int64_t, const int*, const int*, const double*, const int*, const int*, const double*);
+
 // Sharded: the caller hands this rank its column block A[:, J] (CSC, n_loc columns, global row ids) and
 // its row block A[I, :] (CSC, n columns, row ids relative to the block). See rcppml_b200/shard.py.
 template <class ValT>
@@ -1857,6 +1881,14 @@ int rcppml_b200_set_matrix_f32(rcppml_b200_engine* e, int m, int n, int64_t nnz,
 }
 int rcppml_b200_set_matrix_f64(rcppml_b200_engine* e, int m, int n, int64_t nnz, const int* col_ptr, const int* row_idx, const double* values) {
     B200_API_BEGIN e->impl.set_matrix_host<double>(m, n, nnz, col_ptr, row_idx, values); B200_API_END
+}
+int rcppml_b200_set_matrix_with_transpose_f32(rcppml_b200_engine* e, int m, int n, int64_t nnz, const int* col_ptr, const int* row_idx,
+                                              const float* values, const int* t_col_ptr, const int* t_row_idx, const float* t_values) {
+    B200_API_BEGIN e->impl.set_matrix_host_with_transpose<float>(m, n, nnz, col_ptr, row_idx, values, t_col_ptr, t_row_idx, t_values); B200_API_END
+}
+int rcppml_b200_set_matrix_with_transpose_f64(rcppml_b200_engine* e, int m, int n, int64_t nnz, const int* col_ptr, const int* row_idx,
+                                              const double* values, const int* t_col_ptr, const int* t_row_idx, const double* t_values) {
+    B200_API_BEGIN e->impl.set_matrix_host_with_transpose<double>(m, n, nnz, col_ptr, row_idx, values, t_col_ptr, t_row_idx, t_values); B200_API_END
 }
 int rcppml_b200_set_matrix_synthetic(rcppml_b200_engine* e, int m, int n_local, int col_begin, double density, uint64_t seed) {
     B200_API_BEGIN e->impl.set_matrix_synthetic(m, n_local, col_begin, density, seed); B200_API_END

@@ -43,6 +43,9 @@ public:
     template <class ValT>
     void set_matrix_host(int m, int n, int64_t nnz, const int* col_ptr, const int* row_idx, const ValT* values);
     template <class ValT>
+    void set_matrix_host_with_transpose(int m, int n, int64_t nnz, const int* col_ptr, const int* row_idx, const ValT* values,
+                                        const int* t_col_ptr, const int* t_row_idx, const ValT* t_values);
+    template <class ValT>
     void set_matrix_sharded(int m, int n, const int* cb_ptr, const int* cb_idx, const ValT* cb_val, const int* rb_ptr,
                             const int* rb_idx, const ValT* rb_val);
     void set_matrix_synthetic(int m, int n_local, int col_begin, double density, uint64_t seed);

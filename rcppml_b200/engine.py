@@ -76,6 +76,25 @@ class Engine:
         _lib.check(rc, "set_matrix")
         self._refresh_shard(m, n)
 
+    def set_matrix_with_transpose(self, m, n, A, At):
+        """A = (indptr, indices, data) of the m x n matrix, At = the same of its transpose (n x m, ascending column ids
+        per row — e.g. a .spz file written with include_transpose): both are uploaded, no device transpose."""
+        ap, ai = np.ascontiguousarray(A[0], np.int32), np.ascontiguousarray(A[1], np.int32)
+        tp, ti = np.ascontiguousarray(At[0], np.int32), np.ascontiguousarray(At[1], np.int32)
+        nnz = int(ap[n])
+        if A[2].dtype == np.float64:
+            ax, tx = np.ascontiguousarray(A[2], np.float64), np.ascontiguousarray(At[2], np.float64)
+            rc = self._lib.rcppml_b200_set_matrix_with_transpose_f64(self._h, m, n, nnz, _p(ap, C.c_int), _p(ai, C.c_int),
+                                                                     _p(ax, C.c_double), _p(tp, C.c_int), _p(ti, C.c_int),
+                                                                     _p(tx, C.c_double))
+        else:
+            ax, tx = np.ascontiguousarray(A[2], np.float32), np.ascontiguousarray(At[2], np.float32)
+            rc = self._lib.rcppml_b200_set_matrix_with_transpose_f32(self._h, m, n, nnz, _p(ap, C.c_int), _p(ai, C.c_int),
+                                                                     _p(ax, C.c_float), _p(tp, C.c_int), _p(ti, C.c_int),
+                                                                     _p(tx, C.c_float))
+        _lib.check(rc, "set_matrix_with_transpose")
+        self._refresh_shard(m, n)
+
     def set_matrix_synthetic(self, m, n_local, col_begin, density, seed):
         _lib.check(self._lib.rcppml_b200_set_matrix_synthetic(self._h, m, n_local, col_begin, density, seed),
                    "set_matrix_synthetic")

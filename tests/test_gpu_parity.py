@@ -569,6 +569,29 @@ def test_c4_shaped_fit_matches_oracle_with_the_default_kernel_policy(eng, oracle
         assert eng.cd_sweeps() == ref.cd_sweeps
 
 
+def test_pre_stored_transpose_skips_the_device_transpose(eng):
+    """rcppml_b200_set_matrix_with_transpose (a .spz file can carry CSC(A^T)): handing the engine the
+    transpose it would have built gives the same device operands and the same fit, bit for bit."""
+    import rcppml_b200 as rb
+    m, n, k = 2100, 900, 20
+    A = random_csc(m, n, 0.04, 5, ragged=True)
+    At = A.T.tocsc()
+    At.sort_indices()
+    outs = []
+    for pre in (False, True):
+        if pre:
+            eng.set_matrix_with_transpose(m, n, (A.indptr, A.indices, A.data), (At.indptr, At.indices, At.data))
+        else:
+            eng.set_matrix(m, n, A.indptr, A.indices, A.data)
+        tp, ti, tx = eng.get_matrix_t()
+        assert np.array_equal(tp, At.indptr) and np.array_equal(ti, At.indices) and np.array_equal(tx, At.data)
+        eng.init_factors(k, 42)
+        res = eng.fit(rb.make_config(k, max_iter=5, tol=0.0, solver_mode=1, L1=(0.01, 0.01)))
+        assert res.status == 0
+        outs.append(eng.get_factors() + (eng.loss_history(5),))
+    assert all(np.array_equal(a, b) for a, b in zip(outs[0], outs[1]))
+
+
 def test_multi_gpu_matches_single_gpu():
     """Column-sharded fit over NCCL (tests/multigpu_check.py) — needs >= 2 GPUs on the box."""
     import os
