@@ -197,7 +197,10 @@ void Engine::comm_mc_export(char* blob128) {
     McBlob b{};
     b.pid = static_cast<int>(getpid());
     b.fd_W = b.fd_H = b.fd_mcW = b.fd_mcH = -1;
-    prctl(PR_SET_PTRACER, PR_SET_PTRACER_ANY, 0, 0, 0);          // Yama: let the sibling ranks duplicate the descriptors
+    // Yama (ptrace_scope 1) would refuse pidfd_getfd between sibling processes: open the window for the duration of the
+    // hand-over only — comm_mc_finish closes it again together with the exported descriptors
+    prctl(PR_SET_PTRACER, PR_SET_PTRACER_ANY, 0, 0, 0);
+    mc_ptracer_window = true;
     B200_CU_CHECK(drv.MemExportToShareableHandle(&b.fd_W, W_T.phys, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0));
     B200_CU_CHECK(drv.MemExportToShareableHandle(&b.fd_H, H.phys, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0));
     mc_export_fds[0] = b.fd_W; mc_export_fds[1] = b.fd_H;
@@ -301,6 +304,10 @@ void Engine::comm_mc_finish() {
     for (int& fd : mc_export_fds) {
         if (fd >= 0) close(fd);
         fd = -1;
+    }
+    if (mc_ptracer_window) {
+        prctl(PR_SET_PTRACER, 0, 0, 0, 0);
+        mc_ptracer_window = false;
     }
 }
 

@@ -229,6 +229,7 @@ public:
     bool mc_local = false;            // in-process group: the handles are shared and owned by the orchestrator
     MappedHandle peer_map_W[8], peer_map_H[8];   // cross-process: the peers' physical allocations mapped here
     int mc_export_fds[4] = {-1, -1, -1, -1};
+    bool mc_ptracer_window = false;   // PR_SET_PTRACER_ANY is in force (export .. finish)
     void mc_decide();                                        // after rank / world are known
     void mc_grant_local_access(const int* devices);          // in-process: every device of the group may access W_T / H
     void mc_create(CUmemGenericAllocationHandle* hW, CUmemGenericAllocationHandle* hH, bool shareable);
