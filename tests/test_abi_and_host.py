@@ -274,3 +274,72 @@ def test_balanced_cuts_host_logic_and_library_agree():
                 assert lib.rcppml_b200_balanced_col_cuts(indptr.ctypes.data_as(C.POINTER(C.c_int)), n, world, per_item,
                                                          out.ctypes.data_as(C.POINTER(C.c_int))) == 0
                 assert np.array_equal(out, cuts), (world, per_item, out, cuts)
+
+
+def test_bench_parity_object_host_logic(oracle, monkeypatch):
+    """bench.parity_vs_oracle (the N = 1 `parity` object of every bench line) with a stand-in engine: an engine that
+    returns the oracle's own factors is reported ok with zero error and equal zero patterns; one whose W differs in a
+    single entry beyond 1e-5, or whose zero pattern differs, is reported NOT ok. No CUDA."""
+    import sys
+    import types
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    import bench
+    import rcppml_b200 as rb
+    m, n, k, iters = 400, 150, 8, 3
+    Ap, Ai, Ax = oracle.synth_csc(m, n, 0, 0.05, bench.SEED_A)
+    W0, H0 = oracle.initialize_factors(k, m, n, bench.SEED_INIT)
+    ref = oracle.nmf_fit(Ap, Ai, Ax, m, n, k, W0, H0, max_iter=iters, tol=0.0, solver_mode=1)
+    cpu = {"_fit": ref, "_shape": (m, n), "_A": (Ap, Ai, Ax), "full_matrix": False, "sample": "leading block, test"}
+    args = types.SimpleNamespace(k=k, L1=0.0, L2=0.0)
+
+    def make_engine(W, H, d):
+        class Eng:
+            def __init__(self, dev):
+                pass
+
+            def set_matrix(self, *a):
+                pass
+
+            def set_factors(self, *a):
+                pass
+
+            def fit(self, cfg):
+                return types.SimpleNamespace(status=0, iterations=cfg.max_iter)
+
+            def get_factors(self):
+                return W, H, d
+
+            def loss_history(self, count):
+                return ref.loss_history[:count]
+
+            def cd_sweeps(self):
+                return ref.cd_sweeps
+
+            def close(self):
+                pass
+        return Eng
+
+    monkeypatch.setattr(rb, "Engine", make_engine(ref.W_T.copy(), ref.H.copy(), ref.d.copy()))
+    good = bench.parity_vs_oracle(args, None, cpu, 1)
+    assert good["ok"] and good["max_rel_err"] == 0.0 and good["zero_pattern_equal"] and good["bit_identical_W"]
+    assert good["rows_compared_W"] == m and good["rows_compared_H"] == n and good["iterations"] == iters
+    W_bad = ref.W_T.copy()
+    i, j = np.unravel_index(np.argmax(W_bad), W_bad.shape)
+    W_bad[i, j] *= np.float32(1.001)
+    monkeypatch.setattr(rb, "Engine", make_engine(W_bad, ref.H.copy(), ref.d.copy()))
+    bad = bench.parity_vs_oracle(args, None, cpu, 1)
+    assert not bad["ok"] and bad["rel_err"]["W"] > 1e-5 and not bad["bit_identical_W"]
+    H_bad = ref.H.copy()
+    zi = np.argwhere(H_bad == 0)
+    if len(zi):
+        H_bad[tuple(zi[0])] = np.float32(1e-12)            # inside the tolerance, but a different active set
+        monkeypatch.setattr(rb, "Engine", make_engine(ref.W_T.copy(), H_bad, ref.d.copy()))
+        pat = bench.parity_vs_oracle(args, None, cpu, 1)
+        assert not pat["ok"] and not pat["zero_pattern_equal"] and pat["max_rel_err"] <= 1e-5
+    # both arms name the workload identically, whatever the run-specific details
+    a1 = bench.parse_args(["--gpus", "1"])
+    a2 = bench.parse_args(["--impl", "reference", "--gpus", "8", "--steps", "20", "--warmup", "5"])
+    assert bench.workload_string(a1) == bench.workload_string(a2)
+    assert bench.parse_args(["--rows", "5", "--cols", "6", "--rank", "7"]).m == 5
