@@ -2,7 +2,9 @@
 (rcppml_b200/csrc/engine.cu enqueue_iteration + comm.cu) — column blocks of H solved from A[:,J_g],
 row blocks of W solved from A[I_g,:]^T, all-reduced Grams / row sums / cross term, all-gather of the
 factor blocks — restated with the CPU oracle's primitives and gloo collectives, must reproduce the
-unsharded oracle fit. Also covers the host-side shard helpers (rcppml_b200/shard.py)."""
+unsharded oracle fit; likewise the sharded explicit-mask schedule (slices of the mask pattern, all-reduced loss) and a
+work-balanced partition on the reference's skewed pbmc3k block. Also covers the host-side shard helpers
+(rcppml_b200/shard.py)."""
 import os
 import sys
 
@@ -83,6 +85,59 @@ def _sharded_fit(rank, world, A, m, n, k, W0, H0, iters, solver, L1, L2, cuts=No
     return W_T, H, d, np.array(hist), (lo, cnt)
 
 
+def _sharded_masked_fit(rank, world, A, M, m, n, k, W0, H0, iters, solver, L1, L2):
+    """CPU twin of Engine::enqueue_iteration_masked on `world` ranks: every rank solves its column block of H and its row
+    block of W_T from its slices of A AND of the mask pattern (columns J of the pattern, columns I of its transpose);
+    the unmodified Grams, the row sums and the explicit loss over the non-masked non-zeros are all-reduced."""
+    from oracle import oracle as O
+    from rcppml_b200 import shard
+    lo, cnt = shard.block_of(n, world, rank)
+    r0, rc = shard.block_of(m, world, rank)
+    Ap, Ai, Ax = shard.extract_shard(A.indptr, A.indices, A.data, lo, cnt)
+    Ai, Ax = np.ascontiguousarray(Ai, np.int32), np.ascontiguousarray(Ax, np.float32)
+    Mp, Mi, _ = shard.extract_shard(M.indptr, M.indices, M.data, lo, cnt)
+    Mi = np.ascontiguousarray(Mi, np.int32)
+    At, Mt = A.T.tocsc(), M.T.tocsc()
+    At.sort_indices(); Mt.sort_indices()
+    Atp, Ati, Atx = shard.extract_shard(At.indptr, At.indices, At.data, r0, rc)          # (A[I, :])^T: rc columns
+    Ati, Atx = np.ascontiguousarray(Ati, np.int32), np.ascontiguousarray(Atx, np.float32)
+    Mtp, Mti, _ = shard.extract_shard(Mt.indptr, Mt.indices, Mt.data, r0, rc)
+    Mti = np.ascontiguousarray(Mti, np.int32)
+    W_T, H = W0.copy(), H0.copy()
+    hist = []
+
+    def gram(X):
+        G = _allreduce(X.astype(np.float64).T @ X.astype(np.float64)).astype(np.float32)
+        G[np.diag_indices(k)] += np.float32(1e-15)
+        return G
+
+    G_w = gram(W_T[r0:r0 + rc])
+    for it in range(iters):
+        warm = it > 0
+        Hb = H[lo:lo + cnt].copy()
+        O.masked_nnls(Ap, Ai, Ax, m, W_T, G_w, Hb, Mp, Mi, L1=L1[1], L2=L2[1], solver_mode=solver, warm_start=warm)
+        d = _allreduce(np.abs(Hb.astype(np.float64)).sum(axis=0)).astype(np.float32) + np.float32(1e-15)
+        Hb /= d
+        G_h = gram(Hb)
+        H = _allgather_rows(Hb, lo, n)
+        Wb = W_T[r0:r0 + rc].copy()
+        O.masked_nnls(Atp, Ati, Atx, n, H, G_h, Wb, Mtp, Mti, L1=L1[0], L2=L2[0], solver_mode=solver, warm_start=warm)
+        d = _allreduce(np.abs(Wb.astype(np.float64)).sum(axis=0)).astype(np.float32) + np.float32(1e-15)
+        Wb /= d
+        G_w = gram(Wb)
+        W_T = _allgather_rows(Wb, r0, m)
+        # explicit loss over the non-masked non-zeros of MY columns (masked_nnls.hpp:251-282), then over ranks
+        sq = 0.0
+        for jl in range(cnt):
+            rows = Ai[Ap[jl]:Ap[jl + 1]]
+            vals = Ax[Ap[jl]:Ap[jl + 1]]
+            keep = ~np.isin(rows, Mi[Mp[jl]:Mp[jl + 1]])
+            pred = ((W_T[rows[keep]] * d) * H[lo + jl]).sum(axis=1, dtype=np.float32)
+            sq += float(np.sum((vals[keep] - pred).astype(np.float32).astype(np.float64) ** 2))
+        hist.append(np.float32(_allreduce(np.array([sq]))[0]))
+    return W_T, H, d, np.array(hist)
+
+
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -99,6 +154,20 @@ def _worker(rank, world, port, q):
         errs = dict(W=rel_err(W_T, ref.W_T), H=rel_err(H, ref.H), d=rel_err(d, ref.d),
                     loss=rel_err(hist, ref.loss_history))
         msgs.append((solver, errs))
+        ok = ok and max(errs.values()) <= 1e-5
+    # explicit user mask, sharded (Engine::enqueue_iteration_masked): CD and per-column Cholesky
+    m, n, k, iters = 260, 170, 6, 3
+    A = random_csc(m, n, 0.1, 61, ragged=True)
+    M = random_csc(m, n, 0.04, 62)
+    M.sort_indices()
+    W0, H0 = O.initialize_factors(k, m, n, 42)
+    for solver in (0, 1):
+        L1, L2 = (0.01, 0.02), (0.02, 0.01)
+        ref = O.nmf_fit(A.indptr, A.indices, A.data, m, n, k, W0, H0, max_iter=iters, tol=0.0, solver_mode=solver,
+                        L1=L1, L2=L2, threads=1, mask=(M.indptr, M.indices))
+        W_T, H, d, hist = _sharded_masked_fit(rank, world, A, M, m, n, k, W0, H0, iters, solver, L1, L2)
+        errs = dict(W=rel_err(W_T, ref.W_T), H=rel_err(H, ref.H), d=rel_err(d, ref.d), loss=rel_err(hist, ref.loss_history))
+        msgs.append(("masked", solver, errs))
         ok = ok and max(errs.values()) <= 1e-5
     # The reference's own skewed data (pbmc3k block: gene rows with 0 .. 200 non-zeros) under the work-balanced
     # partition the engine's in-process multi-GPU path uses (contiguous ranges cut on the prefix sum of nnz + k).
