@@ -373,6 +373,63 @@ double rcppml_b200_last_call_wall_ms(void);
  * columns, balanced by work = non-zeros + per_item per column (rcppml_b200/shard.py balanced_cuts). */
 int rcppml_b200_balanced_col_cuts(const int* col_ptr, int n, int world, int per_item, int* cuts);
 
+/* ---- Part 3: on-disk ingest — StreamPress v2 `.spz` files -------------------------------------------
+ * rcppml_sp_read_gpu / rcppml_sp_free_gpu replace src/sp_gpu_bridge.cu:42-123 and :133-155, called through R's .C by
+ * st_read_gpu / st_free_gpu (R/sp_gpu.R:53-141): the file is decoded (v2 only: status 4 otherwise; 1 cannot open,
+ * 2 read failed, 3 too small, 5 decode error) and left on `device_id` as CSC — int32 col_ptr[n+1], int32 row_idx[nnz],
+ * double values[nnz] — the three device addresses returned encoded as doubles, which is what
+ * rcppml_gpu_nmf_zerocopy_double takes. The reference's test helper looks the first one up as rcppml_st_read_gpu
+ * (tests/testthat/helper-test-utils.R:278); both spellings are exported. */
+void rcppml_sp_read_gpu(const char** path_ptr, int* device_id, double* out_col_ptr_addr, double* out_row_idx_addr,
+                        double* out_values_addr, int* out_m, int* out_n, double* out_nnz, int* out_status);
+void rcppml_sp_free_gpu(double* col_ptr_addr, double* row_idx_addr, double* values_addr, int* out_status);
+void rcppml_st_read_gpu(const char** path_ptr, int* device_id, double* out_col_ptr_addr, double* out_row_idx_addr,
+                        double* out_values_addr, int* out_m, int* out_n, double* out_nnz, int* out_status);
+void rcppml_st_free_gpu(double* col_ptr_addr, double* row_idx_addr, double* values_addr, int* out_status);
+
+/* The reader by itself (host only, no device): what Rcpp_sp_read / Rcpp_sp_read_transpose / Rcpp_sp_metadata
+ * (src/sparsepress_bridge.cpp:226-266, :273-286, :293-395) do with streampress::v2::decompress_v2 /
+ * decompress_v2_transpose (sparsepress_v2.hpp:897, :1318). Functions return 0 or the status codes above
+ * (6: the file has no pre-stored transpose, 7: bad argument, -1: other; text in rcppml_b200_last_error). */
+typedef struct rcppml_b200_spz rcppml_b200_spz;
+typedef struct {
+    int      m, n;
+    int64_t  nnz;
+    int      chunk_cols, num_chunks;
+    int      value_type;          /* header_v2.hpp:45-53: 0 uint8 1 uint16 2 uint32 3 float32 4 float16 5 quant8 6 float64 */
+    int      row_sorted;
+    int      has_transpose, transpose_chunks, transp_chunk_cols;
+    int      has_obs, has_var, has_metadata;
+    int      row_permutation_len; /* entries of the stored row permutation (0: none) */
+    float    density;
+    int64_t  file_bytes, transpose_offset, metadata_offset, metadata_bytes;
+    uint32_t stored_crc32;        /* footer (header_v2.hpp:233-266); compare with rcppml_b200_spz_crc32 */
+} rcppml_b200_spz_info;
+int  rcppml_b200_spz_open(const char* path, rcppml_b200_spz** out);
+void rcppml_b200_spz_close(rcppml_b200_spz* h);
+int  rcppml_b200_spz_get_info(const rcppml_b200_spz* h, rcppml_b200_spz_info* out);
+int  rcppml_b200_spz_crc32(const rcppml_b200_spz* h, uint32_t* computed);
+/* section 0: A (n columns); section 1: the pre-stored CSC(A^T) (m columns). Any column range [c0, c1). */
+int  rcppml_b200_spz_range_nnz(const rcppml_b200_spz* h, int section, int c0, int c1, int64_t* nnz);
+int  rcppml_b200_spz_col_counts(const rcppml_b200_spz* h, int section, int threads, int* counts);
+/* col_ptr: c1 - c0 + 1 entries rebased to 0; row_idx / values: range_nnz entries. reorder: apply the stored row
+ * permutation as decompress_v2 does (section 0 only). threads <= 0: every core. */
+int  rcppml_b200_spz_read_f32(const rcppml_b200_spz* h, int section, int c0, int c1, int reorder, int threads,
+                              int* col_ptr, int* row_idx, float* values);
+int  rcppml_b200_spz_read_f64(const rcppml_b200_spz* h, int section, int c0, int c1, int reorder, int threads,
+                              int* col_ptr, int* row_idx, double* values);
+/* Raw bytes of a metadata record (header_v2.hpp:108-113: 0 rownames, 1 colnames — NUL-separated —, 2 row permutation). */
+int  rcppml_b200_spz_metadata(const rcppml_b200_spz* h, int key, unsigned char* buf, int64_t capacity, int64_t* bytes);
+/* File -> engine. One GPU: A plus the stored transpose when the file has a usable one (no device transpose; reported in
+ * *used_stored_transpose). After comm_init (+ optional set_partition): this rank decodes only its column block of A and
+ * its row block (columns of the stored transpose); collective like every sharded set_matrix_*. */
+int  rcppml_b200_set_matrix_spz(rcppml_b200_engine* e, const rcppml_b200_spz* h, int threads, int* used_stored_transpose);
+/* Sharded operands with the row block already transposed (what the two sections of a .spz file deliver):
+ * A[:, J] as CSC (n_loc columns, global row ids) and (A[I, :])^T as CSC (m_loc columns, global column ids). */
+int  rcppml_b200_set_matrix_sharded_with_transpose_f32(rcppml_b200_engine* e, int m, int n, const int* colblk_ptr,
+                                                       const int* colblk_idx, const float* colblk_val,
+                                                       const int* tblk_ptr, const int* tblk_idx, const float* tblk_val);
+
 #ifdef __cplusplus
 }
 #endif

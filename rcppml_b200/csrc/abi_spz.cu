@@ -1,0 +1,248 @@
+// abi_spz.cu — on-disk ingest: StreamPress v2 `.spz` files into device memory.
+//   * rcppml_sp_read_gpu / rcppml_sp_free_gpu: the reference's own entry points (src/sp_gpu_bridge.cu:42-152, called by
+//     st_read_gpu / st_free_gpu, R/sp_gpu.R:53-141) — device-resident CSC (int32 pointers and indices, double values)
+//     whose addresses travel as doubles into rcppml_gpu_nmf_zerocopy_double. The reference decodes v2 on the CPU and
+//     uploads ("v2 adapter: CPU decode + GPU upload", sp_gpu_bridge.cu:20); so does this: the decode is the threaded
+//     host reader of spz_reader.cpp, the upload three copies.
+//   * rcppml_b200_spz_*: the reader by itself (host buffers; any column range of A or of the stored transpose).
+//   * rcppml_b200_set_matrix_spz: file -> engine. One GPU: A and, when the file carries it, the pre-stored transpose
+//     (no device transpose). Sharded: this rank decodes ONLY its column block of A and its row block from the
+//     transpose section — no rank ever holds the whole matrix.
+#include "engine.hpp"
+#include "spz_reader.hpp"
+
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+struct rcppml_b200_spz {
+    b200::spz::File file;
+    explicit rcppml_b200_spz(const char* path) : file(path) {}
+};
+
+namespace {
+
+using b200::spz::Error;
+using b200::spz::File;
+
+// Reader errors keep their status code (the reference's 1..5, spz_reader.hpp); anything else is -1.
+template <class F>
+int guarded(F&& body) {
+    try { body(); return 0; }
+    catch (const Error& e) { b200::g_last_error = e.what(); return e.status; }
+    catch (const std::exception& e) { b200::g_last_error = e.what(); return -1; }
+    catch (...) { b200::g_last_error = "unknown error"; return -1; }
+}
+
+struct HostCsc {
+    std::vector<int> p, i;
+    std::vector<float> x;
+    int64_t nnz = 0;
+};
+
+void decode_range(const File& f, int section, uint32_t c0, uint32_t c1, bool reorder, int threads, HostCsc& out) {
+    out.nnz = static_cast<int64_t>(f.range_nnz(section, c0, c1));
+    out.p.resize(static_cast<size_t>(c1 - c0) + 1);
+    out.i.resize(static_cast<size_t>(std::max<int64_t>(out.nnz, 1)));
+    out.x.resize(static_cast<size_t>(std::max<int64_t>(out.nnz, 1)));
+    f.decode<float>(section, c0, c1, out.p.data(), out.i.data(), out.x.data(), reorder, threads);
+}
+
+// The stored transpose describes the matrix as written: with a row permutation in play the reference's reader maps
+// the row indices of A (sparsepress_v2.hpp:1089-1101) but not the columns of the transpose section (:1318-1467), so
+// the two sections no longer describe the same matrix and the transpose is rebuilt on the device instead.
+bool transpose_usable(const File& f) {
+    const auto& in = f.info();
+    return in.transpose_chunks > 0 && in.transpose_nnz == in.nnz && !(in.row_sorted && in.row_permutation_len > 0);
+}
+
+void read_gpu(const char* path, int dev, double* out_col_ptr_addr, double* out_row_idx_addr, double* out_values_addr,
+              int* out_m, int* out_n, double* out_nnz) {
+    File f(path);
+    const auto& in = f.info();
+    const int64_t nnz = static_cast<int64_t>(in.nnz);
+    std::vector<int> p(static_cast<size_t>(in.n) + 1), i(static_cast<size_t>(std::max<int64_t>(nnz, 1)));
+    std::vector<double> x(static_cast<size_t>(std::max<int64_t>(nnz, 1)));
+    f.decode<double>(0, 0, in.n, p.data(), i.data(), x.data(), /*reorder=*/true, /*threads=*/0);
+
+    int prev = 0;
+    B200_CUDA_CHECK(cudaGetDevice(&prev));
+    B200_CUDA_CHECK(cudaSetDevice(dev));
+    int* dp = nullptr; int* di = nullptr; double* dx = nullptr;
+    auto release = [&] { if (dp) cudaFree(dp); if (di) cudaFree(di); if (dx) cudaFree(dx); cudaSetDevice(prev); };
+    try {
+        B200_CUDA_CHECK(cudaMalloc(&dp, p.size() * sizeof(int)));
+        B200_CUDA_CHECK(cudaMalloc(&di, i.size() * sizeof(int)));
+        B200_CUDA_CHECK(cudaMalloc(&dx, x.size() * sizeof(double)));
+        B200_CUDA_CHECK(cudaMemcpy(dp, p.data(), p.size() * sizeof(int), cudaMemcpyHostToDevice));
+        if (nnz > 0) {
+            B200_CUDA_CHECK(cudaMemcpy(di, i.data(), static_cast<size_t>(nnz) * sizeof(int), cudaMemcpyHostToDevice));
+            B200_CUDA_CHECK(cudaMemcpy(dx, x.data(), static_cast<size_t>(nnz) * sizeof(double), cudaMemcpyHostToDevice));
+        }
+    } catch (...) { release(); throw; }
+    cudaSetDevice(prev);
+    *out_m = static_cast<int>(in.m);
+    *out_n = static_cast<int>(in.n);
+    *out_nnz = static_cast<double>(nnz);
+    *out_col_ptr_addr = static_cast<double>(reinterpret_cast<uintptr_t>(dp));
+    *out_row_idx_addr = static_cast<double>(reinterpret_cast<uintptr_t>(di));
+    *out_values_addr = static_cast<double>(reinterpret_cast<uintptr_t>(dx));
+}
+
+}  // namespace
+
+extern "C" {
+
+// ---- the reference's entry points ---------------------------------------------------------------------------------
+
+void rcppml_sp_read_gpu(const char** path_ptr, int* device_id, double* out_col_ptr_addr, double* out_row_idx_addr,
+                        double* out_values_addr, int* out_m, int* out_n, double* out_nnz, int* out_status) {
+    *out_status = -1;
+    const int st = guarded([&] {
+        read_gpu(*path_ptr, *device_id, out_col_ptr_addr, out_row_idx_addr, out_values_addr, out_m, out_n, out_nnz);
+    });
+    if (st != 0) std::fprintf(stderr, "[sp_read_gpu] %s\n", b200::g_last_error.c_str());
+    // 1 cannot open, 2 read failed, 3 too small, 4 not v2, 5 everything the decode can throw (sp_gpu_bridge.cu:57-120)
+    *out_status = (st >= 0 && st <= 4) ? st : 5;
+}
+
+void rcppml_sp_free_gpu(double* col_ptr_addr, double* row_idx_addr, double* values_addr, int* out_status) {
+    *out_status = 0;
+    for (double* a : {col_ptr_addr, row_idx_addr, values_addr}) {
+        if (*a != 0.0) cudaFree(reinterpret_cast<void*>(static_cast<uintptr_t>(*a)));
+        *a = 0.0;
+    }
+    cudaGetLastError();
+}
+
+// The reference's test helper probes the GPU library for `rcppml_st_read_gpu` (tests/testthat/helper-test-utils.R:278)
+// while its bridge defines `rcppml_sp_read_gpu`; both names are exported.
+void rcppml_st_read_gpu(const char** path_ptr, int* device_id, double* a, double* b, double* c, int* out_m, int* out_n,
+                        double* out_nnz, int* out_status) {
+    rcppml_sp_read_gpu(path_ptr, device_id, a, b, c, out_m, out_n, out_nnz, out_status);
+}
+void rcppml_st_free_gpu(double* a, double* b, double* c, int* out_status) { rcppml_sp_free_gpu(a, b, c, out_status); }
+
+// ---- the reader by itself (no device involved) ----------------------------------------------------------------------
+
+int rcppml_b200_spz_open(const char* path, rcppml_b200_spz** out) {
+    *out = nullptr;
+    return guarded([&] { *out = new rcppml_b200_spz(path); });
+}
+
+void rcppml_b200_spz_close(rcppml_b200_spz* h) { delete h; }
+
+int rcppml_b200_spz_get_info(const rcppml_b200_spz* h, rcppml_b200_spz_info* out) {
+    return guarded([&] {
+        const auto& in = h->file.info();
+        std::memset(out, 0, sizeof(*out));
+        out->m = static_cast<int>(in.m); out->n = static_cast<int>(in.n); out->nnz = static_cast<int64_t>(in.nnz);
+        out->chunk_cols = static_cast<int>(in.chunk_cols); out->num_chunks = static_cast<int>(in.num_chunks);
+        out->value_type = in.value_type; out->row_sorted = in.row_sorted;
+        out->has_transpose = in.transpose_chunks > 0 || in.transpose_offset != 0;
+        out->transpose_chunks = static_cast<int>(in.transpose_chunks);
+        out->transp_chunk_cols = static_cast<int>(in.transp_chunk_cols ? in.transp_chunk_cols : in.chunk_cols);
+        out->has_obs = in.obs_table_offset != 0; out->has_var = in.var_table_offset != 0;
+        out->has_metadata = in.metadata_offset != 0;
+        out->row_permutation_len = static_cast<int>(in.row_permutation_len);
+        out->density = in.density;
+        out->file_bytes = static_cast<int64_t>(in.file_bytes);
+        out->transpose_offset = static_cast<int64_t>(in.transpose_offset);
+        out->metadata_offset = static_cast<int64_t>(in.metadata_offset);
+        out->metadata_bytes = static_cast<int64_t>(in.metadata_bytes);
+        out->stored_crc32 = in.footer_crc32;
+    });
+}
+
+int rcppml_b200_spz_crc32(const rcppml_b200_spz* h, uint32_t* computed) {
+    return guarded([&] { *computed = h->file.compute_crc32(); });
+}
+
+int rcppml_b200_spz_range_nnz(const rcppml_b200_spz* h, int section, int c0, int c1, int64_t* nnz) {
+    return guarded([&] {
+        B200_REQUIRE(c0 >= 0 && c1 >= c0, "spz: bad column range");
+        *nnz = static_cast<int64_t>(h->file.range_nnz(section, static_cast<uint32_t>(c0), static_cast<uint32_t>(c1)));
+    });
+}
+
+int rcppml_b200_spz_col_counts(const rcppml_b200_spz* h, int section, int threads, int* counts) {
+    return guarded([&] { h->file.col_counts(section, counts, threads); });
+}
+
+int rcppml_b200_spz_read_f32(const rcppml_b200_spz* h, int section, int c0, int c1, int reorder, int threads, int* col_ptr,
+                             int* row_idx, float* values) {
+    return guarded([&] {
+        B200_REQUIRE(c0 >= 0 && c1 >= c0, "spz: bad column range");
+        h->file.decode<float>(section, static_cast<uint32_t>(c0), static_cast<uint32_t>(c1), col_ptr, row_idx, values,
+                              reorder != 0, threads);
+    });
+}
+
+int rcppml_b200_spz_read_f64(const rcppml_b200_spz* h, int section, int c0, int c1, int reorder, int threads, int* col_ptr,
+                             int* row_idx, double* values) {
+    return guarded([&] {
+        B200_REQUIRE(c0 >= 0 && c1 >= c0, "spz: bad column range");
+        h->file.decode<double>(section, static_cast<uint32_t>(c0), static_cast<uint32_t>(c1), col_ptr, row_idx, values,
+                               reorder != 0, threads);
+    });
+}
+
+int rcppml_b200_spz_metadata(const rcppml_b200_spz* h, int key, unsigned char* buf, int64_t capacity, int64_t* bytes) {
+    return guarded([&] {
+        const auto rec = h->file.metadata_record(static_cast<uint8_t>(key));
+        *bytes = static_cast<int64_t>(rec.size());
+        if (buf && capacity >= static_cast<int64_t>(rec.size()) && !rec.empty()) std::memcpy(buf, rec.data(), rec.size());
+    });
+}
+
+// ---- file -> engine -------------------------------------------------------------------------------------------------
+
+int rcppml_b200_set_matrix_spz(rcppml_b200_engine* e, const rcppml_b200_spz* h, int threads, int* used_stored_transpose) {
+    return guarded([&] {
+        const File& f = h->file;
+        const auto& in = f.info();
+        const int m = static_cast<int>(in.m), n = static_cast<int>(in.n);
+        const bool stored = transpose_usable(f);
+        if (used_stored_transpose) *used_stored_transpose = stored ? 1 : 0;
+        b200::Engine& eng = e->impl;
+        HostCsc a, t;
+        if (eng.world == 1) {
+            decode_range(f, 0, 0, in.n, true, threads, a);
+            if (stored) {
+                decode_range(f, 1, 0, in.m, false, threads, t);
+                eng.set_matrix_host_with_transpose<float>(m, n, a.nnz, a.p.data(), a.i.data(), a.x.data(), t.p.data(),
+                                                          t.i.data(), t.x.data());
+            } else {
+                eng.set_matrix_host<float>(m, n, a.nnz, a.p.data(), a.i.data(), a.x.data());
+            }
+            return;
+        }
+        // sharded: this rank's column block of A, and its row block — as columns of the stored transpose when the file
+        // has one, else filtered out of a full decode (rows relative to the block, the set_matrix_sharded contract)
+        int cb = 0, nl = 0, rb = 0, ml = 0;
+        eng.planned_blocks(m, n, &cb, &nl, &rb, &ml);
+        decode_range(f, 0, static_cast<uint32_t>(cb), static_cast<uint32_t>(cb + nl), true, threads, a);
+        if (stored) {
+            decode_range(f, 1, static_cast<uint32_t>(rb), static_cast<uint32_t>(rb + ml), false, threads, t);
+            eng.set_matrix_sharded_with_transpose<float>(m, n, a.p.data(), a.i.data(), a.x.data(), t.p.data(), t.i.data(),
+                                                         t.x.data());
+            return;
+        }
+        HostCsc full;
+        decode_range(f, 0, 0, in.n, true, threads, full);
+        t.p.assign(static_cast<size_t>(n) + 1, 0);
+        t.i.clear(); t.x.clear();
+        for (int j = 0; j < n; ++j) {
+            for (int q = full.p[j]; q < full.p[j + 1]; ++q) {
+                const int r = full.i[q];
+                if (r >= rb && r < rb + ml) { t.i.push_back(r - rb); t.x.push_back(full.x[q]); }
+            }
+            t.p[j + 1] = static_cast<int>(t.i.size());
+        }
+        if (t.i.empty()) { t.i.push_back(0); t.x.push_back(0.f); }
+        eng.set_matrix_sharded<float>(m, n, a.p.data(), a.i.data(), a.x.data(), t.p.data(), t.i.data(), t.x.data());
+    });
+}
+
+}  // extern "C"

@@ -545,6 +545,30 @@ void Engine::set_matrix_sharded(int m_, int n_, const int* cb_ptr, const int* cb
 template void Engine::set_matrix_sharded<float>(int, int, const int*, const int*, const float*, const int*, const int*, const float*);
 template void Engine::set_matrix_sharded<double>(int, int, const int*, const int*, const double*, const int*, const int*, const double*);
 
+template <class ValT>
+void Engine::set_matrix_sharded_with_transpose(int m_, int n_, const int* cb_ptr, const int* cb_idx, const ValT* cb_val,
+                                               const int* tb_ptr, const int* tb_idx, const ValT* tb_val) {
+    use_device();
+    set_dims(m_, n_);
+    nnz = cb_ptr[n_loc];
+    upload_csc<ValT>(n_loc, nnz, cb_ptr, cb_idx, cb_val, Ap, Ai, Ax);
+    nnz_w = tb_ptr[m_loc];
+    upload_csc<ValT>(std::max(m_loc, 0), nnz_w, tb_ptr, tb_idx, tb_val, Atp, Ati, Atx);
+    finish_matrix();
+    has_mask = false;
+}
+template void Engine::set_matrix_sharded_with_transpose<float>(int, int, const int*, const int*, const float*, const int*, const int*, const float*);
+template void Engine::set_matrix_sharded_with_transpose<double>(int, int, const int*, const int*, const double*, const int*, const int*, const double*);
+
+void Engine::planned_blocks(int m_, int n_, int* cb, int* nl, int* rb, int* ml) const {
+    auto one = [&](const std::vector<int>& pending, int total, int* begin, int* count) {
+        if (static_cast<int>(pending.size()) == world + 1) { *begin = pending[rank]; *count = pending[rank + 1] - pending[rank]; }
+        else block_of(total, world, rank, begin, count);
+    };
+    one(pending_col_cuts, n_, cb, nl);
+    one(pending_row_cuts, m_, rb, ml);
+}
+
 // ---- in-process multi-GPU ingest (abi_reference.cu: RCPPML_NUM_GPUS) ------------------------------------------------
 // Each device receives ONLY its column block of the host matrix over its own PCIe link (nnz/G entries instead of nnz);
 // the row block it needs for the W half-step is assembled from all devices' column blocks over NVLink
@@ -1899,6 +1923,10 @@ int rcppml_b200_set_matrix_synthetic_sharded(rcppml_b200_engine* e, int m, int n
 int rcppml_b200_set_matrix_sharded_f32(rcppml_b200_engine* e, int m, int n, const int* cb_ptr, const int* cb_idx,
                                        const float* cb_val, const int* rb_ptr, const int* rb_idx, const float* rb_val) {
     B200_API_BEGIN e->impl.set_matrix_sharded<float>(m, n, cb_ptr, cb_idx, cb_val, rb_ptr, rb_idx, rb_val); B200_API_END
+}
+int rcppml_b200_set_matrix_sharded_with_transpose_f32(rcppml_b200_engine* e, int m, int n, const int* cb_ptr, const int* cb_idx,
+                                                      const float* cb_val, const int* tb_ptr, const int* tb_idx, const float* tb_val) {
+    B200_API_BEGIN e->impl.set_matrix_sharded_with_transpose<float>(m, n, cb_ptr, cb_idx, cb_val, tb_ptr, tb_idx, tb_val); B200_API_END
 }
 int rcppml_b200_set_partition(rcppml_b200_engine* e, const int* col_cuts, const int* row_cuts) {
     B200_API_BEGIN e->impl.set_partition(col_cuts, row_cuts); B200_API_END

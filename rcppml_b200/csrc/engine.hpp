@@ -48,6 +48,13 @@ public:
     template <class ValT>
     void set_matrix_sharded(int m, int n, const int* cb_ptr, const int* cb_idx, const ValT* cb_val, const int* rb_ptr,
                             const int* rb_idx, const ValT* rb_val);
+    // Sharded, the row block already transposed: A[:, J] (CSC, n_loc columns, global row ids) and (A[I, :])^T (CSC,
+    // m_loc columns, global column ids ascending) — e.g. two column ranges of a .spz file with a pre-stored transpose.
+    template <class ValT>
+    void set_matrix_sharded_with_transpose(int m, int n, const int* cb_ptr, const int* cb_idx, const ValT* cb_val,
+                                           const int* tb_ptr, const int* tb_idx, const ValT* tb_val);
+    // The blocks set_dims would give this rank for an m x n matrix (pending explicit cuts, else equal blocks).
+    void planned_blocks(int m, int n, int* col_begin_out, int* n_loc_out, int* row_begin_out, int* m_loc_out) const;
     void set_matrix_synthetic(int m, int n_local, int col_begin, double density, uint64_t seed);
     void set_matrix_synthetic_sharded(int m, int n, double density, uint64_t seed);
 
