@@ -8,5 +8,8 @@ from .engine import Engine, FitResult, make_config, nccl_unique_id  # noqa: F401
 from .bridge import bridge_nmf_cv_sparse, bridge_nmf_sparse, gpu_detect, gpu_nmf_zerocopy  # noqa: F401
 from .nmf import NMFModel, nmf, nnls  # noqa: F401
 from .project import evaluate, predict  # noqa: F401
+from .streampress import (GpuSparseMatrix, SpzFile, nmf_zerocopy, st_free_gpu, st_info, st_read,  # noqa: F401
+                          st_read_gpu, st_read_transpose)
 
-__all__ = ["Engine", "FitResult", "make_config", "nccl_unique_id", "bridge_nmf_sparse", "bridge_nmf_cv_sparse", "gpu_detect", "gpu_nmf_zerocopy", "nmf", "NMFModel", "nnls", "predict", "evaluate"]
+__all__ = ["Engine", "FitResult", "make_config", "nccl_unique_id", "bridge_nmf_sparse", "bridge_nmf_cv_sparse", "gpu_detect", "gpu_nmf_zerocopy", "nmf", "NMFModel", "nnls", "predict", "evaluate",
+           "SpzFile", "GpuSparseMatrix", "st_info", "st_read", "st_read_transpose", "st_read_gpu", "st_free_gpu", "nmf_zerocopy"]

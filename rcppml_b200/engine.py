@@ -95,6 +95,19 @@ class Engine:
         _lib.check(rc, "set_matrix_with_transpose")
         self._refresh_shard(m, n)
 
+    def set_matrix_spz(self, path, threads=0):
+        """A StreamPress v2 `.spz` file straight into the engine. One GPU: A plus the file's pre-stored
+        transpose when it has a usable one (then no device transpose). After comm_init (+ set_partition): this rank
+        decodes only its column block of A and its row block (columns of the stored transpose) — collective, like
+        every sharded set_matrix_*. Returns True when the stored transpose was used."""
+        from .streampress import SpzFile
+        with SpzFile(path) as f:
+            used = C.c_int(0)
+            rc = self._lib.rcppml_b200_set_matrix_spz(self._h, f._h, int(threads), C.byref(used))
+            _lib.check(rc, "set_matrix_spz")
+            self._refresh_shard(f.raw.m, f.raw.n)
+        return bool(used.value)
+
     def set_matrix_synthetic(self, m, n_local, col_begin, density, seed):
         _lib.check(self._lib.rcppml_b200_set_matrix_synthetic(self._h, m, n_local, col_begin, density, seed),
                    "set_matrix_synthetic")
