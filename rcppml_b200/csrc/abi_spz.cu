@@ -50,7 +50,7 @@ void decode_range(const File& f, int section, uint32_t c0, uint32_t c1, bool reo
 }
 
 // The stored transpose describes the matrix as written: with a row permutation in play the reference's reader maps
-// the row indices of A (sparsepress_v2.hpp:1089-1101) but not the columns of the transpose section (:1318-1467), so
+// the row indices of A (sparsepress_v2.hpp:1093-1104) but not the columns of the transpose section (:1318-1467), so
 // the two sections no longer describe the same matrix and the transpose is rebuilt on the device instead.
 bool transpose_usable(const File& f) {
     const auto& in = f.info();

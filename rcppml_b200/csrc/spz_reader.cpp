@@ -1,6 +1,6 @@
 // spz_reader.cpp — see spz_reader.hpp. Host code only (compiled by g++ with -ffp-contract=off: the QUANT8 value map is
 // `offset + scale * q` with separately rounded multiply and add, as the reference's -O2 build computes it,
-// sparsepress_v2.hpp:1073-1079).
+// sparsepress_v2.hpp:1064-1068).
 #include "spz_reader.hpp"
 
 #include <fcntl.h>
@@ -394,7 +394,7 @@ uint32_t File::section_rows(int section) const { return section == 0 ? info_.m :
 namespace {
 
 // Column counts of a chunk: the varint table that follows the u32 size prefix of a non-empty gap stream
-// (sparsepress_v2.hpp:143-151). An empty chunk is written WITHOUT the prefix (:92, the early return), so its
+// (sparsepress_v2.hpp:143-151). An empty chunk is written WITHOUT the prefix (:94, the early return), so its
 // stream is just num_cols zero bytes; every count is 0 by the descriptor and the stream is not consulted.
 // Returns the cursor positioned at the rANS part of the stream.
 Cursor chunk_counts(const Chunk& ck, std::vector<uint32_t>& counts) {
@@ -575,7 +575,7 @@ void File::decode(int section, uint32_t c0, uint32_t c1, int32_t* p, int32_t* i,
             }
         }
 
-        // gaps -> row indices, the running row restarting at every column (sparsepress_v2.hpp:1018-1029)
+        // gaps -> row indices, the running row restarting at every column (sparsepress_v2.hpp:1016-1027)
         if (gs.has_overflow)
             for (uint64_t k = 0; k < skip; ++k) if (gsym[k] == kEscape) gs.overflow.varint("overflow section truncated");
         const uint32_t* g = gsym + skip;
@@ -598,7 +598,7 @@ void File::decode(int section, uint32_t c0, uint32_t c1, int32_t* p, int32_t* i,
 
     parallel_for(order.size(), threads, [&](size_t k) { chunk_task(pieces[order[k]]); });
 
-    // ---- stored row permutation, applied the way decompress_v2 applies it (sparsepress_v2.hpp:1089-1101): the record
+    // ---- stored row permutation, applied the way decompress_v2 applies it (sparsepress_v2.hpp:1093-1104): the record
     // is used as a plain map on the decoded indices; indices at or beyond its length stay. Rows inside a column are
     // NOT re-sorted afterwards (nor does the reference). ----
     if (section == 0 && reorder && info_.row_sorted) {

@@ -86,7 +86,7 @@ public:
 
     // Decode columns [c0, c1) of a section: p[0 .. c1-c0] (rebased to 0), i[], x[] sized by range_nnz.
     // reorder: apply the stored row permutation exactly as the reference's decompress_v2 does
-    // (sparsepress_v2.hpp:1089-1101; section 0 only — decompress_v2_transpose never reorders). threads <= 0: all cores.
+    // (sparsepress_v2.hpp:1093-1104; section 0 only — decompress_v2_transpose never reorders). threads <= 0: all cores.
     template <typename V>
     void decode(int section, uint32_t c0, uint32_t c1, int32_t* p, int32_t* i, V* x, bool reorder, int threads) const;
 

@@ -90,7 +90,7 @@ def test_golden_file_holds_the_matrix_that_was_written(name):
 
 
 def test_row_sorted_file_applies_the_stored_permutation_like_decompress_v2():
-    """sparsepress_v2.hpp:1089-1101 maps every decoded row index through the stored record; rows of a column are not
+    """sparsepress_v2.hpp:1093-1104 maps every decoded row index through the stored record; rows of a column are not
     re-sorted. With reorder off the indices are the writer's sorted-space rows (ascending-nnz order of rows)."""
     g = np.load(os.path.join(GOLDEN, "u8_rowsort.npz"))
     with S.SpzFile(os.path.join(GOLDEN, "u8_rowsort.spz")) as f:
@@ -100,7 +100,7 @@ def test_row_sorted_file_applies_the_stored_permutation_like_decompress_v2():
         _, i0, _ = f.read(0, None, False)
         _, i1, _ = f.read(0, None, True)
         assert np.array_equal(i1, perm[i0].astype(np.int32))
-        assert np.array_equal(i0, perm[g["a_i"]].astype(np.int32))    # the writer stored perm[row] (sparsepress_v2.hpp:512-516)
+        assert np.array_equal(i0, perm[g["a_i"]].astype(np.int32))    # the writer stored perm[row] (sparsepress_v2.hpp:503-508)
 
 
 @pytest.mark.parametrize("name", ["u8_t", "f32_t", "u16_escapes", "quant8_t", "f64", "f16"])
@@ -248,8 +248,8 @@ def test_files_written_by_the_reference_writer_read_like_the_reference_readers(t
 @have_tool
 def test_empty_chunks_decode_correctly_where_the_reference_reader_damages_the_pointers(tmp_path):
     """The writer emits the gap stream of a chunk WITHOUT non-zeros as bare column counts, with no u32 size prefix
-    (sparsepress_v2.hpp:92, the early return); the reference's readers nevertheless take the first four bytes for the
-    prefix when the stream has at least four (:990-1000, :1379-1391) and read four column counts beyond its end —
+    (sparsepress_v2.hpp:94, the early return); the reference's readers nevertheless take the first four bytes for the
+    prefix when the stream has at least four (:991-1003, :1385-1397) and read four column counts beyond its end —
     the pointers of the last columns of such a chunk come out wrong (here: not even monotone). This reader knows an
     empty chunk from its descriptor and returns the matrix that was written."""
     A = sp.random(40, 64, density=0.2, format="csc", random_state=np.random.default_rng(1), dtype=np.float64)
@@ -280,3 +280,22 @@ def test_the_reference_dataset_pbmc3k(tmp_path):
         p, i, x = f.read(0, None, True, 0, np.float32)
     assert np.array_equal(p, A.indptr) and np.array_equal(i, A.indices) and np.array_equal(x, A.data)
     assert x.max() == 419.0                                           # values above 255 travel as escapes
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU failure mode")
+def test_st_read_gpu_without_a_gpu_fails_loudly():
+    """The device half of the ingest has no host fallback: without a GPU rcppml_sp_read_gpu reports status 5
+    (the reference's catch-all, src/sp_gpu_bridge.cu:117-120) and hands out no pointers."""
+    with pytest.raises(S.SpzError) as ei:
+        S.st_read_gpu(os.path.join(GOLDEN, "u8_t.spz"))
+    assert ei.value.status == 5
+    with pytest.raises(FileNotFoundError):
+        S.st_read_gpu("/nonexistent/path.spz")
