@@ -200,6 +200,38 @@ def main():
                 print(f"cv k={k} solver={solver} world={world} p2p={p2p}: bit-identical={exact} n_test={cv['n_test']} max_rel_err={max(errs):.2e}", flush=True)
             e.close()
     os.environ.pop("RCPPML_B200_MC", None)
+    if os.environ.get("RCPPML_B200_CHECK_SPZ") == "1":
+        # On-disk ingest, sharded: every rank decodes only its column block and its row block of the
+        # file. OPT-IN: written after the round's GPU minutes were spent — not yet run on a multi-GPU box.
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "spz", "f32_t.spz")
+        k = 8
+        cfg = rb.make_config(k, max_iter=4, tol=0.0, solver_mode=1)
+        one = rb.Engine(local)
+        assert one.set_matrix_spz(path)
+        one.init_factors(k, 42, 0)
+        one.fit(cfg)
+        ref_s = one.get_factors() + (one.loss_history(4),)
+        one.close()
+        for balanced in (False, True):
+            e = rb.Engine(local)
+            uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                uid.copy_(torch.frombuffer(bytearray(rb.nccl_unique_id()), dtype=torch.uint8))
+            dist.broadcast(uid, 0)
+            e.comm_init(rank, world, uid.cpu().numpy().tobytes())
+            if balanced:
+                with rb.SpzFile(path) as f:
+                    e.set_partition(shard.balanced_cuts(f.col_counts(0), world, k), shard.balanced_cuts(f.col_counts(1), world, k))
+            assert e.set_matrix_spz(path)
+            e.init_factors(k, 42, 0)
+            e.fit(cfg)
+            got = e.get_factors() + (e.loss_history(4),)
+            errs = [rel_err(a, b) for a, b in zip(got, ref_s)]
+            assert max(errs) <= 1e-5, ("spz", balanced, errs)
+            worst = max(worst, *errs)
+            if rank == 0:
+                print(f"spz sharded ingest world={world} balanced={balanced}: max_rel_err={max(errs):.2e}", flush=True)
+            e.close()
     dist.barrier()
     if rank == 0:
         print(f"MULTIGPU_CHECK_OK world={world} worst_rel_err={worst:.3e}", flush=True)

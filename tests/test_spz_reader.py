@@ -299,3 +299,40 @@ def test_st_read_gpu_without_a_gpu_fails_loudly():
     assert ei.value.status == 5
     with pytest.raises(FileNotFoundError):
         S.st_read_gpu("/nonexistent/path.spz")
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_sharded_ingest_every_rank_decodes_exactly_its_two_blocks(world):
+    """rcppml_b200_set_matrix_spz after comm_init: rank r decodes columns J_r of the main section and columns I_r of the
+    transpose section. Host-side premise of that path: the first IS extract_shard(A, J_r), the second IS the transpose
+    of extract_row_block(A, I_r) (global column ids ascending — what Engine::transpose_csc would have produced on the
+    device), and the cuts of a work-balanced partition come from the chunk tables without decoding anything."""
+    from rcppml_b200 import shard
+    k = 8
+    with S.SpzFile(os.path.join(GOLDEN, "f32_t.spz")) as f:
+        m, n = f.shape
+        P, I, X = f.read(0)
+        col_cuts = shard.balanced_cuts(f.col_counts(0), world, per_item=k)
+        row_cuts = shard.balanced_cuts(f.col_counts(1), world, per_item=k)
+        assert np.array_equal(col_cuts, shard.balanced_cuts(np.diff(P), world, per_item=k))
+        rows_nnz = np.bincount(I, minlength=m)
+        assert np.array_equal(row_cuts, shard.balanced_cuts(rows_nnz, world, per_item=k))
+        seen_cols = seen_rows = 0
+        for r in range(world):
+            for cuts, equal in ((None, True), ((col_cuts, row_cuts), False)):
+                if equal:
+                    (cb, nl), (rb, ml) = shard.block_of(n, world, r), shard.block_of(m, world, r)
+                else:
+                    cb, nl, rb, ml = cuts[0][r], cuts[0][r + 1] - cuts[0][r], cuts[1][r], cuts[1][r + 1] - cuts[1][r]
+                p, i, x = f.read(0, (cb, cb + nl))
+                ep, ei, ex = shard.extract_shard(P, I, X, cb, nl)
+                assert np.array_equal(p, ep) and np.array_equal(i, ei) and np.array_equal(x, ex)
+                tp, ti, tx = f.read(1, (rb, rb + ml), reorder=False)
+                bp, bi, bx = shard.extract_row_block(P, I, X, rb, ml)          # n columns, block-relative rows
+                Bt = sp.csc_matrix((bx, bi, bp), shape=(ml, n)).T.tocsc()      # m_loc columns, global column ids
+                Bt.sort_indices()
+                assert np.array_equal(tp, Bt.indptr) and np.array_equal(ti, Bt.indices) and np.array_equal(tx, Bt.data)
+                if not equal:
+                    seen_cols += nl
+                    seen_rows += ml
+        assert (seen_cols, seen_rows) == (n, m)
