@@ -320,6 +320,9 @@ void File::parse() {
             next_col += ck.num_cols;
             if (data_base + go + ck.gap_bytes > data_end || data_base + vo + ck.value_bytes > data_end)
                 corrupt("chunk stream outside the file");
+            // every column owns at least one varint byte of its chunk's gap stream (sparsepress_v2.hpp:87-94), so the
+            // column count of a section is bounded by the file size — and with it every allocation sized from the header
+            if (ck.gap_bytes < ck.num_cols) corrupt("gap stream shorter than its column table");
             ck.gaps = base_ + data_base + go; ck.values = base_ + data_base + vo;
             ck.nnz_before = before; before += ck.nnz;
         }
