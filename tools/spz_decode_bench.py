@@ -3,7 +3,7 @@
 decompress_v2 (oracle/_ref/spz_ref_tool time ...), same files, same machine, same thread counts. CPU only — this is
 the host half of the on-disk ingest; needs /root/reference-built oracle/_ref (`make -C oracle ref`).
 
-  python tools/spz_decode_bench.py [--out profiles/r02y_spz_decode.json] [--big]
+  python tools/spz_decode_bench.py [--out profiles/r02y_spz_decode.json] [--big] [--c4]
 """
 from __future__ import annotations
 
@@ -53,6 +53,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default="")
     ap.add_argument("--big", action="store_true", help="add a 1e7-nnz float file (about a minute to write)")
+    ap.add_argument("--c4", action="store_true", help="add the C4 shape: 1M x 100K, 1000 float32 non-zeros per column, "
+                    "with transpose section (1 GB file, ~3 GB of scratch disk)")
     args = ap.parse_args()
     cores = os.cpu_count()
     rows = []
@@ -73,11 +75,26 @@ def main():
         cc = 256 if m >= 1000000 else 2048
         subprocess.run([REF_TOOL, "encode", b, s, "auto", "0", "0", str(cc)], check=True)
         cases.append((label, s))
+    if args.c4:
+        m, n, per = 1_000_000, 100_000, 1000
+        b, s = os.path.join(tmp, "c4.bin"), os.path.join(tmp, "c4.spz")
+        with open(b, "wb") as f:                      # the exchange format of spz_ref_tool, written block-wise
+            np.array([m, n], np.int32).tofile(f)
+            np.array([n * per], np.int64).tofile(f)
+            (np.arange(n + 1, dtype=np.int64) * per).astype(np.int32).tofile(f)
+            for _ in range(0, n, 5000):               # strictly increasing rows per column
+                (np.sort(rng.integers(0, m - per, size=(5000, per), dtype=np.int32), axis=1) + np.arange(per, dtype=np.int32)).tofile(f)
+            for _ in range(0, n, 5000):
+                rng.random((5000, per), dtype=np.float32).astype(np.float64).tofile(f)
+        subprocess.run([REF_TOOL, "encode", b, s, "auto", "0", "1", "2048"], check=True)
+        os.remove(b)
+        cases.append(("float32 1000000x100000, 1000 per column (C4: 1e8 non-zeros), chunk 2048, + transpose section", s))
     for label, path in cases:
         row = {"file": label, "file_bytes": os.path.getsize(path)}
         for threads in (1, cores):
-            mine, nnz = time_mine(path, threads)
-            ref = time_ref(path, threads)
+            heavy = os.path.getsize(path) > 500e6
+            mine, nnz = time_mine(path, threads, 3 if heavy else 7)
+            ref = time_ref(path, threads, (1 if threads == 1 else 3) if heavy else 7)
             row[f"threads_{threads}"] = {"reader_ms": round(mine, 2), "reference_ms": round(ref, 2),
                                          "reader_Mnnz_per_s": round(nnz / mine / 1e3, 1),
                                          "reference_Mnnz_per_s": round(nnz / ref / 1e3, 1), "speedup": round(ref / mine, 2)}
