@@ -420,10 +420,13 @@ int  rcppml_b200_spz_read_f64(const rcppml_b200_spz* h, int section, int c0, int
                               int* col_ptr, int* row_idx, double* values);
 /* Raw bytes of a metadata record (header_v2.hpp:108-113: 0 rownames, 1 colnames — NUL-separated —, 2 row permutation). */
 int  rcppml_b200_spz_metadata(const rcppml_b200_spz* h, int key, unsigned char* buf, int64_t capacity, int64_t* bytes);
-/* File -> engine. One GPU: A plus the stored transpose when the file has a usable one (no device transpose; reported in
- * *used_stored_transpose). After comm_init (+ optional set_partition): this rank decodes only its column block of A and
- * its row block (columns of the stored transpose); collective like every sharded set_matrix_*. */
-int  rcppml_b200_set_matrix_spz(rcppml_b200_engine* e, const rcppml_b200_spz* h, int threads, int* used_stored_transpose);
+/* File -> engine. After comm_init (+ optional set_partition): this rank decodes only its column block of A and its row
+ * block (columns of the stored transpose section); collective like every sharded set_matrix_*. stored_transpose: 1 use
+ * the file's transpose section when it has a usable one, 0 never (device transpose / host filter instead), < 0 automatic:
+ * sharded yes, one GPU no (the device transposes 1e8 entries in 6 ms; entropy-decoding them takes the host ~0.5 s).
+ * *used_stored_transpose reports what happened. */
+int  rcppml_b200_set_matrix_spz(rcppml_b200_engine* e, const rcppml_b200_spz* h, int threads, int stored_transpose,
+                                int* used_stored_transpose);
 /* Sharded operands with the row block already transposed (what the two sections of a .spz file deliver):
  * A[:, J] as CSC (n_loc columns, global row ids) and (A[I, :])^T as CSC (m_loc columns, global column ids). */
 int  rcppml_b200_set_matrix_sharded_with_transpose_f32(rcppml_b200_engine* e, int m, int n, const int* colblk_ptr,

@@ -198,14 +198,20 @@ int rcppml_b200_spz_metadata(const rcppml_b200_spz* h, int key, unsigned char* b
 
 // ---- file -> engine -------------------------------------------------------------------------------------------------
 
-int rcppml_b200_set_matrix_spz(rcppml_b200_engine* e, const rcppml_b200_spz* h, int threads, int* used_stored_transpose) {
+int rcppml_b200_set_matrix_spz(rcppml_b200_engine* e, const rcppml_b200_spz* h, int threads, int stored_transpose,
+                               int* used_stored_transpose) {
     return guarded([&] {
         const File& f = h->file;
         const auto& in = f.info();
         const int m = static_cast<int>(in.m), n = static_cast<int>(in.n);
-        const bool stored = transpose_usable(f);
-        if (used_stored_transpose) *used_stored_transpose = stored ? 1 : 0;
         b200::Engine& eng = e->impl;
+        // stored_transpose: 1 use the file's transpose section when it is usable, 0 never, < 0 decide here. On ONE GPU
+        // the section is not worth decoding: entropy-decoding 1e8 entries costs ~0.5 s of host time, the
+        // device transpose of the same matrix 6 ms. Sharded, it is what lets a rank get its row block without decoding
+        // (or receiving) the rest of the matrix.
+        const bool want = stored_transpose > 0 || (stored_transpose < 0 && eng.world > 1);
+        const bool stored = want && transpose_usable(f);
+        if (used_stored_transpose) *used_stored_transpose = stored ? 1 : 0;
         HostCsc a, t;
         if (eng.world == 1) {
             decode_range(f, 0, 0, in.n, true, threads, a);

@@ -95,15 +95,17 @@ class Engine:
         _lib.check(rc, "set_matrix_with_transpose")
         self._refresh_shard(m, n)
 
-    def set_matrix_spz(self, path, threads=0):
-        """A StreamPress v2 `.spz` file straight into the engine. One GPU: A plus the file's pre-stored
-        transpose when it has a usable one (then no device transpose). After comm_init (+ set_partition): this rank
-        decodes only its column block of A and its row block (columns of the stored transpose) — collective, like
-        every sharded set_matrix_*. Returns True when the stored transpose was used."""
+    def set_matrix_spz(self, path, threads=0, stored_transpose=None):
+        """A StreamPress v2 `.spz` file straight into the engine. After comm_init (+ set_partition) this
+        rank decodes only its column block of A and its row block (columns of the file's transpose section) —
+        collective, like every sharded set_matrix_*. stored_transpose: True use the file's transpose section when it is
+        usable, False never, None automatic (sharded: yes; one GPU: no — the device transpose is ~100x cheaper than
+        entropy-decoding the section). Returns True when the stored transpose was used."""
         from .streampress import SpzFile
         with SpzFile(path) as f:
             used = C.c_int(0)
-            rc = self._lib.rcppml_b200_set_matrix_spz(self._h, f._h, int(threads), C.byref(used))
+            mode = -1 if stored_transpose is None else int(bool(stored_transpose))
+            rc = self._lib.rcppml_b200_set_matrix_spz(self._h, f._h, int(threads), mode, C.byref(used))
             _lib.check(rc, "set_matrix_spz")
             self._refresh_shard(f.raw.m, f.raw.n)
         return bool(used.value)

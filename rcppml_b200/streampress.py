@@ -59,7 +59,7 @@ def _bind(lib):
     lib.rcppml_b200_spz_read_f32.argtypes = [H, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, ip, ip, C.POINTER(C.c_float)]
     lib.rcppml_b200_spz_read_f64.argtypes = [H, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, ip, ip, C.POINTER(C.c_double)]
     lib.rcppml_b200_spz_metadata.argtypes = [H, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
-    lib.rcppml_b200_set_matrix_spz.argtypes = [C.c_void_p, H, C.c_int, ip]
+    lib.rcppml_b200_set_matrix_spz.argtypes = [C.c_void_p, H, C.c_int, C.c_int, ip]
     dp = C.POINTER(C.c_double)
     for name in ("rcppml_sp_read_gpu", "rcppml_st_read_gpu"):
         fn = getattr(lib, name)

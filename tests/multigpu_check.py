@@ -207,7 +207,7 @@ def main():
         k = 8
         cfg = rb.make_config(k, max_iter=4, tol=0.0, solver_mode=1)
         one = rb.Engine(local)
-        assert one.set_matrix_spz(path)
+        assert one.set_matrix_spz(path, stored_transpose=True)
         one.init_factors(k, 42, 0)
         one.fit(cfg)
         ref_s = one.get_factors() + (one.loss_history(4),)

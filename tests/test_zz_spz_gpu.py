@@ -99,8 +99,9 @@ def test_nmf_from_a_gpu_sparse_matrix_matches_the_host_path():
 @pytest.mark.parametrize("name", ["u8_t", "f32_t", "u16_escapes", "f32_rowsort_t", "quant8_t"])
 def test_file_to_engine_equals_host_arrays_to_engine(name):
     """rcppml_b200_set_matrix_spz: the device operands (A and A^T) and a fit equal those of set_matrix on the decoded
-    arrays; the stored transpose is used when the file has a usable one (not under a row permutation, and QUANT8
-    quantises the two sections per chunk — the transpose section is then still what the FILE says A^T is)."""
+    arrays. On one GPU the transpose section of the file is left alone by default (the device transpose is far cheaper
+    than decoding it); when asked for it is used if usable (not under a row permutation; QUANT8 quantises the two
+    sections per chunk — the transpose section is then still what the FILE says A^T is)."""
     import rcppml_b200 as rb
     path = os.path.join(GOLDEN, name + ".spz")
     ref = np.load(os.path.join(GOLDEN, name + ".npz"))
@@ -108,7 +109,9 @@ def test_file_to_engine_equals_host_arrays_to_engine(name):
     A = sp.csc_matrix((ref["r1_x"].astype(np.float32), ref["r1_i"], ref["r1_p"]), shape=(m, n))
     eng = rb.Engine(0)
     try:
-        used = eng.set_matrix_spz(path)
+        assert eng.set_matrix_spz(path) is False                                  # one GPU: the device transposes
+        tp0, ti0, tx0 = eng.get_matrix_t()
+        used = eng.set_matrix_spz(path, stored_transpose=True)
         assert used == (("t_p" in ref) and "rowsort" not in name)
         p, i, x = eng.get_matrix()
         assert np.array_equal(p, ref["r1_p"]) and np.array_equal(i, ref["r1_i"]) and np.array_equal(x, ref["r1_x"].astype(np.float32))
@@ -119,6 +122,7 @@ def test_file_to_engine_equals_host_arrays_to_engine(name):
             At = A.T.tocsc()
             At.sort_indices()
             assert np.array_equal(tp, At.indptr) and np.array_equal(ti, At.indices) and np.array_equal(tx, At.data)
+            assert np.array_equal(tp0, At.indptr) and np.array_equal(ti0, At.indices) and np.array_equal(tx0, At.data)
             eng.init_factors(k, 42)
             res = eng.fit(rb.make_config(k, max_iter=5, tol=0.0, solver_mode=1))
             from_file = eng.get_factors() + (eng.loss_history(5),)
