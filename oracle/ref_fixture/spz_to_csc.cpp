@@ -3,7 +3,7 @@
 // no reference source is copied into this repo) and dumps the CSC matrix as raw little-endian arrays:
 //   int32 m, n ; int64 nnz ; int32 p[n+1] ; int32 i[nnz] ; float x[nnz]
 // Used only to materialise the reference's real dataset (inst/extdata/pbmc3k.spz) as a fixture under
-// oracle/_ref/ (git-ignored, travels to the GPU box). The codec itself is out of scope.
+// oracle/_ref/ (git-ignored, travels to the GPU box). The product's own reader of this format is rcppml_b200/csrc/spz_reader.cpp.
 #include <streampress/sparsepress_v2.hpp>
 
 #include <cstdint>
