@@ -418,6 +418,11 @@ int  rcppml_b200_spz_read_f32(const rcppml_b200_spz* h, int section, int c0, int
                               int* col_ptr, int* row_idx, float* values);
 int  rcppml_b200_spz_read_f64(const rcppml_b200_spz* h, int section, int c0, int c1, int reorder, int threads,
                               int* col_ptr, int* row_idx, double* values);
+/* A[row_begin : row_begin + m_loc, :] as CSC over all n columns with block-relative row ids (the row-block operand of
+ * rcppml_b200_set_matrix_sharded_f32) from a file WITHOUT a transpose section: full decode + host filter. capacity:
+ * entries row_idx / values can take (the file's nnz always suffices). */
+int  rcppml_b200_spz_row_block_f32(const rcppml_b200_spz* h, int row_begin, int m_loc, int threads, int* col_ptr,
+                                   int* row_idx, float* values, int64_t capacity, int64_t* nnz);
 /* Raw bytes of a metadata record (header_v2.hpp:108-113: 0 rownames, 1 colnames — NUL-separated —, 2 row permutation). */
 int  rcppml_b200_spz_metadata(const rcppml_b200_spz* h, int key, unsigned char* buf, int64_t capacity, int64_t* bytes);
 /* File -> engine. After comm_init (+ optional set_partition): this rank decodes only its column block of A and its row

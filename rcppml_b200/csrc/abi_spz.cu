@@ -49,6 +49,26 @@ void decode_range(const File& f, int section, uint32_t c0, uint32_t c1, bool reo
     f.decode<float>(section, c0, c1, out.p.data(), out.i.data(), out.x.data(), reorder, threads);
 }
 
+// A[I, :] for a file WITHOUT a usable transpose section: CSC over all n columns, row ids relative to the block (the
+// set_matrix_sharded contract, rcppml_b200/shard.py extract_row_block) — a full decode of A filtered on the host.
+void row_block_by_filter(const File& f, int row_begin, int m_loc, int threads, HostCsc& out) {
+    const auto& in = f.info();
+    const int n = static_cast<int>(in.n);
+    HostCsc full;
+    decode_range(f, 0, 0, in.n, true, threads, full);
+    out.p.assign(static_cast<size_t>(n) + 1, 0);
+    out.i.clear(); out.x.clear();
+    for (int j = 0; j < n; ++j) {
+        for (int q = full.p[j]; q < full.p[j + 1]; ++q) {
+            const int r = full.i[q];
+            if (r >= row_begin && r < row_begin + m_loc) { out.i.push_back(r - row_begin); out.x.push_back(full.x[q]); }
+        }
+        out.p[j + 1] = static_cast<int>(out.i.size());
+    }
+    out.nnz = static_cast<int64_t>(out.i.size());
+    if (out.i.empty()) { out.i.push_back(0); out.x.push_back(0.f); }
+}
+
 // The stored transpose describes the matrix as written: with a row permutation in play the reference's reader maps
 // the row indices of A (sparsepress_v2.hpp:1093-1104) but not the columns of the transpose section (:1318-1467), so
 // the two sections no longer describe the same matrix and the transpose is rebuilt on the device instead.
@@ -196,6 +216,27 @@ int rcppml_b200_spz_metadata(const rcppml_b200_spz* h, int key, unsigned char* b
     });
 }
 
+// Host half of the sharded ingest of a file without a transpose section (see row_block_by_filter); capacity: entries the
+// caller's row_idx / values can take (the file's nnz always suffices). Exposed so that the host logic is testable
+// without a device.
+int rcppml_b200_spz_row_block_f32(const rcppml_b200_spz* h, int row_begin, int m_loc, int threads, int* col_ptr, int* row_idx,
+                                  float* values, int64_t capacity, int64_t* nnz) {
+    return guarded([&] {
+        const auto& in = h->file.info();
+        B200_REQUIRE(row_begin >= 0 && m_loc >= 0 && static_cast<int64_t>(row_begin) + m_loc <= static_cast<int64_t>(in.m),
+                     "spz: row block outside the matrix");
+        HostCsc t;
+        row_block_by_filter(h->file, row_begin, m_loc, threads, t);
+        *nnz = t.nnz;
+        std::memcpy(col_ptr, t.p.data(), t.p.size() * sizeof(int));
+        B200_REQUIRE(capacity >= t.nnz, "spz: row block larger than the caller's buffers");
+        if (t.nnz > 0) {
+            std::memcpy(row_idx, t.i.data(), static_cast<size_t>(t.nnz) * sizeof(int));
+            std::memcpy(values, t.x.data(), static_cast<size_t>(t.nnz) * sizeof(float));
+        }
+    });
+}
+
 // ---- file -> engine -------------------------------------------------------------------------------------------------
 
 int rcppml_b200_set_matrix_spz(rcppml_b200_engine* e, const rcppml_b200_spz* h, int threads, int stored_transpose,
@@ -235,18 +276,7 @@ int rcppml_b200_set_matrix_spz(rcppml_b200_engine* e, const rcppml_b200_spz* h, 
                                                          t.x.data());
             return;
         }
-        HostCsc full;
-        decode_range(f, 0, 0, in.n, true, threads, full);
-        t.p.assign(static_cast<size_t>(n) + 1, 0);
-        t.i.clear(); t.x.clear();
-        for (int j = 0; j < n; ++j) {
-            for (int q = full.p[j]; q < full.p[j + 1]; ++q) {
-                const int r = full.i[q];
-                if (r >= rb && r < rb + ml) { t.i.push_back(r - rb); t.x.push_back(full.x[q]); }
-            }
-            t.p[j + 1] = static_cast<int>(t.i.size());
-        }
-        if (t.i.empty()) { t.i.push_back(0); t.x.push_back(0.f); }
+        row_block_by_filter(f, rb, ml, threads, t);
         eng.set_matrix_sharded<float>(m, n, a.p.data(), a.i.data(), a.x.data(), t.p.data(), t.i.data(), t.x.data());
     });
 }

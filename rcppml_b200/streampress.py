@@ -58,6 +58,8 @@ def _bind(lib):
     lib.rcppml_b200_spz_col_counts.argtypes = [H, C.c_int, C.c_int, ip]
     lib.rcppml_b200_spz_read_f32.argtypes = [H, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, ip, ip, C.POINTER(C.c_float)]
     lib.rcppml_b200_spz_read_f64.argtypes = [H, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, ip, ip, C.POINTER(C.c_double)]
+    lib.rcppml_b200_spz_row_block_f32.argtypes = [H, C.c_int, C.c_int, C.c_int, ip, ip, C.POINTER(C.c_float), C.c_int64,
+                                                  C.POINTER(C.c_int64)]
     lib.rcppml_b200_spz_metadata.argtypes = [H, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
     lib.rcppml_b200_set_matrix_spz.argtypes = [C.c_void_p, H, C.c_int, C.c_int, ip]
     dp = C.POINTER(C.c_double)
@@ -82,6 +84,9 @@ def _check(rc: int, what: str):
 
 class SpzFile:
     """An open `.spz` v2 file (mapped by the library). Use as a context manager or call close()."""
+
+    def row_block(self, row_begin: int, m_loc: int, threads: int = 0):
+        return _row_block(self, row_begin, m_loc, threads)
 
     def __init__(self, path: str):
         self._lib = _bind(_lib.load())
@@ -182,6 +187,20 @@ class SpzFile:
                                                     i.ctypes.data_as(ip), x.ctypes.data_as(C.POINTER(C.c_float)))
         _check(rc, "st_read")
         return p, i[:nnz], x[:nnz]
+
+
+def _row_block(f: "SpzFile", row_begin: int, m_loc: int, threads: int = 0):
+    """(indptr, indices, data) of A[row_begin : row_begin + m_loc, :] with block-relative rows, decoded from the MAIN
+    section and filtered on the host — what a sharded ingest falls back to for a file without a transpose section."""
+    cap = max(int(f.raw.nnz), 1)
+    p = np.zeros(f.raw.n + 1, np.int32)
+    i = np.zeros(cap, np.int32)
+    x = np.zeros(cap, np.float32)
+    nnz = C.c_int64(0)
+    ip = C.POINTER(C.c_int)
+    _check(f._lib.rcppml_b200_spz_row_block_f32(f._h, row_begin, m_loc, threads, p.ctypes.data_as(ip), i.ctypes.data_as(ip),
+                                                x.ctypes.data_as(C.POINTER(C.c_float)), cap, C.byref(nnz)), "spz row block")
+    return p, i[:nnz.value].copy(), x[:nnz.value].copy()
 
 
 def st_info(path: str) -> dict:

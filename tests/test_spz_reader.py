@@ -336,3 +336,24 @@ def test_sharded_ingest_every_rank_decodes_exactly_its_two_blocks(world):
                     seen_cols += nl
                     seen_rows += ml
         assert (seen_cols, seen_rows) == (n, m)
+
+
+@pytest.mark.parametrize("name", ["u16_escapes", "f64", "u8_rowsort"])
+def test_row_block_of_a_file_without_transpose_section(name):
+    """Sharded ingest, fallback: a file without a (usable) transpose section gives a rank its row block by a full decode
+    filtered on the host — the operand contract of set_matrix_sharded (shard.extract_row_block)."""
+    from rcppml_b200 import shard
+    with S.SpzFile(os.path.join(GOLDEN, name + ".spz")) as f:
+        P, I, X = f.read(0)
+        m = f.raw.m
+        for world in (1, 2, 5):
+            total = 0
+            for r in range(world):
+                rb, ml = shard.block_of(m, world, r)
+                p, i, x = f.row_block(rb, ml, threads=2)
+                ep, ei, ex = shard.extract_row_block(P, I, X, rb, ml)
+                assert np.array_equal(p, ep) and np.array_equal(i, ei) and np.array_equal(x, ex)
+                total += len(i)
+            assert total == len(I)
+        with pytest.raises(S.SpzError):
+            f.row_block(m - 1, 2)
