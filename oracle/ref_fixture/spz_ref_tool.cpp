@@ -6,7 +6,9 @@
 // and compare both with rcppml_b200/csrc/spz_reader.cpp. Raw little-endian exchange format ("csc.bin"):
 //   int32 m, n ; int64 nnz ; int32 p[n+1] ; int32 i[nnz] ; double x[nnz]
 //
-//   spz_ref_tool encode  in.bin out.spz <precision> <row_sort 0|1> <include_transpose 0|1> <chunk_cols>
+//   spz_ref_tool encode  in.bin out.spz <precision> <row_sort 0|1> <include_transpose 0|1> <chunk_cols> [obs_bytes var_bytes]
+//                        (obs_bytes / var_bytes: sizes of opaque stand-ins for the serialized obs / var tables the
+//                         writer places between the transpose section and the metadata, sparsepress_v2.hpp:810-818)
 //   spz_ref_tool decode  in.spz out.bin [reorder 0|1] [col_start col_end]
 //   spz_ref_tool decodet in.spz out.bin
 //   spz_ref_tool time    in.spz <repeats> <threads>      (best wall-clock ms of decompress_v2 on the bytes in memory)
@@ -59,13 +61,17 @@ int main(int argc, char** argv) {
     if (argc < 4) { std::fprintf(stderr, "usage: see the header of spz_ref_tool.cpp\n"); return 2; }
     const std::string cmd = argv[1];
     try {
-        if (cmd == "encode" && argc == 8) {
+        if (cmd == "encode" && (argc == 8 || argc == 10)) {
             auto A = read_bin(argv[2]);
             streampress::v2::CompressConfig_v2 cfg;
             cfg.precision = argv[4];
             cfg.row_sort = std::atoi(argv[5]) != 0;
             cfg.include_transpose = std::atoi(argv[6]) != 0;
             cfg.chunk_cols = static_cast<uint32_t>(std::atoi(argv[7]));
+            if (argc == 10) {
+                cfg.obs_buf.assign(static_cast<size_t>(std::atoi(argv[8])), 0xA5);
+                cfg.var_buf.assign(static_cast<size_t>(std::atoi(argv[9])), 0x5A);
+            }
             auto bytes = streampress::v2::compress_v2(A, cfg);
             streampress::v2::write_v2(argv[3], bytes);
             return 0;

@@ -357,3 +357,26 @@ def test_row_block_of_a_file_without_transpose_section(name):
             assert total == len(I)
         with pytest.raises(S.SpzError):
             f.row_block(m - 1, 2)
+
+
+@have_tool
+def test_files_with_obs_and_var_tables_read_the_same(tmp_path):
+    """The writer places the serialized obs / var tables between the transpose section and the metadata and records
+    their offsets in the header's reserved bytes (sparsepress_v2.hpp:810-818, header_v2.hpp:150-163). The ingest does not
+    read the tables; it must not trip over them either."""
+    A = _matrix(np.random.default_rng(9), 300, 120, 0.05, "f")
+    a_bin, plain, tabled, d_bin = (str(tmp_path / n) for n in ("a.bin", "p.spz", "t.spz", "d.bin"))
+    write_bin(a_bin, A)
+    assert ref_tool("encode", a_bin, plain, "auto", 1, 1, 32)[0] == 0
+    assert ref_tool("encode", a_bin, tabled, "auto", 1, 1, 32, 777, 1234)[0] == 0
+    assert os.path.getsize(tabled) == os.path.getsize(plain) + 777 + 1234
+    with S.SpzFile(plain) as f0, S.SpzFile(tabled) as f1:
+        assert not f0.info()["has_obs"] and not f0.info()["has_var"]
+        assert f1.info()["has_obs"] and f1.info()["has_var"] and f1.crc32() == f1.raw.stored_crc32
+        for section, reorder in ((0, True), (0, False), (1, False)):
+            assert same_csc(f1.read(section, None, reorder, 0, np.float64), *f0.read(section, None, reorder, 0, np.float64))
+        assert np.array_equal(f1.row_permutation(), f0.row_permutation()) and len(f1.row_permutation()) == 300
+    assert ref_tool("decode", tabled, d_bin, 1)[0] == 0
+    _, _, p, i, x = read_bin(d_bin)
+    with S.SpzFile(tabled) as f1:
+        assert same_csc(f1.read(0, None, True, 0, np.float64), p, i, x)
