@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstring>
 #include <memory>
+#include <thread>
 #include <vector>
 
 struct rcppml_b200_spz {
@@ -250,6 +251,8 @@ int rcppml_b200_set_matrix_spz(rcppml_b200_engine* e, const rcppml_b200_spz* h, 
         // the section is not worth decoding: entropy-decoding 1e8 entries costs ~0.5 s of host time, the
         // device transpose of the same matrix 6 ms. Sharded, it is what lets a rank get its row block without decoding
         // (or receiving) the rest of the matrix.
+        if (threads <= 0 && eng.world > 1)   // one process per GPU on one host: share the cores between the ranks
+            threads = static_cast<int>(std::max(1u, std::thread::hardware_concurrency() / static_cast<unsigned>(eng.world)));
         const bool want = stored_transpose > 0 || (stored_transpose < 0 && eng.world > 1);
         const bool stored = want && transpose_usable(f);
         if (used_stored_transpose) *used_stored_transpose = stored ? 1 : 0;
