@@ -31,8 +31,10 @@ def _allgather_rows(block, first, total):
     return _allreduce(full)
 
 
-def _sharded_fit(rank, world, A, m, n, k, W0, H0, iters, solver, L1, L2, cuts=None):
-    """cuts = (col_cuts, row_cuts): explicit partition (rcppml_b200.shard.balanced_cuts); None = equal blocks."""
+def _sharded_fit(rank, world, A, m, n, k, W0, H0, iters, solver, L1, L2, cuts=None, operands=None):
+    """cuts = (col_cuts, row_cuts): explicit partition (rcppml_b200.shard.balanced_cuts); None = equal blocks.
+    operands = callable(lo, cnt, r0, rc) -> ((Ap, Ai, Ax), (Atp, Ati, Atx)): this rank's A[:, J] and (A[I, :])^T from
+    somewhere else than slicing A (the .spz ingest); A may then be None."""
     from oracle import oracle as O
     from rcppml_b200 import shard
     if cuts is None:
@@ -41,10 +43,13 @@ def _sharded_fit(rank, world, A, m, n, k, W0, H0, iters, solver, L1, L2, cuts=No
     else:
         lo, cnt = int(cuts[0][rank]), int(cuts[0][rank + 1] - cuts[0][rank])
         r0, rc = int(cuts[1][rank]), int(cuts[1][rank + 1] - cuts[1][rank])
-    Ap, Ai, Ax = shard.extract_shard(A.indptr, A.indices, A.data, lo, cnt)
-    Ai, Ax = np.ascontiguousarray(Ai, np.int32), np.ascontiguousarray(Ax, np.float32)
-    Rp, Ri, Rx = shard.extract_row_block(A.indptr, A.indices, A.data, r0, rc)
-    Atp, Ati, Atx = O.transpose_csc(Rp, Ri, np.ascontiguousarray(Rx, np.float32), rc, n)   # A[I,:]^T: rc columns
+    if operands is not None:
+        (Ap, Ai, Ax), (Atp, Ati, Atx) = operands(lo, cnt, r0, rc)
+    else:
+        Ap, Ai, Ax = shard.extract_shard(A.indptr, A.indices, A.data, lo, cnt)
+        Ai, Ax = np.ascontiguousarray(Ai, np.int32), np.ascontiguousarray(Ax, np.float32)
+        Rp, Ri, Rx = shard.extract_row_block(A.indptr, A.indices, A.data, r0, rc)
+        Atp, Ati, Atx = O.transpose_csc(Rp, Ri, np.ascontiguousarray(Rx, np.float32), rc, n)   # A[I,:]^T: rc columns
     W_T, H = W0.copy(), H0.copy()                      # replicated
     trAtA = np.float32(_allreduce(np.array([np.sum(Ax.astype(np.float64) ** 2)]))[0])
     hist = []
@@ -196,6 +201,62 @@ def test_sharded_schedule_matches_unsharded_oracle():
     q = ctx.Queue()
     port = 29600 + os.getpid() % 300
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, ok, msgs in results:
+        assert ok, (rank, msgs)
+
+
+def _spz_worker(rank, world, port, q):
+    """Sharded ingest of a .spz file, world 2 over gloo: every rank decodes ONLY its column block (a column
+    range of the main section) and its row block (a column range of the transpose section, already (A[I, :])^T) with the
+    product's reader, runs the sharded schedule on them, and must reproduce the unsharded oracle fit of the whole file."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle as O
+    from rcppml_b200 import shard
+    from rcppml_b200 import streampress as S
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "spz", "f32_t.spz")
+    ok, msgs = True, []
+    with S.SpzFile(path) as f:
+        m, n = f.shape
+        k, iters = 6, 3
+        decoded = []
+
+        def operands(lo, cnt, r0, rc):
+            a = f.read(0, (lo, lo + cnt), True, 1, np.float32)
+            t = f.read(1, (r0, r0 + rc), False, 1, np.float32)
+            decoded.append(len(a[1]) + len(t[1]))
+            return a, t
+
+        P, I, X = f.read(0)                               # the checker's view of the whole matrix (not the ranks')
+        W0, H0 = O.initialize_factors(k, m, n, 42)
+        ref = O.nmf_fit(P, I, X, m, n, k, W0, H0, max_iter=iters, tol=0.0, solver_mode=1, L1=(0.01, 0.0), threads=1)
+        balanced = (shard.balanced_cuts(f.col_counts(0), world, per_item=k), shard.balanced_cuts(f.col_counts(1), world, per_item=k))
+        for cuts in (None, balanced):
+            W_T, H, d, hist, _ = _sharded_fit(rank, world, None, m, n, k, W0, H0, iters, 1, (0.01, 0.0), (0.0, 0.0), cuts=cuts,
+                                              operands=operands)
+            errs = dict(W=rel_err(W_T, ref.W_T), H=rel_err(H, ref.H), d=rel_err(d, ref.d), loss=rel_err(hist, ref.loss_history))
+            msgs.append(("spz", cuts is not None, errs, decoded[-1]))
+            ok = ok and max(errs.values()) <= 1e-5
+            # no rank decoded the whole file: its two blocks hold about 2 / world of the non-zeros of ONE section
+            total = torch.tensor([decoded[-1]], dtype=torch.int64)
+            dist.all_reduce(total)
+            ok = ok and int(total[0]) == 2 * len(I) and decoded[-1] < 1.5 * len(I)
+    q.put((rank, ok, msgs))
+    dist.destroy_process_group()
+
+
+def test_sharded_fit_from_an_spz_file_matches_unsharded_oracle():
+    from oracle import oracle as O
+    O.build()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29900 + os.getpid() % 90
+    procs = [ctx.Process(target=_spz_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
     results = [q.get(timeout=180) for _ in procs]
