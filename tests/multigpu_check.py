@@ -202,7 +202,8 @@ def main():
     os.environ.pop("RCPPML_B200_MC", None)
     if os.environ.get("RCPPML_B200_CHECK_SPZ") == "1":
         # On-disk ingest, sharded: every rank decodes only its column block and its row block of the
-        # file. OPT-IN: written after the round's GPU minutes were spent — not yet run on a multi-GPU box.
+        # file. OPT-IN: the one-GPU ingest tests ran on a B200 (tests/test_zz_spz_gpu.py); this sharded variant was written
+        # after the round's multi-GPU minutes were spent and has not run on a multi-GPU box yet.
         path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "spz", "f32_t.spz")
         k = 8
         cfg = rb.make_config(k, max_iter=4, tol=0.0, solver_mode=1)
