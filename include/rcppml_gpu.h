@@ -7,6 +7,8 @@
  * Part 2 are NEW symbols (prefix rcppml_b200_) for callers that keep data resident
  * on the device (bench, multi-GPU, masked fits); they are ABI extensions and are
  * listed as such in INTEGRATION.md.
+ * Part 3 is the on-disk ingest: the reference's rcppml_sp_read_gpu / rcppml_sp_free_gpu (a StreamPress v2 .spz file
+ * decoded and left on the device) and the reader behind them as rcppml_b200_spz_* (host) / rcppml_b200_set_matrix_spz.
  *
  * All symbols: plain C, pointers + sizes only, never throw, never call into R.
  */
