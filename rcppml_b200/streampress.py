@@ -174,15 +174,15 @@ class SpzFile:
         indptr is rebased to 0. dtype float32 (the engine's) or float64 (the R boundary's)."""
         c0, c1 = (0, self.section_cols(section)) if cols is None else (int(cols[0]), int(cols[1]))
         nnz = self.range_nnz(section, c0, c1)
-        p = np.zeros(c1 - c0 + 1, dtype=np.int32)
-        i = np.zeros(max(nnz, 1), dtype=np.int32)
+        p = np.empty(c1 - c0 + 1, dtype=np.int32)          # every entry is written by the decode (and only once)
+        i = np.empty(max(nnz, 1), dtype=np.int32)
         ip = C.POINTER(C.c_int)
         if np.dtype(dtype) == np.float64:
-            x = np.zeros(max(nnz, 1), dtype=np.float64)
+            x = np.empty(max(nnz, 1), dtype=np.float64)
             rc = self._lib.rcppml_b200_spz_read_f64(self._h, section, c0, c1, int(reorder), threads, p.ctypes.data_as(ip),
                                                     i.ctypes.data_as(ip), x.ctypes.data_as(C.POINTER(C.c_double)))
         else:
-            x = np.zeros(max(nnz, 1), dtype=np.float32)
+            x = np.empty(max(nnz, 1), dtype=np.float32)
             rc = self._lib.rcppml_b200_spz_read_f32(self._h, section, c0, c1, int(reorder), threads, p.ctypes.data_as(ip),
                                                     i.ctypes.data_as(ip), x.ctypes.data_as(C.POINTER(C.c_float)))
         _check(rc, "st_read")
